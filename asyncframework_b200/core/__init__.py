@@ -1,0 +1,9 @@
+from .context import AsyncContext, QueueClosed
+from .partial_result import PartialResult
+from .worker_state import StatTable, WorkerState
+from .broadcast import AsyncBroadcast, Broadcast
+from .scheduler import JobFailed, JobWaiter, Scheduler, TaskContext
+from . import barriers, sampler
+
+__all__ = ["AsyncContext", "QueueClosed", "PartialResult", "StatTable", "WorkerState", "AsyncBroadcast",
+           "Broadcast", "JobFailed", "JobWaiter", "Scheduler", "TaskContext", "barriers", "sampler"]

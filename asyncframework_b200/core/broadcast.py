@@ -1,0 +1,129 @@
+"""Broadcast variables, including the versioned ``AsyncBroadcast``.
+
+Parity: ``sc.broadcast`` / ``TorrentBroadcast`` (core/broadcast/TorrentBroadcast.scala) and
+``ASYNCbroadcast`` (core/broadcast/ASYNCbroadcast.scala:12-46): ``value`` reads the current
+version, ``value(index)`` re-reads an *older* version by id (made possible in the reference by the
+mutable broadcast id, Broadcast.scala:73-80,137-149), ``getIndex``/``setID``.
+
+B200 design: a broadcast is a *snapshot slot*.  In-process backends share the tensor by
+reference; on the fused backend the slots are a ring in symmetric HBM (parallel/comm.py) so
+``value(version)`` is a pointer offset, not a block-store fetch.  Snapshotting copies the value at
+broadcast time — the reference serialises ``w`` at broadcast time too (TorrentBroadcast.writeBlocks
+:133-157) while the updater thread keeps mutating it (Hogwild).
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+from collections import OrderedDict
+from typing import Any, Optional
+
+import torch
+
+from ..linalg.vectors import DenseVector
+
+_bcast_ids = itertools.count(0)
+
+
+def _snapshot(value: Any) -> Any:
+    if isinstance(value, torch.Tensor):
+        return value.detach().clone()
+    if isinstance(value, DenseVector):
+        return value.copy()
+    if hasattr(value, "copy"):
+        try:
+            return value.copy()
+        except Exception:
+            pass
+    return value
+
+
+class Broadcast:
+    """Immutable snapshot with an id, ``value``, ``unpersist``/``destroy``."""
+
+    def __init__(self, value: Any, snapshot: bool = True):
+        self.id = next(_bcast_ids)
+        self._value = _snapshot(value) if snapshot else value
+        self._valid = True
+
+    @property
+    def value(self) -> Any:
+        if not self._valid:
+            raise RuntimeError(f"Attempted to use Broadcast({self.id}) after it was destroyed")
+        return self._value
+
+    def get_broadcast_id(self) -> int:
+        return self.id
+
+    def unpersist(self, blocking: bool = False) -> None:
+        pass
+
+    def destroy(self) -> None:
+        self._valid = False
+        self._value = None
+
+
+class _VersionStore:
+    """Ring of the last K versions keyed by broadcast id (shared per AsyncContext)."""
+
+    def __init__(self, slots: int):
+        self.slots = max(1, int(slots))
+        self.lock = threading.Lock()
+        self.versions: "OrderedDict[int, Any]" = OrderedDict()
+
+    def put(self, vid: int, value: Any) -> None:
+        with self.lock:
+            self.versions[vid] = value
+            while len(self.versions) > self.slots:
+                self.versions.popitem(last=False)
+
+    def get(self, vid: int) -> Any:
+        with self.lock:
+            if vid not in self.versions:
+                raise KeyError(f"broadcast version {vid} evicted (ring keeps the last {self.slots}) or never existed")
+            return self.versions[vid]
+
+    def ids(self):
+        with self.lock:
+            return list(self.versions.keys())
+
+
+class AsyncBroadcast:
+    """Versioned broadcast: ``.value``, ``.value_at(version)`` (``value(index)`` in the reference),
+    ``.index``, ``set_id``.  Every ``AsyncBroadcast(ctx, w)`` publishes a new version into the
+    context's ring, so workers can recover history by re-reading old model versions instead of
+    shipping gradients (slides: "recovers history by partial model updates")."""
+
+    def __init__(self, ctx, value: Any, slots: int = 8):
+        store: Optional[_VersionStore] = getattr(ctx, "_bcast_store", None)
+        if store is None or store.slots != slots:
+            store = _VersionStore(slots)
+            setattr(ctx, "_bcast_store", store)
+        self._store = store
+        self._bc = Broadcast(value)
+        self._id = self._bc.id
+        store.put(self._id, self._bc.value)
+
+    @property
+    def value(self) -> Any:
+        return self._store.get(self._id)
+
+    def value_at(self, version: int) -> Any:
+        return self._store.get(int(version))
+
+    def __call__(self, version: Optional[int] = None) -> Any:
+        return self.value if version is None else self.value_at(version)
+
+    @property
+    def index(self) -> int:
+        return self._id
+
+    def get_index(self) -> int:
+        return self._id
+
+    def set_id(self, new_id: int) -> None:
+        self._store.get(int(new_id))  # validate
+        self._id = int(new_id)
+
+    def available_versions(self):
+        return self._store.ids()

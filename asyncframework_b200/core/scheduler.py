@@ -1,0 +1,239 @@
+"""In-process job scheduler: the ``local[N]`` substrate the reference's samples actually run on.
+
+Replaces SparkContext.runJob -> DAGScheduler -> TaskSchedulerImpl -> LocalSchedulerBackend ->
+Executor (core/SparkContext.scala:2038-2064, scheduler/DAGScheduler.scala:587-660,
+scheduler/local/LocalSchedulerBackend.scala:83-88, executor/Executor.scala:290-560) with the part
+ASYNC needs: single-stage jobs of one task per partition, **hard** partition->executor affinity
+(partition p always runs on executor p % N; the reference only has best-effort locality, S4),
+per-task retry (spark.task.maxFailures = 4), a result handler invoked under a lock as tasks
+finish (JobWaiter.taskSucceeded, scheduler/JobWaiter.scala:56-64), and the ASYNC delta:
+**non-blocking mode** — ``set_mode(1)`` makes ``run_job`` return right after submission
+(DAGScheduler.scala:641-660), with the reference's "first async job still blocks" quirk
+available as an option (``block_first_async_job``; Appendix B.4).
+
+Executors are Python threads; heavy work inside tasks is torch / CUDA which releases the GIL.
+When a CUDA device is given each executor owns a CUDA stream so logical workers overlap on one GPU.
+"""
+from __future__ import annotations
+
+import itertools
+import queue
+import threading
+import time
+import traceback
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+
+@dataclass
+class TaskContext:
+    job_id: int
+    partition_id: int
+    attempt: int
+    executor_id: int
+    device: Optional[torch.device] = None
+    stream: Any = None
+    submit_ms: float = 0.0
+    metrics: Dict[str, float] = field(default_factory=dict)
+
+
+class JobFailed(RuntimeError):
+    pass
+
+
+class JobWaiter:
+    """Tracks completion of one job (scheduler/JobWaiter.scala)."""
+
+    def __init__(self, job_id: int, total: int, result_handler: Optional[Callable[[int, Any], None]]):
+        self.job_id = job_id
+        self.total = total
+        self.finished = 0
+        self.result_handler = result_handler
+        self._lock = threading.Lock()
+        self._done = threading.Event()
+        self.failure: Optional[BaseException] = None
+        if total == 0:
+            self._done.set()
+
+    def task_succeeded(self, index: int, result: Any) -> None:
+        with self._lock:  # `synchronized` in the reference
+            if self.result_handler is not None:
+                self.result_handler(index, result)
+            self.finished += 1
+            if self.finished >= self.total:
+                self._done.set()
+
+    def job_failed(self, exc: BaseException) -> None:
+        with self._lock:
+            self.failure = exc
+            self._done.set()
+
+    def wait(self, timeout: Optional[float] = None) -> bool:
+        ok = self._done.wait(timeout)
+        if self.failure is not None:
+            raise JobFailed(f"job {self.job_id} failed: {self.failure}") from self.failure
+        return ok
+
+    @property
+    def done(self) -> bool:
+        return self._done.is_set()
+
+
+class ListenerBus:
+    """Synchronous event fan-out (LiveListenerBus analogue, S14).  Events are plain dicts:
+    job_start / task_start / task_end / task_failed / job_end."""
+
+    def __init__(self):
+        self._listeners: List[Callable[[dict], None]] = []
+
+    def add(self, fn: Callable[[dict], None]) -> None:
+        self._listeners.append(fn)
+
+    def post(self, event: dict) -> None:
+        for fn in self._listeners:
+            try:
+                fn(event)
+            except Exception:  # listeners must never take the scheduler down
+                traceback.print_exc()
+
+
+class _Task:
+    __slots__ = ("job", "partition", "func", "dataset", "attempt", "submit_ms")
+
+    def __init__(self, job, partition, func, dataset, submit_ms):
+        self.job, self.partition, self.func, self.dataset = job, partition, func, dataset
+        self.attempt = 0
+        self.submit_ms = submit_ms
+
+
+class Scheduler:
+    _job_ids = itertools.count(0)
+
+    def __init__(self, num_executors: int = 8, max_failures: int = 4, device=None,
+                 block_first_async_job: bool = True, name: str = "afb"):
+        self.num_executors = int(num_executors)
+        self.max_failures = int(max_failures)
+        self.device = torch.device(device) if device is not None else None
+        self.block_first_async_job = block_first_async_job
+        self.mode = 0            # 0 = blocking, 1 = non-blocking (sc.set_mode)
+        self.first_iter = 1
+        self.listeners = ListenerBus()
+        self.fault_injector: Optional[Callable[[TaskContext], None]] = None
+        self.failed_jobs: List[int] = []
+        self._queues: List["queue.Queue[Optional[_Task]]"] = [queue.Queue() for _ in range(self.num_executors)]
+        self._threads: List[threading.Thread] = []
+        self._stopped = False
+        self._streams = [None] * self.num_executors
+        for e in range(self.num_executors):
+            t = threading.Thread(target=self._executor_loop, args=(e,), name=f"{name}-executor-{e}", daemon=True)
+            t.start()
+            self._threads.append(t)
+
+    # ------------------------------------------------------------------ mode
+    def set_mode(self, mode: int) -> None:
+        self.mode = int(mode)
+
+    # ------------------------------------------------------------------ executors
+    def _executor_loop(self, eid: int) -> None:
+        stream = None
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.Stream(device=self.device)
+            self._streams[eid] = stream
+        q = self._queues[eid]
+        while True:
+            task = q.get()
+            if task is None:
+                return
+            self._run_task(task, eid, stream)
+
+    def _run_task(self, task: _Task, eid: int, stream) -> None:
+        job: JobWaiter = task.job
+        if job.failure is not None:
+            return
+        tctx = TaskContext(job.job_id, task.partition, task.attempt, eid, self.device, stream, task.submit_ms)
+        self.listeners.post({"event": "task_start", "job": job.job_id, "partition": task.partition,
+                             "attempt": task.attempt, "executor": eid, "t_ms": time.perf_counter() * 1e3})
+        t0 = time.perf_counter()
+        try:
+            if self.fault_injector is not None:
+                self.fault_injector(tctx)
+            if stream is not None:
+                with torch.cuda.stream(stream):
+                    result = task.func(tctx, task.dataset.iterator(task.partition, tctx))
+                    stream.synchronize()
+            else:
+                result = task.func(tctx, task.dataset.iterator(task.partition, tctx))
+        except Exception as exc:  # noqa: BLE001
+            task.attempt += 1
+            self.listeners.post({"event": "task_failed", "job": job.job_id, "partition": task.partition,
+                                 "attempt": task.attempt, "error": repr(exc)})
+            if task.attempt >= self.max_failures:
+                self.failed_jobs.append(job.job_id)
+                job.job_failed(exc)
+                on_fail = getattr(job, "on_task_lost", None)
+                if on_fail is not None:
+                    on_fail(task.partition, exc)
+            else:
+                self._queues[eid].put(task)   # retry on the same executor (hard affinity)
+            return
+        dt = (time.perf_counter() - t0) * 1e3
+        self.listeners.post({"event": "task_end", "job": job.job_id, "partition": task.partition,
+                             "executor": eid, "run_ms": dt, "metrics": tctx.metrics})
+        job.task_succeeded(task.partition, result)
+        if job.done:
+            self.listeners.post({"event": "job_end", "job": job.job_id, "t_ms": time.perf_counter() * 1e3})
+
+    # ------------------------------------------------------------------ jobs
+    def submit_job(self, dataset, func: Callable[[TaskContext, Iterable], Any],
+                   partitions: Optional[Sequence[int]] = None,
+                   result_handler: Optional[Callable[[int, Any], None]] = None,
+                   on_task_lost: Optional[Callable[[int, BaseException], None]] = None) -> JobWaiter:
+        if self._stopped:
+            raise RuntimeError("scheduler stopped")
+        parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
+        job = JobWaiter(next(Scheduler._job_ids), len(parts), result_handler)
+        job.on_task_lost = on_task_lost  # type: ignore[attr-defined]
+        now = time.perf_counter() * 1e3
+        self.listeners.post({"event": "job_start", "job": job.job_id, "partitions": parts, "t_ms": now})
+        for p in parts:
+            self._queues[p % self.num_executors].put(_Task(job, p, func, dataset, now))
+        return job
+
+    def run_job(self, dataset, func, partitions=None, result_handler=None, on_task_lost=None):
+        """Blocking in mode 0 (returns the per-partition results in order); in mode 1 returns
+        immediately after submission (except, optionally, for the very first async job)."""
+        results: Dict[int, Any] = {}
+        if result_handler is None:
+            def result_handler(i, r):  # noqa: E306
+                results[i] = r
+        waiter = self.submit_job(dataset, func, partitions, result_handler, on_task_lost)
+        if self.mode == 0 or (self.first_iter == 1 and self.block_first_async_job):
+            waiter.wait()
+            if self.mode == 1:
+                self.first_iter = 0
+            parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
+            return [results.get(p) for p in parts]
+        if self.mode == 1:
+            self.first_iter = 0
+        return waiter
+
+    def stream_for(self, partition: int):
+        return self._streams[partition % self.num_executors]
+
+    def stop(self) -> None:
+        if self._stopped:
+            return
+        self._stopped = True
+        for q in self._queues:
+            q.put(None)
+        for t in self._threads:
+            t.join(timeout=5)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.stop()

@@ -1,0 +1,505 @@
+"""``ShardedDataset`` — the partitioned, lazily-evaluated dataset with the ASYNC actions.
+
+Covers the slice of the RDD API the ASYNC samples use (core/rdd/RDD.scala): ``map`` :370,
+``repartition`` :420-475, ``sample`` :488-503, ``mapPartitionsWithIndex`` :847, ``zipWithIndex``
+:1527 (+ ZippedWithIndexRDD.scala:43-69), ``cache`` :207, ``count`` :1392, ``reduce`` :1017-1042,
+``aggregate`` :1252, ``treeAggregate`` :1358-1388 — and the ASYNC additions ``ASYNCbarrier``
+:1050-1077, ``ASYNCreduce`` :1087-1171, ``ASYNCaggregate`` :1268-1345.
+
+Two evaluation granularities share one lineage graph:
+  * record level  — iterators of Python records (``LabeledPoint`` …): full API generality,
+    used by tests, tiny data and arbitrary user closures;
+  * batch level   — a partition is one columnar ``Shard`` (dense/CSR tensors, possibly in HBM);
+    ``sample``/``zip_with_index``/``async_barrier`` stay vectorised and ``map_batch`` hands the
+    whole shard to torch code or to the fused CUDA kernels.  This is the fast path.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+import threading
+import time
+from typing import Any, Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..core import sampler as _sampler
+from ..core.partial_result import PartialResult
+from ..linalg.vectors import DenseVector, LabeledPoint, SparseVector, Vector
+from .batch import Shard, concat_shards, padded_ld
+
+_EMPTY = object()
+
+
+class ShardedDataset:
+    def __init__(self, scheduler, num_partitions: int,
+                 compute: Optional[Callable[[int, Any], Iterator]] = None,
+                 batch: Optional[Callable[[int, Any], Optional[Shard]]] = None,
+                 parent: Optional["ShardedDataset"] = None, name: str = "dataset"):
+        self.scheduler = scheduler
+        self.num_partitions = int(num_partitions)
+        self._compute = compute
+        self._batch = batch
+        self.parent = parent
+        self.name = name
+        self._cached_batches: Optional[List[Optional[Shard]]] = None
+        self._cached_records: Optional[List[list]] = None
+        self._want_cache = False
+        self._cache_lock = threading.Lock()
+        self.selected_workers: Optional[List[int]] = None   # set by async_barrier
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_shards(cls, scheduler, shards: Sequence[Shard], name: str = "shards") -> "ShardedDataset":
+        shards = list(shards)
+        for p, s in enumerate(shards):
+            s.partition = p
+
+        def batch(p, tctx):
+            return shards[p]
+
+        def compute(p, tctx):
+            s = shards[p]
+            return s.indexed_records() if s.gidx is not None else s.records()
+
+        ds = cls(scheduler, len(shards), compute, batch, None, name)
+        ds._shards = shards  # type: ignore[attr-defined]
+        return ds
+
+    @classmethod
+    def from_records(cls, scheduler, records: Sequence[Any], num_partitions: int, name: str = "records"):
+        """``sc.parallelize``: contiguous slices."""
+        records = list(records)
+        n = len(records)
+        bounds = [n * i // num_partitions for i in range(num_partitions + 1)]
+        parts = [records[bounds[i]:bounds[i + 1]] for i in range(num_partitions)]
+        return cls(scheduler, num_partitions, lambda p, t: iter(parts[p]), None, None, name)
+
+    @classmethod
+    def from_arrays(cls, scheduler, X, y, num_partitions: int, dtype=torch.float64, device=None,
+                    name: str = "arrays") -> "ShardedDataset":
+        X = torch.as_tensor(X, dtype=dtype)
+        y = torch.as_tensor(y, dtype=dtype)
+        n, d = X.shape
+        ld = padded_ld(d)
+        shards = []
+        for p in range(num_partitions):   # round-robin like repartition
+            rows = torch.arange(p, n, num_partitions)
+            Xp = torch.zeros(rows.numel(), ld, dtype=dtype)
+            Xp[:, :d] = X[rows]
+            shards.append(Shard(d, y[rows].clone(), Xp, partition=p).to(device))
+        return cls.from_shards(scheduler, shards, name)
+
+    # ------------------------------------------------------------------ evaluation
+    @property
+    def batch_capable(self) -> bool:
+        return self._batch is not None
+
+    def iterator(self, p: int, tctx=None) -> Iterator:
+        if self._cached_records is not None and self._cached_records[p] is not None:
+            return iter(self._cached_records[p])
+        if self._compute is not None:
+            it = self._compute(p, tctx)
+        else:
+            b = self.batch(p, tctx)
+            it = iter(()) if b is None else (b.indexed_records() if b.gidx is not None else b.records())
+        if self._want_cache and not self.batch_capable:
+            recs = list(it)
+            with self._cache_lock:
+                if self._cached_records is None:
+                    self._cached_records = [None] * self.num_partitions
+                self._cached_records[p] = recs
+            return iter(recs)
+        return it
+
+    def batch(self, p: int, tctx=None) -> Optional[Shard]:
+        if self._batch is None:
+            raise TypeError(f"dataset {self.name!r} has no batch-level view (a record-level map broke the columnar lineage)")
+        if self._cached_batches is not None and self._cached_batches[p] is not _EMPTY:
+            return self._cached_batches[p]
+        b = self._batch(p, tctx)
+        if self._want_cache:
+            with self._cache_lock:
+                if self._cached_batches is None:
+                    self._cached_batches = [_EMPTY] * self.num_partitions
+                self._cached_batches[p] = b
+        return b
+
+    def cache(self) -> "ShardedDataset":
+        """Mark for caching; materialised lazily by the first job (RDD.scala:207)."""
+        self._want_cache = True
+        return self
+
+    persist = cache
+
+    def _derive(self, compute=None, batch=None, name="") -> "ShardedDataset":
+        ds = ShardedDataset(self.scheduler, self.num_partitions, compute, batch, self, name or self.name)
+        ds.selected_workers = self.selected_workers
+        return ds
+
+    # ------------------------------------------------------------------ transformations
+    def map(self, f: Callable[[Any], Any]) -> "ShardedDataset":
+        return self._derive(lambda p, t: (f(r) for r in self.iterator(p, t)), None, "map")
+
+    def filter(self, f: Callable[[Any], bool]) -> "ShardedDataset":
+        return self._derive(lambda p, t: (r for r in self.iterator(p, t) if f(r)), None, "filter")
+
+    def flat_map(self, f) -> "ShardedDataset":
+        return self._derive(lambda p, t: itertools.chain.from_iterable(f(r) for r in self.iterator(p, t)), None, "flat_map")
+
+    def map_partitions_with_index(self, f: Callable[[int, Iterator], Iterator],
+                                  preserves_batch: bool = False) -> "ShardedDataset":
+        """``f(index, iterator) -> iterator``.  With ``preserves_batch=True`` the function is a
+        side-effect hook (e.g. the delay injector): it is invoked once per partition with an
+        empty iterator on the batch path and the shard passes through untouched."""
+        batch = None
+        if preserves_batch and self.batch_capable:
+            def batch(p, t):  # noqa: E306
+                b = self.batch(p, t)
+                if b is not None:
+                    for _ in f(p, iter(())):
+                        pass
+                return b
+        return self._derive(lambda p, t: f(p, self.iterator(p, t)), batch, "map_partitions_with_index")
+
+    def map_partitions(self, f: Callable[[Iterator], Iterator]) -> "ShardedDataset":
+        return self._derive(lambda p, t: f(self.iterator(p, t)), None, "map_partitions")
+
+    def map_batch(self, f: Callable[[Shard], Any]) -> "ShardedDataset":
+        """Batch-level map: one output record ``f(shard)`` per non-empty partition."""
+        def compute(p, t):
+            b = self.batch(p, t)
+            if b is None or b.num_rows == 0:
+                return iter(())
+            return iter((f(b),))
+        return self._derive(compute, None, "map_batch")
+
+    def glom(self) -> "ShardedDataset":
+        return self._derive(lambda p, t: iter((list(self.iterator(p, t)),)), None, "glom")
+
+    def sample(self, with_replacement: bool, fraction: float, seed: Optional[int] = None) -> "ShardedDataset":
+        """Bernoulli sample without replacement (the only mode the reference's drivers use).
+        Membership = hash(seed, global row index) < fraction — see core/sampler.py; an unseeded
+        call draws a fresh seed like the reference's unseeded ``.sample(false, 0.1)`` (B.9)."""
+        if with_replacement:
+            raise NotImplementedError("Poisson sampling with replacement is not used by ASYNC; use fraction<=1 without replacement")
+        if seed is None:
+            seed = int.from_bytes(np.random.bytes(8), "little")
+        seed = int(seed)
+
+        def batch(p, t):
+            b = self.batch(p, t)
+            if b is None:
+                return None
+            idx = b.gidx if b.gidx is not None else (torch.arange(b.num_rows, dtype=torch.int64) + (p << 40))
+            mask = _sampler.bernoulli_mask(seed, idx, fraction)
+            rows = torch.from_numpy(np.nonzero(mask)[0])
+            return b.select(rows)
+
+        def compute(p, t):
+            thr = _sampler.threshold24(fraction)
+            for pos, rec in enumerate(self.iterator(p, t)):
+                gi = rec[1] if (isinstance(rec, tuple) and len(rec) == 2 and isinstance(rec[1], int)) else (pos + (p << 40))
+                if int(_sampler.hash_u24(seed, np.asarray([gi]))[0]) < thr:
+                    yield rec
+
+        return self._derive(compute, batch if self.batch_capable else None, "sample")
+
+    def zip_with_index(self) -> "ShardedDataset":
+        """Global index = partition offset + position; runs a count job over the partitions to
+        get the offsets (ZippedWithIndexRDD.scala:43-56)."""
+        sizes = self.partition_sizes()
+        starts = [0] * self.num_partitions
+        for p in range(1, self.num_partitions):
+            starts[p] = starts[p - 1] + sizes[p - 1]
+
+        def batch(p, t):
+            b = self.batch(p, t)
+            if b is None:
+                return None
+            g = torch.arange(b.num_rows, dtype=torch.int64, device=b.device) + starts[p]
+            return Shard(b.num_features, b.y, b.X, b.indptr, b.indices, b.values, g, p, dict(b.meta))
+
+        def compute(p, t):
+            def strip(r):
+                return r[0] if (isinstance(r, tuple) and len(r) == 2 and isinstance(r[0], LabeledPoint)) else r
+            return ((strip(r), starts[p] + i) for i, r in enumerate(self.iterator(p, t)))
+
+        return self._derive(compute, batch if self.batch_capable else None, "zip_with_index")
+
+    def repartition(self, num_partitions: int) -> "ShardedDataset":
+        """Round-robin redistribution (``coalesce(shuffle=true)``, RDD.scala:420-475); this is the
+        one all-to-all of the pipeline and happens once at load time."""
+        P = int(num_partitions)
+        if self.batch_capable:
+            olds = [self.batch(p) for p in range(self.num_partitions)]
+            olds = [o for o in olds if o is not None]
+            buckets: List[List[Shard]] = [[] for _ in range(P)]
+            start = 0
+            for o in olds:
+                for q in range(P):
+                    first = (q - start) % P
+                    rows = torch.arange(first, o.num_rows, P)
+                    if rows.numel():
+                        buckets[q].append(o.select(rows))
+                start = (start + o.num_rows) % P
+            d = olds[0].num_features if olds else 0
+            shards = []
+            for q in range(P):
+                if buckets[q]:
+                    shards.append(concat_shards(buckets[q], q))
+                else:
+                    proto = olds[0]
+                    shards.append(proto.select(torch.zeros(0, dtype=torch.int64)))
+            return ShardedDataset.from_shards(self.scheduler, shards, "repartition")
+        parts: List[list] = [[] for _ in range(P)]
+        i = 0
+        for p in range(self.num_partitions):
+            for r in self.iterator(p):
+                parts[i % P].append(r)
+                i += 1
+        return ShardedDataset(self.scheduler, P, lambda p, t: iter(parts[p]), None, None, "repartition")
+
+    # ------------------------------------------------------------------ ASYNC: barrier
+    def async_barrier(self, predicate: Callable[[Any], bool], stat) -> "ShardedDataset":
+        """Select the workers that take part in the next round (``ASYNCbarrier``,
+        RDD.scala:1050-1077): partitions whose STAT entry satisfies ``predicate(state) and
+        state.available`` — or that have no entry yet.  Non-selected partitions evaluate to empty.
+        The selection is stored on the returned dataset (not in a process-global, quirk B.2)."""
+        selected: List[int] = []
+        for p in range(self.num_partitions):
+            st = stat.get(p)
+            if st is None:
+                selected.append(p)
+            elif st.alive and st.available and predicate(st):
+                selected.append(p)
+        sel = set(selected)
+
+        def compute(p, t):
+            return self.iterator(p, t) if p in sel else iter(())
+
+        batch = None
+        if self.batch_capable:
+            def batch(p, t):  # noqa: E306
+                return self.batch(p, t) if p in sel else None
+        ds = self._derive(compute, batch, "async_barrier")
+        ds.selected_workers = selected
+        return ds
+
+    ASYNCbarrier = async_barrier
+
+    # ------------------------------------------------------------------ blocking actions
+    def _run(self, func, partitions=None):
+        prev = self.scheduler.mode
+        self.scheduler.set_mode(0)
+        try:
+            return self.scheduler.run_job(self, func, partitions)
+        finally:
+            self.scheduler.set_mode(prev)
+
+    def collect(self) -> list:
+        out = self._run(lambda t, it: list(it))
+        return [r for part in out for r in part]
+
+    def count(self) -> int:
+        return sum(self.partition_sizes())
+
+    def partition_sizes(self) -> List[int]:
+        """``mapPartitionsWithIndex{(i,rows)=>(i,rows.size)}`` histogram (SparkASGDThread.scala:77)."""
+        if self.batch_capable:
+            def f(t, it):
+                b = self.batch(t.partition_id, t)
+                return 0 if b is None else b.num_rows
+        else:
+            def f(t, it):
+                return sum(1 for _ in it)
+        return [int(x) for x in self._run(f)]
+
+    def first(self):
+        for p in range(self.num_partitions):
+            for r in self.iterator(p):
+                return r
+        raise ValueError("empty dataset")
+
+    def take(self, n: int) -> list:
+        out = []
+        for p in range(self.num_partitions):
+            for r in self.iterator(p):
+                out.append(r)
+                if len(out) >= n:
+                    return out
+        return out
+
+    def reduce(self, f: Callable[[Any, Any], Any]):
+        def part(t, it):
+            it = iter(it)
+            try:
+                acc = next(it)
+            except StopIteration:
+                return _EMPTY
+            for r in it:
+                acc = f(acc, r)
+            return acc
+        vals = [v for v in self._run(part) if v is not _EMPTY]
+        if not vals:
+            raise ValueError("empty collection")
+        acc = vals[0]
+        for v in vals[1:]:
+            acc = f(acc, v)
+        return acc
+
+    def aggregate(self, zero_factory, seq_op, comb_op):
+        """``zero_factory`` is a callable returning a fresh zero (the reference clones the zero
+        value per task via serialisation)."""
+        zf = zero_factory if callable(zero_factory) else (lambda: _clone(zero_factory))
+
+        def part(t, it):
+            acc = zf()
+            for r in it:
+                acc = seq_op(acc, r)
+            return acc
+        acc = zf()
+        for v in self._run(part):
+            acc = comb_op(acc, v)
+        return acc
+
+    def tree_aggregate(self, zero_factory, seq_op, comb_op, depth: int = 2):
+        """Hierarchical reduce (RDD.scala:1358-1388): partials are combined in ``depth`` levels."""
+        zf = zero_factory if callable(zero_factory) else (lambda: _clone(zero_factory))
+
+        def part(t, it):
+            acc = zf()
+            for r in it:
+                acc = seq_op(acc, r)
+            return acc
+        partials = self._run(part)
+        scale = max(int(math.ceil(len(partials) ** (1.0 / max(depth, 1)))), 2)
+        while len(partials) > scale + math.ceil(len(partials) / scale):
+            groups = max(len(partials) // scale, 1)
+            merged = []
+            for g in range(groups):
+                grp = partials[g::groups]
+                acc = grp[0]
+                for v in grp[1:]:
+                    acc = comb_op(acc, v)
+                merged.append(acc)
+            partials = merged
+        acc = partials[0]
+        for v in partials[1:]:
+            acc = comb_op(acc, v)
+        return acc
+
+    def foreach_partition(self, f) -> None:
+        self._run(lambda t, it: f(it))
+
+    # ------------------------------------------------------------------ ASYNC actions
+    def _async_submit(self, ctx, part_fn, envelope_ts_only: bool, empty_raises: bool):
+        """Shared machinery of async_reduce / async_aggregate (RDD.scala:1087-1171, 1268-1345)."""
+        sched = self.scheduler
+        selected = list(range(self.num_partitions)) if self.selected_workers is None else list(self.selected_workers)
+        if not selected:
+            return None   # "if the same w is passed here, we shouldn't run the job again" (:1095-1097)
+        start = time.perf_counter() * 1e3
+        ts = ctx.current_time
+        ctx.last_time = ts
+        for p in selected:
+            ctx.mark_submitted(p)      # busy until their result returns (:1138-1142)
+        sel = set(selected)
+
+        def merge(index: int, result):
+            count, value = result
+            with ctx.merge_lock:
+                if value is not _EMPTY:
+                    end = time.perf_counter() * 1e3
+                    staleness = ctx.current_time - ts
+                    ctx.put(PartialResult(value, staleness, ts, count, index, start, end))
+                    free = ctx.mark_finished(index) if index in sel else True
+                    ctx.stat.task_done(index, staleness, end - start)
+                    if not free:
+                        ctx.stat.set_available(index, False)
+                    ctx.add_to_current_time(1)
+                else:
+                    if index in sel:
+                        free = ctx.mark_finished(index)
+                        ctx.dropped_empty += 1
+                        if empty_raises:
+                            ctx.stat.set_available(index, free)
+                            raise ValueError(f"async_aggregate: selected partition {index} produced no records")
+                    else:
+                        free = ctx.inflight(index) == 0
+                    if free:
+                        ctx.stat.set_available(index, True)
+
+        def lost(index: int, exc):   # a failed async task must not strand its worker (quirk B.15)
+            if index in sel:
+                ctx.mark_finished(index)
+            ctx.stat.set_available(index, True)
+
+        sched.set_mode(1)   # ASYNCreduce always switches the scheduler to non-blocking (RDD.scala:1167)
+        # only the selected partitions do work; running the no-op tasks of the others is pure
+        # overhead (the reference runs them and they just flip availability) — skip them.
+        return sched.run_job(self, part_fn, selected, merge, lost)
+
+    def async_reduce(self, f: Callable[[Any, Any], Any], ctx):
+        """Non-blocking reduce: each selected partition's ``reduceLeft(f)`` lands in ``ctx`` as it
+        finishes, tagged with staleness / worker id."""
+        record_stat = ctx.record_stat
+
+        def part(t, it):
+            it = iter(it)
+            try:
+                acc = next(it)
+            except StopIteration:
+                return (0, _EMPTY)
+            n = 1
+            for r in it:
+                acc = f(acc, r)
+                n += 1
+            return (n if record_stat else -(2**31), acc)
+        return self._async_submit(ctx, part, envelope_ts_only=False, empty_raises=False)
+
+    def async_aggregate(self, zero_factory, seq_op, comb_op, ctx, strict_empty: bool = False):
+        """Non-blocking aggregate; the envelope carries the submit timestamp (and, unlike the
+        reference, also the staleness).  ``strict_empty`` reproduces the reference's
+        ``None.get`` failure on an empty sampled partition (RDD.scala:1333, quirk B.5)."""
+        zf = zero_factory if callable(zero_factory) else (lambda: _clone(zero_factory))
+        record_stat = ctx.record_stat
+
+        def part(t, it):
+            acc = zf()
+            n = 0
+            for r in it:
+                acc = seq_op(acc, r)
+                n += 1
+            if n == 0:
+                return (0, _EMPTY)
+            return (n if record_stat else -(2**31), acc)
+        return self._async_submit(ctx, part, envelope_ts_only=True, empty_raises=strict_empty)
+
+    ASYNCreduce = async_reduce
+    ASYNCaggregate = async_aggregate
+
+    # ------------------------------------------------------------------ misc
+    def get_num_partitions(self) -> int:
+        return self.num_partitions
+
+    def shards(self) -> List[Optional[Shard]]:
+        return [self.batch(p) for p in range(self.num_partitions)]
+
+    def __repr__(self) -> str:
+        return f"ShardedDataset({self.name}, P={self.num_partitions}, batch={self.batch_capable})"
+
+
+def _clone(z):
+    if isinstance(z, torch.Tensor):
+        return z.clone()
+    if isinstance(z, DenseVector):
+        return z.copy()
+    if isinstance(z, tuple):
+        return tuple(_clone(v) for v in z)
+    if isinstance(z, list):
+        return [_clone(v) for v in z]
+    if isinstance(z, dict):
+        return {k: _clone(v) for k, v in z.items()}
+    return z

@@ -1,0 +1,238 @@
+// Multithreaded mmap LIBSVM parser (C ABI, loaded through ctypes).
+//
+// Behavioural parity with MLUtils.loadLibSVMFile / parseLibSVMRecord
+// (mllib/util/MLUtils.scala:97-148): lines are trimmed; empty lines and lines starting with
+// '#' are skipped; tokens are split on single spaces with empty tokens dropped; the first
+// token is the label (double); the rest are `index:value` with 1-based indices converted to
+// 0-based; indices must be strictly increasing (so a 0 index in the file fails); a label-only
+// line gives an all-zero row.  Output is CSR (labels, indptr, indices, values) plus the
+// maximum index seen (for the auto feature count, MLUtils.scala:91-95).
+//
+// Design: the file is mmap'ed, cut into T byte ranges aligned to line starts, each parsed by
+// a std::thread into thread-local vectors, then stitched.  No JVM, no per-record allocation.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Chunk {
+  std::vector<double> labels;
+  std::vector<int64_t> row_nnz;
+  std::vector<int32_t> indices;
+  std::vector<double> values;
+  int32_t max_index = -1;
+  std::string error;
+  int64_t first_line = 0;
+};
+
+struct Parsed {
+  std::vector<double> labels;
+  std::vector<int64_t> indptr;
+  std::vector<int32_t> indices;
+  std::vector<double> values;
+  int32_t max_index = -1;
+};
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\f' || c == '\v'; }
+
+// strtod on a bounded token (tokens are short; copy into a stack buffer to NUL-terminate).
+inline bool parse_double(const char* b, const char* e, double* out) {
+  char buf[64];
+  size_t n = static_cast<size_t>(e - b);
+  if (n == 0 || n >= sizeof(buf)) return false;
+  memcpy(buf, b, n);
+  buf[n] = 0;
+  char* endp = nullptr;
+  errno = 0;
+  double v = strtod(buf, &endp);
+  if (endp != buf + n) return false;
+  *out = v;
+  return true;
+}
+
+inline bool parse_int(const char* b, const char* e, int64_t* out) {
+  if (b == e) return false;
+  bool neg = false;
+  if (*b == '-' || *b == '+') { neg = (*b == '-'); ++b; if (b == e) return false; }
+  int64_t v = 0;
+  for (; b < e; ++b) {
+    if (*b < '0' || *b > '9') return false;
+    v = v * 10 + (*b - '0');
+    if (v > (1LL << 40)) return false;
+  }
+  *out = neg ? -v : v;
+  return true;
+}
+
+void parse_range(const char* data, size_t begin, size_t end, Chunk* out) {
+  size_t pos = begin;
+  int64_t line_no = 0;
+  while (pos < end) {
+    size_t eol = pos;
+    while (eol < end && data[eol] != '\n') ++eol;
+    const char* b = data + pos;
+    const char* e = data + eol;
+    pos = eol + 1;
+    ++line_no;
+    while (b < e && is_ws(*b)) ++b;       // trim
+    while (e > b && is_ws(e[-1])) --e;
+    if (b == e || *b == '#') continue;
+    // label
+    const char* t = b;
+    while (t < e && *t != ' ') ++t;
+    double label;
+    if (!parse_double(b, t, &label)) {
+      out->error = "bad label at line " + std::to_string(line_no) + " of chunk: '" + std::string(b, t) + "'";
+      return;
+    }
+    out->labels.push_back(label);
+    int64_t nnz = 0;
+    int64_t prev = -1;
+    b = t;
+    while (b < e) {
+      while (b < e && *b == ' ') ++b;      // empty tokens dropped
+      if (b >= e) break;
+      t = b;
+      while (t < e && *t != ' ') ++t;
+      const char* colon = b;
+      while (colon < t && *colon != ':') ++colon;
+      int64_t idx1;
+      double val;
+      if (colon == t || !parse_int(b, colon, &idx1) || !parse_double(colon + 1, t, &val)) {
+        out->error = "bad index:value token '" + std::string(b, t) + "' at line " + std::to_string(line_no) + " of chunk";
+        return;
+      }
+      int64_t idx0 = idx1 - 1;  // 1-based -> 0-based
+      if (!(idx0 > prev)) {
+        out->error = "indices should be one-based and in ascending order; found current=" +
+                     std::to_string(idx0) + ", previous=" + std::to_string(prev) +
+                     " at line " + std::to_string(line_no) + " of chunk";
+        return;
+      }
+      prev = idx0;
+      out->indices.push_back(static_cast<int32_t>(idx0));
+      out->values.push_back(val);
+      ++nnz;
+      b = t;
+    }
+    out->row_nnz.push_back(nnz);
+    if (prev > out->max_index) out->max_index = static_cast<int32_t>(prev);
+  }
+}
+
+void set_err(char* err, int errlen, const std::string& msg) {
+  if (err && errlen > 0) {
+    snprintf(err, static_cast<size_t>(errlen), "%s", msg.c_str());
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* afb_libsvm_parse(const char* path, int num_threads, char* err, int errlen) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path + ": " + strerror(errno)); return nullptr; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); set_err(err, errlen, "fstat failed"); return nullptr; }
+  size_t size = static_cast<size_t>(st.st_size);
+  auto* result = new Parsed();
+  result->indptr.push_back(0);
+  if (size == 0) { close(fd); return result; }
+  void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) { delete result; set_err(err, errlen, "mmap failed"); return nullptr; }
+  madvise(map, size, MADV_SEQUENTIAL);
+  const char* data = static_cast<const char*>(map);
+
+  int T = std::max(1, num_threads);
+  if (size < (1u << 16)) T = 1;
+  std::vector<size_t> cuts(T + 1);
+  cuts[0] = 0;
+  cuts[T] = size;
+  for (int t = 1; t < T; ++t) {
+    size_t p = size / T * t;
+    if (p < cuts[t - 1]) p = cuts[t - 1];
+    while (p < size && data[p] != '\n') ++p;
+    cuts[t] = std::min(size, p + 1);
+  }
+  std::vector<Chunk> chunks(T);
+  std::vector<std::thread> threads;
+  for (int t = 0; t < T; ++t)
+    threads.emplace_back(parse_range, data, cuts[t], cuts[t + 1], &chunks[t]);
+  for (auto& th : threads) th.join();
+  munmap(map, size);
+
+  size_t rows = 0, nnz = 0;
+  for (auto& c : chunks) {
+    if (!c.error.empty()) { set_err(err, errlen, c.error); delete result; return nullptr; }
+    rows += c.labels.size();
+    nnz += c.values.size();
+  }
+  result->labels.reserve(rows);
+  result->indptr.reserve(rows + 1);
+  result->indices.reserve(nnz);
+  result->values.reserve(nnz);
+  int64_t acc = 0;
+  for (auto& c : chunks) {
+    result->labels.insert(result->labels.end(), c.labels.begin(), c.labels.end());
+    for (int64_t n : c.row_nnz) { acc += n; result->indptr.push_back(acc); }
+    result->indices.insert(result->indices.end(), c.indices.begin(), c.indices.end());
+    result->values.insert(result->values.end(), c.values.begin(), c.values.end());
+    result->max_index = std::max(result->max_index, c.max_index);
+  }
+  return result;
+}
+
+int64_t afb_libsvm_rows(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->labels.size()); }
+int64_t afb_libsvm_nnz(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->values.size()); }
+int32_t afb_libsvm_max_index(void* h) { return static_cast<Parsed*>(h)->max_index; }
+
+void afb_libsvm_copy(void* h, double* labels, int64_t* indptr, int32_t* indices, double* values) {
+  auto* p = static_cast<Parsed*>(h);
+  if (!p->labels.empty()) memcpy(labels, p->labels.data(), p->labels.size() * sizeof(double));
+  memcpy(indptr, p->indptr.data(), p->indptr.size() * sizeof(int64_t));
+  if (!p->values.empty()) {
+    memcpy(indices, p->indices.data(), p->indices.size() * sizeof(int32_t));
+    memcpy(values, p->values.data(), p->values.size() * sizeof(double));
+  }
+}
+
+void afb_libsvm_free(void* h) { delete static_cast<Parsed*>(h); }
+
+// Fast writer: one row per line, `label idx:val ...` with 1-based indices (MLUtils.scala:176-187).
+int afb_libsvm_write(const char* path, int64_t rows, const double* labels, const int64_t* indptr,
+                     const int32_t* indices, const double* values, char* err, int errlen) {
+  FILE* f = fopen(path, "w");
+  if (!f) { set_err(err, errlen, std::string("cannot open ") + path); return -1; }
+  std::vector<char> buf(1 << 20);
+  setvbuf(f, buf.data(), _IOFBF, buf.size());
+  for (int64_t r = 0; r < rows; ++r) {
+    double l = labels[r];
+    if (l == std::floor(l) && std::fabs(l) < 1e15) fprintf(f, "%.1f", l); else fprintf(f, "%.17g", l);
+    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+      double v = values[k];
+      if (v == std::floor(v) && std::fabs(v) < 1e15) fprintf(f, " %d:%.1f", indices[k] + 1, v);
+      else fprintf(f, " %d:%.17g", indices[k] + 1, v);
+    }
+    fputc('\n', f);
+  }
+  fclose(f);
+  return 0;
+}
+
+}  // extern "C"
