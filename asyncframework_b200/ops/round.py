@@ -1,0 +1,257 @@
+"""Launcher for the fused round kernels (csrc/kernels/dense_round.cu, csr_round.cu).
+
+One ``RoundKernel`` = one logical worker bound to one HBM-resident ``Shard``.  It owns the
+worker-local scratch (pulled ``w`` copy, gradient accumulator, control block, SAGA history) and
+holds raw pointers to the *server block* — a byte region laid out by ``ServerLayout`` that lives
+either in ordinary device memory (single process) or in rank 0's symmetric memory, in which case
+the pointers are NVLink peer pointers and the same kernel performs the push/pull over NVSwitch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ..core.sampler import threshold24
+from ..data.batch import Shard
+from . import check, kernels
+from ._signatures import (RESULT_REC_DTYPE, RoundParams, SERVER_CTL_DTYPE, SyncPeers, WORKER_CTL_DTYPE,
+                          WORKER_SLOT_DTYPE)
+
+ALGO = {"grad_only": 0, "asgd": 1, "asaga": 2, "sgd_sync": 3, "saga_sync": 4}
+NEVER_STALE = 1 << 40
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class ServerLayout:
+    """Byte layout of the server block.  Identical on every rank (symmetric allocation)."""
+    ld: int
+    num_workers: int
+    ring_size: int = 4096
+
+    def __post_init__(self):
+        off = 0
+        self.off_w = off; off = _align(off + self.ld * 4)
+        self.off_abar = off; off = _align(off + self.ld * 4)
+        self.off_sctl = off; off = _align(off + SERVER_CTL_DTYPE.itemsize)
+        self.off_status = off; off = _align(off + self.num_workers * WORKER_SLOT_DTYPE.itemsize)
+        self.off_ring = off; off = _align(off + self.ring_size * RESULT_REC_DTYPE.itemsize)
+        self.slot_stride = self.ld + 4
+        self.off_gstage = off; off = _align(off + 2 * self.num_workers * self.slot_stride * 4)
+        self.off_flags = off; off = _align(off + 2 * self.num_workers * 4)
+        self.off_hist_w = off   # AsyncBroadcast ring of K parameter versions follows (optional)
+        self.nbytes = off
+
+    def with_history(self, slots: int) -> int:
+        return self.nbytes + _align(slots * self.ld * 4)
+
+
+class ServerBlock:
+    """Typed views over a server block that lives on *this* device (rank 0's copy is the
+    authoritative parameter server; in BSP modes every rank's copy holds its local replica)."""
+
+    def __init__(self, layout: ServerLayout, buf: torch.Tensor):
+        assert buf.dtype == torch.uint8 and buf.numel() >= layout.nbytes
+        self.layout = layout
+        self.buf = buf
+        L = layout
+        self.w = buf[L.off_w:L.off_w + L.ld * 4].view(torch.float32)
+        self.abar = buf[L.off_abar:L.off_abar + L.ld * 4].view(torch.float32)
+        self.sctl = buf[L.off_sctl:L.off_sctl + SERVER_CTL_DTYPE.itemsize]
+        self.status = buf[L.off_status:L.off_status + L.num_workers * WORKER_SLOT_DTYPE.itemsize]
+        self.ring = buf[L.off_ring:L.off_ring + L.ring_size * RESULT_REC_DTYPE.itemsize]
+        self.gstage = buf[L.off_gstage:L.off_gstage + 2 * L.num_workers * L.slot_stride * 4].view(torch.float32)
+        self.flags = buf[L.off_flags:L.off_flags + 2 * L.num_workers * 4].view(torch.int32)
+
+    @classmethod
+    def allocate(cls, layout: ServerLayout, device) -> "ServerBlock":
+        return cls(layout, torch.zeros(layout.nbytes, dtype=torch.uint8, device=device))
+
+    def reset(self, w0: Optional[torch.Tensor] = None) -> None:
+        self.buf.zero_()
+        if w0 is not None:
+            self.w[: w0.numel()].copy_(w0.to(torch.float32))
+        st = np.zeros(self.layout.num_workers, dtype=WORKER_SLOT_DTYPE)
+        st["available"] = 1
+        st["alive"] = 1
+        self.status.copy_(torch.from_numpy(st.view(np.uint8)).to(self.buf.device))
+        sc = np.zeros(1, dtype=SERVER_CTL_DTYPE)
+        sc["avail_count"] = self.layout.num_workers
+        self.sctl.copy_(torch.from_numpy(sc.view(np.uint8)).to(self.buf.device))
+
+    # host-side reads (sync D2H of a few hundred bytes)
+    def read_sctl(self) -> Dict[str, int]:
+        a = self.sctl.cpu().numpy().view(SERVER_CTL_DTYPE)[0]
+        ck = int(a["clock_k"])
+        return {"clock": ck & 0xFFFFFFFF, "k": ck >> 32, "avail_count": int(a["avail_count"]), "stop": int(a["stop"]),
+                "avg_delay_ns": int(a["avg_delay_ns"]), "cul_count": int(a["cul_count"])}
+
+    def read_status(self) -> np.ndarray:
+        return self.status.cpu().numpy().view(WORKER_SLOT_DTYPE).copy()
+
+    def read_ring(self) -> np.ndarray:
+        return self.ring.cpu().numpy().view(RESULT_REC_DTYPE).copy()
+
+    def request_stop(self) -> None:
+        sc = self.sctl.cpu().numpy().view(SERVER_CTL_DTYPE).copy()
+        sc["stop"] = 1
+        # only the stop word is rewritten so in-flight counters are not clobbered
+        self.buf[self.layout.off_sctl + 12:self.layout.off_sctl + 16].copy_(
+            torch.from_numpy(np.asarray([1], dtype=np.int32).view(np.uint8)).to(self.buf.device))
+
+
+@dataclass
+class ServerPointers:
+    """Raw addresses of a server block as seen from the launching rank (local or peer-mapped)."""
+    base: int
+    layout: ServerLayout
+
+    @property
+    def w(self): return self.base + self.layout.off_w
+    @property
+    def abar(self): return self.base + self.layout.off_abar
+    @property
+    def sctl(self): return self.base + self.layout.off_sctl
+    @property
+    def status(self): return self.base + self.layout.off_status
+    @property
+    def ring(self): return self.base + self.layout.off_ring
+    @property
+    def gstage(self): return self.base + self.layout.off_gstage
+    @property
+    def flags(self): return self.base + self.layout.off_flags
+
+
+class RoundKernel:
+    """One logical worker's fused round: ``launch()`` enqueues exactly one kernel."""
+
+    def __init__(self, shard: Shard, server: ServerPointers, *, algo: str, loss_id: int, num_workers: int,
+                 worker_id: int, total_rows: int, batch_rate: float, gamma: float, seed: int,
+                 taw: int = NEVER_STALE, max_iters: int = 1 << 40, gate_threshold: int = 0,
+                 delay_mode: int = 0, delay_coeff: float = 0.0, warmup_updates: int = 0,
+                 local_block: Optional[ServerBlock] = None, peer_blocks: Optional[List[ServerPointers]] = None,
+                 grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None):
+        if shard.device.type != "cuda":
+            raise ValueError("RoundKernel needs an HBM-resident shard")
+        if shard.dtype != torch.float32:
+            raise TypeError("fused kernels are fp32 (storage and accumulate)")
+        self.lib = kernels()
+        self.shard = shard
+        self.device = shard.device
+        self.algo = algo
+        self.num_workers = num_workers
+        self.worker_id = worker_id
+        d = shard.num_features
+        ld = server.layout.ld
+        self.ld = ld
+        self.is_dense = shard.is_dense
+        if self.is_dense:
+            if shard.X.shape[1] != ld or not shard.X.is_contiguous():
+                raise ValueError(f"dense shard row stride {shard.X.shape[1]} != server ld {ld}")
+            if ld > self.lib.afb_dense_round_max_ld():
+                raise ValueError(f"dense fused kernel supports ld <= {self.lib.afb_dense_round_max_ld()}; use CSR layout")
+        dev = self.device
+        self.w_local = torch.zeros(ld, dtype=torch.float32, device=dev)
+        self.abar_local = torch.zeros(ld, dtype=torch.float32, device=dev)
+        self.g_local = torch.zeros(ld, dtype=torch.float32, device=dev)
+        self.wctl = torch.zeros(WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        saga = algo in ("asaga", "saga_sync")
+        self.hist = torch.zeros(shard.num_rows, dtype=torch.float32, device=dev) if saga else None
+        if rollback is None:
+            rollback = saga and taw < NEVER_STALE and algo == "asaga"
+        self.rollback = bool(rollback)
+        self.hist_prev = torch.zeros(shard.num_rows, dtype=torch.float32, device=dev) if self.rollback else None
+        self.hist_tag = torch.full((shard.num_rows,), -1, dtype=torch.int32, device=dev) if self.rollback else None
+        self.local_block = local_block
+        self.peers_buf = None
+        p = RoundParams()
+        if self.is_dense:
+            p.X = shard.X.data_ptr()
+        else:
+            p.indptr = shard.indptr.data_ptr(); p.indices = shard.indices.data_ptr(); p.values = shard.values.data_ptr()
+        p.y = shard.y.data_ptr()
+        contiguous_gidx = False
+        if shard.gidx is not None and shard.num_rows > 0:
+            g0 = int(shard.gidx[0])
+            contiguous_gidx = bool((shard.gidx[-1] - g0 + 1 == shard.num_rows).item()) and bool(
+                (shard.gidx[1:] - shard.gidx[:-1] == 1).all().item()) if shard.num_rows > 1 else True
+            p.row_base = g0
+        if shard.gidx is not None and not contiguous_gidx:
+            self._gidx = shard.gidx.contiguous()
+            p.gidx = self._gidx.data_ptr()
+        elif shard.gidx is None:
+            p.row_base = worker_id << 40
+        if self.hist is not None:
+            p.hist = self.hist.data_ptr()
+        if self.rollback:
+            p.hist_prev = self.hist_prev.data_ptr(); p.hist_tag = self.hist_tag.data_ptr()
+        p.ld = ld
+        p.w_server = server.w; p.abar_server = server.abar; p.sctl = server.sctl
+        p.status = server.status; p.ring = server.ring
+        p.w_local = self.w_local.data_ptr(); p.abar_local = self.abar_local.data_ptr()
+        p.g_local = self.g_local.data_ptr(); p.wctl = self.wctl.data_ptr()
+        p.n_rows = shard.num_rows; p.d = d; p.algo = ALGO[algo]; p.ring_size = server.layout.ring_size
+        p.num_workers = num_workers; p.worker_id = worker_id
+        p.thr24 = threshold24(batch_rate); p.gate_threshold = int(gate_threshold)
+        p.seed = int(seed); p.taw = int(min(taw, NEVER_STALE)); p.max_iters = int(max_iters)
+        p.gamma = float(gamma)
+        if algo in ("sgd_sync", "saga_sync"):
+            # BSP replica lives in the rank-local server block so rank 0's copy is the model
+            if local_block is None or peer_blocks is None:
+                raise ValueError("sync algorithms need local_block and peer_blocks")
+            p.w_local = local_block.w.data_ptr(); p.abar_local = local_block.abar.data_ptr()
+            p.sctl = local_block.sctl.data_ptr()
+            p.inv_par_recs = 1.0 / (batch_rate * total_rows)
+            sp = SyncPeers()
+            for q, pb in enumerate(peer_blocks):
+                sp.gstage[q] = pb.gstage; sp.flags[q] = pb.flags
+            self._sync_peers_host = sp
+            self.peers_buf = torch.from_numpy(np.frombuffer(bytes(sp), dtype=np.uint8).copy()).to(dev)
+            p.peers = self.peers_buf.data_ptr()
+            p.w_server = local_block.w.data_ptr()
+        else:
+            p.inv_par_recs = 1.0 / (batch_rate * total_rows / num_workers)
+        p.inv_n = 1.0 / total_rows
+        p.delay_coeff = float(delay_coeff); p.delay_mode = int(delay_mode); p.warmup_updates = int(warmup_updates)
+        if seed_mode is None:
+            seed_mode = {"asgd": 0, "asaga": 0, "sgd_sync": 1, "saga_sync": 1, "grad_only": 2}[algo]
+        p.seed_mode = int(seed_mode); p.loss_id = int(loss_id)
+        self.params = p
+        props = torch.cuda.get_device_properties(dev)
+        self.num_sms = props.multi_processor_count
+        self.grid = int(grid) if grid else (self.num_sms if self.is_dense else 2 * self.num_sms)
+        self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
+        self.launches = 0
+
+    # ------------------------------------------------------------------
+    def launch(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(self._launch(C.byref(self.params), self.grid, int(s.cuda_stream)), "round kernel launch")
+        self.launches += 1
+        if self.rollback:
+            check(self.lib.afb_saga_rollback_launch(self.hist.data_ptr(), self.hist_prev.data_ptr(), self.hist_tag.data_ptr(),
+                                                    self.shard.num_rows, self.wctl.data_ptr(), int(s.cuda_stream)), "saga rollback")
+            self.launches += 1
+
+    def set(self, **kw) -> None:
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+
+    def read_ctl(self) -> Dict[str, float]:
+        a = self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE)[0]
+        return {n: (float(a[n]) if a[n].dtype.kind == "f" else int(a[n])) for n in WORKER_CTL_DTYPE.names}
+
+    @property
+    def w_view(self) -> torch.Tensor:
+        """The parameter vector this worker computes with (BSP: the local replica)."""
+        if self.local_block is not None and self.algo in ("sgd_sync", "saga_sync"):
+            return self.local_block.w
+        return self.w_local

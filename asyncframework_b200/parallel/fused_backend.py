@@ -1,0 +1,223 @@
+"""The fused backend: every worker round is ONE hand-written kernel that pulls ``w`` over NVLink,
+computes the sampled gradient in a single pass and pushes/applies it into the server's HBM.
+
+``FusedEngine`` is the public API of this backend (what bench.py, the drivers and users call):
+
+    engine = FusedEngine(cfg, local_shards, total_rows)      # one process per GPU (torchrun) or 1 GPU
+    engine.run_rounds(n)      # enqueue n rounds per local worker; no host sync on the hot path
+    engine.step()             # end-to-end step: H2D round descriptor -> round -> D2H result
+    engine.weights()          # current model (rank 0's server block; BSP: the local replica)
+
+Mapping to the reference: a logical worker = an RDD partition (numPart), rank 0's server block =
+the driver's ``w`` / ``alphaBar`` / ``ScalarMap`` owner, the device-side clock/availability/result
+ring = ASYNCcontext (core/rdd/ASYNCcontext.scala) + workerState, and the gate/staleness logic =
+ASYNCbarrier + the updater thread's ``staleness <= taw`` filter (SparkASGDThread.scala:150-223).
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..config import AsyncConfig
+from ..core.partial_result import PartialResult
+from ..data.batch import Shard
+from ..ops._signatures import RESULT_REC_DTYPE, WORKER_CTL_DTYPE
+from ..ops.round import NEVER_STALE, RoundKernel, ServerBlock, ServerLayout, ServerPointers
+from ..optim.gradient import LOSS_IDS
+from .comm import SymmetricBuffer, allocate_symmetric
+
+ALGO_NAMES = {"asgd": "asgd", "asaga": "asaga", "sgd_sync": "sgd_sync", "saga_sync": "saga_sync"}
+
+
+def straggler_sets(num_partitions: int):
+    """Production-cluster straggler model (SparkASGDThread.scala:121-138): 25 % of the partitions
+    (indices 4c) are stragglers; the first 20 % of those are long-tail, the rest 'normal'."""
+    length = int(round(0.25 * num_partitions))
+    n_normal = int(round(0.8 * length))
+    n_long = length - n_normal
+    long_tail = [c * 4 for c in range(length) if c < n_long]
+    normal = [c * 4 for c in range(length) if c >= n_long]
+    return normal, long_tail
+
+
+class FusedEngine:
+    def __init__(self, cfg: AsyncConfig, local_shards: Sequence[Shard], total_rows: int,
+                 local_worker_ids: Optional[Sequence[int]] = None, device=None, group=None,
+                 ring_size: int = 4096, symm_provider: str = "auto", w0: Optional[torch.Tensor] = None):
+        self.cfg = cfg
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device(device) if device is not None else local_shards[0].device
+        self.P = int(cfg.num_partitions)
+        if local_worker_ids is None:
+            local_worker_ids = [p for p in range(self.P) if p % self.world == self.rank]
+        self.local_worker_ids = list(local_worker_ids)
+        if len(self.local_worker_ids) != len(local_shards):
+            raise ValueError("one shard per local worker expected")
+        self.total_rows = int(total_rows)
+        first = local_shards[0]
+        self.d = first.num_features
+        ld = first.ld if first.is_dense else (self.d + 3) // 4 * 4
+        self.layout = ServerLayout(ld, self.P, ring_size)
+        # ---- symmetric server block (rank 0's copy is the parameter server) ----------------
+        self.symm: SymmetricBuffer = allocate_symmetric(self.layout.nbytes, self.device, group, symm_provider)
+        self.block = ServerBlock(self.layout, self.symm.local)
+        self.block.reset(w0)
+        self.symm.barrier()
+        algo = cfg.algorithm
+        if algo not in ALGO_NAMES:
+            raise ValueError(f"fused backend does not implement {algo!r}")
+        self.algo = algo
+        self.is_async = algo in ("asgd", "asaga")
+        server = ServerPointers(self.symm.ptrs[0], self.layout)
+        # BSP: worker q's staging lives on the rank hosting q
+        peer_blocks = None
+        if not self.is_async:
+            if len(self.local_worker_ids) != 1 and self.world > 1:
+                raise ValueError("BSP fused mode runs one worker per rank")
+            peer_blocks = [ServerPointers(self.symm.ptrs[q % self.world], self.layout) for q in range(self.P)]
+            if self.world == 1 and self.P > 1:
+                raise ValueError("BSP fused mode on a single process supports P == 1 (use the in-process scheduler for P > 1)")
+        gate = 0
+        if self.is_async and cfg.barrier in ("bucket", "bsp"):
+            beta = 1.0 if cfg.barrier == "bsp" else cfg.bucket_ratio
+            gate = int(math.floor(self.P * beta))
+            if gate <= 1:
+                gate = 0          # >= 1 idle worker is always true for the asker itself
+        normal, long_tail = straggler_sets(self.P) if cfg.production_cluster else ([], [])
+        warm = cfg.warmup_updates_per_worker * (self.P if self.is_async else 1)
+        n_local = len(self.local_worker_ids)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.kernels: List[RoundKernel] = []
+        self.streams: List[torch.cuda.Stream] = []
+        for shard, wid in zip(local_shards, self.local_worker_ids):
+            if cfg.production_cluster:
+                dmode = 3 if wid in long_tail else (2 if wid in normal else 0)
+            else:
+                dmode = 1 if (cfg.coeff > 0 and wid == 0) else 0
+            grid = None
+            if n_local > 1:
+                per = max(1, sms // n_local)
+                grid = per if shard.is_dense else 2 * per
+            rk = RoundKernel(shard, server, algo=algo, loss_id=LOSS_IDS[cfg.loss], num_workers=self.P,
+                             worker_id=wid, total_rows=self.total_rows, batch_rate=cfg.batch_rate,
+                             gamma=cfg.step_size, seed=cfg.seed,
+                             taw=cfg.taw if cfg.taw < (1 << 31) - 1 else NEVER_STALE,
+                             max_iters=cfg.num_iterations if self.is_async else (1 << 40),
+                             gate_threshold=gate, delay_mode=dmode, delay_coeff=max(cfg.coeff, 0.0),
+                             warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid)
+            self.kernels.append(rk)
+            self.streams.append(torch.cuda.Stream(device=self.device) if n_local > 1 else torch.cuda.current_stream(self.device))
+        # pinned staging for the end-to-end path
+        self._desc_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self._desc_dev = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._ctl_host = torch.zeros(n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self._ring_seen = 0
+        self.rounds_enqueued = 0
+        self.symm.barrier()
+
+    # ------------------------------------------------------------------ hot path
+    def run_rounds(self, n: int) -> None:
+        """Enqueue ``n`` rounds on every local worker.  No host synchronisation."""
+        for _ in range(n):
+            for rk, st in zip(self.kernels, self.streams):
+                rk.launch(st)
+        self.rounds_enqueued += n
+
+    @property
+    def launches(self) -> int:
+        return sum(rk.launches for rk in self.kernels)
+
+    def synchronize(self) -> None:
+        for st in self.streams:
+            st.synchronize()
+
+    # ------------------------------------------------------------------ end-to-end step
+    def step(self, step_size: Optional[float] = None) -> Dict[str, float]:
+        """One user-visible step: copy this round's descriptor (step size, batch rate, delay
+        coefficient) from pinned host memory to the device, run one fused round per local worker,
+        copy each worker's result record back to pinned memory and return it."""
+        if step_size is not None:
+            for rk in self.kernels:
+                rk.params.gamma = float(step_size)
+        d = self._desc_host
+        d[0] = self.kernels[0].params.gamma
+        d[1] = self.cfg.batch_rate
+        d[2] = self.cfg.coeff
+        d[3] = float(self.rounds_enqueued)
+        self._desc_dev.copy_(d, non_blocking=True)                       # H2D (pinned)
+        for rk, st in zip(self.kernels, self.streams):
+            rk.launch(st)
+        self.rounds_enqueued += 1
+        for i, (rk, st) in enumerate(zip(self.kernels, self.streams)):
+            with torch.cuda.stream(st):
+                self._ctl_host[i].copy_(rk.wctl, non_blocking=True)      # D2H (pinned)
+        self.synchronize()
+        ctl = self._ctl_host.numpy().view(WORKER_CTL_DTYPE).reshape(-1)
+        loss = float(ctl["last_loss"].sum())
+        batch = int(ctl["last_batch"].sum())
+        return {"loss_sum": loss, "batch": batch, "accepted": int((ctl["last_accepted"] == 1).sum()),
+                "k": int(ctl["last_k_after"].max()), "staleness": int(ctl["last_staleness"].max())}
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return int(self._desc_host.numel() * 4)
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return int(self._ctl_host.numel())
+
+    # ------------------------------------------------------------------ state
+    def weights(self) -> torch.Tensor:
+        """Current model: rank 0's server ``w`` (peers read it through the symmetric mapping)."""
+        self.synchronize()
+        if self.is_async and self.rank != 0 and self.world > 1:
+            out = torch.empty(self.layout.ld, dtype=torch.float32, device=self.device)
+            src = self.symm.ptrs[0] + self.layout.off_w
+            import ctypes as C
+            rt = C.CDLL("libcudart.so.12")
+            rt.cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(src), C.c_size_t(self.layout.ld * 4), 3)
+            return out[: self.d]
+        return self.block.w[: self.d].clone()
+
+    def alpha_bar(self) -> torch.Tensor:
+        self.synchronize()
+        return self.block.abar[: self.d].clone()
+
+    def state(self) -> Dict[str, int]:
+        self.synchronize()
+        return self.block.read_sctl()
+
+    def worker_status(self) -> np.ndarray:
+        return self.block.read_status()
+
+    def drain_results(self) -> List[PartialResult]:
+        """New entries of the device result ring as ``PartialResult`` envelopes (rank 0)."""
+        ring = self.block.read_ring()
+        out: List[PartialResult] = []
+        n = self.layout.ring_size
+        while True:
+            rec = ring[self._ring_seen % n]
+            if int(rec["seq"]) != self._ring_seen + 1:
+                break
+            out.append(PartialResult(
+                data={"accepted": bool(rec["accepted"]), "loss_sum": float(rec["loss_sum"]), "step": float(rec["step"]),
+                      "k_after": int(rec["k_after"])},
+                staleness=int(rec["staleness"]), timestamp=int(rec["ts"]), batch_size=int(rec["batch"]),
+                worker_id=int(rec["worker"]), submit_ms=float(rec["t_start_ns"]) * 1e-6,
+                finish_ms=float(rec["t_end_ns"]) * 1e-6))
+            self._ring_seen += 1
+        return out
+
+    def request_stop(self) -> None:
+        if self.rank == 0:
+            self.block.request_stop()
+
+    def barrier(self) -> None:
+        self.symm.barrier()

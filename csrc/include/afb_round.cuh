@@ -1,0 +1,94 @@
+// Parameter blocks for the fused round kernels (mirrored 1:1 by ctypes Structures in
+// asyncframework_b200/ops/_signatures.py — keep field order and types in sync).
+#pragma once
+#include "afb_common.cuh"
+
+namespace afb {
+
+enum Algo : int {
+  ALGO_GRAD_ONLY = 0,   // g_local/loss/count only (used by GradientDescent, NCCL backend, tests)
+  ALGO_ASGD = 1,        // async: push-and-apply  w += -gamma/sqrt(floor(k/P)+1) * g/parRecs
+  ALGO_ASAGA = 2,       // async SAGA: w -= gamma*(g/parRecs + abar); abar += g/N
+  ALGO_SYNC_SGD = 3,    // BSP: all-gather of g over NVLink + replicated apply
+  ALGO_SYNC_SAGA = 4,
+};
+
+struct alignas(16) WorkerCtl {      // worker-local control block (device memory on the worker's GPU)
+  unsigned int chunk_ctr;           // dynamic row-chunk scheduler
+  unsigned int done_ctas;           // last-CTA election
+  unsigned int pull_ticket;         // first-CTA election for the pull
+  unsigned int pull_flag;           // == round+1 once w_local / ts / seed_key are valid
+  unsigned int round;               // rounds executed by this worker (incremented by the kernel)
+  int proceed;                      // set by the pulling CTA: 1 = run the round, 0 = stopped (k >= iters)
+  unsigned int batch_count;         // rows sampled this round
+  float loss_sum;                   // Σ loss this round
+  unsigned long long ts;            // logical clock read at pull
+  unsigned long long k_read;        // accepted-update counter read at pull
+  unsigned long long seed_key;      // mix64(seed_eff) for this round
+  unsigned long long t_start_ns;
+  // results of the last finished round (read by the host without touching the server)
+  int last_accepted;
+  unsigned int last_batch;
+  float last_loss;
+  float last_step;
+  long long last_staleness;
+  long long last_k_after;
+  unsigned long long last_task_ns;
+  unsigned long long rounds_done;
+};
+
+struct alignas(16) SyncPeers {      // BSP all-gather wiring (device array, one per worker)
+  float* gstage[16];                // gstage[q] = peer q's staging buffer [2][P][ld+4] (double-buffered by round parity)
+  unsigned int* flags[16];          // flags[q]  = peer q's arrival flags [2][P]
+  float* mc_gstage;                 // NVLS multicast alias of the staging buffer (or null)
+  unsigned int* mc_flags;           // NVLS multicast alias of the flags (or null)
+};
+
+struct RoundParams {
+  // ---- local shard ---------------------------------------------------------------------
+  const float* X;                   // dense: [n_rows, ld] row-major (null for CSR shards)
+  const long long* indptr;          // CSR: [n_rows+1]
+  const int* indices;               // CSR: [nnz] 0-based feature ids, ascending within a row
+  const float* values;              // CSR: [nnz]
+  const float* y;                   // [n_rows]
+  const long long* gidx;            // [n_rows] global row index, or null => row_base + i
+  float* hist;                      // SAGA: last residual per local row (or null)
+  float* hist_prev;                 // SAGA rollback mode: previous value (or null => write-through)
+  int* hist_tag;                    // SAGA rollback mode: round tag of the last write
+  long long row_base;
+  long long ld;
+  // ---- server state (local or NVLink peer pointers) -----------------------------------------
+  float* w_server;
+  float* abar_server;
+  ServerCtl* sctl;
+  WorkerSlot* status;
+  ResultRec* ring;
+  // ---- worker-local scratch ------------------------------------------------------------------
+  float* w_local;                   // [ld] pulled copy of w (sync modes: the local replica)
+  float* abar_local;                // sync SAGA replica
+  float* g_local;                   // [ld] zero on entry, zero on exit
+  WorkerCtl* wctl;
+  const SyncPeers* peers;           // sync modes only
+  // ---- scalars ---------------------------------------------------------------------------------
+  int n_rows;
+  int d;
+  int algo;
+  int ring_size;
+  int num_workers;                  // P
+  int worker_id;
+  int thr24;                        // Bernoulli threshold (2^24 => every row)
+  int gate_threshold;               // floor(P*beta); 0 => no gating
+  long long seed;
+  long long taw;                    // max staleness (>= 2^31 => never stale: single-atomic fast path)
+  long long max_iters;              // stop once k >= max_iters
+  float gamma;
+  float inv_par_recs;               // 1 / (b*N/P)  (ASGD/ASAGA) or 1 / (b*N) (sync)
+  float inv_n;                      // 1 / N
+  float delay_coeff;                // controlled delay: sleep coeff * avg_delay  (0 => none)
+  int delay_mode;                   // 0 none, 1 controlled (this worker sleeps), 2 production normal, 3 production long tail
+  int warmup_updates;               // calibration window (100*P async)
+  int seed_mode;                    // 0: seed + k_read + 1 ; 1: seed + round + 1 ; 2: seed (fixed)
+  int loss_id;                      // afb::LossId
+};
+
+}  // namespace afb

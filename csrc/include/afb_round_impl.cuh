@@ -1,0 +1,339 @@
+// Shared phases of the fused round kernels: gate + pull (phase 0) and the cross-GPU tail
+// (grid reduce bookkeeping, staleness gate, Hogwild push-and-apply / BSP all-gather apply).
+// Included by dense_round.cu and csr_round.cu; the gradient body in between is layout specific.
+#pragma once
+#include "afb_round.cuh"
+
+namespace afb {
+
+template <int kThreads>
+struct RoundShared {
+  float red[kThreads / 32];
+  unsigned int cnt[kThreads / 32];
+  unsigned int flag;
+  float bcast[4];
+};
+
+// Phase 0.  Returns false when the worker has been stopped (k >= max_iters or stop flag): the
+// kernel must then return immediately (bookkeeping for the next launch is already done).
+template <int kThreads>
+AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round) {
+  const int tid = threadIdx.x;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  const bool is_async = (p.algo == ALGO_ASGD || p.algo == ALGO_ASAGA);
+  // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
+  if (p.algo != ALGO_GRAD_ONLY) {
+    if (tid == 0) sh.flag = atomicAdd(&wc->pull_ticket, 1u);
+    __syncthreads();
+    if (sh.flag == 0) {
+      // This CTA is the puller: bucket gate, logical clock read, P2P fetch of w, delay injection.
+      if (tid == 0) {
+        int proceed = 1;
+        unsigned long long ck = 0;
+        if (is_async) {
+          if (p.gate_threshold > 0) {
+            // partial barrier: start only while >= floor(P*beta) workers are idle (this one included)
+            while (true) {
+              ck = ld_acquire_sys_u64(&p.sctl->clock_k);
+              if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
+              if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= p.gate_threshold) break;
+              __nanosleep(200);
+            }
+          }
+          ck = ld_acquire_sys_u64(&p.sctl->clock_k);
+          if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) proceed = 0;
+          if (proceed) {
+            red_add_release_sys_s32(&p.sctl->avail_count, -1);      // busy from submit until the result lands
+            WorkerSlot* me = p.status + p.worker_id;
+            unsigned long long now = globaltimer_ns();
+            me->available = 0;
+            me->busy_since_ns = now;
+            me->heartbeat_ns = now;
+            if (me->last_finish_ns) me->wait_ns += now - me->last_finish_ns;
+          }
+        } else {
+          ck = static_cast<unsigned long long>(round);             // sync: iteration counter is local
+        }
+        wc->ts = ck & 0xffffffffULL;
+        wc->k_read = is_async ? (ck >> 32) : round;
+        unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
+        if (p.seed_mode == 0) seed_eff += wc->k_read + 1ULL;
+        else if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+        wc->seed_key = mix64(seed_eff);
+        wc->proceed = proceed;
+        wc->t_start_ns = globaltimer_ns();
+      }
+      __syncthreads();
+      if (wc->proceed) {
+        // K10: parameter pull — vectorised sys-scope loads from the server's HBM over NVLink.
+        // (BSP modes keep a bit-identical local replica, so there is nothing to pull.)
+        if (is_async) {
+          for (int v = tid; v < nvec; v += kThreads)
+            *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
+        }
+        if (tid == 0 && p.delay_mode != 0) {
+          // A18 straggler injector: sleep a multiple of the calibrated mean task time.
+          unsigned long long avg = ld_acquire_sys_u64(&p.sctl->avg_delay_ns);
+          if (avg) {
+            float mult = p.delay_coeff;
+            if (p.delay_mode >= 2) {
+              float u = static_cast<float>(hash_u24(wc->seed_key ^ 0xD1B54A32D192ED03ULL, p.worker_id)) * (1.f / 16777216.f);
+              mult = (p.delay_mode == 3) ? (2.5f + 7.5f * u) : (1.5f + u);
+            }
+            sleep_ns(static_cast<unsigned long long>(mult * static_cast<float>(avg)));
+          }
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu_u32(&wc->pull_flag, round + 1u);
+    } else {
+      if (tid == 0) {
+        while (ld_acquire_gpu_u32(&wc->pull_flag) != round + 1u) __nanosleep(64);
+      }
+      __syncthreads();
+    }
+    if (!*reinterpret_cast<volatile int*>(&wc->proceed)) {
+      // stopped: still run the last-CTA bookkeeping so counters reset for the next launch
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int t = atomicAdd(&wc->done_ctas, 1u);
+        if (t == gridDim.x - 1) {
+          wc->done_ctas = 0; wc->pull_ticket = 0; wc->chunk_ctr = 0;
+          wc->last_accepted = -1;
+          __threadfence();
+          wc->round = round + 1u;
+        }
+      }
+      return false;
+    }
+  }
+
+  return true;
+}
+
+// Phase 2b + 3.  Called by every thread after the CTA has flushed its partial gradient into
+// g_local; `loss_acc` / `cnt` are the per-thread (lane-0-valid per warp) loss sum and row count.
+template <int kThreads>
+AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round,
+                             float loss_acc, unsigned int cnt) {
+  constexpr int kWarps = kThreads / 32;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  const bool is_async = (p.algo == ALGO_ASGD || p.algo == ALGO_ASAGA);
+  if (lane == 0) { sh.red[warp] = loss_acc; sh.cnt[warp] = cnt; }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f; unsigned int n = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { l += sh.red[w]; n += sh.cnt[w]; }
+    atomicAdd(&wc->loss_sum, l);
+    atomicAdd(&wc->batch_count, n);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.flag = atomicAdd(&wc->done_ctas, 1u);
+  __syncthreads();
+  const bool is_last_cta = (sh.flag == gridDim.x - 1);
+  __syncthreads();                           // sh.flag is reused below
+  if (!is_last_cta) return;
+
+  // ------------------------------------------------------------------ phase 3 (last CTA): push-and-apply
+  __threadfence();
+  const float round_loss = *reinterpret_cast<volatile float*>(&wc->loss_sum);
+  const unsigned int round_batch = *reinterpret_cast<volatile unsigned int*>(&wc->batch_count);
+
+  if (p.algo == ALGO_GRAD_ONLY) {
+    if (tid == 0) {
+      wc->last_loss = round_loss; wc->last_batch = round_batch;
+      wc->done_ctas = 0; wc->chunk_ctr = 0; wc->loss_sum = 0.f; wc->batch_count = 0;
+      wc->rounds_done += 1ULL;
+      __threadfence();
+      wc->round = round + 1u;
+    }
+    return;   // g_local is the output; the caller consumes and re-zeroes it
+  }
+
+  if (is_async) {
+    // K9 + K5/K6: staleness gate on the server's logical clock, then Hogwild reductions.
+    if (tid == 0) {
+      const unsigned long long ts = wc->ts;
+      unsigned long long old, k_old;
+      long long staleness;
+      int accept;
+      if (p.taw >= (1LL << 31)) {
+        // never stale: one NVLink round trip ticks clock and k together
+        old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, (1ULL << 32) | 1ULL);
+        k_old = old >> 32;
+        staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
+        accept = (static_cast<long long>(k_old) < p.max_iters) ? 1 : 0;
+      } else {
+        old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL);
+        staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
+        // ASGD compares the clock-based staleness (SparkASGDThread.scala:169); ASAGA compares
+        // k - ts (SparkASAGAThread.scala:184, quirk B.6) — both are available here.
+        long long cmp = staleness;
+        if (p.algo == ALGO_ASAGA) cmp = static_cast<long long>(old >> 32) - static_cast<long long>(ts);
+        accept = (cmp <= p.taw) ? 1 : 0;
+        k_old = old >> 32;
+        if (accept) {
+          unsigned long long o2 = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL << 32);
+          k_old = o2 >> 32;
+          if (static_cast<long long>(k_old) >= p.max_iters) accept = 0;
+        }
+      }
+      float step;
+      if (p.algo == ALGO_ASGD) step = p.gamma * rsqrtf(static_cast<float>(k_old / static_cast<unsigned long long>(p.num_workers)) + 1.f);
+      else step = p.gamma;
+      sh.flag = static_cast<unsigned int>(accept);
+      sh.bcast[0] = step;
+      wc->last_staleness = staleness;
+      wc->last_k_after = static_cast<long long>(k_old) + (accept ? 1 : 0);
+      sh.bcast[1] = __uint_as_float(static_cast<unsigned int>(old & 0xffffffffULL));
+    }
+    __syncthreads();
+    const int accept = static_cast<int>(sh.flag);
+    const float step = sh.bcast[0];
+    if (accept) {
+      if (p.algo == ALGO_ASGD) {
+        const float a = -step * p.inv_par_recs;
+        for (int v = tid; v < nvec; v += kThreads) {
+          float4 g = __ldcg(reinterpret_cast<const float4*>(p.g_local + 4 * v));
+          red_add_sys_f32x4(p.w_server + 4 * v, make_float4(a * g.x, a * g.y, a * g.z, a * g.w));
+        }
+      } else {
+        // w <- w - gamma*(g/parRecs + abar)  (abar BEFORE its update);  abar <- abar + g/N
+        const float a = -step * p.inv_par_recs;
+        for (int v = tid; v < nvec; v += kThreads) {
+          float4 g = __ldcg(reinterpret_cast<const float4*>(p.g_local + 4 * v));
+          float4 ab = ld_relaxed_sys_f32x4(p.abar_server + 4 * v);
+          red_add_sys_f32x4(p.w_server + 4 * v, make_float4(a * g.x - step * ab.x, a * g.y - step * ab.y,
+                                                            a * g.z - step * ab.z, a * g.w - step * ab.w));
+          red_add_sys_f32x4(p.abar_server + 4 * v, make_float4(g.x * p.inv_n, g.y * p.inv_n, g.z * p.inv_n, g.w * p.inv_n));
+        }
+      }
+    }
+    for (int v = tid; v < nvec; v += kThreads)
+      *reinterpret_cast<float4*>(p.g_local + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_sys();                               // reductions performed before the completion is published
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned long long now = globaltimer_ns();
+      const unsigned long long task_ns = now - wc->t_start_ns;
+      const unsigned int clock_old = __float_as_uint(sh.bcast[1]);
+      // result ring (backs AsyncContext.collect_all on the fused backend)
+      ResultRec* rec = p.ring + (clock_old % static_cast<unsigned int>(p.ring_size));
+      rec->worker = p.worker_id; rec->accepted = accept;
+      rec->ts = static_cast<long long>(wc->ts); rec->staleness = wc->last_staleness;
+      rec->k_after = wc->last_k_after; rec->batch = round_batch;
+      rec->loss_sum = round_loss; rec->step = accept ? step : 0.f;
+      rec->t_start_ns = wc->t_start_ns; rec->t_end_ns = now;
+      fence_sys();
+      *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(clock_old) + 1ULL;
+      // worker status (device mirror of workerState) + delay-injector calibration (A18)
+      WorkerSlot* me = p.status + p.worker_id;
+      me->staleness = wc->last_staleness;
+      me->num_tasks += 1;
+      me->last_task_ms = static_cast<float>(task_ns) * 1e-6f;
+      me->avg_task_ms += (me->last_task_ms - me->avg_task_ms) / static_cast<float>(me->num_tasks);
+      me->heartbeat_ns = now; me->last_finish_ns = now;
+      if (accept && wc->last_k_after <= static_cast<long long>(p.warmup_updates)) {
+        atomicAdd_system(&p.sctl->cul_time_ns, task_ns);
+        unsigned int c = atomicAdd_system(&p.sctl->cul_count, 1u) + 1u;
+        if (wc->last_k_after == static_cast<long long>(p.warmup_updates) && c > 0) {
+          unsigned long long tot = ld_acquire_sys_u64(&p.sctl->cul_time_ns);
+          atomicExch_system(&p.sctl->avg_delay_ns, tot / c);
+        }
+      }
+      me->available = 1;
+      fence_sys();
+      red_add_release_sys_s32(&p.sctl->avail_count, 1);
+      wc->last_accepted = accept; wc->last_batch = round_batch; wc->last_loss = round_loss;
+      wc->last_step = accept ? step : 0.f; wc->last_task_ns = task_ns;
+      wc->rounds_done += 1ULL;
+      wc->done_ctas = 0; wc->pull_ticket = 0; wc->chunk_ctr = 0; wc->loss_sum = 0.f; wc->batch_count = 0;
+      __threadfence();
+      wc->round = round + 1u;
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- BSP: all-gather over NVLink + replicated apply
+  {
+    const SyncPeers* pe = p.peers;
+    const int P = p.num_workers;
+    const int par = static_cast<int>(round & 1u);
+    const long long slot_stride = p.ld + 4;      // [ld] gradient + {loss, batch, pad, pad}
+    if (tid == 0 && static_cast<int>(round) < p.warmup_updates) {
+      // delay-injector calibration (sync drivers: first `warmup` iterations, SparkASGDSync.scala:157-193)
+      ServerCtl* sc = p.sctl;
+      sc->cul_time_ns += globaltimer_ns() - wc->t_start_ns;
+      sc->cul_count += 1u;
+      if (static_cast<int>(round) + 1 == p.warmup_updates) sc->avg_delay_ns = sc->cul_time_ns / sc->cul_count;
+    }
+    // 1. publish my gradient into slot[worker_id] of every peer's staging buffer (P2P stores)
+    for (int q = 0; q < P; ++q) {
+      float* dst = pe->gstage[q] + (static_cast<long long>(par) * P + p.worker_id) * slot_stride;
+      for (int v = tid; v < nvec; v += kThreads) {
+        float4 g = __ldcg(reinterpret_cast<const float4*>(p.g_local + 4 * v));
+        st_relaxed_sys_f32x4(dst + 4 * v, g);
+      }
+      if (tid == 0) st_relaxed_sys_f32x4(dst + p.ld, make_float4(round_loss, __uint_as_float(round_batch), 0.f, 0.f));
+    }
+    fence_sys();
+    __syncthreads();
+    if (tid < P) st_release_sys_u32(pe->flags[tid] + par * P + p.worker_id, round + 1u);
+    // 2. wait for every worker's slot of this round
+    if (tid < P) {
+      const unsigned int* f = pe->flags[p.worker_id] + par * P + tid;
+      while (ld_acquire_sys_u32(f) != round + 1u) __nanosleep(100);
+    }
+    __syncthreads();
+    // 3. fixed-order reduction => bit-identical replicas on every rank; then the update
+    const float* mine = pe->gstage[p.worker_id] + static_cast<long long>(par) * P * slot_stride;
+    float tot_loss = 0.f; unsigned int tot_batch = 0;
+    for (int q = 0; q < P; ++q) {
+      float4 m = ld_relaxed_sys_f32x4(mine + q * slot_stride + p.ld);
+      tot_loss += m.x; tot_batch += __float_as_uint(m.y);
+    }
+    float step = (p.algo == ALGO_SYNC_SGD) ? p.gamma * rsqrtf(static_cast<float>(round) + 1.f) : p.gamma;
+    for (int v = tid; v < nvec; v += kThreads) {
+      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < P; ++q) {
+        float4 g = ld_relaxed_sys_f32x4(mine + q * slot_stride + 4 * v);
+        G.x += g.x; G.y += g.y; G.z += g.z; G.w += g.w;
+      }
+      float4 w = *reinterpret_cast<float4*>(p.w_local + 4 * v);
+      const float a = step * p.inv_par_recs;
+      if (p.algo == ALGO_SYNC_SGD) {
+        w.x -= a * G.x; w.y -= a * G.y; w.z -= a * G.z; w.w -= a * G.w;
+      } else {
+        float4 ab = *reinterpret_cast<float4*>(p.abar_local + 4 * v);
+        w.x -= a * G.x + step * ab.x; w.y -= a * G.y + step * ab.y;
+        w.z -= a * G.z + step * ab.z; w.w -= a * G.w + step * ab.w;
+        ab.x += G.x * p.inv_n; ab.y += G.y * p.inv_n; ab.z += G.z * p.inv_n; ab.w += G.w * p.inv_n;
+        *reinterpret_cast<float4*>(p.abar_local + 4 * v) = ab;
+      }
+      *reinterpret_cast<float4*>(p.w_local + 4 * v) = w;
+      if (p.worker_id == 0 && p.w_server != p.w_local) *reinterpret_cast<float4*>(p.w_server + 4 * v) = w;
+      *reinterpret_cast<float4*>(p.g_local + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned long long now = globaltimer_ns();
+      wc->last_accepted = 1; wc->last_batch = tot_batch; wc->last_loss = tot_loss; wc->last_step = step;
+      wc->last_staleness = 0; wc->last_k_after = static_cast<long long>(round) + 1;
+      wc->last_task_ns = now - wc->t_start_ns;
+      wc->rounds_done += 1ULL;
+      wc->done_ctas = 0; wc->pull_ticket = 0; wc->chunk_ctr = 0; wc->loss_sum = 0.f; wc->batch_count = 0;
+      __threadfence();
+      wc->round = round + 1u;
+    }
+  }
+}
+
+}  // namespace afb

@@ -1,0 +1,239 @@
+// Fused dense round kernel (sm_100a):  pull(w) -> sample -> x·w -> loss coeff -> g += c·x
+//                                      -> (SAGA history) -> block/grid reduce -> push-and-apply.
+//
+// One launch = one round of one worker.  Hot-op inventory covered: K1 (dot),
+// K2 (residual/loss), K3 (gradient accumulate), K4 (SAGA correction), K5/K6 (SGD/SAGA apply),
+// K7 (history write), K9 (gradient push, in-kernel NVLink reductions into rank-0 HBM),
+// K10 (parameter pull, P2P load by one elected CTA overlapped with the other CTAs' first row
+// fetches), K11 (Bernoulli sampling, evaluated on the fly per row: no index list, no extra pass).
+//
+// Every sampled row is read from HBM exactly once (the reference materialises a dense d-vector
+// per sample).  A warp owns a row: lane l holds columns {4(l+32c)..+3}; dot via
+// shuffle tree, axpy into per-lane register accumulators; rows are double-buffered in registers
+// so two row fetches (2 x ld*4 B) are in flight per warp.  Work distribution is dynamic (64-row
+// chunks from a global counter, next chunk requested one ahead) so binomial sampling noise does
+// not create a tail.  The last CTA to finish (ticket) performs the cross-GPU part: logical-clock
+// atomics, staleness gate, Hogwild `red.add` of the scaled gradient straight into the server's w
+// (and alpha-bar for SAGA), result-ring record, worker-status update.
+#include "afb_round_impl.cuh"
+
+namespace afb {
+
+constexpr int kChunkRows = 64;
+
+template <int NV4>
+struct RowRegs {
+  float4 v[NV4];
+  float y;
+  float h;
+};
+
+template <int NV4>
+AFB_DEVINL void load_row(RowRegs<NV4>& r, const RoundParams& p, int row, int lane, int nvec, bool saga) {
+  const float* xr = p.X + static_cast<long long>(row) * p.ld;
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    int v = lane + 32 * c;
+    r.v[c] = (v < nvec) ? ld_stream_f32x4(xr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  r.y = __ldg(p.y + row);
+  r.h = saga ? p.hist[row] : 0.f;
+}
+
+// Warp-level scheduler state: yields the next selected local row, fetching 64-row chunks from the
+// worker's global counter (the next chunk id is requested before the current one is consumed).
+struct RowScheduler {
+  unsigned int m0, m1;      // selection masks of the current chunk (rows base+lane, base+32+lane)
+  int base;                 // first row of the current chunk
+  unsigned int next_chunk;  // prefetched chunk id
+};
+
+AFB_DEVINL unsigned int fetch_chunk(unsigned int* ctr, int lane) {
+  unsigned int c = 0;
+  if (lane == 0) c = atomicAdd(ctr, 1u);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
+
+AFB_DEVINL void load_chunk_masks(RowScheduler& s, const RoundParams& p, unsigned int chunk, int lane,
+                                 unsigned long long key) {
+  s.base = static_cast<int>(chunk) * kChunkRows;
+  int r0 = s.base + lane, r1 = s.base + 32 + lane;
+  bool s0 = false, s1 = false;
+  if (r0 < p.n_rows) {
+    unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r0]) : static_cast<unsigned long long>(p.row_base + r0);
+    s0 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
+  }
+  if (r1 < p.n_rows) {
+    unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r1]) : static_cast<unsigned long long>(p.row_base + r1);
+    s1 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
+  }
+  s.m0 = __ballot_sync(0xffffffffu, s0);
+  s.m1 = __ballot_sync(0xffffffffu, s1);
+}
+
+AFB_DEVINL int next_row(RowScheduler& s, const RoundParams& p, unsigned int* ctr, int lane,
+                        unsigned long long key, int num_chunks) {
+  while (true) {
+    if (s.m0) { int b = __ffs(s.m0) - 1; s.m0 &= s.m0 - 1; return s.base + b; }
+    if (s.m1) { int b = __ffs(s.m1) - 1; s.m1 &= s.m1 - 1; return s.base + 32 + b; }
+    unsigned int c = s.next_chunk;
+    if (c >= static_cast<unsigned int>(num_chunks)) return -1;
+    s.next_chunk = fetch_chunk(ctr, lane);     // request one ahead
+    load_chunk_masks(s, p, c, lane, key);
+  }
+}
+
+template <int NV4, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) dense_round_kernel(const RoundParams p) {
+  __shared__ RoundShared<kThreads> sh;
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_g = s_dyn;                            // [ld] CTA-level gradient accumulator
+  float* s_w = s_dyn + p.ld;                     // [ld] the pulled parameter vector (read per row via LDS.128)
+  const bool SAGA = (p.hist != nullptr);
+  const int LOSS = p.loss_id;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  const unsigned int round = wc->round;           // written by the previous round's last CTA
+
+  // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
+  if (p.algo != ALGO_GRAD_ONLY) {
+    if (!round_begin<kThreads>(p, sh, round)) return;
+  }
+
+  // ------------------------------------------------------------------ phase 1: fused gradient
+  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY) ? mix64(static_cast<unsigned long long>(p.seed))
+                                                             : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  for (int i = tid; i < p.ld; i += kThreads) { s_g[i] = 0.f; s_w[i] = p.w_local[i]; }
+  __syncthreads();
+  float4 acc[NV4];
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float loss_acc = 0.f;
+  unsigned int cnt = 0;
+
+  const int num_chunks = (p.n_rows + kChunkRows - 1) / kChunkRows;
+  RowScheduler sch;
+  sch.m0 = sch.m1 = 0; sch.base = 0;
+  sch.next_chunk = fetch_chunk(&wc->chunk_ctr, lane);
+
+  RowRegs<NV4> cur, nxt;
+  int rc = next_row(sch, p, &wc->chunk_ctr, lane, key, num_chunks);
+  if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+  while (rc >= 0) {
+    int rn = next_row(sch, p, &wc->chunk_ctr, lane, key, num_chunks);
+    if (rn >= 0) load_row<NV4>(nxt, p, rn, lane, nvec, SAGA);   // prefetch: second row in flight
+    // K1: dot
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NV4; ++c) {
+      int v = lane + 32 * c;
+      if (v < nvec) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_w + 4 * v);
+        d0 = fmaf(cur.v[c].x, wv.x, d0);
+        d1 = fmaf(cur.v[c].y, wv.y, d1);
+        d2 = fmaf(cur.v[c].z, wv.z, d2);
+        d3 = fmaf(cur.v[c].w, wv.w, d3);
+      }
+    }
+    float margin = warp_sum((d0 + d1) + (d2 + d3));
+    // K2 (+K4): coefficient
+    float coeff, loss;
+    loss_coeff_rt(LOSS, margin, cur.y, coeff, loss);
+    float eff = coeff;
+    if (SAGA) {
+      eff = coeff - cur.h;
+      if (lane == 0) {                       // K7: history write (row is owned by this worker)
+        if (p.hist_prev) { p.hist_prev[rc] = cur.h; p.hist_tag[rc] = static_cast<int>(round); }
+        p.hist[rc] = coeff;
+      }
+    }
+    // K3: axpy into register accumulators
+#pragma unroll
+    for (int c = 0; c < NV4; ++c) {
+      acc[c].x = fmaf(eff, cur.v[c].x, acc[c].x);
+      acc[c].y = fmaf(eff, cur.v[c].y, acc[c].y);
+      acc[c].z = fmaf(eff, cur.v[c].z, acc[c].z);
+      acc[c].w = fmaf(eff, cur.v[c].w, acc[c].w);
+    }
+    loss_acc += loss;
+    ++cnt;
+    cur = nxt;
+    rc = rn;
+  }
+
+  // ------------------------------------------------------------------ phase 2: CTA reduce -> g_local
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    int v = lane + 32 * c;
+    if (v < nvec) {
+      atomicAdd(&s_g[4 * v + 0], acc[c].x);
+      atomicAdd(&s_g[4 * v + 1], acc[c].y);
+      atomicAdd(&s_g[4 * v + 2], acc[c].z);
+      atomicAdd(&s_g[4 * v + 3], acc[c].w);
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < nvec; v += kThreads) {
+    float4 gv = *reinterpret_cast<float4*>(&s_g[4 * v]);
+    red_add_gpu_f32x4(p.g_local + 4 * v, gv);
+  }
+  round_finish<kThreads>(p, sh, round, loss_acc, cnt);
+}
+
+// SAGA rollback (finite taw only): undo the history writes of a rejected round.
+__global__ void saga_rollback_kernel(float* hist, const float* hist_prev, const int* hist_tag, int n_rows,
+                                     const WorkerCtl* wc) {
+  if (wc->last_accepted != 0) return;
+  const int tag = static_cast<int>(wc->round) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x)
+    if (hist_tag[i] == tag) hist[i] = hist_prev[i];
+}
+
+template <int NV4, int kThreads>
+static cudaError_t launch_nv(const RoundParams& p, int grid, cudaStream_t stream) {
+  size_t smem = 2 * static_cast<size_t>(p.ld) * sizeof(float);
+  auto k = dense_round_kernel<NV4, kThreads>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  k<<<grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace afb
+
+extern "C" {
+
+// Max row width handled with register accumulators: NV4 <= 16  =>  ld <= 2048 floats.
+int afb_dense_round_max_ld() { return 2048; }
+
+int afb_dense_round_launch(const afb::RoundParams* params, int grid, void* stream) {
+  using namespace afb;
+  const RoundParams& p = *params;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.ld % 4 != 0 || p.ld > 2048 || p.ld <= 0) return static_cast<int>(cudaErrorInvalidValue);
+  int nv4 = static_cast<int>((p.ld / 4 + 31) / 32);
+  cudaError_t e;
+  // <= 8 float4 per lane: 512 threads (128 regs); wider rows: 256 threads (255 regs) so the
+  // accumulators + two in-flight rows stay in registers.
+  switch (nv4) {
+    case 1: e = launch_nv<1, 512>(p, grid, s); break;
+    case 2: e = launch_nv<2, 512>(p, grid, s); break;
+    case 3: case 4: e = launch_nv<4, 512>(p, grid, s); break;
+    case 5: case 6: case 7: e = launch_nv<7, 512>(p, grid, s); break;
+    case 8: e = launch_nv<8, 512>(p, grid, s); break;
+    case 9: case 10: case 11: case 12: e = launch_nv<12, 256>(p, grid, s); break;
+    default: e = launch_nv<16, 256>(p, grid, s); break;
+  }
+  return static_cast<int>(e);
+}
+
+int afb_saga_rollback_launch(float* hist, const float* hist_prev, const int* hist_tag, int n_rows,
+                             const afb::WorkerCtl* wc, void* stream) {
+  afb::saga_rollback_kernel<<<296, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, hist_prev, hist_tag, n_rows, wc);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"
