@@ -1,0 +1,100 @@
+"""Shared driver plumbing: data loading, gradient closure, CLI entry, result printing."""
+from __future__ import annotations
+
+import logging
+import math
+import sys
+import time
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from ..config import AsyncConfig, parse_cli
+from ..core.context import AsyncContext
+from ..core.scheduler import Scheduler
+from ..data.batch import Shard
+from ..data.dataset import ShardedDataset
+from ..data.generators import (LinearDataGenerator, LogisticRegressionDataGenerator, SHAPES, synthetic_dataset)
+from ..data.libsvm import load_libsvm_file
+from ..optim.gradient import Gradient, make_gradient
+
+log = logging.getLogger("asyncframework_b200.algo")
+
+
+def now_ms() -> float:
+    return time.perf_counter() * 1e3
+
+
+def resolve_device(cfg: AsyncConfig) -> torch.device:
+    if cfg.backend in ("cpu",):
+        return torch.device("cpu")
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def compute_dtype(cfg: AsyncConfig, device: torch.device) -> torch.dtype:
+    if device.type == "cuda":
+        return torch.float32
+    return torch.float64 if cfg.dtype in ("float64", "auto", "float32") and cfg.extra.get("cpu_dtype", "float64") == "float64" else torch.float32
+
+
+def load_points(cfg: AsyncConfig, scheduler: Scheduler, device: torch.device, dtype: torch.dtype) -> ShardedDataset:
+    """``MLUtils.loadLibSVMFile(sc, path+file).repartition(numPart)`` (+ the optional unseeded 10 %
+    subsample that 4 of the 5 reference drivers apply at load, quirk B.9 -> ``load_subsample``)."""
+    P = cfg.num_partitions
+    if cfg.synthetic:
+        name = cfg.synthetic
+        rows = cfg.num_rows or None
+        if name == "linear":
+            ds = LinearDataGenerator.generate_linear_dataset(scheduler, rows or 1000, cfg.num_features or 20, 0.1, P,
+                                                             seed=cfg.seed, dtype=dtype, device=device)
+        elif name == "logistic":
+            ds = LogisticRegressionDataGenerator.generate_logistic_dataset(scheduler, rows or 1000, cfg.num_features or 20, 1.0, P,
+                                                                           seed=cfg.seed, dtype=dtype, device=device)
+        elif name in SHAPES:
+            labels = "regression" if cfg.loss.startswith("least_squares") else "binary01"
+            ds = synthetic_dataset(scheduler, name, P, rows, cfg.seed, device, dtype, labels, cfg.num_features or None)
+        else:
+            raise ValueError(f"unknown synthetic dataset {name!r}")
+    else:
+        ds = load_libsvm_file(scheduler, cfg.data_path, cfg.num_features if cfg.num_features > 0 else -1, P,
+                              dtype=dtype, layout=cfg.layout, density_threshold=cfg.density_threshold)
+        if ds.num_features != cfg.num_features and cfg.num_features > 0:
+            raise ValueError(f"num_features mismatch: file has {ds.num_features}, CLI says {cfg.num_features}")
+        ds = ds.repartition(P)
+        if device.type != "cpu":
+            ds = ShardedDataset.from_shards(scheduler, [s.to(device) for s in ds.shards()], ds.name)
+    if cfg.load_subsample:
+        ds = ds.sample(False, cfg.load_subsample, None)
+        ds = ShardedDataset.from_shards(scheduler, [s for s in ds.shards()], "subsampled")
+    return ds
+
+
+def make_scheduler(cfg: AsyncConfig, device: torch.device) -> Scheduler:
+    return Scheduler(num_executors=cfg.num_partitions, device=device if device.type == "cuda" else None,
+                     block_first_async_job=bool(cfg.extra.get("block_first_async_job", True)))
+
+
+def partition_gradient(gradient: Gradient, shard: Shard, w: torch.Tensor, history: Optional[torch.Tensor] = None):
+    """(g[d], loss_sum, n, coeff or None) for one (already sampled) shard — torch oracle path on CPU
+    tensors, fused CUDA kernel on HBM-resident shards."""
+    if shard.device.type == "cuda" and history is None:
+        from ..ops.grad import grad
+        g, l, n = grad(shard, w, gradient.loss_id)
+        return g, l, n, None
+    g, l, n, coeff = gradient.batch(shard, w, history)
+    return g, float(l), n, coeff
+
+
+def run_cli(algorithm: str, main_fn: Callable[[AsyncConfig], object], argv: Optional[List[str]] = None):
+    logging.basicConfig(level=logging.WARNING, format="%(levelname)s %(name)s: %(message)s")
+    cfg = parse_cli(algorithm, sys.argv[1:] if argv is None else argv)
+    layout = [(f, getattr(cfg, f)) for f in ("path", "file", "num_features", "num_rows", "num_partitions", "num_iterations",
+                                             "step_size", "taw", "batch_rate", "bucket_ratio", "printer_freq", "coeff", "seed")]
+    for k, v in layout:                       # the reference echoes its parameters
+        print(f"{k}: {v}")
+    report = main_fn(cfg)
+    if report is not None and hasattr(report, "print_reference_style"):
+        report.print_reference_style()
+    return report

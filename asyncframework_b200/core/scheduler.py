@@ -151,8 +151,8 @@ class Scheduler:
 
     def _run_task(self, task: _Task, eid: int, stream) -> None:
         job: JobWaiter = task.job
-        if job.failure is not None:
-            return
+        # NB: a failed sibling task does not cancel this one — in async mode every worker's result is
+        # independent (the reference silently ignores failed async jobs).
         tctx = TaskContext(job.job_id, task.partition, task.attempt, eid, self.device, stream, task.submit_ms)
         self.listeners.post({"event": "task_start", "job": job.job_id, "partition": task.partition,
                              "attempt": task.attempt, "executor": eid, "t_ms": time.perf_counter() * 1e3})

@@ -1,0 +1,37 @@
+"""Objective evaluation (K12) on HBM-resident shards: Σ_i loss(x_i·w_t, y_i) for T snapshots in one
+pass.  Dense shards with enough snapshots go to the tcgen05 GEMM kernel (eval_tc.cu) when it is
+enabled; everything else runs the exact-fp32 CUDA-core kernels (eval.cu)."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from ..data.batch import Shard
+from . import check, current_stream_ptr, kernels
+
+
+def eval_loss(shard: Shard, W: torch.Tensor, loss_id: int, use_tensor_cores=None) -> torch.Tensor:
+    """``W``: [d, T] snapshots.  Returns float64[T] loss sums over the shard's rows."""
+    lib = kernels()
+    d, T = W.shape
+    ld = shard.ld if shard.is_dense else (shard.num_features + 3) // 4 * 4
+    Wt = torch.zeros(T, ld, dtype=torch.float32, device=shard.device)
+    Wt[:, :d] = W.t().to(torch.float32)
+    out = torch.zeros(T, dtype=torch.float64, device=shard.device)
+    if shard.is_dense:
+        if use_tensor_cores is None:
+            use_tensor_cores = os.environ.get("AFB_EVAL_TC", "0") == "1"
+        if use_tensor_cores and hasattr(lib, "afb_eval_mse_tc") and loss_id in (0, 3):
+            check(lib.afb_eval_mse_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,
+                                      out.data_ptr(), current_stream_ptr()), "eval_mse_tc")
+            if loss_id == 3:
+                out *= 0.5
+            return out
+        check(lib.afb_eval_mse_dense(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,
+                                     loss_id, out.data_ptr(), current_stream_ptr()), "eval_mse_dense")
+    else:
+        check(lib.afb_eval_mse_csr(shard.indptr.data_ptr(), shard.indices.data_ptr(), shard.values.data_ptr(),
+                                   shard.y.data_ptr(), shard.num_rows, ld, Wt.data_ptr(), T, loss_id, out.data_ptr(),
+                                   current_stream_ptr()), "eval_mse_csr")
+    return out

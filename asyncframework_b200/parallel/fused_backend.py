@@ -31,6 +31,24 @@ from ..ops.round import NEVER_STALE, RoundKernel, ServerBlock, ServerLayout, Ser
 from ..optim.gradient import LOSS_IDS
 from .comm import SymmetricBuffer, allocate_symmetric
 
+_CUDART = None
+
+
+def _cudart():
+    global _CUDART
+    if _CUDART is None:
+        import ctypes as C
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _CUDART = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _CUDART is None:
+            raise RuntimeError("libcudart not found")
+    return _CUDART
+
+
 ALGO_NAMES = {"asgd": "asgd", "asaga": "asaga", "sgd_sync": "sgd_sync", "saga_sync": "saga_sync"}
 
 
@@ -178,12 +196,8 @@ class FusedEngine:
         """Current model: rank 0's server ``w`` (peers read it through the symmetric mapping)."""
         self.synchronize()
         if self.is_async and self.rank != 0 and self.world > 1:
-            out = torch.empty(self.layout.ld, dtype=torch.float32, device=self.device)
-            src = self.symm.ptrs[0] + self.layout.off_w
-            import ctypes as C
-            rt = C.CDLL("libcudart.so.12")
-            rt.cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(src), C.c_size_t(self.layout.ld * 4), 3)
-            return out[: self.d]
+            host = self._peer_read(self.symm.ptrs[0] + self.layout.off_w, self.layout.ld * 4).view(np.float32)
+            return torch.from_numpy(host.copy()).to(self.device)[: self.d]
         return self.block.w[: self.d].clone()
 
     def alpha_bar(self) -> torch.Tensor:
@@ -193,6 +207,27 @@ class FusedEngine:
     def state(self) -> Dict[str, int]:
         self.synchronize()
         return self.block.read_sctl()
+
+    def _peer_read(self, addr: int, nbytes: int) -> np.ndarray:
+        """Blocking copy of ``nbytes`` from a (possibly peer-mapped) device address to the host."""
+        import ctypes as C
+        rt = _cudart()
+        host = np.empty(nbytes, dtype=np.uint8)
+        rc = rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(addr), C.c_size_t(nbytes), 2)
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpy(D2H, peer) failed: {rc}")
+        return host
+
+    def server_state(self) -> Dict[str, int]:
+        """Clock / accepted-update counter of the parameter server (rank 0), readable from any rank."""
+        self.synchronize()
+        if self.rank == 0 or self.world == 1 or not self.is_async:
+            return self.block.read_sctl()
+        from ..ops._signatures import SERVER_CTL_DTYPE
+        a = self._peer_read(self.symm.ptrs[0] + self.layout.off_sctl, SERVER_CTL_DTYPE.itemsize).view(SERVER_CTL_DTYPE)[0]
+        ck = int(a["clock_k"])
+        return {"clock": ck & 0xFFFFFFFF, "k": ck >> 32, "avail_count": int(a["avail_count"]), "stop": int(a["stop"]),
+                "avg_delay_ns": int(a["avg_delay_ns"]), "cul_count": int(a["cul_count"])}
 
     def worker_status(self) -> np.ndarray:
         return self.block.read_status()

@@ -1,0 +1,230 @@
+"""RDD-slice semantics + the ASYNC runtime (context / barrier / async actions / scheduler modes),
+driven deterministically like DAGSchedulerSuite drives completions by hand."""
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from asyncframework_b200.core import AsyncBroadcast, AsyncContext, Scheduler, barriers
+from asyncframework_b200.core.sampler import bernoulli_mask, mix64_int, threshold24
+from asyncframework_b200.data import LinearDataGenerator, ShardedDataset
+
+
+def test_sampler_is_deterministic_and_unbiased():
+    idx = np.arange(200000)
+    m1 = bernoulli_mask(43, idx, 0.1)
+    assert np.array_equal(m1, bernoulli_mask(43, idx, 0.1))
+    assert abs(m1.mean() - 0.1) < 0.003
+    assert abs((m1 & bernoulli_mask(44, idx, 0.1)).mean() - 0.01) < 0.002      # independent across seeds
+    assert bernoulli_mask(1, idx, 1.0).all() and not bernoulli_mask(1, idx, 0.0).any()
+    assert threshold24(0.5) == 1 << 23 and mix64_int(0) == 0
+
+
+def test_parallelize_map_reduce_aggregate(scheduler):
+    ds = ShardedDataset.from_records(scheduler, list(range(100)), 7)
+    assert ds.count() == 100 and ds.map(lambda x: x * 2).reduce(lambda a, b: a + b) == 9900
+    assert ds.filter(lambda x: x % 2 == 0).count() == 50
+    assert ds.aggregate(lambda: 0, lambda a, x: a + x, lambda a, b: a + b) == 4950
+    assert ds.tree_aggregate(lambda: 0, lambda a, x: a + x, lambda a, b: a + b, depth=2) == 4950
+    assert sorted(ds.collect()) == list(range(100)) and ds.first() == 0 and len(ds.take(5)) == 5
+    assert sum(len(g) for g in ds.glom().collect()) == 100
+
+
+def test_repartition_zip_with_index_sample(scheduler):
+    X, y, _ = LinearDataGenerator.generate_linear_arrays(1003, 5, seed=1)
+    ds = ShardedDataset.from_arrays(scheduler, X, y, 3).repartition(4)
+    sizes = ds.partition_sizes()
+    assert sum(sizes) == 1003 and max(sizes) - min(sizes) <= 1           # round-robin balance
+    zi = ds.zip_with_index()
+    g = torch.cat([s.gidx for s in zi.shards()])
+    assert sorted(g.tolist()) == list(range(1003))
+    assert zi.batch(1).gidx[0].item() == sizes[0]                          # offset = Σ previous sizes
+    s1 = zi.sample(False, 0.3, 7)
+    s2 = zi.sample(False, 0.3, 7)
+    assert s1.partition_sizes() == s2.partition_sizes()
+    n = s1.count()
+    assert abs(n - 300) < 60
+    # record-level and batch-level sampling select the same rows
+    rec_idx = sorted(i for _, i in s1.map(lambda r: r).collect())
+    bat_idx = sorted(torch.cat([s.gidx for s in s1.shards()]).tolist())
+    assert rec_idx == bat_idx
+    with pytest.raises(NotImplementedError):
+        zi.sample(True, 0.5, 1)
+
+
+def test_cache_materialises_once(scheduler):
+    calls = {"n": 0}
+    base = ShardedDataset.from_records(scheduler, list(range(20)), 2)
+
+    def f(x):
+        calls["n"] += 1
+        return x + 1
+    ds = base.map(f).cache()
+    assert ds.count() == 20 and ds.count() == 20
+    assert calls["n"] == 20
+
+
+def test_async_context_queue_clock_stat():
+    ctx = AsyncContext(4)
+    assert ctx.size() == 0 and not ctx.has_next() and ctx.collect(timeout=0.01) is None
+    from asyncframework_b200.core import PartialResult
+    ctx.put(PartialResult("a", 1, 5, 10, 2))
+    ctx.put(PartialResult("b", 0, 6, 11, 3))
+    assert ctx.size() == 2 and ctx.has_next()
+    assert ctx.collect() == "a"
+    env = ctx.collect_all()
+    assert (env.data, env.staleness, env.timestamp, env.batch_size, env.worker_id) == ("b", 0, 6, 11, 3)
+    assert ctx.add_to_current_time(1) == 0 and ctx.current_time == 1
+    assert ctx.stat.get(0) is None and len(ctx.stat) == 0
+    ctx.stat.task_done(1, 3, 10.0)
+    ctx.stat.task_done(1, 5, 20.0)
+    st = ctx.stat[1]
+    assert st.staleness == 5 and st.num_tasks == 2 and st.avg_task_time_ms == pytest.approx(15.0) and st.available
+    ctx.stat.set_available(2, False)
+    assert st.available_workers() == 1 and st.max_staleness() == 5
+    # blocking take wakes up when another thread puts
+    t = threading.Timer(0.05, lambda: ctx.put(PartialResult("late", 0, 0, 0, 0)))
+    t.start()
+    assert ctx.collect(timeout=2.0) == "late"
+
+
+def test_async_broadcast_versions():
+    ctx = AsyncContext(2)
+    w = torch.zeros(3)
+    a0 = AsyncBroadcast(ctx, w, slots=2)
+    w += 1
+    a1 = AsyncBroadcast(ctx, w, slots=2)
+    assert a0.value.tolist() == [0, 0, 0] and a1.value.tolist() == [1, 1, 1]      # snapshot at broadcast time
+    assert a1.value_at(a0.index).tolist() == [0, 0, 0] and a1(a0.index).tolist() == [0, 0, 0]
+    w += 1
+    a2 = AsyncBroadcast(ctx, w, slots=2)
+    with pytest.raises(KeyError):
+        a2.value_at(a0.index)                                                    # ring of 2 evicted version 0
+    a2.set_id(a1.index)
+    assert a2.value.tolist() == [1, 1, 1] and a2.get_index() == a1.index
+
+
+def test_barrier_predicates_and_selection(scheduler):
+    ds = ShardedDataset.from_records(scheduler, list(range(8)), 4)
+    ctx = AsyncContext(4, scheduler)
+    # no entries yet -> every partition is selected (RDD.scala:1053-1064)
+    assert ds.async_barrier(barriers.bsp(4), ctx.stat).selected_workers == [0, 1, 2, 3]
+    for p in range(4):
+        ctx.stat.task_done(p, p, 1.0)
+    ctx.stat.set_available(3, False)
+    assert ds.async_barrier(barriers.asp(), ctx.stat).selected_workers == [0, 1, 2]
+    assert ds.async_barrier(barriers.bucket(4, 0.75), ctx.stat).selected_workers == [0, 1, 2]
+    assert ds.async_barrier(barriers.bsp(4), ctx.stat).selected_workers == []
+    assert ds.async_barrier(barriers.ssp(2), ctx.stat).selected_workers == []      # max staleness is 3
+    assert ds.async_barrier(lambda st: st.staleness <= 1, ctx.stat).selected_workers == [0, 1]
+    sel = ds.async_barrier(barriers.asp(), ctx.stat)
+    assert sorted(sel.collect()) == [0, 1, 2, 3, 4, 5]                              # partition 3 is empty
+
+
+def test_first_async_job_blocks_like_the_reference(scheduler):
+    """DAGScheduler.first_iter quirk (Appendix B.4): the first async job waits for all tasks."""
+    ds = ShardedDataset.from_records(scheduler, [1, 2, 3, 4], 2)
+    ctx = AsyncContext(2, scheduler)
+    ds.async_reduce(lambda a, b: a + b, ctx)
+    assert ctx.size() == 2 and scheduler.first_iter == 0              # both results already there
+    out = ds.async_reduce(lambda a, b: a + b, ctx)                      # later jobs return a waiter immediately
+    out.wait(5)
+    assert ctx.size() == 4
+
+
+def test_async_reduce_scripted_completions():
+    """Release tasks by hand and check staleness / clock / availability bookkeeping."""
+    scheduler = Scheduler(3, block_first_async_job=False)
+    P = 3
+    ds = ShardedDataset.from_records(scheduler, [1, 2, 3, 4, 5, 6], P)
+    ctx = AsyncContext(P, scheduler)
+    ctx.set_record_stat(True)
+    gates = {p: threading.Event() for p in range(P)}
+
+    def gated(p, it):
+        gates[p].wait(5)
+        return it
+    job = ds.map_partitions_with_index(gated).async_reduce(lambda a, b: a + b, ctx)
+    # first async job blocks by default (quirk B.4) => run it in a thread
+    assert scheduler.mode == 1
+    for p in range(P):
+        assert not ctx.stat[p].available
+    for p in (2, 0, 1):
+        gates[p].set()
+        t0 = time.time()
+        while ctx.size() == 0 and time.time() - t0 < 5:
+            time.sleep(0.001)
+        env = ctx.collect_all(timeout=1)
+        assert env.worker_id == p and env.batch_size == 2 and env.data == [3, 7, 11][p]
+    assert ctx.current_time == 3
+    assert all(ctx.stat[p].available for p in range(P))
+    scheduler.stop()
+
+
+def test_async_reduce_nonblocking_and_staleness():
+    sched = Scheduler(2, block_first_async_job=False)
+    try:
+        ds = ShardedDataset.from_records(sched, [10, 20], 2)
+        ctx = AsyncContext(2, sched)
+        gates = [threading.Event(), threading.Event()]
+        t0 = time.time()
+        ds.map_partitions_with_index(lambda p, it: (gates[p].wait(5), it)[1]).async_reduce(lambda a, b: a + b, ctx)
+        assert time.time() - t0 < 1.0 and ctx.size() == 0              # returned before any task finished
+        gates[0].set()
+        r0 = ctx.collect_all(timeout=5)
+        assert r0.staleness == 0 and r0.timestamp == 0
+        gates[1].set()
+        r1 = ctx.collect_all(timeout=5)
+        assert r1.staleness == 1 and r1.timestamp == 0                  # one result merged since its submit
+        assert ctx.stat.max_staleness() == 1
+    finally:
+        sched.stop()
+
+
+def test_async_aggregate_and_empty_partitions(scheduler):
+    ds = ShardedDataset.from_records(scheduler, [1, 2, 3], 3).filter(lambda x: x != 2)
+    ctx = AsyncContext(3, scheduler)
+    ds.async_aggregate(lambda: [0, 0], lambda a, x: [a[0] + x, a[1] + 1], lambda a, b: [a[0] + b[0], a[1] + b[1]], ctx)
+    got = sorted((ctx.collect_all(timeout=2).data[0]) for _ in range(2))
+    assert got == [1, 3] and ctx.collect_all(timeout=0.05) is None
+    assert ctx.dropped_empty == 1 and ctx.stat[1].available             # empty partition freed, no queue entry
+
+
+def test_task_retry_and_failure_isolation():
+    sched = Scheduler(2, max_failures=3)
+    try:
+        ds = ShardedDataset.from_records(sched, list(range(10)), 2)
+        attempts = {"n": 0}
+
+        def inject(tctx):
+            if tctx.partition_id == 1 and tctx.attempt < 2:
+                attempts["n"] += 1
+                raise RuntimeError("injected")
+        sched.fault_injector = inject
+        assert ds.count() == 10 and attempts["n"] == 2                  # FailureSuite: retried then succeeded
+        sched.fault_injector = lambda t: (_ for _ in ()).throw(RuntimeError("always")) if t.partition_id == 0 else None
+        from asyncframework_b200.core import JobFailed
+        with pytest.raises(JobFailed):
+            ds.count()
+        # async job failure must not strand the worker (quirk B.15 fixed)
+        ctx = AsyncContext(2, sched)
+        sched.block_first_async_job = False
+        ds.async_reduce(lambda a, b: a + b, ctx)
+        r = ctx.collect_all(timeout=5)
+        assert r.worker_id == 1
+        t0 = time.time()
+        while not ctx.stat[0].available and time.time() - t0 < 5:
+            time.sleep(0.01)
+        assert ctx.stat[0].available
+    finally:
+        sched.stop()
+
+
+def test_listener_bus_events(scheduler):
+    events = []
+    scheduler.listeners.add(events.append)
+    ShardedDataset.from_records(scheduler, list(range(4)), 2).count()
+    kinds = [e["event"] for e in events]
+    assert kinds.count("job_start") == 1 and kinds.count("task_end") == 2 and kinds.count("job_end") == 1

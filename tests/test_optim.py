@@ -1,0 +1,146 @@
+"""Gradient / Updater / GradientDescent / GLM tests in the GradientDescentSuite style
+(mllib test GradientDescentSuite.scala:67-183, LinearRegressionSuite.scala:46-154)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from asyncframework_b200.data import LinearDataGenerator, LogisticRegressionDataGenerator, ShardedDataset, generate_gd_input
+from asyncframework_b200.data.batch import Shard
+from asyncframework_b200.linalg import Vectors
+from asyncframework_b200.models import (LassoWithSGD, LinearRegressionModel, LinearRegressionWithSGD, LogisticRegressionModel,
+                                        LogisticRegressionWithSGD, RidgeRegressionWithSGD, SVMWithSGD)
+from asyncframework_b200.models.glm import GeneralizedLinearModel
+from asyncframework_b200.optim import (AsyncLeastSquaresGradient, GradientDescent, HingeGradient, L1Updater,
+                                       LeastSquaresGradient, LogisticGradient, SimpleUpdater, SquaredL2Updater,
+                                       run_mini_batch_sgd)
+
+
+@pytest.mark.parametrize("grad", [LeastSquaresGradient(), AsyncLeastSquaresGradient(), LogisticGradient(), HingeGradient()])
+def test_gradients_match_autograd(grad):
+    torch.manual_seed(0)
+    X = torch.randn(50, 6, dtype=torch.float64)
+    y = (torch.rand(50) < 0.5).double()
+    w = torch.randn(6, dtype=torch.float64, requires_grad=True)
+    coeff, loss = grad.coefficients(X @ w, y)
+    loss.sum().backward()
+    manual = X.t() @ coeff.detach()
+    scale = 2.0 if isinstance(grad, AsyncLeastSquaresGradient) else 1.0      # its reported loss is diff² but coeff is diff
+    assert torch.allclose(w.grad, manual * scale, atol=1e-9)
+    # record-level API agrees with the batch API
+    shard = Shard(6, y, torch.cat([X, torch.zeros(50, 2, dtype=torch.float64)], 1))
+    g, l, n, _ = grad.batch(shard, w.detach())
+    cum = Vectors.zeros(6)
+    tot = sum(grad.compute(shard.row(i).features, float(y[i]), Vectors.dense(w.detach()), cum) for i in range(50))
+    assert torch.allclose(cum.values, g, atol=1e-9) and abs(tot - float(l)) < 1e-9 and n == 50
+
+
+def test_logistic_loss_is_stable_for_huge_margins():
+    g = LogisticGradient()
+    c, l = g.coefficients(torch.tensor([800.0, -800.0], dtype=torch.float64), torch.tensor([1.0, 0.0], dtype=torch.float64))
+    assert torch.isfinite(l).all() and l.abs().max() < 1e-9 and c.abs().max() < 1e-9
+
+
+def test_multinomial_logistic_gradient_matches_autograd():
+    K, d = 4, 3
+    torch.manual_seed(1)
+    x = torch.randn(d, dtype=torch.float64)
+    W = torch.randn((K - 1) * d, dtype=torch.float64, requires_grad=True)
+    for label in range(K):
+        g, loss = LogisticGradient(K).compute(Vectors.dense(x), float(label), Vectors.dense(W.detach()))
+        margins = torch.cat([torch.zeros(1, dtype=torch.float64), W.reshape(K - 1, d) @ x])
+        ref = -torch.log_softmax(margins, 0)[label]
+        (gr,) = torch.autograd.grad(ref, W)
+        assert abs(loss - float(ref)) < 1e-9 and torch.allclose(g.values, gr, atol=1e-9)
+
+
+def test_updaters_fork_schedules():
+    w, g = torch.tensor([1.0, -2.0], dtype=torch.float64), torch.tensor([0.5, 0.5], dtype=torch.float64)
+    nw, reg = SimpleUpdater().compute(w, g, 1.0, 4, 0.0)
+    assert torch.allclose(nw, w - 0.5 * g) and reg == 0.0                      # eta/sqrt(t) kept (Updater.scala:77)
+    nw, reg = SquaredL2Updater().compute(w, g, 0.1, 100, 0.5)
+    assert torch.allclose(nw, w * (1 - 0.05) - 0.1 * g)                         # CONSTANT step in the fork (:151-158)
+    assert reg == pytest.approx(0.25 * float((nw ** 2).sum()))
+    nw2, _ = SquaredL2Updater("sqrt").compute(w, g, 0.1, 100, 0.5)             # upstream behaviour available
+    assert torch.allclose(nw2, w * (1 - 0.005) - 0.01 * g)
+    nw, reg = L1Updater().compute(torch.tensor([0.3, -2.0], dtype=torch.float64), torch.zeros(2, dtype=torch.float64), 1.0, 9, 0.5)
+    assert nw.tolist() == [0.0, -1.5] and reg == pytest.approx(0.75)
+
+
+def test_gd_loss_decreases_and_first_iteration_loss_with_l2(scheduler):
+    pts = generate_gd_input(2.0, -1.5, 2000, 42)
+    X = np.array([[1.0, float(p.features[0])] for p in pts])
+    y = np.array([p.label for p in pts])
+    ds = ShardedDataset.from_arrays(scheduler, X, y, 2)
+    w0 = torch.zeros(2, dtype=torch.float64)
+    _, loss, _ = run_mini_batch_sgd(ds, LogisticGradient(), SimpleUpdater(), 1.0, 10, 0.0, 1.0, w0)
+    assert loss[0] > loss[-1] and all(b < a * 1.05 for a, b in zip(loss, loss[1:]))
+    # regularisation: loss[0] differs by regVal(initial weights), then both decrease
+    w1 = torch.tensor([-1.0, 1.0], dtype=torch.float64)
+    _, l0, _ = run_mini_batch_sgd(ds, LogisticGradient(), SquaredL2Updater(), 1.0, 1, 0.0, 1.0, w1)
+    _, l1, _ = run_mini_batch_sgd(ds, LogisticGradient(), SquaredL2Updater(), 1.0, 1, 1.0, 1.0, w1)
+    assert l1[0] - l0[0] == pytest.approx(0.5 * 1.0 * float((w1 ** 2).sum()), rel=1e-9)
+
+
+def test_gd_convergence_tolerance_stops_early(scheduler):
+    X, y, _ = LinearDataGenerator.generate_linear_arrays(500, 3, eps=0.01, seed=3)
+    ds = ShardedDataset.from_arrays(scheduler, X, y, 2)
+    w0 = torch.zeros(3, dtype=torch.float64)
+    _, loss_tight, _ = run_mini_batch_sgd(ds, LeastSquaresGradient(), SimpleUpdater(), 1.0, 500, 0.0, 1.0, w0, 0.0)
+    _, loss_loose, _ = run_mini_batch_sgd(ds, LeastSquaresGradient(), SimpleUpdater(), 1.0, 500, 0.0, 1.0, w0, 0.1)
+    assert len(loss_tight) == 500 and len(loss_loose) < 500
+
+
+def test_linear_regression_with_sgd_history_and_predict(scheduler, tmp_path):
+    ds = LinearDataGenerator.generate_linear_dataset(scheduler, 2000, 10, 0.05, 2, seed=7)
+    model = LinearRegressionWithSGD.train(ds, iterations=250, step=1.0, mini_batch_fraction=1.0, convergence_tol=0.0)
+    assert np.abs(model.weights.numpy() - ds.true_weights).max() < 0.05
+    assert len(model.weight_history) == 3 and LinearRegressionWithSGD.h is model.weight_history   # i = 1, 100, 200
+    assert all(isinstance(t, int) for t, _ in model.weight_history)
+    x = torch.ones(10, dtype=torch.float64)
+    assert model.predict(x) == pytest.approx(float(model.weights.sum()))
+    assert model.predict(Vectors.dense(x)) == pytest.approx(float(model.weights.sum()))
+    model.save(str(tmp_path / "m"))
+    back = GeneralizedLinearModel.load(str(tmp_path / "m"))
+    assert isinstance(back, LinearRegressionModel) and torch.allclose(back.weights, model.weights.double())
+    # intercept support (trailing 1.0 feature split off afterwards)
+    X, y, w = LinearDataGenerator.generate_linear_arrays(2000, 4, eps=0.01, seed=5, intercept=2.0)
+    dsi = ShardedDataset.from_arrays(scheduler, X, y, 2)
+    mi = LinearRegressionWithSGD.train(dsi, iterations=400, step=1.0, intercept=True, convergence_tol=0.0)
+    assert abs(mi.intercept - 2.0) < 0.1 and np.abs(mi.weights.numpy() - w).max() < 0.1
+
+
+def test_logistic_svm_ridge_lasso(scheduler, tmp_path):
+    ds = LogisticRegressionDataGenerator.generate_logistic_dataset(scheduler, 2000, 5, 1.5, 2, seed=9)
+    m = LogisticRegressionWithSGD.train(ds, iterations=100, step=1.0, reg_param=0.0, intercept=True)
+    X = torch.cat([s.X[:, :5] for s in ds.shards()])
+    y = torch.cat([s.y for s in ds.shards()])
+    acc = float((m.predict(X) == y).double().mean())
+    assert acc > 0.85
+    m.clear_threshold()
+    p = m.predict(X)
+    assert float(p.min()) >= 0.0 and float(p.max()) <= 1.0
+    m.set_threshold(0.5).save(str(tmp_path / "lr"))
+    assert isinstance(GeneralizedLinearModel.load(str(tmp_path / "lr")), LogisticRegressionModel)
+    svm = SVMWithSGD.train(ds, iterations=100, step=1.0, reg_param=0.01, intercept=True)
+    assert float((svm.predict(X) == y).double().mean()) > 0.85
+    bad = ShardedDataset.from_arrays(scheduler, np.random.randn(10, 2), np.arange(10.0), 2)
+    with pytest.raises(ValueError, match="validation"):
+        LogisticRegressionWithSGD.train(bad, iterations=2)
+    lin = LinearDataGenerator.generate_linear_dataset(scheduler, 500, 5, 0.05, 2, seed=1)
+    r = RidgeRegressionWithSGD(1.0, 100, 0.1).run(lin)
+    l = LassoWithSGD(1.0, 100, 0.1).run(lin)
+    plain = LinearRegressionWithSGD(1.0, 100).run(lin)
+    assert float(r.weights.norm()) < float(plain.weights.norm()) and float(l.weights.abs().sum()) < float(plain.weights.abs().sum())
+
+
+def test_feature_scaling_path(scheduler):
+    X, y, w = LinearDataGenerator.generate_linear_arrays(1500, 3, eps=0.01, seed=11)
+    X = X * np.array([1.0, 10.0, 0.1])
+    ds = ShardedDataset.from_arrays(scheduler, X, y, 2)
+    alg = LinearRegressionWithSGD(0.5, 600)
+    alg.optimizer.set_convergence_tol(0.0)
+    alg.set_feature_scaling(True)
+    m = alg.run(ds)
+    assert np.abs(m.weights.numpy() - w / np.array([1.0, 10.0, 0.1])).max() < 0.2
