@@ -4,7 +4,6 @@ the numerics tests.  Returns ``(g[d], loss_sum, sampled_rows)``.
 """
 from __future__ import annotations
 
-import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -12,25 +11,17 @@ import torch
 from ..data.batch import Shard
 from .round import RoundKernel, ServerLayout, ServerPointers
 
-_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
-
-
-class _Holder:
-    def __init__(self, rk: RoundKernel):
-        self.rk = rk
-
-
 def _kernel_for(shard: Shard, loss_id: int) -> RoundKernel:
-    key = shard.y   # tensors are weak-referenceable; the shard dataclass is not hashable
-    h = _cache.get(key)
-    if h is None or h.rk.params.loss_id != loss_id:
+    """One cached grad-only RoundKernel per shard (kept in ``shard.meta`` so it dies with the shard)."""
+    rk = shard.meta.get("_grad_kernel")
+    if rk is None:
         ld = shard.ld if shard.is_dense else (shard.num_features + 3) // 4 * 4
         layout = ServerLayout(ld, 1, ring_size=1)
         rk = RoundKernel(shard, ServerPointers(0, layout), algo="grad_only", loss_id=loss_id, num_workers=1,
                          worker_id=0, total_rows=max(shard.num_rows, 1), batch_rate=1.0, gamma=0.0, seed=0)
-        h = _Holder(rk)
-        _cache[key] = h
-    return h.rk
+        shard.meta["_grad_kernel"] = rk
+    rk.params.loss_id = int(loss_id)
+    return rk
 
 
 def grad(shard: Shard, w: torch.Tensor, loss_id: int, fraction: float = 1.0, seed: int = 0,
