@@ -112,7 +112,7 @@ def build_kernels(force: bool = False, verbose: bool = False, keep_ptx: bool = F
         odg.write_text(sdg)
     if log_lines:
         (ROOT / "build" / "ptxas.log").write_text("\n".join(log_lines))
-    _run([nvcc, "-shared", *NVCC_ARCH, "-o", str(out), *[str(o) for o in objs], "-lcuda"], verbose)
+    _run([nvcc, "-shared", *NVCC_ARCH, "-o", str(out), *[str(o) for o in objs]], verbose)
     stamp.write_text(dg)
     return out
 

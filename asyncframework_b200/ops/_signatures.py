@@ -38,8 +38,9 @@ WORKER_CTL_DTYPE = np.dtype([
     ("ts", "<u8"), ("k_read", "<u8"), ("seed_key", "<u8"), ("t_start_ns", "<u8"),
     ("last_accepted", "<i4"), ("last_batch", "<u4"), ("last_loss", "<f4"), ("last_step", "<f4"),
     ("last_staleness", "<i8"), ("last_k_after", "<i8"), ("last_task_ns", "<u8"), ("rounds_done", "<u8"),
+    ("wait_ns", "<u8"), ("last_finish_ns", "<u8"), ("avg_task_ms", "<f4"), ("pad_f", "<f4"), ("pad_u", "<u8"),
 ], align=False)
-assert WORKER_CTL_DTYPE.itemsize == 112
+assert WORKER_CTL_DTYPE.itemsize == 144
 
 SERVER_CTL_DTYPE = np.dtype({
     "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns"],
@@ -71,6 +72,7 @@ def declare(lib: C.CDLL) -> None:
     P = C.POINTER
     sig("afb_dense_round_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_dense_round_max_ld", C.c_int, [])
+    sig("afb_dense_round_ctas_per_sm", C.c_int, [i64])
     sig("afb_csr_round_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_saga_rollback_launch", C.c_int, [vp, vp, vp, C.c_int, vp, vp])
     sig("afb_axpy", C.c_int, [f32, vp, vp, i64, vp])
@@ -80,7 +82,7 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_sample_rows_v2", C.c_int, [vp, i64, i64, i64, C.c_int, vp, vp, vp, vp])
     sig("afb_eval_mse_dense", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, C.c_int, vp, vp])
     sig("afb_eval_mse_csr", C.c_int, [vp, vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, vp, vp])
-    sig("afb_eval_mse_tc", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, vp, vp])
+    sig("afb_eval_mse_tc", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, vp, vp, vp])
     sig("afb_abi_sizeof", C.c_int, [C.c_int])
     sig("afb_ipc_get_handle", C.c_int, [vp, vp])
     sig("afb_ipc_open_handle", C.c_int, [vp, P(vp)])

@@ -21,10 +21,11 @@ def eval_loss(shard: Shard, W: torch.Tensor, loss_id: int, use_tensor_cores=None
     out = torch.zeros(T, dtype=torch.float64, device=shard.device)
     if shard.is_dense:
         if use_tensor_cores is None:
-            use_tensor_cores = os.environ.get("AFB_EVAL_TC", "0") == "1"
+            use_tensor_cores = os.environ.get("AFB_EVAL_TC", "0") == "1" and T >= 8 and shard.num_rows >= 128
         if use_tensor_cores and hasattr(lib, "afb_eval_mse_tc") and loss_id in (0, 3):
+            scratch = torch.empty(64 * ld, dtype=torch.float32, device=shard.device)
             check(lib.afb_eval_mse_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,
-                                      out.data_ptr(), current_stream_ptr()), "eval_mse_tc")
+                                      out.data_ptr(), scratch.data_ptr(), current_stream_ptr()), "eval_mse_tc")
             if loss_id == 3:
                 out *= 0.5
             return out

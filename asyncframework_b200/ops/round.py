@@ -227,7 +227,10 @@ class RoundKernel:
         self.params = p
         props = torch.cuda.get_device_properties(dev)
         self.num_sms = props.multi_processor_count
-        self.grid = int(grid) if grid else (self.num_sms if self.is_dense else 2 * self.num_sms)
+        # resident-CTA capacity of the kernel on this device; `grid` (if given) is the share of it
+        # this logical worker should occupy when several workers co-run on one GPU
+        self.ctas_per_sm = self.lib.afb_dense_round_ctas_per_sm(ld) if self.is_dense else 2
+        self.grid = int(grid) if grid else self.ctas_per_sm * self.num_sms
         self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         self.launches = 0
 

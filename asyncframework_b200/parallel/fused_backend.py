@@ -121,8 +121,10 @@ class FusedEngine:
                 dmode = 1 if (cfg.coeff > 0 and wid == 0) else 0
             grid = None
             if n_local > 1:
-                per = max(1, sms // n_local)
-                grid = per if shard.is_dense else 2 * per
+                # co-resident logical workers split the resident-CTA capacity (2 CTAs/SM): with two
+                # workers per GPU each gets one CTA per SM, so one worker's NVLink latency phases
+                # overlap the other's HBM streaming
+                grid = max(1, (2 * sms) // n_local)
             rk = RoundKernel(shard, server, algo=algo, loss_id=LOSS_IDS[cfg.loss], num_workers=self.P,
                              worker_id=wid, total_rows=self.total_rows, batch_rate=cfg.batch_rate,
                              gamma=cfg.step_size, seed=cfg.seed,
@@ -155,6 +157,22 @@ class FusedEngine:
     def synchronize(self) -> None:
         for st in self.streams:
             st.synchronize()
+
+    def fork(self, event: torch.cuda.Event) -> None:
+        """Make every worker stream wait for ``event`` (recorded on the launching stream)."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            if st != cur:
+                st.wait_event(event)
+
+    def join(self) -> None:
+        """Make the launching stream wait for everything enqueued on the worker streams."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            if st != cur:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
 
     # ------------------------------------------------------------------ end-to-end step
     def step(self, step_size: Optional[float] = None) -> Dict[str, float]:

@@ -1,0 +1,79 @@
+"""Failure detection: heartbeat watchdog over the worker-status table.
+
+Spark: executors heartbeat every 10 s and are expired after ``spark.network.timeout``
+(core/HeartbeatReceiver.scala:75-87,123-134,193-220); ASYNC itself has no recovery — a lost worker
+stays ``available=false`` forever.  Here every worker stamps a heartbeat (host table:
+``StatTable.heartbeat``; fused backend: ``WorkerSlot.heartbeat_ns`` written by the round kernel) and
+this watchdog marks silent workers dead.  Async modes continue with P−1 workers (dead workers are
+excluded from ``available_workers`` and from barrier selection); sync modes abort.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from typing import Callable, List, Optional
+
+
+class HeartbeatWatchdog:
+    def __init__(self, stat, timeout_s: float = 30.0, period_s: float = 0.5,
+                 on_dead: Optional[Callable[[int], None]] = None, only_busy: bool = True):
+        self.stat = stat
+        self.timeout_ms = timeout_s * 1e3
+        self.period_s = period_s
+        self.on_dead = on_dead
+        self.only_busy = only_busy
+        self.dead: List[int] = []
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+
+    def check_once(self) -> List[int]:
+        newly = []
+        for p in list(self.stat):
+            ws = self.stat[p]
+            if not ws.alive:
+                continue
+            busy = not ws.available
+            if (busy or not self.only_busy) and ws.heartbeat_age_ms > self.timeout_ms:
+                self.stat.set_alive(p, False)
+                self.stat.set_available(p, False)
+                self.dead.append(p)
+                newly.append(p)
+                if self.on_dead:
+                    self.on_dead(p)
+        return newly
+
+    def _loop(self):
+        while not self._stop.wait(self.period_s):
+            self.check_once()
+
+    def start(self) -> "HeartbeatWatchdog":
+        self._thread = threading.Thread(target=self._loop, name="afb-watchdog", daemon=True)
+        self._thread.start()
+        return self
+
+    def stop(self) -> None:
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+
+
+class DeviceWatchdog:
+    """Same policy for the fused backend: polls the device-side status table of the server block
+    (heartbeat_ns is a globaltimer stamp; compared against the newest stamp seen)."""
+
+    def __init__(self, engine, timeout_s: float = 30.0):
+        self.engine = engine
+        self.timeout_ns = int(timeout_s * 1e9)
+        self.dead: List[int] = []
+
+    def check_once(self) -> List[int]:
+        st = self.engine.worker_status()
+        newest = int(st["heartbeat_ns"].max())
+        newly = []
+        for p in range(len(st)):
+            busy = int(st[p]["available"]) == 0
+            hb = int(st[p]["heartbeat_ns"])
+            if busy and hb and newest - hb > self.timeout_ns and p not in self.dead:
+                self.dead.append(p)
+                newly.append(p)
+        return newly

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--loss", default="logistic")
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workers-per-gpu", type=int, default=0, help="logical workers (partitions) per GPU; 0 = auto")
     return ap.parse_args()
 
 
@@ -71,12 +72,18 @@ def main() -> int:
     rank, local_rank, world = init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    P = world
+    # logical workers (= the reference's partitions).  The reference's clusters run 2 tasks per
+    # executor (1 executor x 2 cores, README.md:56); two workers per GPU play the same role: one
+    # worker's NVLink pull/push latency hides behind the other's HBM streaming.
+    wpg = args.workers_per_gpu or (2 if (world > 1 and args.impl == "ours" and args.algo in ("asgd", "asaga")) else 1)
+    P = world * wpg
     sizes = shard_rows(args.rows, P)
-    offset = sum(sizes[:rank])
+    ids = [p for p in range(P) if p % world == rank]
     t0 = time.time()
-    shard = synthetic_shard(args.shape, sizes[rank], rank, P, seed=42, device=dev, num_features=args.features,
-                            labels="binary01" if args.loss != "least_squares" else "regression", row_offset=offset)
+    shards = [synthetic_shard(args.shape, sizes[p], p, P, seed=42, device=dev, num_features=args.features,
+                              labels="binary01" if args.loss != "least_squares" else "regression", row_offset=sum(sizes[:p]))
+              for p in ids]
+    shard = shards[0]
     torch.cuda.synchronize()
     gen_s = time.time() - t0
 
@@ -98,7 +105,7 @@ def main() -> int:
         launches_of = lambda: 0                              # noqa: E731
     else:
         from asyncframework_b200.parallel.fused_backend import FusedEngine
-        eng = FusedEngine(cfg, [shard], args.rows, device=dev)
+        eng = FusedEngine(cfg, shards, args.rows, ids, device=dev)
         run = eng.run_rounds
         launches_of = lambda: eng.launches                   # noqa: E731
 
@@ -111,7 +118,11 @@ def main() -> int:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    if args.impl == "ours":
+        eng.fork(e0)                 # worker streams start after e0
     run(args.steps)
+    if args.impl == "ours":
+        eng.join()                   # launching stream waits for every worker stream
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -129,9 +140,11 @@ def main() -> int:
         t1 = time.perf_counter()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
+        eng.fork(e2)
         last = None
         for _ in range(args.steps):
             last = eng.step()
+        eng.join()
         e3.record()
         torch.cuda.synchronize()
         e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t1) * 1e3)
@@ -149,7 +162,7 @@ def main() -> int:
     else:
         k_total = eng.k
     if rank == 0:
-        bytes_per_gpu_step = sizes[0] * args.batch_rate * (shard.ld if shard.is_dense else 0) * 4
+        bytes_per_gpu_step = sum(sizes[p] for p in ids) * args.batch_rate * (shard.ld if shard.is_dense else 0) * 4
         out = {
             "metric": "sgd_iterations_per_sec", "value": args.steps / (ms_max * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
@@ -161,7 +174,8 @@ def main() -> int:
                        "sampling_rate": args.batch_rate, "seq_len": None, "parallelism": f"dp{world} parameter-server (rank 0 = server + worker)",
                        "updates_per_iteration": P, "accepted_updates_total": int(k_total),
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
-                                    f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of a {shard.nbytes() / 1e9:.2f} GB HBM-resident shard",
+                                    f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
+                       "workers_per_gpu": wpg,
                        "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); per-step H2D = round descriptor, D2H = result record",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,

@@ -35,6 +35,13 @@ struct alignas(16) WorkerCtl {      // worker-local control block (device memory
   long long last_k_after;
   unsigned long long last_task_ns;
   unsigned long long rounds_done;
+  // worker-local running statistics (published to the server's status table with posted stores,
+  // so the hot path never does a read-modify-write over NVLink)
+  unsigned long long wait_ns;       // Σ (round start − previous finish)            (A19)
+  unsigned long long last_finish_ns;
+  float avg_task_ms;
+  float pad_f;
+  unsigned long long pad_u;
 };
 
 struct alignas(16) SyncPeers {      // BSP all-gather wiring (device array, one per worker)

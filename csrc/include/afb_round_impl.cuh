@@ -28,32 +28,42 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
     __syncthreads();
     if (sh.flag == 0) {
       // This CTA is the puller: bucket gate, logical clock read, P2P fetch of w, delay injection.
+      // Gate (thread 0), then ONE NVLink round trip: the logical-clock read and the vectorised
+      // fetch of w are issued together (ts may be at most in-flight-updates older than w: conservative).
       if (tid == 0) {
         int proceed = 1;
-        unsigned long long ck = 0;
         if (is_async) {
           if (p.gate_threshold > 0) {
             // partial barrier: start only while >= floor(P*beta) workers are idle (this one included)
             while (true) {
-              ck = ld_acquire_sys_u64(&p.sctl->clock_k);
-              if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
+              unsigned long long ck0 = ld_acquire_sys_u64(&p.sctl->clock_k);
+              if (static_cast<long long>(ck0 >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
               if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= p.gate_threshold) break;
               __nanosleep(200);
             }
           }
+        }
+        wc->proceed = proceed;
+      }
+      __syncthreads();
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (is_async && tid < nvec) wv = ld_relaxed_sys_f32x4(p.w_server + 4 * tid);          // K10 (first chunk)
+      if (tid == 0) {
+        int proceed = 1;
+        unsigned long long ck = static_cast<unsigned long long>(round);                       // sync: local iteration counter
+        if (is_async) {
           ck = ld_acquire_sys_u64(&p.sctl->clock_k);
           if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) proceed = 0;
           if (proceed) {
             red_add_release_sys_s32(&p.sctl->avail_count, -1);      // busy from submit until the result lands
             WorkerSlot* me = p.status + p.worker_id;
             unsigned long long now = globaltimer_ns();
-            me->available = 0;
+            if (wc->last_finish_ns) wc->wait_ns += now - wc->last_finish_ns;
+            me->available = 0;                                      // posted stores only (no remote reads)
             me->busy_since_ns = now;
             me->heartbeat_ns = now;
-            if (me->last_finish_ns) me->wait_ns += now - me->last_finish_ns;
+            me->wait_ns = wc->wait_ns;
           }
-        } else {
-          ck = static_cast<unsigned long long>(round);             // sync: iteration counter is local
         }
         wc->ts = ck & 0xffffffffULL;
         wc->k_read = is_async ? (ck >> 32) : round;
@@ -64,14 +74,15 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
         wc->proceed = proceed;
         wc->t_start_ns = globaltimer_ns();
       }
-      __syncthreads();
-      if (wc->proceed) {
+      if (is_async) {
         // K10: parameter pull — vectorised sys-scope loads from the server's HBM over NVLink.
         // (BSP modes keep a bit-identical local replica, so there is nothing to pull.)
-        if (is_async) {
-          for (int v = tid; v < nvec; v += kThreads)
-            *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
-        }
+        if (tid < nvec) *reinterpret_cast<float4*>(p.w_local + 4 * tid) = wv;
+        for (int v = tid + kThreads; v < nvec; v += kThreads)
+          *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
+      }
+      __syncthreads();
+      if (wc->proceed) {
         if (tid == 0 && p.delay_mode != 0) {
           // A18 straggler injector: sleep a multiple of the calibrated mean task time.
           unsigned long long avg = ld_acquire_sys_u64(&p.sctl->avg_delay_ns);
@@ -219,39 +230,49 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
     }
     for (int v = tid; v < nvec; v += kThreads)
       *reinterpret_cast<float4*>(p.g_local + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_sys();                               // reductions performed before the completion is published
-    __syncthreads();
+    unsigned long long now = 0, task_ns = 0;
+    unsigned int clock_old = 0;
+    ResultRec* rec = nullptr;
     if (tid == 0) {
-      const unsigned long long now = globaltimer_ns();
-      const unsigned long long task_ns = now - wc->t_start_ns;
-      const unsigned int clock_old = __float_as_uint(sh.bcast[1]);
-      // result ring (backs AsyncContext.collect_all on the fused backend)
-      ResultRec* rec = p.ring + (clock_old % static_cast<unsigned int>(p.ring_size));
+      now = globaltimer_ns();
+      task_ns = now - wc->t_start_ns;
+      clock_old = __float_as_uint(sh.bcast[1]);
+      // result ring (backs AsyncContext.collect_all on the fused backend): posted stores, published below
+      rec = p.ring + (clock_old % static_cast<unsigned int>(p.ring_size));
       rec->worker = p.worker_id; rec->accepted = accept;
       rec->ts = static_cast<long long>(wc->ts); rec->staleness = wc->last_staleness;
       rec->k_after = wc->last_k_after; rec->batch = round_batch;
       rec->loss_sum = round_loss; rec->step = accept ? step : 0.f;
       rec->t_start_ns = wc->t_start_ns; rec->t_end_ns = now;
-      fence_sys();
-      *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(clock_old) + 1ULL;
-      // worker status (device mirror of workerState) + delay-injector calibration (A18)
+      // worker status (device mirror of workerState)
       WorkerSlot* me = p.status + p.worker_id;
+      const unsigned long long ntasks = wc->rounds_done + 1ULL;
+      const float task_ms = static_cast<float>(task_ns) * 1e-6f;
+      wc->avg_task_ms += (task_ms - wc->avg_task_ms) / static_cast<float>(ntasks);
+      wc->last_finish_ns = now;
       me->staleness = wc->last_staleness;
-      me->num_tasks += 1;
-      me->last_task_ms = static_cast<float>(task_ns) * 1e-6f;
-      me->avg_task_ms += (me->last_task_ms - me->avg_task_ms) / static_cast<float>(me->num_tasks);
+      me->num_tasks = static_cast<long long>(ntasks);
+      me->last_task_ms = task_ms;
+      me->avg_task_ms = wc->avg_task_ms;
       me->heartbeat_ns = now; me->last_finish_ns = now;
-      if (accept && wc->last_k_after <= static_cast<long long>(p.warmup_updates)) {
-        atomicAdd_system(&p.sctl->cul_time_ns, task_ns);
-        unsigned int c = atomicAdd_system(&p.sctl->cul_count, 1u) + 1u;
-        if (wc->last_k_after == static_cast<long long>(p.warmup_updates) && c > 0) {
-          unsigned long long tot = ld_acquire_sys_u64(&p.sctl->cul_time_ns);
-          atomicExch_system(&p.sctl->avg_delay_ns, tot / c);
-        }
+      // delay-injector calibration (A18): fire-and-forget accumulation during the warm-up window;
+      // the worker that lands update #warmup publishes the mean.
+      if (accept && p.warmup_updates > 0 && wc->last_k_after <= static_cast<long long>(p.warmup_updates)) {
+        asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&p.sctl->cul_time_ns), "l"(task_ns) : "memory");
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(&p.sctl->cul_count), "r"(1u) : "memory");
       }
       me->available = 1;
-      fence_sys();
+    }
+    fence_sys();                               // ONE fence: reductions + record + status performed before publication
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(clock_old) + 1ULL;
       red_add_release_sys_s32(&p.sctl->avail_count, 1);
+      if (accept && p.warmup_updates > 0 && wc->last_k_after == static_cast<long long>(p.warmup_updates)) {
+        unsigned long long tot = ld_acquire_sys_u64(&p.sctl->cul_time_ns);
+        unsigned int c = ld_acquire_sys_u32(&p.sctl->cul_count);
+        if (c) atomicExch_system(&p.sctl->avg_delay_ns, tot / c);
+      }
       wc->last_accepted = accept; wc->last_batch = round_batch; wc->last_loss = round_loss;
       wc->last_step = accept ? step : 0.f; wc->last_task_ns = task_ns;
       wc->rounds_done += 1ULL;

@@ -84,7 +84,7 @@ AFB_DEVINL int next_row(RowScheduler& s, const RoundParams& p, unsigned int* ctr
 }
 
 template <int NV4, int kThreads>
-__global__ void __launch_bounds__(kThreads, 1) dense_round_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 1) dense_round_kernel(const RoundParams p) {
   __shared__ RoundShared<kThreads> sh;
   extern __shared__ __align__(16) float s_dyn[];
   float* s_g = s_dyn;                            // [ld] CTA-level gradient accumulator
@@ -208,6 +208,8 @@ extern "C" {
 
 // Max row width handled with register accumulators: NV4 <= 16  =>  ld <= 2048 floats.
 int afb_dense_round_max_ld() { return 2048; }
+// resident CTAs per SM of the dense kernel for a given row width (grid sizing)
+int afb_dense_round_ctas_per_sm(long long ld) { return ((ld / 4 + 31) / 32) <= 8 ? 2 : 1; }
 
 int afb_dense_round_launch(const afb::RoundParams* params, int grid, void* stream) {
   using namespace afb;
@@ -216,14 +218,16 @@ int afb_dense_round_launch(const afb::RoundParams* params, int grid, void* strea
   if (p.ld % 4 != 0 || p.ld > 2048 || p.ld <= 0) return static_cast<int>(cudaErrorInvalidValue);
   int nv4 = static_cast<int>((p.ld / 4 + 31) / 32);
   cudaError_t e;
-  // <= 8 float4 per lane: 512 threads (128 regs); wider rows: 256 threads (255 regs) so the
-  // accumulators + two in-flight rows stay in registers.
+  // <= 8 float4 per lane: 256 threads x 2 CTAs/SM (128 regs) — two co-resident CTAs let two logical
+  // workers (or two rounds) share an SM so one worker's NVLink pull/push latency hides behind the
+  // other's HBM streaming; wider rows: 256 threads x 1 CTA/SM (255 regs) so the accumulators + two
+  // in-flight rows stay in registers.
   switch (nv4) {
-    case 1: e = launch_nv<1, 512>(p, grid, s); break;
-    case 2: e = launch_nv<2, 512>(p, grid, s); break;
-    case 3: case 4: e = launch_nv<4, 512>(p, grid, s); break;
-    case 5: case 6: case 7: e = launch_nv<7, 512>(p, grid, s); break;
-    case 8: e = launch_nv<8, 512>(p, grid, s); break;
+    case 1: e = launch_nv<1, 256>(p, grid, s); break;
+    case 2: e = launch_nv<2, 256>(p, grid, s); break;
+    case 3: case 4: e = launch_nv<4, 256>(p, grid, s); break;
+    case 5: case 6: case 7: e = launch_nv<7, 256>(p, grid, s); break;
+    case 8: e = launch_nv<8, 256>(p, grid, s); break;
     case 9: case 10: case 11: case 12: e = launch_nv<12, 256>(p, grid, s); break;
     default: e = launch_nv<16, 256>(p, grid, s); break;
   }

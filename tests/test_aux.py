@@ -1,0 +1,51 @@
+"""Auxiliary subsystems: checkpoint/resume, heartbeat watchdog, trace recorder."""
+import json
+import time
+
+import torch
+
+from asyncframework_b200.core import AsyncContext, Scheduler
+from asyncframework_b200.data import ShardedDataset
+from asyncframework_b200.utils import HeartbeatWatchdog, TraceRecorder, load_checkpoint, save_checkpoint
+from asyncframework_b200.utils.checkpoint import load_model_text, save_model_text
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    w = torch.randn(10)
+    p = save_checkpoint(str(tmp_path / "ck" / "rank0.pt"), w=w, k=123, clock=150, alpha_bar=w * 2,
+                        history={0: torch.arange(5.0), 3: torch.ones(2)}, config={"seed": 42})
+    ck = load_checkpoint(p)
+    assert ck["k"] == 123 and ck["clock"] == 150 and torch.equal(ck["w"], w) and torch.equal(ck["alpha_bar"], w * 2)
+    assert sorted(ck["history"]) == [0, 3] and ck["config"]["seed"] == 42
+    assert load_checkpoint(str(tmp_path / "ck"))["k"] == 123             # directory form picks rank file
+    save_model_text(str(tmp_path / "m.txt"), w, 0.5)
+    w2, b = load_model_text(str(tmp_path / "m.txt"))
+    assert torch.allclose(w2.float(), w) and b == 0.5
+
+
+def test_watchdog_marks_silent_busy_worker_dead():
+    ctx = AsyncContext(3)
+    for p in range(3):
+        ctx.stat.task_done(p, 0, 1.0)
+    ctx.mark_submitted(1)                       # busy and silent
+    dead = []
+    wd = HeartbeatWatchdog(ctx.stat, timeout_s=0.05, period_s=0.01, on_dead=dead.append).start()
+    t0 = time.time()
+    while not dead and time.time() - t0 < 2:
+        ctx.stat.heartbeat(0)
+        time.sleep(0.01)
+    wd.stop()
+    assert dead == [1] and not ctx.stat[1].alive
+    assert ctx.stat.available_workers() == 2    # the run continues with P-1
+
+
+def test_trace_recorder(tmp_path):
+    s = Scheduler(2)
+    try:
+        tr = TraceRecorder().attach(s)
+        ShardedDataset.from_records(s, list(range(10)), 4).count()
+        tr.dump(str(tmp_path / "trace.json"))
+        d = json.load(open(tmp_path / "trace.json"))
+        assert len(d["traceEvents"]) == 4 and d["counters"]["tasks"] == 4 and d["counters"]["jobs"] == 1
+    finally:
+        s.stop()
