@@ -74,6 +74,8 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_dense_round_max_ld", C.c_int, [])
     sig("afb_dense_round_ctas_per_sm", C.c_int, [i64])
     sig("afb_csr_round_launch", C.c_int, [P(RoundParams), C.c_int, vp])
+    sig("afb_dense_round_pipe_launch", C.c_int, [P(RoundParams), C.c_int, vp])
+    sig("afb_dense_round_pipe_max_ld", C.c_int, [])
     sig("afb_saga_rollback_launch", C.c_int, [vp, vp, vp, C.c_int, vp, vp])
     sig("afb_axpy", C.c_int, [f32, vp, vp, i64, vp])
     sig("afb_scal", C.c_int, [f32, vp, i64, vp])
@@ -89,6 +91,7 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_ipc_close_handle", C.c_int, [vp])
     sig("afb_enable_peer_access", C.c_int, [C.c_int, C.c_int])
     sig("afb_p2p_pingpong", C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp])
-    sig("afb_push_apply_launch", C.c_int, [P(RoundParams), C.c_int, vp])
-    sig("afb_pull_launch", C.c_int, [vp, vp, i64, vp])
+    sig("afb_push_apply_launch", C.c_int, [P(RoundParams), vp, C.c_int, vp])
+    sig("afb_broadcast_mc", C.c_int, [vp, vp, i64, vp, vp, vp])
+    sig("afb_broadcast_p2p", C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp])
     sig("afb_l2_flush", C.c_int, [vp, i64, vp])

@@ -13,7 +13,11 @@ from .round import RoundKernel, ServerLayout, ServerPointers
 
 def _kernel_for(shard: Shard, loss_id: int) -> RoundKernel:
     """One cached grad-only RoundKernel per shard (kept in ``shard.meta`` so it dies with the shard)."""
+    import os
+    variant = os.environ.get("AFB_DENSE_VARIANT", "simple")
     rk = shard.meta.get("_grad_kernel")
+    if rk is not None and shard.is_dense and rk.variant != variant and not (variant == "pipe" and rk.variant == "simple" and rk.ld > 1024):
+        rk = None
     if rk is None:
         ld = shard.ld if shard.is_dense else (shard.num_features + 3) // 4 * 4
         layout = ServerLayout(ld, 1, ring_size=1)

@@ -36,6 +36,7 @@ class ServerLayout:
     ld: int
     num_workers: int
     ring_size: int = 4096
+    history_slots: int = 0
 
     def __post_init__(self):
         off = 0
@@ -47,11 +48,10 @@ class ServerLayout:
         self.slot_stride = self.ld + 4
         self.off_gstage = off; off = _align(off + 2 * self.num_workers * self.slot_stride * 4)
         self.off_flags = off; off = _align(off + 2 * self.num_workers * 4)
-        self.off_hist_w = off   # AsyncBroadcast ring of K parameter versions follows (optional)
+        # AsyncBroadcast: ring of K parameter versions + {version counter, kernel scratch} words
+        self.off_version = off; off = _align(off + 16)
+        self.off_hist_w = off; off = _align(off + max(self.history_slots, 0) * self.ld * 4)
         self.nbytes = off
-
-    def with_history(self, slots: int) -> int:
-        return self.nbytes + _align(slots * self.ld * 4)
 
 
 class ServerBlock:
@@ -70,6 +70,9 @@ class ServerBlock:
         self.ring = buf[L.off_ring:L.off_ring + L.ring_size * RESULT_REC_DTYPE.itemsize]
         self.gstage = buf[L.off_gstage:L.off_gstage + 2 * L.num_workers * L.slot_stride * 4].view(torch.float32)
         self.flags = buf[L.off_flags:L.off_flags + 2 * L.num_workers * 4].view(torch.int32)
+        self.version_words = buf[L.off_version:L.off_version + 16].view(torch.int32)
+        self.hist_w = (buf[L.off_hist_w:L.off_hist_w + L.history_slots * L.ld * 4].view(torch.float32).view(L.history_slots, L.ld)
+                       if L.history_slots > 0 else None)
 
     @classmethod
     def allocate(cls, layout: ServerLayout, device) -> "ServerBlock":
@@ -138,7 +141,8 @@ class RoundKernel:
                  taw: int = NEVER_STALE, max_iters: int = 1 << 40, gate_threshold: int = 0,
                  delay_mode: int = 0, delay_coeff: float = 0.0, warmup_updates: int = 0,
                  local_block: Optional[ServerBlock] = None, peer_blocks: Optional[List[ServerPointers]] = None,
-                 grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None):
+                 grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None,
+                 variant: Optional[str] = None):
         if shard.device.type != "cuda":
             raise ValueError("RoundKernel needs an HBM-resident shard")
         if shard.dtype != torch.float32:
@@ -231,7 +235,19 @@ class RoundKernel:
         # this logical worker should occupy when several workers co-run on one GPU
         self.ctas_per_sm = self.lib.afb_dense_round_ctas_per_sm(ld) if self.is_dense else 2
         self.grid = int(grid) if grid else self.ctas_per_sm * self.num_sms
-        self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
+        # dense variants: "simple" = register double-buffered LDG kernel, "pipe" = TMA (cp.async.bulk)
+        # producer/consumer pipeline.  Both are fully fused rounds with identical semantics.
+        import os
+        variant = variant or os.environ.get("AFB_DENSE_VARIANT", "simple")
+        if self.is_dense and variant == "pipe" and ld <= self.lib.afb_dense_round_pipe_max_ld():
+            self.variant = "pipe"
+            self._launch = self.lib.afb_dense_round_pipe_launch
+            self.ctas_per_sm = 2
+            if not grid:
+                self.grid = 2 * self.num_sms
+        else:
+            self.variant = "simple" if self.is_dense else "csr"
+            self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         self.launches = 0
 
     # ------------------------------------------------------------------

@@ -82,7 +82,7 @@ class FusedEngine:
         first = local_shards[0]
         self.d = first.num_features
         ld = first.ld if first.is_dense else (self.d + 3) // 4 * 4
-        self.layout = ServerLayout(ld, self.P, ring_size)
+        self.layout = ServerLayout(ld, self.P, ring_size, history_slots=int(cfg.history_slots))
         # ---- symmetric server block (rank 0's copy is the parameter server) ----------------
         self.symm: SymmetricBuffer = allocate_symmetric(self.layout.nbytes, self.device, group, symm_provider)
         self.block = ServerBlock(self.layout, self.symm.local)
@@ -267,6 +267,50 @@ class FusedEngine:
                 finish_ms=float(rec["t_end_ns"]) * 1e-6))
             self._ring_seen += 1
         return out
+
+    # ------------------------------------------------------------------ versioned broadcast (A8/A9)
+    def publish_version(self) -> int:
+        """``ASYNCbroadcast``: rank 0 publishes the current ``w`` as a new version into slot
+        ``version % K`` of EVERY rank's history ring — one NVLS multicast store stream when the fabric
+        supports it (``multimem.st``), peer stores otherwise — and bumps every rank's version counter.
+        Returns the new version id.  Collective: call on all ranks."""
+        import ctypes as C
+        from ..ops import check, kernels
+        K = self.layout.history_slots
+        if K <= 0:
+            raise ValueError("history_slots == 0: versioned broadcast disabled")
+        self.synchronize()
+        self.barrier()
+        version = int(self.block.version_words[0].item()) + (0 if self.rank else 0)
+        slot = version % K
+        if self.rank == 0:
+            lib = kernels()
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            off = self.layout.off_hist_w + slot * self.layout.ld * 4
+            done = self.block.version_words[2:3]
+            if self.symm.multicast_ptr:
+                check(lib.afb_broadcast_mc(self.block.w.data_ptr(), self.symm.multicast_ptr + off, self.layout.ld,
+                                           self.symm.multicast_ptr + self.layout.off_version, done.data_ptr(), st), "broadcast_mc")
+            else:
+                dst = (C.c_void_p * self.world)(*[p + off for p in self.symm.ptrs])
+                flg = (C.c_void_p * self.world)(*[p + self.layout.off_version for p in self.symm.ptrs])
+                check(lib.afb_broadcast_p2p(self.block.w.data_ptr(), dst, flg, self.world, self.layout.ld, done.data_ptr(), st),
+                      "broadcast_p2p")
+            torch.cuda.synchronize(self.device)
+        self.barrier()
+        return version
+
+    def version_value(self, version: int) -> torch.Tensor:
+        """``ASYNCbroadcast.value(index)``: a previously published version, read from the LOCAL ring."""
+        K = self.layout.history_slots
+        cur = int(self.block.version_words[0].item())
+        if not (cur - K <= version < cur):
+            raise KeyError(f"version {version} not in the ring (current {cur}, slots {K})")
+        return self.block.hist_w[version % K, : self.d].clone()
+
+    @property
+    def version(self) -> int:
+        return int(self.block.version_words[0].item())
 
     def request_stop(self) -> None:
         if self.rank == 0:

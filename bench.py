@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--loss", default="logistic")
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe"], help="dense kernel variant (default: env/auto)")
     ap.add_argument("--workers-per-gpu", type=int, default=0, help="logical workers (partitions) per GPU; 0 = auto")
     return ap.parse_args()
 
@@ -69,6 +70,8 @@ def main() -> int:
     from asyncframework_b200.parallel.comm import init_distributed, max_over_ranks, sum_over_ranks
     from asyncframework_b200.utils.clocks import ClockSampler
 
+    if args.variant:
+        os.environ["AFB_DENSE_VARIANT"] = args.variant
     rank, local_rank, world = init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -175,7 +178,7 @@ def main() -> int:
                        "updates_per_iteration": P, "accepted_updates_total": int(k_total),
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
                                     f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
-                       "workers_per_gpu": wpg,
+                       "workers_per_gpu": wpg, "dense_variant": (eng.kernels[0].variant if args.impl == "ours" else None),
                        "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); per-step H2D = round descriptor, D2H = result record",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,

@@ -14,6 +14,12 @@ struct RoundShared {
   float bcast[4];
 };
 
+AFB_DEVINL unsigned int fetch_chunk_ctr(unsigned int* ctr, int lane) {
+  unsigned int c = 0;
+  if (lane == 0) c = atomicAdd(ctr, 1u);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
+
 // Phase 0.  Returns false when the worker has been stopped (k >= max_iters or stop flag): the
 // kernel must then return immediately (bookkeeping for the next launch is already done).
 template <int kThreads>

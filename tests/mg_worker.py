@@ -138,6 +138,37 @@ def main():
         eng.barrier()
         del eng
 
+    # ---- 3. versioned broadcast (AsyncBroadcast ring in symmetric memory, NVLS multicast when available) ---
+    parts = make_parts(world, 256, d, 3, True)
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=256 * world, num_partitions=world, num_iterations=1 << 30,
+                      step_size=0.5, batch_rate=0.5, loss="logistic", seed=1, backend="fused", barrier="asp", history_slots=3)
+    eng = FusedEngine(cfg, [shard_of(parts[rank], d, dev, rank)], 256 * world, device=dev)
+    vals = []
+    for i in range(4):
+        eng.run_rounds(2)
+        eng.synchronize()
+        eng.barrier()
+        v = eng.publish_version()
+        w_now = eng.weights().clone()
+        if world > 1:
+            dist.broadcast(w_now, 0)
+        vals.append((v, w_now))
+    ok = eng.version == 4
+    for v, wv in vals[1:]:
+        ok = ok and bool(torch.allclose(eng.version_value(v), wv))
+    try:
+        eng.version_value(0)
+        ok = False
+    except KeyError:
+        pass
+    flags = torch.tensor([1.0 if ok else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out["versioned_broadcast_ok"] = bool(flags.item() == 1.0)
+    out["versioned_broadcast_multicast"] = bool(eng.symm.multicast_ptr)
+    eng.barrier()
+    del eng
+
     if rank == 0:
         print("MG_RESULT " + json.dumps(out))
     if world > 1:

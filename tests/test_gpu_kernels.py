@@ -42,9 +42,15 @@ def test_abi_sizes():
     assert lib.afb_abi_sizeof(5) == C.sizeof(S.SyncPeers)
 
 
+@pytest.fixture(params=["simple", "pipe"])
+def dense_variant(request, monkeypatch):
+    monkeypatch.setenv("AFB_DENSE_VARIANT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("d", [20, 128, 784, 1000, 2000])
 @pytest.mark.parametrize("loss", ["least_squares", "logistic", "hinge", "least_squares_half"])
-def test_dense_grad_full(d, loss):
+def test_dense_grad_full(d, loss, dense_variant):
     from asyncframework_b200.ops.grad import grad
     from asyncframework_b200.optim.gradient import LOSS_IDS
     sh = _dense_shard(3000, d, seed=d)
@@ -56,7 +62,7 @@ def test_dense_grad_full(d, loss):
     assert torch.allclose(g.cpu().double(), gr, rtol=2e-4, atol=2e-3 * math.sqrt(d))
 
 
-def test_dense_grad_sampled_matches_cpu_sampler():
+def test_dense_grad_sampled_matches_cpu_sampler(dense_variant):
     from asyncframework_b200.core.sampler import bernoulli_mask
     from asyncframework_b200.ops.grad import grad
     from asyncframework_b200.optim.gradient import LOSS_IDS
@@ -71,12 +77,12 @@ def test_dense_grad_sampled_matches_cpu_sampler():
         assert abs(l - lr) <= 2e-4 * max(1.0, abs(lr))
 
 
-def test_dense_grad_saga_history():
+def test_dense_grad_saga_history(dense_variant):
     from asyncframework_b200.ops.grad import grad
     from asyncframework_b200.optim.gradient import LOSS_IDS
-    sh = _dense_shard(2000, 100, seed=5, labels01=False)
+    sh = _dense_shard(2003, 100, seed=5, labels01=False)
     w = torch.randn(100) * 0.1
-    hist = torch.randn(2000).cuda() * 0.2
+    hist = torch.randn(2003).cuda() * 0.2
     h0 = hist.clone()
     g, l, n = grad(sh, w.cuda(), LOSS_IDS["least_squares"], history=hist)
     gr, lr, nr, coeff = _ref_grad(sh, w, "least_squares", None, h0)
@@ -122,7 +128,7 @@ def test_level1_and_updaters():
     assert torch.allclose(w2, ref2, atol=1e-6) and abs(sq - float((ref2.double() ** 2).sum())) < 1e-2
 
 
-def test_asgd_round_single_gpu_semantics():
+def test_asgd_round_single_gpu_semantics(dense_variant):
     """One worker, async mode: every launch ticks clock and k, applies w += -gamma/sqrt(k+1)*g/parRecs."""
     from asyncframework_b200.core.sampler import bernoulli_mask
     from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
@@ -154,7 +160,7 @@ def test_asgd_round_single_gpu_semantics():
     assert [int(r["seq"]) for r in ring[:3]] == [1, 2, 3] and all(int(r["accepted"]) == 1 for r in ring[:3])
 
 
-def test_asaga_round_single_gpu_semantics():
+def test_asaga_round_single_gpu_semantics(dense_variant):
     from asyncframework_b200.core.sampler import bernoulli_mask
     from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
     from asyncframework_b200.optim.gradient import LOSS_IDS

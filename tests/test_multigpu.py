@@ -30,3 +30,4 @@ def test_fused_paths_on_all_visible_gpus():
         assert out[key + "_workers_seen"] == list(range(n))
     assert out["asgd_taw0_stale_applied"] == 0                # no update applied with staleness > taw
     assert out["asgd_tawinf_accepted"] >= 60 * n
+    assert out["versioned_broadcast_ok"]
