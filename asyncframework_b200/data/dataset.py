@@ -192,6 +192,10 @@ class ShardedDataset:
             b = self.batch(p, t)
             if b is None:
                 return None
+            if b.device.type == "cuda":
+                from ..ops.sampling import sample_rows          # K11 compaction kernel, same hash
+                rows = sample_rows(b.num_rows, fraction, seed, b.gidx, p << 40, b.device)
+                return b.select(rows)
             idx = b.gidx if b.gidx is not None else (torch.arange(b.num_rows, dtype=torch.int64) + (p << 40))
             mask = _sampler.bernoulli_mask(seed, idx, fraction)
             rows = torch.from_numpy(np.nonzero(mask)[0])
@@ -413,12 +417,14 @@ class ShardedDataset:
                 if value is not _EMPTY:
                     end = time.perf_counter() * 1e3
                     staleness = ctx.current_time - ts
-                    ctx.put(PartialResult(value, staleness, ts, count, index, start, end))
                     free = ctx.mark_finished(index) if index in sel else True
                     ctx.stat.task_done(index, staleness, end - start)
                     if not free:
                         ctx.stat.set_available(index, False)
                     ctx.add_to_current_time(1)
+                    # publish LAST: whoever dequeues the result already sees the ticked clock and the
+                    # refreshed STAT entry (the reference enqueues first, RDD.scala:1155-1158)
+                    ctx.put(PartialResult(value, staleness, ts, count, index, start, end))
                 else:
                     if index in sel:
                         free = ctx.mark_finished(index)

@@ -1,0 +1,69 @@
+"""Drivers and the general API on a single GPU (fused backend with several logical workers, and the
+in-process scheduler over HBM-resident shards)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sample_rows_kernel_matches_cpu_hash():
+    from asyncframework_b200.core.sampler import bernoulli_mask
+    from asyncframework_b200.ops.sampling import sample_rows
+    g = (torch.arange(100003, dtype=torch.int64) * 3 + 17).cuda()
+    for seed, frac in [(1, 0.1), (2**40 + 5, 0.37), (9, 1.0), (9, 0.0)]:
+        rows = sample_rows(g.numel(), frac, seed, g)
+        ref = np.nonzero(bernoulli_mask(seed, g.cpu(), frac))[0]
+        assert np.array_equal(rows.cpu().numpy(), ref)
+    rows = sample_rows(5000, 0.25, 77, None, row_base=123456, device="cuda")
+    ref = np.nonzero(bernoulli_mask(77, np.arange(5000) + 123456, 0.25))[0]
+    assert np.array_equal(rows.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("alg,step,P", [("asgd", 1.0, 4), ("asaga", 0.05, 4), ("sgd_sync", 1.0, 1), ("saga_sync", 0.3, 1)])
+def test_fused_driver_single_gpu(alg, step, P):
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    cfg = AsyncConfig(algorithm=alg, synthetic="linear", num_rows=4000, num_features=20, num_partitions=P,
+                      num_iterations=400 if P > 1 else 120, step_size=step, batch_rate=0.2, printer_freq=100, backend="fused",
+                      loss="least_squares", bucket_ratio=0.5, barrier="bucket", rounds_per_graph=8, layout="dense")
+    rep = algo.run(cfg)
+    objs = [o for _, o in rep.objective]
+    assert rep.iterations >= cfg.num_iterations
+    assert objs[0] > 0.3 and objs[-1] < 0.05
+    if P > 1:
+        assert len(rep.waiting_ms) == P and sum(rep.staleness_hist.values()) >= cfg.num_iterations
+
+
+def test_fused_driver_delay_injection_and_taw():
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    cfg = AsyncConfig(algorithm="asgd", synthetic="linear", num_rows=8000, num_features=20, num_partitions=4,
+                      num_iterations=600, step_size=1.0, batch_rate=0.2, printer_freq=300, backend="fused",
+                      bucket_ratio=0.5, barrier="bucket", coeff=1.0, warmup_updates_per_worker=20, taw=1, layout="dense")
+    rep = algo.run(cfg)
+    assert rep.objective[-1][1] < 0.05
+    assert rep.extra["avg_delay_ms"] > 0                    # calibrated on the device after 20*P updates
+    # worker 0 is the straggler: it completes fewer rounds than the others
+    tasks = rep.extra["avg_task_ms"]
+    assert tasks[0] > 1.3 * min(tasks[p] for p in (1, 2, 3))
+    assert rep.dropped >= 0 and max(rep.staleness_hist) >= 1
+
+
+def test_inprocess_api_on_hbm_shards(scheduler):
+    """The general closure API (async_barrier/sample/map_batch/async_reduce) over CUDA-resident shards."""
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    cfg = AsyncConfig(algorithm="sgd_sync", synthetic="linear", num_rows=3000, num_features=16, num_partitions=3,
+                      num_iterations=40, step_size=1.0, batch_rate=0.3, printer_freq=20, backend="auto")
+    rep = algo.run(cfg)
+    assert rep.final_weights.is_cuda and rep.objective[-1][1] < 0.05
+
+
+def test_glm_training_on_gpu_uses_fused_kernels(scheduler):
+    from asyncframework_b200.data import LinearDataGenerator, ShardedDataset
+    from asyncframework_b200.models import LinearRegressionWithSGD
+    X, y, w = LinearDataGenerator.generate_linear_arrays(3000, 12, eps=0.05, seed=2)
+    ds = ShardedDataset.from_arrays(scheduler, X, y, 2, dtype=torch.float32, device="cuda")
+    m = LinearRegressionWithSGD.train(ds, iterations=150, step=1.0, mini_batch_fraction=0.5, convergence_tol=0.0)
+    assert m.weights.is_cuda and np.abs(m.weights.cpu().numpy() - w).max() < 0.08
