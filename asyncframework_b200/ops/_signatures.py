@@ -92,6 +92,8 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_enable_peer_access", C.c_int, [C.c_int, C.c_int])
     sig("afb_p2p_pingpong", C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp])
     sig("afb_push_apply_launch", C.c_int, [P(RoundParams), vp, C.c_int, vp])
+    sig("afb_gate_launch", C.c_int, [P(RoundParams), vp])
+    sig("afb_pull_w_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_broadcast_mc", C.c_int, [vp, vp, i64, vp, vp, vp])
     sig("afb_broadcast_p2p", C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp])
     sig("afb_l2_flush", C.c_int, [vp, i64, vp])

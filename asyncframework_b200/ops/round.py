@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -249,10 +250,28 @@ class RoundKernel:
             self.variant = "simple" if self.is_dense else "csr"
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         self.launches = 0
+        # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
+        self.split = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
+        if self.split:
+            import copy
+            pg = RoundParams.from_buffer_copy(bytes(p))
+            pg.algo = ALGO["grad_only"]
+            pg.seed_mode = 3
+            self.params_grad = pg
+            self.push_ctl = torch.zeros(32, dtype=torch.uint8, device=dev)
+            self.comm_grid = max(1, min(self.num_sms, (ld // 4 + 255) // 256))
 
     # ------------------------------------------------------------------
     def launch(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if self.split:
+            sp = int(s.cuda_stream)
+            check(self.lib.afb_gate_launch(C.byref(self.params), sp), "gate")
+            check(self.lib.afb_pull_w_launch(C.byref(self.params), self.comm_grid, sp), "pull_w")
+            check(self._launch(C.byref(self.params_grad), self.grid, sp), "grad (split round)")
+            check(self.lib.afb_push_apply_launch(C.byref(self.params), self.push_ctl.data_ptr(), self.comm_grid, sp), "push_apply")
+            self.launches += 4
+            return
         check(self._launch(C.byref(self.params), self.grid, int(s.cuda_stream)), "round kernel launch")
         self.launches += 1
         if self.rollback:
@@ -263,6 +282,8 @@ class RoundKernel:
     def set(self, **kw) -> None:
         for k, v in kw.items():
             setattr(self.params, k, v)
+            if self.split and k not in ("algo", "seed_mode"):
+                setattr(self.params_grad, k, v)
 
     def read_ctl(self) -> Dict[str, float]:
         a = self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE)[0]

@@ -140,6 +140,10 @@ class FusedEngine:
         self._ctl_host = torch.zeros(n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
         self._ring_seen = 0
         self.rounds_enqueued = 0
+        self._graph = None
+        self._graph_rounds = 0
+        self._graph_launches = 0
+        self._graph_kernel_launches = 0
         self.symm.barrier()
 
     # ------------------------------------------------------------------ hot path
@@ -152,7 +156,56 @@ class FusedEngine:
 
     @property
     def launches(self) -> int:
-        return sum(rk.launches for rk in self.kernels)
+        return sum(rk.launches for rk in self.kernels) + self._graph_launches
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def build_graph(self, rounds: int) -> None:
+        """Capture ``rounds`` rounds of every local worker into one CUDA graph.  Everything that
+        changes from round to round (round counter, seeds, step size via k, stop condition) lives in
+        device memory, so a replay is exactly ``run_rounds(rounds)`` with one host call — this removes
+        the launch-bound regime for small rounds (epsilon / rcv1 shapes)."""
+        self.synchronize()
+        cap = torch.cuda.Stream(device=self.device)
+        g = torch.cuda.CUDAGraph()
+        before = [rk.launches for rk in self.kernels]
+        cap.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(g, stream=cap):
+            fork = torch.cuda.Event()
+            fork.record(cap)
+            side = []
+            for rk, st in zip(self.kernels, self._graph_streams(cap)):
+                if st != cap:
+                    st.wait_event(fork)
+                for _ in range(rounds):
+                    rk.launch(st)
+                if st != cap:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    side.append(ev)
+            for ev in side:
+                cap.wait_event(ev)
+        self._graph = g
+        self._graph_rounds = rounds
+        self._graph_kernel_launches = sum(rk.launches - b for rk, b in zip(self.kernels, before))
+        for rk, b in zip(self.kernels, before):          # capture does not execute: undo the launch counters
+            rk.launches = b
+
+    def _graph_streams(self, cap):
+        if len(self.kernels) == 1:
+            return [cap]
+        if not hasattr(self, "_gstreams"):
+            self._gstreams = [cap] + [torch.cuda.Stream(device=self.device) for _ in self.kernels[1:]]
+        self._gstreams[0] = cap
+        return self._gstreams
+
+    def run_graph(self, replays: int = 1) -> None:
+        """Replay the captured graph on the current stream (``replays * rounds`` rounds per worker)."""
+        if self._graph is None:
+            raise RuntimeError("build_graph() first")
+        for _ in range(replays):
+            self._graph.replay()
+        self.rounds_enqueued += replays * self._graph_rounds
+        self._graph_launches += replays * self._graph_kernel_launches
 
     def synchronize(self) -> None:
         for st in self.streams:

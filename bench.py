@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe"], help="dense kernel variant (default: env/auto)")
+    ap.add_argument("--graph", type=int, default=0, help="replay a CUDA graph of this many rounds (0 = plain launches)")
     ap.add_argument("--workers-per-gpu", type=int, default=0, help="logical workers (partitions) per GPU; 0 = auto")
     return ap.parse_args()
 
@@ -109,7 +110,13 @@ def main() -> int:
     else:
         from asyncframework_b200.parallel.fused_backend import FusedEngine
         eng = FusedEngine(cfg, shards, args.rows, ids, device=dev)
-        run = eng.run_rounds
+        if args.graph > 0:
+            if args.steps % args.graph or max(args.warmup, 3) % args.graph:
+                raise SystemExit("--steps and --warmup must be multiples of --graph")
+            eng.build_graph(args.graph)
+            run = lambda n: eng.run_graph(n // args.graph)    # noqa: E731
+        else:
+            run = eng.run_rounds
         launches_of = lambda: eng.launches                   # noqa: E731
 
     # ---- warm-up (untimed) -------------------------------------------------------------
@@ -121,10 +128,10 @@ def main() -> int:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    if args.impl == "ours":
+    if args.impl == "ours" and not args.graph:
         eng.fork(e0)                 # worker streams start after e0
     run(args.steps)
-    if args.impl == "ours":
+    if args.impl == "ours" and not args.graph:
         eng.join()                   # launching stream waits for every worker stream
     e1.record()
     torch.cuda.synchronize()
@@ -178,7 +185,7 @@ def main() -> int:
                        "updates_per_iteration": P, "accepted_updates_total": int(k_total),
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
                                     f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
-                       "workers_per_gpu": wpg, "dense_variant": (eng.kernels[0].variant if args.impl == "ours" else None),
+                       "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph, "dense_variant": (eng.kernels[0].variant if args.impl == "ours" else None),
                        "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); per-step H2D = round descriptor, D2H = result record",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,

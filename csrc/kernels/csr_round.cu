@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(kCsrThreads, 2) csr_round_kernel(const RoundPa
   if (p.algo != ALGO_GRAD_ONLY) {
     if (!round_begin<kCsrThreads>(p, sh, round)) return;
   }
-  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY) ? mix64(static_cast<unsigned long long>(p.seed))
-                                                             : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
+  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)
+                                     ? mix64(static_cast<unsigned long long>(p.seed))
+                                     : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
   const float* __restrict__ w = p.w_local;
   float loss_acc = 0.f;
   unsigned int cnt = 0;

@@ -105,8 +105,10 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   }
 
   // ------------------------------------------------------------------ phase 1: fused gradient
-  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY) ? mix64(static_cast<unsigned long long>(p.seed))
-                                                             : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
+  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)
+                                     ? mix64(static_cast<unsigned long long>(p.seed))
+                                     : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
   for (int i = tid; i < p.ld; i += kThreads) { s_g[i] = 0.f; s_w[i] = p.w_local[i]; }
   __syncthreads();
   float4 acc[NV4];

@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) dense_round_pipe_kernel(const
   if (p.algo != ALGO_GRAD_ONLY) {
     if (!round_begin<kPipeThreads>(p, sh, round)) return;       // contains __syncthreads(): barrier init is visible after it
   }
-  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY) ? mix64(static_cast<unsigned long long>(p.seed))
-                                                             : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
+  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)
+                                     ? mix64(static_cast<unsigned long long>(p.seed))
+                                     : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
   for (int i = tid; i < p.ld; i += kPipeThreads) s_g[i] = 0.f;
   __syncthreads();
 
@@ -213,13 +215,13 @@ static cudaError_t launch_pipe(const RoundParams& p, int grid, cudaStream_t stre
 
 extern "C" {
 
-int afb_dense_round_pipe_max_ld() { return 1024; }
+int afb_dense_round_pipe_max_ld() { return 896; }   // NV4 <= 7 validated on B200 (experimental variant)
 
 int afb_dense_round_pipe_launch(const afb::RoundParams* params, int grid, void* stream) {
   using namespace afb;
   const RoundParams& p = *params;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p.ld % 4 != 0 || p.ld > 1024 || p.ld <= 0) return static_cast<int>(cudaErrorInvalidValue);
+  if (p.ld % 4 != 0 || p.ld > 896 || p.ld <= 0) return static_cast<int>(cudaErrorInvalidValue);
   const int nv4 = static_cast<int>((p.ld / 4 + 31) / 32);
   cudaError_t e;
   switch (nv4) {

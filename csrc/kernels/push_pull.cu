@@ -58,12 +58,68 @@ __global__ void broadcast_p2p_kernel(const float* __restrict__ src, PeerList pee
   }
 }
 
+// ---- split round for wide models: gate -> multi-CTA pull -> (grad kernel) -> multi-CTA push ------------
+// A 47 236-wide model is 189 KB: one CTA pulling / pushing it serialises ~50 NVLink round trips, so for
+// wide models the round is split into small kernels whose data movement uses many CTAs.
+__global__ void gate_kernel(const RoundParams p) {
+  if (threadIdx.x != 0) return;
+  WorkerCtl* wc = p.wctl;
+  const unsigned int round = wc->round;
+  int proceed = 1;
+  if (p.gate_threshold > 0) {
+    while (true) {
+      unsigned long long ck0 = ld_acquire_sys_u64(&p.sctl->clock_k);
+      if (static_cast<long long>(ck0 >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
+      if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= p.gate_threshold) break;
+      __nanosleep(200);
+    }
+  }
+  unsigned long long ck = ld_acquire_sys_u64(&p.sctl->clock_k);
+  if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) proceed = 0;
+  if (proceed) {
+    red_add_release_sys_s32(&p.sctl->avail_count, -1);
+    WorkerSlot* me = p.status + p.worker_id;
+    unsigned long long now = globaltimer_ns();
+    if (wc->last_finish_ns) wc->wait_ns += now - wc->last_finish_ns;
+    me->available = 0; me->busy_since_ns = now; me->heartbeat_ns = now; me->wait_ns = wc->wait_ns;
+  }
+  wc->ts = ck & 0xffffffffULL;
+  wc->k_read = ck >> 32;
+  unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
+  if (p.seed_mode == 0) seed_eff += wc->k_read + 1ULL;
+  else if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+  wc->seed_key = mix64(seed_eff);
+  wc->proceed = proceed;
+  wc->t_start_ns = globaltimer_ns();
+  if (!proceed) wc->last_accepted = -1;
+  if (proceed && p.delay_mode != 0) {
+    unsigned long long avg = ld_acquire_sys_u64(&p.sctl->avg_delay_ns);
+    if (avg) {
+      float mult = p.delay_coeff;
+      if (p.delay_mode >= 2) {
+        float u = static_cast<float>(hash_u24(wc->seed_key ^ 0xD1B54A32D192ED03ULL, p.worker_id)) * (1.f / 16777216.f);
+        mult = (p.delay_mode == 3) ? (2.5f + 7.5f * u) : (1.5f + u);
+      }
+      sleep_ns(static_cast<unsigned long long>(mult * static_cast<float>(avg)));
+    }
+  }
+}
+
+__global__ void pull_w_kernel(const RoundParams p) {
+  if (!*reinterpret_cast<volatile int*>(&p.wctl->proceed)) return;
+  const long long nvec = p.ld >> 2;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x)
+    *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
+}
+
 // ---- standalone push-and-apply -------------------------------------------------------------------
 struct PushCtl { unsigned int decided; int accept; float step; unsigned int clock_old; unsigned int done; unsigned int pad[3]; };
 
 __global__ void __launch_bounds__(512) push_apply_kernel(const RoundParams p, PushCtl* pc) {
   const int tid = threadIdx.x;
   WorkerCtl* wc = p.wctl;
+  if (!*reinterpret_cast<volatile int*>(&wc->proceed)) return;     // stopped round: nothing was computed
   const long long nvec = p.ld >> 2;
   __shared__ int s_accept;
   __shared__ float s_step;
@@ -130,12 +186,25 @@ __global__ void __launch_bounds__(512) push_apply_kernel(const RoundParams p, Pu
       rec->staleness = wc->last_staleness; rec->k_after = wc->last_k_after; rec->batch = wc->last_batch;
       rec->loss_sum = wc->last_loss; rec->step = accept ? step : 0.f; rec->t_start_ns = wc->t_start_ns; rec->t_end_ns = now;
       WorkerSlot* me = p.status + p.worker_id;
-      me->staleness = wc->last_staleness; me->heartbeat_ns = now; me->last_finish_ns = now; me->available = 1;
+      const float task_ms = static_cast<float>(now - wc->t_start_ns) * 1e-6f;
+      wc->avg_task_ms += (task_ms - wc->avg_task_ms) / static_cast<float>(wc->rounds_done ? wc->rounds_done : 1ULL);
+      me->staleness = wc->last_staleness; me->num_tasks = static_cast<long long>(wc->rounds_done);
+      me->last_task_ms = task_ms; me->avg_task_ms = wc->avg_task_ms;
+      me->heartbeat_ns = now; me->last_finish_ns = now; me->available = 1;
+      if (accept && p.warmup_updates > 0 && wc->last_k_after <= static_cast<long long>(p.warmup_updates)) {
+        asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&p.sctl->cul_time_ns), "l"(now - wc->t_start_ns) : "memory");
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(&p.sctl->cul_count), "r"(1u) : "memory");
+      }
       fence_sys();
       *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(pc->clock_old) + 1ULL;
       red_add_release_sys_s32(&p.sctl->avail_count, 1);
       wc->last_accepted = accept; wc->last_step = accept ? step : 0.f;
       wc->last_task_ns = now - wc->t_start_ns; wc->last_finish_ns = now;
+      if (accept && p.warmup_updates > 0 && wc->last_k_after == static_cast<long long>(p.warmup_updates)) {
+        unsigned long long tot = ld_acquire_sys_u64(&p.sctl->cul_time_ns);
+        unsigned int c = ld_acquire_sys_u32(&p.sctl->cul_count);
+        if (c) atomicExch_system(&p.sctl->avg_delay_ns, tot / c);
+      }
     }
   }
 }
@@ -163,6 +232,16 @@ int afb_broadcast_p2p(const float* src, void* const* dst, void* const* flags, in
   int grid = static_cast<int>(std::min<long long>(148, (n4 + 255) / 256));
   if (grid < 1) grid = 1;
   afb::broadcast_p2p_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, pl, n4, done_ctr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int afb_gate_launch(const afb::RoundParams* params, void* stream) {
+  afb::gate_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*params);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int afb_pull_w_launch(const afb::RoundParams* params, int grid, void* stream) {
+  afb::pull_w_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params);
   return static_cast<int>(cudaGetLastError());
 }
 
