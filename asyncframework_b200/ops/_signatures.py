@@ -76,6 +76,9 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_csr_round_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_dense_round_pipe_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_dense_round_pipe_max_ld", C.c_int, [])
+    sig("afb_dense_round_ring_launch", C.c_int, [P(RoundParams), C.c_int, vp])
+    sig("afb_dense_round_ring_max_ld", C.c_int, [])
+    sig("afb_sleep", C.c_int, [i64, vp])
     sig("afb_saga_rollback_launch", C.c_int, [vp, vp, vp, C.c_int, vp, vp])
     sig("afb_axpy", C.c_int, [f32, vp, vp, i64, vp])
     sig("afb_scal", C.c_int, [f32, vp, i64, vp])
@@ -97,3 +100,4 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_broadcast_mc", C.c_int, [vp, vp, i64, vp, vp, vp])
     sig("afb_broadcast_p2p", C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp])
     sig("afb_l2_flush", C.c_int, [vp, i64, vp])
+    sig("afb_peer_copy", C.c_int, [vp, vp, i64, vp])

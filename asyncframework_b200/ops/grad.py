@@ -16,7 +16,7 @@ def _kernel_for(shard: Shard, loss_id: int) -> RoundKernel:
     import os
     variant = os.environ.get("AFB_DENSE_VARIANT", "simple")
     rk = shard.meta.get("_grad_kernel")
-    if rk is not None and shard.is_dense and rk.variant != variant and not (variant == "pipe" and rk.variant == "simple" and rk.ld > 896):
+    if rk is not None and shard.is_dense and rk.variant != variant and not (variant in ("pipe", "ring") and rk.variant == "simple" and rk.ld > 896):
         rk = None
     if rk is None:
         ld = shard.ld if shard.is_dense else (shard.num_features + 3) // 4 * 4

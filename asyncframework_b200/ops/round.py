@@ -240,7 +240,13 @@ class RoundKernel:
         # producer/consumer pipeline.  Both are fully fused rounds with identical semantics.
         import os
         variant = variant or os.environ.get("AFB_DENSE_VARIANT", "simple")
-        if self.is_dense and variant == "pipe" and ld <= self.lib.afb_dense_round_pipe_max_ld():
+        if self.is_dense and variant == "ring" and ld <= self.lib.afb_dense_round_ring_max_ld():
+            self.variant = "ring"
+            self._launch = self.lib.afb_dense_round_ring_launch
+            self.ctas_per_sm = 2
+            if not grid:
+                self.grid = 2 * self.num_sms
+        elif self.is_dense and variant == "pipe" and ld <= self.lib.afb_dense_round_pipe_max_ld():
             self.variant = "pipe"
             self._launch = self.lib.afb_dense_round_pipe_launch
             self.ctas_per_sm = 2

@@ -211,6 +211,17 @@ class FusedEngine:
         for st in self.streams:
             st.synchronize()
 
+    def stagger(self, period_us: float) -> None:
+        """Offset the local workers' round cadence by ``period/num_local`` each (one-time device-side
+        sleep on their streams) so their NVLink round trips and HBM streaming phases interleave instead
+        of staying in lock-step."""
+        from ..ops import check, kernels
+        n = len(self.kernels)
+        for j, st in enumerate(self.streams):
+            if j == 0 or n < 2:
+                continue
+            check(kernels().afb_sleep(int(period_us * 1e3 * j / n), int(st.cuda_stream)), "stagger")
+
     def fork(self, event: torch.cuda.Event) -> None:
         """Make every worker stream wait for ``event`` (recorded on the launching stream)."""
         cur = torch.cuda.current_stream(self.device)
@@ -280,14 +291,15 @@ class FusedEngine:
         return self.block.read_sctl()
 
     def _peer_read(self, addr: int, nbytes: int) -> np.ndarray:
-        """Blocking copy of ``nbytes`` from a (possibly peer-mapped) device address to the host."""
-        import ctypes as C
-        rt = _cudart()
-        host = np.empty(nbytes, dtype=np.uint8)
-        rc = rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(addr), C.c_size_t(nbytes), 2)
-        if rc != 0:
-            raise RuntimeError(f"cudaMemcpy(D2H, peer) failed: {rc}")
-        return host
+        """Copy ``nbytes`` (multiple of 4) from a peer-mapped device address to the host: an in-kernel
+        NVLink load into a local bounce buffer (the path the round kernels use), then a local D2H copy."""
+        from ..ops import check, kernels
+        n = (nbytes + 3) // 4 * 4
+        if getattr(self, "_bounce", None) is None or self._bounce.numel() < n:
+            self._bounce = torch.empty(max(n, 4096), dtype=torch.uint8, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        check(kernels().afb_peer_copy(self._bounce.data_ptr(), addr, n, int(st.cuda_stream)), "peer_copy")
+        return self._bounce[:n].cpu().numpy()[:nbytes].copy()
 
     def server_state(self) -> Dict[str, int]:
         """Clock / accepted-update counter of the parameter server (rank 0), readable from any rank."""

@@ -39,8 +39,9 @@ def parse():
     ap.add_argument("--loss", default="logistic")
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe"], help="dense kernel variant (default: env/auto)")
+    ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe", "ring"], help="dense kernel variant (default: env/auto)")
     ap.add_argument("--graph", type=int, default=0, help="replay a CUDA graph of this many rounds (0 = plain launches)")
+    ap.add_argument("--stagger-us", type=float, default=0.0, help="one-time phase offset between co-located workers")
     ap.add_argument("--workers-per-gpu", type=int, default=0, help="logical workers (partitions) per GPU; 0 = auto")
     return ap.parse_args()
 
@@ -120,6 +121,8 @@ def main() -> int:
         launches_of = lambda: eng.launches                   # noqa: E731
 
     # ---- warm-up (untimed) -------------------------------------------------------------
+    if args.impl == "ours" and args.stagger_us > 0:
+        eng.stagger(args.stagger_us)
     run(max(args.warmup, 3))
     barrier()
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------

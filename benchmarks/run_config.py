@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 2-5 on the fused backend (run under torchrun for N > 1):
+
+  mnist8m_asgd   ASGD logistic, dense 8.1M x 784, sampling 0.1
+  epsilon_asaga  ASAGA (per-sample history), dense 400k x 2000, sampling 0.1
+  rcv1_asgd      ASGD, CSR 677k x 47 236 (~74 nnz/row), sampling 0.05
+  straggler      ASAGA vs synchronous SAGA under delay intensity {0.3, 0.6, 1.0}, mnist8m shape
+
+Each run reports device-timed iterations/s (max over ranks) and wall-clock to a target training loss
+(full-data objective evaluated with the K12 kernel every `--eval-every` iterations).
+One iteration = every worker completes one round (b*N rows in total).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from asyncframework_b200.algo.fused_driver import evaluate_snapshots  # noqa: E402
+from asyncframework_b200.config import AsyncConfig  # noqa: E402
+from asyncframework_b200.data.generators import SHAPES, shard_rows, synthetic_shard  # noqa: E402
+from asyncframework_b200.parallel.comm import init_distributed, max_over_ranks  # noqa: E402
+from asyncframework_b200.parallel.fused_backend import FusedEngine  # noqa: E402
+
+CONFIGS = {
+    "mnist8m_asgd": dict(shape="mnist8m", algo="asgd", loss="logistic", b=0.1, gamma=2e-6, rows=None),
+    "epsilon_asaga": dict(shape="epsilon", algo="asaga", loss="logistic", b=0.1, gamma=0.5, rows=None),
+    "rcv1_asgd": dict(shape="rcv1", algo="asgd", loss="logistic", b=0.05, gamma=2.0, rows=None),
+}
+
+
+def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, eval_every, target_frac, coeff=0.0,
+            wpg=1, warm_per_worker=20, rounds_per_batch=10):
+    P = world * wpg if algo in ("asgd", "asaga") else world
+    total = int(rows or SHAPES[shape][0])
+    sizes = shard_rows(total, P)
+    ids = [p for p in range(P) if p % world == rank]
+    labels = "regression" if loss.startswith("least_squares") else "binary01"
+    shards = [synthetic_shard(shape, sizes[p], p, P, 42, dev, torch.float32, None, labels, sum(sizes[:p])) for p in ids]
+    cfg = AsyncConfig(algorithm=algo, num_features=shards[0].num_features, num_rows=total, num_partitions=P,
+                      num_iterations=1 << 40, step_size=gamma, batch_rate=b, loss=loss, seed=42, backend="fused",
+                      barrier="asp", coeff=coeff, warmup_updates_per_worker=warm_per_worker)
+    eng = FusedEngine(cfg, shards, total, ids, device=dev)
+
+    def objective():
+        return evaluate_snapshots(eng, shards, [(0.0, eng.weights())] if rank == 0 else [(0.0, None)], loss, total)[0][1] \
+            if rank == 0 or world > 1 else None
+
+    def objective_all():
+        snaps = [(0.0, eng.weights())]
+        val = evaluate_snapshots(eng, shards, snaps, loss, total)
+        return val[0][1] if val else None
+
+    obj0 = objective_all()
+    if world > 1:
+        t = torch.tensor([obj0 if obj0 is not None else 0.0], device=dev, dtype=torch.float64)
+        dist.broadcast(t, 0)
+        obj0 = float(t.item())
+    eng.run_rounds(5)                       # warm-up
+    eng.synchronize()
+    eng.barrier()
+    curve = [(0.0, obj0)]
+    target = None
+    t_target = None
+    done = 0
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    while done < iters:
+        n = min(eval_every, iters - done)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.fork(e0)
+        for _ in range(0, n, rounds_per_batch):
+            eng.run_rounds(min(rounds_per_batch, n))
+        eng.join()
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+        done += n
+        eng.barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        obj = objective_all()
+        if world > 1:
+            t = torch.tensor([obj if obj is not None else 0.0], device=dev, dtype=torch.float64)
+            dist.broadcast(t, 0)
+            obj = float(t.item())
+        curve.append((wall, obj))
+        if target is None:
+            target = obj0 * target_frac
+        if t_target is None and obj <= target:
+            t_target = wall
+            break
+    dev_ms = max_over_ranks(dev_ms, dev)
+    st = eng.server_state()
+    res = {"config": name, "algo": algo, "shape": shape, "n_gpus": world, "workers": P, "delay_intensity": coeff,
+           "iterations": done, "iterations_per_s": done / (dev_ms * 1e-3), "ms_per_iteration": dev_ms / done,
+           "objective_start": obj0, "objective_end": curve[-1][1], "target": target, "wall_ms_to_target": t_target,
+           "accepted_updates": st["k"] if eng.is_async else done, "avg_delay_ms": st["avg_delay_ns"] * 1e-6,
+           "curve": [(round(a, 2), round(o, 6)) for a, o in curve]}
+    eng.barrier()
+    del eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=list(CONFIGS) + ["straggler"])
+    ap.add_argument("--iters", type=int, default=400)
+    ap.add_argument("--eval-every", type=int, default=50)
+    ap.add_argument("--target-frac", type=float, default=0.9, help="target = this fraction of the initial objective")
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--workers-per-gpu", type=int, default=1)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rank, local_rank, world = init_distributed()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    results = []
+    if args.config == "straggler":
+        for coeff in (0.0, 0.3, 0.6, 1.0):
+            for algo, gamma in (("asaga", 3e-7), ("saga_sync", 3e-7)):
+                results.append(run_one("straggler", algo, "mnist8m", "logistic", 0.1, gamma, args.rows or None, world, rank, dev,
+                                       args.iters, args.eval_every, args.target_frac, coeff=coeff,
+                                       wpg=args.workers_per_gpu if algo == "asaga" else 1))
+                if rank == 0:
+                    r = results[-1]
+                    print(f"[straggler] {algo:10s} delay={coeff:.1f} it/s={r['iterations_per_s']:.1f} "
+                          f"t_target={r['wall_ms_to_target']} obj {r['objective_start']:.4f}->{r['objective_end']:.4f}", flush=True)
+    else:
+        c = CONFIGS[args.config]
+        results.append(run_one(args.config, c["algo"], c["shape"], c["loss"], c["b"], c["gamma"], args.rows or c["rows"], world,
+                               rank, dev, args.iters, args.eval_every, args.target_frac, wpg=args.workers_per_gpu))
+    if rank == 0:
+        for r in results:
+            print("CONFIG_RESULT " + json.dumps(r))
+        if args.out:
+            with open(args.out, "a") as f:
+                for r in results:
+                    f.write(json.dumps(r) + "\n")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,19 @@ __global__ void l2_flush_kernel(float4* buf, long long n4) {
   for (; i < n4; i += stride) buf[i] = make_float4(1.f, 2.f, 3.f, 4.f);
 }
 
+__global__ void sleep_kernel(long long ns) { if (threadIdx.x == 0) sleep_ns(static_cast<unsigned long long>(ns)); }
+
+// Generic peer -> local copy with sys-scope loads (used for host reads of the server's control words:
+// the same in-kernel NVLink load path as the round kernels, then an ordinary local D2H copy).
+__global__ void peer_copy_kernel(unsigned int* dst, const unsigned int* src, long long n_words) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src + i) : "memory");
+    dst[i] = v;
+  }
+}
+
 // P2P litmus: ping-pong a flag between two GPUs `iters` times (release/acquire at sys scope).
 __global__ void p2p_pingpong_kernel(unsigned int* mine, unsigned int* theirs, int iters, int first, unsigned long long* ns_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -162,6 +175,21 @@ int afb_enable_peer_access(int dev, int peer) {
   cudaSetDevice(cur);
   if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
   return static_cast<int>(e);
+}
+
+int afb_sleep(long long ns, void* stream) {
+  afb::sleep_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ns);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int afb_peer_copy(void* dst_local, const void* src_peer, long long nbytes, void* stream) {
+  long long n = nbytes / 4;
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid < 1) grid = 1;
+  if (grid > 148) grid = 148;
+  afb::peer_copy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned int*>(dst_local),
+                                                                            static_cast<const unsigned int*>(src_peer), n);
+  return static_cast<int>(cudaGetLastError());
 }
 
 int afb_p2p_pingpong(void* mine, void* theirs, int iters, int first, void* ns_out, void* stream) {

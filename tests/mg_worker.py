@@ -110,7 +110,9 @@ def main():
                           barrier="asp")
         eng = FusedEngine(cfg, [shard_of(parts[rank], d, dev, rank)], n_per * world, device=dev)
         losses = []
-        for _ in range(100):
+        nsteps = 0
+        for _ in range(200):
+            nsteps += 1
             r = eng.step()
             if r["accepted"] >= 0 and r["batch"] > 0:
                 losses.append(r["loss_sum"] / r["batch"])
@@ -122,6 +124,11 @@ def main():
         st = eng.server_state()
         w = eng.weights().double().cpu().numpy()
         key = f"{algo}_taw{0 if taw == 0 else 'inf'}"
+        ns = torch.tensor([float(nsteps)], device=dev)
+        lst_ns = [torch.zeros_like(ns) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(lst_ns, ns)
+        out[key + "_steps_per_rank"] = [int(t.item()) for t in lst_ns] if world > 1 else [nsteps]
         out[key + "_k"] = st["k"]
         out[key + "_clock"] = st["clock"]
         out[key + "_avail"] = st["avail_count"]

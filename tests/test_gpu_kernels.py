@@ -42,7 +42,7 @@ def test_abi_sizes():
     assert lib.afb_abi_sizeof(5) == C.sizeof(S.SyncPeers)
 
 
-@pytest.fixture(params=["simple", "pipe"])
+@pytest.fixture(params=["simple", "pipe", "ring"])
 def dense_variant(request, monkeypatch):
     monkeypatch.setenv("AFB_DENSE_VARIANT", request.param)
     return request.param
