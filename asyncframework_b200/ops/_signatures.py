@@ -39,8 +39,9 @@ WORKER_CTL_DTYPE = np.dtype([
     ("last_accepted", "<i4"), ("last_batch", "<u4"), ("last_loss", "<f4"), ("last_step", "<f4"),
     ("last_staleness", "<i8"), ("last_k_after", "<i8"), ("last_task_ns", "<u8"), ("rounds_done", "<u8"),
     ("wait_ns", "<u8"), ("last_finish_ns", "<u8"), ("avg_task_ms", "<f4"), ("pad_f", "<f4"), ("pad_u", "<u8"),
+    ("dbg_ns", "<u8", (8,)),
 ], align=False)
-assert WORKER_CTL_DTYPE.itemsize == 144
+assert WORKER_CTL_DTYPE.itemsize == 208
 
 SERVER_CTL_DTYPE = np.dtype({
     "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns"],

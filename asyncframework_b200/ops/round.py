@@ -143,7 +143,7 @@ class RoundKernel:
                  delay_mode: int = 0, delay_coeff: float = 0.0, warmup_updates: int = 0,
                  local_block: Optional[ServerBlock] = None, peer_blocks: Optional[List[ServerPointers]] = None,
                  grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None,
-                 variant: Optional[str] = None):
+                 variant: Optional[str] = None, wctl: Optional[torch.Tensor] = None):
         if shard.device.type != "cuda":
             raise ValueError("RoundKernel needs an HBM-resident shard")
         if shard.dtype != torch.float32:
@@ -167,7 +167,9 @@ class RoundKernel:
         self.w_local = torch.zeros(ld, dtype=torch.float32, device=dev)
         self.abar_local = torch.zeros(ld, dtype=torch.float32, device=dev)
         self.g_local = torch.zeros(ld, dtype=torch.float32, device=dev)
-        self.wctl = torch.zeros(WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        # control block: caller may pass a slice of a contiguous per-rank array (one D2H for all workers)
+        self.wctl = wctl if wctl is not None else torch.zeros(WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        assert self.wctl.numel() == WORKER_CTL_DTYPE.itemsize and self.wctl.is_contiguous()
         saga = algo in ("asaga", "saga_sync")
         self.hist = torch.zeros(shard.num_rows, dtype=torch.float32, device=dev) if saga else None
         if rollback is None:
@@ -291,9 +293,12 @@ class RoundKernel:
             if self.split and k not in ("algo", "seed_mode"):
                 setattr(self.params_grad, k, v)
 
+    def read_ctl_raw(self):
+        return self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE)[0]
+
     def read_ctl(self) -> Dict[str, float]:
-        a = self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE)[0]
-        return {n: (float(a[n]) if a[n].dtype.kind == "f" else int(a[n])) for n in WORKER_CTL_DTYPE.names}
+        a = self.read_ctl_raw()
+        return {n: (float(a[n]) if a[n].dtype.kind == "f" else int(a[n])) for n in WORKER_CTL_DTYPE.names if n != "dbg_ns"}
 
     @property
     def w_view(self) -> torch.Tensor:

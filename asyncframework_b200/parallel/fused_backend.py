@@ -114,7 +114,8 @@ class FusedEngine:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.kernels: List[RoundKernel] = []
         self.streams: List[torch.cuda.Stream] = []
-        for shard, wid in zip(local_shards, self.local_worker_ids):
+        self.wctl_all = torch.zeros(n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        for li, (shard, wid) in enumerate(zip(local_shards, self.local_worker_ids)):
             if cfg.production_cluster:
                 dmode = 3 if wid in long_tail else (2 if wid in normal else 0)
             else:
@@ -131,13 +132,21 @@ class FusedEngine:
                              taw=cfg.taw if cfg.taw < (1 << 31) - 1 else NEVER_STALE,
                              max_iters=cfg.num_iterations if self.is_async else (1 << 40),
                              gate_threshold=gate, delay_mode=dmode, delay_coeff=max(cfg.coeff, 0.0),
-                             warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid)
+                             warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid,
+                             wctl=self.wctl_all[li])
             self.kernels.append(rk)
             self.streams.append(torch.cuda.Stream(device=self.device) if n_local > 1 else torch.cuda.current_stream(self.device))
-        # pinned staging for the end-to-end path
-        self._desc_host = torch.zeros(16, dtype=torch.float32).pin_memory()
-        self._desc_dev = torch.zeros(16, dtype=torch.float32, device=self.device)
-        self._ctl_host = torch.zeros(n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        # pinned staging for the end-to-end path (double-buffered: step i+1 is submitted before the
+        # result of step i is read, so the per-step host work never idles the GPU)
+        self._desc_host = torch.zeros(2, 16, dtype=torch.float32).pin_memory()
+        self._desc_np = self._desc_host.numpy()
+        self._desc_dev = torch.zeros(2, 16, dtype=torch.float32, device=self.device)
+        self._ctl_host = torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self._ctl_np = self._ctl_host.numpy()
+        self._step_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._step_pending = [False, False]
+        self._step_idx = 0
+        self._io_stream = torch.cuda.Stream(device=self.device)
         self._ring_seen = 0
         self.rounds_enqueued = 0
         self._graph = None
@@ -239,39 +248,76 @@ class FusedEngine:
                 cur.wait_event(ev)
 
     # ------------------------------------------------------------------ end-to-end step
-    def step(self, step_size: Optional[float] = None) -> Dict[str, float]:
+    def _parse_result(self, slot: int) -> Dict[str, float]:
+        ctl = self._ctl_np[slot].view(WORKER_CTL_DTYPE).reshape(-1)
+        return {"loss_sum": float(ctl["last_loss"].sum()), "batch": int(ctl["last_batch"].sum()),
+                "accepted": int((ctl["last_accepted"] == 1).sum()), "k": int(ctl["last_k_after"].max()),
+                "staleness": int(ctl["last_staleness"].max())}
+
+    def step(self, step_size: Optional[float] = None, lag: int = 0) -> Optional[Dict[str, float]]:
         """One user-visible step: copy this round's descriptor (step size, batch rate, delay
-        coefficient) from pinned host memory to the device, run one fused round per local worker,
-        copy each worker's result record back to pinned memory and return it."""
+        coefficient, round id) from pinned host memory to the device, run one fused round per local
+        worker, copy every worker's result record back to pinned memory.
+
+        ``lag=0`` waits for this step's record and returns it.  ``lag=1`` returns the record of the
+        PREVIOUS step (None on the first call): the copies still happen every step, but the host reads
+        results one step behind so the device never waits for Python (call ``flush_steps()`` at the end)."""
         if step_size is not None:
             for rk in self.kernels:
                 rk.params.gamma = float(step_size)
-        d = self._desc_host
+        slot = self._step_idx & 1
+        if self._step_pending[slot]:                 # slot reuse: its previous occupant must have been read
+            self._step_events[slot].synchronize()
+        d = self._desc_np[slot]
         d[0] = self.kernels[0].params.gamma
         d[1] = self.cfg.batch_rate
         d[2] = self.cfg.coeff
         d[3] = float(self.rounds_enqueued)
-        self._desc_dev.copy_(d, non_blocking=True)                       # H2D (pinned)
+        cur = torch.cuda.current_stream(self.device)
+        self._desc_dev[slot].copy_(self._desc_host[slot], non_blocking=True)            # H2D (pinned)
+        multi = len(self.kernels) > 1
+        if multi:
+            fork = torch.cuda.Event()
+            fork.record(cur)
         for rk, st in zip(self.kernels, self.streams):
+            if multi and st != cur:
+                st.wait_event(fork)
             rk.launch(st)
+        if multi:
+            self.join()
         self.rounds_enqueued += 1
-        for i, (rk, st) in enumerate(zip(self.kernels, self.streams)):
-            with torch.cuda.stream(st):
-                self._ctl_host[i].copy_(rk.wctl, non_blocking=True)      # D2H (pinned)
-        self.synchronize()
-        ctl = self._ctl_host.numpy().view(WORKER_CTL_DTYPE).reshape(-1)
-        loss = float(ctl["last_loss"].sum())
-        batch = int(ctl["last_batch"].sum())
-        return {"loss_sum": loss, "batch": batch, "accepted": int((ctl["last_accepted"] == 1).sum()),
-                "k": int(ctl["last_k_after"].max()), "staleness": int(ctl["last_staleness"].max())}
+        self._ctl_host[slot].copy_(self.wctl_all, non_blocking=True)                    # D2H (pinned), all local workers
+        self._step_events[slot].record(cur)
+        self._step_pending[slot] = True
+        self._step_idx += 1
+        if lag == 0:
+            self._step_events[slot].synchronize()
+            self._step_pending[slot] = False
+            return self._parse_result(slot)
+        prev = slot ^ 1
+        if self._step_pending[prev]:
+            self._step_events[prev].synchronize()
+            self._step_pending[prev] = False
+            return self._parse_result(prev)
+        return None
+
+    def flush_steps(self) -> Optional[Dict[str, float]]:
+        """Wait for (and return) the newest outstanding lagged step result."""
+        last = None
+        for slot in ((self._step_idx & 1), (self._step_idx & 1) ^ 1):
+            if self._step_pending[slot]:
+                self._step_events[slot].synchronize()
+                self._step_pending[slot] = False
+                last = self._parse_result(slot)
+        return last
 
     @property
     def h2d_bytes_per_step(self) -> int:
-        return int(self._desc_host.numel() * 4)
+        return int(self._desc_host[0].numel() * 4)
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        return int(self._ctl_host.numel())
+        return int(self._ctl_host[0].numel())
 
     # ------------------------------------------------------------------ state
     def weights(self) -> torch.Tensor:

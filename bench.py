@@ -153,11 +153,11 @@ def main() -> int:
         t1 = time.perf_counter()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        eng.fork(e2)
         last = None
         for _ in range(args.steps):
-            last = eng.step()
-        eng.join()
+            r = eng.step(lag=1)          # H2D descriptor + round + D2H record EVERY step; results read one step behind
+            last = r or last
+        last = eng.flush_steps() or last
         e3.record()
         torch.cuda.synchronize()
         e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t1) * 1e3)
@@ -169,6 +169,12 @@ def main() -> int:
                "last_loss_per_row": (last["loss_sum"] / max(last["batch"], 1)) if last else None}
     clocks = sampler.stop() if sampler is not None else None
 
+    phases = None
+    if args.impl == "ours" and eng.is_async:
+        ctl = eng.kernels[0].read_ctl_raw()
+        t = [int(x) for x in ctl["dbg_ns"]]
+        names = ["gate", "pull_rtt", "compute", "clock_rtt", "reds_issue", "fence_rtt", "publish"]
+        phases = {n: (t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names)}
     if args.impl == "ours":
         st = eng.state()
         k_total = st["k"] if eng.is_async else eng.kernels[0].read_ctl()["last_k_after"]
@@ -189,10 +195,11 @@ def main() -> int:
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
                                     f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
                        "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph, "dense_variant": (eng.kernels[0].variant if args.impl == "ours" else None),
-                       "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); per-step H2D = round descriptor, D2H = result record",
+                       "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); every step: pinned H2D round descriptor -> fused round(s) -> pinned D2H result records (host reads them one step behind)",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,
             "gpu_launches": launches_all,
+            "last_round_phases_us_rank0_worker0": phases,
             "clocks": clocks,
         }
         if e2e is not None:

@@ -42,6 +42,10 @@ struct alignas(16) WorkerCtl {      // worker-local control block (device memory
   float avg_task_ms;
   float pad_f;
   unsigned long long pad_u;
+  // phase timestamps of the last round (globaltimer ns): [0] kernel entry (puller), [1] gate passed,
+  // [2] w + clock landed, [3] last CTA elected (compute done), [4] clock ticket returned,
+  // [5] reductions issued, [6] fence done, [7] published
+  unsigned long long dbg_ns[8];
 };
 
 struct alignas(16) SyncPeers {      // BSP all-gather wiring (device array, one per worker)

@@ -38,6 +38,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
       // fetch of w are issued together (ts may be at most in-flight-updates older than w: conservative).
       if (tid == 0) {
         int proceed = 1;
+        wc->dbg_ns[0] = globaltimer_ns();
         if (is_async) {
           if (p.gate_threshold > 0) {
             // partial barrier: start only while >= floor(P*beta) workers are idle (this one included)
@@ -50,6 +51,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
           }
         }
         wc->proceed = proceed;
+        wc->dbg_ns[1] = globaltimer_ns();
       }
       __syncthreads();
       float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -88,6 +90,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
           *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
       }
       __syncthreads();
+      if (tid == 0) wc->dbg_ns[2] = globaltimer_ns();
       if (wc->proceed) {
         if (tid == 0 && p.delay_mode != 0) {
           // A18 straggler injector: sleep a multiple of the calibrated mean task time.
@@ -160,6 +163,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
   if (!is_last_cta) return;
 
   // ------------------------------------------------------------------ phase 3 (last CTA): push-and-apply
+  if (tid == 0) wc->dbg_ns[3] = globaltimer_ns();
   __threadfence();
   const float round_loss = *reinterpret_cast<volatile float*>(&wc->loss_sum);
   const unsigned int round_batch = *reinterpret_cast<volatile unsigned int*>(&wc->batch_count);
@@ -203,6 +207,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
           if (static_cast<long long>(k_old) >= p.max_iters) accept = 0;
         }
       }
+      wc->dbg_ns[4] = globaltimer_ns();
       float step;
       if (p.algo == ALGO_ASGD) step = p.gamma * rsqrtf(static_cast<float>(k_old / static_cast<unsigned long long>(p.num_workers)) + 1.f);
       else step = p.gamma;
@@ -241,6 +246,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
     ResultRec* rec = nullptr;
     if (tid == 0) {
       now = globaltimer_ns();
+      wc->dbg_ns[5] = now;
       task_ns = now - wc->t_start_ns;
       clock_old = __float_as_uint(sh.bcast[1]);
       // result ring (backs AsyncContext.collect_all on the fused backend): posted stores, published below
@@ -272,6 +278,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
     fence_sys();                               // ONE fence: reductions + record + status performed before publication
     __syncthreads();
     if (tid == 0) {
+      wc->dbg_ns[6] = globaltimer_ns();
       *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(clock_old) + 1ULL;
       red_add_release_sys_s32(&p.sctl->avail_count, 1);
       if (accept && p.warmup_updates > 0 && wc->last_k_after == static_cast<long long>(p.warmup_updates)) {
@@ -283,6 +290,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
       wc->last_step = accept ? step : 0.f; wc->last_task_ns = task_ns;
       wc->rounds_done += 1ULL;
       wc->done_ctas = 0; wc->pull_ticket = 0; wc->chunk_ctr = 0; wc->loss_sum = 0.f; wc->batch_count = 0;
+      wc->dbg_ns[7] = globaltimer_ns();
       __threadfence();
       wc->round = round + 1u;
     }
