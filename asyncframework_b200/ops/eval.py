@@ -1,6 +1,8 @@
 """Objective evaluation (K12) on HBM-resident shards: Σ_i loss(x_i·w_t, y_i) for T snapshots in one
-pass.  Dense shards with enough snapshots go to the tcgen05 GEMM kernel (eval_tc.cu) when it is
-enabled; everything else runs the exact-fp32 CUDA-core kernels (eval.cu)."""
+pass.  Dense shards with >= 8 snapshots and a squared-error objective go to the tcgen05 GEMM kernel
+(eval_tc.cu; X consumed as tf32, parameters split hi/lo => ~1e-3 relative accuracy on generic data,
+exact on integer/bf16-representable data); set AFB_EVAL_TC=0 to force the exact-fp32 CUDA-core
+kernels (eval.cu), which also serve CSR shards and the logistic / hinge objectives."""
 from __future__ import annotations
 
 import os
@@ -21,7 +23,7 @@ def eval_loss(shard: Shard, W: torch.Tensor, loss_id: int, use_tensor_cores=None
     out = torch.zeros(T, dtype=torch.float64, device=shard.device)
     if shard.is_dense:
         if use_tensor_cores is None:
-            use_tensor_cores = os.environ.get("AFB_EVAL_TC", "0") == "1" and T >= 8 and shard.num_rows >= 128
+            use_tensor_cores = os.environ.get("AFB_EVAL_TC", "1") == "1" and T >= 8 and shard.num_rows >= 128
         if use_tensor_cores and hasattr(lib, "afb_eval_mse_tc") and loss_id in (0, 3):
             scratch = torch.empty(64 * ld, dtype=torch.float32, device=shard.device)
             check(lib.afb_eval_mse_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,

@@ -229,7 +229,11 @@ class RoundKernel:
         p.inv_n = 1.0 / total_rows
         p.delay_coeff = float(delay_coeff); p.delay_mode = int(delay_mode); p.warmup_updates = int(warmup_updates)
         if seed_mode is None:
+            # 0: seed + k_read + 1 (the reference's `seed + k + 1`, k read from the server at pull time)
+            # 1: seed + round + 1  (worker-local round counter: lets the first row fetch overlap the pull)
             seed_mode = {"asgd": 0, "asaga": 0, "sgd_sync": 1, "saga_sync": 1, "grad_only": 2}[algo]
+            if algo in ("asgd", "asaga") and os.environ.get("AFB_SEED_MODE", "round") == "round":
+                seed_mode = 1
         p.seed_mode = int(seed_mode); p.loss_id = int(loss_id)
         self.params = p
         props = torch.cuda.get_device_properties(dev)

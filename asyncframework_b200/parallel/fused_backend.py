@@ -423,6 +423,52 @@ class FusedEngine:
     def version(self) -> int:
         return int(self.block.version_words[0].item())
 
+    # ------------------------------------------------------------------ AsyncContext bridge
+    def start_result_pump(self, ctx, period_s: float = 0.002):
+        """Feed a host ``AsyncContext`` from the device: a daemon thread on rank 0 drains the result
+        ring into ``ctx`` (so ``ctx.collect_all()`` / ``size()`` / ``has_next()`` work on the fused
+        backend exactly like on the in-process backend), mirrors the device worker-status table into
+        ``ctx.stat`` and keeps ``ctx.current_time`` equal to the device logical clock."""
+        import threading
+
+        stop = threading.Event()
+        side = torch.cuda.Stream(device=self.device)
+
+        def pump():
+            torch.cuda.set_device(self.device)
+            while not stop.is_set():
+                with torch.cuda.stream(side):
+                    ring = self.block.ring.cpu().numpy().view(RESULT_REC_DTYPE)
+                    status = self.block.read_status()
+                n = self.layout.ring_size
+                while True:
+                    rec = ring[self._ring_seen % n]
+                    if int(rec["seq"]) != self._ring_seen + 1:
+                        break
+                    ctx.put(PartialResult(
+                        data={"accepted": bool(rec["accepted"]), "loss_sum": float(rec["loss_sum"]), "step": float(rec["step"]),
+                              "k_after": int(rec["k_after"])},
+                        staleness=int(rec["staleness"]), timestamp=int(rec["ts"]), batch_size=int(rec["batch"]),
+                        worker_id=int(rec["worker"]), submit_ms=float(rec["t_start_ns"]) * 1e-6,
+                        finish_ms=float(rec["t_end_ns"]) * 1e-6))
+                    self._ring_seen += 1
+                    ctx.current_time = self._ring_seen
+                for p in range(self.P):
+                    ctx.stat.set_state(p, int(status[p]["staleness"]), float(status[p]["avg_task_ms"]),
+                                       bool(status[p]["available"]), int(status[p]["num_tasks"]))
+                stop.wait(period_s)
+
+        th = threading.Thread(target=pump, name="afb-result-pump", daemon=True)
+        th.start()
+        self._pump = (th, stop)
+        return th
+
+    def stop_result_pump(self) -> None:
+        if getattr(self, "_pump", None):
+            self._pump[1].set()
+            self._pump[0].join(timeout=5)
+            self._pump = None
+
     def request_stop(self) -> None:
         if self.rank == 0:
             self.block.request_stop()

@@ -40,30 +40,54 @@ AFB_DEVINL void load_row(RowRegs<NV4>& r, const RoundParams& p, int row, int lan
   r.h = saga ? p.hist[row] : 0.f;
 }
 
-// Warp-level scheduler state: yields the next selected local row, fetching 64-row chunks from the
-// worker's global counter (the next chunk id is requested before the current one is consumed).
+// Warp-level scheduler state: yields the next selected local row.  Work units are row chunks taken
+// from the worker's global counter (the next chunk id is requested before the current one is consumed):
+//   * the first `static_chunks` chunks are assigned statically (chunk = global warp id) so a launch does
+//     not start with thousands of same-address atomics;
+//   * chunks are 64 rows except for the last ~2 chunks per warp, which are 16 rows (guided
+//     self-scheduling) so the drain at the end of a round costs ~2 rows per warp instead of ~7.
 struct RowScheduler {
   unsigned int m0, m1;      // selection masks of the current chunk (rows base+lane, base+32+lane)
   int base;                 // first row of the current chunk
   unsigned int next_chunk;  // prefetched chunk id
+  int n_big;                // number of 64-row chunks
+  int num_chunks;           // total chunks (big + small)
+  unsigned int static_chunks;
 };
 
-AFB_DEVINL unsigned int fetch_chunk(unsigned int* ctr, int lane) {
+constexpr int kSmallChunkRows = 16;
+
+AFB_DEVINL void sched_init(RowScheduler& s, int n_rows, unsigned int total_warps, unsigned int gwarp) {
+  // small-chunk region: ~2 small chunks per warp at the very end of the shard (never more than 1/4 of it)
+  long long small_rows = static_cast<long long>(total_warps) * 2 * kSmallChunkRows;
+  if (small_rows > n_rows / 4) small_rows = n_rows / 4;
+  const int big_rows = n_rows - static_cast<int>(small_rows);
+  s.n_big = big_rows / kChunkRows;
+  const int rest = n_rows - s.n_big * kChunkRows;
+  s.num_chunks = s.n_big + (rest + kSmallChunkRows - 1) / kSmallChunkRows;
+  s.static_chunks = total_warps;
+  s.m0 = s.m1 = 0; s.base = 0;
+  s.next_chunk = gwarp;                       // first unit: no atomic
+}
+
+AFB_DEVINL unsigned int fetch_chunk(unsigned int* ctr, int lane, unsigned int static_chunks) {
   unsigned int c = 0;
   if (lane == 0) c = atomicAdd(ctr, 1u);
-  return __shfl_sync(0xffffffffu, c, 0);
+  return __shfl_sync(0xffffffffu, c, 0) + static_chunks;
 }
 
 AFB_DEVINL void load_chunk_masks(RowScheduler& s, const RoundParams& p, unsigned int chunk, int lane,
                                  unsigned long long key) {
-  s.base = static_cast<int>(chunk) * kChunkRows;
+  int size;
+  if (static_cast<int>(chunk) < s.n_big) { s.base = static_cast<int>(chunk) * kChunkRows; size = kChunkRows; }
+  else { s.base = s.n_big * kChunkRows + (static_cast<int>(chunk) - s.n_big) * kSmallChunkRows; size = kSmallChunkRows; }
   int r0 = s.base + lane, r1 = s.base + 32 + lane;
   bool s0 = false, s1 = false;
-  if (r0 < p.n_rows) {
+  if (lane < size && r0 < p.n_rows) {
     unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r0]) : static_cast<unsigned long long>(p.row_base + r0);
     s0 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
   }
-  if (r1 < p.n_rows) {
+  if (32 + lane < size && r1 < p.n_rows) {
     unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r1]) : static_cast<unsigned long long>(p.row_base + r1);
     s1 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
   }
@@ -72,13 +96,13 @@ AFB_DEVINL void load_chunk_masks(RowScheduler& s, const RoundParams& p, unsigned
 }
 
 AFB_DEVINL int next_row(RowScheduler& s, const RoundParams& p, unsigned int* ctr, int lane,
-                        unsigned long long key, int num_chunks) {
+                        unsigned long long key) {
   while (true) {
     if (s.m0) { int b = __ffs(s.m0) - 1; s.m0 &= s.m0 - 1; return s.base + b; }
     if (s.m1) { int b = __ffs(s.m1) - 1; s.m1 &= s.m1 - 1; return s.base + 32 + b; }
     unsigned int c = s.next_chunk;
-    if (c >= static_cast<unsigned int>(num_chunks)) return -1;
-    s.next_chunk = fetch_chunk(ctr, lane);     // request one ahead
+    if (c >= static_cast<unsigned int>(s.num_chunks)) return -1;
+    s.next_chunk = fetch_chunk(ctr, lane, s.static_chunks);     // request one ahead
     load_chunk_masks(s, p, c, lane, key);
   }
 }
@@ -99,6 +123,29 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   WorkerCtl* wc = p.wctl;
   const unsigned int round = wc->round;           // written by the previous round's last CTA
 
+  float4 acc[NV4];
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float loss_acc = 0.f;
+  unsigned int cnt = 0;
+  RowScheduler sch;
+  sched_init(sch, p.n_rows, gridDim.x * (kThreads / 32), blockIdx.x * (kThreads / 32) + (tid >> 5));
+  RowRegs<NV4> cur, nxt;
+  int rc = -1;
+  unsigned long long key = 0;
+
+  // When the sampling seed does not depend on the server's k (seed_mode 1: seed + round + 1, or a
+  // fixed seed), every warp can hash its first chunk and put its first row fetch in flight BEFORE the
+  // parameter pull completes: the NVLink round trip of phase 0 overlaps the first HBM round trip.
+  const bool early = (p.algo != ALGO_GRAD_ONLY) && (p.seed_mode == 1 || p.seed_mode == 2);
+  if (early) {
+    unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
+    if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+    key = mix64(seed_eff);
+    rc = next_row(sch, p, &wc->chunk_ctr, lane, key);
+    if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+  }
+
   // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
   if (p.algo != ALGO_GRAD_ONLY) {
     if (!round_begin<kThreads>(p, sh, round)) return;
@@ -106,27 +153,19 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
 
   // ------------------------------------------------------------------ phase 1: fused gradient
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
-  const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)
-                                     ? mix64(static_cast<unsigned long long>(p.seed))
-                                     : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  if (!early) {
+    key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)
+              ? mix64(static_cast<unsigned long long>(p.seed))
+              : *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  }
   for (int i = tid; i < p.ld; i += kThreads) { s_g[i] = 0.f; s_w[i] = p.w_local[i]; }
   __syncthreads();
-  float4 acc[NV4];
-#pragma unroll
-  for (int c = 0; c < NV4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float loss_acc = 0.f;
-  unsigned int cnt = 0;
-
-  const int num_chunks = (p.n_rows + kChunkRows - 1) / kChunkRows;
-  RowScheduler sch;
-  sch.m0 = sch.m1 = 0; sch.base = 0;
-  sch.next_chunk = fetch_chunk(&wc->chunk_ctr, lane);
-
-  RowRegs<NV4> cur, nxt;
-  int rc = next_row(sch, p, &wc->chunk_ctr, lane, key, num_chunks);
-  if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+  if (!early) {
+    rc = next_row(sch, p, &wc->chunk_ctr, lane, key);
+    if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+  }
   while (rc >= 0) {
-    int rn = next_row(sch, p, &wc->chunk_ctr, lane, key, num_chunks);
+    int rn = next_row(sch, p, &wc->chunk_ctr, lane, key);
     if (rn >= 0) load_row<NV4>(nxt, p, rn, lane, nvec, SAGA);   // prefetch: second row in flight
     // K1: dot
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;

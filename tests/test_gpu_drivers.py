@@ -67,3 +67,33 @@ def test_glm_training_on_gpu_uses_fused_kernels(scheduler):
     ds = ShardedDataset.from_arrays(scheduler, X, y, 2, dtype=torch.float32, device="cuda")
     m = LinearRegressionWithSGD.train(ds, iterations=150, step=1.0, mini_batch_fraction=0.5, convergence_tol=0.0)
     assert m.weights.is_cuda and np.abs(m.weights.cpu().numpy() - w).max() < 0.08
+
+
+def test_fused_engine_feeds_async_context():
+    """collect_all()/stat on the fused backend: the device result ring pumps into a host AsyncContext."""
+    import time
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.core import AsyncContext
+    from asyncframework_b200.data.generators import synthetic_shard
+    from asyncframework_b200.parallel.fused_backend import FusedEngine
+    P = 3
+    shards = [synthetic_shard("epsilon", 2000, p, P, 5, "cuda", num_features=64, labels="regression", row_offset=2000 * p) for p in range(P)]
+    cfg = AsyncConfig(algorithm="asgd", num_features=64, num_rows=6000, num_partitions=P, num_iterations=30, step_size=0.5,
+                      batch_rate=0.25, loss="least_squares", barrier="asp", backend="fused")
+    eng = FusedEngine(cfg, shards, 6000, list(range(P)), device="cuda")
+    ctx = AsyncContext(P)
+    eng.start_result_pump(ctx)
+    eng.run_rounds(12)
+    eng.synchronize()
+    got = []
+    t0 = time.time()
+    while len(got) < 30 and time.time() - t0 < 10:
+        r = ctx.collect_all(timeout=0.5)
+        if r is not None:
+            got.append(r)
+    eng.stop_result_pump()
+    assert len(got) == 30 and sum(1 for r in got if r.data["accepted"]) == 30       # exactly num_iterations accepted
+    assert sorted({r.worker_id for r in got}) == [0, 1, 2]
+    assert all(r.batch_size > 0 and r.staleness >= 0 and r.finish_ms >= r.submit_ms for r in got)
+    assert [r.data["k_after"] for r in got] == list(range(1, 31))
+    assert ctx.stat.available_workers() == P and ctx.current_time >= 30
