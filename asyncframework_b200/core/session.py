@@ -1,0 +1,105 @@
+"""``AsyncSession`` — the SparkContext-shaped entry point.
+
+Bundles what ``new SparkContext(conf)`` sets up for the ASYNC samples (core/SparkContext.scala:
+432-571): the scheduler ("local[N]" executors), broadcast factory, dataset constructors
+(``parallelize``, ``text_file``, ``load_libsvm_file``), the blocking/non-blocking job mode switch
+(``set_mode``, SparkContext.scala:87-104) and log level.  Master URL grammar follows
+SparkContext.scala:2805-2811: ``local``, ``local[N]``, ``local[*]``, ``local[N,F]`` (F = max task
+failures); ``fused`` selects the multi-GPU fused backend (one process per GPU, see FusedEngine).
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Any, Iterable, Optional, Sequence
+
+import torch
+
+from ..config import AsyncConfig
+from .broadcast import AsyncBroadcast, Broadcast
+from .context import AsyncContext
+from .scheduler import Scheduler
+
+_LOCAL_N = re.compile(r"^local\[(\*|\d+)(?:\s*,\s*(\d+))?\]$")
+
+
+class AsyncSession:
+    def __init__(self, master: str = "local[*]", app_name: str = "asyncframework_b200", device=None,
+                 conf: Optional[AsyncConfig] = None):
+        self.master = master
+        self.app_name = app_name
+        self.conf = conf or AsyncConfig()
+        n, max_fail = self._parse_master(master)
+        self.device = torch.device(device) if device is not None else None
+        self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name)
+        self._stopped = False
+
+    @staticmethod
+    def _parse_master(master: str):
+        if master == "local":
+            return 1, 1
+        m = _LOCAL_N.match(master)
+        if m:
+            n = (os.cpu_count() or 1) if m.group(1) == "*" else int(m.group(1))
+            return max(1, n), int(m.group(2)) if m.group(2) else 4
+        if master in ("fused", "gloo"):
+            return 1, 4
+        raise ValueError(f"Could not parse Master URL: '{master}'")
+
+    # ---- datasets -----------------------------------------------------------------------
+    @property
+    def default_parallelism(self) -> int:
+        return self.scheduler.num_executors
+
+    def parallelize(self, data: Iterable[Any], num_slices: Optional[int] = None):
+        from ..data.dataset import ShardedDataset
+        return ShardedDataset.from_records(self.scheduler, list(data), num_slices or self.default_parallelism)
+
+    def text_file(self, path: str, min_partitions: Optional[int] = None):
+        """Line records of a file or a directory of part files (``sc.textFile``, SparkContext.scala:837)."""
+        from ..data.libsvm import _input_files
+        lines = []
+        for f in _input_files(path):
+            with open(f) as fh:
+                lines.extend(l.rstrip("\n") for l in fh)
+        return self.parallelize(lines, min_partitions or self.default_parallelism)
+
+    def load_libsvm_file(self, path: str, num_features: int = -1, min_partitions: Optional[int] = None, **kw):
+        from ..data.libsvm import load_libsvm_file
+        return load_libsvm_file(self.scheduler, path, num_features, min_partitions or self.default_parallelism, **kw)
+
+    # ---- broadcast / async context -----------------------------------------------------------
+    def broadcast(self, value: Any) -> Broadcast:
+        return Broadcast(value)
+
+    def async_context(self, num_workers: Optional[int] = None) -> AsyncContext:
+        return AsyncContext(num_workers or self.default_parallelism, self.scheduler)
+
+    def async_broadcast(self, ctx: AsyncContext, value: Any, slots: int = 8) -> AsyncBroadcast:
+        return AsyncBroadcast(ctx, value, slots)
+
+    # ---- job mode / misc ---------------------------------------------------------------------
+    def set_mode(self, mode: int) -> None:
+        self.scheduler.set_mode(mode)
+
+    @property
+    def mode(self) -> int:
+        return self.scheduler.mode
+
+    def set_log_level(self, level: str) -> None:
+        from ..utils.logging import set_log_level
+        set_log_level(level)
+
+    def add_listener(self, fn) -> None:
+        self.scheduler.listeners.add(fn)
+
+    def stop(self) -> None:
+        if not self._stopped:
+            self.scheduler.stop()
+            self._stopped = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.stop()

@@ -1,6 +1,6 @@
 from .vectors import DenseVector, LabeledPoint, SparseVector, Vector, Vectors
-from . import blas_util
+from . import blas_util, converters
 from .blas_util import axpy_op, dot_op, scal_op
 
 __all__ = ["DenseVector", "LabeledPoint", "SparseVector", "Vector", "Vectors",
-           "blas_util", "axpy_op", "dot_op", "scal_op"]
+           "blas_util", "converters", "axpy_op", "dot_op", "scal_op"]

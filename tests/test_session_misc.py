@@ -1,0 +1,61 @@
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from asyncframework_b200 import AsyncSession, Vectors
+from asyncframework_b200.linalg import converters
+from asyncframework_b200.utils.metrics import ConsoleSink, CsvSink, JsonlSink, MetricsRegistry, SchedulerSource
+
+
+def test_session_master_urls_and_ops(tmp_path):
+    with pytest.raises(ValueError):
+        AsyncSession("spark://host:7077")
+    with AsyncSession("local[3,2]") as sc:
+        assert sc.default_parallelism == 3 and sc.scheduler.max_failures == 2
+        assert sc.parallelize(range(10)).map(lambda x: x * x).reduce(lambda a, b: a + b) == 285
+        p = tmp_path / "t.txt"
+        p.write_text("a b\nc\n\nd e f\n")
+        assert sc.text_file(str(p), 2).flat_map(lambda l: l.split()).count() == 6
+        (tmp_path / "d.libsvm").write_text("1 1:2.0 3:1.0\n0 2:5.0\n")
+        ds = sc.load_libsvm_file(str(tmp_path / "d.libsvm"))
+        assert ds.count() == 2 and ds.num_features == 3
+        ctx = sc.async_context()
+        sc.set_mode(1)
+        assert sc.mode == 1 and sc.broadcast([1, 2]).value == [1, 2]
+        ab = sc.async_broadcast(ctx, torch.ones(2))
+        assert ab.value.tolist() == [1.0, 1.0]
+        sc.set_mode(0)
+    assert AsyncSession("local").default_parallelism == 1
+
+
+def test_converters_roundtrip():
+    sv = Vectors.sparse(5, [1, 3], [2.0, -1.0])
+    t = converters.to_torch(sv)
+    assert t.tolist() == [0, 2, 0, -1, 0] and np.array_equal(converters.to_numpy(sv), t.numpy())
+    assert converters.from_torch(t, sparse=True) == sv and converters.to_sparse([0.0, 1.0]).indices.tolist() == [1]
+    assert converters.to_dense(sv).values.tolist() == [0, 2, 0, -1, 0]
+
+
+def test_metrics_registry_and_sinks(tmp_path, scheduler):
+    from asyncframework_b200.data import ShardedDataset
+    lines = []
+    reg = MetricsRegistry().add_sink(ConsoleSink(lines.append)).add_sink(CsvSink(str(tmp_path / "csv"))).add_sink(
+        JsonlSink(str(tmp_path / "m.jsonl")))
+    SchedulerSource(reg, scheduler)
+    reg.gauge("answer", lambda: 42)
+    ShardedDataset.from_records(scheduler, list(range(8)), 4).count()
+    snap = reg.report()
+    assert snap["scheduler.jobs"] == 1 and snap["scheduler.tasks"] == 4 and snap["answer"] == 42
+    assert snap["scheduler.task_run_ms.count"] == 4
+    assert any("scheduler.tasks" in l for l in lines)
+    assert (tmp_path / "csv" / "scheduler.tasks.csv").read_text().splitlines()[1].endswith("4.0")
+    assert json.loads((tmp_path / "m.jsonl").read_text())["answer"] == 42
+
+
+def test_launcher_runs_driver_inline(capsys):
+    from asyncframework_b200 import launch
+    rc = launch.main(["--gpus", "1", "sgd_sync", "x", "x", "10", "400", "2", "15", "1.0", "0.3", "5", "0", "42",
+                      "--synthetic=linear", "--backend=cpu"])
+    assert rc == 0
