@@ -132,7 +132,7 @@ def synthetic_shard(shape: str, rows: int, partition: int, num_partitions: int, 
                 nz = torch.rand(n, d, generator=g, device=dev) < 0.19
                 pix = torch.randint(1, 256, (n, d), generator=g, device=dev, dtype=torch.int32).to(torch.float32)
                 blk = pix * nz
-                scale = 1.0 / (255.0 * math.sqrt(0.19 * d))
+                scale = 12.0 / (255.0 * math.sqrt(0.19 * d))    # margin std ~2: a learnable but noisy problem
             else:  # epsilon: unit-norm gaussian rows
                 blk = torch.randn(n, d, generator=g, device=dev)
                 blk = blk / blk.norm(dim=1, keepdim=True).clamp_min(1e-12)

@@ -244,7 +244,6 @@ class RoundKernel:
         self.grid = int(grid) if grid else self.ctas_per_sm * self.num_sms
         # dense variants: "simple" = register double-buffered LDG kernel, "pipe" = TMA (cp.async.bulk)
         # producer/consumer pipeline.  Both are fully fused rounds with identical semantics.
-        import os
         variant = variant or os.environ.get("AFB_DENSE_VARIANT", "simple")
         if self.is_dense and variant == "ring" and ld <= self.lib.afb_dense_round_ring_max_ld():
             self.variant = "ring"
@@ -265,7 +264,6 @@ class RoundKernel:
         # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
         self.split = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
         if self.split:
-            import copy
             pg = RoundParams.from_buffer_copy(bytes(p))
             pg.algo = ALGO["grad_only"]
             pg.seed_mode = 3

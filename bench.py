@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=ROWS)
     ap.add_argument("--features", type=int, default=FEATURES)
     ap.add_argument("--batch-rate", type=float, default=BATCH_RATE)
-    ap.add_argument("--step-size", type=float, default=2e-6)
+    ap.add_argument("--step-size", type=float, default=0.0, help="per-update step (0 = 8e-6 / #workers for async, 8e-6 for sync)")
     ap.add_argument("--loss", default="logistic")
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
@@ -97,6 +97,8 @@ def main() -> int:
         if world > 1:
             dist.barrier()
 
+    if args.step_size <= 0:
+        args.step_size = 8e-6 / P if args.algo in ("asgd", "asaga") else 8e-6
     cfg = AsyncConfig(algorithm=args.algo, num_features=args.features, num_rows=args.rows, num_partitions=P,
                       num_iterations=1 << 40, step_size=args.step_size, batch_rate=args.batch_rate, bucket_ratio=0.0,
                       barrier="asp", loss=args.loss, seed=42, backend="fused")

@@ -31,9 +31,11 @@ from asyncframework_b200.parallel.comm import init_distributed, max_over_ranks  
 from asyncframework_b200.parallel.fused_backend import FusedEngine  # noqa: E402
 
 CONFIGS = {
-    "mnist8m_asgd": dict(shape="mnist8m", algo="asgd", loss="logistic", b=0.1, gamma=2e-6, rows=None),
-    "epsilon_asaga": dict(shape="epsilon", algo="asaga", loss="logistic", b=0.1, gamma=0.5, rows=None),
-    "rcv1_asgd": dict(shape="rcv1", algo="asgd", loss="logistic", b=0.05, gamma=2.0, rows=None),
+    # gamma is the per-ITERATION step; async algorithms apply P updates per iteration, so they run with
+    # gamma / P per update (the reference's README does the same: async step = sync step / #partitions)
+    "mnist8m_asgd": dict(shape="mnist8m", algo="asgd", loss="logistic", b=0.1, gamma=8e-6, rows=None),
+    "epsilon_asaga": dict(shape="epsilon", algo="asaga", loss="logistic", b=0.1, gamma=2.0, rows=None),
+    "rcv1_asgd": dict(shape="rcv1", algo="asgd", loss="logistic", b=0.05, gamma=4.0, rows=None),
 }
 
 
@@ -45,6 +47,8 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
     ids = [p for p in range(P) if p % world == rank]
     labels = "regression" if loss.startswith("least_squares") else "binary01"
     shards = [synthetic_shard(shape, sizes[p], p, P, 42, dev, torch.float32, None, labels, sum(sizes[:p])) for p in ids]
+    if algo in ("asgd", "asaga"):
+        gamma = gamma / P
     cfg = AsyncConfig(algorithm=algo, num_features=shards[0].num_features, num_rows=total, num_partitions=P,
                       num_iterations=1 << 40, step_size=gamma, batch_rate=b, loss=loss, seed=42, backend="fused",
                       barrier="asp", coeff=coeff, warmup_updates_per_worker=warm_per_worker)
@@ -127,7 +131,7 @@ def main():
     results = []
     if args.config == "straggler":
         for coeff in (0.0, 0.3, 0.6, 1.0):
-            for algo, gamma in (("asaga", 3e-7), ("saga_sync", 3e-7)):
+            for algo, gamma in (("asaga", 3e-6), ("saga_sync", 3e-6)):
                 results.append(run_one("straggler", algo, "mnist8m", "logistic", 0.1, gamma, args.rows or None, world, rank, dev,
                                        args.iters, args.eval_every, args.target_frac, coeff=coeff,
                                        wpg=args.workers_per_gpu if algo == "asaga" else 1))
