@@ -24,6 +24,7 @@ class RoundParams(C.Structure):
         ("seed", i64), ("taw", i64), ("max_iters", i64),
         ("gamma", f32), ("inv_par_recs", f32), ("inv_n", f32), ("delay_coeff", f32),
         ("delay_mode", i32), ("warmup_updates", i32), ("seed_mode", i32), ("loss_id", i32),
+        ("round_host", i32), ("pdl", i32),
     ]
 
 

@@ -261,6 +261,11 @@ class RoundKernel:
             self.variant = "simple" if self.is_dense else "csr"
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         self.launches = 0
+        self.rounds_launched = 0
+        # programmatic dependent launch (simple dense variant, non-split, no rollback kernel in between):
+        # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail
+        self.use_pdl = (self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
+                        and os.environ.get("AFB_PDL", "1") == "1")
         # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
         self.split = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
         if self.split:
@@ -281,9 +286,16 @@ class RoundKernel:
             check(self._launch(C.byref(self.params_grad), self.grid, sp), "grad (split round)")
             check(self.lib.afb_push_apply_launch(C.byref(self.params), self.push_ctl.data_ptr(), self.comm_grid, sp), "push_apply")
             self.launches += 4
+            self.rounds_launched += 1
             return
+        if self.use_pdl and not torch.cuda.is_current_stream_capturing():
+            self.params.pdl = 1
+            self.params.round_host = self.rounds_launched
+        else:
+            self.params.pdl = 0
         check(self._launch(C.byref(self.params), self.grid, int(s.cuda_stream)), "round kernel launch")
         self.launches += 1
+        self.rounds_launched += 1
         if self.rollback:
             check(self.lib.afb_saga_rollback_launch(self.hist.data_ptr(), self.hist_prev.data_ptr(), self.hist_tag.data_ptr(),
                                                     self.shard.num_rows, self.wctl.data_ptr(), int(s.cuda_stream)), "saga rollback")

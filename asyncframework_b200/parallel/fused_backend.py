@@ -72,6 +72,8 @@ class FusedEngine:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.device = torch.device(device) if device is not None else local_shards[0].device
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.P = int(cfg.num_partitions)
         if local_worker_ids is None:
             local_worker_ids = [p for p in range(self.P) if p % self.world == self.rank]

@@ -100,6 +100,8 @@ struct RoundParams {
   int warmup_updates;               // calibration window (100*P async)
   int seed_mode;                    // 0: seed + k_read + 1 ; 1: seed + round + 1 ; 2: seed (fixed)
   int loss_id;                      // afb::LossId
+  int round_host;                   // PDL: the round index counted by the host (== wctl->round at kernel start)
+  int pdl;                          // 1: launched with programmatic stream serialization (see dense_round.cu)
 };
 
 }  // namespace afb

@@ -77,7 +77,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
         wc->k_read = is_async ? (ck >> 32) : round;
         unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
         if (p.seed_mode == 0) seed_eff += wc->k_read + 1ULL;
-        else if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+        else if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(p.pdl ? static_cast<unsigned int>(p.round_host) : round) + 1ULL;
         wc->seed_key = mix64(seed_eff);
         wc->proceed = proceed;
         wc->t_start_ns = globaltimer_ns();

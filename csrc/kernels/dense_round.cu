@@ -121,7 +121,11 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   const int warp = tid >> 5;
   const int nvec = static_cast<int>(p.ld >> 2);
   WorkerCtl* wc = p.wctl;
-  const unsigned int round = wc->round;           // written by the previous round's last CTA
+  // Programmatic dependent launch: this grid may start while the PREVIOUS round's last CTA is still in
+  // its NVLink tail.  Everything before `griddepcontrol.wait` touches only immutable inputs (X, y, gidx)
+  // and uses the host-counted round index; all protocol state is read after the wait.
+  const bool pdl = (p.pdl != 0);
+  const unsigned int seed_round = pdl ? static_cast<unsigned int>(p.round_host) : wc->round;   // sampling-seed input only
 
   float4 acc[NV4];
 #pragma unroll
@@ -140,10 +144,27 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   const bool early = (p.algo != ALGO_GRAD_ONLY) && (p.seed_mode == 1 || p.seed_mode == 2);
   if (early) {
     unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
-    if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+    if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(seed_round) + 1ULL;
     key = mix64(seed_eff);
-    rc = next_row(sch, p, &wc->chunk_ctr, lane, key);
-    if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+    // statically assigned first chunk only: no atomics on the chunk counter before the dependency wait
+    const unsigned int c0 = sch.next_chunk;
+    sch.next_chunk = 0xffffffffu;                 // "not fetched yet"
+    if (c0 < static_cast<unsigned int>(sch.num_chunks)) {
+      load_chunk_masks(sch, p, c0, lane, key);
+      if (sch.m0) { int b = __ffs(sch.m0) - 1; sch.m0 &= sch.m0 - 1; rc = sch.base + b; }
+      else if (sch.m1) { int b = __ffs(sch.m1) - 1; sch.m1 &= sch.m1 - 1; rc = sch.base + 32 + b; }
+      if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA && !pdl);   // hist is mutable: not before the wait
+    }
+  }
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const unsigned int round = *reinterpret_cast<volatile unsigned int*>(&wc->round);   // protocol round (device truth)
+  if (early) {
+    if (pdl && SAGA && rc >= 0) cur.h = p.hist[rc];
+    sch.next_chunk = fetch_chunk(&wc->chunk_ctr, lane, sch.static_chunks);
+    if (rc < 0) {
+      rc = next_row(sch, p, &wc->chunk_ctr, lane, key);
+      if (rc >= 0) load_row<NV4>(cur, p, rc, lane, nvec, SAGA);
+    }
   }
 
   // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
@@ -222,6 +243,9 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
     float4 gv = *reinterpret_cast<float4*>(&s_g[4 * v]);
     red_add_gpu_f32x4(p.g_local + 4 * v, gv);
   }
+  // this CTA's part of the round is done: let the next round's grid start its prologue (first-row
+  // prefetch) while the last CTA of this grid runs the NVLink tail
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   round_finish<kThreads>(p, sh, round, loss_acc, cnt);
 }
 
@@ -239,6 +263,15 @@ static cudaError_t launch_nv(const RoundParams& p, int grid, cudaStream_t stream
   size_t smem = 2 * static_cast<size_t>(p.ld) * sizeof(float);
   auto k = dense_round_kernel<NV4, kThreads>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, p);
+  }
   k<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
