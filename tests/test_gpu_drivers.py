@@ -97,3 +97,41 @@ def test_fused_engine_feeds_async_context():
     assert all(r.batch_size > 0 and r.staleness >= 0 and r.finish_ms >= r.submit_ms for r in got)
     assert [r.data["k_after"] for r in got] == list(range(1, 31))
     assert ctx.stat.available_workers() == P and ctx.current_time >= 30
+
+
+def test_cuda_graph_replay_matches_plain_launches():
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.data.generators import synthetic_shard
+    from asyncframework_b200.parallel.fused_backend import FusedEngine
+
+    def make():
+        sh = synthetic_shard("epsilon", 4000, 0, 1, 5, "cuda", num_features=128, labels="regression")
+        cfg = AsyncConfig(algorithm="sgd_sync", num_features=128, num_rows=4000, num_partitions=1, num_iterations=1 << 30,
+                          step_size=0.5, batch_rate=0.25, loss="least_squares", backend="fused")
+        return FusedEngine(cfg, [sh], 4000, [0], device="cuda")
+    a, b = make(), make()
+    a.run_rounds(12)
+    b.build_graph(4)
+    b.run_graph(3)
+    a.synchronize(); b.synchronize()
+    assert b.launches == 12 and a.launches == 12
+    assert torch.allclose(a.weights(), b.weights(), rtol=1e-4, atol=1e-6)
+    assert a.kernels[0].read_ctl()["round"] == b.kernels[0].read_ctl()["round"] == 12
+
+
+def test_fused_checkpoint_and_resume(tmp_path):
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.utils import load_checkpoint
+    base = dict(algorithm="asaga", synthetic="linear", num_rows=4000, num_features=20, num_partitions=2, step_size=0.05,
+                batch_rate=0.2, printer_freq=100, backend="fused", loss="least_squares", barrier="asp", layout="dense",
+                rounds_per_graph=5)
+    cfg = AsyncConfig(num_iterations=200, checkpoint_dir=str(tmp_path / "ck"), checkpoint_every=100, **base)
+    rep = algo.run(cfg)
+    ck = load_checkpoint(str(tmp_path / "ck"))
+    assert ck["k"] >= 100 and ck["alpha_bar"] is not None and sorted(ck["history"]) == [0, 1]
+    cfg2 = AsyncConfig(num_iterations=100, resume=str(tmp_path / "ck"), **base)
+    rep2 = algo.run(cfg2)
+    # resumed run starts from the checkpointed model: its first objective is far below the cold-start one
+    assert rep2.objective[0][1] < 0.5 * rep.objective[0][1]
+    assert rep2.objective[-1][1] < 0.05
