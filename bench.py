@@ -177,6 +177,9 @@ def main() -> int:
         t = [int(x) for x in ctl["dbg_ns"]]
         names = ["gate", "pull_rtt", "compute", "clock_rtt", "reds_issue", "fence_rtt", "publish"]
         phases = {n: (t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names)}
+        # absolute phase stamps of the last round of every local worker, relative to worker 0's kernel entry
+        t00 = t[0]
+        phases["workers_abs_us"] = [[round((int(x) - t00) / 1e3, 1) for x in rk.read_ctl_raw()["dbg_ns"]] for rk in eng.kernels]
     if args.impl == "ours":
         st = eng.state()
         k_total = st["k"] if eng.is_async else eng.kernels[0].read_ctl()["last_k_after"]
