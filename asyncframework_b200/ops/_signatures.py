@@ -41,8 +41,10 @@ WORKER_CTL_DTYPE = np.dtype([
     ("last_staleness", "<i8"), ("last_k_after", "<i8"), ("last_task_ns", "<u8"), ("rounds_done", "<u8"),
     ("wait_ns", "<u8"), ("last_finish_ns", "<u8"), ("avg_task_ms", "<f4"), ("pad_f", "<f4"), ("pad_u", "<u8"),
     ("dbg_ns", "<u8", (8,)),
+    ("tk_flag", "<u4"), ("tk_accept", "<i4"), ("tk_step", "<f4"), ("tk_clock_old", "<u4"),
+    ("tk_staleness", "<i8"), ("tk_k_after", "<i8"),
 ], align=False)
-assert WORKER_CTL_DTYPE.itemsize == 208
+assert WORKER_CTL_DTYPE.itemsize == 240
 
 SERVER_CTL_DTYPE = np.dtype({
     "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns"],

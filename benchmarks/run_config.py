@@ -40,7 +40,7 @@ CONFIGS = {
 
 
 def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, eval_every, target_frac, coeff=0.0,
-            wpg=1, warm_per_worker=20, rounds_per_batch=10):
+            wpg=1, warm_per_worker=20, rounds_per_batch=10, by_updates=False):
     P = world * wpg if algo in ("asgd", "asaga") else world
     total = int(rows or SHAPES[shape][0])
     sizes = shard_rows(total, P)
@@ -49,8 +49,12 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
     shards = [synthetic_shard(shape, sizes[p], p, P, 42, dev, torch.float32, None, labels, sum(sizes[:p])) for p in ids]
     if algo in ("asgd", "asaga"):
         gamma = gamma / P
+    is_async = algo in ("asgd", "asaga")
+    # `by_updates`: an async run is finished when the SERVER has accepted iters*P updates (the reference's
+    # termination rule, `k >= numIteration`): fast workers keep going while a straggler sleeps.
+    max_updates = iters * P if (by_updates and is_async) else (1 << 40)
     cfg = AsyncConfig(algorithm=algo, num_features=shards[0].num_features, num_rows=total, num_partitions=P,
-                      num_iterations=1 << 40, step_size=gamma, batch_rate=b, loss=loss, seed=42, backend="fused",
+                      num_iterations=max_updates, step_size=gamma, batch_rate=b, loss=loss, seed=42, backend="fused",
                       barrier="asp", coeff=coeff, warmup_updates_per_worker=warm_per_worker)
     eng = FusedEngine(cfg, shards, total, ids, device=dev)
 
@@ -68,9 +72,40 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
         t = torch.tensor([obj0 if obj0 is not None else 0.0], device=dev, dtype=torch.float64)
         dist.broadcast(t, 0)
         obj0 = float(t.item())
-    eng.run_rounds(5)                       # warm-up
+    if not (by_updates and is_async):
+        eng.run_rounds(5)                   # warm-up
     eng.synchronize()
     eng.barrier()
+    if by_updates and is_async:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        eng.fork(e0)
+        rounds = 0
+        while True:
+            eng.run_rounds(rounds_per_batch)
+            rounds += rounds_per_batch
+            if eng.server_state()["k"] >= max_updates or rounds > 50 * iters:
+                break
+        eng.join()
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+        eng.barrier()
+        obj = objective_all()
+        if world > 1:
+            t = torch.tensor([obj if obj is not None else 0.0], device=dev, dtype=torch.float64)
+            dist.broadcast(t, 0)
+            obj = float(t.item())
+        st = eng.server_state()
+        res = {"config": name, "algo": algo, "shape": shape, "n_gpus": world, "workers": P, "delay_intensity": coeff,
+               "iterations": iters, "iterations_per_s": iters / (dev_ms * 1e-3), "ms_per_iteration": dev_ms / iters,
+               "objective_start": obj0, "objective_end": obj, "accepted_updates": min(st["k"], max_updates),
+               "local_rounds_rank0": rounds, "avg_delay_ms": st["avg_delay_ns"] * 1e-6, "mode": "fixed total updates (iters*P)"}
+        eng.barrier()
+        del eng
+        torch.cuda.empty_cache()
+        return res
     curve = [(0.0, obj0)]
     target = None
     t_target = None
@@ -124,21 +159,23 @@ def main():
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--workers-per-gpu", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--delays", type=float, nargs="+", default=[0.0, 0.3, 0.6, 1.0])
     args = ap.parse_args()
     rank, local_rank, world = init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     results = []
     if args.config == "straggler":
-        for coeff in (0.0, 0.3, 0.6, 1.0):
+        for coeff in args.delays:
             for algo, gamma in (("asaga", 3e-6), ("saga_sync", 3e-6)):
                 results.append(run_one("straggler", algo, "mnist8m", "logistic", 0.1, gamma, args.rows or None, world, rank, dev,
-                                       args.iters, args.eval_every, args.target_frac, coeff=coeff,
-                                       wpg=args.workers_per_gpu if algo == "asaga" else 1))
+                                       args.iters, args.iters, args.target_frac, coeff=coeff,
+                                       wpg=args.workers_per_gpu if algo == "asaga" else 1, by_updates=True))
                 if rank == 0:
                     r = results[-1]
-                    print(f"[straggler] {algo:10s} delay={coeff:.1f} it/s={r['iterations_per_s']:.1f} "
-                          f"t_target={r['wall_ms_to_target']} obj {r['objective_start']:.4f}->{r['objective_end']:.4f}", flush=True)
+                    print(f"[straggler] {algo:10s} delay={coeff:.1f} equal-work it/s={r['iterations_per_s']:.1f} "
+                          f"ms/it={r['ms_per_iteration']:.4f} obj {r['objective_start']:.4f}->{r['objective_end']:.4f} "
+                          f"avg_delay_ms={r['avg_delay_ms']:.4f}", flush=True)
     else:
         c = CONFIGS[args.config]
         results.append(run_one(args.config, c["algo"], c["shape"], c["loss"], c["b"], c["gamma"], args.rows or c["rows"], world,

@@ -46,6 +46,14 @@ struct alignas(16) WorkerCtl {      // worker-local control block (device memory
   // [2] w + clock landed, [3] last CTA elected (compute done), [4] clock ticket returned,
   // [5] reductions issued, [6] fence done, [7] published
   unsigned long long dbg_ns[8];
+  // early logical-clock ticket: taken by the FIRST CTA that finishes its gradient work so the NVLink
+  // round trip of the atomic overlaps the drain of the compute phase; consumed by the last CTA
+  unsigned int tk_flag;             // == round+1 once the fields below are valid
+  int tk_accept;
+  float tk_step;
+  unsigned int tk_clock_old;
+  long long tk_staleness;
+  long long tk_k_after;
 };
 
 struct alignas(16) SyncPeers {      // BSP all-gather wiring (device array, one per worker)

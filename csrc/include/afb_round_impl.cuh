@@ -20,47 +20,68 @@ AFB_DEVINL unsigned int fetch_chunk_ctr(unsigned int* ctr, int lane) {
   return __shfl_sync(0xffffffffu, c, 0);
 }
 
-// Phase 0.  Returns false when the worker has been stopped (k >= max_iters or stop flag): the
-// kernel must then return immediately (bookkeeping for the next launch is already done).
+// Phase 0 is split in two so that its NVLink round trip overlaps useful work:
+//   round_begin_issue()    - puller election (ticket), bucket gate, and the pull's loads are ISSUED
+//                            (clock word + first chunk of w stay in registers, latency in flight);
+//   ... the caller hashes its first row chunk / prefetches its first rows here ...
+//   round_begin_complete() - the puller consumes the loads, publishes w_local / ts / seed and releases
+//                            the CTA-visible flag; every other CTA waits for the flag.
+// Returns false when the worker has been stopped (k >= max_iters or stop flag): the kernel must then
+// return immediately (bookkeeping for the next launch is already done).
+struct RoundPull {
+  float4 wv;
+  unsigned long long ck;
+  bool puller;
+};
+
 template <int kThreads>
-AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round) {
+AFB_DEVINL void round_begin_issue(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round, RoundPull& pl) {
   const int tid = threadIdx.x;
   const int nvec = static_cast<int>(p.ld >> 2);
   WorkerCtl* wc = p.wctl;
   const bool is_async = (p.algo == ALGO_ASGD || p.algo == ALGO_ASAGA);
-  // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
-  if (p.algo != ALGO_GRAD_ONLY) {
-    if (tid == 0) sh.flag = atomicAdd(&wc->pull_ticket, 1u);
-    __syncthreads();
-    if (sh.flag == 0) {
-      // This CTA is the puller: bucket gate, logical clock read, P2P fetch of w, delay injection.
-      // Gate (thread 0), then ONE NVLink round trip: the logical-clock read and the vectorised
-      // fetch of w are issued together (ts may be at most in-flight-updates older than w: conservative).
-      if (tid == 0) {
-        int proceed = 1;
-        wc->dbg_ns[0] = globaltimer_ns();
-        if (is_async) {
-          if (p.gate_threshold > 0) {
-            // partial barrier: start only while >= floor(P*beta) workers are idle (this one included)
-            while (true) {
-              unsigned long long ck0 = ld_acquire_sys_u64(&p.sctl->clock_k);
-              if (static_cast<long long>(ck0 >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
-              if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= p.gate_threshold) break;
-              __nanosleep(200);
-            }
-          }
-        }
-        wc->proceed = proceed;
-        wc->dbg_ns[1] = globaltimer_ns();
+  pl.wv = make_float4(0.f, 0.f, 0.f, 0.f);
+  pl.ck = static_cast<unsigned long long>(round);               // sync: local iteration counter
+  pl.puller = false;
+  if (p.algo == ALGO_GRAD_ONLY) return;
+  if (tid == 0) sh.flag = atomicAdd(&wc->pull_ticket, 1u);
+  __syncthreads();
+  pl.puller = (sh.flag == 0);
+  if (!pl.puller) return;
+  // This CTA is the puller: bucket gate, then ONE NVLink round trip — the logical-clock read and the
+  // vectorised fetch of w are issued together (ts may be at most in-flight-updates older than w).
+  if (tid == 0) {
+    wc->dbg_ns[0] = globaltimer_ns();
+    if (is_async && p.gate_threshold > 0) {
+      // partial barrier: start only while >= floor(P*beta) workers are idle (this one included)
+      while (true) {
+        unsigned long long ck0 = ld_acquire_sys_u64(&p.sctl->clock_k);
+        if (static_cast<long long>(ck0 >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) break;
+        if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= p.gate_threshold) break;
+        __nanosleep(200);
       }
-      __syncthreads();
-      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (is_async && tid < nvec) wv = ld_relaxed_sys_f32x4(p.w_server + 4 * tid);          // K10 (first chunk)
+    }
+    wc->dbg_ns[1] = globaltimer_ns();
+  }
+  if (is_async && p.gate_threshold > 0) __syncthreads();         // nobody reads w before the gate opens
+  if (is_async) {
+    if (tid < nvec) pl.wv = ld_relaxed_sys_f32x4(p.w_server + 4 * tid);          // K10 (first chunk), in flight
+    if (tid == 0) pl.ck = ld_acquire_sys_u64(&p.sctl->clock_k);
+  }
+}
+
+template <int kThreads>
+AFB_DEVINL bool round_begin_complete(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round, const RoundPull& pl) {
+  const int tid = threadIdx.x;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  const bool is_async = (p.algo == ALGO_ASGD || p.algo == ALGO_ASAGA);
+  if (p.algo != ALGO_GRAD_ONLY) {
+    if (pl.puller) {
       if (tid == 0) {
         int proceed = 1;
-        unsigned long long ck = static_cast<unsigned long long>(round);                       // sync: local iteration counter
+        const unsigned long long ck = pl.ck;
         if (is_async) {
-          ck = ld_acquire_sys_u64(&p.sctl->clock_k);
           if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) proceed = 0;
           if (proceed) {
             red_add_release_sys_s32(&p.sctl->avail_count, -1);      // busy from submit until the result lands
@@ -85,7 +106,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
       if (is_async) {
         // K10: parameter pull — vectorised sys-scope loads from the server's HBM over NVLink.
         // (BSP modes keep a bit-identical local replica, so there is nothing to pull.)
-        if (tid < nvec) *reinterpret_cast<float4*>(p.w_local + 4 * tid) = wv;
+        if (tid < nvec) *reinterpret_cast<float4*>(p.w_local + 4 * tid) = pl.wv;
         for (int v = tid + kThreads; v < nvec; v += kThreads)
           *reinterpret_cast<float4*>(p.w_local + 4 * v) = ld_relaxed_sys_f32x4(p.w_server + 4 * v);
       }
@@ -110,7 +131,7 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
       if (tid == 0) st_release_gpu_u32(&wc->pull_flag, round + 1u);
     } else {
       if (tid == 0) {
-        while (ld_acquire_gpu_u32(&wc->pull_flag) != round + 1u) __nanosleep(64);
+        while (ld_acquire_gpu_u32(&wc->pull_flag) != round + 1u) __nanosleep(32);
       }
       __syncthreads();
     }
@@ -131,6 +152,13 @@ AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, con
   }
 
   return true;
+}
+
+template <int kThreads>
+AFB_DEVINL bool round_begin(const RoundParams& p, RoundShared<kThreads>& sh, const unsigned int round) {
+  RoundPull pl;
+  round_begin_issue<kThreads>(p, sh, round, pl);
+  return round_begin_complete<kThreads>(p, sh, round, pl);
 }
 
 // Phase 2b + 3.  Called by every thread after the CTA has flushed its partial gradient into
@@ -158,8 +186,46 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
   __syncthreads();
   if (tid == 0) sh.flag = atomicAdd(&wc->done_ctas, 1u);
   __syncthreads();
-  const bool is_last_cta = (sh.flag == gridDim.x - 1);
+  const unsigned int my_ticket = sh.flag;
+  const bool is_last_cta = (my_ticket == gridDim.x - 1);
   __syncthreads();                           // sh.flag is reused below
+
+  // K9 (part 1): the first CTA to finish takes the logical-clock ticket — staleness gate, accepted-update
+  // counter, step size — while the remaining CTAs are still draining; the last CTA only has to apply.
+  if (is_async && my_ticket == 0 && tid == 0) {
+    const unsigned long long ts = wc->ts;
+    unsigned long long old, k_old;
+    long long staleness;
+    int accept;
+    if (p.taw >= (1LL << 31)) {
+      // never stale: one NVLink round trip ticks clock and k together
+      old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, (1ULL << 32) | 1ULL);
+      k_old = old >> 32;
+      staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
+      accept = (static_cast<long long>(k_old) < p.max_iters) ? 1 : 0;
+    } else {
+      old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL);
+      staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
+      // ASGD compares the clock-based staleness (SparkASGDThread.scala:169); ASAGA compares
+      // k - ts (SparkASAGAThread.scala:184, quirk B.6) — both are available here.
+      long long cmp = staleness;
+      if (p.algo == ALGO_ASAGA) cmp = static_cast<long long>(old >> 32) - static_cast<long long>(ts);
+      accept = (cmp <= p.taw) ? 1 : 0;
+      k_old = old >> 32;
+      if (accept) {
+        unsigned long long o2 = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL << 32);
+        k_old = o2 >> 32;
+        if (static_cast<long long>(k_old) >= p.max_iters) accept = 0;
+      }
+    }
+    float step;
+    if (p.algo == ALGO_ASGD) step = p.gamma * rsqrtf(static_cast<float>(k_old / static_cast<unsigned long long>(p.num_workers)) + 1.f);
+    else step = p.gamma;
+    wc->tk_accept = accept; wc->tk_step = step; wc->tk_clock_old = static_cast<unsigned int>(old & 0xffffffffULL);
+    wc->tk_staleness = staleness; wc->tk_k_after = static_cast<long long>(k_old) + (accept ? 1 : 0);
+    __threadfence();
+    st_release_gpu_u32(&wc->tk_flag, round + 1u);
+  }
   if (!is_last_cta) return;
 
   // ------------------------------------------------------------------ phase 3 (last CTA): push-and-apply
@@ -180,42 +246,15 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
   }
 
   if (is_async) {
-    // K9 + K5/K6: staleness gate on the server's logical clock, then Hogwild reductions.
+    // K9 (part 2) + K5/K6: Hogwild reductions with the decision taken by the ticket holder.
     if (tid == 0) {
-      const unsigned long long ts = wc->ts;
-      unsigned long long old, k_old;
-      long long staleness;
-      int accept;
-      if (p.taw >= (1LL << 31)) {
-        // never stale: one NVLink round trip ticks clock and k together
-        old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, (1ULL << 32) | 1ULL);
-        k_old = old >> 32;
-        staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
-        accept = (static_cast<long long>(k_old) < p.max_iters) ? 1 : 0;
-      } else {
-        old = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL);
-        staleness = static_cast<long long>(old & 0xffffffffULL) - static_cast<long long>(ts);
-        // ASGD compares the clock-based staleness (SparkASGDThread.scala:169); ASAGA compares
-        // k - ts (SparkASAGAThread.scala:184, quirk B.6) — both are available here.
-        long long cmp = staleness;
-        if (p.algo == ALGO_ASAGA) cmp = static_cast<long long>(old >> 32) - static_cast<long long>(ts);
-        accept = (cmp <= p.taw) ? 1 : 0;
-        k_old = old >> 32;
-        if (accept) {
-          unsigned long long o2 = atom_add_acqrel_sys_u64(&p.sctl->clock_k, 1ULL << 32);
-          k_old = o2 >> 32;
-          if (static_cast<long long>(k_old) >= p.max_iters) accept = 0;
-        }
-      }
+      while (ld_acquire_gpu_u32(&wc->tk_flag) != round + 1u) __nanosleep(32);
       wc->dbg_ns[4] = globaltimer_ns();
-      float step;
-      if (p.algo == ALGO_ASGD) step = p.gamma * rsqrtf(static_cast<float>(k_old / static_cast<unsigned long long>(p.num_workers)) + 1.f);
-      else step = p.gamma;
-      sh.flag = static_cast<unsigned int>(accept);
-      sh.bcast[0] = step;
-      wc->last_staleness = staleness;
-      wc->last_k_after = static_cast<long long>(k_old) + (accept ? 1 : 0);
-      sh.bcast[1] = __uint_as_float(static_cast<unsigned int>(old & 0xffffffffULL));
+      sh.flag = static_cast<unsigned int>(*reinterpret_cast<volatile int*>(&wc->tk_accept));
+      sh.bcast[0] = *reinterpret_cast<volatile float*>(&wc->tk_step);
+      sh.bcast[1] = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(&wc->tk_clock_old));
+      wc->last_staleness = *reinterpret_cast<volatile long long*>(&wc->tk_staleness);
+      wc->last_k_after = *reinterpret_cast<volatile long long*>(&wc->tk_k_after);
     }
     __syncthreads();
     const int accept = static_cast<int>(sh.flag);

@@ -158,6 +158,12 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   }
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned int round = *reinterpret_cast<volatile unsigned int*>(&wc->round);   // protocol round (device truth)
+
+  // ------------------------------------------------------------------ phase 0a: elect the puller, put the pull in flight
+  RoundPull pl;
+  round_begin_issue<kThreads>(p, sh, round, pl);
+
+  // ... while the NVLink round trip is in flight: first dynamic chunk id + first row fetch
   if (early) {
     if (pdl && SAGA && rc >= 0) cur.h = p.hist[rc];
     sch.next_chunk = fetch_chunk(&wc->chunk_ctr, lane, sch.static_chunks);
@@ -167,10 +173,8 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
     }
   }
 
-  // ------------------------------------------------------------------ phase 0: gate + pull (one CTA)
-  if (p.algo != ALGO_GRAD_ONLY) {
-    if (!round_begin<kThreads>(p, sh, round)) return;
-  }
+  // ------------------------------------------------------------------ phase 0b: w_local / ts / seed published
+  if (!round_begin_complete<kThreads>(p, sh, round, pl)) return;
 
   // ------------------------------------------------------------------ phase 1: fused gradient
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate

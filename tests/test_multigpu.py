@@ -23,7 +23,7 @@ def test_fused_paths_on_all_visible_gpus():
     assert out["world"] == n and out["peer_read_ok"]
     assert out["sgd_sync_relerr"] < 2e-3 and out["saga_sync_relerr"] < 2e-3
     assert out["sgd_sync_replicas_identical"] and out["saga_sync_replicas_identical"]
-    for key, iters in (("asgd_tawinf", 60 * n), ("asaga_tawinf", 60 * n), ("asgd_taw0", 60 * n)):
+    for key, iters in (("asgd_tawinf", 60 * n), ("asaga_tawinf", 60 * n), ("asgd_taw0", 15 * n)):
         assert out[key + "_k"] >= iters and out[key + "_finite"]
         assert out[key + "_avail"] == n                       # every worker idle again
         assert out[key + "_loss_last"] < out[key + "_loss_first"]
