@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Regenerate profiles/README.md from the JSON results copied under profiles/bench/."""
+import glob
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+hbm = peaks["hbm_gbs"]
+
+
+def load(path):
+    try:
+        return json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def table(title, files):
+    out = [f"### {title}", "",
+           "| file | impl | algo | N | workers/GPU | iterations/s | ms/iteration | GB/s per GPU | of measured HBM | e2e iterations/s |",
+           "|---|---|---|---|---|---|---|---|---|---|"]
+    for f in files:
+        d = load(f)
+        if not d or "value" not in d:
+            continue
+        e2e = (d.get("e2e") or {}).get("value")
+        out.append(f"| {os.path.basename(f)} | {d['impl']} | {d['config']['model'].split()[0]} | {d['n_gpus']} | "
+                   f"{d['config'].get('workers_per_gpu')} | {d['value']:.1f} | {d['ms_per_step']:.4f} | {d['hbm_gbps_per_gpu']:.0f} | "
+                   f"{d['hbm_gbps_per_gpu'] / hbm * 100:.1f}% | {'' if e2e is None else f'{e2e:.1f}'} |")
+    return out + [""]
+
+
+out = ["# Measured results (B200, this repo)", "",
+       "All numbers are device-timed with CUDA events on the launching stream (worker streams fork/join on those events), max over",
+       "ranks, after warm-up; every round streams a fresh Bernoulli sample (inputs >> the 126 MB L2) out of HBM-resident shards;",
+       "SM clocks / throttle reasons are sampled through NVML during the timed region (none seen: 1965 MHz, `reasons: []`).",
+       f"Roofline denominator: measured copy bandwidth `hbm_gbs` = {hbm} GB/s from `MEASURED_PEAKS.json` (\"of measured\").",
+       "Headline workload (BASELINE.json config 2): ASGD logistic regression, mnist8m shape (8.1 M x 784 fp32), sampling rate 0.1;",
+       "one iteration = every worker completes one round = 810 000 rows sampled, gradient computed, pushed and applied.", ""]
+for run, title in (("run11", "Final build (prologue overlap, early clock ticket, PDL, guided scheduling) — 8-GPU box"),
+                   ("run9", "Previous build (guided scheduling + early prefetch + PDL) — 8-GPU box"),
+                   ("", "First scaling pass (register double-buffered kernel, 2 workers/GPU) — 8-GPU box")):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench", run, "*.json"))) if run else \
+        sorted(glob.glob(os.path.join(ROOT, "profiles", "bench", "sc_*.json")))
+    if files:
+        out += table(title, files)
+        ours = {}
+        nccl = {}
+        for f in files:
+            d = load(f)
+            if not d or "value" not in d:
+                continue
+            base = os.path.basename(f)
+            if d["impl"] == "ours" and d["config"]["model"].startswith("ASGD") and "_w1" not in base and "graph" not in base \
+                    and "nopdl" not in base and "seedk" not in base:
+                ours[d["n_gpus"]] = max(ours.get(d["n_gpus"], 0), d["value"])
+            if d["impl"] == "nccl":
+                nccl[d["n_gpus"]] = d["value"]
+        if 1 in ours:
+            out.append("Strong scaling (fixed 8.1 M-row dataset): " + ", ".join(
+                f"N={n}: {v:.0f} it/s ({v / ours[1] / n * 100:.0f} %)" for n, v in sorted(ours.items())))
+        if nccl:
+            out.append("")
+            out.append("vs the PyTorch + NCCL + cuBLAS baseline (`baseline/nccl_sync.py`, same box): " + ", ".join(
+                f"N={n}: {ours[n] / v:.1f}x" for n, v in sorted(nccl.items()) if n in ours))
+        out.append("")
+cfgs = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench", "*", "configs*.jsonl")))
+if cfgs:
+    out += ["## Other BASELINE configs (8 GPUs, `benchmarks/run_config.py`)", "",
+            "| config | algo | delay intensity | workers | iterations/s | ms/iteration | objective start -> end | mode |", "|---|---|---|---|---|---|---|---|"]
+    for c in cfgs:
+        for line in open(c):
+            r = json.loads(line)
+            out.append(f"| {r['config']} | {r['algo']} | {r['delay_intensity']} | {r['workers']} | {r['iterations_per_s']:.0f} | "
+                       f"{r['ms_per_iteration']:.4f} | {r['objective_start']:.4f} -> {r['objective_end']:.4f} | {r.get('mode', 'fixed rounds per worker')} ({os.path.basename(os.path.dirname(c))}) |")
+    out.append("")
+ev = os.path.join(ROOT, "profiles", "bench", "eval_bench_r1.log")
+if os.path.exists(ev):
+    out += ["## Objective evaluation (K12): tcgen05/TMEM GEMM vs exact CUDA-core kernel (1 GPU, 2 M x 784)", "",
+            "| T snapshots | tcgen05 ms | HBM GB/s | useful TFLOP/s | CUDA-core ms | speed-up | max rel. diff |", "|---|---|---|---|---|---|---|"]
+    for line in open(ev):
+        if line.startswith("EVAL_RESULT "):
+            r = json.loads(line[len("EVAL_RESULT "):])
+            out.append(f"| {r['T']} | {r['tc_ms']:.3f} | {r['tc_hbm_gbps']:.0f} | {r['tc_useful_tflops']:.1f} | {r['cc_ms']:.2f} | "
+                       f"{r['speedup']:.1f}x | {r['max_rel_diff']:.1e} |")
+    out += ["", "ncu (`eval_tc_r1_ncu_raw.csv`): 492 us for 3.14 GB read = 6.38 TB/s DRAM (78 % of ncu's nominal peak), tensor pipe active 16 %,",
+            "116 registers/thread, 2 TMEM accumulator buffers x 64 columns.", ""]
+out += ["## Kernel evidence", "",
+        "* `dense_round_r1_ncu_raw.csv`, `dense_round_r2_ncu_raw.csv` — `ncu --set full` raw metrics of the fused dense round kernel: 413-419 us",
+        "  under ncu, 2.62 GB DRAM read for 2.54 GB algorithmic bytes (3 % extra: labels, ids), DRAM throughput 76.5-77.7 % of ncu's nominal",
+        "  peak (6.25-6.35 TB/s), dominant stall `long_scoreboard` (HBM), tensor pipe 0 % (CUDA-core GEMV by design, DESIGN.md §2.1).",
+        "* `launches_r2.csv` — launch list of the timed region: only `dense_round_kernel<7,256>`, one launch per worker round.",
+        "* `sass/INDEX.md` + `sass/*.txt` — per-kernel SASS opcode histograms: `UTCHMMA`/`LDTM`/`UTMALDG` in `eval_tc_kernel`, `UBLKCP`/`SYNCS` in the",
+        "  TMA round variants, `REDG.E.ADD.F32x4...STRONG.SYS` + `LDG.E.128.STRONG.SYS` (NVLink peer reductions/loads) and",
+        "  `ATOMG.E.ADD.64.STRONG.SYS` (logical clock) in every round kernel, `ACQBULK`/`PREEXIT` (programmatic dependent launch).",
+        "* `sanitizer/` — compute-sanitizer memcheck / racecheck / synccheck summaries.", ""]
+open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(out) + "\n")
+print("profiles/README.md written,", len(out), "lines")
