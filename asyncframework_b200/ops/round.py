@@ -263,9 +263,10 @@ class RoundKernel:
         self.launches = 0
         self.rounds_launched = 0
         # programmatic dependent launch (simple dense variant, non-split, no rollback kernel in between):
-        # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail
+        # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail.
+        # Opt-in (AFB_PDL=1): measured +0.5 % at N=2 but -3 % at N=8 (profiles/README.md, run11), so off by default.
         self.use_pdl = (self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
-                        and os.environ.get("AFB_PDL", "1") == "1")
+                        and os.environ.get("AFB_PDL", "0") == "1")
         # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
         self.split = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
         if self.split:
