@@ -76,7 +76,13 @@ def evaluate_snapshots(engine: FusedEngine, shards: List[Shard], snaps: List[Tup
         dist.broadcast(W, 0)
     tot = torch.zeros(T, dtype=torch.float64, device=dev)
     for s in shards:
-        tot += eval_loss(s, W, LOSS_IDS[loss])
+        if s.device.type == "cuda":
+            tot += eval_loss(s, W, LOSS_IDS[loss])
+        else:
+            from ..optim.gradient import make_gradient
+            M = torch.stack([s.matvec(W[:, t]) for t in range(T)], dim=1).double()
+            _, L = make_gradient(loss).coefficients(M, s.y.double()[:, None].expand_as(M))
+            tot += L.sum(0)
     if engine.world > 1:
         dist.all_reduce(tot)
     vals = (tot / total_rows).tolist()
@@ -85,8 +91,12 @@ def evaluate_snapshots(engine: FusedEngine, shards: List[Shard], snaps: List[Tup
 
 def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
     rank, local_rank, world = init_distributed()
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
+    if torch.cuda.is_available():
+        device = torch.device("cuda", local_rank)
+        torch.cuda.set_device(device)
+    else:
+        # no GPU: the same host logic runs against the pure-Python round simulator (ops/round_sim.py)
+        device = torch.device("cpu")
     if cfg.num_partitions % world != 0:
         raise ValueError(f"num_partitions ({cfg.num_partitions}) must be a multiple of the number of ranks ({world})")
     metrics = MetricsLog(cfg.metrics_path if rank == 0 else None)

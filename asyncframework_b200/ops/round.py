@@ -134,6 +134,16 @@ class ServerPointers:
     def flags(self): return self.base + self.layout.off_flags
 
 
+class _SimLib:
+    """Stand-in for libafb_kernels.so when a RoundKernel runs against the CPU simulator."""
+
+    def afb_dense_round_max_ld(self): return 1 << 30
+    def afb_dense_round_ctas_per_sm(self, ld): return 2
+    def afb_dense_round_ring_max_ld(self): return 0
+    def afb_dense_round_pipe_max_ld(self): return 0
+    afb_dense_round_launch = afb_csr_round_launch = afb_dense_round_ring_launch = afb_dense_round_pipe_launch = None
+
+
 class RoundKernel:
     """One logical worker's fused round: ``launch()`` enqueues exactly one kernel."""
 
@@ -143,12 +153,15 @@ class RoundKernel:
                  delay_mode: int = 0, delay_coeff: float = 0.0, warmup_updates: int = 0,
                  local_block: Optional[ServerBlock] = None, peer_blocks: Optional[List[ServerPointers]] = None,
                  grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None,
-                 variant: Optional[str] = None, wctl: Optional[torch.Tensor] = None):
-        if shard.device.type != "cuda":
+                 variant: Optional[str] = None, wctl: Optional[torch.Tensor] = None, sim_server_block=None):
+        # CPU shards run against the pure-Python round simulator (ops/round_sim.py): same byte layouts and
+        # protocol, used by the CPU test-suite; CUDA shards always run the hand-written kernels.
+        self.sim = shard.device.type != "cuda"
+        if self.sim and os.environ.get("AFB_ALLOW_SIM", "1") != "1":
             raise ValueError("RoundKernel needs an HBM-resident shard")
         if shard.dtype != torch.float32:
             raise TypeError("fused kernels are fp32 (storage and accumulate)")
-        self.lib = kernels()
+        self.lib = kernels() if not self.sim else _SimLib()
         self.shard = shard
         self.device = shard.device
         self.algo = algo
@@ -236,8 +249,7 @@ class RoundKernel:
                 seed_mode = 1
         p.seed_mode = int(seed_mode); p.loss_id = int(loss_id)
         self.params = p
-        props = torch.cuda.get_device_properties(dev)
-        self.num_sms = props.multi_processor_count
+        self.num_sms = torch.cuda.get_device_properties(dev).multi_processor_count if not self.sim else 148
         # resident-CTA capacity of the kernel on this device; `grid` (if given) is the share of it
         # this logical worker should occupy when several workers co-run on one GPU
         self.ctas_per_sm = self.lib.afb_dense_round_ctas_per_sm(ld) if self.is_dense else 2
@@ -262,13 +274,16 @@ class RoundKernel:
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         self.launches = 0
         self.rounds_launched = 0
+        if self.sim:
+            from .round_sim import RoundSim
+            self._sim = RoundSim(self, sim_server_block)
         # programmatic dependent launch (simple dense variant, non-split, no rollback kernel in between):
         # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail.
         # Opt-in (AFB_PDL=1): measured +0.5 % at N=2 but -3 % at N=8 (profiles/README.md, run11), so off by default.
-        self.use_pdl = (self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
+        self.use_pdl = (not self.sim and self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
                         and os.environ.get("AFB_PDL", "0") == "1")
         # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
-        self.split = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
+        self.split = (not self.sim) and (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
         if self.split:
             pg = RoundParams.from_buffer_copy(bytes(p))
             pg.algo = ALGO["grad_only"]
@@ -278,7 +293,12 @@ class RoundKernel:
             self.comm_grid = max(1, min(self.num_sms, (ld // 4 + 255) // 256))
 
     # ------------------------------------------------------------------
-    def launch(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+    def launch(self, stream=None) -> None:
+        if self.sim:
+            self._sim.launch()
+            self.launches += 1
+            self.rounds_launched += 1
+            return
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         if self.split:
             sp = int(s.cuda_stream)

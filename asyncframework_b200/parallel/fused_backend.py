@@ -29,6 +29,7 @@ from ..data.batch import Shard
 from ..ops._signatures import RESULT_REC_DTYPE, WORKER_CTL_DTYPE
 from ..ops.round import NEVER_STALE, RoundKernel, ServerBlock, ServerLayout, ServerPointers
 from ..optim.gradient import LOSS_IDS
+from . import _devapi as _dev
 from .comm import SymmetricBuffer, allocate_symmetric
 
 _CUDART = None
@@ -113,7 +114,7 @@ class FusedEngine:
         normal, long_tail = straggler_sets(self.P) if cfg.production_cluster else ([], [])
         warm = cfg.warmup_updates_per_worker * (self.P if self.is_async else 1)
         n_local = len(self.local_worker_ids)
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        sms = _dev.device_sms(self.device)
         self.kernels: List[RoundKernel] = []
         self.streams: List[torch.cuda.Stream] = []
         self.wctl_all = torch.zeros(n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
@@ -135,20 +136,19 @@ class FusedEngine:
                              max_iters=cfg.num_iterations if self.is_async else (1 << 40),
                              gate_threshold=gate, delay_mode=dmode, delay_coeff=max(cfg.coeff, 0.0),
                              warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid,
-                             wctl=self.wctl_all[li])
+                             wctl=self.wctl_all[li], sim_server_block=self.block if self.device.type != "cuda" else None)
             self.kernels.append(rk)
-            self.streams.append(torch.cuda.Stream(device=self.device) if n_local > 1 else torch.cuda.current_stream(self.device))
+            self.streams.append(_dev.new_stream(self.device) if n_local > 1 else _dev.current_stream(self.device))
         # pinned staging for the end-to-end path (double-buffered: step i+1 is submitted before the
         # result of step i is read, so the per-step host work never idles the GPU)
-        self._desc_host = torch.zeros(2, 16, dtype=torch.float32).pin_memory()
+        self._desc_host = _dev.pin(torch.zeros(2, 16, dtype=torch.float32), self.device)
         self._desc_np = self._desc_host.numpy()
         self._desc_dev = torch.zeros(2, 16, dtype=torch.float32, device=self.device)
-        self._ctl_host = torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self._ctl_host = _dev.pin(torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8), self.device)
         self._ctl_np = self._ctl_host.numpy()
-        self._step_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._step_events = [_dev.new_event(self.device), _dev.new_event(self.device)]
         self._step_pending = [False, False]
         self._step_idx = 0
-        self._io_stream = torch.cuda.Stream(device=self.device)
         self._ring_seen = 0
         self.rounds_enqueued = 0
         self._graph = None
@@ -175,6 +175,8 @@ class FusedEngine:
         changes from round to round (round counter, seeds, step size via k, stop condition) lives in
         device memory, so a replay is exactly ``run_rounds(rounds)`` with one host call — this removes
         the launch-bound regime for small rounds (epsilon / rcv1 shapes)."""
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
         self.synchronize()
         cap = torch.cuda.Stream(device=self.device)
         g = torch.cuda.CUDAGraph()
@@ -233,19 +235,19 @@ class FusedEngine:
                 continue
             check(kernels().afb_sleep(int(period_us * 1e3 * j / n), int(st.cuda_stream)), "stagger")
 
-    def fork(self, event: torch.cuda.Event) -> None:
+    def fork(self, event) -> None:
         """Make every worker stream wait for ``event`` (recorded on the launching stream)."""
-        cur = torch.cuda.current_stream(self.device)
+        cur = _dev.current_stream(self.device)
         for st in self.streams:
             if st != cur:
                 st.wait_event(event)
 
     def join(self) -> None:
         """Make the launching stream wait for everything enqueued on the worker streams."""
-        cur = torch.cuda.current_stream(self.device)
+        cur = _dev.current_stream(self.device)
         for st in self.streams:
             if st != cur:
-                ev = torch.cuda.Event()
+                ev = _dev.new_event(self.device)
                 ev.record(st)
                 cur.wait_event(ev)
 
@@ -275,11 +277,11 @@ class FusedEngine:
         d[1] = self.cfg.batch_rate
         d[2] = self.cfg.coeff
         d[3] = float(self.rounds_enqueued)
-        cur = torch.cuda.current_stream(self.device)
+        cur = _dev.current_stream(self.device)
         self._desc_dev[slot].copy_(self._desc_host[slot], non_blocking=True)            # H2D (pinned)
         multi = len(self.kernels) > 1
         if multi:
-            fork = torch.cuda.Event()
+            fork = _dev.new_event(self.device)
             fork.record(cur)
         for rk, st in zip(self.kernels, self.streams):
             if multi and st != cur:
@@ -394,8 +396,13 @@ class FusedEngine:
             raise ValueError("history_slots == 0: versioned broadcast disabled")
         self.synchronize()
         self.barrier()
-        version = int(self.block.version_words[0].item()) + (0 if self.rank else 0)
+        version = int(self.block.version_words[0].item())
         slot = version % K
+        if self.device.type != "cuda":
+            # simulator: every rank == this process; the "multicast" is a tensor copy + version bump
+            self.block.hist_w[slot].copy_(self.block.w)
+            self.block.version_words[0] += 1
+            return version
         if self.rank == 0:
             lib = kernels()
             st = torch.cuda.current_stream(self.device).cuda_stream
@@ -434,12 +441,12 @@ class FusedEngine:
         import threading
 
         stop = threading.Event()
-        side = torch.cuda.Stream(device=self.device)
+        side = _dev.new_stream(self.device)
 
         def pump():
-            torch.cuda.set_device(self.device)
+            _dev.set_device(self.device)
             while not stop.is_set():
-                with torch.cuda.stream(side):
+                with _dev.stream_ctx(side, self.device):
                     ring = self.block.ring.cpu().numpy().view(RESULT_REC_DTYPE)
                     status = self.block.read_status()
                 n = self.layout.ring_size

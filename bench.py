@@ -47,6 +47,8 @@ def parse():
 
 
 def reference_unavailable():
+    if int(os.environ.get("RANK", "0")) != 0:      # under torchrun only rank 0 reports
+        return 0
     print(json.dumps({"impl": "reference", "unavailable":
                       "reference is a JVM/Scala Apache Spark 2.3.2 fork (no setup.py/pyproject, `pip install /root/reference` "
                       "fails: not installable) and this image has no Java/Scala/sbt; it has no GPU code path"}))

@@ -1,0 +1,155 @@
+"""The fused backend's host logic against the pure-Python round simulator (no GPU needed):
+the simulator itself is checked against the NumPy oracle, then FusedEngine / run_fused / the result
+pump / checkpointing run on top of it."""
+import math
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from asyncframework_b200 import algo
+from asyncframework_b200.algo.oracle import AsyncOracle, run_asaga_oracle, run_asgd_oracle, run_saga_sync_oracle, run_sgd_sync_oracle
+from asyncframework_b200.config import AsyncConfig
+from asyncframework_b200.core import AsyncContext
+from asyncframework_b200.data.batch import Shard, padded_ld
+from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+from asyncframework_b200.optim.gradient import LOSS_IDS
+from asyncframework_b200.parallel.fused_backend import FusedEngine
+
+
+def _parts(P, n, d, seed, labels01):
+    rng = np.random.RandomState(seed)
+    wstar = rng.randn(d) * 0.5
+    out, off = [], 0
+    for p in range(P):
+        X = (rng.randn(n, d) * 0.4).astype(np.float32).astype(np.float64)
+        y = ((rng.rand(n) < 1 / (1 + np.exp(-X @ wstar))).astype(np.float64) if labels01
+             else (X @ wstar + 0.05 * rng.randn(n)).astype(np.float32).astype(np.float64))
+        out.append((X, y, np.arange(n) + off))
+        off += n
+    return out
+
+
+def _shard(part, d, p):
+    X, y, g = part
+    Xp = torch.zeros(X.shape[0], padded_ld(d), dtype=torch.float32)
+    Xp[:, :d] = torch.from_numpy(X).float()
+    return Shard(d, torch.from_numpy(y).float(), Xp, gidx=torch.from_numpy(g), partition=p)
+
+
+@pytest.mark.parametrize("algo_name,loss,gamma", [("asgd", "logistic", 0.8), ("asaga", "least_squares", 0.05)])
+def test_simulated_round_matches_oracle_single_worker(algo_name, loss, gamma):
+    d, n = 30, 800
+    parts = _parts(1, n, d, 3, loss == "logistic")
+    sh = _shard(parts[0], d, 0)
+    layout = ServerLayout(sh.ld, 1, ring_size=64)
+    blk = ServerBlock.allocate(layout, "cpu")
+    blk.reset()
+    rk = RoundKernel(sh, ServerPointers(blk.buf.data_ptr(), layout), algo=algo_name, loss_id=LOSS_IDS[loss], num_workers=1,
+                     worker_id=0, total_rows=n, batch_rate=0.3, gamma=gamma, seed=42, seed_mode=0, sim_server_block=blk)
+    assert rk.sim
+    for _ in range(6):
+        rk.launch()
+    events = []
+    for _ in range(6):
+        events += [("submit", [0]), ("complete", 0)]
+    orc = AsyncOracle(parts, loss, 0.3, gamma, 10**9, 42)
+    ref = (run_asgd_oracle if algo_name == "asgd" else run_asaga_oracle)(orc, events, 10**6)
+    assert np.allclose(blk.w[:d].double().numpy(), ref.w, rtol=2e-4, atol=1e-6)
+    st = blk.read_sctl()
+    assert st["k"] == 6 and st["clock"] == 6 and st["avail_count"] == 1
+    ring = blk.read_ring()
+    assert [int(r["seq"]) for r in ring[:6]] == [1, 2, 3, 4, 5, 6]
+
+
+def test_simulated_bsp_matches_sync_oracle():
+    d, n = 20, 600
+    for algo_name, loss, gamma, fn in (("sgd_sync", "logistic", 0.7, run_sgd_sync_oracle), ("saga_sync", "least_squares", 0.05, run_saga_sync_oracle)):
+        parts = _parts(1, n, d, 5, loss == "logistic")
+        cfg = AsyncConfig(algorithm=algo_name, num_features=d, num_rows=n, num_partitions=1, num_iterations=12, step_size=gamma,
+                          batch_rate=0.4, loss=loss, seed=42, backend="fused")
+        eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+        eng.run_rounds(12)
+        ref = fn(AsyncOracle(parts, loss, 0.4, gamma, 10**9, 42), 12)
+        assert np.allclose(eng.weights().double().numpy(), ref.w, rtol=2e-4, atol=1e-6)
+
+
+def test_fused_engine_protocol_on_simulator():
+    """4 logical workers interleaved on one simulated server: clock/k/staleness/availability/ring invariants,
+    the max_iters stop, the taw filter and the AsyncContext result pump."""
+    P, d, n = 4, 24, 500
+    parts = _parts(P, n, d, 9, True)
+    shards = [_shard(parts[p], d, p) for p in range(P)]
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n * P, num_partitions=P, num_iterations=50, step_size=0.8,
+                      batch_rate=0.3, loss="logistic", seed=1, backend="fused", barrier="asp", history_slots=2)
+    eng = FusedEngine(cfg, shards, n * P, list(range(P)), device="cpu")
+    ctx = AsyncContext(P)
+    eng.start_result_pump(ctx, period_s=0.001)
+    losses = []
+    for _ in range(20):
+        r = eng.step()
+        if r["batch"]:
+            losses.append(r["loss_sum"] / r["batch"])
+    st = eng.server_state()
+    assert st["k"] == 50 and st["clock"] == 50 and st["avail_count"] == P          # stops exactly at max_iters
+    assert losses[-1] < losses[0]
+    got = []
+    t0 = time.time()
+    while len(got) < 50 and time.time() - t0 < 5:
+        r = ctx.collect_all(timeout=0.2)
+        if r is not None:
+            got.append(r)
+    eng.stop_result_pump()
+    assert len(got) == 50 and [r.data["k_after"] for r in got] == list(range(1, 51))
+    assert sorted({r.worker_id for r in got}) == list(range(P))
+    assert all(r.staleness == 0 for r in got)            # sequential launches: nobody merges between a pull and its push
+    assert ctx.stat.available_workers() == P
+    v0 = eng.publish_version()
+    eng.block.w.add_(1.0)
+    v1 = eng.publish_version()
+    assert (v0, v1) == (0, 1) and torch.allclose(eng.version_value(v1) - eng.version_value(v0), torch.ones(d))
+    with pytest.raises(RuntimeError):
+        eng.build_graph(2)
+
+
+def test_staleness_filter_and_saga_rollback_on_simulator():
+    """A result whose staleness exceeds taw must tick the clock, NOT the accepted-update counter, leave w
+    untouched and roll the worker's SAGA history back (SparkASAGAThread.scala:184-231)."""
+    P, d, n = 2, 10, 300
+    parts = _parts(P, n, d, 4, False)
+    layout = ServerLayout(padded_ld(d), P, ring_size=32)
+    blk = ServerBlock.allocate(layout, "cpu")
+    blk.reset()
+
+    def mk(p):
+        return RoundKernel(_shard(parts[p], d, p), ServerPointers(blk.buf.data_ptr(), layout), algo="asaga",
+                           loss_id=LOSS_IDS["least_squares"], num_workers=P, worker_id=p, total_rows=n * P, batch_rate=0.5,
+                           gamma=0.05, seed=7, taw=0, sim_server_block=blk)
+    a, b = mk(0), mk(1)
+    assert a.rollback and b.rollback
+    a.launch()                                        # accepted: k 0 -> 1
+    w_after_a = blk.w.clone()
+    hist_before = b.hist.clone()
+    b.params.taw = -1                                 # a sequential model cannot interleave: force "too stale"
+    b.launch()
+    st = blk.read_sctl()
+    assert st["k"] == 1 and st["clock"] == 2          # merged (clock ticks) but not accepted
+    assert torch.equal(blk.w, w_after_a)              # w untouched
+    assert torch.equal(b.hist, hist_before)           # history rolled back
+    assert b.read_ctl()["last_accepted"] == 0 and int(blk.read_ring()[1]["accepted"]) == 0
+    assert st["avail_count"] == P                     # the worker is re-queued (available again)
+
+
+@pytest.mark.parametrize("alg,step,P", [("asgd", 1.0, 4), ("asaga", 0.05, 4), ("sgd_sync", 1.0, 1), ("saga_sync", 0.3, 1)])
+def test_fused_driver_on_simulator(alg, step, P, tmp_path):
+    cfg = AsyncConfig(algorithm=alg, synthetic="linear", num_rows=2000, num_features=12, num_partitions=P,
+                      num_iterations=300 if P > 1 else 100, step_size=step, batch_rate=0.2, printer_freq=100, backend="fused",
+                      loss="least_squares", barrier="asp", rounds_per_graph=5, layout="dense",
+                      checkpoint_dir=str(tmp_path / "ck"), checkpoint_every=100)
+    rep = algo.run(cfg)
+    objs = [o for _, o in rep.objective]
+    assert rep.iterations >= cfg.num_iterations and objs[0] > 0.3 and objs[-1] < 0.05
+    from asyncframework_b200.utils import load_checkpoint
+    ck = load_checkpoint(str(tmp_path / "ck"))
+    assert ck["k"] >= 100 and ck["w"].numel() == 12
