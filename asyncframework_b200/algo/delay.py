@@ -43,6 +43,15 @@ class DelayInjector:
         self._rng = rng or random.Random()
         self.injected_ms = 0.0
 
+    def __getstate__(self):          # shipped inside task closures to executor processes
+        st = dict(self.__dict__)
+        st["_lock"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._lock = threading.Lock()
+
     @property
     def mode(self) -> str:
         return "production" if self.production else ("controlled" if self.coeff > 0 else "none")

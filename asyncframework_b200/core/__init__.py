@@ -3,8 +3,9 @@ from .partial_result import PartialResult
 from .worker_state import StatTable, WorkerState
 from .broadcast import AsyncBroadcast, Broadcast
 from .scheduler import JobFailed, JobWaiter, Scheduler, TaskContext
+from .cluster import ClusterScheduler
 from .session import AsyncSession
 from . import barriers, sampler
 
 __all__ = ["AsyncContext", "QueueClosed", "PartialResult", "StatTable", "WorkerState", "AsyncBroadcast",
-           "Broadcast", "JobFailed", "JobWaiter", "Scheduler", "TaskContext", "AsyncSession", "barriers", "sampler"]
+           "Broadcast", "JobFailed", "JobWaiter", "Scheduler", "TaskContext", "AsyncSession", "ClusterScheduler", "barriers", "sampler"]

@@ -21,6 +21,7 @@ from .context import AsyncContext
 from .scheduler import Scheduler
 
 _LOCAL_N = re.compile(r"^local\[(\*|\d+)(?:\s*,\s*(\d+))?\]$")
+_LOCAL_CLUSTER = re.compile(r"^local-cluster\[\s*(\d+)\s*(?:,\s*(\d+)\s*(?:,\s*(\d+)\s*)?)?\]$")
 
 
 class AsyncSession:
@@ -31,7 +32,11 @@ class AsyncSession:
         self.conf = conf or AsyncConfig()
         n, max_fail = self._parse_master(master)
         self.device = torch.device(device) if device is not None else None
-        self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name)
+        if master.startswith("local-cluster"):
+            from .cluster import ClusterScheduler
+            self.scheduler = ClusterScheduler(n, max_failures=max_fail, name=app_name)
+        else:
+            self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name)
         self._stopped = False
 
     @staticmethod
@@ -42,6 +47,9 @@ class AsyncSession:
         if m:
             n = (os.cpu_count() or 1) if m.group(1) == "*" else int(m.group(1))
             return max(1, n), int(m.group(2)) if m.group(2) else 4
+        m = _LOCAL_CLUSTER.match(master)
+        if m:                                  # local-cluster[numExecutors, coresPerExecutor, memoryMB]
+            return max(1, int(m.group(1))), 4
         if master in ("fused", "gloo"):
             return 1, 4
         raise ValueError(f"Could not parse Master URL: '{master}'")

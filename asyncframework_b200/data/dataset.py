@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
 import threading
 import time
 from typing import Any, Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
@@ -29,7 +30,27 @@ from ..core.partial_result import PartialResult
 from ..linalg.vectors import DenseVector, LabeledPoint, SparseVector, Vector
 from .batch import Shard, concat_shards, padded_ld
 
-_EMPTY = object()
+class _Empty:
+    """Picklable singleton marker for "no value" (survives a trip through an executor process)."""
+    _inst = None
+
+    def __new__(cls):
+        if cls._inst is None:
+            cls._inst = super().__new__(cls)
+        return cls._inst
+
+    def __reduce__(self):
+        return (_Empty, ())
+
+    def __repr__(self):
+        return "<EMPTY>"
+
+
+_EMPTY = _Empty()
+_ds_ids = itertools.count(1)
+# executor-side block store: cached partitions keyed by (dataset id, partition, kind); lives in whichever
+# process evaluates the partition (BlockManager MEMORY_ONLY analogue for the process-based scheduler)
+_BLOCK_STORE: dict = {}
 
 
 class ShardedDataset:
@@ -48,6 +69,7 @@ class ShardedDataset:
         self._want_cache = False
         self._cache_lock = threading.Lock()
         self.selected_workers: Optional[List[int]] = None   # set by async_barrier
+        self.ds_id = (os.getpid() << 32) | next(_ds_ids)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -96,9 +118,24 @@ class ShardedDataset:
     def batch_capable(self) -> bool:
         return self._batch is not None
 
+    # -- pickling (task binaries shipped to executor processes): the scheduler and locks stay behind ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["scheduler"] = None
+        st["_cache_lock"] = None
+        st["_cached_batches"] = None
+        st["_cached_records"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._cache_lock = threading.Lock()
+
     def iterator(self, p: int, tctx=None) -> Iterator:
         if self._cached_records is not None and self._cached_records[p] is not None:
             return iter(self._cached_records[p])
+        if self._want_cache and (self.ds_id, p, "r") in _BLOCK_STORE:
+            return iter(_BLOCK_STORE[(self.ds_id, p, "r")])
         if self._compute is not None:
             it = self._compute(p, tctx)
         else:
@@ -110,6 +147,7 @@ class ShardedDataset:
                 if self._cached_records is None:
                     self._cached_records = [None] * self.num_partitions
                 self._cached_records[p] = recs
+            _BLOCK_STORE[(self.ds_id, p, "r")] = recs
             return iter(recs)
         return it
 
@@ -118,12 +156,15 @@ class ShardedDataset:
             raise TypeError(f"dataset {self.name!r} has no batch-level view (a record-level map broke the columnar lineage)")
         if self._cached_batches is not None and self._cached_batches[p] is not _EMPTY:
             return self._cached_batches[p]
+        if self._want_cache and (self.ds_id, p, "b") in _BLOCK_STORE:
+            return _BLOCK_STORE[(self.ds_id, p, "b")]
         b = self._batch(p, tctx)
         if self._want_cache:
             with self._cache_lock:
                 if self._cached_batches is None:
                     self._cached_batches = [_EMPTY] * self.num_partitions
                 self._cached_batches[p] = b
+            _BLOCK_STORE[(self.ds_id, p, "b")] = b
         return b
 
     def cache(self) -> "ShardedDataset":
