@@ -49,3 +49,23 @@ def test_trace_recorder(tmp_path):
         assert len(d["traceEvents"]) == 4 and d["counters"]["tasks"] == 4 and d["counters"]["jobs"] == 1
     finally:
         s.stop()
+
+
+def test_event_log_replay(tmp_path):
+    from asyncframework_b200.utils.eventlog import EventLog, replay, summarize
+    s = Scheduler(2, max_failures=3)
+    try:
+        log = EventLog(str(tmp_path / "events.jsonl")).attach(s)
+        ds = ShardedDataset.from_records(s, list(range(12)), 3)
+        ds.count()
+        s.fault_injector = lambda t: (_ for _ in ()).throw(RuntimeError("x")) if (t.partition_id == 2 and t.attempt == 0) else None
+        ds.map(lambda x: x + 1).count()
+        log.close()
+        jobs = replay(str(tmp_path / "events.jsonl"))
+        assert len(jobs) == 2
+        a, b = [jobs[k] for k in sorted(jobs)]
+        assert a["tasks"] == 3 and a["failures"] == 0 and a["finished"] and a["executors"] == [0, 1]
+        assert b["tasks"] == 3 and b["failures"] == 1 and b["finished"]
+        assert len(summarize(str(tmp_path / "events.jsonl"))) == 2
+    finally:
+        s.stop()
