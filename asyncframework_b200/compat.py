@@ -1,0 +1,101 @@
+"""Reference-spelling compatibility layer: the Scala names of the ASYNC API on top of this framework, so a
+program written against ASYNCframework/ASYNCframework can be transcribed line by line.
+
+    from asyncframework_b200.compat import *
+    sc = SparkContext("local[8]")
+    points = MLUtils.loadLibSVMFile(sc, path).repartition(numPart)
+    AC = ASYNCcontext(numPart, sc)
+    ...
+    pointsIndexed.ASYNCbarrier(f, AC.STAT).sample(False, b, seed + k + 1).map(...).ASYNCreduce(comOp, AC)
+    info = AC.ASYNCcollectAll(); info.getStaleness(); info.gettaskResult(); info.getWorkerID()
+
+Reference symbols: core/rdd/ASYNCcontext.scala, workerState.scala, RDDPartialRes.scala, RDD.scala:1044-1345,
+broadcast/ASYNCbroadcast.scala, mllib/BLASUtil.scala, mllib/util/MLUtils.scala.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+from .core.broadcast import AsyncBroadcast as _AsyncBroadcast
+from .core.context import AsyncContext as _AsyncContext
+from .core.partial_result import PartialResult as RDDPartialRes
+from .core.session import AsyncSession as _AsyncSession
+from .core.worker_state import WorkerState as workerState
+from .data.dataset import ShardedDataset as RDD
+from .data.libsvm import MLUtils as _MLUtils
+from .linalg import DenseVector, LabeledPoint, SparseVector, Vectors  # noqa: F401
+from .linalg.blas_util import axpy_op as axpyOp, dot_op as dotOp, scal_op as scalOp  # noqa: F401
+from .models import LinearRegressionWithSGD, LogisticRegressionWithSGD, SVMWithSGD  # noqa: F401
+from .optim import (GradientDescent, HingeGradient, L1Updater, LeastSquaresGradient, LogisticGradient,  # noqa: F401
+                    SimpleUpdater, SquaredL2Updater)
+
+
+class SparkContext(_AsyncSession):
+    """``new SparkContext(conf)`` — master URL as first argument; ``setLogLevel``, ``set_mode``, ``broadcast``,
+    ``parallelize``, ``textFile``."""
+
+    def setLogLevel(self, level: str) -> None:
+        self.set_log_level(level)
+
+    def textFile(self, path: str, minPartitions: Optional[int] = None):
+        return self.text_file(path, minPartitions)
+
+
+class ASYNCcontext(_AsyncContext):
+    """``new ASYNCcontext[T]()``; pass the SparkContext (or a scheduler) so ``set_mode`` reaches it."""
+
+    def __init__(self, num_workers: int, sc: Any = None):
+        super().__init__(num_workers, getattr(sc, "scheduler", sc))
+
+    def getSize(self) -> int: return self.size()
+    def hasNext(self) -> bool: return self.has_next()
+    def getCurrentTime(self) -> int: return self.current_time
+    def setCurrentTime(self, t: int) -> None: self.current_time = t
+    def add2currentTime(self, t: int) -> None: self.add_to_current_time(t)
+    def setLastTime(self, t: int) -> None: self.last_time = t
+    def isOld(self) -> bool: return self.is_old()
+    def setRecordStat(self, b: bool) -> None: self.set_record_stat(b)
+    def getRecordStat(self) -> bool: return self.record_stat
+
+
+class ASYNCbroadcast(_AsyncBroadcast):
+    """``new ASYNCbroadcast(sc, w)`` needs the context that owns the version ring: pass the ASYNCcontext."""
+
+    def __init__(self, ctx, value, slots: int = 8):
+        super().__init__(ctx, value, slots)
+
+    def getIndex(self) -> int: return self.index
+    def setID(self, i: int) -> None: self.set_id(i)
+
+
+class MLUtils(_MLUtils):
+    @staticmethod
+    def loadLibSVMFile(sc, path: str, numFeatures: int = -1, minPartitions: Optional[int] = None, **kw):
+        return sc.load_libsvm_file(path, numFeatures, minPartitions, **kw)
+
+    @staticmethod
+    def saveAsLibSVMFile(data, dir_path: str) -> None:
+        from .data.libsvm import save_as_libsvm_file
+        save_as_libsvm_file(data, dir_path)
+
+
+# --- camelCase accessors on the shared classes (added once, idempotent) -----------------------------------
+def _alias(cls, **names):
+    for new, old in names.items():
+        if not hasattr(cls, new):
+            setattr(cls, new, getattr(cls, old) if isinstance(old, str) else old)
+
+
+_alias(RDDPartialRes, gettaskResult="get_task_result", getStaleness="get_staleness", getbatchSize="get_batch_size",
+       getWorkerID="get_worker_id", getTimestamp="get_timestamp")
+_alias(workerState, getStaleness=lambda self: self.staleness, getAvailability=lambda self: self.available,
+       getNumTasks=lambda self: self.num_tasks, getAverageTaskTime=lambda self: self.avg_task_time_ms,
+       getAvailableWorkers=lambda self: self.available_workers(), getMaxStaleness=lambda self: self.max_staleness(),
+       setAvailability=lambda self, v: setattr(self, "available", v))
+_alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partitions_with_index", getNumPartitions="get_num_partitions",
+       treeAggregate="tree_aggregate", flatMap="flat_map", mapPartitions="map_partitions", foreachPartition="foreach_partition")
+
+__all__ = ["SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",
+           "DenseVector", "SparseVector", "LabeledPoint", "axpyOp", "dotOp", "scalOp", "GradientDescent", "LeastSquaresGradient",
+           "LogisticGradient", "HingeGradient", "SimpleUpdater", "L1Updater", "SquaredL2Updater", "LinearRegressionWithSGD",
+           "LogisticRegressionWithSGD", "SVMWithSGD"]

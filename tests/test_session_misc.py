@@ -59,3 +59,19 @@ def test_launcher_runs_driver_inline(capsys):
     rc = launch.main(["--gpus", "1", "sgd_sync", "x", "x", "10", "400", "2", "15", "1.0", "0.3", "5", "0", "42",
                       "--synthetic=linear", "--backend=cpu"])
     assert rc == 0
+
+
+def test_compat_layer_and_transcribed_example():
+    import importlib.util
+    import os
+    from asyncframework_b200 import compat
+    assert issubclass(compat.ASYNCcontext, compat._AsyncContext) and hasattr(compat.RDD, "ASYNCreduce")
+    for name in ("gettaskResult", "getStaleness", "getbatchSize", "getWorkerID"):
+        assert hasattr(compat.RDDPartialRes, name)
+    for name in ("getStaleness", "getAvailability", "getNumTasks", "getAvailableWorkers", "getMaxStaleness"):
+        assert hasattr(compat.workerState, name)
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("spark_asgd_sync", os.path.join(here, "examples", "spark_asgd_sync.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(numIteration=25) < 0.1            # record-level closures, the reference's own spelling
