@@ -107,7 +107,7 @@ class ShardedDataset:
         ld = padded_ld(d)
         shards = []
         for p in range(num_partitions):   # round-robin like repartition
-            rows = torch.arange(p, n, num_partitions)
+            rows = torch.arange(p, n, num_partitions) if p < n else torch.zeros(0, dtype=torch.int64)
             Xp = torch.zeros(rows.numel(), ld, dtype=dtype)
             Xp[:, :d] = X[rows]
             shards.append(Shard(d, y[rows].clone(), Xp, partition=p).to(device))
@@ -285,6 +285,8 @@ class ShardedDataset:
             for o in olds:
                 for q in range(P):
                     first = (q - start) % P
+                    if first >= o.num_rows:
+                        continue
                     rows = torch.arange(first, o.num_rows, P)
                     if rows.numel():
                         buckets[q].append(o.select(rows))
