@@ -97,6 +97,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
 
         need = math.floor(P * cfg.bucket_ratio)
         pred = barriers.bucket(P, cfg.bucket_ratio)
+        last_k, resubmits = -1, 0
         while state["k"] < iters:
             k = state["k"]
             init_workers = P if k == 0 else AC.stat.available_workers()
@@ -109,7 +110,12 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                     time.sleep(0.001)
                     continue
                 delayed = filtered.map_partitions_with_index(delay.hook(), preserves_batch=True)
-                sampled = delayed.sample(False, b, cfg.seed + k + 1)
+                # seed = seed + k + 1 as in the reference; if k has not advanced since the last submission
+                # (every sampled partition came back empty) perturb it, otherwise the identical empty sample
+                # would be redrawn forever (tiny b*N/P only)
+                resubmits = resubmits + 1 if k == last_k else 0
+                last_k = k
+                sampled = delayed.sample(False, b, cfg.seed + k + 1 + 7919 * resubmits)
                 index_grad = sampled.map_batch(lambda s, a=a: partition_gradient(gradient, s, a.value)[0])
                 index_grad.async_reduce(lambda x, y: x.add_(y), AC)
                 waits.on_submit(workers, now_ms())

@@ -170,8 +170,11 @@ def run_async_gloo(cfg: AsyncConfig):
     # worker loop (rank 0 is also a worker and talks to the server state directly)
     w_local = torch.zeros(d, dtype=torch.float64)
     ts, k_seen = 0, 0
+    last_k, resubmits = -1, 0
     while True:
-        rows = _sampled(shard, cfg.seed + k_seen + 1, cfg.batch_rate)
+        resubmits = resubmits + 1 if k_seen == last_k else 0       # same empty-sample guard as algo/asgd.py
+        last_k = k_seen
+        rows = _sampled(shard, cfg.seed + k_seen + 1 + 7919 * resubmits, cfg.batch_rate)
         if rows.numel():
             sub = shard.select(rows)
             g, l, n, coeff = grad.batch(sub, w_local, hist[rows] if saga else None)
