@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--loss", default="logistic")
     ap.add_argument("--shape", default="mnist8m")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                    help="cpu = contract smoke-test against the pure-Python round simulator (NOT a benchmark)")
     ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe", "ring"], help="dense kernel variant (default: env/auto)")
     ap.add_argument("--graph", type=int, default=0, help="replay a CUDA graph of this many rounds (0 = plain launches)")
     ap.add_argument("--stagger-us", type=float, default=0.0, help="one-time phase offset between co-located workers")
@@ -77,8 +79,9 @@ def main() -> int:
     if args.variant:
         os.environ["AFB_DENSE_VARIANT"] = args.variant
     rank, local_rank, world = init_distributed()
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    from asyncframework_b200.parallel import _devapi as _dev
+    dev = torch.device("cuda", local_rank) if args.device == "cuda" else torch.device("cpu")
+    _dev.set_device(dev)
     # logical workers (= the reference's partitions).  The reference's clusters run 2 tasks per
     # executor (1 executor x 2 cores, README.md:56); two workers per GPU play the same role: one
     # worker's NVLink pull/push latency hides behind the other's HBM streaming.
@@ -91,11 +94,11 @@ def main() -> int:
                               labels="binary01" if args.loss != "least_squares" else "regression", row_offset=sum(sizes[:p]))
               for p in ids]
     shard = shards[0]
-    torch.cuda.synchronize()
+    _dev.synchronize(dev)
     gen_s = time.time() - t0
 
     def barrier():
-        torch.cuda.synchronize()
+        _dev.synchronize(dev)
         if world > 1:
             dist.barrier()
 
@@ -132,7 +135,7 @@ def main() -> int:
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     l0 = launches_of()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = _dev.new_event(dev, enable_timing=True), _dev.new_event(dev, enable_timing=True)
     barrier()
     e0.record()
     if args.impl == "ours" and not args.graph:
@@ -141,7 +144,7 @@ def main() -> int:
     if args.impl == "ours" and not args.graph:
         eng.join()                   # launching stream waits for every worker stream
     e1.record()
-    torch.cuda.synchronize()
+    _dev.synchronize(dev)
     ms = e0.elapsed_time(e1)
     barrier()
     launches = launches_of() - l0
@@ -155,7 +158,7 @@ def main() -> int:
             eng.step()
         barrier()
         t1 = time.perf_counter()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2, e3 = _dev.new_event(dev, enable_timing=True), _dev.new_event(dev, enable_timing=True)
         e2.record()
         last = None
         for _ in range(args.steps):
@@ -163,7 +166,7 @@ def main() -> int:
             last = r or last
         last = eng.flush_steps() or last
         e3.record()
-        torch.cuda.synchronize()
+        _dev.synchronize(dev)
         e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t1) * 1e3)
         barrier()
         e2e_ms = max_over_ranks(e2e_ms, dev)
@@ -193,6 +196,7 @@ def main() -> int:
             "metric": "sgd_iterations_per_sec", "value": args.steps / (ms_max * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+            "device": args.device,
             "data": "synthetic (mnist8m shape: integer pixels 0..255, ~19% non-zero, random-init true weights; no network for the real dataset)",
             "impl": args.impl,
             "config": {"model": f"{args.algo.upper()} {args.loss} regression (linear model, d={args.features})",
