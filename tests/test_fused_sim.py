@@ -153,3 +153,22 @@ def test_fused_driver_on_simulator(alg, step, P, tmp_path):
     from asyncframework_b200.utils import load_checkpoint
     ck = load_checkpoint(str(tmp_path / "ck"))
     assert ck["k"] >= 100 and ck["w"].numel() == 12
+
+
+def test_device_watchdog_on_simulated_status_table():
+    """DeviceWatchdog flags a worker that went busy and then silent (heartbeat older than the newest by > timeout)."""
+    from asyncframework_b200.ops._signatures import WORKER_SLOT_DTYPE
+    from asyncframework_b200.utils import DeviceWatchdog
+    P, d, n = 3, 8, 200
+    parts = _parts(P, n, d, 2, True)
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n * P, num_partitions=P, num_iterations=1 << 30, step_size=0.5,
+                      batch_rate=0.5, loss="logistic", backend="fused", barrier="asp")
+    eng = FusedEngine(cfg, [_shard(parts[p], d, p) for p in range(P)], n * P, list(range(P)), device="cpu")
+    eng.run_rounds(2)
+    wd = DeviceWatchdog(eng, timeout_s=1e-3)
+    assert wd.check_once() == []
+    st = eng.block.status.numpy().view(WORKER_SLOT_DTYPE)
+    st["available"][1] = 0                                   # worker 1 started a round ...
+    st["heartbeat_ns"][1] = int(st["heartbeat_ns"].max()) - 10_000_000      # ... 10 ms before everybody's last sign of life
+    assert wd.check_once() == [1] and wd.dead == [1]
+    assert wd.check_once() == []                             # reported once
