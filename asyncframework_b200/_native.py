@@ -116,6 +116,31 @@ def kernels() -> C.CDLL:
         return lib
 
 
+_experimental: Optional[C.CDLL] = None
+
+
+def experimental() -> C.CDLL:
+    """``libafb_experimental.so`` (csrc/experimental): loaded only on explicit request, never by the default path."""
+    global _experimental
+    if _experimental is not None:
+        return _experimental
+    with _lock:
+        if _experimental is not None:
+            return _experimental
+        path = LIBDIR / "libafb_experimental.so"
+        if not path.exists():
+            raise NativeLibraryError(f"{path} is missing: run `python -m asyncframework_b200.build`")
+        try:
+            lib = C.CDLL(str(path))
+        except OSError as e:
+            raise NativeLibraryError(f"cannot load {path}: {e}") from e
+        from .ops._signatures import RoundParams
+        _sig(lib, "afb_dense_round_persist_max_ld", C.c_int, [])
+        _sig(lib, "afb_dense_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p])
+        _experimental = lib
+        return lib
+
+
 def kernels_available() -> bool:
     try:
         kernels()

@@ -272,6 +272,15 @@ class RoundKernel:
         else:
             self.variant = "simple" if self.is_dense else "csr"
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
+        # "persist" (EXPERIMENTAL, csrc/experimental/dense_round_persist.cu): launch_rounds(n) is ONE resident kernel that
+        # loops over n rounds; single rounds (launch()) still use the simple kernel.  Never selected implicitly.
+        self.persist = (variant == "persist" and self.is_dense and algo != "grad_only" and not self.rollback)
+        self._persist_lib = None
+        if self.persist and not self.sim:
+            from .._native import experimental
+            self._persist_lib = experimental()
+            if ld > self._persist_lib.afb_dense_round_persist_max_ld():
+                self.persist = False
         self.launches = 0
         self.rounds_launched = 0
         if self.sim:
@@ -321,6 +330,29 @@ class RoundKernel:
             check(self.lib.afb_saga_rollback_launch(self.hist.data_ptr(), self.hist_prev.data_ptr(), self.hist_tag.data_ptr(),
                                                     self.shard.num_rows, self.wctl.data_ptr(), int(s.cuda_stream)), "saga rollback")
             self.launches += 1
+
+    def launch_rounds(self, n: int, stream=None, share: int = 1) -> None:
+        """Enqueue ``n`` consecutive rounds.  Default: ``n`` launches.  With the experimental persistent variant: one
+        resident kernel looping over the rounds (``share`` = persistent grids co-running on this GPU; the launcher refuses a
+        grid that cannot be fully co-resident, because the in-kernel round barrier would deadlock)."""
+        if n <= 0:
+            return
+        if not self.persist or n == 1:
+            for _ in range(n):
+                self.launch(stream)
+            return
+        if self.sim:
+            for _ in range(n):                       # protocol-wise a persistent launch IS n back-to-back rounds
+                self._sim.launch()
+            self.launches += 1
+            self.rounds_launched += n
+            return
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.params.pdl = 0
+        check(self._persist_lib.afb_dense_round_persist_launch(C.byref(self.params), int(n), self.grid, int(share), int(s.cuda_stream)),
+              "persistent round kernel launch")
+        self.launches += 1
+        self.rounds_launched += n
 
     def set(self, **kw) -> None:
         for k, v in kw.items():

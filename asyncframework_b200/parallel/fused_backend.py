@@ -160,9 +160,14 @@ class FusedEngine:
     # ------------------------------------------------------------------ hot path
     def run_rounds(self, n: int) -> None:
         """Enqueue ``n`` rounds on every local worker.  No host synchronisation."""
-        for _ in range(n):
+        if all(rk.persist for rk in self.kernels):
+            # experimental persistent variant: one resident kernel per worker loops over the n rounds
             for rk, st in zip(self.kernels, self.streams):
-                rk.launch(st)
+                rk.launch_rounds(n, st, share=len(self.kernels))
+        else:
+            for _ in range(n):
+                for rk, st in zip(self.kernels, self.streams):
+                    rk.launch(st)
         self.rounds_enqueued += n
 
     @property
@@ -189,8 +194,7 @@ class FusedEngine:
             for rk, st in zip(self.kernels, self._graph_streams(cap)):
                 if st != cap:
                     st.wait_event(fork)
-                for _ in range(rounds):
-                    rk.launch(st)
+                rk.launch_rounds(rounds, st, share=len(self.kernels))
                 if st != cap:
                     ev = torch.cuda.Event()
                     ev.record(st)

@@ -34,3 +34,15 @@ def test_every_declared_entry_point_exists():
         fn = getattr(lib, name)
         assert fn.argtypes is not None, f"{name} has no declared signature"
     assert lib.afb_dense_round_max_ld() == 2048 and lib.afb_dense_round_ctas_per_sm(784) == 2 and lib.afb_dense_round_ctas_per_sm(2000) == 1
+
+
+def test_experimental_library_is_separate_and_declares_the_persistent_launcher():
+    from asyncframework_b200 import _native
+    path = _native.LIBDIR / "libafb_experimental.so"
+    if not path.exists():
+        pytest.skip("libafb_experimental.so not built")
+    lib = _native.experimental()
+    assert lib.afb_dense_round_persist_max_ld() == 2048
+    assert lib.afb_dense_round_persist_launch.argtypes is not None
+    # the default library must not contain the experimental entry point (work in progress cannot leak into the default path)
+    assert not hasattr(_native.kernels(), "afb_dense_round_persist_launch")

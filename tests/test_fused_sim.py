@@ -2,6 +2,7 @@
 the simulator itself is checked against the NumPy oracle, then FusedEngine / run_fused / the result
 pump / checkpointing run on top of it."""
 import math
+import os
 import time
 
 import numpy as np
@@ -172,3 +173,27 @@ def test_device_watchdog_on_simulated_status_table():
     st["heartbeat_ns"][1] = int(st["heartbeat_ns"].max()) - 10_000_000      # ... 10 ms before everybody's last sign of life
     assert wd.check_once() == [1] and wd.dead == [1]
     assert wd.check_once() == []                             # reported once
+
+
+def test_persistent_variant_is_n_back_to_back_rounds_on_the_simulator():
+    """launch_rounds(n) of the (experimental) persistent variant must be protocol-identical to n single launches."""
+    P, d, n = 2, 12, 300
+    parts = _parts(P, n, d, 5, False)
+    cfg = AsyncConfig(algorithm="asaga", num_features=d, num_rows=n * P, num_partitions=P, num_iterations=1 << 30, step_size=0.05,
+                      batch_rate=0.3, loss="least_squares", backend="fused", barrier="asp")
+    outs = []
+    for variant in ("simple", "persist"):
+        os.environ["AFB_DENSE_VARIANT"] = variant
+        try:
+            eng = FusedEngine(cfg, [_shard(parts[p], d, p) for p in range(P)], n * P, list(range(P)), device="cpu")
+        finally:
+            os.environ.pop("AFB_DENSE_VARIANT", None)
+        assert all(rk.persist == (variant == "persist") for rk in eng.kernels)
+        eng.run_rounds(6)
+        st = eng.server_state()
+        outs.append((eng.weights().clone(), st["k"], st["clock"], eng.launches))
+    # the simulator runs workers in launch order: simple interleaves w0,w1,w0,w1..., persist runs w0 x6 then w1 x6, so only
+    # the protocol counters (not the weights) must agree; the launch count shows the one-launch-per-worker structure
+    assert outs[0][1] == outs[1][1] == 12 and outs[0][2] == outs[1][2] == 12
+    assert outs[0][3] == 12 and outs[1][3] == 2
+    assert torch.isfinite(outs[1][0]).all()

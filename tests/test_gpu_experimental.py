@@ -1,0 +1,53 @@
+"""Opt-in GPU tests of csrc/experimental (persistent multi-round kernel).  Skipped unless AFB_TEST_EXPERIMENTAL=1: the kernel
+spins on device memory between rounds, so it is only ever run under an explicit `timeout` until it has been validated on
+hardware (`AFB_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -x -q`)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("AFB_TEST_EXPERIMENTAL", "0") != "1", reason="set AFB_TEST_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("algo,loss,d", [("asgd", "logistic", 784), ("asaga", "least_squares", 200), ("asgd", "logistic", 1000)])
+def test_persistent_rounds_match_single_round_launches(algo, loss, d):
+    """n rounds in ONE persistent launch == n launches of the one-round kernel (single worker: deterministic)."""
+    from tests.test_gpu_kernels import _dense_shard
+    from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    n, b, gamma, seed, rounds = 6000, 0.25, 0.05, 5, 7
+    sh = _dense_shard(n, d, seed=3, labels01=(loss == "logistic"))
+    res = {}
+    for variant in ("simple", "persist"):
+        layout = ServerLayout(sh.ld, 1, ring_size=64)
+        blk = ServerBlock.allocate(layout, "cuda")
+        blk.reset()
+        rk = RoundKernel(sh, ServerPointers(blk.buf.data_ptr(), layout), algo=algo, loss_id=LOSS_IDS[loss], num_workers=1,
+                         worker_id=0, total_rows=n, batch_rate=b, gamma=gamma, seed=seed, variant=variant, max_iters=rounds - 1)
+        assert rk.persist == (variant == "persist")
+        rk.launch_rounds(rounds)              # the last round hits k >= max_iters: the persistent grid must exit cleanly
+        torch.cuda.synchronize()
+        st = blk.read_sctl()
+        res[variant] = (blk.w.clone(), blk.abar.clone(), st["k"], st["clock"], rk.read_ctl()["rounds_done"], rk.launches)
+    a, c = res["simple"], res["persist"]
+    assert a[2] == c[2] == rounds - 1 and a[3] == c[3]
+    assert c[5] == 1 and a[5] == rounds
+    assert torch.allclose(a[0], c[0], rtol=1e-4, atol=1e-6) and torch.allclose(a[1], c[1], rtol=1e-4, atol=1e-6)
+
+
+def test_persistent_launch_refuses_non_resident_grid():
+    from tests.test_gpu_kernels import _dense_shard
+    from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    sh = _dense_shard(2000, 784, seed=3)
+    layout = ServerLayout(sh.ld, 1, ring_size=64)
+    blk = ServerBlock.allocate(layout, "cuda")
+    blk.reset()
+    rk = RoundKernel(sh, ServerPointers(blk.buf.data_ptr(), layout), algo="asgd", loss_id=LOSS_IDS["logistic"], num_workers=1,
+                     worker_id=0, total_rows=2000, batch_rate=0.5, gamma=0.1, seed=1, variant="persist")
+    with pytest.raises(RuntimeError):
+        rk.launch_rounds(4, share=2)          # full-capacity grid x 2 co-running grids cannot be resident
+    torch.cuda.synchronize()
