@@ -1,0 +1,355 @@
+"""CTA-level interleaving model of the fused round protocol (race detection for the *algorithm*).
+
+``ops/round_sim.py`` is the sequential spec of one round.  This module models what the simulator cannot: the
+*concurrency inside a grid* — G CTAs of one worker racing through puller election, dynamic chunk scheduling,
+the grid-level reduction, the early clock ticket, last-CTA election, the reset of the per-round counters and
+(persistent variant, ``csrc/experimental/dense_round_persist.cu``) the in-kernel round barrier on
+``WorkerCtl.round`` — with several workers sharing one server.  Every CTA is a Python generator that yields
+after each access to shared state, in the order the CUDA code performs them (``csrc/include/afb_round_impl.cuh``,
+``csrc/kernels/dense_round.cu``); ``explore`` runs them under a seeded random / bursty scheduler and checks:
+
+* every row chunk of every executed round is processed exactly once (no chunk lost or duplicated by the
+  static-first-chunk + one-ahead dynamic fetch scheme, no counter reset racing a late fetch);
+* the server's ``w`` equals the sum of the contributions of the accepted rounds (no gradient leaks from one
+  round into the next through ``g_local``, none is lost);
+* ``k`` = number of accepted rounds, ``clock`` = number of finished rounds, ``avail_count`` returns to P;
+* all per-round counters are zero at the end; no deadlock (every generator spinning with no progress).
+
+It is sequentially consistent (one access at a time), so it checks protocol logic, not the PTX memory model —
+the fences/scopes are covered by the litmus test (`afb_p2p_pingpong`) and compute-sanitizer racecheck on the GPU.
+Mutations (``bug=...``) remove one synchronisation edge each; the tests assert the checker catches every one.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass, field
+from typing import Dict, Generator, List, Optional
+
+SPIN = "spin"
+
+
+@dataclass
+class Server:
+    P: int
+    max_iters: int = 1 << 40
+    taw: int = 1 << 40
+    clock: int = 0
+    k: int = 0
+    w: int = 0
+    avail: int = 0
+    stop: int = 0
+    ring: List[tuple] = field(default_factory=list)
+
+    def __post_init__(self):
+        self.avail = self.P
+
+
+@dataclass
+class WorkerCtl:
+    chunk_ctr: int = 0
+    done_ctas: int = 0
+    pull_ticket: int = 0
+    pull_flag: int = 0
+    round: int = 0
+    proceed: int = 0
+    batch_count: int = 0
+    ts: int = 0
+    g: int = 0
+    tk_flag: int = 0
+    tk_accept: int = 0
+    tk_clock_old: int = 0
+    rounds_done: int = 0
+    last_accepted: int = 0
+
+
+def contrib(worker: int, rnd: int, chunk: int) -> int:
+    """Distinct per (worker, round, chunk) so a sum identifies exactly which chunks were accumulated."""
+    return 1 + chunk + 1009 * rnd + 1000003 * worker
+
+
+class WorkerModel:
+    """One logical worker: G CTAs x `rounds` rounds in ONE persistent launch, or one launch per round."""
+
+    def __init__(self, sv: Server, wid: int, G: int, n_chunks: int, bug: Optional[str] = None, sync_peers: Optional[list] = None):
+        self.sv, self.wid, self.G, self.n_chunks, self.bug = sv, wid, G, n_chunks, bug
+        self.wc = WorkerCtl()
+        # BSP mode (ALGO_SYNC_*): `sync_peers` is the list of all workers; each owns a staging buffer
+        # stage[parity][q] and arrival flags flag[parity][q] that every peer writes over NVLink, and a local replica
+        self.sync_peers = sync_peers
+        self.stage = [[0] * sv.P for _ in range(2)]
+        self.flag = [[0] * sv.P for _ in range(2)]
+        self.w_replica = 0
+        self.covered: Dict[int, List[int]] = {}
+        self.accepted_rounds: List[int] = []
+        self.executed_rounds: List[int] = []
+        self.staleness: List[int] = []
+
+    # ------------------------------------------------------------------ one round of one CTA
+    def _round(self, cid: int, rnd: int, wait: bool) -> Generator:
+        sv, wc, G = self.sv, self.wc, self.G
+        # prologue on immutable inputs: first chunk is static (chunk id == CTA id), nothing shared is touched
+        c = cid
+        if wait and self.bug != "no_round_barrier":
+            while wc.round != rnd:                     # round barrier of the persistent kernel
+                yield SPIN
+        # ---- round_begin_issue: puller election
+        t = wc.pull_ticket; wc.pull_ticket = t + 1     # atomicAdd
+        yield
+        puller = (t == 0)
+        is_async = self.sync_peers is None
+        ck = (rnd, rnd)                                 # BSP: the local round counter plays the clock
+        if puller and is_async:
+            ck = (sv.clock, sv.k)                       # one 64-bit load
+            yield
+        # ---- first dynamic chunk id requested while the pull is in flight
+        nxt = wc.chunk_ctr + G; wc.chunk_ctr += 1      # atomicAdd (+ static_chunks)
+        yield
+        # ---- round_begin_complete
+        if puller:
+            proceed = 0 if (is_async and (ck[1] >= sv.max_iters or sv.stop)) else 1
+            if proceed and is_async:
+                sv.avail -= 1
+                yield
+            wc.ts = ck[0]
+            wc.proceed = proceed
+            yield
+            wc.pull_flag = rnd + 1                      # release
+            yield
+        else:
+            while wc.pull_flag != rnd + 1:
+                yield SPIN
+        if not wc.proceed:
+            t = wc.done_ctas; wc.done_ctas = t + 1
+            yield
+            if t == G - 1:
+                wc.done_ctas = 0; wc.pull_ticket = 0; wc.chunk_ctr = 0
+                wc.last_accepted = -1
+                yield
+                wc.round = rnd + 1
+                yield
+            return False
+        if cid == 0:
+            self.executed_rounds.append(rnd)
+        cov = self.covered.setdefault(rnd, [0] * self.n_chunks)
+        # ---- gradient: chunks, the next id always requested one ahead
+        local = 0
+        while c < self.n_chunks:
+            cov[c] += 1
+            local += contrib(self.wid, rnd, c)
+            yield
+            c = nxt
+            if c >= self.n_chunks:
+                break
+            nxt = wc.chunk_ctr + G; wc.chunk_ctr += 1
+            yield
+        wc.g += local                                   # red.gpu.add into g_local
+        yield
+        # ---- round_finish
+        wc.batch_count += 1
+        yield
+        ticket = wc.done_ctas; wc.done_ctas = ticket + 1
+        yield
+        if ticket == 0 and is_async:                     # early clock ticket (first CTA to finish)
+            old_clock, old_k = sv.clock, sv.k
+            if sv.taw >= (1 << 31):
+                sv.clock += 1; sv.k += 1                 # single 64-bit atomic (never-stale fast path)
+                yield
+                accept = 1 if old_k < sv.max_iters else 0  # k may overshoot max_iters; the overshoot is never applied
+            else:
+                sv.clock += 1                            # first atomic: clock only
+                yield
+                accept = 1 if (old_clock - wc.ts) <= sv.taw else 0
+                if accept:
+                    old_k = sv.k; sv.k += 1              # second atomic: k
+                    yield
+                    if old_k >= sv.max_iters:
+                        accept = 0
+            self.staleness.append(old_clock - wc.ts)
+            wc.tk_accept = accept; wc.tk_clock_old = old_clock
+            yield
+            wc.tk_flag = rnd + 1
+            yield
+        if ticket != G - 1:
+            return True
+        if not is_async:
+            yield from self._bsp_tail(rnd)
+            return True
+        # ---- last CTA: push-and-apply, reset, publish
+        while wc.tk_flag != rnd + 1:
+            yield SPIN
+        accept = wc.tk_accept
+        g = wc.g
+        yield
+        if accept:
+            sv.w += g                                    # Hogwild reductions into the server
+            self.accepted_rounds.append(rnd)
+            yield
+        if self.bug != "late_g_zero":
+            wc.g = 0
+            yield
+        sv.ring.append((wc.tk_clock_old, self.wid, accept))
+        sv.avail += 1
+        yield
+        wc.last_accepted = accept
+        wc.rounds_done += 1
+        wc.done_ctas = 0; wc.pull_ticket = 0
+        yield
+        wc.chunk_ctr = 0; wc.batch_count = 0
+        yield
+        wc.round = rnd + 1                               # release: everything above is visible first
+        yield
+        if self.bug == "late_g_zero":
+            wc.g = 0                                     # (mutation) zeroing g_local after publication wipes the next round's partial sums
+            yield
+        return True
+
+    def _bsp_tail(self, rnd: int) -> Generator:
+        """Last CTA, BSP: all-gather of g into every peer's staging slot (double-buffered by round parity), arrival
+        flags, wait for all P flags, fixed-order reduction, replicated apply."""
+        wc, P = self.wc, self.sv.P
+        par = 0 if self.bug == "single_buffer" else (rnd & 1)
+        g = wc.g
+        yield
+        for q in range(P):
+            self.sync_peers[q].stage[par][self.wid] = g
+            yield
+        for q in range(P):
+            self.sync_peers[q].flag[par][self.wid] = rnd + 1
+            yield
+        for q in range(P):
+            while self.flag[par][q] != rnd + 1:
+                yield SPIN
+        tot = 0
+        for q in range(P):
+            tot += self.stage[par][q]
+            yield
+        self.w_replica += tot
+        self.accepted_rounds.append(rnd)
+        wc.g = 0
+        yield
+        wc.last_accepted = 1
+        wc.rounds_done += 1
+        wc.done_ctas = 0; wc.pull_ticket = 0
+        yield
+        wc.chunk_ctr = 0; wc.batch_count = 0
+        yield
+        wc.round = rnd + 1
+        yield
+
+    # ------------------------------------------------------------------ launch shapes
+    def persistent_cta(self, cid: int, rounds: int) -> Generator:
+        round0 = self.wc.round                           # same value in every CTA (see the kernel's comment)
+        yield
+        for it in range(rounds):
+            alive = yield from self._round(cid, round0 + it, wait=(it > 0))
+            if not alive:
+                return
+
+    def single_round_cta(self, cid: int) -> Generator:
+        rnd = self.wc.round
+        yield
+        yield from self._round(cid, rnd, wait=False)
+
+    # ------------------------------------------------------------------ end-of-run invariants
+    def check(self) -> None:
+        wc = self.wc
+        for rnd in self.executed_rounds:
+            cov = self.covered[rnd]
+            bad = [i for i, v in enumerate(cov) if v != 1]
+            assert not bad, f"worker {self.wid} round {rnd}: chunks processed != once: {[(i, cov[i]) for i in bad][:6]}"
+        for rnd in self.covered:
+            assert rnd in self.executed_rounds, f"worker {self.wid}: chunk work in a round that was not started ({rnd})"
+        assert wc.g == 0 and wc.done_ctas == 0 and wc.pull_ticket == 0 and wc.chunk_ctr == 0 and wc.batch_count == 0, \
+            f"worker {self.wid}: per-round state not reset: {wc}"
+
+    def expected_w(self) -> int:
+        return sum(contrib(self.wid, r, c) for r in self.accepted_rounds for c in range(self.n_chunks))
+
+
+class Deadlock(AssertionError):
+    pass
+
+
+def run_schedule(gens: List[Generator], rng: random.Random, burst: int = 1, max_steps: int = 2_000_000) -> int:
+    """Advance the generators one shared-memory access at a time.  `burst` > 1 lets the chosen generator run up to that
+    many consecutive steps (adversarial: one CTA races far ahead / another is descheduled for long).  A full sweep in
+    which every live generator only spins is a deadlock."""
+    live = list(gens)
+    steps = 0
+    spinning = set()
+    while live:
+        g = rng.choice(live)
+        for _ in range(rng.randint(1, burst)):
+            try:
+                r = next(g)
+            except StopIteration:
+                live.remove(g)
+                spinning.discard(id(g))
+                spinning.clear()
+                break
+            steps += 1
+            if r == SPIN:
+                spinning.add(id(g))
+                if len(spinning) == len(live):
+                    raise Deadlock(f"all {len(live)} live CTAs are spinning")
+                break                                    # a spinning CTA gives up the rest of its burst
+            spinning.clear()
+        if steps > max_steps:
+            raise Deadlock("step budget exhausted")
+    return steps
+
+
+def explore(P: int = 2, G: int = 3, n_chunks: int = 7, rounds: int = 4, mode: str = "persist", seed: int = 0, burst: int = 1,
+            max_iters: int = 1 << 40, bug: Optional[str] = None, algo: str = "async", taw: int = 1 << 40) -> Dict[str, int]:
+    """Run one random schedule of P workers x G CTAs x `rounds` rounds and check every invariant."""
+    rng = random.Random(seed)
+    sv = Server(P, max_iters=max_iters, taw=taw)
+    workers: List[WorkerModel] = []
+    for wid in range(P):
+        workers.append(WorkerModel(sv, wid, G, n_chunks, bug, sync_peers=workers if algo == "sync" else None))
+    steps = 0
+    if mode == "persist":
+        gens = [w.persistent_cta(c, rounds) for w in workers for c in range(G)]
+        steps = run_schedule(gens, rng, burst)
+    elif mode == "launch":
+        # one grid per round per worker; grids of one worker are stream-ordered (kernel boundary = full barrier),
+        # different workers' grids interleave freely
+        def worker_stream(w: WorkerModel) -> Generator:
+            for _ in range(rounds):
+                ctas = [w.single_round_cta(c) for c in range(G)]
+                live = list(ctas)
+                while live:
+                    g = rng.choice(live)
+                    try:
+                        r = next(g)
+                    except StopIteration:
+                        live.remove(g)
+                        continue
+                    yield r if len(live) == 1 else None   # a spin inside a grid with other runnable CTAs is not a deadlock signal
+        steps = run_schedule([worker_stream(w) for w in workers], rng, burst)
+    else:
+        raise ValueError(mode)
+    for w in workers:
+        w.check()
+    if algo == "sync":
+        exp = sum(contrib(w.wid, r, c) for w in workers for r in range(rounds) for c in range(n_chunks))
+        for w in workers:
+            assert w.accepted_rounds == list(range(rounds)), f"worker {w.wid} ran rounds {w.accepted_rounds}"
+            assert w.w_replica == exp, f"replica of worker {w.wid} diverged: {w.w_replica} != {exp}"
+        return {"steps": steps, "accepted": rounds * P, "finished": rounds * P, "k": rounds}
+    exp_w = sum(w.expected_w() for w in workers)
+    accepted = sum(len(w.accepted_rounds) for w in workers)
+    finished = sum(len(w.executed_rounds) for w in workers)
+    assert sv.w == exp_w, f"server w {sv.w} != sum of accepted contributions {exp_w}"
+    assert sv.clock == finished, f"clock {sv.clock} != finished rounds {finished}"
+    if taw >= (1 << 31):
+        assert accepted == min(finished, max_iters), f"accepted {accepted} != min(finished {finished}, max_iters {max_iters})"
+    else:
+        assert accepted <= max_iters and sv.k >= accepted
+        for w in workers:
+            assert all(st >= 0 for st in w.staleness)
+        n_fresh = sum(1 for w in workers for st in w.staleness if st <= taw)
+        assert accepted == min(n_fresh, max_iters) or max_iters < n_fresh, f"accepted {accepted} but {n_fresh} results were within taw"
+    assert sv.avail == P, f"avail_count {sv.avail} != P"
+    assert sorted(r[0] for r in sv.ring) == list(range(finished)), "result-ring sequence numbers are not a permutation of the clock"
+    return {"steps": steps, "accepted": accepted, "finished": finished, "k": sv.k}
