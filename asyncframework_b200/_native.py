@@ -59,6 +59,8 @@ def runtime() -> C.CDLL:
         _sig(lib, "afb_queue_destroy", None, [vp])
         _sig(lib, "afb_queue_put", None, [vp, C.POINTER(Record)])
         _sig(lib, "afb_queue_take", C.c_int, [vp, C.POINTER(Record), f64])
+        _sig(lib, "afb_queue_take_batch", C.c_int, [vp, C.POINTER(Record), C.c_int, f64])
+        _sig(lib, "afb_queue_bench", f64, [C.c_int, i64, C.c_int])
         _sig(lib, "afb_queue_size", i64, [vp])
         _sig(lib, "afb_queue_close", None, [vp])
         _sig(lib, "afb_queue_reopen", None, [vp])

@@ -137,6 +137,25 @@ class AsyncContext(Generic[T]):
         """Blocking take returning the envelope (``ASYNCcollectAll``)."""
         return self._take(timeout)
 
+    def drain(self, max_results: int = 256, timeout: Optional[float] = None) -> list:
+        """Blocking batch take: waits like ``collect_all`` for the first result, then returns every result that is already
+        queued (up to ``max_results``) from ONE native call — the server loop's way to merge a burst of completions
+        without a Python<->C++ round trip per record."""
+        n_max = max(1, int(max_results))
+        recs = (_native.Record * n_max)()
+        rc = self._rt.afb_queue_take_batch(self._q, recs, n_max, -1.0 if timeout is None else float(timeout) * 1e3)
+        if rc == 0:
+            return []
+        if rc < 0:
+            raise QueueClosed("AsyncContext result queue closed")
+        out = []
+        with self._payload_lock:
+            for i in range(rc):
+                r = recs[i]
+                out.append(PartialResult(self._payloads.pop(r.payload_id), int(r.staleness), int(r.ts), int(r.batch_size),
+                                         int(r.worker), float(r.t_submit_ms), float(r.t_finish_ms)))
+        return out
+
     def size(self) -> int:
         return int(self._rt.afb_queue_size(self._q))
 

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -89,6 +90,27 @@ int afb_queue_take(void* h, Record* out, double timeout_ms) {
   *out = q->q.front();
   q->q.pop_front();
   return 1;
+}
+
+// Batch take: blocks like afb_queue_take for the FIRST record, then drains up to max_n records that are already
+// queued under the same lock acquisition.  Returns the number of records written, 0 on timeout, -1 if closed and empty.
+int afb_queue_take_batch(void* h, Record* out, int max_n, double timeout_ms) {
+  auto* q = static_cast<ResultQueue*>(h);
+  if (max_n <= 0) return 0;
+  std::unique_lock<std::mutex> lk(q->mu);
+  auto ready = [&] { return !q->q.empty() || q->closed; };
+  if (timeout_ms < 0) {
+    q->cv.wait(lk, ready);
+  } else if (!q->cv.wait_for(lk, std::chrono::duration<double, std::milli>(timeout_ms), ready)) {
+    return 0;
+  }
+  if (q->q.empty()) return -1;
+  int n = 0;
+  while (n < max_n && !q->q.empty()) {
+    out[n++] = q->q.front();
+    q->q.pop_front();
+  }
+  return n;
 }
 
 int64_t afb_queue_size(void* h) {
@@ -192,5 +214,30 @@ int64_t afb_table_max_staleness(void* h) {
 }
 
 double afb_now_ms() { return now_ms(); }
+
+// Native self-benchmark of the result queue: `producers` threads put `per_producer` records each while the calling
+// thread takes them (single records, or batches of `batch` when batch > 1).  Returns the elapsed seconds.
+double afb_queue_bench(int producers, int64_t per_producer, int batch) {
+  auto* q = static_cast<ResultQueue*>(afb_queue_create());
+  std::vector<std::thread> th;
+  const double t0 = now_ms();
+  for (int p = 0; p < producers; ++p)
+    th.emplace_back([q, p, per_producer] {
+      Record r{};
+      r.worker = p;
+      for (int64_t i = 0; i < per_producer; ++i) { r.payload_id = i; afb_queue_put(q, &r); }
+    });
+  const int64_t total = static_cast<int64_t>(producers) * per_producer;
+  int64_t got = 0;
+  std::vector<Record> buf(static_cast<size_t>(batch > 1 ? batch : 1));
+  while (got < total) {
+    int n = (batch > 1) ? afb_queue_take_batch(q, buf.data(), batch, -1.0) : afb_queue_take(q, buf.data(), -1.0);
+    if (n > 0) got += n;
+  }
+  const double dt = (now_ms() - t0) * 1e-3;
+  for (auto& t : th) t.join();
+  afb_queue_destroy(q);
+  return dt;
+}
 
 }  // extern "C"

@@ -39,18 +39,21 @@ struct Chunk {
   int64_t first_line = 0;
 };
 
+// A parsed file stays in its per-thread chunks; afb_libsvm_copy() scatters them straight into the caller's arrays
+// (one parallel copy instead of a serial stitch followed by a second copy).
 struct Parsed {
-  std::vector<double> labels;
-  std::vector<int64_t> indptr;
-  std::vector<int32_t> indices;
-  std::vector<double> values;
+  std::vector<Chunk> chunks;
+  std::vector<size_t> row_off;   // first row of chunk c
+  std::vector<size_t> nnz_off;   // first non-zero of chunk c
+  size_t rows = 0;
+  size_t nnz = 0;
   int32_t max_index = -1;
 };
 
 inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\f' || c == '\v'; }
 
-// strtod on a bounded token (tokens are short; copy into a stack buffer to NUL-terminate).
-inline bool parse_double(const char* b, const char* e, double* out) {
+// strtod on a bounded token (tokens are short; copy into a stack buffer to NUL-terminate).  Slow path only.
+inline bool parse_double_slow(const char* b, const char* e, double* out) {
   char buf[64];
   size_t n = static_cast<size_t>(e - b);
   if (n == 0 || n >= sizeof(buf)) return false;
@@ -61,6 +64,33 @@ inline bool parse_double(const char* b, const char* e, double* out) {
   double v = strtod(buf, &endp);
   if (endp != buf + n) return false;
   *out = v;
+  return true;
+}
+
+constexpr double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                               1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// Plain decimals ([+-]digits[.digits], the only form LIBSVM writers emit for pixel / tf-idf data) are converted
+// exactly without strtod: when the digit string fits in 2^53 and there are <= 22 fraction digits, mantissa and
+// 10^frac are both exactly representable and one IEEE division gives the correctly rounded result (Clinger's
+// fast path).  Anything else (exponents, inf/nan, hex, > 15-16 digits) goes to strtod, so acceptance and values
+// are identical to the slow path.
+inline bool parse_double(const char* b, const char* e, double* out) {
+  const char* p = b;
+  if (p == e) return false;
+  bool neg = false;
+  if (*p == '-' || *p == '+') { neg = (*p == '-'); ++p; }
+  uint64_t mant = 0;
+  int digits = 0, frac = 0;
+  while (p < e && static_cast<unsigned>(*p - '0') <= 9u) { mant = mant * 10 + static_cast<unsigned>(*p - '0'); ++p; ++digits; }
+  if (p < e && *p == '.') {
+    ++p;
+    while (p < e && static_cast<unsigned>(*p - '0') <= 9u) { mant = mant * 10 + static_cast<unsigned>(*p - '0'); ++p; ++digits; ++frac; }
+  }
+  if (p != e || digits == 0 || digits > 18 || mant > (1ULL << 53) || frac > 22) return parse_double_slow(b, e, out);
+  double v = static_cast<double>(mant);
+  if (frac) v /= kPow10[frac];
+  *out = neg ? -v : v;
   return true;
 }
 
@@ -81,9 +111,15 @@ inline bool parse_int(const char* b, const char* e, int64_t* out) {
 void parse_range(const char* data, size_t begin, size_t end, Chunk* out) {
   size_t pos = begin;
   int64_t line_no = 0;
+  // size the output once: >= 4 bytes per "i:v " token, >= 2 bytes per line
+  const size_t span = end - begin;
+  out->indices.reserve(span / 6 + 16);
+  out->values.reserve(span / 6 + 16);
+  out->labels.reserve(span / 512 + 16);
+  out->row_nnz.reserve(span / 512 + 16);
   while (pos < end) {
-    size_t eol = pos;
-    while (eol < end && data[eol] != '\n') ++eol;
+    const void* nl = memchr(data + pos, '\n', end - pos);
+    size_t eol = nl ? static_cast<size_t>(static_cast<const char*>(nl) - data) : end;
     const char* b = data + pos;
     const char* e = data + eol;
     pos = eol + 1;
@@ -106,13 +142,28 @@ void parse_range(const char* data, size_t begin, size_t end, Chunk* out) {
     while (b < e) {
       while (b < e && *b == ' ') ++b;      // empty tokens dropped
       if (b >= e) break;
-      t = b;
+      // fused scan of `index:value`: digits up to ':' are accumulated while scanning (the common case); any
+      // other shape falls back to the generic token parsers below
+      const char* q = b;
+      int64_t idx1 = 0;
+      int nd = 0;
+      while (q < e && static_cast<unsigned>(*q - '0') <= 9u && nd < 12) { idx1 = idx1 * 10 + (*q - '0'); ++q; ++nd; }
+      const char* colon;
+      bool ok;
+      if (nd > 0 && q < e && *q == ':') {
+        colon = q;
+        ok = true;
+      } else {
+        t = b;
+        while (t < e && *t != ' ') ++t;
+        colon = b;
+        while (colon < t && *colon != ':') ++colon;
+        ok = (colon != t) && parse_int(b, colon, &idx1);
+      }
+      t = colon;
       while (t < e && *t != ' ') ++t;
-      const char* colon = b;
-      while (colon < t && *colon != ':') ++colon;
-      int64_t idx1;
       double val;
-      if (colon == t || !parse_int(b, colon, &idx1) || !parse_double(colon + 1, t, &val)) {
+      if (!ok || !parse_double(colon + 1, t, &val)) {
         out->error = "bad index:value token '" + std::string(b, t) + "' at line " + std::to_string(line_no) + " of chunk";
         return;
       }
@@ -151,7 +202,6 @@ void* afb_libsvm_parse(const char* path, int num_threads, char* err, int errlen)
   if (fstat(fd, &st) != 0) { close(fd); set_err(err, errlen, "fstat failed"); return nullptr; }
   size_t size = static_cast<size_t>(st.st_size);
   auto* result = new Parsed();
-  result->indptr.push_back(0);
   if (size == 0) { close(fd); return result; }
   void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
   close(fd);
@@ -170,46 +220,50 @@ void* afb_libsvm_parse(const char* path, int num_threads, char* err, int errlen)
     while (p < size && data[p] != '\n') ++p;
     cuts[t] = std::min(size, p + 1);
   }
-  std::vector<Chunk> chunks(T);
+  std::vector<Chunk>& chunks = result->chunks;
+  chunks.resize(T);
   std::vector<std::thread> threads;
   for (int t = 0; t < T; ++t)
     threads.emplace_back(parse_range, data, cuts[t], cuts[t + 1], &chunks[t]);
   for (auto& th : threads) th.join();
   munmap(map, size);
 
-  size_t rows = 0, nnz = 0;
   for (auto& c : chunks) {
     if (!c.error.empty()) { set_err(err, errlen, c.error); delete result; return nullptr; }
-    rows += c.labels.size();
-    nnz += c.values.size();
-  }
-  result->labels.reserve(rows);
-  result->indptr.reserve(rows + 1);
-  result->indices.reserve(nnz);
-  result->values.reserve(nnz);
-  int64_t acc = 0;
-  for (auto& c : chunks) {
-    result->labels.insert(result->labels.end(), c.labels.begin(), c.labels.end());
-    for (int64_t n : c.row_nnz) { acc += n; result->indptr.push_back(acc); }
-    result->indices.insert(result->indices.end(), c.indices.begin(), c.indices.end());
-    result->values.insert(result->values.end(), c.values.begin(), c.values.end());
+    result->row_off.push_back(result->rows);
+    result->nnz_off.push_back(result->nnz);
+    result->rows += c.labels.size();
+    result->nnz += c.values.size();
     result->max_index = std::max(result->max_index, c.max_index);
   }
   return result;
 }
 
-int64_t afb_libsvm_rows(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->labels.size()); }
-int64_t afb_libsvm_nnz(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->values.size()); }
+int64_t afb_libsvm_rows(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->rows); }
+int64_t afb_libsvm_nnz(void* h) { return static_cast<int64_t>(static_cast<Parsed*>(h)->nnz); }
 int32_t afb_libsvm_max_index(void* h) { return static_cast<Parsed*>(h)->max_index; }
 
 void afb_libsvm_copy(void* h, double* labels, int64_t* indptr, int32_t* indices, double* values) {
   auto* p = static_cast<Parsed*>(h);
-  if (!p->labels.empty()) memcpy(labels, p->labels.data(), p->labels.size() * sizeof(double));
-  memcpy(indptr, p->indptr.data(), p->indptr.size() * sizeof(int64_t));
-  if (!p->values.empty()) {
-    memcpy(indices, p->indices.data(), p->indices.size() * sizeof(int32_t));
-    memcpy(values, p->values.data(), p->values.size() * sizeof(double));
+  indptr[0] = 0;
+  auto scatter = [&](size_t ci) {
+    const Chunk& c = p->chunks[ci];
+    const size_t r0 = p->row_off[ci], z0 = p->nnz_off[ci];
+    if (!c.labels.empty()) memcpy(labels + r0, c.labels.data(), c.labels.size() * sizeof(double));
+    int64_t acc = static_cast<int64_t>(z0);
+    for (size_t i = 0; i < c.row_nnz.size(); ++i) { acc += c.row_nnz[i]; indptr[r0 + i + 1] = acc; }
+    if (!c.values.empty()) {
+      memcpy(indices + z0, c.indices.data(), c.indices.size() * sizeof(int32_t));
+      memcpy(values + z0, c.values.data(), c.values.size() * sizeof(double));
+    }
+  };
+  if (p->chunks.size() <= 1) {
+    if (!p->chunks.empty()) scatter(0);
+    return;
   }
+  std::vector<std::thread> threads;
+  for (size_t ci = 0; ci < p->chunks.size(); ++ci) threads.emplace_back(scatter, ci);
+  for (auto& th : threads) th.join();
 }
 
 void afb_libsvm_free(void* h) { delete static_cast<Parsed*>(h); }

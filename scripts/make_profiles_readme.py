@@ -75,6 +75,19 @@ if cfgs:
             out.append(f"| {r['config']} | {r['algo']} | {r['delay_intensity']} | {r['workers']} | {r['iterations_per_s']:.0f} | "
                        f"{r['ms_per_iteration']:.4f} | {r['objective_start']:.4f} -> {r['objective_end']:.4f} | {r.get('mode', 'fixed rounds per worker')} ({os.path.basename(os.path.dirname(c))}) |")
     out.append("")
+hr = os.path.join(ROOT, "profiles", "host_runtime.json")
+if os.path.exists(hr):
+    h = json.load(open(hr))
+    lp, rq, wt = h["libsvm_parser"], h["result_queue"], h["worker_table"]
+    out += ["## Host runtime (C++, measured on the build container's 8 shared vCPUs, so +-30 % run to run: `benchmarks/host_runtime_bench.py`)", "",
+            f"LIBSVM ingest (K14; {lp['file_mb']} MB file, {lp['rows']} rows, {lp['nnz']} non-zeros, file -> CSR NumPy arrays, median of 7):", "",
+            "| parser | MB/s |", "|---|---|"]
+    for k in sorted((k for k in lp if k.startswith("native_")), key=lambda k: int(k.split("_")[1][:-1])):
+        out.append(f"| C++ mmap parser, {k.split('_')[1][:-1]} thread(s) | {lp[k]} |")
+    out += [f"| pure-Python parser of the same grammar (`parse_libsvm_record`) | {lp['python_mb_s']} |", "",
+            f"Result queue ({rq['producers']} producer threads, {rq['records']} records): {rq['single_take_mrec_s']} M records/s with single takes, "
+            f"{rq['batch64_take_mrec_s']} M records/s with `take_batch(64)` (`AsyncContext.drain`).  Worker table (P = {wt['P']}, through ctypes): "
+            f"{wt['task_done_mops_s']} M `task_done`/s, {wt['available_workers_scan_mops_s']} M `available_workers` scans/s.", ""]
 ev = os.path.join(ROOT, "profiles", "bench", "eval_bench_r1.log")
 if os.path.exists(ev):
     out += ["## Objective evaluation (K12): tcgen05/TMEM GEMM vs exact CUDA-core kernel (1 GPU, 2 M x 784)", "",

@@ -37,3 +37,30 @@ def test_host_runtime_stress_tsan(tmp_path):
         pytest.skip("TSAN cannot map its shadow memory in this container")
     assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
     assert run.returncode == 0 and "OK" in run.stdout, run.stdout + run.stderr[-2000:]
+
+
+def test_batch_take_preserves_order_and_blocks_like_take():
+    import threading
+    import time
+    from asyncframework_b200.core import AsyncContext
+    from asyncframework_b200.core.context import QueueClosed
+    from asyncframework_b200.core.partial_result import PartialResult
+    ctx = AsyncContext(4)
+    for i in range(10):
+        ctx.put(PartialResult({"i": i}, staleness=i, timestamp=i, batch_size=1, worker_id=i % 4))
+    first = ctx.drain(4)
+    assert [r.data["i"] for r in first] == [0, 1, 2, 3] and [r.worker_id for r in first] == [0, 1, 2, 3]
+    assert [r.data["i"] for r in ctx.drain(100)] == [4, 5, 6, 7, 8, 9] and ctx.size() == 0
+    t0 = time.perf_counter()
+    assert ctx.drain(8, timeout=0.05) == [] and time.perf_counter() - t0 >= 0.04          # timeout, nothing queued
+    got = []
+    th = threading.Thread(target=lambda: got.extend(ctx.drain(8)))                           # blocks until the first result
+    th.start()
+    time.sleep(0.05)
+    ctx.put(PartialResult("late", 0, 0, 1, 2))
+    th.join(timeout=5)
+    assert [r.data for r in got] == ["late"]
+    ctx.close()
+    with pytest.raises(QueueClosed):
+        ctx.drain(1)
+    assert not ctx._payloads                                                                    # no payload leaked
