@@ -90,3 +90,42 @@ def test_mlutils_helpers():
     import math
     assert abs(MLUtils.log1p_exp(800.0) - 800.0) < 1e-9 and abs(MLUtils.log1p_exp(-800.0)) < 1e-9
     assert abs(MLUtils.log1p_exp(0.3) - math.log(1 + math.exp(0.3))) < 1e-12
+
+
+def test_native_decimal_fast_path_is_correctly_rounded(tmp_path):
+    """The parser converts plain decimals without strtod; every value must equal Python's float(token) bit for bit,
+    including tokens that must take the slow path (exponents, > 15 digits, inf/nan)."""
+    import random
+    from asyncframework_b200.data.libsvm import parse_libsvm_file_csr
+    rng = random.Random(7)
+    toks = ["0", "-0", "+1", "1.", ".5", "-.25", "0.1", "0.30000000000000004", "123456789012345", "9007199254740993", "1e-3", "-2.5E+7",
+            "0.000000000000000000001", "123456.789012345678901234", "1e22", "1e23", "4.9e-324", "1.7976931348623157e308", "inf", "-inf",
+            "00012.5000", "3.14159265358979323846", "255", "0.00392156862745098", "179769313486231570000"]
+    for _ in range(3000):
+        nd, nf = rng.randint(0, 17), rng.randint(0, 20)
+        t = "".join(rng.choice("0123456789") for _ in range(nd))
+        if nf:
+            t += "." + "".join(rng.choice("0123456789") for _ in range(nf))
+        if not any(c.isdigit() for c in t):
+            t = "7" + t
+        toks.append(rng.choice(["", "-", "+"]) + t)
+    path = tmp_path / "vals.libsvm"
+    with open(path, "w") as f:
+        for i in range(0, len(toks), 10):
+            row = toks[i:i + 10]
+            f.write(f"{row[0]} " + " ".join(f"{j + 1}:{v}" for j, v in enumerate(row)) + "\n")
+    labels, indptr, indices, values, mx = parse_libsvm_file_csr(str(path), num_threads=3)
+    exp = np.array([float(t) for t in toks], dtype=np.float64)
+    assert len(values) == len(toks)
+    assert np.array_equal(values.view(np.uint64), exp.view(np.uint64))
+    assert np.array_equal(labels.view(np.uint64), exp[::10].view(np.uint64))
+    assert np.array_equal(np.diff(indptr), np.minimum(10, len(toks) - np.arange(0, len(toks), 10)))
+
+
+@pytest.mark.parametrize("bad", ["1 1:2 x:3", "1 2:1 2:3", "1 0:5", "1 3:", "1 :4", "1 3:4:5", "abc 1:2", "1 1:2\t2:3", "1 5:1e", "1 1:--2"])
+def test_native_parser_rejects_malformed_tokens(tmp_path, bad):
+    from asyncframework_b200.data.libsvm import parse_libsvm_file_csr
+    path = tmp_path / "bad.libsvm"
+    path.write_text("1 1:1\n" + bad + "\n")
+    with pytest.raises(ValueError):
+        parse_libsvm_file_csr(str(path))
