@@ -27,7 +27,7 @@ from ..core import barriers
 from ..core.broadcast import AsyncBroadcast
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli
+from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -58,7 +58,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         N = points.count()
         sizes = points.partition_sizes()
         d = next(s for s in points.shards() if s is not None).num_features
-        print(dict(enumerate(sizes)))
+        say(cfg, dict(enumerate(sizes)))
         gradient = make_gradient(cfg.loss)
         w = torch.zeros(d, dtype=dtype, device=device)
         alpha_bar = torch.zeros_like(w)
@@ -103,7 +103,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                         w.add_(alpha_bar, alpha=-gamma)
                         alpha_bar.add_(g.to(w.dtype), alpha=1.0 / N)
                         if k % cfg.printer_freq == 0:
-                            print(f"Iteration {k} is finished")
+                            say(cfg, f"Iteration {k} is finished")
                             opt_vars.append((now_ms() - start, w.detach().clone()))
                             metrics.emit("snapshot", k=k, elapsed_ms=now_ms() - start)
                         state["k"] = k + 1

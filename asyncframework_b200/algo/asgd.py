@@ -23,7 +23,7 @@ import torch
 from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
-from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli)
+from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say)
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 from ..optim.gradient import make_gradient
@@ -44,7 +44,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         P = cfg.num_partitions
         N = points.count()
         d = next(s for s in points.shards() if s is not None).num_features
-        print(dict(enumerate(points.partition_sizes())))           # "check how balanced the data is" (:77)
+        say(cfg, dict(enumerate(points.partition_sizes())))           # "check how balanced the data is" (:77)
         gradient = make_gradient(cfg.loss)
         w = torch.zeros(d, dtype=dtype, device=device)
         AC: AsyncContext = AsyncContext(P, sched)
@@ -86,7 +86,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                         else:
                             w.add_(g.to(w.dtype), alpha=eta / par_recs)
                         if k % cfg.printer_freq == 0:
-                            print(f"Iteration {k} is finished")
+                            say(cfg, f"Iteration {k} is finished")
                             opt_vars.append((now_ms() - start, w.detach().clone()))
                             metrics.emit("snapshot", k=k, elapsed_ms=now_ms() - start)
                         state["k"] = k + 1

@@ -87,6 +87,12 @@ def partition_gradient(gradient: Gradient, shard: Shard, w: torch.Tensor, histor
     return g, float(l), n, coeff
 
 
+def say(cfg: AsyncConfig, *args) -> None:
+    """The reference drivers narrate on stdout (partition sizes, "Iteration k is finished"); ``cfg.quiet`` mutes that."""
+    if not getattr(cfg, "quiet", False):
+        print(*args)
+
+
 def run_cli(algorithm: str, main_fn: Callable[[AsyncConfig], object], argv: Optional[List[str]] = None):
     logging.basicConfig(level=logging.WARNING, format="%(levelname)s %(name)s: %(message)s")
     cfg = parse_cli(algorithm, sys.argv[1:] if argv is None else argv)

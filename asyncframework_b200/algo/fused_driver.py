@@ -21,6 +21,7 @@ from ..data.generators import SHAPES, shard_rows, synthetic_shard
 from ..optim.gradient import LOSS_IDS
 from ..parallel.comm import init_distributed
 from ..parallel.fused_backend import FusedEngine
+from .common import say
 from .telemetry import MetricsLog, RunReport
 
 
@@ -139,7 +140,7 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
             k += n
         if rank == 0 and k >= next_snap:
             snaps.append(((time.perf_counter() - t0) * 1e3, engine.weights().clone()))
-            print(f"Iteration {k} is finished")
+            say(cfg, f"Iteration {k} is finished")
             metrics.emit("snapshot", k=k, elapsed_ms=snaps[-1][0])
             while next_snap <= k:
                 next_snap += cfg.printer_freq

@@ -16,7 +16,7 @@ from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli
+from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -39,7 +39,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         P = cfg.num_partitions
         N = points.count()
         d = next(s for s in points.shards() if s is not None).num_features
-        print(dict(enumerate(points.partition_sizes())))
+        say(cfg, dict(enumerate(points.partition_sizes())))
         gradient = make_gradient(cfg.loss)
         w = torch.zeros(d, dtype=dtype, device=device)
         AC: AsyncContext = AsyncContext(P, sched)
@@ -85,7 +85,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             w.add_(acc, alpha=-gamma / math.sqrt(k + 1) / (b * N))
             losses.append(loss_sum / max(cnt, 1))
             if k % cfg.printer_freq == 0:
-                print(f"Iteration {k} is finished")
+                say(cfg, f"Iteration {k} is finished")
                 opt_vars.append((now_ms() - start, w.detach().clone()))
                 metrics.emit("snapshot", k=k, elapsed_ms=now_ms() - start, loss=losses[-1])
         elapsed = now_ms() - start

@@ -5,8 +5,11 @@ Compare with ASYNCsamples/src/main/scala/org/apache/async/SparkASGDSync.scala:15
     python examples/spark_asgd_sync.py [libsvm_path] [d]
 """
 import math
+import os
 import sys
 import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from a source checkout
 
 import torch
 

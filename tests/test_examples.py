@@ -1,0 +1,40 @@
+"""The scripts under examples/ must keep running (CPU paths) — they are the user-facing documentation."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, *args, timeout=240):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script), *args], capture_output=True, text=True, timeout=timeout,
+                         env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    return res.stdout
+
+
+def test_spark_asgd_sync_example():
+    out = _run("spark_asgd_sync.py")
+    assert float(out.strip().splitlines()[-1].split()[-1]) < 0.2
+
+
+def test_python_api_example():
+    out = _run("async_sgd_python_api.py", "--updates", "120")
+    last = out.strip().splitlines()[-1]
+    assert "objective" in last and float(last.split()[-1]) < 0.05
+
+
+def test_fused_engine_example_on_the_simulator():
+    out = _run("fused_engine.py")
+    assert "k = 20 accepted updates" in out and "worker table" in out
+
+
+@pytest.mark.timeout(400)
+def test_straggler_sweep_example():
+    out = _run("straggler_sweep.py", "--rows", "4000", timeout=380)
+    rows = [l.split() for l in out.strip().splitlines()[1:]]
+    assert len(rows) == 8 and {r[0] for r in rows} == {"asaga", "saga_sync"}
+    assert all(int(r[4]) > 0 for r in rows)
