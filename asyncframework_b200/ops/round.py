@@ -274,13 +274,23 @@ class RoundKernel:
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
         # "persist" (EXPERIMENTAL, csrc/experimental/dense_round_persist.cu): launch_rounds(n) is ONE resident kernel that
         # loops over n rounds; single rounds (launch()) still use the simple kernel.  Never selected implicitly.
-        self.persist = (variant == "persist" and self.is_dense and algo != "grad_only" and not self.rollback)
+        # "pipelined" (EXPERIMENTAL, csrc/experimental/dense_round_pipelined.cu): ASGD only; launch_rounds(n) is one resident
+        # kernel in which round r+1 overlaps round r's NVLink tail (one own update in flight).  Falls back to "persist" when
+        # the round is not eligible (other algorithm, bucket gate, delay injection, server-k sampling seed).
+        self.pipelined = (variant == "pipelined" and self.is_dense and algo == "asgd" and int(gate_threshold) == 0
+                          and int(delay_mode) == 0 and int(p.seed_mode) in (1, 2))
+        self.persist = (variant in ("persist", "pipelined") and not self.pipelined and self.is_dense and algo != "grad_only"
+                        and not self.rollback)
         self._persist_lib = None
-        if self.persist and not self.sim:
+        if (self.persist or self.pipelined) and not self.sim:
             from .._native import experimental
             self._persist_lib = experimental()
             if ld > self._persist_lib.afb_dense_round_persist_max_ld():
-                self.persist = False
+                self.persist = self.pipelined = False
+        if self.pipelined and not self.sim:
+            self._pipe_state = torch.zeros(self._persist_lib.afb_pipe_state_bytes(), dtype=torch.uint8, device=dev)
+            self._pipe_g2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
+            self._pipe_w2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
         self.launches = 0
         self.rounds_launched = 0
         if self.sim:
@@ -337,18 +347,30 @@ class RoundKernel:
         grid that cannot be fully co-resident, because the in-kernel round barrier would deadlock)."""
         if n <= 0:
             return
-        if not self.persist or n == 1:
+        if not (self.persist or self.pipelined) or n == 1:
             for _ in range(n):
                 self.launch(stream)
             return
         if self.sim:
-            for _ in range(n):                       # protocol-wise a persistent launch IS n back-to-back rounds
-                self._sim.launch()
+            if self.pipelined:
+                self._sim.launch_pipelined(n)
+            else:
+                for _ in range(n):                   # protocol-wise a persistent launch IS n back-to-back rounds
+                    self._sim.launch()
             self.launches += 1
             self.rounds_launched += n
             return
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.params.pdl = 0
+        if self.pipelined:
+            if share != 1:
+                raise ValueError("the pipelined variant needs the whole GPU: one logical worker per GPU")
+            check(self._persist_lib.afb_dense_round_pipelined_launch(C.byref(self.params), int(n), self.grid, self._pipe_state.data_ptr(),
+                                                                     self._pipe_g2.data_ptr(), self._pipe_w2.data_ptr(), int(s.cuda_stream)),
+                  "pipelined round kernel launch")
+            self.launches += 1
+            self.rounds_launched += n
+            return
         check(self._persist_lib.afb_dense_round_persist_launch(C.byref(self.params), int(n), self.grid, int(share), int(s.cuda_stream)),
               "persistent round kernel launch")
         self.launches += 1
@@ -366,6 +388,11 @@ class RoundKernel:
     def read_ctl(self) -> Dict[str, float]:
         a = self.read_ctl_raw()
         return {n: (float(a[n]) if a[n].dtype.kind == "f" else int(a[n])) for n in WORKER_CTL_DTYPE.names if n != "dbg_ns"}
+
+    @property
+    def variant_effective(self) -> str:
+        """The kernel ``launch_rounds`` actually uses (an experimental request that is not eligible falls back)."""
+        return "pipelined" if self.pipelined else ("persist" if self.persist else self.variant)
 
     @property
     def w_view(self) -> torch.Tensor:

@@ -236,6 +236,114 @@ class WorkerModel:
         wc.round = rnd + 1
         yield
 
+    # ------------------------------------------------------------------ pipelined persistent rounds (experimental design)
+    def _pipe_state(self):
+        return WorkerCtl()
+
+    def pipelined_cta(self, cid: int, rounds: int) -> Generator:
+        """Persistent grid in which round r+1's pull and gradient phase overlap round r's NVLink tail: every piece of
+        per-round state (tickets, chunk counter, g_local, pulled w / clock, early ticket) is double-buffered by round
+        parity; a CTA may start round r once round r-2 has been PUBLISHED (its buffers are clean), and the last CTA to
+        finish round r applies it while everybody else is already streaming round r+1.  The worker therefore computes
+        round r+1 on parameters that do not contain its own round-r update (one own update in flight)."""
+        sv, wc, G = self.sv, self.wc, self.G
+        if not hasattr(self, "pb"):
+            self.pb = [self._pipe_state(), self._pipe_state()]
+        round0 = wc.round
+        yield
+        for it in range(rounds):
+            rnd = round0 + it
+            S = self.pb[0 if self.bug == "pipe_single_buffer" else (rnd & 1)]
+            c = cid
+            if it >= 2 and self.bug != "pipe_no_reuse_wait":
+                while wc.round < rnd - 1:                  # round r-2 published => parity buffers are clean
+                    yield SPIN
+            t = S.pull_ticket; S.pull_ticket = t + 1
+            yield
+            puller = (t == 0)
+            ck = None
+            if puller:
+                ck = (sv.clock, sv.k)
+                yield
+            nxt = S.chunk_ctr + G; S.chunk_ctr += 1
+            yield
+            if puller:
+                S.ts = ck[0]
+                S.proceed = 0 if (ck[1] >= sv.max_iters or sv.stop) else 1
+                yield
+                S.pull_flag = rnd + 1
+                yield
+            else:
+                while S.pull_flag != rnd + 1:
+                    yield SPIN
+            if not S.proceed:
+                t = S.done_ctas; S.done_ctas = t + 1
+                yield
+                if t == G - 1:
+                    while wc.round != rnd:                 # the previous round's tail publishes first
+                        yield SPIN
+                    S.done_ctas = 0; S.pull_ticket = 0; S.chunk_ctr = 0
+                    wc.last_accepted = -1
+                    yield
+                    wc.round = rnd + 1
+                    yield
+                return
+            if cid == 0:
+                self.executed_rounds.append(rnd)
+            cov = self.covered.setdefault(rnd, [0] * self.n_chunks)
+            local = 0
+            while c < self.n_chunks:
+                cov[c] += 1
+                local += contrib(self.wid, rnd, c)
+                yield
+                c = nxt
+                if c >= self.n_chunks:
+                    break
+                nxt = S.chunk_ctr + G; S.chunk_ctr += 1
+                yield
+            S.g += local
+            yield
+            S.batch_count += 1
+            yield
+            ticket = S.done_ctas; S.done_ctas = ticket + 1
+            yield
+            if ticket == 0:
+                old_clock, old_k = sv.clock, sv.k
+                sv.clock += 1; sv.k += 1
+                yield
+                S.tk_accept = 1 if old_k < sv.max_iters else 0
+                S.tk_clock_old = old_clock
+                self.staleness.append(old_clock - S.ts)
+                yield
+                S.tk_flag = rnd + 1
+                yield
+            if ticket != G - 1:
+                continue
+            # ---- tail of round rnd, overlapping everybody else's round rnd+1
+            while wc.round != rnd:                         # tails are applied and published in round order
+                yield SPIN
+            while S.tk_flag != rnd + 1:
+                yield SPIN
+            accept = S.tk_accept
+            g = S.g
+            yield
+            if accept:
+                sv.w += g
+                self.accepted_rounds.append(rnd)
+                yield
+            S.g = 0
+            yield
+            sv.ring.append((S.tk_clock_old, self.wid, accept))
+            yield
+            wc.last_accepted = accept
+            wc.rounds_done += 1
+            S.done_ctas = 0; S.pull_ticket = 0
+            yield
+            S.chunk_ctr = 0; S.batch_count = 0
+            yield
+            wc.round = rnd + 1
+            yield
+
     # ------------------------------------------------------------------ launch shapes
     def persistent_cta(self, cid: int, rounds: int) -> Generator:
         round0 = self.wc.round                           # same value in every CTA (see the kernel's comment)
@@ -259,8 +367,9 @@ class WorkerModel:
             assert not bad, f"worker {self.wid} round {rnd}: chunks processed != once: {[(i, cov[i]) for i in bad][:6]}"
         for rnd in self.covered:
             assert rnd in self.executed_rounds, f"worker {self.wid}: chunk work in a round that was not started ({rnd})"
-        assert wc.g == 0 and wc.done_ctas == 0 and wc.pull_ticket == 0 and wc.chunk_ctr == 0 and wc.batch_count == 0, \
-            f"worker {self.wid}: per-round state not reset: {wc}"
+        for st in [wc] + list(getattr(self, "pb", [])):
+            assert st.g == 0 and st.done_ctas == 0 and st.pull_ticket == 0 and st.chunk_ctr == 0 and st.batch_count == 0, \
+                f"worker {self.wid}: per-round state not reset: {st}"
 
     def expected_w(self) -> int:
         return sum(contrib(self.wid, r, c) for r in self.accepted_rounds for c in range(self.n_chunks))
@@ -310,6 +419,9 @@ def explore(P: int = 2, G: int = 3, n_chunks: int = 7, rounds: int = 4, mode: st
     steps = 0
     if mode == "persist":
         gens = [w.persistent_cta(c, rounds) for w in workers for c in range(G)]
+        steps = run_schedule(gens, rng, burst)
+    elif mode == "pipelined":
+        gens = [w.pipelined_cta(c, rounds) for w in workers for c in range(G)]
         steps = run_schedule(gens, rng, burst)
     elif mode == "launch":
         # one grid per round per worker; grids of one worker are stream-ordered (kernel boundary = full barrier),

@@ -59,7 +59,17 @@ class RoundSim:
     def _sctl(self, block):
         return block.sctl.numpy().view(SERVER_CTL_DTYPE)[0:1]
 
-    def launch(self) -> None:
+    def launch_pipelined(self, n: int) -> None:
+        """``n`` rounds of the pipelined persistent kernel (csrc/experimental/dense_round_pipelined.cu): round i+1's pull is
+        issued before round i's update has been applied, so each round computes on parameters that lack the worker's own
+        previous update (everything else — clock, tickets, ring, status — is identical to ``n`` single launches)."""
+        w_next = None
+        for _ in range(n):
+            before = self.server.w.clone()           # what the next round's puller reads: the server BEFORE this round's apply
+            self.launch(w_pulled=w_next)
+            w_next = before
+
+    def launch(self, w_pulled: Optional[torch.Tensor] = None) -> None:
         rk, p = self.rk, self.rk.params
         wc = self._wc()
         algo = int(p.algo)
@@ -87,7 +97,7 @@ class RoundSim:
                 me["busy_since_ns"] = t_entry
                 me["heartbeat_ns"] = t_entry
                 me["wait_ns"] = wc["wait_ns"][0]
-                rk.w_local.copy_(srv.w)                                    # K10
+                rk.w_local.copy_(srv.w if w_pulled is None else w_pulled)  # K10
             else:
                 ck = rnd
             wc["ts"] = ck & 0xFFFFFFFF

@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
                     help="cpu = contract smoke-test against the pure-Python round simulator (NOT a benchmark)")
-    ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe", "ring", "persist"],
+    ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe", "ring", "persist", "pipelined"],
                     help="dense kernel variant (default: env/auto; persist = experimental one-launch-per-K-rounds kernel)")
     ap.add_argument("--graph", type=int, default=0, help="replay a CUDA graph of this many rounds (0 = plain launches)")
     ap.add_argument("--stagger-us", type=float, default=0.0, help="one-time phase offset between co-located workers")
@@ -87,6 +87,8 @@ def main() -> int:
     # executor (1 executor x 2 cores, README.md:56); two workers per GPU play the same role: one
     # worker's NVLink pull/push latency hides behind the other's HBM streaming.
     wpg = args.workers_per_gpu or (2 if (world > 1 and args.impl == "ours" and args.algo in ("asgd", "asaga")) else 1)
+    if args.variant == "pipelined" and not args.workers_per_gpu:
+        wpg = 1                                   # the pipelined persistent kernel owns every SM of its GPU
     P = world * wpg
     sizes = shard_rows(args.rows, P)
     ids = [p for p in range(P) if p % world == rank]
@@ -206,7 +208,7 @@ def main() -> int:
                        "updates_per_iteration": P, "accepted_updates_total": int(k_total),
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
                                     f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
-                       "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph, "dense_variant": (("persist" if eng.kernels[0].persist else eng.kernels[0].variant) if args.impl == "ours" else None),
+                       "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph, "dense_variant": (eng.kernels[0].variant_effective if args.impl == "ours" else None),
                        "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); every step: pinned H2D round descriptor -> fused round(s) -> pinned D2H result records (host reads them one step behind)",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,

@@ -75,6 +75,20 @@ if cfgs:
             out.append(f"| {r['config']} | {r['algo']} | {r['delay_intensity']} | {r['workers']} | {r['iterations_per_s']:.0f} | "
                        f"{r['ms_per_iteration']:.4f} | {r['objective_start']:.4f} -> {r['objective_end']:.4f} | {r.get('mode', 'fixed rounds per worker')} ({os.path.basename(os.path.dirname(c))}) |")
     out.append("")
+tm = os.path.join(ROOT, "profiles", "round_timeline_model.json")
+if os.path.exists(tm):
+    t = json.load(open(tm))
+    out += ["## Latency-aware roofline at 8 GPUs (MODEL, not a measurement: `benchmarks/round_timeline_model.py`)", "",
+            "The HBM roofline (bytes / measured copy bandwidth = 20.7 k it/s at N=8) ignores the ~29 us of serial work per round (inter-kernel gap 11.5,",
+            "pull 3.7, fill/drain 10, tail 4 us; device timestamps above).  A fluid timeline of the co-resident workers with those measured terms",
+            "reproduces the measured rates (`w1_launch` / `w2_lockstep` 12.6 k vs measured 12.7-12.8 k it/s: the two workers of a GPU run in lock-step, so",
+            "their serial phases do not hide behind each other) and predicts what the experimental kernels under `csrc/experimental/` can buy",
+            "(alpha = share of the HBM bandwidth one of two co-resident workers can draw alone, unknown until measured):", "",
+            "| alpha | " + " | ".join(k for k in next(iter(t["by_alpha"].values()))) + " |",
+            "|---|" + "---|" * len(next(iter(t["by_alpha"].values())))]
+    for a, row in t["by_alpha"].items():
+        out.append(f"| {a} | " + " | ".join(str(v) for v in row.values()) + " |")
+    out.append("")
 hr = os.path.join(ROOT, "profiles", "host_runtime.json")
 if os.path.exists(hr):
     h = json.load(open(hr))

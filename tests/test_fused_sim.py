@@ -197,3 +197,45 @@ def test_persistent_variant_is_n_back_to_back_rounds_on_the_simulator():
     assert outs[0][1] == outs[1][1] == 12 and outs[0][2] == outs[1][2] == 12
     assert outs[0][3] == 12 and outs[1][3] == 2
     assert torch.isfinite(outs[1][0]).all()
+
+
+def test_pipelined_variant_semantics_on_the_simulator():
+    """Pipelined persistent rounds: same protocol counters as n single launches, but round i+1 is computed on parameters
+    that lack the worker's own round-i update (one own update in flight) — checked against a NumPy transcription."""
+    d, n, b, gamma, seed, rounds = 10, 400, 0.5, 0.4, 3, 5
+    parts = _parts(1, n, d, 9, True)
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=gamma,
+                      batch_rate=b, loss="logistic", backend="fused", barrier="asp", seed=seed)
+    os.environ["AFB_DENSE_VARIANT"] = "pipelined"
+    try:
+        eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+    finally:
+        os.environ.pop("AFB_DENSE_VARIANT", None)
+    rk = eng.kernels[0]
+    assert rk.pipelined and not rk.persist and rk.variant_effective == "pipelined"
+    eng.run_rounds(rounds)
+    st = eng.server_state()
+    assert st["k"] == rounds and st["clock"] == rounds and eng.launches == 1
+    # reference: w_pulled(0) = w0; w_pulled(i+1) = server BEFORE update i  (=> update i is computed on w_{i-1})
+    from asyncframework_b200.core.sampler import bernoulli_mask
+    X, y, gid = parts[0]
+    X, y = torch.from_numpy(X), torch.from_numpy(y)
+    w_srv = torch.zeros(d, dtype=torch.float64)
+    w_pull = w_srv.clone()
+    for i in range(rounds):
+        rows = torch.from_numpy(np.nonzero(bernoulli_mask(seed + i + 1, gid, b))[0])
+        m = X[rows] @ w_pull
+        g = X[rows].T @ (torch.sigmoid(m) - y[rows])
+        before = w_srv.clone()
+        w_srv = w_srv - gamma / math.sqrt(i + 1) * g / (b * n)
+        w_pull = before
+    assert torch.allclose(eng.weights()[:d].double(), w_srv, rtol=1e-4, atol=1e-6)
+    # an ineligible request (ASAGA) falls back to the barrier-persistent variant and says so
+    cfg2 = AsyncConfig(algorithm="asaga", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=0.05,
+                       batch_rate=b, loss="least_squares", backend="fused", barrier="asp")
+    os.environ["AFB_DENSE_VARIANT"] = "pipelined"
+    try:
+        eng2 = FusedEngine(cfg2, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+    finally:
+        os.environ.pop("AFB_DENSE_VARIANT", None)
+    assert eng2.kernels[0].variant_effective == "persist"

@@ -51,3 +51,33 @@ def test_persistent_launch_refuses_non_resident_grid():
     with pytest.raises(RuntimeError):
         rk.launch_rounds(4, share=2)          # full-capacity grid x 2 co-running grids cannot be resident
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("d", [784, 200, 1000])
+def test_pipelined_rounds_match_the_simulator_semantics(d):
+    """Single worker => deterministic: n pipelined rounds on the GPU == the simulator's transcription of the same schedule
+    (round i+1 computed on the parameters pulled before update i landed)."""
+    from tests.test_gpu_kernels import _dense_shard
+    from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    n, b, gamma, seed, rounds = 6000, 0.25, 0.05, 5, 8
+    sh = _dense_shard(n, d, seed=3, labels01=True)
+    res = {}
+    for dev in ("cuda", "cpu"):
+        s = sh if dev == "cuda" else sh.to("cpu")
+        layout = ServerLayout(s.ld, 1, ring_size=64)
+        blk = ServerBlock.allocate(layout, dev)
+        blk.reset()
+        rk = RoundKernel(s, ServerPointers(blk.buf.data_ptr(), layout), algo="asgd", loss_id=LOSS_IDS["logistic"], num_workers=1,
+                         worker_id=0, total_rows=n, batch_rate=b, gamma=gamma, seed=seed, variant="pipelined", max_iters=rounds - 2,
+                         sim_server_block=blk if dev == "cpu" else None)
+        assert rk.pipelined
+        rk.launch_rounds(rounds)              # k reaches max_iters inside the launch: the grid must drain and exit
+        if dev == "cuda":
+            torch.cuda.synchronize()
+        st = blk.read_sctl()
+        res[dev] = (blk.w.cpu().clone(), st["k"], st["clock"], st["avail_count"], rk.read_ctl()["rounds_done"])
+    g, c = res["cuda"], res["cpu"]
+    assert g[1] == rounds - 2 and g[3] == 1          # accepted updates, worker idle again
+    assert g[1] <= c[1] + 1 and abs(g[2] - c[2]) <= 1  # the device may start one more round before it sees k >= max_iters
+    assert torch.allclose(g[0], c[0], rtol=2e-3, atol=1e-5)

@@ -75,3 +75,21 @@ def test_finite_taw_two_atomic_path(mode):
         r = explore(P=3, G=2, n_chunks=4, rounds=4, mode=mode, seed=seed, burst=1 + seed % 20, taw=0)
         saw_reject |= r["accepted"] < r["finished"]
     assert saw_reject
+
+
+@pytest.mark.parametrize("burst", [1, 8, 60])
+def test_pipelined_rounds_overlapping_tail(burst):
+    """Design check for the pipelined persistent kernel: round r+1 streams while round r's last CTA applies; state is
+    double-buffered by parity; a CTA may enter round r only after round r-2 has been published."""
+    for seed in range(60):
+        r = explore(P=2, G=3, n_chunks=7, rounds=6, mode="pipelined", seed=seed, burst=burst)
+        assert r["finished"] == 12 and r["accepted"] == 12
+        explore(P=1, G=4, n_chunks=3, rounds=5, mode="pipelined", seed=seed, burst=burst)
+        explore(P=3, G=1, n_chunks=2, rounds=4, mode="pipelined", seed=seed, burst=burst)
+        r = explore(P=2, G=3, n_chunks=5, rounds=7, mode="pipelined", seed=seed, burst=burst, max_iters=5)
+        assert r["accepted"] == 5
+
+
+def test_checker_catches_pipelined_buffer_reuse_bugs():
+    assert _fails_somewhere(P=1, G=3, n_chunks=6, rounds=5, mode="pipelined", burst=25, bug="pipe_no_reuse_wait") is not None
+    assert _fails_somewhere(P=1, G=3, n_chunks=6, rounds=5, mode="pipelined", burst=25, bug="pipe_single_buffer") is not None
