@@ -93,6 +93,8 @@ class ClusterScheduler:
         self._jobs: Dict[int, dict] = {}
         self._lock = threading.Lock()
         self._stopped = False
+        self._blocks_held: Dict[int, set] = {}       # source block id -> executors that already hold its data
+        self.last_task_binary_bytes = 0
         for e in range(self.num_executors):
             parent, child = self._ctx.Pipe()
             p = self._ctx.Process(target=_executor_main, args=(e, child), name=f"{name}-executor-{e}", daemon=True)
@@ -191,8 +193,14 @@ class ClusterScheduler:
         job_id = next(ClusterScheduler._job_ids)
         waiter = JobWaiter(job_id, len(parts), result_handler)
         now = time.perf_counter() * 1e3
-        payload = cloudpickle.dumps((dataset, func, self.fault_injector))
         executors = sorted({p % self.num_executors for p in parts})
+        # source data travels once per executor: blocks every target executor already holds are pickled as references
+        from ..data.dataset import ShippingContext
+        with self._lock:
+            held = {b: set(es) for b, es in self._blocks_held.items()}
+        with ShippingContext(lambda b: all(e in held.get(b, ()) for e in executors)) as ship:
+            payload = cloudpickle.dumps((dataset, func, self.fault_injector))
+        self.last_task_binary_bytes = len(payload)
         with self._lock:
             self._jobs[job_id] = {"waiter": waiter, "pending": set(parts), "on_task_lost": on_task_lost,
                                   "executors": executors, "submit_ms": now}
@@ -200,6 +208,9 @@ class ClusterScheduler:
                              "task_binary_bytes": len(payload)})
         for e in executors:
             self._send(e, ("binary", job_id, payload))
+        with self._lock:                              # only now may a later job refer to these blocks by id (pipe order)
+            for b in ship.shipped:
+                self._blocks_held.setdefault(b, set()).update(executors)
         for p in parts:
             self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0,
                                  "executor": p % self.num_executors, "t_ms": now})

@@ -52,6 +52,70 @@ _ds_ids = itertools.count(1)
 # process evaluates the partition (BlockManager MEMORY_ONLY analogue for the process-based scheduler)
 _BLOCK_STORE: dict = {}
 
+# ---- ship-once source data (cluster mode) -------------------------------------------------------------------
+# A dataset's SOURCE (the parallelised records / the HBM or host shards) sits at the root of its lineage, and the
+# lineage is part of every job's task binary.  Spark ships a ParallelCollectionRDD's data with every task; for an
+# iterative optimiser that submits one job per round that would re-send the whole training set each round.  Here the
+# source is wrapped in a SourceBlock: while a ClusterScheduler pickles a task binary, a block that every target
+# executor already holds is replaced by its id (a few bytes) and resolved from the executor-side store — the
+# "task size should be small" property the reference's cluster tests check (LinearRegressionClusterSuite,
+# mllib/regression/LinearRegressionSuite.scala:152-166).
+_SOURCE_STORE: dict = {}
+_block_ids = itertools.count(1)
+_pickle_ctx = threading.local()
+
+
+class BlockMissing(RuntimeError):
+    """An executor was sent a block reference for data it does not hold (e.g. a replaced executor)."""
+
+
+class SourceBlock:
+    __slots__ = ("block_id", "data")
+
+    def __init__(self, data, block_id: Optional[int] = None):
+        self.block_id = block_id if block_id is not None else ((os.getpid() << 32) | next(_block_ids))
+        self.data = data
+
+    @staticmethod
+    def _with_data(block_id, data):
+        _SOURCE_STORE[block_id] = data
+        return SourceBlock(data, block_id)
+
+    @staticmethod
+    def _from_store(block_id):
+        try:
+            return SourceBlock(_SOURCE_STORE[block_id], block_id)
+        except KeyError:
+            raise BlockMissing(f"source block {block_id:#x} is not in this executor's store") from None
+
+    def __reduce__(self):
+        ctx = getattr(_pickle_ctx, "ctx", None)
+        if ctx is not None and ctx.holds(self.block_id):
+            return (SourceBlock._from_store, (self.block_id,))
+        if ctx is not None:
+            ctx.shipping(self.block_id)
+        return (SourceBlock._with_data, (self.block_id, self.data))
+
+
+class ShippingContext:
+    """Installed by ClusterScheduler.submit_job around cloudpickle.dumps: decides per block whether the data or only the
+    reference travels, and records what was shipped."""
+
+    def __init__(self, held_by_all_targets: Callable[[int], bool]):
+        self.holds = held_by_all_targets
+        self.shipped: List[int] = []
+
+    def shipping(self, block_id: int) -> None:
+        self.shipped.append(block_id)
+
+    def __enter__(self):
+        _pickle_ctx.ctx = self
+        return self
+
+    def __exit__(self, *exc):
+        _pickle_ctx.ctx = None
+        return False
+
 
 class ShardedDataset:
     def __init__(self, scheduler, num_partitions: int,
@@ -77,17 +141,16 @@ class ShardedDataset:
         shards = list(shards)
         for p, s in enumerate(shards):
             s.partition = p
+        blk = SourceBlock(shards)
 
         def batch(p, tctx):
-            return shards[p]
+            return blk.data[p]
 
         def compute(p, tctx):
-            s = shards[p]
+            s = blk.data[p]
             return s.indexed_records() if s.gidx is not None else s.records()
 
-        ds = cls(scheduler, len(shards), compute, batch, None, name)
-        ds._shards = shards  # type: ignore[attr-defined]
-        return ds
+        return cls(scheduler, len(shards), compute, batch, None, name)
 
     @classmethod
     def from_records(cls, scheduler, records: Sequence[Any], num_partitions: int, name: str = "records"):
@@ -95,8 +158,8 @@ class ShardedDataset:
         records = list(records)
         n = len(records)
         bounds = [n * i // num_partitions for i in range(num_partitions + 1)]
-        parts = [records[bounds[i]:bounds[i + 1]] for i in range(num_partitions)]
-        return cls(scheduler, num_partitions, lambda p, t: iter(parts[p]), None, None, name)
+        blk = SourceBlock([records[bounds[i]:bounds[i + 1]] for i in range(num_partitions)])
+        return cls(scheduler, num_partitions, lambda p, t: iter(blk.data[p]), None, None, name)
 
     @classmethod
     def from_arrays(cls, scheduler, X, y, num_partitions: int, dtype=torch.float64, device=None,

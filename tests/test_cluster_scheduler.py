@@ -111,3 +111,28 @@ def test_lost_executor_fails_the_job_and_frees_the_worker():
         assert ctx.stat[0].available                                       # its worker is not stranded (quirk B.15 fixed)
     finally:
         s.stop()
+
+
+def test_task_binary_is_small_after_the_first_job(cluster):
+    """Source data travels to an executor once; later jobs over the same dataset ship only the lineage + closure
+    (the LinearRegressionClusterSuite "task size should be small" check)."""
+    rng = np.random.RandomState(0)
+    X = rng.randn(4000, 64)
+    y = rng.randn(4000)
+    sizes = []
+    cluster.listeners.add(lambda ev: sizes.append(ev["task_binary_bytes"]) if ev.get("event") == "job_start" else None)
+    ds = ShardedDataset.from_arrays(cluster, X, y, 4).zip_with_index().cache()      # zip_with_index runs the first job
+    n1 = ds.count()
+    first = max(sizes)
+    assert sum(1 for b in sizes if b > 100_000) == 1                               # ... and only that one carried the data
+    w = torch.zeros(64, dtype=torch.float64)
+    tot = ds.map_batch(lambda s, w=w: float((s.matvec(w) - s.y).pow(2).sum())).reduce(lambda a, b: a + b)
+    second = cluster.last_task_binary_bytes
+    assert n1 == 4000 and abs(tot - float((y ** 2).sum())) < 1e-6
+    assert first > 4000 * 64 * 8 and second < 20_000, (first, second)
+    # a different dataset over new data ships its own block once
+    ds2 = ShardedDataset.from_records(cluster, list(range(50_000)), 4)
+    assert ds2.count() == 50_000
+    big = cluster.last_task_binary_bytes
+    assert ds2.map(lambda x: x % 7).reduce(lambda a, b: a + b) == sum(i % 7 for i in range(50_000))
+    assert cluster.last_task_binary_bytes < big // 10
