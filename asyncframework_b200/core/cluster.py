@@ -38,38 +38,64 @@ from .scheduler import JobFailed, JobWaiter, ListenerBus, TaskContext  # noqa: F
 
 
 def _executor_main(eid: int, conn) -> None:
-    """Executor process: receive task binaries and task launches, send back results."""
+    """Executor process.  A receiver thread owns the pipe: task binaries and control messages ("drop" = the job finished
+    or was cancelled, "stop") take effect immediately, task launches are queued for the single task thread — so a
+    cancellation overtakes the tasks that are still queued behind a running one."""
+    import queue as _queue
     import torch
     torch.set_num_threads(1)
     binaries: Dict[int, Any] = {}
-    while True:
-        try:
-            msg = conn.recv()
-        except EOFError:
-            return
-        kind = msg[0]
-        if kind == "stop":
-            return
-        if kind == "binary":
-            _, job_id, payload = msg
-            binaries[job_id] = cloudpickle.loads(payload)
-            continue
-        if kind == "drop":
-            binaries.pop(msg[1], None)
-            continue
-        if kind == "task":
-            _, job_id, partition, attempt, submit_ms = msg
-            t0 = time.perf_counter()
+    tasks: "_queue.Queue" = _queue.Queue()
+    send_lock = threading.Lock()
+
+    def send(msg) -> None:
+        with send_lock:
+            conn.send(msg)
+
+    def receiver() -> None:
+        while True:
             try:
-                dataset, func, fault = binaries[job_id]
-                tctx = TaskContext(job_id, partition, attempt, eid, None, None, submit_ms)
-                if fault is not None:
-                    fault(tctx)
-                result = func(tctx, dataset.iterator(partition, tctx))
-                data = cloudpickle.dumps(result)
-                conn.send(("ok", job_id, partition, attempt, data, (time.perf_counter() - t0) * 1e3))
-            except BaseException as exc:  # noqa: BLE001
-                conn.send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
+                msg = conn.recv()
+            except (EOFError, OSError):
+                tasks.put(None)
+                return
+            kind = msg[0]
+            if kind == "stop":
+                tasks.put(None)
+                return
+            if kind == "binary":
+                try:
+                    binaries[msg[1]] = cloudpickle.loads(msg[2])
+                except BaseException as exc:  # noqa: BLE001  (reported when the job's tasks run)
+                    binaries[msg[1]] = exc
+            elif kind == "drop":
+                binaries.pop(msg[1], None)
+            elif kind == "task":
+                tasks.put(msg)
+
+    threading.Thread(target=receiver, daemon=True, name=f"executor-{eid}-recv").start()
+    while True:
+        msg = tasks.get()
+        if msg is None:
+            return
+        _, job_id, partition, attempt, submit_ms = msg
+        t0 = time.perf_counter()
+        binary = binaries.get(job_id)
+        if binary is None:                        # job finished or cancelled while this task was queued
+            send(("gone", job_id, partition, attempt, "", 0.0))
+            continue
+        try:
+            if isinstance(binary, BaseException):
+                raise binary
+            dataset, func, fault = binary
+            tctx = TaskContext(job_id, partition, attempt, eid, None, None, submit_ms)
+            if fault is not None:
+                fault(tctx)
+            result = func(tctx, dataset.iterator(partition, tctx))
+            data = cloudpickle.dumps(result)
+            send(("ok", job_id, partition, attempt, data, (time.perf_counter() - t0) * 1e3))
+        except BaseException as exc:  # noqa: BLE001
+            send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
 
 
 class ClusterScheduler:
@@ -134,6 +160,8 @@ class ClusterScheduler:
             if job is None:
                 continue
             waiter: JobWaiter = job["waiter"]
+            if kind == "gone":
+                continue
             if kind == "ok":
                 self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
                                      "run_ms": run_ms, "metrics": {"result_bytes": len(data)}})
@@ -156,6 +184,31 @@ class ClusterScheduler:
                     job["pending"].discard(partition)
                 else:
                     self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
+
+    def cancel_job(self, job_id: int, reason: str = "cancelled by user") -> bool:
+        """``SparkContext.cancelJob`` over executor processes: the waiter raises JobCancelled, the task binary is dropped on
+        the executors (queued tasks of the job then return immediately), results still in flight are ignored and the
+        submitter is told about every partition that will not deliver (async actions free their workers)."""
+        with self._lock:
+            job = self._jobs.pop(job_id, None)
+        if job is None or job["waiter"].done:
+            return False
+        job["waiter"].cancel(reason)
+        for e in job["executors"]:
+            try:
+                self._send(e, ("drop", job_id))
+            except (OSError, BrokenPipeError):
+                pass
+        if job["on_task_lost"] is not None:
+            for p in sorted(job["pending"]):
+                job["on_task_lost"](p, job["waiter"].failure)
+        self.listeners.post({"event": "job_end", "job": job_id, "cancelled": True, "t_ms": time.perf_counter() * 1e3})
+        return True
+
+    def cancel_all_jobs(self) -> int:
+        with self._lock:
+            ids = list(self._jobs)
+        return sum(1 for j in ids if self.cancel_job(j))
 
     def _executor_lost(self, eid: int) -> None:
         if self._stopped:

@@ -37,10 +37,19 @@ class TaskContext:
     stream: Any = None
     submit_ms: float = 0.0
     metrics: Dict[str, float] = field(default_factory=dict)
+    job: Any = None
+
+    def is_cancelled(self) -> bool:
+        """``TaskContext.isInterrupted``: true once the job this task belongs to has been cancelled."""
+        return bool(getattr(self.job, "cancelled", False))
 
 
 class JobFailed(RuntimeError):
     pass
+
+
+class JobCancelled(JobFailed):
+    """Raised by ``JobWaiter.wait`` after ``cancel()`` (SparkException "Job N cancelled", DAGScheduler.scala:816-823)."""
 
 
 class JobWaiter:
@@ -54,11 +63,25 @@ class JobWaiter:
         self._lock = threading.Lock()
         self._done = threading.Event()
         self.failure: Optional[BaseException] = None
+        self.cancelled = False
         if total == 0:
+            self._done.set()
+
+    def cancel(self, reason: str = "cancelled by user") -> None:
+        """``JobWaiter.cancel`` / ``SparkContext.cancelJob`` (scheduler/JobWaiter.scala:49-51): tasks of this job that have
+        not started are skipped, results of tasks that are already running are discarded, ``wait`` raises
+        :class:`JobCancelled`.  Running closures can poll ``TaskContext.is_cancelled()`` to stop early."""
+        with self._lock:
+            if self._done.is_set():
+                return
+            self.cancelled = True
+            self.failure = JobCancelled(f"job {self.job_id} {reason}")
             self._done.set()
 
     def task_succeeded(self, index: int, result: Any) -> None:
         with self._lock:  # `synchronized` in the reference
+            if self.cancelled:
+                return
             if self.result_handler is not None:
                 self.result_handler(index, result)
             self.finished += 1
@@ -72,6 +95,8 @@ class JobWaiter:
 
     def wait(self, timeout: Optional[float] = None) -> bool:
         ok = self._done.wait(timeout)
+        if isinstance(self.failure, JobCancelled):
+            raise self.failure
         if self.failure is not None:
             raise JobFailed(f"job {self.job_id} failed: {self.failure}") from self.failure
         return ok
@@ -125,6 +150,8 @@ class Scheduler:
         self._queues: List["queue.Queue[Optional[_Task]]"] = [queue.Queue() for _ in range(self.num_executors)]
         self._threads: List[threading.Thread] = []
         self._stopped = False
+        self._active: Dict[int, JobWaiter] = {}
+        self._jobs_lock = threading.Lock()
         self._streams = [None] * self.num_executors
         for e in range(self.num_executors):
             t = threading.Thread(target=self._executor_loop, args=(e,), name=f"{name}-executor-{e}", daemon=True)
@@ -153,7 +180,11 @@ class Scheduler:
         job: JobWaiter = task.job
         # NB: a failed sibling task does not cancel this one — in async mode every worker's result is
         # independent (the reference silently ignores failed async jobs).
-        tctx = TaskContext(job.job_id, task.partition, task.attempt, eid, self.device, stream, task.submit_ms)
+        tctx = TaskContext(job.job_id, task.partition, task.attempt, eid, self.device, stream, task.submit_ms, job=job)
+        if job.cancelled:                       # cancelled before this task started: skip it
+            self.listeners.post({"event": "task_skipped", "job": job.job_id, "partition": task.partition, "executor": eid})
+            self._task_lost(job, task.partition)
+            return
         self.listeners.post({"event": "task_start", "job": job.job_id, "partition": task.partition,
                              "attempt": task.attempt, "executor": eid, "t_ms": time.perf_counter() * 1e3})
         t0 = time.perf_counter()
@@ -167,6 +198,9 @@ class Scheduler:
             else:
                 result = task.func(tctx, task.dataset.iterator(task.partition, tctx))
         except Exception as exc:  # noqa: BLE001
+            if job.cancelled:                   # an interrupted task of a cancelled job is not a failure to retry
+                self._task_lost(job, task.partition)
+                return
             task.attempt += 1
             self.listeners.post({"event": "task_failed", "job": job.job_id, "partition": task.partition,
                                  "attempt": task.attempt, "error": repr(exc)})
@@ -179,12 +213,22 @@ class Scheduler:
             else:
                 self._queues[eid].put(task)   # retry on the same executor (hard affinity)
             return
+        if job.cancelled:                       # finished after the cancellation: the result is discarded
+            self._task_lost(job, task.partition)
+            return
         dt = (time.perf_counter() - t0) * 1e3
         self.listeners.post({"event": "task_end", "job": job.job_id, "partition": task.partition,
                              "executor": eid, "run_ms": dt, "metrics": tctx.metrics})
         job.task_succeeded(task.partition, result)
         if job.done:
             self.listeners.post({"event": "job_end", "job": job.job_id, "t_ms": time.perf_counter() * 1e3})
+
+    @staticmethod
+    def _task_lost(job: JobWaiter, partition: int) -> None:
+        """Tell the submitter (async actions free the worker here) that this partition will not deliver a result."""
+        on_fail = getattr(job, "on_task_lost", None)
+        if on_fail is not None:
+            on_fail(partition, job.failure)
 
     # ------------------------------------------------------------------ jobs
     def submit_job(self, dataset, func: Callable[[TaskContext, Iterable], Any],
@@ -196,6 +240,9 @@ class Scheduler:
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
         job = JobWaiter(next(Scheduler._job_ids), len(parts), result_handler)
         job.on_task_lost = on_task_lost  # type: ignore[attr-defined]
+        with self._jobs_lock:
+            self._active = {j: w for j, w in self._active.items() if not w.done}
+            self._active[job.job_id] = job
         now = time.perf_counter() * 1e3
         self.listeners.post({"event": "job_start", "job": job.job_id, "partitions": parts, "t_ms": now})
         for p in parts:
@@ -219,6 +266,22 @@ class Scheduler:
         if self.mode == 1:
             self.first_iter = 0
         return waiter
+
+    def cancel_job(self, job_id: int, reason: str = "cancelled by user") -> bool:
+        """``SparkContext.cancelJob``; returns False when the job is unknown or already finished."""
+        with self._jobs_lock:
+            job = self._active.get(job_id)
+        if job is None or job.done:
+            return False
+        job.cancel(reason)
+        self.listeners.post({"event": "job_end", "job": job_id, "cancelled": True, "t_ms": time.perf_counter() * 1e3})
+        return True
+
+    def cancel_all_jobs(self) -> int:
+        """``SparkContext.cancelAllJobs``: returns how many jobs were cancelled."""
+        with self._jobs_lock:
+            ids = [j for j, w in self._active.items() if not w.done]
+        return sum(1 for j in ids if self.cancel_job(j))
 
     def stream_for(self, partition: int):
         return self._streams[partition % self.num_executors]

@@ -136,3 +136,22 @@ def test_task_binary_is_small_after_the_first_job(cluster):
     big = cluster.last_task_binary_bytes
     assert ds2.map(lambda x: x % 7).reduce(lambda a, b: a + b) == sum(i % 7 for i in range(50_000))
     assert cluster.last_task_binary_bytes < big // 10
+
+
+def test_cancel_job_over_executor_processes(cluster):
+    from asyncframework_b200.core import JobCancelled
+    ds = ShardedDataset.from_records(cluster, list(range(16)), 8)
+
+    def slow(tctx, it):
+        import time as _t
+        _t.sleep(0.4)
+        return sum(it)
+
+    w = cluster.submit_job(ds, slow)                 # 8 tasks x 0.4 s on 2 executors = 1.6 s if it ran to completion
+    time.sleep(0.1)
+    t0 = time.perf_counter()
+    assert cluster.cancel_job(w.job_id) and not cluster.cancel_job(w.job_id)
+    with pytest.raises(JobCancelled):
+        w.wait(5)
+    assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 136      # queued tasks of the dropped job returned at once
+    assert time.perf_counter() - t0 < 1.4

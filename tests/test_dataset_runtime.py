@@ -228,3 +228,49 @@ def test_listener_bus_events(scheduler):
     ShardedDataset.from_records(scheduler, list(range(4)), 2).count()
     kinds = [e["event"] for e in events]
     assert kinds.count("job_start") == 1 and kinds.count("task_end") == 2 and kinds.count("job_end") == 1
+
+
+def test_job_cancellation_skips_pending_tasks_and_frees_async_workers():
+    """JobWaiter.cancel / cancel_job / cancel_all_jobs (JobCancellationSuite analogue): pending tasks are skipped, running
+    closures can poll is_cancelled(), wait() raises JobCancelled, and an ASYNC job's workers become available again."""
+    import threading
+    import time
+    from asyncframework_b200.core import AsyncContext, JobCancelled, Scheduler
+    from asyncframework_b200.data import ShardedDataset
+    sched = Scheduler(2, block_first_async_job=False)
+    try:
+        started, release, ran = threading.Event(), threading.Event(), []
+
+        def slow(tctx, it):
+            ran.append(tctx.partition_id)
+            started.set()
+            while not release.is_set() and not tctx.is_cancelled():
+                time.sleep(0.002)
+            return sum(it)
+
+        ds = ShardedDataset.from_records(sched, list(range(40)), 8)          # 8 tasks on 2 executors: 6 stay queued
+        events = []
+        sched.listeners.add(events.append)
+        w = sched.submit_job(ds, slow)
+        assert started.wait(5)
+        assert sched.cancel_job(w.job_id) and not sched.cancel_job(w.job_id)
+        with pytest.raises(JobCancelled):
+            w.wait(5)
+        release.set()
+        assert ds.count() == 40                                              # executors drained the skipped tasks and still work
+        assert len(ran) <= 2 + 0 and sum(1 for e in events if e["event"] == "task_skipped") >= 6
+        # asynchronous action: cancelling returns every selected worker to the available pool, no result is queued
+        AC = AsyncContext(8, sched)
+        AC.blocking = False
+        release.clear(); started.clear()
+        ds.map_partitions_with_index(lambda p, it: (started.set(), [release.wait(5)], list(it))[2]).async_reduce(lambda a, b: a + b, AC)
+        assert started.wait(5) and AC.stat.available_workers() < 8
+        assert sched.cancel_all_jobs() == 1
+        release.set()
+        deadline = time.time() + 5
+        while AC.stat.available_workers() < 8 and time.time() < deadline:
+            time.sleep(0.01)
+        assert AC.stat.available_workers() == 8 and AC.size() == 0
+    finally:
+        release.set()
+        sched.stop()
