@@ -27,7 +27,7 @@ from ..core import barriers
 from ..core.broadcast import AsyncBroadcast
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say
+from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -64,6 +64,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         alpha_bar = torch.zeros_like(w)
         hist = [torch.zeros(n, dtype=dtype, device=device) for n in sizes]      # sharded ScalarMap
         AC: AsyncContext = AsyncContext(P, sched)
+        watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(True)
         points_indexed = points.zip_with_index().cache()
         # remember each row's local position so sampled shards can address the history shard
@@ -154,9 +155,12 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         rep.extra["alpha_bar_norm"] = float(alpha_bar.norm())
         if cfg.eval_objective:
             rep.objective = evaluate_objective(points, opt_vars + [(elapsed, w.detach().clone())], cfg.loss)
+        rep.extra["dead_workers"] = list(watchdog.dead)
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'watchdog' in locals():
+            watchdog.stop()
         metrics.close()
         if own:
             sched.stop()

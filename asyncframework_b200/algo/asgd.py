@@ -23,7 +23,7 @@ import torch
 from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
-from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say)
+from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog)
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 from ..optim.gradient import make_gradient
@@ -48,6 +48,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         gradient = make_gradient(cfg.loss)
         w = torch.zeros(d, dtype=dtype, device=device)
         AC: AsyncContext = AsyncContext(P, sched)
+        watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(bool(cfg.extra.get("record_stat", True)))
         points_indexed = points.zip_with_index().cache()
         state = {"k": 0, "dropped": 0}
@@ -133,9 +134,12 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         rep.extra["injected_delay_ms"] = delay.injected_ms
         if cfg.eval_objective:
             rep.objective = evaluate_objective(points, opt_vars + [(elapsed, w.detach().clone())], cfg.loss)
+        rep.extra["dead_workers"] = list(watchdog.dead)
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'watchdog' in locals():
+            watchdog.stop()
         metrics.close()
         if own_sched:
             sched.stop()

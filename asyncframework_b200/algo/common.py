@@ -87,6 +87,24 @@ def partition_gradient(gradient: Gradient, shard: Shard, w: torch.Tensor, histor
     return g, float(l), n, coeff
 
 
+def start_watchdog(cfg: AsyncConfig, AC, metrics=None):
+    """Failure detection for the host drivers: a worker that stays busy without a heartbeat for
+    ``cfg.heartbeat_timeout_s`` is marked dead in ``AC.stat`` — async drivers then continue with the remaining workers
+    (dead workers are never selected by ``async_barrier`` nor counted as available), sync drivers abort."""
+    from ..utils.watchdog import HeartbeatWatchdog
+
+    def on_dead(worker: int) -> None:
+        say(cfg, f"worker {worker} declared dead (no heartbeat for {cfg.heartbeat_timeout_s} s)")
+        if metrics is not None:
+            metrics.emit("worker_dead", worker=worker)
+    timeout = float(cfg.heartbeat_timeout_s)
+    return HeartbeatWatchdog(AC.stat, timeout_s=timeout, period_s=max(0.01, min(0.5, timeout / 4)), on_dead=on_dead).start()
+
+
+class WorkerLost(RuntimeError):
+    """A synchronous (BSP) run cannot make progress without every worker."""
+
+
 def say(cfg: AsyncConfig, *args) -> None:
     """The reference drivers narrate on stdout (partition sizes, "Iteration k is finished"); ``cfg.quiet`` mutes that."""
     if not getattr(cfg, "quiet", False):

@@ -128,6 +128,10 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
     t0 = time.perf_counter()
     k = 0
     ck_next = cfg.checkpoint_every if cfg.checkpoint_every else None
+    # failure detection: rank 0 polls the device-side status table at every snapshot; a worker that has been
+    # busy without a heartbeat for cfg.heartbeat_timeout_s is reported (asynchronous runs simply continue without it)
+    from ..utils.watchdog import DeviceWatchdog
+    watchdog = DeviceWatchdog(engine, timeout_s=cfg.heartbeat_timeout_s) if (rank == 0 and is_async) else None
     while True:
         if is_async:
             engine.run_rounds(R)
@@ -142,6 +146,10 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
             snaps.append(((time.perf_counter() - t0) * 1e3, engine.weights().clone()))
             say(cfg, f"Iteration {k} is finished")
             metrics.emit("snapshot", k=k, elapsed_ms=snaps[-1][0])
+            if watchdog is not None:
+                for wdead in watchdog.check_once():
+                    say(cfg, f"worker {wdead} declared dead (no device heartbeat for {cfg.heartbeat_timeout_s} s)")
+                    metrics.emit("worker_dead", worker=wdead)
             while next_snap <= k:
                 next_snap += cfg.printer_freq
         if ck_next is not None and k >= ck_next and cfg.checkpoint_dir:
@@ -165,6 +173,9 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
             rep.staleness_hist[r.staleness] = rep.staleness_hist.get(r.staleness, 0) + 1
         rep.extra["avg_task_ms"] = {p: float(status[p]["avg_task_ms"]) for p in range(P)}
         rep.extra["avg_delay_ms"] = engine.server_state()["avg_delay_ns"] * 1e-6
+        if watchdog is not None:
+            watchdog.check_once()
+            rep.extra["dead_workers"] = list(watchdog.dead)
         snaps.append((elapsed, engine.weights().clone()))
     rep.final_weights = engine.weights().clone()
     if cfg.eval_objective:

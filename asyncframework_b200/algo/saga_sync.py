@@ -15,7 +15,7 @@ from ..core import barriers
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
 from .asaga import saga_partition
-from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say
+from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog, WorkerLost
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -43,6 +43,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         hist = [torch.zeros(n, dtype=dtype, device=device) for n in sizes]
         starts = [sum(sizes[:p]) for p in range(P)]
         AC: AsyncContext = AsyncContext(P, sched)
+        watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(True)
         points_indexed = points.zip_with_index().cache()
         opt_vars = [(0.0, w.detach().clone())]
@@ -68,6 +69,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             expected, got = len(filtered.selected_workers), 0
             while got < expected:
                 info = AC.collect_all(timeout=0.05)
+                if watchdog.dead:
+                    raise WorkerLost(f"worker(s) {watchdog.dead} stopped responding in iteration {k}: a BSP run cannot continue")
                 if info is None:
                     if AC.size() == 0 and AC.dropped_empty + got >= expected:
                         break
@@ -98,6 +101,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'watchdog' in locals():
+            watchdog.stop()
         metrics.close()
         if own:
             sched.stop()

@@ -16,7 +16,7 @@ from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say
+from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog, WorkerLost
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -43,6 +43,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         gradient = make_gradient(cfg.loss)
         w = torch.zeros(d, dtype=dtype, device=device)
         AC: AsyncContext = AsyncContext(P, sched)
+        watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(True)
         points_indexed = points.zip_with_index().cache()
         opt_vars = [(0.0, w.detach().clone())]
@@ -69,6 +70,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             got = 0
             while got < expected:
                 info = AC.collect_all(timeout=0.05)
+                if watchdog.dead:
+                    raise WorkerLost(f"worker(s) {watchdog.dead} stopped responding in iteration {k}: a BSP run cannot continue")
                 if info is None:
                     # an empty sampled partition yields no result (quirk B.5): don't wait forever
                     if AC.size() == 0 and AC.dropped_empty + got >= expected:
@@ -101,6 +104,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **{k2: v for k2, v in rep.to_dict().items() if k2 != "extra"})
         return rep
     finally:
+        if 'watchdog' in locals():
+            watchdog.stop()
         metrics.close()
         if own:
             sched.stop()

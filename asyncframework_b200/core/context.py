@@ -104,6 +104,7 @@ class AsyncContext(Generic[T]):
     def mark_submitted(self, worker: int) -> None:
         with self._inflight_lock:
             self._inflight[worker] += 1
+        self.stat.heartbeat(worker)          # "busy since": the watchdog measures silence from the submission, not from the last result
         self.stat.set_available(worker, False)
 
     def mark_finished(self, worker: int) -> bool:

@@ -227,3 +227,51 @@ def test_metrics_jsonl(tmp_path):
     algo.run(_cfg("sgd_sync", num_iterations=20, step_size=1.0, metrics_path=path, printer_freq=5))
     kinds = [json.loads(l)["kind"] for l in open(path)]
     assert kinds.count("snapshot") == 4 and kinds[-1] == "report"
+
+
+def test_async_driver_survives_a_hung_worker_and_sync_driver_aborts():
+    """Failure detection wired into the drivers: a worker whose task never returns is declared dead after
+    heartbeat_timeout_s; ASGD finishes with the remaining workers, synchronous SGD raises WorkerLost."""
+    import threading
+    from asyncframework_b200.algo.common import WorkerLost
+    from asyncframework_b200.core import Scheduler
+    release = threading.Event()
+    hung = {"n": 0}
+
+    def injector(tctx):
+        if tctx.partition_id == 2:
+            injector.calls += 1
+            if injector.calls == 6:              # worker 2's sixth task never returns
+                hung["n"] += 1
+                release.wait(20)                 # its executor thread is stuck until the test ends
+
+    try:
+        for name in ("asgd", "sgd_sync"):
+            sched = Scheduler(4, block_first_async_job=False)
+            injector.calls = 0
+            sched.fault_injector = injector
+            cfg = _cfg(name, num_iterations=3000 if name == "asgd" else 30, step_size=0.5, bucket_ratio=0.5, quiet=True, printer_freq=1000)
+            cfg.heartbeat_timeout_s = 0.05
+            cfg.eval_objective = False
+            holder = {}
+            runner = threading.Thread(target=lambda: holder.update(_try(lambda: algo.run(cfg, scheduler=sched))), daemon=True)
+            runner.start()
+            runner.join(60)
+            assert not runner.is_alive()
+            release.set()
+            sched.stop()
+            release.clear()
+            if name == "asgd":
+                rep = holder["ok"]
+                assert rep.accepted == 3000 and rep.extra["dead_workers"] == [2] and hung["n"] >= 1
+            else:
+                assert isinstance(holder["err"], WorkerLost)
+    finally:
+        release.set()
+
+
+def _try(fn):
+    try:
+        return {"ok": fn()}
+    except BaseException as exc:  # noqa: BLE001
+        return {"err": exc}
