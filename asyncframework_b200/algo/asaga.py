@@ -27,7 +27,7 @@ from ..core import barriers
 from ..core.broadcast import AsyncBroadcast
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog
+from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog, HostCheckpointer
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -70,6 +70,15 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         # remember each row's local position so sampled shards can address the history shard
         local_pos = {p: None for p in range(P)}
         state = {"k": 0, "dropped": 0}
+        ckpt = HostCheckpointer(cfg)
+        ck = ckpt.resume(device, dtype)
+        if ck is not None:
+            w.copy_(ck["w"])
+            if ck.get("alpha_bar") is not None:
+                alpha_bar.copy_(ck["alpha_bar"])
+            for p_, h_ in ck["history"].items():
+                hist[p_].copy_(h_)
+            state["k"] = int(ck["k"])
         opt_vars = [(0.0, w.detach().clone())]
         waits = WaitTimer()
         delay = DelayInjector(P, cfg.coeff, cfg.warmup_updates_per_worker * P)
@@ -108,6 +117,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                             opt_vars.append((now_ms() - start, w.detach().clone()))
                             metrics.emit("snapshot", k=k, elapsed_ms=now_ms() - start)
                         state["k"] = k + 1
+                        ckpt.maybe_save(k + 1, lambda: dict(w=w.detach().clone(), alpha_bar=alpha_bar.detach().clone(),
+                                                            history={p_: h_.detach().clone() for p_, h_ in enumerate(hist)}))
                     else:
                         state["dropped"] += 1                                   # history untouched
         th = threading.Thread(target=updater, name="asaga-updater", daemon=True)
@@ -115,10 +126,10 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
 
         need = math.floor(P * cfg.bucket_ratio)
         pred = barriers.bucket(P, cfg.bucket_ratio)
-        last_k, resubmits = -1, 0
+        last_k, resubmits, submitted = -1, 0, 0
         while state["k"] < iters:
             k = state["k"]
-            init_workers = P if k == 0 else AC.stat.available_workers()
+            init_workers = P if submitted == 0 else AC.stat.available_workers()   # STAT is empty before the first submission
             if init_workers >= need:
                 a = AsyncBroadcast(AC, w, slots=cfg.history_slots)                # versioned broadcast (:268)
                 delay.maybe_calibrate(k)
@@ -142,6 +153,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                 sampled.map_batch(task).async_aggregate(
                     lambda: None, lambda acc, r: r if acc is None else acc, lambda x, y: x if y is None else y, AC)
                 waits.on_submit(workers, now_ms())
+                submitted += 1
             else:
                 time.sleep(0.001)
         th.join(timeout=10)
@@ -159,6 +171,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'ckpt' in locals():
+            ckpt.close()
         if 'watchdog' in locals():
             watchdog.stop()
         metrics.close()

@@ -23,7 +23,7 @@ import torch
 from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
-from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog)
+from .common import (compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog, HostCheckpointer)
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 from ..optim.gradient import make_gradient
@@ -52,6 +52,11 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         AC.set_record_stat(bool(cfg.extra.get("record_stat", True)))
         points_indexed = points.zip_with_index().cache()
         state = {"k": 0, "dropped": 0}
+        ckpt = HostCheckpointer(cfg)
+        ck = ckpt.resume(device, dtype)
+        if ck is not None:
+            w.copy_(ck["w"])
+            state["k"] = int(ck["k"])
         opt_vars = [(0.0, w.detach().clone())]
         waits = WaitTimer()
         delay = DelayInjector(P, cfg.coeff, cfg.warmup_updates_per_worker * P)
@@ -91,6 +96,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                             opt_vars.append((now_ms() - start, w.detach().clone()))
                             metrics.emit("snapshot", k=k, elapsed_ms=now_ms() - start)
                         state["k"] = k + 1
+                        ckpt.maybe_save(k + 1, lambda: dict(w=w.detach().clone()))
                     else:
                         state["dropped"] += 1                                   # drop; worker is re-queued by STAT
         th = threading.Thread(target=updater, name="asgd-updater", daemon=True)
@@ -98,10 +104,10 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
 
         need = math.floor(P * cfg.bucket_ratio)
         pred = barriers.bucket(P, cfg.bucket_ratio)
-        last_k, resubmits = -1, 0
+        last_k, resubmits, submitted = -1, 0, 0
         while state["k"] < iters:
             k = state["k"]
-            init_workers = P if k == 0 else AC.stat.available_workers()
+            init_workers = P if submitted == 0 else AC.stat.available_workers()   # STAT is empty before the first submission
             if init_workers >= need:
                 a = AC.broadcast(w)                                             # snapshot of w NOW (:242)
                 delay.maybe_calibrate(k)
@@ -120,6 +126,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
                 index_grad = sampled.map_batch(lambda s, a=a: partition_gradient(gradient, s, a.value)[0])
                 index_grad.async_reduce(lambda x, y: x.add_(y), AC)
                 waits.on_submit(workers, now_ms())
+                submitted += 1
             else:
                 time.sleep(0.001)
         th.join(timeout=10)
@@ -138,6 +145,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'ckpt' in locals():
+            ckpt.close()
         if 'watchdog' in locals():
             watchdog.stop()
         metrics.close()

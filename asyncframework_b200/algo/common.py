@@ -101,6 +101,59 @@ def start_watchdog(cfg: AsyncConfig, AC, metrics=None):
     return HeartbeatWatchdog(AC.stat, timeout_s=timeout, period_s=max(0.01, min(0.5, timeout / 4)), on_dead=on_dead).start()
 
 
+class HostCheckpointer:
+    """``--checkpoint_dir/--checkpoint_every/--resume`` for the host (cpu) drivers — the same file format as the fused
+    backend (utils/checkpoint.py); files are written by a background thread from copies of the state, so the updater never
+    waits for the disk."""
+
+    def __init__(self, cfg: AsyncConfig):
+        self.cfg = cfg
+        self.every = int(cfg.checkpoint_every) if (cfg.checkpoint_every and cfg.checkpoint_dir) else 0
+        self.next = self.every
+        self._writer = None
+
+    def resume(self, device, dtype):
+        """Returns the checkpoint dict (tensors on ``device``/``dtype``) or None when ``cfg.resume`` is unset."""
+        if not self.cfg.resume:
+            return None
+        from ..utils.checkpoint import load_checkpoint
+        ck = load_checkpoint(self.cfg.resume, map_location="cpu")
+        ck["w"] = ck["w"].to(device=device, dtype=dtype)
+        if ck.get("alpha_bar") is not None:
+            ck["alpha_bar"] = ck["alpha_bar"].to(device=device, dtype=dtype)
+        ck["history"] = {int(p): h.to(device=device, dtype=dtype) for p, h in (ck.get("history") or {}).items()}
+        while self.every and self.next <= int(ck["k"]):
+            self.next += self.every
+        return ck
+
+    def maybe_save(self, k: int, make_state) -> bool:
+        """``make_state()`` -> dict(w=..., alpha_bar=..., history={p: tensor}) of COPIES, called only when a snapshot is due."""
+        if not self.every or k < self.next:
+            return False
+        import json
+        import os
+        from ..utils.checkpoint import AsyncCheckpointWriter
+        if self._writer is None:
+            self._writer = AsyncCheckpointWriter()
+        d = self.cfg.checkpoint_dir
+        os.makedirs(d, exist_ok=True)
+
+        def publish(k=k):
+            tmp = os.path.join(d, "latest.json.tmp")
+            with open(tmp, "w") as f:
+                json.dump({"k": int(k), "world": 1}, f)
+            os.replace(tmp, os.path.join(d, "latest.json"))
+        self._writer.submit(None, after=publish, path=os.path.join(d, "rank0.pt"), k=int(k), config=self.cfg.to_dict(), **make_state())
+        while self.next <= k:
+            self.next += self.every
+        return True
+
+    def close(self) -> None:
+        if self._writer is not None:
+            self._writer.close()
+            self._writer = None
+
+
 class WorkerLost(RuntimeError):
     """A synchronous (BSP) run cannot make progress without every worker."""
 

@@ -128,6 +128,10 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
     t0 = time.perf_counter()
     k = 0
     ck_next = cfg.checkpoint_every if cfg.checkpoint_every else None
+    ck_writer = None
+    if ck_next is not None and cfg.checkpoint_dir:
+        from ..utils.checkpoint import AsyncCheckpointWriter
+        ck_writer = AsyncCheckpointWriter()          # snapshots are written in the background (copy-on-snapshot)
     # failure detection: rank 0 polls the device-side status table at every snapshot; a worker that has been
     # busy without a heartbeat for cfg.heartbeat_timeout_s is reported (asynchronous runs simply continue without it)
     from ..utils.watchdog import DeviceWatchdog
@@ -154,12 +158,14 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
                 next_snap += cfg.printer_freq
         if ck_next is not None and k >= ck_next and cfg.checkpoint_dir:
             from ..utils.checkpoint import save_engine_checkpoint
-            save_engine_checkpoint(engine, cfg, k)
+            save_engine_checkpoint(engine, cfg, k, writer=ck_writer)
             ck_next += cfg.checkpoint_every
         if k >= iters:
             break
     engine.synchronize()
     elapsed = (time.perf_counter() - t0) * 1e3
+    if ck_writer is not None:
+        ck_writer.close()
     engine.barrier()
     rep = RunReport(cfg.algorithm, P, iterations=k, elapsed_ms=elapsed, snapshots=snaps, accepted=k)
     if rank == 0:

@@ -15,7 +15,7 @@ from ..core import barriers
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
 from .asaga import saga_partition
-from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog, WorkerLost
+from .common import compute_dtype, load_points, make_scheduler, now_ms, resolve_device, run_cli, say, start_watchdog, WorkerLost, HostCheckpointer
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -46,12 +46,22 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(True)
         points_indexed = points.zip_with_index().cache()
+        ckpt = HostCheckpointer(cfg)
+        ck = ckpt.resume(device, dtype)
+        k0 = 0
+        if ck is not None:
+            w.copy_(ck["w"])
+            if ck.get("alpha_bar") is not None:
+                alpha_bar.copy_(ck["alpha_bar"])
+            for p_, h_ in ck["history"].items():
+                hist[p_].copy_(h_)
+            k0 = int(ck["k"])
         opt_vars = [(0.0, w.detach().clone())]
         waits = WaitTimer()
         delay = DelayInjector(P, cfg.coeff, cfg.warmup_updates_per_worker)
         b, gamma = cfg.batch_rate, cfg.step_size
         start = now_ms()
-        for k in range(cfg.num_iterations):
+        for k in range(k0, cfg.num_iterations):
             a = AC.broadcast(w)
             delay.maybe_calibrate(k)
             filtered = points_indexed.async_barrier(barriers.asp(), AC.stat)
@@ -86,6 +96,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             w.add_(G, alpha=-gamma / (b * N))
             w.add_(alpha_bar, alpha=-gamma)
             alpha_bar.add_(G, alpha=1.0 / N)
+            ckpt.maybe_save(k + 1, lambda: dict(w=w.detach().clone(), alpha_bar=alpha_bar.detach().clone(),
+                                                history={p_: h_.detach().clone() for p_, h_ in enumerate(hist)}))
             if k % cfg.printer_freq == 0:
                 say(cfg, f"Iteration {k} is finished")
                 opt_vars.append((now_ms() - start, w.detach().clone()))
@@ -101,6 +113,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **rep.to_dict())
         return rep
     finally:
+        if 'ckpt' in locals():
+            ckpt.close()
         if 'watchdog' in locals():
             watchdog.stop()
         metrics.close()

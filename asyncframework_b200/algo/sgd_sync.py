@@ -16,7 +16,7 @@ from ..config import AsyncConfig
 from ..core import barriers
 from ..core.context import AsyncContext
 from ..optim.gradient import make_gradient
-from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog, WorkerLost
+from .common import compute_dtype, load_points, make_scheduler, now_ms, partition_gradient, resolve_device, run_cli, say, start_watchdog, WorkerLost, HostCheckpointer
 from .delay import DelayInjector
 from .telemetry import MetricsLog, RunReport, WaitTimer, evaluate_objective
 
@@ -46,13 +46,19 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         watchdog = start_watchdog(cfg, AC, metrics)
         AC.set_record_stat(True)
         points_indexed = points.zip_with_index().cache()
+        ckpt = HostCheckpointer(cfg)
+        ck = ckpt.resume(device, dtype)
+        k0 = 0
+        if ck is not None:
+            w.copy_(ck["w"])
+            k0 = int(ck["k"])
         opt_vars = [(0.0, w.detach().clone())]
         waits = WaitTimer()
         delay = DelayInjector(P, cfg.coeff, cfg.warmup_updates_per_worker)
         b, gamma = cfg.batch_rate, cfg.step_size
         start = now_ms()
         losses = []
-        for k in range(cfg.num_iterations):
+        for k in range(k0, cfg.num_iterations):
             a = AC.broadcast(w)
             delay.maybe_calibrate(k)
             filtered = points_indexed.async_barrier(barriers.asp(), AC.stat)
@@ -87,6 +93,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             AC.dropped_empty = 0
             w.add_(acc, alpha=-gamma / math.sqrt(k + 1) / (b * N))
             losses.append(loss_sum / max(cnt, 1))
+            ckpt.maybe_save(k + 1, lambda: dict(w=w.detach().clone()))
             if k % cfg.printer_freq == 0:
                 say(cfg, f"Iteration {k} is finished")
                 opt_vars.append((now_ms() - start, w.detach().clone()))
@@ -104,6 +111,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         metrics.emit("report", **{k2: v for k2, v in rep.to_dict().items() if k2 != "extra"})
         return rep
     finally:
+        if 'ckpt' in locals():
+            ckpt.close()
         if 'watchdog' in locals():
             watchdog.stop()
         metrics.close()

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import json
 import os
+import queue
+import threading
 import time
 from typing import Any, Dict, Optional
 
@@ -45,18 +47,94 @@ def load_checkpoint(path: str, map_location="cpu") -> Dict[str, Any]:
     return ck
 
 
-def save_engine_checkpoint(engine, cfg, k: int) -> str:
-    """Snapshot a FusedEngine: rank-local file with this rank's history shards + (rank 0) the model."""
+class AsyncCheckpointWriter:
+    """Copy-on-snapshot checkpointing that does not stall the update stream: the caller takes device-side
+    copies of the state (a few KB of model + the history shards, D2D on the launching stream) and hands them over with a
+    CUDA event; a background thread waits for the event, moves the copies to the host and writes the file.  Rounds
+    enqueued after the snapshot never wait for the D2H transfer or the disk.  At most ``max_pending`` snapshots are
+    buffered (a slower disk then back-pressures ``submit``)."""
+
+    def __init__(self, max_pending: int = 2):
+        self._q: "queue.Queue" = queue.Queue(maxsize=max_pending)
+        self.written = 0
+        self.error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._loop, name="afb-checkpoint-writer", daemon=True)
+        self._thread.start()
+
+    def _loop(self) -> None:
+        while True:
+            job = self._q.get()
+            try:
+                if job is None:
+                    return
+                event, kwargs, after = job
+                if event is not None:
+                    event.synchronize()               # the device-side copies are complete
+                save_checkpoint(**kwargs)
+                if after is not None:
+                    after()
+                self.written += 1
+            except BaseException as exc:  # noqa: BLE001  (surfaced by flush/close)
+                self.error = exc
+            finally:
+                self._q.task_done()
+
+    def submit(self, event, after=None, **save_kwargs) -> None:
+        if self.error is not None:
+            raise RuntimeError("checkpoint writer failed") from self.error
+        self._q.put((event, save_kwargs, after))
+
+    def flush(self) -> None:
+        self._q.join()
+        if self.error is not None:
+            raise RuntimeError("checkpoint writer failed") from self.error
+
+    def close(self) -> None:
+        self._q.join()
+        self._q.put(None)
+        self._thread.join(timeout=30)
+        if self.error is not None:
+            raise RuntimeError("checkpoint writer failed") from self.error
+
+
+def save_engine_checkpoint(engine, cfg, k: int, writer: Optional[AsyncCheckpointWriter] = None) -> str:
+    """Snapshot a FusedEngine: rank-local file with this rank's history shards + (rank 0) the model.  With a ``writer`` the
+    state is copied on the device and written in the background; without one the call returns after the file is on disk."""
     d = cfg.checkpoint_dir
     os.makedirs(d, exist_ok=True)
     st = engine.server_state()
-    hist = {wid: rk.hist for rk, wid in zip(engine.kernels, engine.local_worker_ids) if rk.hist is not None}
     path = os.path.join(d, f"rank{engine.rank}.pt")
-    save_checkpoint(path, w=engine.weights(), k=k, clock=st["clock"], alpha_bar=engine.alpha_bar(), history=hist,
-                    config=cfg.to_dict(), extra={"world": engine.world})
-    if engine.rank == 0:
-        with open(os.path.join(d, "latest.json"), "w") as f:
-            json.dump({"k": int(k), "time": time.time(), "world": engine.world}, f)
+    rank, world = engine.rank, engine.world
+
+    def publish_latest():
+        if rank == 0:
+            tmp = os.path.join(d, "latest.json.tmp")
+            with open(tmp, "w") as f:
+                json.dump({"k": int(k), "time": time.time(), "world": world}, f)
+            os.replace(tmp, os.path.join(d, "latest.json"))
+
+    if writer is None:
+        hist = {wid: rk.hist for rk, wid in zip(engine.kernels, engine.local_worker_ids) if rk.hist is not None}
+        save_checkpoint(path, w=engine.weights(), k=k, clock=st["clock"], alpha_bar=engine.alpha_bar(), history=hist,
+                        config=cfg.to_dict(), extra={"world": world})
+        publish_latest()
+        return path
+    from ..parallel import _devapi as _dev
+    # copy-on-snapshot: device-side clones ordered after the rounds already enqueued on the worker streams
+    cur = _dev.current_stream(engine.device)
+    for stt in engine.streams:
+        if stt is not cur:
+            ev = _dev.new_event(engine.device)
+            ev.record(stt)
+            cur.wait_event(ev)
+    hist = {wid: rk.hist.clone() for rk, wid in zip(engine.kernels, engine.local_worker_ids) if rk.hist is not None}
+    w = engine.weights().clone()
+    ab = engine.alpha_bar()
+    ab = None if ab is None else ab.clone()
+    done = _dev.new_event(engine.device)
+    done.record(cur)
+    writer.submit(done, after=publish_latest, path=path, w=w, k=k, clock=st["clock"], alpha_bar=ab, history=hist,
+                  config=cfg.to_dict(), extra={"world": world})
     return path
 
 

@@ -2,6 +2,7 @@
 import json
 import time
 
+import pytest
 import torch
 
 from asyncframework_b200.core import AsyncContext, Scheduler
@@ -69,3 +70,18 @@ def test_event_log_replay(tmp_path):
         assert len(summarize(str(tmp_path / "events.jsonl"))) == 2
     finally:
         s.stop()
+
+
+def test_async_checkpoint_writer_orders_and_reports_errors(tmp_path):
+    from asyncframework_b200.utils.checkpoint import AsyncCheckpointWriter
+    wr = AsyncCheckpointWriter(max_pending=2)
+    published = []
+    for k in (10, 20, 30):
+        wr.submit(None, after=lambda k=k: published.append(k), path=str(tmp_path / "ck" / "rank0.pt"), w=torch.full((4,), float(k)), k=k)
+    wr.flush()
+    assert published == [10, 20, 30] and wr.written == 3
+    ck = load_checkpoint(str(tmp_path / "ck" / "rank0.pt"))
+    assert ck["k"] == 30 and float(ck["w"][0]) == 30.0
+    wr.submit(None, path=str(tmp_path / "ck"), w=torch.zeros(1), k=1)          # a directory: the write fails ...
+    with pytest.raises(RuntimeError):
+        wr.close()                                                            # ... and the failure surfaces on close

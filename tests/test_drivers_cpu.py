@@ -275,3 +275,31 @@ def _try(fn):
         return {"ok": fn()}
     except BaseException as exc:  # noqa: BLE001
         return {"err": exc}
+
+
+@pytest.mark.parametrize("name,step", [("sgd_sync", 0.5), ("saga_sync", 0.05)])
+def test_host_driver_checkpoint_resume_is_exact_for_bsp(name, step, tmp_path):
+    """Synchronous drivers are deterministic: 40 iterations == 20 iterations + checkpoint + resume for 20 more."""
+    full = algo.run(_cfg(name, num_iterations=40, step_size=step, quiet=True))
+    ckdir = str(tmp_path / "ck")
+    algo.run(_cfg(name, num_iterations=20, step_size=step, quiet=True, checkpoint_dir=ckdir, checkpoint_every=10))
+    from asyncframework_b200.utils import load_checkpoint
+    ck = load_checkpoint(ckdir)
+    assert ck["k"] == 20 and ck["config"]["algorithm"] == name
+    if name == "saga_sync":
+        assert ck["alpha_bar"] is not None and len(ck["history"]) == 4
+    resumed = algo.run(_cfg(name, num_iterations=40, step_size=step, quiet=True, resume=ckdir))
+    assert torch.allclose(resumed.final_weights, full.final_weights, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,step", [("asgd", 0.5), ("asaga", 0.05)])
+def test_host_driver_checkpoint_resume_async(name, step, tmp_path):
+    ckdir = str(tmp_path / "ck")
+    first = algo.run(_cfg(name, num_iterations=150, step_size=step, quiet=True, checkpoint_dir=ckdir, checkpoint_every=50))
+    from asyncframework_b200.utils import load_checkpoint
+    ck = load_checkpoint(ckdir)
+    assert ck["k"] in (100, 150) and ck["w"].numel() == 20
+    resumed = algo.run(_cfg(name, num_iterations=300, step_size=step, quiet=True, resume=ckdir))
+    assert resumed.accepted == 300
+    assert resumed.objective[-1][1] <= first.objective[-1][1] * 1.05        # continued from the checkpoint, not from zero
+    assert resumed.objective[0][1] < first.objective[0][1] * 0.5

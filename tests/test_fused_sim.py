@@ -154,6 +154,11 @@ def test_fused_driver_on_simulator(alg, step, P, tmp_path):
     from asyncframework_b200.utils import load_checkpoint
     ck = load_checkpoint(str(tmp_path / "ck"))
     assert ck["k"] >= 100 and ck["w"].numel() == 12
+    import json
+    latest = json.load(open(tmp_path / "ck" / "latest.json"))          # published by the background writer AFTER the file
+    assert latest["k"] == ck["k"] and not list((tmp_path / "ck").glob("*.tmp"))
+    if alg in ("asaga", "saga_sync"):
+        assert set(ck["history"]) == set(range(P)) and all(h.numel() > 0 for h in ck["history"].values())
 
 
 def test_device_watchdog_on_simulated_status_table():
