@@ -68,13 +68,21 @@ for run, title in (("run11", "Final build (prologue overlap, early clock ticket,
 cfgs = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench", "*", "configs*.jsonl")))
 if cfgs:
     out += ["## Other BASELINE configs (8 GPUs, `benchmarks/run_config.py`)", "",
-            "| config | algo | delay intensity | workers | iterations/s | ms/iteration | objective start -> end | mode |", "|---|---|---|---|---|---|---|---|"]
+            "| config | algo | delay intensity | workers | iterations/s | ms/iteration | device ms for the run | objective start -> end | mode |", "|---|---|---|---|---|---|---|---|---|"]
+    eq = {}
     for c in cfgs:
         for line in open(c):
             r = json.loads(line)
+            total_ms = r['ms_per_iteration'] * r['iterations']
             out.append(f"| {r['config']} | {r['algo']} | {r['delay_intensity']} | {r['workers']} | {r['iterations_per_s']:.0f} | "
-                       f"{r['ms_per_iteration']:.4f} | {r['objective_start']:.4f} -> {r['objective_end']:.4f} | {r.get('mode', 'fixed rounds per worker')} ({os.path.basename(os.path.dirname(c))}) |")
+                       f"{r['ms_per_iteration']:.4f} | {total_ms:.1f} | {r['objective_start']:.4f} -> {r['objective_end']:.4f} | {r.get('mode', 'fixed rounds per worker')} ({os.path.basename(os.path.dirname(c))}) |")
+            if r['config'] == 'straggler' and 'run11' in c:
+                eq.setdefault(r['delay_intensity'], {})[r['algo']] = (total_ms, r['objective_end'])
     out.append("")
+    if eq:
+        out += ["Wall-clock (device time) to the same training loss, equal work (300 x 8 sampled batches; run11): " + "; ".join(
+            f"delay {d}: ASAGA {v['asaga'][0]:.1f} ms (loss {v['asaga'][1]:.4f}) vs synchronous SAGA {v['saga_sync'][0]:.1f} ms "
+            f"(loss {v['saga_sync'][1]:.4f}) = {v['saga_sync'][0] / v['asaga'][0]:.2f}x" for d, v in sorted(eq.items()) if 'asaga' in v and 'saga_sync' in v) + ".", ""]
 tm = os.path.join(ROOT, "profiles", "round_timeline_model.json")
 if os.path.exists(tm):
     t = json.load(open(tm))

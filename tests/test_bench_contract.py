@@ -37,3 +37,18 @@ def test_bench_json_contract_on_simulator():
     assert 0.0 < e["last_loss_per_row"] < 1.0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["config"]["accepted_updates_total"] == (3 + 5 + 3 + 5) * 2   # warm-up + timed + e2e warm-up + e2e, 2 workers
+
+
+def test_time_to_loss_benchmark_runs_on_the_simulator():
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "time_to_loss.py"), "--impl", "ours", "--target", "0.6",
+                          "--eval-every", "5", "--max-iters", "60", "--gamma", "1e-4"], capture_output=True, text=True, timeout=240,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), cwd=root)
+    assert res.returncode == 0, res.stderr[-1500:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("TIME_TO_LOSS ")][-1]
+    r = json.loads(line[len("TIME_TO_LOSS "):])
+    assert r["impl"] == "ours" and r["reached"] and r["ms_to_target"] > 0 and r["curve"][0][1] > r["curve"][-1][1]
