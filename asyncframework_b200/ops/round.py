@@ -281,7 +281,14 @@ class RoundKernel:
                           and int(delay_mode) == 0 and int(p.seed_mode) in (1, 2))
         self.persist = (variant in ("persist", "pipelined") and not self.pipelined and self.is_dense and algo != "grad_only"
                         and not self.rollback)
+        # CSR shards: "persist"/"pipelined" select the persistent fused wide-model round (csrc/experimental/csr_round_persist.cu):
+        # one resident grid, multi-CTA pull/push separated by in-kernel grid barriers instead of the 4-launch split round
+        self.persist_csr = (variant in ("persist", "pipelined") and not self.is_dense and algo in ("asgd", "asaga") and not self.rollback)
         self._persist_lib = None
+        if self.persist_csr and not self.sim:
+            from .._native import experimental
+            self._persist_lib = experimental()
+            self._grid_bar = torch.zeros(self._persist_lib.afb_grid_bar_bytes(), dtype=torch.uint8, device=dev)
         if (self.persist or self.pipelined) and not self.sim:
             from .._native import experimental
             self._persist_lib = experimental()
@@ -347,7 +354,7 @@ class RoundKernel:
         grid that cannot be fully co-resident, because the in-kernel round barrier would deadlock)."""
         if n <= 0:
             return
-        if not (self.persist or self.pipelined) or n == 1:
+        if not (self.persist or self.pipelined or self.persist_csr) or (n == 1 and not self.persist_csr):
             for _ in range(n):
                 self.launch(stream)
             return
@@ -362,6 +369,12 @@ class RoundKernel:
             return
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.params.pdl = 0
+        if self.persist_csr:
+            check(self._persist_lib.afb_csr_round_persist_launch(C.byref(self.params), int(n), self.grid, int(share), self._grid_bar.data_ptr(),
+                                                                 int(s.cuda_stream)), "persistent CSR round kernel launch")
+            self.launches += 1
+            self.rounds_launched += n
+            return
         if self.pipelined:
             if share != 1:
                 raise ValueError("the pipelined variant needs the whole GPU: one logical worker per GPU")
@@ -392,7 +405,7 @@ class RoundKernel:
     @property
     def variant_effective(self) -> str:
         """The kernel ``launch_rounds`` actually uses (an experimental request that is not eligible falls back)."""
-        return "pipelined" if self.pipelined else ("persist" if self.persist else self.variant)
+        return "pipelined" if self.pipelined else ("persist" if (self.persist or self.persist_csr) else self.variant)
 
     @property
     def w_view(self) -> torch.Tensor:

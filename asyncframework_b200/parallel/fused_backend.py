@@ -160,7 +160,7 @@ class FusedEngine:
     # ------------------------------------------------------------------ hot path
     def run_rounds(self, n: int) -> None:
         """Enqueue ``n`` rounds on every local worker.  No host synchronisation."""
-        if all(rk.persist or rk.pipelined for rk in self.kernels):
+        if all(rk.persist or rk.pipelined or rk.persist_csr for rk in self.kernels):
             # experimental persistent variant: one resident kernel per worker loops over the n rounds
             for rk, st in zip(self.kernels, self.streams):
                 rk.launch_rounds(n, st, share=len(self.kernels))

@@ -244,3 +244,20 @@ def test_pipelined_variant_semantics_on_the_simulator():
     finally:
         os.environ.pop("AFB_DENSE_VARIANT", None)
     assert eng2.kernels[0].variant_effective == "persist"
+
+
+def test_persistent_csr_variant_on_the_simulator():
+    """CSR shards + AFB_DENSE_VARIANT=persist select the persistent wide-model round; on the simulator that is n rounds."""
+    from asyncframework_b200.data.generators import synthetic_shard
+    cfg = AsyncConfig(algorithm="asgd", num_features=300, num_rows=600, num_partitions=2, num_iterations=1 << 30, step_size=0.5,
+                      batch_rate=0.3, loss="logistic", backend="fused", barrier="asp")
+    shards = [synthetic_shard("rcv1", 300, p, 2, seed=3, device="cpu", num_features=300, row_offset=300 * p) for p in range(2)]
+    os.environ["AFB_DENSE_VARIANT"] = "persist"
+    try:
+        eng = FusedEngine(cfg, shards, 600, [0, 1], device="cpu")
+    finally:
+        os.environ.pop("AFB_DENSE_VARIANT", None)
+    assert all(rk.persist_csr and rk.variant_effective == "persist" for rk in eng.kernels)
+    eng.run_rounds(4)
+    st = eng.server_state()
+    assert st["k"] == 8 and eng.launches == 2 and torch.isfinite(eng.weights()).all()

@@ -81,3 +81,34 @@ def test_pipelined_rounds_match_the_simulator_semantics(d):
     assert g[1] == rounds - 2 and g[3] == 1          # accepted updates, worker idle again
     assert g[1] <= c[1] + 1 and abs(g[2] - c[2]) <= 1  # the device may start one more round before it sees k >= max_iters
     assert torch.allclose(g[0], c[0], rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("algo,loss,d", [("asgd", "logistic", 47236), ("asaga", "least_squares", 6000)])
+def test_persistent_csr_round_matches_the_split_round(algo, loss, d):
+    """Wide sparse model: n rounds in ONE persistent launch with in-kernel grid barriers (multi-CTA pull / push) == n split
+    rounds (gate, pull, grad, push kernels).  Single worker; float atomics reorder sums, hence the tolerance."""
+    from asyncframework_b200.data.generators import synthetic_shard
+    from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    n, b, gamma, seed, rounds = 20000, 0.2, 0.05, 5, 6
+    sh = synthetic_shard("rcv1", n, 0, 1, seed=3, device="cuda", num_features=d,
+                         labels="binary01" if loss == "logistic" else "regression")
+    ld = (d + 3) // 4 * 4
+    res = {}
+    for variant in ("simple", "persist"):
+        layout = ServerLayout(ld, 1, ring_size=64)
+        blk = ServerBlock.allocate(layout, "cuda")
+        blk.reset()
+        rk = RoundKernel(sh, ServerPointers(blk.buf.data_ptr(), layout), algo=algo, loss_id=LOSS_IDS[loss], num_workers=1,
+                         worker_id=0, total_rows=n, batch_rate=b, gamma=gamma, seed=seed, variant=variant, max_iters=rounds - 1)
+        assert rk.persist_csr == (variant == "persist")
+        rk.launch_rounds(rounds)
+        torch.cuda.synchronize()
+        st = blk.read_sctl()
+        res[variant] = (blk.w.clone(), blk.abar.clone(), st["k"], st["clock"], st["avail_count"], rk.launches,
+                        None if rk.hist is None else rk.hist.clone())
+    a, c = res["simple"], res["persist"]
+    assert a[2] == c[2] == rounds - 1 and a[3] == c[3] and c[4] == 1 and c[5] == 1
+    assert torch.allclose(a[0], c[0], rtol=1e-3, atol=1e-5) and torch.allclose(a[1], c[1], rtol=1e-3, atol=1e-6)
+    if a[6] is not None:
+        assert torch.allclose(a[6], c[6], rtol=1e-3, atol=1e-5)
