@@ -141,6 +141,9 @@ def experimental() -> C.CDLL:
         _sig(lib, "afb_dense_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p])
         _sig(lib, "afb_pipe_state_bytes", C.c_int, [])
         _sig(lib, "afb_dense_round_pipelined_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+        _sig(lib, "afb_dense_round_bf16_max_ld", C.c_int, [])
+        _sig(lib, "afb_dense_round_bf16_ctas_per_sm", C.c_int, [C.c_longlong])
+        _sig(lib, "afb_dense_round_bf16_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_void_p])
         _sig(lib, "afb_grid_bar_bytes", C.c_int, [])
         _sig(lib, "afb_csr_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
         _experimental = lib

@@ -99,11 +99,14 @@ def _true_weights(d: int, seed: int, device, dtype) -> torch.Tensor:
 
 def synthetic_shard(shape: str, rows: int, partition: int, num_partitions: int, seed: int = 42,
                     device=None, dtype: torch.dtype = torch.float32, num_features: Optional[int] = None,
-                    labels: str = "binary01", row_offset: int = 0, chunk_rows: int = 262_144) -> Shard:
+                    labels: str = "binary01", row_offset: int = 0, chunk_rows: int = 262_144,
+                    row_dtype: Optional[torch.dtype] = None) -> Shard:
     """One shard of a synthetic dataset of the named shape.
 
     labels: ``binary01`` (logistic, {0,1}), ``pm1`` (±1), ``regression`` (x·w* + noise).
     Generated in chunks so peak temporary memory stays small next to a multi-GB shard.
+    ``row_dtype=torch.bfloat16`` (dense shapes) stores the feature rows in bf16 (labels stay ``dtype``); the mnist shapes hold
+    integer pixel values 0..255, which bf16 represents exactly.
     """
     if shape not in SHAPES:
         raise KeyError(f"unknown shape {shape!r}; known: {sorted(SHAPES)}")
@@ -122,8 +125,9 @@ def synthetic_shard(shape: str, rows: int, partition: int, num_partitions: int, 
         return b if labels == "binary01" else 2.0 * b - 1.0
 
     if layout == "dense":
-        ld = padded_ld(d)
-        X = torch.zeros(rows, ld, dtype=dtype, device=dev)
+        xdt = row_dtype or dtype
+        ld = padded_ld(d) if xdt != torch.bfloat16 else (d + 7) // 8 * 8      # rows are whole 16-byte chunks
+        X = torch.zeros(rows, ld, dtype=xdt, device=dev)
         for a in range(0, rows, chunk_rows):
             b = min(rows, a + chunk_rows)
             n = b - a
@@ -137,7 +141,7 @@ def synthetic_shard(shape: str, rows: int, partition: int, num_partitions: int, 
                 blk = torch.randn(n, d, generator=g, device=dev)
                 blk = blk / blk.norm(dim=1, keepdim=True).clamp_min(1e-12)
                 scale = 4.0
-            X[a:b, :d] = blk.to(dtype)
+            X[a:b, :d] = blk.to(xdt)
             y[a:b] = make_labels((blk @ wstar) * scale).to(dtype)
             del blk
         sh = Shard(d, y, X, partition=partition)

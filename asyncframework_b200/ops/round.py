@@ -159,8 +159,16 @@ class RoundKernel:
         self.sim = shard.device.type != "cuda"
         if self.sim and os.environ.get("AFB_ALLOW_SIM", "1") != "1":
             raise ValueError("RoundKernel needs an HBM-resident shard")
-        if shard.dtype != torch.float32:
-            raise TypeError("fused kernels are fp32 (storage and accumulate)")
+        # bf16 ROW STORAGE (dense shards only; EXPERIMENTAL, csrc/experimental/dense_round_bf16.cu): X is bf16, everything else
+        # (labels, parameters, gradient, accumulation) stays fp32.  Half the HBM bytes per round.
+        self.bf16_rows = shard.is_dense and shard.X.dtype == torch.bfloat16
+        if self.bf16_rows:
+            if shard.y.dtype != torch.float32:
+                raise TypeError("bf16 row storage keeps the labels in fp32")
+            if shard.X.shape[1] % 8 != 0:
+                raise ValueError("bf16 rows need ld % 8 == 0 (16-byte chunks)")
+        elif shard.dtype != torch.float32:
+            raise TypeError("fused kernels are fp32 (storage and accumulate), or bf16 row storage with fp32 math")
         self.lib = kernels() if not self.sim else _SimLib()
         self.shard = shard
         self.device = shard.device
@@ -272,6 +280,18 @@ class RoundKernel:
         else:
             self.variant = "simple" if self.is_dense else "csr"
             self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
+        if self.bf16_rows:
+            self.variant = "bf16"
+            if not self.sim:
+                from .._native import experimental
+                exp = experimental()
+                if ld > exp.afb_dense_round_bf16_max_ld():
+                    raise ValueError(f"bf16 dense kernel supports ld <= {exp.afb_dense_round_bf16_max_ld()}")
+                self._launch = exp.afb_dense_round_bf16_launch
+                self.ctas_per_sm = exp.afb_dense_round_bf16_ctas_per_sm(ld)
+                if not grid:
+                    self.grid = self.ctas_per_sm * self.num_sms
+            variant = "bf16"                       # the persistent / pipelined experimental kernels are fp32-row only
         # "persist" (EXPERIMENTAL, csrc/experimental/dense_round_persist.cu): launch_rounds(n) is ONE resident kernel that
         # loops over n rounds; single rounds (launch()) still use the simple kernel.  Never selected implicitly.
         # "pipelined" (EXPERIMENTAL, csrc/experimental/dense_round_pipelined.cu): ASGD only; launch_rounds(n) is one resident
@@ -306,7 +326,7 @@ class RoundKernel:
         # programmatic dependent launch (simple dense variant, non-split, no rollback kernel in between):
         # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail.
         # Opt-in (AFB_PDL=1): measured +0.5 % at N=2 but -3 % at N=8 (profiles/README.md, run11), so off by default.
-        self.use_pdl = (not self.sim and self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
+        self.use_pdl = (not self.sim and self.variant == "simple" and not self.bf16_rows and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
                         and os.environ.get("AFB_PDL", "0") == "1")
         # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
         self.split = (not self.sim) and (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))

@@ -120,6 +120,11 @@ class RoundSim:
             seed_eff += rnd + 1
         # ---------------------------------------------------------------- phase 1: fused gradient
         sh = rk.shard
+        if sh.is_dense and sh.X.dtype == torch.bfloat16:       # bf16 row storage: widened exactly, math in fp32 like the kernel
+            if getattr(self, "_f32_shard", None) is None:
+                from ..data.batch import Shard
+                self._f32_shard = Shard(sh.num_features, sh.y, sh.X.to(torch.float32), gidx=sh.gidx, partition=sh.partition)
+            sh = self._f32_shard
         gidx = sh.gidx.numpy() if (sh.gidx is not None and int(p.gidx or 0)) else (np.arange(sh.num_rows, dtype=np.int64) + int(p.row_base))
         rows = torch.from_numpy(np.nonzero(hash_u24(seed_eff, gidx) < int(p.thr24))[0])
         w = (rk.w_view if algo in (ALGO_SYNC_SGD, ALGO_SYNC_SAGA) else rk.w_local)[:d].to(torch.float32)

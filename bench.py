@@ -43,6 +43,8 @@ def parse():
                     help="cpu = contract smoke-test against the pure-Python round simulator (NOT a benchmark)")
     ap.add_argument("--variant", default=None, choices=[None, "simple", "pipe", "ring", "persist", "pipelined"],
                     help="dense kernel variant (default: env/auto; persist = experimental one-launch-per-K-rounds kernel)")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="row storage of the dense shards (math is fp32 either way); bf16 = experimental kernel, exact for integer pixels")
     ap.add_argument("--graph", type=int, default=0, help="replay a CUDA graph of this many rounds (0 = plain launches)")
     ap.add_argument("--stagger-us", type=float, default=0.0, help="one-time phase offset between co-located workers")
     ap.add_argument("--workers-per-gpu", type=int, default=0, help="logical workers (partitions) per GPU; 0 = auto")
@@ -94,7 +96,8 @@ def main() -> int:
     ids = [p for p in range(P) if p % world == rank]
     t0 = time.time()
     shards = [synthetic_shard(args.shape, sizes[p], p, P, seed=42, device=dev, num_features=args.features,
-                              labels="binary01" if args.loss != "least_squares" else "regression", row_offset=sum(sizes[:p]))
+                              labels="binary01" if args.loss != "least_squares" else "regression", row_offset=sum(sizes[:p]),
+                              row_dtype=(torch.bfloat16 if (args.dtype == "bf16" and args.impl == "ours") else None))
               for p in ids]
     shard = shards[0]
     _dev.synchronize(dev)
@@ -194,11 +197,12 @@ def main() -> int:
     else:
         k_total = eng.k
     if rank == 0:
-        bytes_per_gpu_step = sum(sizes[p] for p in ids) * args.batch_rate * (shard.ld if shard.is_dense else 0) * 4
+        bytes_per_gpu_step = sum(sizes[p] for p in ids) * args.batch_rate * (shard.ld if shard.is_dense else 0) * (shard.X.element_size() if shard.is_dense else 4)
         out = {
             "metric": "sgd_iterations_per_sec", "value": args.steps / (ms_max * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": ("bf16 rows, fp32 accumulate" if (args.dtype == "bf16" and args.impl == "ours") else "fp32"),
             "device": args.device,
             "data": "synthetic (mnist8m shape: integer pixels 0..255, ~19% non-zero, random-init true weights; no network for the real dataset)",
             "impl": args.impl,

@@ -261,3 +261,20 @@ def test_persistent_csr_variant_on_the_simulator():
     eng.run_rounds(4)
     st = eng.server_state()
     assert st["k"] == 8 and eng.launches == 2 and torch.isfinite(eng.weights()).all()
+
+
+def test_bf16_row_storage_on_the_simulator_is_exact_for_integer_pixels():
+    """bf16 ROW STORAGE, fp32 math: for the mnist shapes (integer pixels) the rounds are bit-identical to fp32 storage."""
+    from asyncframework_b200.data.generators import synthetic_shard
+    outs = []
+    for row_dtype in (None, torch.bfloat16):
+        sh = synthetic_shard("mnist", 500, 0, 1, seed=3, device="cpu", num_features=784, row_dtype=row_dtype)
+        assert sh.y.dtype == torch.float32 and sh.X.dtype == (row_dtype or torch.float32) and sh.X.shape[1] == 784
+        cfg = AsyncConfig(algorithm="asgd", num_features=784, num_rows=500, num_partitions=1, num_iterations=1 << 30, step_size=1e-4,
+                          batch_rate=0.3, loss="logistic", backend="fused", barrier="asp")
+        eng = FusedEngine(cfg, [sh], 500, [0], device="cpu")
+        assert eng.kernels[0].bf16_rows == (row_dtype is not None)
+        assert eng.kernels[0].variant_effective == ("bf16" if row_dtype is not None else "simple")
+        eng.run_rounds(4)
+        outs.append(eng.weights().clone())
+    assert torch.equal(outs[0], outs[1]) and outs[0].abs().sum() > 0

@@ -112,3 +112,36 @@ def test_persistent_csr_round_matches_the_split_round(algo, loss, d):
     assert torch.allclose(a[0], c[0], rtol=1e-3, atol=1e-5) and torch.allclose(a[1], c[1], rtol=1e-3, atol=1e-6)
     if a[6] is not None:
         assert torch.allclose(a[6], c[6], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("algo,loss,d", [("asgd", "logistic", 784), ("asaga", "least_squares", 200), ("asgd", "logistic", 2000)])
+def test_bf16_row_storage_kernel_matches_fp32_kernel_on_bf16_exact_data(algo, loss, d):
+    """Rows that are exactly representable in bf16 (integer pixels) must give the same rounds from the bf16-storage kernel
+    as from the fp32 kernel (both accumulate in fp32; only the summation order inside a row differs)."""
+    from asyncframework_b200.data.batch import Shard
+    from asyncframework_b200.ops.round import RoundKernel, ServerBlock, ServerLayout, ServerPointers
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    n, b, gamma, seed, rounds = 6000, 0.25, 1e-6, 5, 5
+    g = torch.Generator().manual_seed(1)
+    ld = (d + 7) // 8 * 8
+    X = torch.zeros(n, ld)
+    X[:, :d] = (torch.randint(0, 256, (n, d), generator=g) * (torch.rand(n, d, generator=g) < 0.2)).float()
+    y = (torch.rand(n, generator=g) < 0.5).float() if loss == "logistic" else torch.randn(n, generator=g)
+    gidx = torch.arange(n, dtype=torch.int64)
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        sh = Shard(d, y.cuda(), X.to(dt).cuda(), gidx=gidx.cuda())
+        layout = ServerLayout(ld, 1, ring_size=64)
+        blk = ServerBlock.allocate(layout, "cuda")
+        blk.reset()
+        rk = RoundKernel(sh, ServerPointers(blk.buf.data_ptr(), layout), algo=algo, loss_id=LOSS_IDS[loss], num_workers=1,
+                         worker_id=0, total_rows=n, batch_rate=b, gamma=gamma, seed=seed)
+        assert rk.bf16_rows == (dt == torch.bfloat16)
+        for _ in range(rounds):
+            rk.launch()
+        torch.cuda.synchronize()
+        st = blk.read_sctl()
+        res[dt] = (blk.w.clone(), st["k"], rk.read_ctl()["last_batch"])
+    a, c = res[torch.float32], res[torch.bfloat16]
+    assert a[1] == c[1] == rounds and a[2] == c[2]
+    assert torch.allclose(a[0], c[0], rtol=1e-4, atol=1e-7)
