@@ -38,6 +38,8 @@ class NcclSyncSGD:
         mask = torch.rand(self.X.shape[0], generator=self.gen, device=self.X.device) < self.b
         idx = mask.nonzero(as_tuple=True)[0]
         Xb = self.X[idx]
+        if Xb.dtype != self.w.dtype:             # bf16 row storage: gather in bf16, widen for the fp32 GEMVs (what stock PyTorch offers)
+            Xb = Xb.to(self.w.dtype)
         yb = self.y[idx]
         margin = Xb @ self.w
         if self.loss == "logistic":

@@ -97,7 +97,7 @@ def main() -> int:
     t0 = time.time()
     shards = [synthetic_shard(args.shape, sizes[p], p, P, seed=42, device=dev, num_features=args.features,
                               labels="binary01" if args.loss != "least_squares" else "regression", row_offset=sum(sizes[:p]),
-                              row_dtype=(torch.bfloat16 if (args.dtype == "bf16" and args.impl == "ours") else None))
+                              row_dtype=(torch.bfloat16 if args.dtype == "bf16" else None))
               for p in ids]
     shard = shards[0]
     _dev.synchronize(dev)
@@ -202,7 +202,7 @@ def main() -> int:
             "metric": "sgd_iterations_per_sec", "value": args.steps / (ms_max * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": ("bf16 rows, fp32 accumulate" if (args.dtype == "bf16" and args.impl == "ours") else "fp32"),
+            "dtype": ("bf16 rows, fp32 accumulate" if args.dtype == "bf16" else "fp32"),
             "device": args.device,
             "data": "synthetic (mnist8m shape: integer pixels 0..255, ~19% non-zero, random-init true weights; no network for the real dataset)",
             "impl": args.impl,
