@@ -155,3 +155,31 @@ def test_cancel_job_over_executor_processes(cluster):
         w.wait(5)
     assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 136      # queued tasks of the dropped job returned at once
     assert time.perf_counter() - t0 < 1.4
+
+
+def test_concurrent_job_submission_from_many_threads(cluster):
+    """ThreadingSuite analogue: several driver threads submit jobs over shared and private datasets at once; every job gets its
+    own results, source blocks are shipped exactly once per executor even when first uses race."""
+    import threading
+    shared = ShardedDataset.from_records(cluster, list(range(2000)), 4)
+    errors, sums = [], {}
+
+    def driver(i):
+        try:
+            mine = ShardedDataset.from_records(cluster, list(range(i, i + 500)), 3)
+            for r in range(4):
+                a = shared.map(lambda x, i=i, r=r: x * (i + 1) + r).reduce(lambda p, q: p + q)
+                b = mine.map(lambda x: x * x).reduce(lambda p, q: p + q)
+                assert a == (i + 1) * sum(range(2000)) + r * 2000, (i, r, a)
+                assert b == sum(x * x for x in range(i, i + 500)), (i, r, b)
+            sums[i] = True
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=driver, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors, errors[:3]
+    assert len(sums) == 6 and not any(t.is_alive() for t in threads)
