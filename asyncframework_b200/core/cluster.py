@@ -272,20 +272,22 @@ class ClusterScheduler:
             self._finish_job(job_id)
         return waiter
 
-    def run_job(self, dataset, func, partitions=None, result_handler=None, on_task_lost=None):
+    def run_job(self, dataset, func, partitions=None, result_handler=None, on_task_lost=None, blocking: Optional[bool] = None):
         results: Dict[int, Any] = {}
         if result_handler is None:
             def result_handler(i, r):  # noqa: E306
                 results[i] = r
         waiter = self.submit_job(dataset, func, partitions, result_handler, on_task_lost)
-        if self.mode == 0 or (self.first_iter == 1 and self.block_first_async_job):
+        # `blocking` overrides the scheduler-wide mode for THIS job: blocking actions (collect/reduce/...) pass True and
+        # async actions pass False, so concurrent driver threads never observe each other's temporary mode flips
+        nonblocking = (self.mode == 1) if blocking is None else (not blocking)
+        if not nonblocking or (self.first_iter == 1 and self.block_first_async_job):
             waiter.wait()
-            if self.mode == 1:
+            if nonblocking:
                 self.first_iter = 0
             parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
             return [results.get(p) for p in parts]
-        if self.mode == 1:
-            self.first_iter = 0
+        self.first_iter = 0
         return waiter
 
     def kill_executor(self, eid: int) -> None:

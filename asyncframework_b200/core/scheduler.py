@@ -249,7 +249,7 @@ class Scheduler:
             self._queues[p % self.num_executors].put(_Task(job, p, func, dataset, now))
         return job
 
-    def run_job(self, dataset, func, partitions=None, result_handler=None, on_task_lost=None):
+    def run_job(self, dataset, func, partitions=None, result_handler=None, on_task_lost=None, blocking: Optional[bool] = None):
         """Blocking in mode 0 (returns the per-partition results in order); in mode 1 returns
         immediately after submission (except, optionally, for the very first async job)."""
         results: Dict[int, Any] = {}
@@ -257,14 +257,16 @@ class Scheduler:
             def result_handler(i, r):  # noqa: E306
                 results[i] = r
         waiter = self.submit_job(dataset, func, partitions, result_handler, on_task_lost)
-        if self.mode == 0 or (self.first_iter == 1 and self.block_first_async_job):
+        # `blocking` overrides the scheduler-wide mode for THIS job: blocking actions (collect/reduce/...) pass True and
+        # async actions pass False, so concurrent driver threads never observe each other's temporary mode flips
+        nonblocking = (self.mode == 1) if blocking is None else (not blocking)
+        if not nonblocking or (self.first_iter == 1 and self.block_first_async_job):
             waiter.wait()
-            if self.mode == 1:
+            if nonblocking:
                 self.first_iter = 0
             parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
             return [results.get(p) for p in parts]
-        if self.mode == 1:
-            self.first_iter = 0
+        self.first_iter = 0
         return waiter
 
     def cancel_job(self, job_id: int, reason: str = "cancelled by user") -> bool:

@@ -401,12 +401,9 @@ class ShardedDataset:
 
     # ------------------------------------------------------------------ blocking actions
     def _run(self, func, partitions=None):
-        prev = self.scheduler.mode
-        self.scheduler.set_mode(0)
-        try:
-            return self.scheduler.run_job(self, func, partitions)
-        finally:
-            self.scheduler.set_mode(prev)
+        # blocking for THIS job only; the scheduler-wide mode (sc.set_mode) is left alone, so actions issued from several
+        # driver threads cannot see each other's temporary state
+        return self.scheduler.run_job(self, func, partitions, blocking=True)
 
     def collect(self) -> list:
         out = self._run(lambda t, it: list(it))
@@ -551,7 +548,7 @@ class ShardedDataset:
         sched.set_mode(1)   # ASYNCreduce always switches the scheduler to non-blocking (RDD.scala:1167)
         # only the selected partitions do work; running the no-op tasks of the others is pure
         # overhead (the reference runs them and they just flip availability) — skip them.
-        return sched.run_job(self, part_fn, selected, merge, lost)
+        return sched.run_job(self, part_fn, selected, merge, lost, blocking=False)
 
     def async_reduce(self, f: Callable[[Any, Any], Any], ctx):
         """Non-blocking reduce: each selected partition's ``reduceLeft(f)`` lands in ``ctx`` as it
