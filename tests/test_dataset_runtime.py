@@ -274,3 +274,47 @@ def test_job_cancellation_skips_pending_tasks_and_frees_async_workers():
     finally:
         release.set()
         sched.stop()
+
+
+def test_blocking_and_async_actions_from_concurrent_driver_threads():
+    """ThreadingSuite analogue for the in-process scheduler: blocking actions keep returning results (never a JobWaiter) while
+    other driver threads issue ASYNC actions that leave the scheduler in non-blocking mode."""
+    import threading
+    from asyncframework_b200.core import AsyncContext, Scheduler
+    from asyncframework_b200.data import ShardedDataset
+    sched = Scheduler(4, block_first_async_job=False)
+    try:
+        ds = ShardedDataset.from_records(sched, list(range(400)), 4).cache()
+        errors = []
+
+        def blocking_driver(i):
+            try:
+                for r in range(40):
+                    assert ds.map(lambda x, i=i: x + i).reduce(lambda a, b: a + b) == sum(range(400)) + 400 * i
+                    assert ds.count() == 400
+            except BaseException as exc:  # noqa: BLE001
+                errors.append(repr(exc))
+
+        def async_driver():
+            try:
+                AC = AsyncContext(4, sched)
+                got = 0
+                for r in range(25):
+                    ds.map(lambda x: 1).async_reduce(lambda a, b: a + b, AC)
+                    for _ in range(4):
+                        info = AC.collect_all(timeout=10)
+                        assert info is not None and info.data == 100
+                        got += 1
+                assert got == 100
+            except BaseException as exc:  # noqa: BLE001
+                errors.append(repr(exc))
+
+        threads = [threading.Thread(target=blocking_driver, args=(i,)) for i in range(3)] + [threading.Thread(target=async_driver)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert not errors, errors[:3]
+        assert not any(t.is_alive() for t in threads)
+    finally:
+        sched.stop()
