@@ -212,7 +212,9 @@ def main() -> int:
                        "updates_per_iteration": P, "accepted_updates_total": int(k_total),
                        "l2_policy": "inputs larger than L2: each round streams a fresh Bernoulli sample "
                                     f"(~{bytes_per_gpu_step / 1e6:.0f} MB/GPU) out of {sum(sh.nbytes() for sh in shards) / 1e9:.2f} GB of HBM-resident shards",
-                       "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph, "dense_variant": (eng.kernels[0].variant_effective if args.impl == "ours" else None),
+                       "workers_per_gpu": wpg, "cuda_graph_rounds": args.graph,
+                       "pdl": (bool(eng.kernels[0].use_pdl) if args.impl == "ours" else None),
+                       "seed_mode": (int(eng.kernels[0].params.seed_mode) if args.impl == "ours" else None), "dense_variant": (eng.kernels[0].variant_effective if args.impl == "ours" else None),
                        "e2e_inputs": "dataset cached in HBM (as the reference's .cache()); every step: pinned H2D round descriptor -> fused round(s) -> pinned D2H result records (host reads them one step behind)",
                        "datagen_s": round(gen_s, 2)},
             "hbm_gbps_per_gpu": bytes_per_gpu_step / (ms_max / args.steps * 1e-3) / 1e9,

@@ -38,7 +38,7 @@ out = ["# Measured results (B200, this repo)", "",
        f"Roofline denominator: measured copy bandwidth `hbm_gbs` = {hbm} GB/s from `MEASURED_PEAKS.json` (\"of measured\").",
        "Headline workload (BASELINE.json config 2): ASGD logistic regression, mnist8m shape (8.1 M x 784 fp32), sampling rate 0.1;",
        "one iteration = every worker completes one round = 810 000 rows sampled, gradient computed, pushed and applied.", ""]
-for run, title in (("run11", "Final build (prologue overlap, early clock ticket, PDL, guided scheduling) — 8-GPU box"),
+for run, title in (("run11", "Final build (prologue overlap, early clock ticket, guided scheduling) — 8-GPU box.  PDL was still the default in this session: every row except `_nopdl` ran with programmatic dependent launch; the `_w1` vs `_w1_nopdl` pair (-3 %) is why the shipped default is PDL off"),
                    ("run9", "Previous build (guided scheduling + early prefetch + PDL) — 8-GPU box"),
                    ("", "First scaling pass (register double-buffered kernel, 2 workers/GPU) — 8-GPU box")):
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench", run, "*.json"))) if run else \
