@@ -34,6 +34,7 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
 
 import cloudpickle
 
+from . import accumulator as _acc
 from .scheduler import JobFailed, JobWaiter, ListenerBus, TaskContext  # noqa: F401
 
 
@@ -89,12 +90,14 @@ def _executor_main(eid: int, conn) -> None:
                 raise binary
             dataset, func, fault = binary
             tctx = TaskContext(job_id, partition, attempt, eid, None, None, submit_ms)
+            _acc.begin_task()
             if fault is not None:
                 fault(tctx)
             result = func(tctx, dataset.iterator(partition, tctx))
-            data = cloudpickle.dumps(result)
+            data = cloudpickle.dumps((result, _acc.end_task(True)))      # accumulator updates ride with the result
             send(("ok", job_id, partition, attempt, data, (time.perf_counter() - t0) * 1e3))
         except BaseException as exc:  # noqa: BLE001
+            _acc.end_task(False)
             send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
 
 
@@ -166,7 +169,10 @@ class ClusterScheduler:
                 self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
                                      "run_ms": run_ms, "metrics": {"result_bytes": len(data)}})
                 try:
-                    waiter.task_succeeded(partition, pickle.loads(data))
+                    result, acc_updates = pickle.loads(data)
+                    if not waiter.cancelled:
+                        _acc.merge_updates(acc_updates)
+                    waiter.task_succeeded(partition, result)
                 except Exception as exc:  # a raising result handler fails the job, not the receiver thread
                     waiter.job_failed(exc)
                 job["pending"].discard(partition)

@@ -26,6 +26,8 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
 
+from . import accumulator as _acc
+
 
 @dataclass
 class TaskContext:
@@ -188,6 +190,7 @@ class Scheduler:
         self.listeners.post({"event": "task_start", "job": job.job_id, "partition": task.partition,
                              "attempt": task.attempt, "executor": eid, "t_ms": time.perf_counter() * 1e3})
         t0 = time.perf_counter()
+        _acc.begin_task()
         try:
             if self.fault_injector is not None:
                 self.fault_injector(tctx)
@@ -198,6 +201,7 @@ class Scheduler:
             else:
                 result = task.func(tctx, task.dataset.iterator(task.partition, tctx))
         except Exception as exc:  # noqa: BLE001
+            _acc.end_task(False)                # a failed attempt's accumulator updates are dropped
             if job.cancelled:                   # an interrupted task of a cancelled job is not a failure to retry
                 self._task_lost(job, task.partition)
                 return
@@ -214,8 +218,10 @@ class Scheduler:
                 self._queues[eid].put(task)   # retry on the same executor (hard affinity)
             return
         if job.cancelled:                       # finished after the cancellation: the result is discarded
+            _acc.end_task(False)
             self._task_lost(job, task.partition)
             return
+        _acc.merge_updates(_acc.end_task(True))   # exactly once, for the successful attempt
         dt = (time.perf_counter() - t0) * 1e3
         self.listeners.post({"event": "task_end", "job": job.job_id, "partition": task.partition,
                              "executor": eid, "run_ms": dt, "metrics": tctx.metrics})

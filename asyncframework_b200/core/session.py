@@ -80,6 +80,20 @@ class AsyncSession:
     def broadcast(self, value: Any) -> Broadcast:
         return Broadcast(value)
 
+    def long_accumulator(self, name: Optional[str] = None):
+        """``sc.longAccumulator``: tasks ``add``, the driver reads ``.value`` (updates of successful tasks only, exactly once)."""
+        from .accumulator import Accumulator
+        return Accumulator(0, name)
+
+    def double_accumulator(self, name: Optional[str] = None):
+        from .accumulator import Accumulator
+        return Accumulator(0.0, name)
+
+    def accumulator(self, zero, name: Optional[str] = None, op=None):
+        """General accumulator: ``op`` must be associative and commutative (default ``+``)."""
+        from .accumulator import Accumulator
+        return Accumulator(zero, name, op)
+
     def async_context(self, num_workers: Optional[int] = None) -> AsyncContext:
         return AsyncContext(num_workers or self.default_parallelism, self.scheduler)
 

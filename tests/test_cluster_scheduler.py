@@ -183,3 +183,19 @@ def test_concurrent_job_submission_from_many_threads(cluster):
         t.join(60)
     assert not errors, errors[:3]
     assert len(sums) == 6 and not any(t.is_alive() for t in threads)
+
+
+def test_accumulators_over_executor_processes(cluster):
+    from asyncframework_b200.core import Accumulator
+    seen, total = Accumulator(0, "seen"), Accumulator(0.0, "total")
+    ds = ShardedDataset.from_records(cluster, list(range(60)), 4)
+
+    def f(x):
+        seen.add(1)
+        total.add(x * 0.5)
+        return x
+    assert sorted(ds.map(f).collect()) == list(range(60))
+    assert seen.value == 60 and total.value == 0.5 * sum(range(60))
+    assert ds.map(f).count() == 60 and seen.value == 120          # a second job keeps accumulating
+    with pytest.raises(Exception):
+        ds.map(lambda x: seen.value).collect()                     # tasks may only add: reading on an executor is an error

@@ -318,3 +318,40 @@ def test_blocking_and_async_actions_from_concurrent_driver_threads():
         assert not any(t.is_alive() for t in threads)
     finally:
         sched.stop()
+
+
+def test_accumulators_count_successful_attempts_exactly_once():
+    """sc.longAccumulator semantics (AccumulatorSuite): tasks add, driver reads; a failed attempt's updates are dropped, the
+    retried attempt counts once."""
+    from asyncframework_b200 import AsyncSession
+    sc = AsyncSession("local[3]")
+    try:
+        rows, big = sc.long_accumulator("rows"), sc.double_accumulator("sum")
+        ds = sc.parallelize(list(range(100)), 4)
+
+        def f(x):
+            rows.add(1)
+            big.add(float(x))
+            return x
+        assert ds.map(f).count() == 100
+        assert rows.value == 100 and big.value == float(sum(range(100)))
+        # a task that fails on its first attempt after adding: only the successful retry is counted
+        attempts = {}
+
+        def flaky(tctx):
+            n = attempts.get(tctx.partition_id, 0)
+            attempts[tctx.partition_id] = n + 1
+            if tctx.partition_id == 1 and n == 0:
+                rows.add(1000)                           # belongs to the attempt that is about to fail
+                raise RuntimeError("injected")
+        sc.scheduler.fault_injector = flaky
+        rows.reset()
+        assert ds.map(f).count() == 100 and rows.value == 100 and attempts[1] == 2
+        sc.scheduler.fault_injector = None
+        rows.add(5)                                      # driver-side add applies directly
+        assert rows.value == 105
+        mx = sc.accumulator(float("-inf"), "max", op=max)
+        ds.map(lambda x: mx.add(float(x))).count()
+        assert mx.value == 99.0
+    finally:
+        sc.stop()
