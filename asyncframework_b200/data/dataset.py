@@ -237,6 +237,51 @@ class ShardedDataset:
 
     persist = cache
 
+    def checkpoint(self, directory: str) -> "ShardedDataset":
+        """``rdd.checkpoint()`` (RDD.scala:1773, ReliableCheckpointRDD.scala:121-210): every partition is materialised by a job
+        and written to ``directory/part-<p>.pt`` (columnar shard when the dataset is batch-capable, records otherwise); the
+        returned dataset reads those files and has NO parent — the lineage is truncated, so later jobs (and task binaries in
+        cluster mode) no longer carry or recompute it.  Eager, unlike Spark's mark-then-write-after-the-next-job."""
+        os.makedirs(directory, exist_ok=True)
+        batchy = self.batch_capable
+
+        def write(tctx, it):
+            p = tctx.partition_id
+            payload = {"batch": self.batch(p, tctx)} if batchy else {"records": list(it)}
+            if batchy and payload["batch"] is not None:
+                payload["batch"] = payload["batch"].to("cpu")
+            tmp = os.path.join(directory, f"part-{p:05d}.pt.tmp")
+            torch.save(payload, tmp)
+            os.replace(tmp, os.path.join(directory, f"part-{p:05d}.pt"))
+            return p
+        self._run(write)
+        with open(os.path.join(directory, "_SUCCESS"), "w") as f:
+            f.write(f"{self.num_partitions} {int(batchy)}\n")
+        return ShardedDataset.from_checkpoint(self.scheduler, directory)
+
+    @classmethod
+    def from_checkpoint(cls, scheduler, directory: str) -> "ShardedDataset":
+        """Re-open a dataset written by :meth:`checkpoint` (``sc.checkpointFile``)."""
+        with open(os.path.join(directory, "_SUCCESS")) as f:
+            n, batchy = (int(t) for t in f.read().split())
+
+        def load(p):
+            return torch.load(os.path.join(directory, f"part-{p:05d}.pt"), weights_only=False)
+
+        def compute(p, tctx):
+            d = load(p)
+            if "records" in d:
+                return iter(d["records"])
+            s = d["batch"]
+            return iter(()) if s is None else (s.indexed_records() if s.gidx is not None else s.records())
+
+        def batch(p, tctx):
+            s = load(p)["batch"]
+            if s is not None:
+                s.partition = p
+            return s
+        return cls(scheduler, n, compute, batch if batchy else None, None, f"checkpoint:{os.path.basename(directory)}")
+
     def _derive(self, compute=None, batch=None, name="") -> "ShardedDataset":
         ds = ShardedDataset(self.scheduler, self.num_partitions, compute, batch, self, name or self.name)
         ds.selected_workers = self.selected_workers

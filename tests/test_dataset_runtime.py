@@ -355,3 +355,25 @@ def test_accumulators_count_successful_attempts_exactly_once():
         assert mx.value == 99.0
     finally:
         sc.stop()
+
+
+def test_dataset_checkpoint_truncates_lineage(tmp_path, scheduler):
+    """rdd.checkpoint(): partitions are written once, the re-opened dataset has no parent and gives the same answers."""
+    from asyncframework_b200.data import LinearDataGenerator, ShardedDataset
+    calls = {"n": 0}
+
+    def expensive(x):
+        calls["n"] += 1
+        return x * 3
+    ds = ShardedDataset.from_records(scheduler, list(range(50)), 4).map(expensive)
+    ck = ds.checkpoint(str(tmp_path / "rec"))
+    n_after_write = calls["n"]
+    assert ck.parent is None and sorted(ck.collect()) == [3 * i for i in range(50)] and ck.count() == 50
+    assert calls["n"] == n_after_write == 50                      # the lineage was not recomputed by the later jobs
+    pts = LinearDataGenerator.generate_linear_dataset(scheduler, 200, 6, 0.1, 3, seed=2).zip_with_index()
+    ckb = pts.checkpoint(str(tmp_path / "batch"))
+    assert ckb.batch_capable and ckb.parent is None and ckb.partition_sizes() == pts.partition_sizes()
+    a = torch.cat([s.X for s in pts.shards()])
+    b = torch.cat([s.X for s in ShardedDataset.from_checkpoint(scheduler, str(tmp_path / "batch")).shards()])
+    assert torch.equal(a, b)
+    assert ckb.sample(False, 0.5, 7).count() == pts.sample(False, 0.5, 7).count()      # gidx survived: same Bernoulli sample
