@@ -65,6 +65,16 @@ _block_ids = itertools.count(1)
 _pickle_ctx = threading.local()
 
 
+def _stable_hash(key) -> int:
+    """Partitioner hash that is identical in every process (Python's ``hash`` of str/bytes is salted per process, so executor
+    processes would disagree on a key's partition)."""
+    if isinstance(key, int) and not isinstance(key, bool):
+        return key & 0x7FFFFFFFFFFFFFFF
+    import pickle
+    import zlib
+    return zlib.crc32(pickle.dumps(key, protocol=4))
+
+
 class BlockMissing(RuntimeError):
     """An executor was sent a block reference for data it does not hold (e.g. a replaced executor)."""
 
@@ -443,6 +453,133 @@ class ShardedDataset:
         return ds
 
     ASYNCbarrier = async_barrier
+
+    # ------------------------------------------------------------------ the wider RDD surface (record path; data-prep scale)
+    def union(self, other: "ShardedDataset") -> "ShardedDataset":
+        """``rdd.union``: partitions of ``self`` followed by the partitions of ``other`` (no shuffle)."""
+        n1 = self.num_partitions
+        a, b = self, other
+        ds = ShardedDataset(self.scheduler, n1 + other.num_partitions,
+                            lambda p, t: a.iterator(p, t) if p < n1 else b.iterator(p - n1, t), None, None, "union")
+        ds._union_parents = (a, b)  # type: ignore[attr-defined]  (keeps both lineages alive / picklable)
+        return ds
+
+    def zip(self, other: "ShardedDataset") -> "ShardedDataset":
+        """``rdd.zip``: pairs records position by position; both sides need the same partitioning."""
+        if other.num_partitions != self.num_partitions:
+            raise ValueError("zip: both datasets must have the same number of partitions")
+
+        def compute(p, t):
+            xs, ys = list(self.iterator(p, t)), list(other.iterator(p, t))
+            if len(xs) != len(ys):
+                raise ValueError(f"zip: partition {p} has {len(xs)} vs {len(ys)} records")
+            return iter(list(zip(xs, ys)))
+        ds = self._derive(compute, None, "zip")
+        ds._zip_other = other  # type: ignore[attr-defined]
+        return ds
+
+    def key_by(self, f) -> "ShardedDataset":
+        return self.map(lambda r: (f(r), r))
+
+    def keys(self) -> "ShardedDataset":
+        return self.map(lambda kv: kv[0])
+
+    def values(self) -> "ShardedDataset":
+        return self.map(lambda kv: kv[1])
+
+    def map_values(self, f) -> "ShardedDataset":
+        return self.map(lambda kv: (kv[0], f(kv[1])))
+
+    def foreach(self, f) -> None:
+        self._run(lambda t, it: [f(r) for r in it] and None)
+
+    def _shuffle(self, num_partitions: Optional[int], map_side) -> "ShardedDataset":
+        """Hash shuffle at data-prep scale: each map task returns its output bucketed by target partition, the driver regroups
+        (the reference only shuffles while preparing data: repartition / reduceByKey, SparkASGDThread.scala:73,77)."""
+        P = int(num_partitions or self.num_partitions)
+
+        def part(t, it):
+            buckets: List[list] = [[] for _ in range(P)]
+            for k, v in map_side(it):
+                buckets[_stable_hash(k) % P].append((k, v))
+            return buckets
+        outs = self._run(part)
+        merged = [[kv for b in outs for kv in b[q]] for q in range(P)]
+        blk = SourceBlock(merged)
+        return ShardedDataset(self.scheduler, P, lambda p, t: iter(blk.data[p]), None, None, "shuffled")
+
+    def reduce_by_key(self, f, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``rdd.reduceByKey`` with map-side combining."""
+        def combine(it):
+            acc: dict = {}
+            for k, v in it:
+                acc[k] = f(acc[k], v) if k in acc else v
+            return acc.items()
+        sh = self._shuffle(num_partitions, combine)
+
+        def compute(p, t):
+            return iter(list(combine(sh.iterator(p, t))))
+        return sh._derive(compute, None, "reduce_by_key")
+
+    def group_by_key(self, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        sh = self._shuffle(num_partitions, lambda it: it)
+
+        def compute(p, t):
+            acc: dict = {}
+            for k, v in sh.iterator(p, t):
+                acc.setdefault(k, []).append(v)
+            return iter(list(acc.items()))
+        return sh._derive(compute, None, "group_by_key")
+
+    def distinct(self, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.map(lambda r: (r, None)).reduce_by_key(lambda a, b: a, num_partitions).keys()
+
+    def count_by_key(self) -> dict:
+        return dict(self.map_values(lambda v: 1).reduce_by_key(lambda a, b: a + b).collect())
+
+    def count_by_value(self) -> dict:
+        return dict(self.map(lambda r: (r, 1)).reduce_by_key(lambda a, b: a + b).collect())
+
+    def sort_by(self, key=lambda r: r, ascending: bool = True, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``rdd.sortBy``: total order across partitions (range partitioning on the driver; data-prep scale)."""
+        P = int(num_partitions or self.num_partitions)
+        recs = sorted(self.collect(), key=key, reverse=not ascending)
+        return ShardedDataset.from_records(self.scheduler, recs, max(1, P), "sorted")
+
+    def top(self, n: int, key=lambda r: r) -> list:
+        import heapq
+        parts = self._run(lambda t, it: heapq.nlargest(n, it, key=key))
+        return heapq.nlargest(n, [r for part in parts for r in part], key=key)
+
+    def take_sample(self, with_replacement: bool, num: int, seed: int = 42) -> list:
+        import random
+        recs = self.collect()
+        rng = random.Random(seed)
+        return [rng.choice(recs) for _ in range(num)] if with_replacement else rng.sample(recs, min(num, len(recs)))
+
+    def sum(self):
+        return self.aggregate(lambda: 0, lambda a, x: a + x, lambda a, b: a + b)
+
+    def max(self, key=lambda r: r):
+        return self.reduce(lambda a, b: a if key(a) >= key(b) else b)
+
+    def min(self, key=lambda r: r):
+        return self.reduce(lambda a, b: a if key(a) <= key(b) else b)
+
+    def mean(self) -> float:
+        s, n = self.aggregate(lambda: (0.0, 0), lambda a, x: (a[0] + x, a[1] + 1), lambda a, b: (a[0] + b[0], a[1] + b[1]))
+        if n == 0:
+            raise ValueError("empty collection")
+        return s / n
+
+    def coalesce(self, num_partitions: int) -> "ShardedDataset":
+        """``rdd.coalesce(n, shuffle = true)`` == repartition (the form the reference uses, RDD.scala:420-475)."""
+        return self.repartition(num_partitions)
+
+    def zip_with_unique_id(self) -> "ShardedDataset":
+        """``rdd.zipWithUniqueId``: ids k, k+P, k+2P, ... in partition k — unique without the counting job zip_with_index needs."""
+        P = self.num_partitions
+        return self._derive(lambda p, t: ((r, p + i * P) for i, r in enumerate(self.iterator(p, t))), None, "zip_with_unique_id")
 
     # ------------------------------------------------------------------ blocking actions
     def _run(self, func, partitions=None):

@@ -199,3 +199,14 @@ def test_accumulators_over_executor_processes(cluster):
     assert ds.map(f).count() == 60 and seen.value == 120          # a second job keeps accumulating
     with pytest.raises(Exception):
         ds.map(lambda x: seen.value).collect()                     # tasks may only add: reading on an executor is an error
+
+
+def test_key_value_shuffles_agree_across_executor_processes(cluster):
+    """Each executor process salts hash() differently; the shuffle partitioner must not depend on it."""
+    words = ShardedDataset.from_records(cluster, ("a b a c b a d e f a " * 20).split(), 4)
+    counts = dict(words.map(lambda w: (w, 1)).reduce_by_key(lambda x, y: x + y, 3).collect())
+    assert counts == {"a": 80, "b": 40, "c": 20, "d": 20, "e": 20, "f": 20}
+    assert sorted(words.distinct().collect()) == list("abcdef")
+    a = ShardedDataset.from_records(cluster, list(range(12)), 3)
+    assert sorted(a.union(a.map(lambda x: x + 100)).collect()) == list(range(12)) + list(range(100, 112))
+    assert a.zip(a.map(lambda x: -x)).collect() == [(i, -i) for i in range(12)]

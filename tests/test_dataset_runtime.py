@@ -377,3 +377,31 @@ def test_dataset_checkpoint_truncates_lineage(tmp_path, scheduler):
     b = torch.cat([s.X for s in ShardedDataset.from_checkpoint(scheduler, str(tmp_path / "batch")).shards()])
     assert torch.equal(a, b)
     assert ckb.sample(False, 0.5, 7).count() == pts.sample(False, 0.5, 7).count()      # gidx survived: same Bernoulli sample
+
+
+def test_wider_rdd_surface(scheduler):
+    """union / zip / key-value ops / shuffles / ordering / numeric actions (RDDSuite + PairRDDFunctionsSuite analogue)."""
+    from asyncframework_b200.data import ShardedDataset
+    a = ShardedDataset.from_records(scheduler, list(range(10)), 3)
+    b = ShardedDataset.from_records(scheduler, list(range(100, 105)), 2)
+    u = a.union(b)
+    assert u.num_partitions == 5 and sorted(u.collect()) == list(range(10)) + list(range(100, 105))
+    assert a.zip(a.map(lambda x: x * x)).collect() == [(i, i * i) for i in range(10)]
+    words = ShardedDataset.from_records(scheduler, "a b a c b a d".split(), 3)
+    counts = dict(words.map(lambda w: (w, 1)).reduce_by_key(lambda x, y: x + y).collect())
+    assert counts == {"a": 3, "b": 2, "c": 1, "d": 1} == words.count_by_value()
+    groups = dict(words.key_by(lambda w: w).group_by_key(2).map_values(len).collect())
+    assert groups == counts
+    assert sorted(words.distinct().collect()) == ["a", "b", "c", "d"]
+    kv = a.key_by(lambda x: x % 3)
+    assert kv.count_by_key() == {0: 4, 1: 3, 2: 3} and sorted(kv.keys().distinct().collect()) == [0, 1, 2]
+    assert sorted(kv.map_values(lambda v: -v).values().collect()) == sorted(-i for i in range(10))
+    assert a.sort_by(lambda x: -x).collect() == list(range(9, -1, -1)) and a.top(3) == [9, 8, 7]
+    assert a.sum() == 45 and a.max() == 9 and a.min() == 0 and a.mean() == 4.5
+    assert len(a.take_sample(False, 4, seed=1)) == 4 and len(a.take_sample(True, 20, seed=1)) == 20
+    ids = a.zip_with_unique_id().collect()
+    assert len({i for _, i in ids}) == 10 and sorted(r for r, _ in ids) == list(range(10))
+    assert a.coalesce(2).num_partitions == 2 and sorted(a.coalesce(2).collect()) == list(range(10))
+    seen = []
+    a.foreach(seen.append)
+    assert sorted(seen) == list(range(10))
