@@ -93,7 +93,11 @@ _alias(workerState, getStaleness=lambda self: self.staleness, getAvailability=la
        getAvailableWorkers=lambda self: self.available_workers(), getMaxStaleness=lambda self: self.max_staleness(),
        setAvailability=lambda self, v: setattr(self, "available", v))
 _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partitions_with_index", getNumPartitions="get_num_partitions",
-       treeAggregate="tree_aggregate", flatMap="flat_map", mapPartitions="map_partitions", foreachPartition="foreach_partition")
+       treeAggregate="tree_aggregate", flatMap="flat_map", mapPartitions="map_partitions", foreachPartition="foreach_partition",
+       reduceByKey="reduce_by_key", groupByKey="group_by_key", keyBy="key_by", mapValues="map_values", countByKey="count_by_key",
+       countByValue="count_by_value", sortBy="sort_by", takeSample="take_sample", zipWithUniqueId="zip_with_unique_id")
+_alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
+       cancelJob=lambda self, job_id: self.scheduler.cancel_job(job_id), cancelAllJobs=lambda self: self.scheduler.cancel_all_jobs())
 
 __all__ = ["SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",
            "DenseVector", "SparseVector", "LabeledPoint", "axpyOp", "dotOp", "scalOp", "GradientDescent", "LeastSquaresGradient",
