@@ -70,12 +70,24 @@ class _VersionStore:
         self.slots = max(1, int(slots))
         self.lock = threading.Lock()
         self.versions: "OrderedDict[int, Any]" = OrderedDict()
+        self.handles: dict = {}            # version id -> TorrentBroadcast (cluster deployments only)
 
-    def put(self, vid: int, value: Any) -> None:
+    def put(self, vid: int, value: Any, handle: Any = None) -> None:
+        evicted = []
         with self.lock:
             self.versions[vid] = value
+            if handle is not None:
+                self.handles[vid] = handle
             while len(self.versions) > self.slots:
-                self.versions.popitem(last=False)
+                old, _ = self.versions.popitem(last=False)
+                h = self.handles.pop(old, None)
+                if h is not None:
+                    evicted.append(h)
+        for h in evicted:                 # cluster mode: a version that left the ring is removed from every block store
+            try:
+                h.destroy()
+            except Exception:  # noqa: BLE001
+                pass
 
     def get(self, vid: int) -> Any:
         with self.lock:
@@ -100,16 +112,50 @@ class AsyncBroadcast:
             store = _VersionStore(slots)
             setattr(ctx, "_bcast_store", store)
         self._store = store
-        self._bc = Broadcast(value)
-        self._id = self._bc.id
-        store.put(self._id, self._bc.value)
+        from .env import AsyncEnv
+        env = AsyncEnv.get()
+        if env is not None and env.is_driver:
+            # cluster deployment: every version is a TorrentBroadcast, so executors can read ``value`` AND older versions
+            # (``value(index)``) out of the block store by id — the reference's mutable-broadcast-id mechanism (A8/A9)
+            from .torrent_broadcast import TorrentBroadcast
+            self._bc = TorrentBroadcast(value, env)
+            self._id = self._bc.id
+            store.put(self._id, self._bc.value, self._bc)
+        else:
+            self._bc = Broadcast(value)
+            self._id = self._bc.id
+            store.put(self._id, self._bc.value)
+
+    # -- pickling: inside a task binary only the torrent handle + the current id travel --------------------------------
+    def __reduce__(self):
+        from .torrent_broadcast import TorrentBroadcast
+        if not isinstance(self._bc, TorrentBroadcast):
+            raise TypeError("an AsyncBroadcast can only be shipped to executor processes in a cluster deployment "
+                            "(local-cluster[n] / spark://...), where its versions live in the block store")
+        return (_rebuild_async_broadcast, (self._bc, self._id))
 
     @property
     def value(self) -> Any:
+        if self._store is None:
+            return self._read_remote(self._id)
         return self._store.get(self._id)
 
     def value_at(self, version: int) -> Any:
+        if self._store is None:
+            return self._read_remote(int(version))
         return self._store.get(int(version))
+
+    def _read_remote(self, vid: int) -> Any:
+        """Executor side: temporarily re-point the handle at version ``vid``, read it, restore the id
+        (ASYNCbroadcast.scala:24-40 does exactly this around ``bc.value``)."""
+        saved = self._bc.get_broadcast_id()
+        self._bc.change_broadcast_id(vid)
+        try:
+            return self._bc.value
+        except KeyError:
+            raise KeyError(f"broadcast version {vid} evicted from the ring or never existed") from None
+        finally:
+            self._bc.change_broadcast_id(saved)
 
     def __call__(self, version: Optional[int] = None) -> Any:
         return self.value if version is None else self.value_at(version)
@@ -122,8 +168,15 @@ class AsyncBroadcast:
         return self._id
 
     def set_id(self, new_id: int) -> None:
-        self._store.get(int(new_id))  # validate
+        if self._store is not None:
+            self._store.get(int(new_id))  # validate
         self._id = int(new_id)
 
     def available_versions(self):
-        return self._store.ids()
+        return self._store.ids() if self._store is not None else [self._id]
+
+
+def _rebuild_async_broadcast(handle, vid: int) -> "AsyncBroadcast":
+    ab = AsyncBroadcast.__new__(AsyncBroadcast)
+    ab._store, ab._bc, ab._id = None, handle, vid
+    return ab

@@ -1,22 +1,30 @@
-"""``local-cluster[n]``: a scheduler whose executors are separate OS processes.
+"""Cluster-mode scheduler: executors are separate OS processes (``local-cluster[n]``) or processes launched by
+standalone Worker daemons on any host (``spark://host:port``, see :mod:`asyncframework_b200.deploy`).
 
-This is the analogue of Spark's ``local-cluster[n, cores, memMB]`` master (core/deploy/
-LocalSparkCluster.scala:49-70) that the reference's test estate uses for "multi-process on one box"
-(SURVEY §4), and it exercises the pieces the in-process ``Scheduler`` short-circuits:
+This is the analogue of Spark's ``local-cluster[n, cores, memMB]`` master (core/deploy/LocalSparkCluster.scala:49-70)
+and of ``CoarseGrainedSchedulerBackend`` / ``CoarseGrainedExecutorBackend`` (core/scheduler/cluster/
+CoarseGrainedSchedulerBackend.scala:121,239,288-311; core/executor/CoarseGrainedExecutorBackend.scala:92,143), and
+it exercises the pieces the in-process ``Scheduler`` short-circuits:
 
-  * **task binary** — ``(dataset lineage, func)`` is serialised ONCE per job with cloudpickle (closures,
-    captured broadcast snapshots, delay-injector state…) and cached per executor, like
-    ``DAGScheduler.submitMissingTasks`` broadcasting the task binary (scheduler/DAGScheduler.scala:1051-1063);
-  * **task launch / status RPC** — small control messages over per-executor pipes
-    (CoarseGrainedSchedulerBackend ``LaunchTask`` / ``StatusUpdate``);
-  * **task-result path** — pickled results come back to a driver-side receiver thread which invokes the
-    job's result handler (JobWaiter.taskSucceeded) — so ``async_reduce`` / ``async_aggregate`` deliver
-    results one at a time exactly as on the in-process backend;
-  * **executor-side block store** — ``cache()``d partitions live in the executor process across jobs,
-    keyed by dataset id (BlockManager MEMORY_ONLY);
-  * **failure handling** — a task exception is retried on the same executor up to ``max_failures``; an
-    executor process that dies is detected (its pipe closes), its in-flight tasks fail the job and the
-    async bookkeeping frees the worker.
+  * **task binary** — ``(dataset lineage, func)`` is serialised ONCE per job with cloudpickle (closures, captured
+    broadcast handles, delay-injector state…) and cached per executor, like ``DAGScheduler.submitMissingTasks``
+    broadcasting the task binary (scheduler/DAGScheduler.scala:1051-1063);
+  * **task launch / status RPC** — small control messages (``LaunchTask`` / ``StatusUpdate``) over a pluggable
+    transport: per-executor pipes (``local-cluster``) or the TCP :class:`~asyncframework_b200.rpc.RpcEnv`
+    (standalone);
+  * **task-result path** — a serialised result up to ``max_direct_result_size`` (1 MiB) rides inside the status
+    message; a larger one is stored in the executor's BlockManager and the driver **pulls** it over the bulk
+    chunk-fetch path on a 4-thread result-getter pool, then deletes the block (``IndirectTaskResult``,
+    executor/Executor.scala:453-480; scheduler/TaskResultGetter.scala:57-125); results that would take the
+    job's total above ``max_result_size`` abort the job (TaskSetManager.scala:706-712);
+  * **per-process runtime** — the driver and every executor own an :class:`~asyncframework_b200.core.env.AsyncEnv`
+    (RpcEnv + BlockManager registered with the driver's BlockManagerMaster): ``cache()``d partitions are
+    ``rdd_<id>_<p>`` blocks of the executor's store, broadcasts are piece-wise TorrentBroadcasts;
+  * **failure handling** — a task exception is retried on the same executor up to ``max_failures``; an executor
+    process that dies is detected (pipe EOF / RPC disconnect).  With ``recover_lost_executors`` the slot is
+    re-filled (a new process for ``local-cluster``, a Master-scheduled replacement for standalone), the lost
+    tasks are re-launched there and the blocks it held are re-shipped (executor-lost resubmission,
+    DAGScheduler.scala:1520); otherwise its in-flight tasks fail the job and the async bookkeeping frees the worker.
 
 Interface-compatible with ``core.scheduler.Scheduler`` (``submit_job`` / ``run_job`` / ``set_mode`` /
 ``listeners`` / ``stop``), so every driver and the whole ShardedDataset API run unchanged.
@@ -27,9 +35,11 @@ import itertools
 import multiprocessing as mp
 import os
 import pickle
+import queue as _queue
 import threading
 import time
 import traceback
+from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
 
 import cloudpickle
@@ -38,104 +48,219 @@ from . import accumulator as _acc
 from .scheduler import JobFailed, JobWaiter, ListenerBus, TaskContext  # noqa: F401
 
 
-def _executor_main(eid: int, conn) -> None:
-    """Executor process.  A receiver thread owns the pipe: task binaries and control messages ("drop" = the job finished
-    or was cancelled, "stop") take effect immediately, task launches are queued for the single task thread — so a
-    cancellation overtakes the tasks that are still queued behind a running one."""
-    import queue as _queue
+# =================================================================================================== executor side
+class ExecutorBackend:
+    """Transport-agnostic executor.  Feed it driver messages with :meth:`handle` (from a receiver thread / an RPC
+    inbox) and run :meth:`run_tasks` on the task thread; status messages leave through ``send``.
+
+    Task binaries and control messages ("drop" = the job finished or was cancelled, "stop") take effect
+    immediately, task launches are queued for the task thread — so a cancellation overtakes the tasks that are
+    still queued behind a running one."""
+
+    def __init__(self, eid: int, send: Callable[[tuple], None]):
+        self.eid = eid
+        self._send = send
+        self.binaries: Dict[int, Any] = {}
+        self.tasks: "_queue.Queue" = _queue.Queue()
+        self._send_lock = threading.Lock()
+        self.tasks_run = 0
+
+    def send(self, msg: tuple) -> None:
+        with self._send_lock:
+            self._send(msg)
+
+    def handle(self, msg: tuple) -> bool:
+        kind = msg[0]
+        if kind == "stop":
+            self.tasks.put(None)
+            return False
+        if kind == "binary":
+            try:
+                self.binaries[msg[1]] = cloudpickle.loads(msg[2])
+            except BaseException as exc:  # noqa: BLE001  (reported when the job's tasks run)
+                self.binaries[msg[1]] = exc
+        elif kind == "drop":
+            self.binaries.pop(msg[1], None)
+        elif kind == "task":
+            self.tasks.put(msg)
+        return True
+
+    def close(self) -> None:
+        self.tasks.put(None)
+
+    def run_tasks(self) -> None:
+        from .env import AsyncEnv
+        from ..storage.block_manager import StorageLevel
+        while True:
+            msg = self.tasks.get()
+            if msg is None:
+                return
+            _, job_id, partition, attempt, submit_ms = msg
+            t0 = time.perf_counter()
+            binary = self.binaries.get(job_id)
+            if binary is None:                        # job finished or cancelled while this task was queued
+                self.send(("gone", job_id, partition, attempt, "", 0.0))
+                continue
+            try:
+                if isinstance(binary, BaseException):
+                    raise binary
+                dataset, func, fault = binary
+                tctx = TaskContext(job_id, partition, attempt, self.eid, None, None, submit_ms)
+                _acc.begin_task()
+                if fault is not None:
+                    fault(tctx)
+                result = func(tctx, dataset.iterator(partition, tctx))
+                data = cloudpickle.dumps((result, _acc.end_task(True)))      # accumulator updates ride with the result
+                run_ms = (time.perf_counter() - t0) * 1e3
+                self.tasks_run += 1
+                env = AsyncEnv.get()
+                if env is not None and len(data) > env.limits.max_direct_result_size:
+                    block_id = f"taskresult_{job_id}_{partition}_{attempt}"
+                    env.block_manager.put_bytes(block_id, data, StorageLevel.MEMORY_AND_DISK_SER)  # type: ignore[attr-defined]
+                    self.send(("indirect", job_id, partition, attempt, (block_id, len(data), tuple(env.block_manager.id)), run_ms))
+                else:
+                    self.send(("ok", job_id, partition, attempt, data, run_ms))
+            except BaseException as exc:  # noqa: BLE001
+                _acc.end_task(False)
+                self.send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
+
+
+def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
+    """``local-cluster`` executor process: control messages over a pipe, blocks over its own RpcEnv."""
     import torch
     torch.set_num_threads(1)
-    binaries: Dict[int, Any] = {}
-    tasks: "_queue.Queue" = _queue.Queue()
-    send_lock = threading.Lock()
-
-    def send(msg) -> None:
-        with send_lock:
-            conn.send(msg)
+    env = None
+    if driver_address is not None:
+        from .env import AsyncEnv
+        env = AsyncEnv.create_executor(str(eid), driver_address, limits)
+    backend = ExecutorBackend(eid, conn.send)
 
     def receiver() -> None:
         while True:
             try:
                 msg = conn.recv()
             except (EOFError, OSError):
-                tasks.put(None)
+                backend.close()
                 return
-            kind = msg[0]
-            if kind == "stop":
-                tasks.put(None)
+            if not backend.handle(msg):
                 return
-            if kind == "binary":
-                try:
-                    binaries[msg[1]] = cloudpickle.loads(msg[2])
-                except BaseException as exc:  # noqa: BLE001  (reported when the job's tasks run)
-                    binaries[msg[1]] = exc
-            elif kind == "drop":
-                binaries.pop(msg[1], None)
-            elif kind == "task":
-                tasks.put(msg)
 
     threading.Thread(target=receiver, daemon=True, name=f"executor-{eid}-recv").start()
-    while True:
-        msg = tasks.get()
-        if msg is None:
-            return
-        _, job_id, partition, attempt, submit_ms = msg
-        t0 = time.perf_counter()
-        binary = binaries.get(job_id)
-        if binary is None:                        # job finished or cancelled while this task was queued
-            send(("gone", job_id, partition, attempt, "", 0.0))
-            continue
+    try:
+        backend.run_tasks()
+    finally:
+        if env is not None:
+            env.stop()
+
+
+# =================================================================================================== transports
+class PipeTransport:
+    """``local-cluster[n]``: the scheduler forks ``n`` executor processes itself and talks to them over pipes."""
+
+    def __init__(self, num_executors: int, name: str):
+        self.num_executors = num_executors
+        self.name = name
+        self._ctx = mp.get_context("spawn")
+        self._conns: List[Any] = [None] * num_executors
+        self._procs: List[Any] = [None] * num_executors
+        self._send_locks = [threading.Lock() for _ in range(num_executors)]
+        self._gen = [0] * num_executors
+        self.sched: "ClusterScheduler" = None  # type: ignore[assignment]
+
+    def start(self, sched: "ClusterScheduler") -> None:
+        self.sched = sched
+        for e in range(self.num_executors):
+            self._launch(e)
+
+    def _launch(self, e: int) -> None:
+        parent, child = self._ctx.Pipe()
+        env = self.sched.env
+        p = self._ctx.Process(target=_executor_main, name=f"{self.name}-executor-{e}", daemon=True,
+                              args=(e, child, tuple(env.rpc_env.address) if env is not None else None,
+                                    env.limits if env is not None else None))
+        p.start()
+        child.close()
+        self._conns[e], self._procs[e] = parent, p
+        self._gen[e] += 1
+        threading.Thread(target=self._recv_loop, args=(e, parent, self._gen[e]), daemon=True,
+                         name=f"{self.name}-recv-{e}").start()
+
+    def _recv_loop(self, eid: int, conn, gen: int) -> None:
+        while not self.sched._stopped:
+            try:
+                msg = conn.recv()
+            except (EOFError, OSError):
+                if gen == self._gen[eid]:
+                    self.sched._executor_lost(eid)
+                return
+            self.sched._on_message(eid, msg)
+
+    def send(self, eid: int, msg: tuple) -> None:
+        with self._send_locks[eid]:
+            self._conns[eid].send(msg)
+
+    def relaunch(self, eid: int) -> bool:
         try:
-            if isinstance(binary, BaseException):
-                raise binary
-            dataset, func, fault = binary
-            tctx = TaskContext(job_id, partition, attempt, eid, None, None, submit_ms)
-            _acc.begin_task()
-            if fault is not None:
-                fault(tctx)
-            result = func(tctx, dataset.iterator(partition, tctx))
-            data = cloudpickle.dumps((result, _acc.end_task(True)))      # accumulator updates ride with the result
-            send(("ok", job_id, partition, attempt, data, (time.perf_counter() - t0) * 1e3))
-        except BaseException as exc:  # noqa: BLE001
-            _acc.end_task(False)
-            send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
+            self._conns[eid].close()
+        except OSError:
+            pass
+        self._launch(eid)
+        return True
+
+    def kill(self, eid: int) -> None:
+        self._procs[eid].kill()
+
+    def stop(self) -> None:
+        for e, c in enumerate(self._conns):
+            try:
+                with self._send_locks[e]:
+                    c.send(("stop",))
+            except (OSError, BrokenPipeError, AttributeError):
+                pass
+        for p in self._procs:
+            if p is None:
+                continue
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+        for c in self._conns:
+            try:
+                c.close()
+            except (OSError, AttributeError):
+                pass
 
 
+# =================================================================================================== driver side
 class ClusterScheduler:
     _job_ids = itertools.count(1_000_000)
 
     def __init__(self, num_executors: int = 2, max_failures: int = 4, block_first_async_job: bool = True,
-                 name: str = "afb-cluster"):
+                 name: str = "afb-cluster", transport=None, limits=None, recover_lost_executors: bool = False,
+                 use_env: bool = True):
         self.num_executors = int(num_executors)
         self.max_failures = int(max_failures)
         self.block_first_async_job = block_first_async_job
+        self.recover_lost_executors = recover_lost_executors
         self.mode = 0
         self.first_iter = 1
         self.device = None
         self.listeners = ListenerBus()
         self.fault_injector: Optional[Callable[[TaskContext], None]] = None
         self.failed_jobs: List[int] = []
-        self._ctx = mp.get_context("spawn")
-        self._conns = []
-        self._procs = []
-        self._send_locks = []
         self._jobs: Dict[int, dict] = {}
         self._lock = threading.Lock()
         self._stopped = False
         self._blocks_held: Dict[int, set] = {}       # source block id -> executors that already hold its data
         self.last_task_binary_bytes = 0
-        for e in range(self.num_executors):
-            parent, child = self._ctx.Pipe()
-            p = self._ctx.Process(target=_executor_main, args=(e, child), name=f"{name}-executor-{e}", daemon=True)
-            p.start()
-            child.close()
-            self._conns.append(parent)
-            self._procs.append(p)
-            self._send_locks.append(threading.Lock())
-        self._receivers = [threading.Thread(target=self._recv_loop, args=(e,), daemon=True, name=f"{name}-recv-{e}")
-                           for e in range(self.num_executors)]
-        for t in self._receivers:
-            t.start()
+        self.indirect_results = 0
+        self.executors_recovered = 0
+        self._getter = ThreadPoolExecutor(4, thread_name_prefix=f"{name}-task-result-getter")
+        self.env = None
+        if use_env:
+            from .env import AsyncEnv, RuntimeLimits
+            self.env = AsyncEnv.create_driver(limits or RuntimeLimits(), name=f"{name}-driver")
+        self.transport = transport if transport is not None else PipeTransport(self.num_executors, name)
+        self.transport.start(self)
 
     # ------------------------------------------------------------------ mode
     def set_mode(self, mode: int) -> None:
@@ -146,50 +271,85 @@ class ClusterScheduler:
 
     # ------------------------------------------------------------------ plumbing
     def _send(self, eid: int, msg) -> None:
-        with self._send_locks[eid]:
-            self._conns[eid].send(msg)
+        self.transport.send(eid, msg)
 
-    def _recv_loop(self, eid: int) -> None:
-        conn = self._conns[eid]
-        while not self._stopped:
-            try:
-                msg = conn.recv()
-            except (EOFError, OSError):
-                self._executor_lost(eid)
-                return
-            kind, job_id, partition, attempt, data, run_ms = msg
-            with self._lock:
-                job = self._jobs.get(job_id)
-            if job is None:
-                continue
-            waiter: JobWaiter = job["waiter"]
-            if kind == "gone":
-                continue
-            if kind == "ok":
-                self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
-                                     "run_ms": run_ms, "metrics": {"result_bytes": len(data)}})
-                try:
-                    result, acc_updates = pickle.loads(data)
-                    if not waiter.cancelled:
-                        _acc.merge_updates(acc_updates)
-                    waiter.task_succeeded(partition, result)
-                except Exception as exc:  # a raising result handler fails the job, not the receiver thread
-                    waiter.job_failed(exc)
-                job["pending"].discard(partition)
-                if waiter.done:
-                    self._finish_job(job_id)
+    def _on_message(self, eid: int, msg: tuple) -> None:
+        kind, job_id, partition, attempt, data, run_ms = msg
+        with self._lock:
+            job = self._jobs.get(job_id)
+        if job is None or kind == "gone":
+            if kind == "indirect" and self.env is not None:       # nobody will read it: free the executor's block
+                self._getter.submit(self._drop_result_block, data[0])
+            return
+        if kind == "ok":
+            self._task_succeeded(eid, job_id, job, partition, data, run_ms, len(data))
+        elif kind == "indirect":
+            self._getter.submit(self._fetch_indirect, eid, job_id, job, partition, data, run_ms)
+        else:
+            attempt += 1
+            self.listeners.post({"event": "task_failed", "job": job_id, "partition": partition, "attempt": attempt, "error": data})
+            if attempt >= self.max_failures:
+                self.failed_jobs.append(job_id)
+                exc = RuntimeError(f"task {partition} of job {job_id} failed {attempt} times: {data.splitlines()[0]}")
+                self._fail_task(job, partition, exc)
             else:
-                attempt += 1
-                self.listeners.post({"event": "task_failed", "job": job_id, "partition": partition, "attempt": attempt, "error": data})
-                if attempt >= self.max_failures:
-                    self.failed_jobs.append(job_id)
-                    exc = RuntimeError(f"task {partition} of job {job_id} failed {attempt} times: {data.splitlines()[0]}")
-                    if job["on_task_lost"] is not None:
-                        job["on_task_lost"](partition, exc)
-                    waiter.job_failed(exc)
-                    job["pending"].discard(partition)
-                else:
-                    self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
+                self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
+
+    def _fail_task(self, job: dict, partition: int, exc: BaseException) -> None:
+        if job["on_task_lost"] is not None:
+            job["on_task_lost"](partition, exc)
+        job["waiter"].job_failed(exc)
+        job["pending"].discard(partition)
+
+    def _task_succeeded(self, eid: int, job_id: int, job: dict, partition: int, data: bytes, run_ms: float, nbytes: int) -> None:
+        waiter: JobWaiter = job["waiter"]
+        limit = self.env.limits.max_result_size if self.env is not None else 0
+        with self._lock:
+            job["result_bytes"] += nbytes
+            too_big = bool(limit) and job["result_bytes"] > limit
+        if too_big:
+            exc = RuntimeError(f"Total size of serialized results of job {job_id} ({job['result_bytes']} bytes) is bigger "
+                               f"than max_result_size ({limit} bytes)")
+            self.failed_jobs.append(job_id)
+            self._fail_task(job, partition, exc)
+            return
+        self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
+                             "run_ms": run_ms, "metrics": {"result_bytes": nbytes}})
+        try:
+            result, acc_updates = pickle.loads(data)
+            if not waiter.cancelled:
+                _acc.merge_updates(acc_updates)
+            waiter.task_succeeded(partition, result)
+        except Exception as exc:  # a raising result handler fails the job, not the receiver thread
+            waiter.job_failed(exc)
+        job["pending"].discard(partition)
+        if waiter.done:
+            self._finish_job(job_id)
+
+    def _fetch_indirect(self, eid: int, job_id: int, job: dict, partition: int, ref, run_ms: float) -> None:
+        """``TaskResultGetter.enqueueSuccessfulTask`` for an IndirectTaskResult: pull the block, then delete it."""
+        from ..storage.block_manager import BlockManagerId
+        block_id, size, holder = ref
+        limit = self.env.limits.max_result_size
+        if limit and size > limit:
+            self._drop_result_block(block_id)
+            self.failed_jobs.append(job_id)
+            self._fail_task(job, partition, RuntimeError(
+                f"result of task {partition} of job {job_id} ({size} bytes) is bigger than max_result_size ({limit} bytes)"))
+            return
+        data = self.env.block_manager.get_remote_bytes(block_id, [BlockManagerId(*holder)])
+        self._drop_result_block(block_id)
+        if data is None:                               # the executor died between the status message and the fetch
+            self._fail_task(job, partition, RuntimeError(f"lost the result block {block_id} of job {job_id}"))
+            return
+        self.indirect_results += 1
+        self._task_succeeded(eid, job_id, job, partition, data, run_ms, size)
+
+    def _drop_result_block(self, block_id: str) -> None:
+        try:
+            self.env.bm_master.remove_block(block_id)
+        except Exception:  # noqa: BLE001
+            pass
 
     def cancel_job(self, job_id: int, reason: str = "cancelled by user") -> bool:
         """``SparkContext.cancelJob`` over executor processes: the waiter raises JobCancelled, the task binary is dropped on
@@ -203,7 +363,7 @@ class ClusterScheduler:
         for e in job["executors"]:
             try:
                 self._send(e, ("drop", job_id))
-            except (OSError, BrokenPipeError):
+            except Exception:  # noqa: BLE001  (a dead executor has nothing to drop)
                 pass
         if job["on_task_lost"] is not None:
             for p in sorted(job["pending"]):
@@ -219,16 +379,53 @@ class ClusterScheduler:
     def _executor_lost(self, eid: int) -> None:
         if self._stopped:
             return
+        self.listeners.post({"event": "executor_lost", "executor": eid, "t_ms": time.perf_counter() * 1e3})
         with self._lock:
             jobs = list(self._jobs.items())
+            for held in self._blocks_held.values():       # whatever it cached is gone: re-ship on next use
+                held.discard(eid)
+        if self.env is not None:
+            try:
+                self.env.bm_master.remove_executor(str(eid))
+            except Exception:  # noqa: BLE001
+                pass
+        if self.recover_lost_executors and self._recover(eid, jobs):
+            return
         for job_id, job in jobs:
             lost = [p for p in list(job["pending"]) if p % self.num_executors == eid]
             for p in lost:
-                exc = RuntimeError(f"executor {eid} lost while running partition {p} of job {job_id}")
-                if job["on_task_lost"] is not None:
-                    job["on_task_lost"](p, exc)
-                job["waiter"].job_failed(exc)
-                job["pending"].discard(p)
+                self._fail_task(job, p, RuntimeError(f"executor {eid} lost while running partition {p} of job {job_id}"))
+
+    def _recover(self, eid: int, jobs) -> bool:
+        """Re-fill the slot and re-launch what the dead executor was running (DAGScheduler.handleExecutorLost ->
+        resubmit).  The replacement starts with an empty store, so task binaries are re-sent WITH their source
+        blocks."""
+        try:
+            if not self.transport.relaunch(eid):
+                return False
+        except Exception:  # noqa: BLE001
+            traceback.print_exc()
+            return False
+        self.executors_recovered += 1
+        self.listeners.post({"event": "executor_added", "executor": eid, "t_ms": time.perf_counter() * 1e3})
+        for job_id, job in jobs:
+            lost = sorted(p for p in job["pending"] if p % self.num_executors == eid)
+            if not lost:
+                continue
+            job["lost_count"] = job.get("lost_count", 0) + 1
+            if job["lost_count"] >= self.max_failures:
+                for p in lost:
+                    self._fail_task(job, p, RuntimeError(f"executor {eid} lost {job['lost_count']} times during job {job_id}"))
+                continue
+            try:
+                self._send(eid, ("binary", job_id, job["make_payload"]([eid])))
+                for p in lost:
+                    self.listeners.post({"event": "task_resubmitted", "job": job_id, "partition": p, "executor": eid})
+                    self._send(eid, ("task", job_id, p, 0, job["submit_ms"]))
+            except Exception as exc:  # noqa: BLE001
+                for p in lost:
+                    self._fail_task(job, p, exc)
+        return True
 
     def _finish_job(self, job_id: int) -> None:
         with self._lock:
@@ -238,7 +435,7 @@ class ClusterScheduler:
         for e in job["executors"]:
             try:
                 self._send(e, ("drop", job_id))
-            except (OSError, BrokenPipeError):
+            except Exception:  # noqa: BLE001
                 pass
         self.listeners.post({"event": "job_end", "job": job_id, "t_ms": time.perf_counter() * 1e3})
 
@@ -255,20 +452,28 @@ class ClusterScheduler:
         executors = sorted({p % self.num_executors for p in parts})
         # source data travels once per executor: blocks every target executor already holds are pickled as references
         from ..data.dataset import ShippingContext
-        with self._lock:
-            held = {b: set(es) for b, es in self._blocks_held.items()}
-        with ShippingContext(lambda b: all(e in held.get(b, ()) for e in executors)) as ship:
-            payload = cloudpickle.dumps((dataset, func, self.fault_injector))
+        fault = self.fault_injector
+
+        def make_payload(targets: List[int]) -> bytes:
+            with self._lock:
+                held = {b: set(es) for b, es in self._blocks_held.items()}
+            with ShippingContext(lambda b: all(e in held.get(b, ()) for e in targets)) as ship:
+                payload = cloudpickle.dumps((dataset, func, fault))
+            make_payload.shipped = ship.shipped        # type: ignore[attr-defined]
+            return payload
+
+        payload = make_payload(executors)
         self.last_task_binary_bytes = len(payload)
         with self._lock:
             self._jobs[job_id] = {"waiter": waiter, "pending": set(parts), "on_task_lost": on_task_lost,
-                                  "executors": executors, "submit_ms": now}
+                                  "executors": executors, "submit_ms": now, "result_bytes": 0,
+                                  "make_payload": make_payload}
         self.listeners.post({"event": "job_start", "job": job_id, "partitions": parts, "t_ms": now,
                              "task_binary_bytes": len(payload)})
         for e in executors:
             self._send(e, ("binary", job_id, payload))
-        with self._lock:                              # only now may a later job refer to these blocks by id (pipe order)
-            for b in ship.shipped:
+        with self._lock:                              # only now may a later job refer to these blocks by id (message order)
+            for b in make_payload.shipped:            # type: ignore[attr-defined]
                 self._blocks_held.setdefault(b, set()).update(executors)
         for p in parts:
             self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0,
@@ -298,27 +503,20 @@ class ClusterScheduler:
 
     def kill_executor(self, eid: int) -> None:
         """Fault injection: kill one executor process (FailureSuite / DistributedSuite style)."""
-        self._procs[eid].kill()
+        self.transport.kill(eid)
+
+    def storage_status(self) -> dict:
+        """Per-process block-store usage as the driver's BlockManagerMaster sees it (``sc.getExecutorStorageStatus``)."""
+        return {} if self.env is None else self.env.bm_master.storage_status()
 
     def stop(self) -> None:
         if self._stopped:
             return
         self._stopped = True
-        for e, c in enumerate(self._conns):
-            try:
-                with self._send_locks[e]:
-                    c.send(("stop",))
-            except (OSError, BrokenPipeError):
-                pass
-        for p in self._procs:
-            p.join(timeout=5)
-            if p.is_alive():
-                p.terminate()
-        for c in self._conns:
-            try:
-                c.close()
-            except OSError:
-                pass
+        self.transport.stop()
+        self._getter.shutdown(wait=False)
+        if self.env is not None:
+            self.env.stop()
 
     def __enter__(self):
         return self

@@ -82,6 +82,7 @@ class AsyncEnv:
         rpc.setup_endpoint(BlockUploadEndpoint.NAME, BlockUploadEndpoint(bm))
         env = cls("driver", rpc, bm, limits, True, BlockManagerMaster(master_ref))
         env.master_endpoint = master_ep
+        env._prev = cls._instance if (cls._instance is not None and not cls._instance._stopped) else None
         cls.set(env)
         return env
 
@@ -105,5 +106,6 @@ class AsyncEnv:
             self.block_manager.stop()
         finally:
             self.rpc_env.shutdown()
-            if AsyncEnv._instance is self:
-                AsyncEnv.set(None)
+            if AsyncEnv._instance is self:       # several drivers in one process (tests): fall back to the outer one
+                prev = getattr(self, "_prev", None)
+                AsyncEnv.set(prev if prev is not None and not prev._stopped else None)

@@ -78,6 +78,11 @@ class AsyncSession:
 
     # ---- broadcast / async context -----------------------------------------------------------
     def broadcast(self, value: Any) -> Broadcast:
+        """In-process masters share the snapshot by reference (like Spark's local mode); cluster masters write a
+        piece-wise :class:`TorrentBroadcast` into the driver's block manager and ship only the handle."""
+        if getattr(self.scheduler, "env", None) is not None:
+            from .torrent_broadcast import TorrentBroadcast
+            return TorrentBroadcast(value, self.scheduler.env)
         return Broadcast(value)
 
     def long_accumulator(self, name: Optional[str] = None):

@@ -52,6 +52,28 @@ _ds_ids = itertools.count(1)
 # process evaluates the partition (BlockManager MEMORY_ONLY analogue for the process-based scheduler)
 _BLOCK_STORE: dict = {}
 
+
+def _cache_get(ds_id: int, p: int, kind: str):
+    """(found, value) from the executor's BlockManager when this process has an AsyncEnv (cluster executors: the block is
+    ``rdd_<dataset>_<partition>``, accounted, evictable and visible in the driver's storage status), else from the
+    plain per-process dict."""
+    from ..core.env import AsyncEnv
+    env = AsyncEnv.get()
+    if env is not None and not env.is_driver:
+        return env.block_manager.get_local_values(f"rdd_{ds_id}_{p}{kind}")
+    key = (ds_id, p, kind)
+    return (True, _BLOCK_STORE[key]) if key in _BLOCK_STORE else (False, None)
+
+
+def _cache_put(ds_id: int, p: int, kind: str, value) -> None:
+    from ..core.env import AsyncEnv
+    env = AsyncEnv.get()
+    if env is not None and not env.is_driver:
+        from ..storage.block_manager import StorageLevel
+        env.block_manager.put_single(f"rdd_{ds_id}_{p}{kind}", value, StorageLevel.MEMORY_ONLY)   # does not fit -> recomputed next time
+        return
+    _BLOCK_STORE[(ds_id, p, kind)] = value
+
 # ---- ship-once source data (cluster mode) -------------------------------------------------------------------
 # A dataset's SOURCE (the parallelised records / the HBM or host shards) sits at the root of its lineage, and the
 # lineage is part of every job's task binary.  Spark ships a ParallelCollectionRDD's data with every task; for an
@@ -207,8 +229,10 @@ class ShardedDataset:
     def iterator(self, p: int, tctx=None) -> Iterator:
         if self._cached_records is not None and self._cached_records[p] is not None:
             return iter(self._cached_records[p])
-        if self._want_cache and (self.ds_id, p, "r") in _BLOCK_STORE:
-            return iter(_BLOCK_STORE[(self.ds_id, p, "r")])
+        if self._want_cache:
+            found, recs = _cache_get(self.ds_id, p, "r")
+            if found:
+                return iter(recs)
         if self._compute is not None:
             it = self._compute(p, tctx)
         else:
@@ -220,7 +244,7 @@ class ShardedDataset:
                 if self._cached_records is None:
                     self._cached_records = [None] * self.num_partitions
                 self._cached_records[p] = recs
-            _BLOCK_STORE[(self.ds_id, p, "r")] = recs
+            _cache_put(self.ds_id, p, "r", recs)
             return iter(recs)
         return it
 
@@ -229,15 +253,17 @@ class ShardedDataset:
             raise TypeError(f"dataset {self.name!r} has no batch-level view (a record-level map broke the columnar lineage)")
         if self._cached_batches is not None and self._cached_batches[p] is not _EMPTY:
             return self._cached_batches[p]
-        if self._want_cache and (self.ds_id, p, "b") in _BLOCK_STORE:
-            return _BLOCK_STORE[(self.ds_id, p, "b")]
+        if self._want_cache:
+            found, blk = _cache_get(self.ds_id, p, "b")
+            if found:
+                return blk
         b = self._batch(p, tctx)
         if self._want_cache:
             with self._cache_lock:
                 if self._cached_batches is None:
                     self._cached_batches = [_EMPTY] * self.num_partitions
                 self._cached_batches[p] = b
-            _BLOCK_STORE[(self.ds_id, p, "b")] = b
+            _cache_put(self.ds_id, p, "b", b)
         return b
 
     def cache(self) -> "ShardedDataset":

@@ -210,3 +210,80 @@ def test_key_value_shuffles_agree_across_executor_processes(cluster):
     a = ShardedDataset.from_records(cluster, list(range(12)), 3)
     assert sorted(a.union(a.map(lambda x: x + 100)).collect()) == list(range(12)) + list(range(100, 112))
     assert a.zip(a.map(lambda x: -x)).collect() == [(i, -i) for i in range(12)]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# runtime around the executors: block managers, torrent broadcast, indirect results, executor recovery
+def test_cached_partitions_are_blocks_of_the_executor_block_managers(cluster):
+    from asyncframework_b200.data.dataset import ShardedDataset
+    ds = ShardedDataset.from_records(cluster, list(range(40)), 4).map(lambda x: x * 2).cache()
+    assert ds.count() == 40
+    st = cluster.storage_status()
+    rdd_blocks = {b for m, s in st.items() for b in s["blocks"] if b.startswith(f"rdd_{ds.ds_id}_")}
+    assert rdd_blocks == {f"rdd_{ds.ds_id}_{p}r" for p in range(4)}
+    assert all(s["mem_used"] > 0 for m, s in st.items() if m.executor_id != "driver")
+    assert cluster.env.bm_master.remove_rdd(ds.ds_id) == 4                    # unpersist
+    assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == sum(2 * x + 1 for x in range(40))   # recomputed
+
+
+def test_torrent_broadcast_and_async_broadcast_history_in_executor_processes():
+    import torch
+    from asyncframework_b200.core.session import AsyncSession
+    from asyncframework_b200.core.torrent_broadcast import TorrentBroadcast
+    with AsyncSession("local-cluster[2]") as sc:
+        w = torch.arange(200_000, dtype=torch.float64)
+        bc = sc.broadcast(w)
+        assert isinstance(bc, TorrentBroadcast)
+        ds = sc.parallelize(range(8), 4)
+        out = ds.map(lambda i: float(bc.value[i])).collect()
+        assert out == [float(i) for i in range(8)]
+        assert sc.scheduler.last_task_binary_bytes < 50_000                 # the 1.6 MB tensor did not ride in the task binary
+        ctx = sc.async_context(4)
+        v0 = sc.async_broadcast(ctx, torch.zeros(4))
+        v1 = sc.async_broadcast(ctx, torch.ones(4))
+        i0 = v0.index
+        got = ds.map(lambda i: (float(v1.value[0]), float(v1.value_at(i0)[0]), v1.index)).collect()
+        assert got == [(1.0, 0.0, v1.index)] * 8                            # current version AND an older one, by id
+        bc.destroy()
+
+
+def test_large_results_take_the_indirect_path_and_max_result_size_aborts():
+    import numpy as np
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.core.env import RuntimeLimits
+    from asyncframework_b200.core.scheduler import JobFailed
+    from asyncframework_b200.data.dataset import ShardedDataset
+    lim = RuntimeLimits(max_direct_result_size=64 * 1024, max_result_size=3 << 20)
+    with ClusterScheduler(2, limits=lim) as s:
+        ds = ShardedDataset.from_records(s, list(range(4)), 4)
+        small = ds.map(lambda i: i).collect()
+        assert small == [0, 1, 2, 3] and s.indirect_results == 0
+        big = ds.map_partitions(lambda it: [np.full(40_000, float(next(iter(it))))]).collect()    # 320 KB per task
+        assert [float(a[0]) for a in big] == [0.0, 1.0, 2.0, 3.0] and s.indirect_results == 4
+        time.sleep(0.3)
+        st = s.storage_status()
+        assert not any(b.startswith("taskresult_") for m in st.values() for b in m["blocks"])      # fetched, then deleted
+        with pytest.raises(JobFailed, match="max_result_size"):
+            ds.map_partitions(lambda it: [np.zeros(200_000)]).collect()                              # 4 x 1.6 MB > 3 MiB
+
+
+def test_lost_executor_is_replaced_and_its_tasks_are_resubmitted():
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.data.dataset import ShardedDataset
+    events = []
+    with ClusterScheduler(2, recover_lost_executors=True) as s:
+        s.listeners.add(lambda e: events.append(e["event"]))
+        ds = ShardedDataset.from_records(s, list(range(20)), 4)
+        assert ds.count() == 20                                           # executors now hold the source blocks
+
+        def slow(tctx, it):
+            time.sleep(1.0)
+            return sum(it)
+        w = s.submit_job(ds, slow, result_handler=(res := {}).__setitem__)
+        time.sleep(0.3)
+        s.kill_executor(1)                                                # dies mid-task; partitions 1 and 3 are lost
+        assert w.wait(30)
+        assert res == {p: sum(range(5 * p, 5 * p + 5)) for p in range(4)}
+        assert s.executors_recovered == 1
+        assert "executor_lost" in events and "executor_added" in events and "task_resubmitted" in events
+        assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 210   # the replacement got the data re-shipped
