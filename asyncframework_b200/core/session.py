@@ -5,7 +5,7 @@ Bundles what ``new SparkContext(conf)`` sets up for the ASYNC samples (core/Spar
 (``parallelize``, ``text_file``, ``load_libsvm_file``), the blocking/non-blocking job mode switch
 (``set_mode``, SparkContext.scala:87-104) and log level.  Master URL grammar follows
 SparkContext.scala:2805-2811: ``local``, ``local[N]``, ``local[*]``, ``local[N,F]`` (F = max task
-failures); ``fused`` selects the multi-GPU fused backend (one process per GPU, see FusedEngine).
+failures), ``local-cluster[n,c,m]`` (executor processes), ``spark://host:port`` (standalone master); ``fused`` selects the multi-GPU fused backend (one process per GPU, see FusedEngine).
 """
 from __future__ import annotations
 
@@ -26,7 +26,8 @@ _LOCAL_CLUSTER = re.compile(r"^local-cluster\[\s*(\d+)\s*(?:,\s*(\d+)\s*(?:,\s*(
 
 class AsyncSession:
     def __init__(self, master: str = "local[*]", app_name: str = "asyncframework_b200", device=None,
-                 conf: Optional[AsyncConfig] = None):
+                 conf: Optional[AsyncConfig] = None, num_executors: Optional[int] = None, cores_per_executor: int = 1,
+                 executor_memory_mb: int = 512):
         self.master = master
         self.app_name = app_name
         self.conf = conf or AsyncConfig()
@@ -35,6 +36,14 @@ class AsyncSession:
         if master.startswith("local-cluster"):
             from .cluster import ClusterScheduler
             self.scheduler = ClusterScheduler(n, max_failures=max_fail, name=app_name)
+        elif master.startswith(("spark://", "async://")):
+            # standalone cluster manager (deploy/master.py, deploy/worker.py): executors are forked by Worker daemons on
+            # any host and talk to this driver over TCP; a lost executor is replaced by the Master and its tasks re-run
+            from ..deploy.client import StandaloneTransport
+            from .cluster import ClusterScheduler
+            transport = StandaloneTransport(master, num_executors, cores_per_executor, executor_memory_mb, app_name)
+            self.scheduler = ClusterScheduler(num_executors or 1, max_failures=max_fail, name=app_name, transport=transport,
+                                              recover_lost_executors=True)
         else:
             self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name)
         self._stopped = False
@@ -51,6 +60,8 @@ class AsyncSession:
         if m:                                  # local-cluster[numExecutors, coresPerExecutor, memoryMB]
             return max(1, int(m.group(1))), 4
         if master in ("fused", "gloo"):
+            return 1, 4
+        if re.match(r"^(spark|async)://[^:/]+:\d+$", master):
             return 1, 4
         raise ValueError(f"Could not parse Master URL: '{master}'")
 

@@ -1,0 +1,214 @@
+"""Application side of the standalone deployment: the driver's scheduler backend + an in-process test cluster.
+
+``StandaloneTransport`` is what ``StandaloneSchedulerBackend`` + ``StandaloneAppClient`` + the ``DriverEndpoint`` of
+``CoarseGrainedSchedulerBackend`` are in the reference (core/scheduler/cluster/StandaloneSchedulerBackend.scala:37,
+core/deploy/client/StandaloneAppClient.scala, CoarseGrainedSchedulerBackend.scala:121,239): it registers the
+application with the Master, receives ``ExecutorAdded`` / ``ExecutorUpdated``, accepts ``RegisterExecutor`` from the
+executors the workers fork, routes their ``StatusUpdate`` messages into :class:`ClusterScheduler` and turns a dropped
+executor connection into ``_executor_lost`` — after which the Master re-fills the slot and the scheduler re-launches
+the lost tasks on the replacement.
+
+``LocalStandaloneCluster`` = ``LocalSparkCluster`` (core/deploy/LocalSparkCluster.scala:49-70): a Master and ``n``
+Workers inside this process (each with its own RpcEnv), forking real executor processes — the multi-process,
+real-TCP deployment on one box.
+"""
+from __future__ import annotations
+
+import os
+import signal
+import threading
+import time
+from typing import Dict, List, Optional
+
+from ..rpc import RpcAddress, RpcCallContext, RpcEndpoint, RpcEndpointRef, RpcError
+from .master import start_master
+from .worker import start_worker
+
+
+class _DriverEndpoint(RpcEndpoint):
+    NAME = "CoarseGrainedScheduler"
+
+    def __init__(self, transport: "StandaloneTransport"):
+        self.t = transport
+
+    def receive(self, msg, sender) -> None:
+        op = msg[0]
+        if op == "status":
+            _, slot, exec_id, status = msg
+            if self.t.exec_ids.get(slot) == exec_id:         # ignore stragglers from a replaced executor
+                self.t.sched._on_message(slot, status)
+        elif op == "executor_added":
+            self.t.events.append(msg)
+        elif op == "executor_updated":
+            self.t.events.append(msg)
+            _, exec_id, slot, state, message, exit_code = msg
+            if state in ("EXITED", "KILLED", "FAILED", "LOST"):
+                self.t._slot_down(slot, exec_id, f"{state}: {message}")
+        elif op == "application_removed":
+            self.t.app_state = msg[1]
+            if msg[1] == "FAILED":
+                self.t._app_failed()
+        else:
+            raise RpcError(f"driver endpoint: unknown message {op!r}")
+
+    def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
+        if msg[0] == "register_executor":
+            _, slot, exec_id, ref, cores, pid, host = msg
+            if not (0 <= slot < self.t.num_executors):
+                ctx.reply(("refused", f"slot {slot} out of range"))
+                return
+            with self.t.cv:
+                self.t.refs[slot] = ref
+                self.t.exec_ids[slot] = exec_id
+                self.t.pids[slot] = (host, pid)
+                self.t.addresses[slot] = ref.address
+                self.t.cv.notify_all()
+            ctx.reply(("registered", self.t.sched.env.limits))
+        else:
+            ctx.send_failure(RpcError(f"driver endpoint: unknown request {msg[0]!r}"))
+
+    def on_disconnected(self, address: RpcAddress) -> None:
+        for slot, addr in list(self.t.addresses.items()):
+            if addr == address:
+                self.t._slot_down(slot, self.t.exec_ids.get(slot), "connection lost")
+
+
+class StandaloneTransport:
+    """Plug into ``ClusterScheduler(transport=...)``.  ``num_executors=None`` asks the master for one executor per
+    alive worker (the standalone default: an application takes every worker)."""
+
+    def __init__(self, master_url: str, num_executors: Optional[int] = None, cores_per_executor: int = 1,
+                 memory_mb: int = 512, app_name: str = "asyncframework_b200", register_timeout: float = 60.0):
+        self.master_address = RpcAddress.parse(master_url)
+        self.num_executors = num_executors
+        self.cores_per_executor, self.memory_mb, self.app_name = cores_per_executor, memory_mb, app_name
+        self.register_timeout = register_timeout
+        self.refs: Dict[int, RpcEndpointRef] = {}
+        self.exec_ids: Dict[int, int] = {}
+        self.pids: Dict[int, tuple] = {}
+        self.addresses: Dict[int, RpcAddress] = {}
+        self.cv = threading.Condition()
+        self.events: List[tuple] = []
+        self.app_id: Optional[str] = None
+        self.app_state = "RUNNING"
+        self.sched = None
+        self.master: Optional[RpcEndpointRef] = None
+
+    # ---- ClusterScheduler transport interface -------------------------------------------------------------------------
+    def start(self, sched) -> None:
+        if sched.env is None:
+            raise RuntimeError("the standalone deployment needs the scheduler's AsyncEnv (use_env=True)")
+        self.sched = sched
+        env = sched.env.rpc_env
+        env.setup_endpoint(_DriverEndpoint.NAME, _DriverEndpoint(self))
+        self.master = env.endpoint_ref(self.master_address, "Master")
+        me = env.endpoint_ref(None, _DriverEndpoint.NAME)
+        self.app_id, granted = self.master.ask_sync(
+            ("register_app", self.app_name, self.num_executors, self.cores_per_executor, self.memory_mb, me, str(env.address)), 30)
+        self.num_executors = granted
+        sched.num_executors = granted
+        deadline = time.time() + self.register_timeout
+        with self.cv:                       # spark.scheduler.minRegisteredResourcesRatio = 1.0: wait for every slot
+            while len(self.refs) < granted:
+                left = deadline - time.time()
+                if left <= 0 or self.app_state != "RUNNING":
+                    raise RuntimeError(f"only {len(self.refs)} of {granted} executors registered with the driver within "
+                                       f"{self.register_timeout:.0f} s (master {self.master_address}, app {self.app_id}, "
+                                       f"state {self.app_state}) — are enough workers with free cores alive?")
+                self.cv.wait(min(left, 0.5))
+
+    def send(self, eid: int, msg: tuple) -> None:
+        ref = self.refs.get(eid)
+        if ref is None:
+            raise OSError(f"executor slot {eid} is down")
+        ref.send(msg)
+
+    def _slot_down(self, slot: int, exec_id, why: str) -> None:
+        with self.cv:
+            if self.exec_ids.get(slot) != exec_id or slot not in self.refs:
+                return                                   # already handled (both the disconnect and the master report arrive)
+            del self.refs[slot]
+            self.addresses.pop(slot, None)
+        if self.sched is not None and not self.sched._stopped:
+            # off the inbox thread: recovery waits for the replacement's RegisterExecutor, which this inbox must serve
+            threading.Thread(target=self.sched._executor_lost, args=(slot,), daemon=True,
+                             name=f"executor-lost-{slot}").start()
+
+    def relaunch(self, eid: int) -> bool:
+        """The Master re-fills the slot on its own; wait for the replacement to register."""
+        deadline = time.time() + self.register_timeout
+        with self.cv:
+            while eid not in self.refs:
+                left = deadline - time.time()
+                if left <= 0 or self.app_state != "RUNNING" or self.sched._stopped:
+                    return False
+                self.cv.wait(min(left, 0.5))
+        return True
+
+    def _app_failed(self) -> None:
+        with self.cv:
+            self.cv.notify_all()
+
+    def kill(self, eid: int) -> None:
+        """Fault injection: SIGKILL the executor process of a slot (same host) or ask the master to do it."""
+        host, pid = self.pids.get(eid, (None, None))
+        if pid is not None and host in ("127.0.0.1", "localhost"):
+            try:
+                os.kill(pid, signal.SIGKILL)
+                return
+            except ProcessLookupError:
+                pass
+        self.master.ask_sync(("kill_executor", self.app_id, eid), 10)
+
+    def stop(self) -> None:
+        # unregister FIRST: an executor that exits because of "stop" while the application is still registered would look
+        # like a lost executor to the Master and be re-launched
+        try:
+            if self.master is not None and self.app_id is not None:
+                self.master.send(("unregister_app", self.app_id))
+        except RpcError:
+            pass
+        for ref in list(self.refs.values()):
+            try:
+                ref.send(("stop",))
+            except (RpcError, OSError):
+                pass
+        time.sleep(0.05)                     # let the one-way messages leave before the env closes its sockets
+
+
+class LocalStandaloneCluster:
+    """Master + ``num_workers`` Workers in this process, real executor processes, real TCP."""
+
+    def __init__(self, num_workers: int = 2, cores_per_worker: int = 1, memory_per_worker: int = 1024,
+                 worker_timeout: float = 60.0, heartbeat_interval: float = 1.0, secret: Optional[str] = None):
+        self.master_env, self.master = start_master("127.0.0.1", 0, worker_timeout, secret)
+        self.master_url = f"spark://{self.master_env.address}"
+        self.worker_envs, self.workers = [], []
+        for i in range(num_workers):
+            e, w = start_worker(self.master_url, cores_per_worker, memory_per_worker, heartbeat_interval=heartbeat_interval,
+                                secret=secret, worker_id=f"worker-{i}")
+            self.worker_envs.append(e)
+            self.workers.append(w)
+
+    def add_worker(self, cores: int = 1, memory_mb: int = 1024, **kw):
+        e, w = start_worker(self.master_url, cores, memory_mb, worker_id=f"worker-{len(self.workers)}", **kw)
+        self.worker_envs.append(e)
+        self.workers.append(w)
+        return w
+
+    def stop_worker(self, i: int) -> None:
+        self.worker_envs[i].shutdown()
+
+    def state(self) -> dict:
+        return self.master_env.endpoint_ref(None, "Master").ask_sync(("state",), 10)
+
+    def stop(self) -> None:
+        for e in self.worker_envs:
+            e.shutdown()
+        self.master_env.shutdown()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.stop()

@@ -1,0 +1,310 @@
+"""Standalone cluster manager — the Master daemon.
+
+Reference: ``Master`` (core/deploy/master/Master.scala:41): workers register and heartbeat; applications register
+with a resource request; the master places executors on workers (``schedule`` / ``startExecutorsOnWorkers``,
+spread-out by default), tells the worker to ``LaunchExecutor``, relays ``ExecutorStateChanged`` to the
+application's driver, re-launches executors that exit abnormally (bounded by ``MAX_EXECUTOR_RETRIES``), times out
+silent workers (``spark.worker.timeout`` = 60 s, ``CheckForWorkerTimeOut``) and cleans up when a driver
+disconnects.  README.md:56 runs the paper's experiments on such a 1-master + 8-worker standalone cluster.
+
+Run it: ``python -m asyncframework_b200.deploy.master --host 0.0.0.0 --port 7077``; applications connect with the
+master URL ``spark://host:7077`` (``async://`` is accepted as an alias).
+
+Executors have a *slot* (0..n-1): the driver binds partition p to slot p % n (hard shard↔worker affinity, SURVEY
+S4), so when an executor dies the master re-fills the SAME slot and the driver re-ships that slot's data.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+from ..rpc import RpcAddress, RpcCallContext, RpcEndpoint, RpcEndpointRef, RpcEnv, RpcError
+
+MAX_EXECUTOR_RETRIES = 10
+
+
+@dataclass
+class WorkerInfo:
+    id: str
+    host: str
+    port: int
+    cores: int
+    memory_mb: int
+    ref: RpcEndpointRef
+    cores_used: int = 0
+    memory_used: int = 0
+    last_heartbeat: float = field(default_factory=time.time)
+    state: str = "ALIVE"                      # ALIVE | DEAD
+    executors: Dict[str, int] = field(default_factory=dict)       # "app/exec" -> cores
+
+
+@dataclass
+class ExecutorDesc:
+    exec_id: int
+    slot: int
+    worker_id: str
+    cores: int
+    memory_mb: int
+    state: str = "LAUNCHING"                  # LAUNCHING | RUNNING | EXITED | KILLED | FAILED | LOST
+
+
+@dataclass
+class AppInfo:
+    id: str
+    name: str
+    driver: RpcEndpointRef
+    driver_url: str
+    num_executors: int
+    cores_per_executor: int
+    memory_per_executor: int
+    submit_time: float = field(default_factory=time.time)
+    state: str = "RUNNING"                    # RUNNING | FINISHED | FAILED
+    executors: Dict[int, ExecutorDesc] = field(default_factory=dict)
+    retries: int = 0
+    next_exec_id: int = 0
+
+
+class Master(RpcEndpoint):
+    NAME = "Master"
+
+    def __init__(self, worker_timeout: float = 60.0, spread_out: bool = True):
+        self.worker_timeout = worker_timeout
+        self.spread_out = spread_out
+        self.workers: Dict[str, WorkerInfo] = {}
+        self.apps: Dict[str, AppInfo] = {}
+        self.completed_apps: List[AppInfo] = []
+        self._app_ids = itertools.count(0)
+        self._stop = threading.Event()
+        self.start_time = time.time()
+
+    # ------------------------------------------------------------------ lifecycle
+    def on_start(self) -> None:
+        threading.Thread(target=self._timeout_loop, daemon=True, name="master-worker-timeout").start()
+
+    def on_stop(self) -> None:
+        self._stop.set()
+
+    def _timeout_loop(self) -> None:
+        while not self._stop.wait(max(0.05, self.worker_timeout / 4)):
+            try:
+                self.self_ref.send(("check_worker_timeouts",))
+            except RpcError:
+                return
+
+    # ------------------------------------------------------------------ messages
+    def receive(self, msg, sender: Optional[RpcAddress]) -> None:
+        op = msg[0]
+        if op == "heartbeat":
+            w = self.workers.get(msg[1])
+            if w is not None and w.state == "ALIVE":
+                w.last_heartbeat = time.time()
+            elif sender is not None:                     # a worker we forgot (master restart / expiry): ask it to re-register
+                try:
+                    self.rpc_env.endpoint_ref(sender, "Worker").send(("reconnect",))
+                except RpcError:
+                    pass
+        elif op == "check_worker_timeouts":
+            now = time.time()
+            for w in [w for w in self.workers.values() if w.state == "ALIVE" and now - w.last_heartbeat > self.worker_timeout]:
+                self._remove_worker(w, f"no heartbeat in {self.worker_timeout:.0f} s")
+        elif op == "executor_state_changed":
+            _, app_id, exec_id, state, message, exit_code = msg
+            self._executor_state_changed(app_id, exec_id, state, message, exit_code)
+        elif op == "unregister_app":
+            self._finish_app(msg[1], "FINISHED")
+        else:
+            raise RpcError(f"Master: unknown one-way message {op!r}")
+
+    def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
+        op = msg[0]
+        if op == "register_worker":
+            _, wid, host, port, cores, memory_mb, ref = msg
+            old = self.workers.get(wid)
+            if old is not None and old.state == "ALIVE":
+                ctx.reply(("failed", f"duplicate worker id {wid}"))
+                return
+            self.workers[wid] = WorkerInfo(wid, host, port, int(cores), int(memory_mb), ref)
+            ctx.reply(("registered", str(self.rpc_env.address)))
+            self._schedule()
+        elif op == "register_app":
+            _, name, num_executors, cores_per_executor, memory_mb, driver_ref, driver_url = msg
+            app_id = f"app-{time.strftime('%Y%m%d%H%M%S')}-{next(self._app_ids):04d}"
+            if num_executors is None:                   # default: one executor on every alive worker
+                num_executors = max(1, sum(1 for w in self.workers.values() if w.state == "ALIVE"))
+            self.apps[app_id] = AppInfo(app_id, name, driver_ref, driver_url, int(num_executors),
+                                        int(cores_per_executor), int(memory_mb))
+            ctx.reply((app_id, int(num_executors)))
+            self._schedule()
+        elif op == "state":
+            ctx.reply(self.state())
+        elif op == "kill_executor":                      # administrative / fault injection
+            _, app_id, slot = msg
+            app = self.apps.get(app_id)
+            done = False
+            if app is not None:
+                for ex in app.executors.values():
+                    if ex.slot == slot and ex.state in ("LAUNCHING", "RUNNING"):
+                        w = self.workers.get(ex.worker_id)
+                        if w is not None:
+                            w.ref.send(("kill_executor", app_id, ex.exec_id, True))
+                            done = True
+            ctx.reply(done)
+        else:
+            ctx.send_failure(RpcError(f"Master: unknown request {op!r}"))
+
+    def on_disconnected(self, address: RpcAddress) -> None:
+        for w in [w for w in self.workers.values() if w.state == "ALIVE" and (w.host, w.port) == (address.host, address.port)]:
+            self._remove_worker(w, "connection lost")
+        for app in [a for a in self.apps.values() if a.driver.address == address]:
+            self._finish_app(app.id, "FINISHED")       # a driver that goes away ends its application
+
+    # ------------------------------------------------------------------ scheduling
+    def _schedule(self) -> None:
+        """Fill every empty slot of every running app: spread-out = the alive worker with the most free cores first
+        (``spark.deploy.spreadOut``), consolidate = pack the first worker that fits."""
+        for app in sorted(self.apps.values(), key=lambda a: a.submit_time):          # FIFO across applications
+            if app.state != "RUNNING":
+                continue
+            filled = {ex.slot for ex in app.executors.values() if ex.state in ("LAUNCHING", "RUNNING")}
+            for slot in range(app.num_executors):
+                if slot in filled:
+                    continue
+                usable = [w for w in self.workers.values() if w.state == "ALIVE"
+                          and w.cores - w.cores_used >= app.cores_per_executor
+                          and w.memory_mb - w.memory_used >= app.memory_per_executor]
+                if not usable:
+                    break
+                if self.spread_out:
+                    on_worker = {w.id: sum(1 for ex in app.executors.values()
+                                           if ex.worker_id == w.id and ex.state in ("LAUNCHING", "RUNNING")) for w in usable}
+                    w = min(usable, key=lambda w: (on_worker[w.id], -(w.cores - w.cores_used), w.id))
+                else:
+                    w = sorted(usable, key=lambda w: w.id)[0]
+                self._launch(app, slot, w)
+
+    def _launch(self, app: AppInfo, slot: int, w: WorkerInfo) -> None:
+        exec_id = app.next_exec_id
+        app.next_exec_id += 1
+        ex = ExecutorDesc(exec_id, slot, w.id, app.cores_per_executor, app.memory_per_executor)
+        app.executors[exec_id] = ex
+        w.cores_used += ex.cores
+        w.memory_used += ex.memory_mb
+        w.executors[f"{app.id}/{exec_id}"] = ex.cores
+        try:
+            w.ref.send(("launch_executor", app.id, exec_id, slot, app.driver_url, ex.cores, ex.memory_mb))
+            app.driver.send(("executor_added", exec_id, slot, w.id, f"{w.host}:{w.port}", ex.cores))
+        except RpcError as exc:
+            self._executor_state_changed(app.id, exec_id, "FAILED", f"cannot reach worker {w.id}: {exc}", None)
+
+    def _release(self, app: AppInfo, ex: ExecutorDesc) -> None:
+        w = self.workers.get(ex.worker_id)
+        if w is not None and w.executors.pop(f"{app.id}/{ex.exec_id}", None) is not None:
+            w.cores_used -= ex.cores
+            w.memory_used -= ex.memory_mb
+
+    def _executor_state_changed(self, app_id: str, exec_id: int, state: str, message: str, exit_code) -> None:
+        app = self.apps.get(app_id)
+        if app is None:
+            return
+        ex = app.executors.get(exec_id)
+        if ex is None:
+            return
+        old, ex.state = ex.state, state
+        if state == "RUNNING":
+            app.retries = 0
+        try:
+            app.driver.send(("executor_updated", exec_id, ex.slot, state, message, exit_code))
+        except RpcError:
+            pass
+        if state in ("EXITED", "KILLED", "FAILED", "LOST") and old not in ("EXITED", "KILLED", "FAILED", "LOST"):
+            self._release(app, ex)
+            normal = (state == "EXITED" and exit_code == 0) or (state == "KILLED" and message == "app finished")
+            if app.state == "RUNNING" and not normal:
+                app.retries += 1
+                if app.retries >= MAX_EXECUTOR_RETRIES and not any(e.state == "RUNNING" for e in app.executors.values()):
+                    self._finish_app(app.id, "FAILED")        # Master.scala: "Application ... failed N times; removing it"
+                    return
+            self._schedule()
+
+    def _remove_worker(self, w: WorkerInfo, reason: str) -> None:
+        w.state = "DEAD"
+        for key in list(w.executors):
+            app_id, exec_id = key.rsplit("/", 1)
+            self._executor_state_changed(app_id, int(exec_id), "LOST", f"worker {w.id} lost: {reason}", None)
+        self.workers.pop(w.id, None)
+        self._schedule()
+
+    def _finish_app(self, app_id: str, state: str) -> None:
+        app = self.apps.pop(app_id, None)
+        if app is None:
+            return
+        app.state = state
+        for ex in app.executors.values():
+            if ex.state in ("LAUNCHING", "RUNNING"):
+                w = self.workers.get(ex.worker_id)
+                if w is not None:
+                    try:
+                        w.ref.send(("kill_executor", app_id, ex.exec_id, False))
+                    except RpcError:
+                        pass
+                self._release(app, ex)
+                ex.state = "KILLED"
+        try:
+            app.driver.send(("application_removed", state))
+        except RpcError:
+            pass
+        self.completed_apps.append(app)
+        del self.completed_apps[:-50]
+        self._schedule()
+
+    # ------------------------------------------------------------------ status (MasterWebUI /json)
+    def state(self) -> dict:
+        def app_d(a: AppInfo) -> dict:
+            return {"id": a.id, "name": a.name, "state": a.state, "submit_time": a.submit_time,
+                    "num_executors": a.num_executors, "cores_per_executor": a.cores_per_executor,
+                    "executors": [{"id": e.exec_id, "slot": e.slot, "worker": e.worker_id, "state": e.state, "cores": e.cores}
+                                  for e in a.executors.values()]}
+        return {"url": f"spark://{self.rpc_env.address}", "status": "ALIVE", "uptime_s": time.time() - self.start_time,
+                "workers": [{"id": w.id, "host": w.host, "port": w.port, "cores": w.cores, "cores_used": w.cores_used,
+                             "memory_mb": w.memory_mb, "memory_used": w.memory_used, "state": w.state,
+                             "last_heartbeat": w.last_heartbeat, "executors": sorted(w.executors)}
+                            for w in self.workers.values()],
+                "active_apps": [app_d(a) for a in self.apps.values()],
+                "completed_apps": [app_d(a) for a in self.completed_apps]}
+
+
+def start_master(host: str = "127.0.0.1", port: int = 7077, worker_timeout: float = 60.0, secret: Optional[str] = None,
+                 spread_out: bool = True):
+    """Returns ``(rpc_env, master_endpoint)``; the URL is ``spark://<rpc_env.address>``."""
+    env = RpcEnv("master", host, port, secret=secret)
+    master = Master(worker_timeout, spread_out)
+    env.setup_endpoint(Master.NAME, master)
+    return env, master
+
+
+def main(argv=None) -> None:
+    ap = argparse.ArgumentParser(description="asyncframework_b200 standalone master")
+    ap.add_argument("--host", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=7077)
+    ap.add_argument("--webui-port", type=int, default=0, help="serve the JSON status page on this port (0 = off)")
+    ap.add_argument("--worker-timeout", type=float, default=60.0)
+    ap.add_argument("--secret", default=None)
+    a = ap.parse_args(argv)
+    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret)
+    print(f"Master started at spark://{env.address}", flush=True)
+    if a.webui_port:
+        from ..utils.status_server import serve_json
+        serve_json(a.host, a.webui_port, {"/json": master.state, "/": master.state})
+    try:
+        while True:
+            time.sleep(3600)
+    except KeyboardInterrupt:
+        env.shutdown()
+
+
+if __name__ == "__main__":
+    main()

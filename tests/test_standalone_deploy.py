@@ -1,0 +1,102 @@
+"""Standalone deployment: Master + Workers + forked executor processes over TCP (``spark://host:port``).
+Mirrors the reference's MasterSuite / WorkerSuite / StandaloneDynamicAllocation-less parts of DistributedSuite
+(core/src/test/scala/org/apache/spark/deploy/{master,worker}) at the behaviour level."""
+import os
+import time
+
+import pytest
+import torch
+
+from asyncframework_b200 import AsyncSession
+from asyncframework_b200.deploy import LocalStandaloneCluster
+from asyncframework_b200.rpc import RpcEnv
+
+
+def _wait(pred, timeout=30.0, step=0.05):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if pred():
+            return True
+        time.sleep(step)
+    return False
+
+
+@pytest.fixture(scope="module")
+def cluster():
+    with LocalStandaloneCluster(num_workers=2, cores_per_worker=2, memory_per_worker=2048, heartbeat_interval=0.5) as c:
+        yield c
+
+
+def test_workers_register_and_master_reports_state(cluster):
+    st = cluster.state()
+    assert st["status"] == "ALIVE" and st["url"] == cluster.master_url
+    assert sorted(w["id"] for w in st["workers"]) == ["worker-0", "worker-1"]
+    assert all(w["state"] == "ALIVE" and w["cores"] == 2 and w["cores_used"] == 0 for w in st["workers"])
+    assert st["active_apps"] == []
+
+
+def test_application_runs_closures_broadcasts_and_async_reduce_on_remote_executors(cluster):
+    with AsyncSession(cluster.master_url, app_name="it") as sc:
+        assert sc.scheduler.num_executors == 2                                # one executor per alive worker by default
+        st = cluster.state()
+        (app,) = st["active_apps"]
+        assert app["name"] == "it" and sorted(e["slot"] for e in app["executors"] if e["state"] == "RUNNING") == [0, 1]
+        assert sorted(e["worker"] for e in app["executors"]) == ["worker-0", "worker-1"]      # spread out
+        assert all(w["cores_used"] == 1 for w in st["workers"])
+        ds = sc.parallelize(range(100), 4)
+        pids = set(ds.map(lambda x: os.getpid()).collect())
+        assert len(pids) == 2 and os.getpid() not in pids
+        w = torch.arange(300_000, dtype=torch.float64)                           # 2.4 MB: piece-wise torrent broadcast
+        bc = sc.broadcast(w)
+        assert ds.map(lambda i: float(bc.value[i] * 2)).reduce(lambda a, b: a + b) == float(sum(2 * i for i in range(100)))
+        # the ASYNC actions work unchanged over the network transport
+        ctx = sc.async_context(4)
+        ds.map(lambda x: x * x).async_reduce(lambda a, b: a + b, ctx)
+        got = sorted(ctx.collect() for _ in range(4))
+        assert sum(got) == sum(x * x for x in range(100)) and ctx.current_time == 4
+        big = ds.map_partitions(lambda it: [torch.zeros(400_000)]).collect()     # 1.6 MB results: indirect path
+        assert len(big) == 4 and sc.scheduler.indirect_results == 4
+    assert _wait(lambda: cluster.state()["active_apps"] == [])
+    st = cluster.state()
+    assert st["completed_apps"][-1]["state"] == "FINISHED"
+    assert _wait(lambda: all(w["cores_used"] == 0 for w in cluster.state()["workers"]))
+
+
+def test_killed_executor_is_relaunched_by_the_master_and_tasks_are_resubmitted(cluster):
+    with AsyncSession(cluster.master_url, app_name="ft") as sc:
+        s = sc.scheduler
+        ds = sc.parallelize(range(20), 4)
+        assert ds.count() == 20
+
+        def slow(tctx, it):
+            time.sleep(1.5)
+            return sum(it)
+        res = {}
+        w = s.submit_job(ds, slow, result_handler=res.__setitem__)
+        time.sleep(0.4)
+        s.kill_executor(1)
+        assert w.wait(90)
+        assert res == {p: sum(range(5 * p, 5 * p + 5)) for p in range(4)}
+        assert s.executors_recovered == 1
+        app = cluster.state()["active_apps"][0]
+        assert sorted(e["state"] for e in app["executors"]) == ["EXITED", "RUNNING", "RUNNING"]
+        assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 210
+
+
+def test_master_times_out_a_silent_worker_and_rejects_a_wrong_secret():
+    with LocalStandaloneCluster(num_workers=1, worker_timeout=1.0, heartbeat_interval=0.2, secret="k") as c:
+        assert len(c.state()["workers"]) == 1
+        c.workers[0]._stop.set()                                  # stops heartbeating but keeps the connection
+        assert _wait(lambda: len(c.state()["workers"]) == 0, 10)
+        intruder = RpcEnv("x", server=False, secret="not-k")
+        with pytest.raises(Exception, match="authentication"):
+            intruder.endpoint_ref(c.master_env.address, "Master").ask_sync(("state",), 3)
+        intruder.shutdown()
+
+
+def test_application_waits_for_resources_and_fails_clearly_when_none_come():
+    with LocalStandaloneCluster(num_workers=0) as c:
+        with pytest.raises(RuntimeError, match="executors registered"):
+            from asyncframework_b200.core.cluster import ClusterScheduler
+            from asyncframework_b200.deploy import StandaloneTransport
+            ClusterScheduler(1, transport=StandaloneTransport(c.master_url, 1, register_timeout=1.5))
