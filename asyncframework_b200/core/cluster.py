@@ -110,8 +110,11 @@ class ExecutorBackend:
                 if fault is not None:
                     fault(tctx)
                 result = func(tctx, dataset.iterator(partition, tctx))
+                t1 = time.perf_counter()
                 data = cloudpickle.dumps((result, _acc.end_task(True)))      # accumulator updates ride with the result
-                run_ms = (time.perf_counter() - t0) * 1e3
+                t2 = time.perf_counter()
+                # TaskMetrics (executor/TaskMetrics.scala): executorRunTime, resultSerializationTime
+                run_ms = {"run_ms": (t1 - t0) * 1e3, "serialize_ms": (t2 - t1) * 1e3}
                 self.tasks_run += 1
                 env = AsyncEnv.get()
                 if env is not None and len(data) > env.limits.max_direct_result_size:
@@ -300,9 +303,18 @@ class ClusterScheduler:
             job["on_task_lost"](partition, exc)
         job["waiter"].job_failed(exc)
         job["pending"].discard(partition)
+        if not job.get("failed_posted"):
+            job["failed_posted"] = True
+            self.listeners.post({"event": "job_end", "job": job["waiter"].job_id, "failed": True, "error": str(exc)[:300],
+                                 "t_ms": time.perf_counter() * 1e3})
 
-    def _task_succeeded(self, eid: int, job_id: int, job: dict, partition: int, data: bytes, run_ms: float, nbytes: int) -> None:
+    def _task_succeeded(self, eid: int, job_id: int, job: dict, partition: int, data: bytes, run_ms, nbytes: int,
+                        extra: Optional[dict] = None) -> None:
         waiter: JobWaiter = job["waiter"]
+        metrics = dict(run_ms) if isinstance(run_ms, dict) else {"run_ms": float(run_ms)}
+        metrics.update(extra or {})
+        metrics["result_bytes"] = nbytes
+        run_ms = metrics.pop("run_ms")
         limit = self.env.limits.max_result_size if self.env is not None else 0
         with self._lock:
             job["result_bytes"] += nbytes
@@ -313,10 +325,17 @@ class ClusterScheduler:
             self.failed_jobs.append(job_id)
             self._fail_task(job, partition, exc)
             return
-        self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
-                             "run_ms": run_ms, "metrics": {"result_bytes": nbytes}})
+        t0 = time.perf_counter()
         try:
-            result, acc_updates = pickle.loads(data)
+            decoded = pickle.loads(data)
+        except Exception as exc:  # noqa: BLE001
+            self._fail_task(job, partition, RuntimeError(f"cannot deserialize the result of task {partition}: {exc!r}"))
+            return
+        metrics["deserialize_ms"] = (time.perf_counter() - t0) * 1e3           # TaskMetrics.resultDeserializationTime (driver side)
+        self.listeners.post({"event": "task_end", "job": job_id, "partition": partition, "executor": eid,
+                             "run_ms": run_ms, "metrics": metrics})
+        try:
+            result, acc_updates = decoded
             if not waiter.cancelled:
                 _acc.merge_updates(acc_updates)
             waiter.task_succeeded(partition, result)
@@ -337,13 +356,15 @@ class ClusterScheduler:
             self._fail_task(job, partition, RuntimeError(
                 f"result of task {partition} of job {job_id} ({size} bytes) is bigger than max_result_size ({limit} bytes)"))
             return
+        t0 = time.perf_counter()
         data = self.env.block_manager.get_remote_bytes(block_id, [BlockManagerId(*holder)])
+        fetch_ms = (time.perf_counter() - t0) * 1e3
         self._drop_result_block(block_id)
         if data is None:                               # the executor died between the status message and the fetch
             self._fail_task(job, partition, RuntimeError(f"lost the result block {block_id} of job {job_id}"))
             return
         self.indirect_results += 1
-        self._task_succeeded(eid, job_id, job, partition, data, run_ms, size)
+        self._task_succeeded(eid, job_id, job, partition, data, run_ms, size, {"fetch_wait_ms": fetch_ms, "indirect": 1})
 
     def _drop_result_block(self, block_id: str) -> None:
         try:

@@ -210,7 +210,11 @@ class Scheduler:
                                  "attempt": task.attempt, "error": repr(exc)})
             if task.attempt >= self.max_failures:
                 self.failed_jobs.append(job.job_id)
+                first_failure = job.failure is None
                 job.job_failed(exc)
+                if first_failure:
+                    self.listeners.post({"event": "job_end", "job": job.job_id, "failed": True, "error": repr(exc)[:300],
+                                         "t_ms": time.perf_counter() * 1e3})
                 on_fail = getattr(job, "on_task_lost", None)
                 if on_fail is not None:
                     on_fail(task.partition, exc)

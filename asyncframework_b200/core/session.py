@@ -111,7 +111,10 @@ class AsyncSession:
         return Accumulator(zero, name, op)
 
     def async_context(self, num_workers: Optional[int] = None) -> AsyncContext:
-        return AsyncContext(num_workers or self.default_parallelism, self.scheduler)
+        ctx = AsyncContext(num_workers or self.default_parallelism, self.scheduler)
+        if getattr(self, "status_store", None) is not None:
+            self.status_store.watch_context(ctx)
+        return ctx
 
     def async_broadcast(self, ctx: AsyncContext, value: Any, slots: int = 8) -> AsyncBroadcast:
         return AsyncBroadcast(ctx, value, slots)
@@ -131,8 +134,35 @@ class AsyncSession:
     def add_listener(self, fn) -> None:
         self.scheduler.listeners.add(fn)
 
+    # ---- observability (web UI / REST / metrics) ---------------------------------------------------------
+    def start_ui(self, host: str = "127.0.0.1", port: int = 0, event_log: Optional[str] = None):
+        """Attach the status store + metrics registry to the scheduler's listener bus and serve them over HTTP
+        (``spark.ui.port``; REST under ``/api/v1/applications``, ``/metrics/json``, ``/metrics/prometheus``).  ``event_log``
+        additionally appends every event to a JSONL file the :class:`HistoryServer` can replay (``spark.eventLog.enabled``)."""
+        from ..utils.metrics import MetricsRegistry, SchedulerSource
+        from ..utils.status import AppStatusStore
+        from ..utils.status_server import StatusServer
+        if getattr(self, "ui", None) is not None:
+            return self.ui
+        app_id = getattr(getattr(self.scheduler, "transport", None), "app_id", None)
+        self.status_store = AppStatusStore(self.app_name, app_id).attach(
+            self.scheduler, {"master": self.master, "app_name": self.app_name, "conf": self.conf.to_dict(),
+                             "num_executors": self.scheduler.num_executors})
+        self.metrics = MetricsRegistry()
+        SchedulerSource(self.metrics, self.scheduler)
+        if event_log:
+            from ..utils.eventlog import EventLog
+            self._event_log = EventLog(event_log).attach(self.scheduler)
+        self.ui = StatusServer(self.status_store, self.metrics, host, port)
+        return self.ui
+
     def stop(self) -> None:
         if not self._stopped:
+            if getattr(self, "ui", None) is not None:
+                self.status_store.stop()
+                self.ui.stop()
+            if getattr(self, "_event_log", None) is not None:
+                self._event_log.close()
             self.scheduler.stop()
             self._stopped = True
 

@@ -298,7 +298,8 @@ def main(argv=None) -> None:
     print(f"Master started at spark://{env.address}", flush=True)
     if a.webui_port:
         from ..utils.status_server import serve_json
-        serve_json(a.host, a.webui_port, {"/json": master.state, "/": master.state})
+        state = lambda: master.self_ref.ask_sync(("state",), 10)  # noqa: E731  (through the inbox: no torn reads)
+        serve_json(a.host, a.webui_port, {"/json": state, "/": state})
     try:
         while True:
             time.sleep(3600)

@@ -58,6 +58,10 @@ def replay(path: str) -> Dict[int, dict]:
             elif kind == "job_end":
                 j["t_end"] = ev.get("t_ms")
                 j["finished"] = True
+                if ev.get("failed"):
+                    j["failed"] = True
+                if ev.get("cancelled"):
+                    j["cancelled"] = True
     out = {}
     for jid, j in jobs.items():
         j["executors"] = sorted(e for e in j["executors"] if e is not None)

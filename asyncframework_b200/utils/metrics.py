@@ -102,6 +102,160 @@ class JsonlSink(Sink):
             f.write(json.dumps({"t": ts, **snap}) + "\n")
 
 
+def _prom_name(name: str) -> str:
+    import re
+    n = re.sub(r"[^a-zA-Z0-9_:]", "_", name)
+    return n if not n[0].isdigit() else "_" + n
+
+
+def prometheus_text(snap: Dict[str, float], prefix: str = "afb_") -> str:
+    """Prometheus text exposition format 0.0.4 of a snapshot (PrometheusServlet's role; every value is a gauge)."""
+    lines = []
+    for k in sorted(snap):
+        n = prefix + _prom_name(k)
+        lines.append(f"# TYPE {n} gauge")
+        lines.append(f"{n} {float(snap[k]):.10g}")
+    return "\n".join(lines) + "\n"
+
+
+class PrometheusFileSink(Sink):
+    """Writes the exposition text atomically to a file (node-exporter textfile collector style)."""
+
+    def __init__(self, path: str, prefix: str = "afb_"):
+        self.path, self.prefix = path, prefix
+
+    def write(self, ts, snap):
+        tmp = self.path + ".tmp"
+        with open(tmp, "w") as f:
+            f.write(prometheus_text(snap, self.prefix))
+        os.replace(tmp, self.path)
+
+
+class StatsdSink(Sink):
+    """``StatsdSink`` (core/metrics/sink/StatsdSink.scala): one UDP datagram per batch of ``name:value|g`` lines."""
+
+    def __init__(self, host: str = "127.0.0.1", port: int = 8125, prefix: str = "afb", max_datagram: int = 1400):
+        import socket
+        self.addr, self.prefix, self.max_datagram = (host, port), prefix, max_datagram
+        self.sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+
+    def write(self, ts, snap):
+        batch, size = [], 0
+        for k in sorted(snap):
+            line = f"{self.prefix}.{k}:{float(snap[k]):.10g}|g"
+            if size + len(line) + 1 > self.max_datagram and batch:
+                self.sock.sendto("\n".join(batch).encode(), self.addr)
+                batch, size = [], 0
+            batch.append(line)
+            size += len(line) + 1
+        if batch:
+            self.sock.sendto("\n".join(batch).encode(), self.addr)
+
+
+class GraphiteSink(Sink):
+    """``GraphiteSink`` (core/metrics/sink/GraphiteSink.scala): plaintext protocol ``<path> <value> <unix ts>\\n`` over TCP;
+    reconnects on every report so a restarted carbon daemon does not wedge the reporter."""
+
+    def __init__(self, host: str, port: int = 2003, prefix: str = "afb", timeout: float = 2.0):
+        self.addr, self.prefix, self.timeout = (host, port), prefix, timeout
+        self.errors = 0
+
+    def write(self, ts, snap):
+        import socket
+        payload = "".join(f"{self.prefix}.{k} {float(snap[k]):.10g} {int(ts)}\n" for k in sorted(snap)).encode()
+        try:
+            with socket.create_connection(self.addr, timeout=self.timeout) as s:
+                s.sendall(payload)
+        except OSError:
+            self.errors += 1                # a metrics sink must never take the job down
+
+
+class Slf4jSink(Sink):
+    """``Slf4jSink``: the snapshot goes through the framework logger at INFO."""
+
+    def __init__(self, logger_name: str = "asyncframework_b200.metrics"):
+        import logging
+        self.log = logging.getLogger(logger_name)
+
+    def write(self, ts, snap):
+        for k in sorted(snap):
+            self.log.info("type=GAUGE, name=%s, value=%.10g", k, snap[k])
+
+
+_SINK_CLASSES = {"console": ConsoleSink, "csv": CsvSink, "jsonl": JsonlSink, "prometheus": PrometheusFileSink,
+                 "statsd": StatsdSink, "graphite": GraphiteSink, "slf4j": Slf4jSink}
+
+
+class MetricsSystem:
+    """Registry + sinks + a periodic reporter thread, configurable from ``metrics.properties``-style keys
+    (core/metrics/MetricsSystem.scala:97-190, MetricsConfig): ``*.sink.<name>.class`` picks the sink,
+    ``*.sink.<name>.<option>`` are its constructor arguments, ``*.sink.<name>.period`` (seconds) the report period —
+    one reporter thread at the smallest period drives all sinks."""
+
+    def __init__(self, registry: Optional[MetricsRegistry] = None):
+        self.registry = registry or MetricsRegistry()
+        self.period = 10.0
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+
+    @classmethod
+    def from_properties(cls, props: Dict[str, str], registry: Optional[MetricsRegistry] = None) -> "MetricsSystem":
+        ms = cls(registry)
+        sinks: Dict[str, Dict[str, str]] = {}
+        for key, val in props.items():
+            parts = key.split(".")
+            if len(parts) >= 4 and parts[1] == "sink":          # <instance>.sink.<name>.<option>
+                sinks.setdefault(parts[2], {})[".".join(parts[3:])] = val
+        periods = []
+        for name, opts in sinks.items():
+            kind = opts.pop("class", name).rsplit(".", 1)[-1].lower().replace("sink", "")
+            if kind not in _SINK_CLASSES:
+                raise ValueError(f"unknown metrics sink {kind!r} (have: {sorted(_SINK_CLASSES)})")
+            if "period" in opts:
+                periods.append(float(opts.pop("period")))
+            opts.pop("unit", None)
+            kwargs = {k: (int(v) if k in ("port", "max_datagram") else v) for k, v in opts.items()}
+            ms.registry.add_sink(_SINK_CLASSES[kind](**kwargs))
+        if periods:
+            ms.period = min(periods)
+        return ms
+
+    @staticmethod
+    def load_properties(path: str) -> Dict[str, str]:
+        out = {}
+        with open(path) as f:
+            for line in f:
+                line = line.strip()
+                if line and not line.startswith("#") and "=" in line:
+                    k, v = line.split("=", 1)
+                    out[k.strip()] = v.strip()
+        return out
+
+    def start(self, period: Optional[float] = None) -> "MetricsSystem":
+        if period is not None:
+            self.period = period
+        if self._thread is None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._loop, daemon=True, name="metrics-reporter")
+            self._thread.start()
+        return self
+
+    def _loop(self) -> None:
+        while not self._stop.wait(self.period):
+            try:
+                self.registry.report()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def stop(self, final_report: bool = True) -> None:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+            self._thread = None
+        if final_report:
+            self.registry.report()
+
+
 class SchedulerSource:
     """DAGSchedulerSource/ExecutorSource analogue: counts jobs/tasks/failures and task run time."""
 
@@ -116,5 +270,16 @@ class SchedulerSource:
         elif kind == "task_end":
             self.r.inc(self.prefix + ".tasks")
             self.r.observe(self.prefix + ".task_run_ms", ev.get("run_ms", 0.0))
+            m = ev.get("metrics") or {}
+            for k in ("result_bytes",):
+                if k in m:
+                    self.r.inc(self.prefix + "." + k, float(m[k]))
+            for k in ("deserialize_ms", "serialize_ms", "fetch_wait_ms"):
+                if k in m:
+                    self.r.observe(self.prefix + ".task_" + k, float(m[k]))
         elif kind == "task_failed":
             self.r.inc(self.prefix + ".task_failures")
+        elif kind == "executor_lost":
+            self.r.inc(self.prefix + ".executors_lost")
+        elif kind == "task_resubmitted":
+            self.r.inc(self.prefix + ".tasks_resubmitted")
