@@ -263,7 +263,11 @@ class ClusterScheduler:
             from .env import AsyncEnv, RuntimeLimits
             self.env = AsyncEnv.create_driver(limits or RuntimeLimits(), name=f"{name}-driver")
         self.transport = transport if transport is not None else PipeTransport(self.num_executors, name)
-        self.transport.start(self)
+        try:
+            self.transport.start(self)
+        except BaseException:
+            self.stop()                    # do not leak the driver env / half-started executors
+            raise
 
     # ------------------------------------------------------------------ mode
     def set_mode(self, mode: int) -> None:

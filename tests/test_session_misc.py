@@ -11,7 +11,10 @@ from asyncframework_b200.utils.metrics import ConsoleSink, CsvSink, JsonlSink, M
 
 def test_session_master_urls_and_ops(tmp_path):
     with pytest.raises(ValueError):
-        AsyncSession("spark://host:7077")
+        AsyncSession("mesos://host:5050")
+    from asyncframework_b200.rpc import RpcError
+    with pytest.raises(RpcError, match="cannot connect"):      # standalone master URL is understood; nobody listens there
+        AsyncSession("spark://127.0.0.1:1")
     with AsyncSession("local[3,2]") as sc:
         assert sc.default_parallelism == 3 and sc.scheduler.max_failures == 2
         assert sc.parallelize(range(10)).map(lambda x: x * x).reduce(lambda a, b: a + b) == 285
