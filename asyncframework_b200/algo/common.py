@@ -72,6 +72,15 @@ def load_points(cfg: AsyncConfig, scheduler: Scheduler, device: torch.device, dt
 
 
 def make_scheduler(cfg: AsyncConfig, device: torch.device) -> Scheduler:
+    master = getattr(cfg, "master", "") or ""
+    if master.startswith(("local-cluster", "spark://", "async://")):
+        # ``--master`` / ``spark.master``: the driver's closures run in executor processes (forked locally or by standalone
+        # Workers); the data then lives on the CPU of those processes — GPU training at scale is the fused backend's job
+        from ..core.session import AsyncSession
+        sess = AsyncSession(master, app_name=f"{cfg.algorithm}", conf=cfg)
+        sess.scheduler.block_first_async_job = bool(cfg.extra.get("block_first_async_job", True))
+        sess.scheduler._owning_session = sess
+        return sess.scheduler
     return Scheduler(num_executors=cfg.num_partitions, device=device if device.type == "cuda" else None,
                      block_first_async_job=bool(cfg.extra.get("block_first_async_job", True)))
 

@@ -96,6 +96,13 @@ class WaitTimer:
         return now_ms - self.submit.get(worker, now_ms)
 
 
+def _eval_on_device(s, W, loss_id):
+    """Module-level on purpose: the closure below is pickled BY VALUE for executor processes, and a ``from ..ops import``
+    inside it makes cloudpickle chase ``torch.ops`` (registered in ``sys.modules``, not picklable)."""
+    from ..ops.eval import eval_loss
+    return eval_loss(s, W.to(s.device), loss_id).double().cpu()
+
+
 def evaluate_objective(points, snapshots: List[Tuple[float, torch.Tensor]], loss: str = "least_squares") -> List[Tuple[float, float]]:
     """One pass over the data computing the objective of EVERY snapshot (K12: X[N×d]·W[d×T]).
 
@@ -112,8 +119,7 @@ def evaluate_objective(points, snapshots: List[Tuple[float, torch.Tensor]], loss
         if s is None or s.num_rows == 0:
             return acc
         if s.device.type == "cuda":
-            from ..ops import eval as eval_ops
-            part = eval_ops.eval_loss(s, W.to(s.device), grad.loss_id).double().cpu()
+            part = _eval_on_device(s, W, grad.loss_id)
         else:
             Wd = W.to(s.device)
             if s.is_dense:

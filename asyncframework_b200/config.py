@@ -83,6 +83,7 @@ class AsyncConfig:
     heartbeat_timeout_s: float = 30.0
     rounds_per_graph: int = 16       # CUDA-graph batch of rounds on the fused backend
     synthetic: Optional[str] = None  # mnist8m | epsilon | rcv1 | linear | logistic
+    master: str = ""                 # "" = local[P] in-process; local-cluster[n] / spark://host:port run the closures in executor processes
     quiet: bool = False              # suppress the reference-style progress lines on stdout ("Iteration k is finished", ...)
     extra: Dict[str, Any] = field(default_factory=dict)
 

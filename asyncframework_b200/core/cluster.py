@@ -101,6 +101,7 @@ class ExecutorBackend:
             if binary is None:                        # job finished or cancelled while this task was queued
                 self.send(("gone", job_id, partition, attempt, "", 0.0))
                 continue
+            self.send(("started", job_id, partition, attempt, "", 0.0))     # queued != running: speculation needs to know
             try:
                 if isinstance(binary, BaseException):
                     raise binary
@@ -239,7 +240,9 @@ class ClusterScheduler:
 
     def __init__(self, num_executors: int = 2, max_failures: int = 4, block_first_async_job: bool = True,
                  name: str = "afb-cluster", transport=None, limits=None, recover_lost_executors: bool = False,
-                 use_env: bool = True):
+                 use_env: bool = True, speculation: bool = False, speculation_multiplier: float = 1.5,
+                 speculation_quantile: float = 0.75, speculation_interval: float = 0.1, speculation_min_ms: float = 100.0,
+                 blacklist: bool = False, blacklist_max_failures: int = 2, blacklist_timeout: float = 3600.0):
         self.num_executors = int(num_executors)
         self.max_failures = int(max_failures)
         self.block_first_async_job = block_first_async_job
@@ -257,6 +260,18 @@ class ClusterScheduler:
         self.last_task_binary_bytes = 0
         self.indirect_results = 0
         self.executors_recovered = 0
+        # speculation (TaskSetManager.checkSpeculatableTasks, scheduler/TaskSetManager.scala:975) and executor blacklisting
+        # (scheduler/BlacklistTracker.scala:50).  Both are off by default, as in the reference: asynchrony is this
+        # framework's answer to stragglers; they exist for the synchronous drivers and for flaky hosts.
+        self.speculation = speculation
+        self.speculation_multiplier, self.speculation_quantile = speculation_multiplier, speculation_quantile
+        self.speculation_interval, self.speculation_min_ms = speculation_interval, speculation_min_ms
+        self.speculated_tasks = 0
+        self.speculative_wins = 0
+        self.blacklist_enabled = blacklist
+        self.blacklist_max_failures, self.blacklist_timeout = blacklist_max_failures, blacklist_timeout
+        self._exec_failures: Dict[int, int] = {}
+        self._blacklisted: Dict[int, float] = {}          # executor -> expiry (monotonic)
         self._getter = ThreadPoolExecutor(4, thread_name_prefix=f"{name}-task-result-getter")
         self.env = None
         if use_env:
@@ -268,6 +283,8 @@ class ClusterScheduler:
         except BaseException:
             self.stop()                    # do not leak the driver env / half-started executors
             raise
+        if self.speculation:
+            threading.Thread(target=self._speculation_loop, daemon=True, name=f"{name}-speculation").start()
 
     # ------------------------------------------------------------------ mode
     def set_mode(self, mode: int) -> None:
@@ -275,6 +292,84 @@ class ClusterScheduler:
 
     def stream_for(self, partition: int):
         return None
+
+    # ------------------------------------------------------------------ placement
+    def is_blacklisted(self, eid: int) -> bool:
+        exp = self._blacklisted.get(eid)
+        if exp is None:
+            return False
+        if time.monotonic() >= exp:                     # BlacklistTracker.applyBlacklistTimeout
+            self._blacklisted.pop(eid, None)
+            self._exec_failures.pop(eid, None)
+            self.listeners.post({"event": "executor_unblacklisted", "executor": eid})
+            return False
+        return True
+
+    def _route(self, partition: int, avoid: Optional[int] = None) -> int:
+        """Home executor of a partition is ``p % n`` (hard affinity: that is where its cached blocks live).  A blacklisted
+        (or explicitly avoided) home falls over to the next healthy executor, which recomputes from lineage."""
+        n = self.num_executors
+        home = partition % n
+        for step in range(n):
+            e = (home + step) % n
+            if e != avoid and not self.is_blacklisted(e):
+                return e
+        return home                                     # everyone is blacklisted: Spark aborts; we keep the home executor
+
+    def _note_failure(self, eid: int) -> None:
+        if not self.blacklist_enabled:
+            return
+        self._exec_failures[eid] = self._exec_failures.get(eid, 0) + 1
+        healthy = sum(1 for e in range(self.num_executors) if e != eid and not self.is_blacklisted(e))
+        if self._exec_failures[eid] >= self.blacklist_max_failures and eid not in self._blacklisted and healthy > 0:
+            self._blacklisted[eid] = time.monotonic() + self.blacklist_timeout
+            self.listeners.post({"event": "executor_blacklisted", "executor": eid, "failures": self._exec_failures[eid]})
+
+    def _launch(self, job_id: int, job: dict, partition: int, attempt: int, eid: int, speculative: bool = False) -> None:
+        """Send one task attempt to ``eid``, shipping the job's binary there first if that executor has not seen it."""
+        if eid not in job["executors"]:
+            self._send(eid, ("binary", job_id, job["make_payload"]([eid])))
+            job["executors"].append(eid)
+            with self._lock:
+                for b in job["make_payload"].shipped:     # type: ignore[attr-defined]
+                    self._blocks_held.setdefault(b, set()).add(eid)
+        if not speculative:
+            job["assigned"][partition] = eid
+            job["started"].pop(partition, None)       # set again by the executor's "started" message
+        self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
+
+    # ------------------------------------------------------------------ speculation
+    def _speculation_loop(self) -> None:
+        while not self._stopped:
+            time.sleep(self.speculation_interval)
+            with self._lock:
+                jobs = list(self._jobs.items())
+            for job_id, job in jobs:
+                try:
+                    self._check_speculatable(job_id, job)
+                except Exception:  # noqa: BLE001
+                    traceback.print_exc()
+
+    def _check_speculatable(self, job_id: int, job: dict) -> None:
+        done = job["durations"]
+        total = len(done) + len(job["pending"])
+        if total < 2 or len(done) < max(1, int(self.speculation_quantile * total)) or not job["pending"]:
+            return
+        med = sorted(done)[len(done) // 2]
+        threshold = max(self.speculation_multiplier * med, self.speculation_min_ms)
+        now = time.perf_counter()
+        for p in sorted(job["pending"]):
+            t0 = job["started"].get(p)
+            if t0 is None or p in job["speculated"] or (now - t0) * 1e3 <= threshold:
+                continue
+            target = self._route(p, avoid=job["assigned"].get(p))
+            if target == job["assigned"].get(p):
+                continue
+            job["speculated"][p] = target
+            self.speculated_tasks += 1
+            self.listeners.post({"event": "task_speculated", "job": job_id, "partition": p, "executor": target,
+                                 "running_ms": (now - t0) * 1e3, "median_ms": med})
+            self._launch(job_id, job, p, 1000, target, speculative=True)       # attempt >= 1000 marks a speculative copy
 
     # ------------------------------------------------------------------ plumbing
     def _send(self, eid: int, msg) -> None:
@@ -284,6 +379,10 @@ class ClusterScheduler:
         kind, job_id, partition, attempt, data, run_ms = msg
         with self._lock:
             job = self._jobs.get(job_id)
+        if kind == "started":
+            if job is not None and attempt < 1000:
+                job["started"][partition] = time.perf_counter()
+            return
         if job is None or kind == "gone":
             if kind == "indirect" and self.env is not None:       # nobody will read it: free the executor's block
                 self._getter.submit(self._drop_result_block, data[0])
@@ -293,14 +392,21 @@ class ClusterScheduler:
         elif kind == "indirect":
             self._getter.submit(self._fetch_indirect, eid, job_id, job, partition, data, run_ms)
         else:
+            if attempt >= 1000:                       # a failed speculative copy is simply dropped; the original still runs
+                job["speculated"].pop(partition, None)
+                return
+            if partition not in job["pending"]:
+                return
             attempt += 1
-            self.listeners.post({"event": "task_failed", "job": job_id, "partition": partition, "attempt": attempt, "error": data})
+            self.listeners.post({"event": "task_failed", "job": job_id, "partition": partition, "attempt": attempt,
+                                 "executor": eid, "error": data})
+            self._note_failure(eid)
             if attempt >= self.max_failures:
                 self.failed_jobs.append(job_id)
                 exc = RuntimeError(f"task {partition} of job {job_id} failed {attempt} times: {data.splitlines()[0]}")
                 self._fail_task(job, partition, exc)
-            else:
-                self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
+            else:                                      # same executor unless it just got blacklisted
+                self._launch(job_id, job, partition, attempt, self._route(partition))
 
     def _fail_task(self, job: dict, partition: int, exc: BaseException) -> None:
         if job["on_task_lost"] is not None:
@@ -315,6 +421,12 @@ class ClusterScheduler:
     def _task_succeeded(self, eid: int, job_id: int, job: dict, partition: int, data: bytes, run_ms, nbytes: int,
                         extra: Optional[dict] = None) -> None:
         waiter: JobWaiter = job["waiter"]
+        with self._lock:
+            if partition not in job["pending"] or partition in job["claimed"]:
+                return                                 # the other copy of a speculated / resubmitted task already delivered
+            job["claimed"].add(partition)
+        if job["speculated"].get(partition) == eid:
+            self.speculative_wins += 1
         metrics = dict(run_ms) if isinstance(run_ms, dict) else {"run_ms": float(run_ms)}
         metrics.update(extra or {})
         metrics["result_bytes"] = nbytes
@@ -329,6 +441,7 @@ class ClusterScheduler:
             self.failed_jobs.append(job_id)
             self._fail_task(job, partition, exc)
             return
+        job["durations"].append(float(metrics.get("run_ms", 0.0)))
         t0 = time.perf_counter()
         try:
             decoded = pickle.loads(data)
@@ -417,7 +530,7 @@ class ClusterScheduler:
         if self.recover_lost_executors and self._recover(eid, jobs):
             return
         for job_id, job in jobs:
-            lost = [p for p in list(job["pending"]) if p % self.num_executors == eid]
+            lost = [p for p in list(job["pending"]) if job["assigned"].get(p, p % self.num_executors) == eid]
             for p in lost:
                 self._fail_task(job, p, RuntimeError(f"executor {eid} lost while running partition {p} of job {job_id}"))
 
@@ -434,7 +547,9 @@ class ClusterScheduler:
         self.executors_recovered += 1
         self.listeners.post({"event": "executor_added", "executor": eid, "t_ms": time.perf_counter() * 1e3})
         for job_id, job in jobs:
-            lost = sorted(p for p in job["pending"] if p % self.num_executors == eid)
+            lost = sorted(p for p in job["pending"] if job["assigned"].get(p, p % self.num_executors) == eid)
+            if eid in job["executors"]:
+                job["executors"].remove(eid)           # the replacement has no binary yet: _launch re-ships it
             if not lost:
                 continue
             job["lost_count"] = job.get("lost_count", 0) + 1
@@ -443,10 +558,9 @@ class ClusterScheduler:
                     self._fail_task(job, p, RuntimeError(f"executor {eid} lost {job['lost_count']} times during job {job_id}"))
                 continue
             try:
-                self._send(eid, ("binary", job_id, job["make_payload"]([eid])))
                 for p in lost:
                     self.listeners.post({"event": "task_resubmitted", "job": job_id, "partition": p, "executor": eid})
-                    self._send(eid, ("task", job_id, p, 0, job["submit_ms"]))
+                    self._launch(job_id, job, p, 0, eid)
             except Exception as exc:  # noqa: BLE001
                 for p in lost:
                     self._fail_task(job, p, exc)
@@ -474,7 +588,8 @@ class ClusterScheduler:
         job_id = next(ClusterScheduler._job_ids)
         waiter = JobWaiter(job_id, len(parts), result_handler)
         now = time.perf_counter() * 1e3
-        executors = sorted({p % self.num_executors for p in parts})
+        assigned = {p: self._route(p) for p in parts}
+        executors = sorted(set(assigned.values()))
         # source data travels once per executor: blocks every target executor already holds are pickled as references
         from ..data.dataset import ShippingContext
         fault = self.fault_injector
@@ -492,7 +607,8 @@ class ClusterScheduler:
         with self._lock:
             self._jobs[job_id] = {"waiter": waiter, "pending": set(parts), "on_task_lost": on_task_lost,
                                   "executors": executors, "submit_ms": now, "result_bytes": 0,
-                                  "make_payload": make_payload}
+                                  "make_payload": make_payload, "assigned": assigned, "started": {}, "durations": [],
+                                  "speculated": {}, "claimed": set()}
         self.listeners.post({"event": "job_start", "job": job_id, "partitions": parts, "t_ms": now,
                              "task_binary_bytes": len(payload)})
         for e in executors:
@@ -502,8 +618,8 @@ class ClusterScheduler:
                 self._blocks_held.setdefault(b, set()).update(executors)
         for p in parts:
             self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0,
-                                 "executor": p % self.num_executors, "t_ms": now})
-            self._send(p % self.num_executors, ("task", job_id, p, 0, now))
+                                 "executor": assigned[p], "t_ms": now})
+            self._send(assigned[p], ("task", job_id, p, 0, now))
         if not parts:
             self._finish_job(job_id)
         return waiter

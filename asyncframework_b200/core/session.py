@@ -25,28 +25,67 @@ _LOCAL_CLUSTER = re.compile(r"^local-cluster\[\s*(\d+)\s*(?:,\s*(\d+)\s*(?:,\s*(
 
 
 class AsyncSession:
-    def __init__(self, master: str = "local[*]", app_name: str = "asyncframework_b200", device=None,
-                 conf: Optional[AsyncConfig] = None, num_executors: Optional[int] = None, cores_per_executor: int = 1,
-                 executor_memory_mb: int = 512):
+    def __init__(self, master: Optional[str] = None, app_name: Optional[str] = None, device=None,
+                 conf=None, num_executors: Optional[int] = None, cores_per_executor: Optional[int] = None,
+                 executor_memory_mb: Optional[int] = None, runtime_conf=None):
+        """``conf`` may be the algorithm-level :class:`AsyncConfig` or the runtime :class:`AsyncConf` (``new
+        SparkContext(conf)``); explicit arguments win over ``spark.master`` / ``spark.app.name`` / ``spark.executor.*``."""
+        from ..conf import AsyncConf
+        if isinstance(conf, AsyncConf):
+            runtime_conf, conf = conf, None
+        rc = runtime_conf if runtime_conf is not None else AsyncConf()
+        self.runtime_conf = rc.validate()
+        master = master or rc.get("spark.master")
+        app_name = app_name or rc.get("spark.app.name")
+        num_executors = num_executors or (rc.get("spark.executor.instances") or None)
+        cores_per_executor = cores_per_executor or rc.get("spark.executor.cores")
+        executor_memory_mb = executor_memory_mb or (max(1, rc.get("spark.executor.memory") >> 20) if rc.contains("spark.executor.memory") else 512)
         self.master = master
         self.app_name = app_name
         self.conf = conf or AsyncConfig()
         n, max_fail = self._parse_master(master)
+        if rc.contains("spark.task.maxFailures"):
+            max_fail = rc.get("spark.task.maxFailures")
         self.device = torch.device(device) if device is not None else None
+        cluster_kw = dict(max_failures=max_fail, name=app_name, limits=rc.runtime_limits(),
+                          block_first_async_job=rc.get("spark.async.blockFirstJob"),
+                          speculation=rc.get("spark.speculation"), speculation_multiplier=rc.get("spark.speculation.multiplier"),
+                          speculation_quantile=rc.get("spark.speculation.quantile"), speculation_interval=rc.get("spark.speculation.interval"),
+                          blacklist=rc.get("spark.blacklist.enabled"),
+                          blacklist_max_failures=rc.get("spark.blacklist.application.maxFailedTasksPerExecutor"),
+                          blacklist_timeout=rc.get("spark.blacklist.timeout"))
         if master.startswith("local-cluster"):
             from .cluster import ClusterScheduler
-            self.scheduler = ClusterScheduler(n, max_failures=max_fail, name=app_name)
+            self.scheduler = ClusterScheduler(n, recover_lost_executors=rc.contains("spark.async.recoverLostExecutors")
+                                              and rc.get("spark.async.recoverLostExecutors"), **cluster_kw)
         elif master.startswith(("spark://", "async://")):
             # standalone cluster manager (deploy/master.py, deploy/worker.py): executors are forked by Worker daemons on
             # any host and talk to this driver over TCP; a lost executor is replaced by the Master and its tasks re-run
             from ..deploy.client import StandaloneTransport
             from .cluster import ClusterScheduler
-            transport = StandaloneTransport(master, num_executors, cores_per_executor, executor_memory_mb, app_name)
-            self.scheduler = ClusterScheduler(num_executors or 1, max_failures=max_fail, name=app_name, transport=transport,
-                                              recover_lost_executors=True)
+            transport = StandaloneTransport(master, num_executors, cores_per_executor, executor_memory_mb, app_name,
+                                            register_timeout=max(30.0, rc.get("spark.network.timeout") / 2))
+            self.scheduler = ClusterScheduler(num_executors or 1, transport=transport,
+                                              recover_lost_executors=rc.get("spark.async.recoverLostExecutors"), **cluster_kw)
         else:
-            self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name)
+            self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name,
+                                       block_first_async_job=rc.get("spark.async.blockFirstJob"))
         self._stopped = False
+        if rc.get("spark.ui.enabled") or rc.get("spark.eventLog.enabled"):
+            log = None
+            if rc.get("spark.eventLog.enabled"):
+                os.makedirs(rc.get("spark.eventLog.dir"), exist_ok=True)
+                import time as _t
+                log = os.path.join(rc.get("spark.eventLog.dir"), f"{app_name}-{int(_t.time() * 1000)}.jsonl")
+            self.start_ui(port=rc.get("spark.ui.port") if rc.get("spark.ui.enabled") else 0, event_log=log)
+        if rc.get("spark.metrics.conf"):
+            from ..utils.metrics import MetricsSystem, SchedulerSource
+            self.metrics_system = MetricsSystem.from_properties(MetricsSystem.load_properties(rc.get("spark.metrics.conf")),
+                                                                getattr(self, "metrics", None))
+            if getattr(self, "metrics", None) is None:
+                self.metrics = self.metrics_system.registry
+                SchedulerSource(self.metrics, self.scheduler)
+            self.metrics_system.start()
 
     @staticmethod
     def _parse_master(master: str):
@@ -158,6 +197,8 @@ class AsyncSession:
 
     def stop(self) -> None:
         if not self._stopped:
+            if getattr(self, "metrics_system", None) is not None:
+                self.metrics_system.stop()
             if getattr(self, "ui", None) is not None:
                 self.status_store.stop()
                 self.ui.stop()

@@ -287,3 +287,73 @@ def test_lost_executor_is_replaced_and_its_tasks_are_resubmitted():
         assert s.executors_recovered == 1
         assert "executor_lost" in events and "executor_added" in events and "task_resubmitted" in events
         assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 210   # the replacement got the data re-shipped
+
+
+def test_speculative_copy_of_a_straggling_task_wins():
+    """TaskSetManagerSuite "speculative tasks": one executor is slow for one partition; a copy on the other executor
+    delivers first and the straggler's late result is ignored."""
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.data.dataset import ShardedDataset
+    events = []
+    with ClusterScheduler(2, speculation=True, speculation_multiplier=2.0, speculation_quantile=0.5,
+                          speculation_interval=0.05, speculation_min_ms=50.0) as s:
+        s.listeners.add(events.append)
+        ds = ShardedDataset.from_records(s, list(range(40)), 4)
+        assert ds.count() == 40
+
+        def work(tctx, it):
+            if tctx.partition_id == 3 and tctx.attempt < 1000:
+                time.sleep(5.0)                    # the straggler: only the ORIGINAL attempt is slow
+            else:
+                time.sleep(0.1)
+            return sum(it)
+        t0 = time.time()
+        res = {}
+        w = s.submit_job(ds, work, result_handler=res.__setitem__)
+        assert w.wait(20)
+        assert time.time() - t0 < 4.0                                         # did not wait for the 5 s straggler
+        assert res == {p: sum(range(10 * p, 10 * p + 10)) for p in range(4)}
+        assert s.speculated_tasks >= 1 and s.speculative_wins >= 1             # (a loaded CI box may speculate another task too)
+        spec = {e["partition"]: e for e in events if e["event"] == "task_speculated"}
+        assert spec[3]["executor"] == 0                                        # home of partition 3 is executor 1
+        time.sleep(0.2)
+        assert len(res) == 4                                                   # nothing delivered twice
+
+
+def test_failing_executor_is_blacklisted_and_its_partitions_move():
+    """BlacklistTrackerSuite: after two failed tasks executor 1 is excluded; retries and later jobs run on executor 0."""
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.data.dataset import ShardedDataset
+    events = []
+    with ClusterScheduler(2, max_failures=4, blacklist=True, blacklist_max_failures=2, blacklist_timeout=0.8) as s:
+        s.listeners.add(events.append)
+        ds = ShardedDataset.from_records(s, list(range(40)), 4)
+
+        def flaky(tctx, it):
+            if tctx.executor_id == 1:
+                raise RuntimeError("bad disk on executor 1")
+            return (tctx.executor_id, sum(it))
+        out = s.run_job(ds, flaky)
+        assert [o[1] for o in out] == [sum(range(10 * p, 10 * p + 10)) for p in range(4)]
+        assert {o[0] for o in out} == {0}                                      # everything ended up on executor 0
+        assert s.is_blacklisted(1) and not s.is_blacklisted(0)
+        assert any(e["event"] == "executor_blacklisted" and e["executor"] == 1 for e in events)
+        out2 = s.run_job(ds, lambda tctx, it: tctx.executor_id)
+        assert out2 == [0, 0, 0, 0]                                            # new jobs avoid it too
+        time.sleep(1.0)                                                        # blacklist timeout expires
+        assert not s.is_blacklisted(1)
+        assert s.run_job(ds, lambda tctx, it: tctx.executor_id) == [0, 1, 0, 1]
+        assert any(e["event"] == "executor_unblacklisted" for e in events)
+
+
+@pytest.mark.parametrize("algorithm", ["asgd", "asaga", "sgd_sync", "saga_sync", "sgd_mllib"])
+def test_every_driver_runs_end_to_end_on_executor_processes(algorithm):
+    """``--master=local-cluster[2]``: data prep, the training loop AND the final objective evaluation all ship closures to
+    executor processes (regression: the evaluation closure used to drag ``torch.ops`` into the task binary)."""
+    cfg = AsyncConfig(algorithm=algorithm, synthetic="linear", num_rows=400, num_features=6, num_partitions=2,
+                      num_iterations=12 if "sync" in algorithm or algorithm == "sgd_mllib" else 40, step_size=0.3,
+                      batch_rate=0.4, printer_freq=4, backend="cpu", master="local-cluster[2]", quiet=True, bucket_ratio=0.5)
+    rep = algo.run(cfg)
+    assert rep.objective, "objective-vs-time table missing"
+    first, last = rep.objective[0][1], rep.objective[-1][1]
+    assert np.isfinite(last) and last < first, (first, last)
