@@ -279,6 +279,7 @@ class AsyncConf:
             storage_memory=int(g("spark.executor.memory") * g("spark.memory.fraction")),
             compression_codec=g("spark.io.compression.codec"), serializer=g("spark.serializer"),
             local_dir=g("spark.local.dir") or None, network_timeout=g("spark.network.timeout"),
+            heartbeat_interval=g("spark.executor.heartbeatInterval"),
             auth_secret=(g("spark.authenticate.secret") or None) if g("spark.authenticate") else None)
 
     @staticmethod

@@ -48,6 +48,14 @@ from . import accumulator as _acc
 from .scheduler import JobFailed, JobWaiter, ListenerBus, TaskContext  # noqa: F401
 
 
+def thread_dump() -> List[dict]:
+    """Stack of every thread of this process (``Utils.getThreadDump``; served by the UI's thread-dump page)."""
+    import sys
+    names = {t.ident: t.name for t in threading.enumerate()}
+    return [{"thread_id": tid, "name": names.get(tid, "?"), "stack": "".join(traceback.format_stack(frame))}
+            for tid, frame in sorted(sys._current_frames().items())]
+
+
 # =================================================================================================== executor side
 class ExecutorBackend:
     """Transport-agnostic executor.  Feed it driver messages with :meth:`handle` (from a receiver thread / an RPC
@@ -83,10 +91,33 @@ class ExecutorBackend:
             self.binaries.pop(msg[1], None)
         elif kind == "task":
             self.tasks.put(msg)
+        elif kind == "thread_dump":                      # ExecutorThreadDumpPage: answered by the receiver thread, even mid-task
+            self.send(("threads", -1, -1, msg[1], thread_dump(), 0.0))
         return True
 
     def close(self) -> None:
+        self._closed = True
         self.tasks.put(None)
+
+    def start_heartbeats(self, interval: float) -> None:
+        """Executor -> driver liveness + progress (``Executor.reportHeartBeat``, executor/Executor.scala:770-815): a
+        separate thread, so a long task still heartbeats but a wedged or stopped PROCESS does not."""
+        def loop():
+            import os
+            while not getattr(self, "_closed", False):
+                time.sleep(interval)
+                try:
+                    from .env import AsyncEnv
+                    env = AsyncEnv.get()
+                    mem = env.block_manager.memory_status() if env is not None else (0, 0)
+                    self.send(("heartbeat", -1, -1, 0, {"tasks_run": self.tasks_run, "queued": self.tasks.qsize(),
+                                                       "active": self.active_task, "pid": os.getpid(),
+                                                       "storage_max": mem[0], "storage_free": mem[1]}, 0.0))
+                except Exception:  # noqa: BLE001  (the driver is gone: the receiver will shut us down)
+                    return
+        threading.Thread(target=loop, daemon=True, name=f"executor-{self.eid}-heartbeat").start()
+
+    active_task = None
 
     def run_tasks(self) -> None:
         from .env import AsyncEnv
@@ -102,6 +133,7 @@ class ExecutorBackend:
                 self.send(("gone", job_id, partition, attempt, "", 0.0))
                 continue
             self.send(("started", job_id, partition, attempt, "", 0.0))     # queued != running: speculation needs to know
+            self.active_task = (job_id, partition, attempt)
             try:
                 if isinstance(binary, BaseException):
                     raise binary
@@ -127,6 +159,8 @@ class ExecutorBackend:
             except BaseException as exc:  # noqa: BLE001
                 _acc.end_task(False)
                 self.send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
+            finally:
+                self.active_task = None
 
 
 def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
@@ -150,6 +184,8 @@ def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
                 return
 
     threading.Thread(target=receiver, daemon=True, name=f"executor-{eid}-recv").start()
+    if limits is not None:
+        backend.start_heartbeats(limits.heartbeat_interval)
     try:
         backend.run_tasks()
     finally:
@@ -208,6 +244,9 @@ class PipeTransport:
             self._conns[eid].close()
         except OSError:
             pass
+        old = self._procs[eid]
+        if old is not None and old.is_alive():
+            old.kill()
         self._launch(eid)
         return True
 
@@ -270,6 +309,10 @@ class ClusterScheduler:
         self.speculative_wins = 0
         self.blacklist_enabled = blacklist
         self.blacklist_max_failures, self.blacklist_timeout = blacklist_max_failures, blacklist_timeout
+        self._dump_waiters: Dict[int, Any] = {}
+        self._dump_ids = itertools.count(1)
+        self.executor_heartbeats: Dict[int, dict] = {}     # executor -> last heartbeat payload (+ "t" = monotonic arrival time)
+        self.executors_expired = 0
         self._exec_failures: Dict[int, int] = {}
         self._blacklisted: Dict[int, float] = {}          # executor -> expiry (monotonic)
         self._getter = ThreadPoolExecutor(4, thread_name_prefix=f"{name}-task-result-getter")
@@ -283,6 +326,8 @@ class ClusterScheduler:
         except BaseException:
             self.stop()                    # do not leak the driver env / half-started executors
             raise
+        if self.env is not None:
+            threading.Thread(target=self._heartbeat_monitor, daemon=True, name=f"{name}-heartbeat-receiver").start()
         if self.speculation:
             threading.Thread(target=self._speculation_loop, daemon=True, name=f"{name}-speculation").start()
 
@@ -338,6 +383,26 @@ class ClusterScheduler:
             job["started"].pop(partition, None)       # set again by the executor's "started" message
         self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
 
+    # ------------------------------------------------------------------ liveness
+    def _heartbeat_monitor(self) -> None:
+        """``HeartbeatReceiver.expireDeadHosts`` (core/HeartbeatReceiver.scala:193-220): an executor that has heartbeated at
+        least once and then stays silent for ``network_timeout`` is wedged (stopped process, dead host behind a live TCP
+        connection): kill it, which takes the ordinary lost-executor path (replacement + resubmission, or job failure)."""
+        timeout = self.env.limits.network_timeout
+        period = max(0.05, min(timeout / 4, 5.0))
+        while not self._stopped:
+            time.sleep(period)
+            now = time.monotonic()
+            for eid, hb in list(self.executor_heartbeats.items()):
+                if now - hb["t"] > timeout:
+                    self.executor_heartbeats.pop(eid, None)
+                    self.executors_expired += 1
+                    self.listeners.post({"event": "executor_expired", "executor": eid, "silent_s": now - hb["t"]})
+                    try:
+                        self.transport.kill(eid)
+                    except Exception:  # noqa: BLE001
+                        threading.Thread(target=self._executor_lost, args=(eid,), daemon=True).start()
+
     # ------------------------------------------------------------------ speculation
     def _speculation_loop(self) -> None:
         while not self._stopped:
@@ -379,6 +444,14 @@ class ClusterScheduler:
         kind, job_id, partition, attempt, data, run_ms = msg
         with self._lock:
             job = self._jobs.get(job_id)
+        if kind == "heartbeat":
+            self.executor_heartbeats[eid] = {**data, "t": time.monotonic()}
+            return
+        if kind == "threads":
+            fut = self._dump_waiters.pop(attempt, None)
+            if fut is not None:
+                fut.set_result(data)
+            return
         if kind == "started":
             if job is not None and attempt < 1000:
                 job["started"][partition] = time.perf_counter()
@@ -642,9 +715,28 @@ class ClusterScheduler:
         self.first_iter = 0
         return waiter
 
+    def request_total_executors(self, total: int) -> bool:
+        """``sc.requestTotalExecutors``: supported by transports with a cluster manager behind them (standalone)."""
+        if not hasattr(self.transport, "request_total_executors"):
+            raise NotImplementedError(f"{type(self.transport).__name__} has a fixed set of executors")
+        return self.transport.request_total_executors(int(total))
+
     def kill_executor(self, eid: int) -> None:
         """Fault injection: kill one executor process (FailureSuite / DistributedSuite style)."""
         self.transport.kill(eid)
+
+    def thread_dump(self, eid, timeout: float = 10.0) -> List[dict]:
+        """Thread stacks of the driver (``eid="driver"``) or of an executor process."""
+        if eid == "driver":
+            return thread_dump()
+        from concurrent.futures import Future
+        token, fut = next(self._dump_ids), Future()
+        self._dump_waiters[token] = fut
+        self._send(int(eid), ("thread_dump", token))
+        try:
+            return fut.result(timeout)
+        finally:
+            self._dump_waiters.pop(token, None)
 
     def storage_status(self) -> dict:
         """Per-process block-store usage as the driver's BlockManagerMaster sees it (``sc.getExecutorStorageStatus``)."""

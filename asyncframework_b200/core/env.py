@@ -32,7 +32,8 @@ class RuntimeLimits:
     compression_codec: str = "zlib"                # spark.io.compression.codec
     serializer: str = "pickle"                     # spark.serializer
     local_dir: Optional[str] = None                # spark.local.dir
-    network_timeout: float = 120.0                 # spark.network.timeout
+    network_timeout: float = 120.0                 # spark.network.timeout (also: executor heartbeat expiry)
+    heartbeat_interval: float = 10.0               # spark.executor.heartbeatInterval
     auth_secret: Optional[str] = None              # spark.authenticate.secret
 
 

@@ -54,7 +54,7 @@ class _DriverEndpoint(RpcEndpoint):
     def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
         if msg[0] == "register_executor":
             _, slot, exec_id, ref, cores, pid, host = msg
-            if not (0 <= slot < self.t.num_executors):
+            if slot < 0:
                 ctx.reply(("refused", f"slot {slot} out of range"))
                 return
             with self.t.cv:
@@ -71,6 +71,8 @@ class _DriverEndpoint(RpcEndpoint):
         for slot, addr in list(self.t.addresses.items()):
             if addr == address:
                 self.t._slot_down(slot, self.t.exec_ids.get(slot), "connection lost")
+        if address == self.t.master_address and self.t.sched is not None and not self.t.sched._stopped:
+            threading.Thread(target=self.t._reregister_loop, daemon=True, name="app-client-reregister").start()
 
 
 class StandaloneTransport:
@@ -93,6 +95,8 @@ class StandaloneTransport:
         self.app_state = "RUNNING"
         self.sched = None
         self.master: Optional[RpcEndpointRef] = None
+        self.master_reconnects = 0
+        self._reregistering = False
 
     # ---- ClusterScheduler transport interface -------------------------------------------------------------------------
     def start(self, sched) -> None:
@@ -133,6 +137,64 @@ class StandaloneTransport:
             # off the inbox thread: recovery waits for the replacement's RegisterExecutor, which this inbox must serve
             threading.Thread(target=self.sched._executor_lost, args=(slot,), daemon=True,
                              name=f"executor-lost-{slot}").start()
+
+    def _reregister_loop(self) -> None:
+        """The master went away (restart / failover to a standby on the same address): keep the executors running and
+        re-register the application under its existing id until a master answers (StandaloneAppClient ``MasterChanged``)."""
+        with self.cv:
+            if self._reregistering:
+                return
+            self._reregistering = True
+        try:
+            self._reregister()
+        finally:
+            self._reregistering = False
+
+    def _reregister(self) -> None:
+        env = self.sched.env.rpc_env
+        me = env.endpoint_ref(None, _DriverEndpoint.NAME)
+        delay = 0.2
+        while not self.sched._stopped and self.app_state == "RUNNING":
+            try:
+                ref = env.endpoint_ref(self.master_address, "Master")
+                reply = ref.ask_sync(("reregister_app", self.app_id, self.app_name, self.num_executors, self.cores_per_executor,
+                                      self.memory_mb, me, str(env.address)), 5)
+                if reply[0] == "registered":
+                    self.master = ref
+                    self.master_reconnects += 1
+                    return
+            except RpcError:
+                pass
+            time.sleep(delay)
+            delay = min(delay * 2, 5.0)
+
+    def request_total_executors(self, total: int, timeout: Optional[float] = None) -> bool:
+        """Dynamic allocation: grow or shrink the application to ``total`` executor slots.  Partition p lives on slot
+        p % total afterwards, so only call this between jobs (cached blocks of re-homed partitions are recomputed)."""
+        with self.sched._lock:
+            if self.sched._jobs:
+                raise RuntimeError("request_total_executors while jobs are running would re-home their partitions")
+        old = self.num_executors
+        if not self.master.ask_sync(("request_total_executors", self.app_id, int(total)), 10):
+            return False
+        if total < old:
+            with self.cv:
+                for slot in range(total, old):
+                    self.refs.pop(slot, None)
+                    self.addresses.pop(slot, None)
+                    self.exec_ids[slot] = -1              # late status / disconnect events of the released executors are stale
+        self.num_executors = total
+        deadline = time.time() + (timeout or self.register_timeout)
+        with self.cv:
+            while any(slot not in self.refs for slot in range(total)):
+                left = deadline - time.time()
+                if left <= 0:
+                    return False
+                self.cv.wait(min(left, 0.5))
+        self.sched.num_executors = total
+        with self.sched._lock:
+            self.sched._blocks_held.clear()               # the partition -> slot map changed: re-ship source blocks on demand
+        return True
 
     def relaunch(self, eid: int) -> bool:
         """The Master re-fills the slot on its own; wait for the replacement to register."""
@@ -180,8 +242,10 @@ class LocalStandaloneCluster:
     """Master + ``num_workers`` Workers in this process, real executor processes, real TCP."""
 
     def __init__(self, num_workers: int = 2, cores_per_worker: int = 1, memory_per_worker: int = 1024,
-                 worker_timeout: float = 60.0, heartbeat_interval: float = 1.0, secret: Optional[str] = None):
-        self.master_env, self.master = start_master("127.0.0.1", 0, worker_timeout, secret)
+                 worker_timeout: float = 60.0, heartbeat_interval: float = 1.0, secret: Optional[str] = None,
+                 recovery_dir: Optional[str] = None):
+        self._master_args = dict(worker_timeout=worker_timeout, secret=secret, recovery_dir=recovery_dir, recovery_grace=1.5)
+        self.master_env, self.master = start_master("127.0.0.1", 0, **self._master_args)
         self.master_url = f"spark://{self.master_env.address}"
         self.worker_envs, self.workers = [], []
         for i in range(num_workers):
@@ -198,6 +262,13 @@ class LocalStandaloneCluster:
 
     def stop_worker(self, i: int) -> None:
         self.worker_envs[i].shutdown()
+
+    def restart_master(self, down_for: float = 0.3) -> None:
+        """Kill the master and bring a new one up on the SAME address (FaultToleranceTest's "kill leader")."""
+        addr = self.master_env.address
+        self.master_env.shutdown()
+        time.sleep(down_for)
+        self.master_env, self.master = start_master(addr.host, addr.port, **self._master_args)
 
     def state(self) -> dict:
         return self.master_env.endpoint_ref(None, "Master").ask_sync(("state",), 10)

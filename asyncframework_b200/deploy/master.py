@@ -71,19 +71,81 @@ class AppInfo:
 class Master(RpcEndpoint):
     NAME = "Master"
 
-    def __init__(self, worker_timeout: float = 60.0, spread_out: bool = True):
+    def __init__(self, worker_timeout: float = 60.0, spread_out: bool = True, recovery_dir: Optional[str] = None,
+                 recovery_grace: float = 2.0):
         self.worker_timeout = worker_timeout
         self.spread_out = spread_out
+        # FILESYSTEM recovery mode (spark.deploy.recoveryMode=FILESYSTEM, FileSystemPersistenceEngine): registrations are
+        # persisted; a restarted master on the same address starts RECOVERING — workers and drivers notice the dropped
+        # connection, re-register (workers report the executors they are still running, drivers their application id and
+        # slots), the master adopts them, and only after the grace period does it schedule again, so nothing that is
+        # still alive gets launched twice.
+        self.recovery_dir = recovery_dir
+        self.recovery_grace = recovery_grace
+        self.recovering_until = 0.0
+        self.status = "ALIVE"
+        self._reported: Dict[tuple, tuple] = {}       # (app_id, exec_id) -> (worker_id, slot, cores, memory) reported by workers
+        self.recovered = {"workers": 0, "apps": 0, "executors": 0}
         self.workers: Dict[str, WorkerInfo] = {}
         self.apps: Dict[str, AppInfo] = {}
         self.completed_apps: List[AppInfo] = []
         self._app_ids = itertools.count(0)
+        self._next_app_id = 0
         self._stop = threading.Event()
         self.start_time = time.time()
 
     # ------------------------------------------------------------------ lifecycle
     def on_start(self) -> None:
         threading.Thread(target=self._timeout_loop, daemon=True, name="master-worker-timeout").start()
+        prior = self._load_persisted()
+        if prior is not None:
+            self._app_ids = itertools.count(prior.get("next_app", 0))
+            if prior.get("apps") or prior.get("workers"):
+                self.status = "RECOVERING"
+                self.recovering_until = time.time() + self.recovery_grace
+                self.expected = {"workers": sorted(prior.get("workers", [])), "apps": sorted(prior.get("apps", []))}
+
+                def done():
+                    time.sleep(self.recovery_grace)
+                    try:
+                        self.self_ref.send(("complete_recovery",))
+                    except RpcError:
+                        pass
+                threading.Thread(target=done, daemon=True, name="master-recovery").start()
+
+    # ------------------------------------------------------------------ persistence
+    def _state_file(self) -> Optional[str]:
+        import os
+        if not self.recovery_dir:
+            return None
+        os.makedirs(self.recovery_dir, exist_ok=True)
+        return os.path.join(self.recovery_dir, "master-state.json")
+
+    def _persist(self) -> None:
+        path = self._state_file()
+        if path is None:
+            return
+        import json
+        import os
+        snap = {"next_app": self._next_app_id, "workers": sorted(self.workers), "apps": sorted(self.apps), "t": time.time()}
+        tmp = path + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(snap, f)
+        os.replace(tmp, path)
+
+    def _load_persisted(self) -> Optional[dict]:
+        path = self._state_file()
+        if path is None:
+            return None
+        import json
+        import os
+        if not os.path.exists(path):
+            return None
+        try:
+            with open(path) as f:
+                return json.load(f)
+        except (OSError, ValueError):
+            return None
 
     def on_stop(self) -> None:
         self._stop.set()
@@ -116,28 +178,72 @@ class Master(RpcEndpoint):
             self._executor_state_changed(app_id, exec_id, state, message, exit_code)
         elif op == "unregister_app":
             self._finish_app(msg[1], "FINISHED")
+        elif op == "complete_recovery":
+            self.status = "ALIVE"
+            self.recovering_until = 0.0
+            self._schedule()
         else:
             raise RpcError(f"Master: unknown one-way message {op!r}")
 
     def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
         op = msg[0]
         if op == "register_worker":
-            _, wid, host, port, cores, memory_mb, ref = msg
+            _, wid, host, port, cores, memory_mb, ref = msg[:7]
+            running = msg[7] if len(msg) > 7 else []
             old = self.workers.get(wid)
             if old is not None and old.state == "ALIVE":
                 ctx.reply(("failed", f"duplicate worker id {wid}"))
                 return
             self.workers[wid] = WorkerInfo(wid, host, port, int(cores), int(memory_mb), ref)
             ctx.reply(("registered", str(self.rpc_env.address)))
+            for app_id, exec_id, slot, ecores, emem in running:       # executors that survived a master restart
+                self._reported[(app_id, exec_id)] = (wid, slot, ecores, emem)
+                app = self.apps.get(app_id)
+                if app is not None:
+                    self._adopt(app, exec_id)
+                elif self.status == "ALIVE":                           # nobody owns it any more
+                    ref.send(("kill_executor", app_id, exec_id, False))
+            if running:
+                self.recovered["workers"] += 1
+            self._persist()
+            self._schedule()
+        elif op == "reregister_app":
+            _, app_id, name, num_executors, cores_per_executor, memory_mb, driver_ref, driver_url = msg
+            if app_id not in self.apps:
+                self.apps[app_id] = AppInfo(app_id, name, driver_ref, driver_url, int(num_executors), int(cores_per_executor), int(memory_mb))
+                self.recovered["apps"] += 1
+            app = self.apps[app_id]
+            app.driver = driver_ref
+            for (a, exec_id) in [k for k in self._reported if k[0] == app_id]:
+                self._adopt(app, exec_id)
+            ctx.reply(("registered", app_id))
+            self._persist()
+            self._schedule()
+        elif op == "request_total_executors":                          # dynamic allocation (ExecutorAllocationManager ->
+            _, app_id, total = msg                                     #   StandaloneSchedulerBackend.doRequestTotalExecutors)
+            app = self.apps.get(app_id)
+            if app is None:
+                ctx.reply(False)
+                return
+            app.num_executors = int(total)
+            for ex in app.executors.values():                          # shrink: release the highest slots
+                if ex.slot >= app.num_executors and ex.state in ("LAUNCHING", "RUNNING"):
+                    w = self.workers.get(ex.worker_id)
+                    if w is not None:
+                        w.ref.send(("kill_executor", app_id, ex.exec_id, False))
+            ctx.reply(True)
             self._schedule()
         elif op == "register_app":
             _, name, num_executors, cores_per_executor, memory_mb, driver_ref, driver_url = msg
-            app_id = f"app-{time.strftime('%Y%m%d%H%M%S')}-{next(self._app_ids):04d}"
+            n = next(self._app_ids)
+            self._next_app_id = n + 1
+            app_id = f"app-{time.strftime('%Y%m%d%H%M%S')}-{n:04d}"
             if num_executors is None:                   # default: one executor on every alive worker
                 num_executors = max(1, sum(1 for w in self.workers.values() if w.state == "ALIVE"))
             self.apps[app_id] = AppInfo(app_id, name, driver_ref, driver_url, int(num_executors),
                                         int(cores_per_executor), int(memory_mb))
             ctx.reply((app_id, int(num_executors)))
+            self._persist()
             self._schedule()
         elif op == "state":
             ctx.reply(self.state())
@@ -163,9 +269,27 @@ class Master(RpcEndpoint):
             self._finish_app(app.id, "FINISHED")       # a driver that goes away ends its application
 
     # ------------------------------------------------------------------ scheduling
+    def _adopt(self, app: AppInfo, exec_id: int) -> None:
+        """Take over an executor that a worker reports as running for ``app`` (master restart)."""
+        rep = self._reported.pop((app.id, exec_id), None)
+        if rep is None or exec_id in app.executors:
+            return
+        wid, slot, cores, mem = rep
+        w = self.workers.get(wid)
+        if w is None:
+            return
+        app.executors[exec_id] = ExecutorDesc(exec_id, slot, wid, cores, mem, "RUNNING")
+        app.next_exec_id = max(app.next_exec_id, exec_id + 1)
+        w.cores_used += cores
+        w.memory_used += mem
+        w.executors[f"{app.id}/{exec_id}"] = cores
+        self.recovered["executors"] += 1
+
     def _schedule(self) -> None:
         """Fill every empty slot of every running app: spread-out = the alive worker with the most free cores first
         (``spark.deploy.spreadOut``), consolidate = pack the first worker that fits."""
+        if time.time() < self.recovering_until:          # RECOVERING: wait for workers/drivers to report what is still alive
+            return
         for app in sorted(self.apps.values(), key=lambda a: a.submit_time):          # FIFO across applications
             if app.state != "RUNNING":
                 continue
@@ -222,7 +346,8 @@ class Master(RpcEndpoint):
             pass
         if state in ("EXITED", "KILLED", "FAILED", "LOST") and old not in ("EXITED", "KILLED", "FAILED", "LOST"):
             self._release(app, ex)
-            normal = (state == "EXITED" and exit_code == 0) or (state == "KILLED" and message == "app finished")
+            normal = (state == "EXITED" and exit_code == 0) or (state == "KILLED" and message == "app finished") \
+                or ex.slot >= app.num_executors
             if app.state == "RUNNING" and not normal:
                 app.retries += 1
                 if app.retries >= MAX_EXECUTOR_RETRIES and not any(e.state == "RUNNING" for e in app.executors.values()):
@@ -259,6 +384,7 @@ class Master(RpcEndpoint):
             pass
         self.completed_apps.append(app)
         del self.completed_apps[:-50]
+        self._persist()
         self._schedule()
 
     # ------------------------------------------------------------------ status (MasterWebUI /json)
@@ -268,7 +394,7 @@ class Master(RpcEndpoint):
                     "num_executors": a.num_executors, "cores_per_executor": a.cores_per_executor,
                     "executors": [{"id": e.exec_id, "slot": e.slot, "worker": e.worker_id, "state": e.state, "cores": e.cores}
                                   for e in a.executors.values()]}
-        return {"url": f"spark://{self.rpc_env.address}", "status": "ALIVE", "uptime_s": time.time() - self.start_time,
+        return {"url": f"spark://{self.rpc_env.address}", "status": self.status, "recovered": dict(self.recovered), "uptime_s": time.time() - self.start_time,
                 "workers": [{"id": w.id, "host": w.host, "port": w.port, "cores": w.cores, "cores_used": w.cores_used,
                              "memory_mb": w.memory_mb, "memory_used": w.memory_used, "state": w.state,
                              "last_heartbeat": w.last_heartbeat, "executors": sorted(w.executors)}
@@ -278,10 +404,10 @@ class Master(RpcEndpoint):
 
 
 def start_master(host: str = "127.0.0.1", port: int = 7077, worker_timeout: float = 60.0, secret: Optional[str] = None,
-                 spread_out: bool = True):
+                 spread_out: bool = True, recovery_dir: Optional[str] = None, recovery_grace: float = 2.0):
     """Returns ``(rpc_env, master_endpoint)``; the URL is ``spark://<rpc_env.address>``."""
     env = RpcEnv("master", host, port, secret=secret)
-    master = Master(worker_timeout, spread_out)
+    master = Master(worker_timeout, spread_out, recovery_dir, recovery_grace)
     env.setup_endpoint(Master.NAME, master)
     return env, master
 
@@ -293,8 +419,9 @@ def main(argv=None) -> None:
     ap.add_argument("--webui-port", type=int, default=0, help="serve the JSON status page on this port (0 = off)")
     ap.add_argument("--worker-timeout", type=float, default=60.0)
     ap.add_argument("--secret", default=None)
+    ap.add_argument("--recovery-dir", default=None, help="persist registrations here and recover them after a restart")
     a = ap.parse_args(argv)
-    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret)
+    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret, recovery_dir=a.recovery_dir)
     print(f"Master started at spark://{env.address}", flush=True)
     if a.webui_port:
         from ..utils.status_server import serve_json

@@ -130,8 +130,10 @@ class Worker(RpcEndpoint):
                 try:
                     self.master = self.rpc_env.endpoint_ref(self.master_address, "Master")
                     me = self.self_ref                  # pickles with this env's listening address
+                    running = [(r.app_id, r.exec_id, r.slot, r.cores, r.memory_mb) for r in list(self.executors.values())
+                               if r.proc is not None and r.proc.poll() is None]
                     reply = self.master.ask_sync(("register_worker", self.id, self.rpc_env.address.host, self.rpc_env.address.port,
-                                                  self.cores, self.memory_mb, me), 10)
+                                                  self.cores, self.memory_mb, me, running), 10)
                     if reply[0] == "registered":
                         self.registered.set()
                         delay = 0.2

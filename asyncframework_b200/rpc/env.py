@@ -609,6 +609,10 @@ class RpcEnv:
         for ib in inboxes:
             ib.stop()
         if self._server is not None:
+            try:                      # wake the accept() thread: a plain close() leaves it blocked on the fd NUMBER, and if a
+                self._server.shutdown(socket.SHUT_RDWR)   # new listener re-uses that number it would steal its connections
+            except OSError:
+                pass
             try:
                 self._server.close()
             except OSError:

@@ -117,6 +117,7 @@ class StatusServer:
             f"{base}/{app}/jobs/(\\d+)": self._job,
             f"{base}/{app}/executors": store.executor_list,
             f"{base}/{app}/allexecutors": store.executor_list,
+            f"{base}/{app}/executors/([^/]+)/threads": self._threads,
             f"{base}/{app}/storage/rdd": store.rdd_storage,
             f"{base}/{app}/environment": lambda: store.environment,
             f"{base}/{app}/async/workers": store.async_workers,
@@ -135,6 +136,15 @@ class StatusServer:
         if j is None:
             raise KeyError(f"job {job_id}")
         return j
+
+    def _threads(self, executor_id: str):
+        sched = self.store._scheduler
+        if hasattr(sched, "thread_dump"):
+            return sched.thread_dump(executor_id)
+        if executor_id != "driver":
+            raise KeyError(f"executor {executor_id} (executors of an in-process master are threads of the driver: ask for 'driver')")
+        from ..core.cluster import thread_dump
+        return thread_dump()
 
     def _prometheus(self):
         from .metrics import prometheus_text

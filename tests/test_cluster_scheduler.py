@@ -357,3 +357,30 @@ def test_every_driver_runs_end_to_end_on_executor_processes(algorithm):
     assert rep.objective, "objective-vs-time table missing"
     first, last = rep.objective[0][1], rep.objective[-1][1]
     assert np.isfinite(last) and last < first, (first, last)
+
+
+def test_wedged_executor_is_expired_by_missing_heartbeats_and_replaced():
+    """HeartbeatReceiverSuite: a SIGSTOPped executor keeps its pipe open but stops heartbeating; the driver expires it
+    after ``network_timeout``, kills it and the slot is re-filled."""
+    import signal
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.core.env import RuntimeLimits
+    from asyncframework_b200.data.dataset import ShardedDataset
+    events = []
+    lim = RuntimeLimits(heartbeat_interval=0.1, network_timeout=1.0)
+    with ClusterScheduler(2, limits=lim, recover_lost_executors=True) as s:
+        s.listeners.add(events.append)
+        ds = ShardedDataset.from_records(s, list(range(20)), 4)
+        assert ds.count() == 20
+        t0 = time.time()
+        while len(s.executor_heartbeats) < 2 and time.time() - t0 < 10:
+            time.sleep(0.05)
+        hb = s.executor_heartbeats[1]
+        assert hb["tasks_run"] == 2 and hb["storage_max"] > 0
+        os.kill(hb["pid"], signal.SIGSTOP)                      # wedged, not dead
+        res = {}
+        w = s.submit_job(ds, lambda tctx, it: sum(it), result_handler=res.__setitem__)
+        assert w.wait(30)
+        assert res == {p: sum(range(5 * p, 5 * p + 5)) for p in range(4)}
+        assert s.executors_expired == 1 and s.executors_recovered == 1
+        assert [e["executor"] for e in events if e["event"] == "executor_expired"] == [1]

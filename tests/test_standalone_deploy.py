@@ -100,3 +100,47 @@ def test_application_waits_for_resources_and_fails_clearly_when_none_come():
             from asyncframework_b200.core.cluster import ClusterScheduler
             from asyncframework_b200.deploy import StandaloneTransport
             ClusterScheduler(1, transport=StandaloneTransport(c.master_url, 1, register_timeout=1.5))
+
+
+def test_master_restart_recovers_workers_apps_and_running_executors(tmp_path):
+    """FaultToleranceTest / PersistenceEngineSuite at the behaviour level: the master dies and comes back on the same
+    address; workers re-register WITH their running executors, the driver re-registers its application id, nothing is
+    launched twice, and the recovered master still replaces an executor that dies afterwards."""
+    with LocalStandaloneCluster(num_workers=2, cores_per_worker=2, heartbeat_interval=0.2, recovery_dir=str(tmp_path)) as c:
+        with AsyncSession(c.master_url, app_name="ha") as sc:
+            ds = sc.parallelize(range(20), 4)
+            assert ds.count() == 20
+            app_id = sc.scheduler.transport.app_id
+            before = sorted((e["id"], e["slot"], e["worker"]) for e in c.state()["active_apps"][0]["executors"])
+            c.restart_master()
+            assert _wait(lambda: sc.scheduler.transport.master_reconnects == 1, 20)
+            assert _wait(lambda: len(c.state()["workers"]) == 2 and c.state()["status"] == "ALIVE", 20)
+            st = c.state()
+            assert st["recovered"] == {"workers": 2, "apps": 1, "executors": 2}
+            (app,) = st["active_apps"]
+            assert app["id"] == app_id
+            assert sorted((e["id"], e["slot"], e["worker"]) for e in app["executors"]) == before      # adopted, not relaunched
+            assert all(w["cores_used"] == 1 for w in st["workers"])
+            assert ds.map(lambda x: x * 2).reduce(lambda a, b: a + b) == 380                           # executors never stopped
+            sc.scheduler.kill_executor(0)                                                               # new master still manages the app
+            assert _wait(lambda: sc.scheduler.executors_recovered == 1, 60)
+            assert ds.count() == 20
+        assert _wait(lambda: c.state()["active_apps"] == [])
+        # a NEW application after the restart does not reuse an application id
+        with AsyncSession(c.master_url, app_name="after") as sc2:
+            assert sc2.scheduler.transport.app_id.rsplit("-", 1)[1] != app_id.rsplit("-", 1)[1]
+
+
+def test_dynamic_allocation_grows_and_shrinks_the_application(cluster):
+    with AsyncSession(cluster.master_url, app_name="dyn", num_executors=1) as sc:
+        s = sc.scheduler
+        ds = sc.parallelize(range(40), 4)
+        assert len(set(ds.map(lambda x: os.getpid()).collect())) == 1
+        assert s.request_total_executors(3)
+        assert s.num_executors == 3 and _wait(lambda: sum(w["cores_used"] for w in cluster.state()["workers"]) == 3)
+        assert len(set(ds.map(lambda x: os.getpid()).collect())) == 3
+        assert ds.reduce(lambda a, b: a + b) == 780
+        assert s.request_total_executors(2)
+        assert _wait(lambda: sum(w["cores_used"] for w in cluster.state()["workers"]) == 2)
+        assert len(set(ds.map(lambda x: os.getpid()).collect())) == 2
+        assert s.executors_recovered == 0                       # released executors are not "lost"

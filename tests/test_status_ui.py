@@ -85,6 +85,9 @@ def test_ui_reports_block_manager_storage_for_cluster_masters():
         assert rdd[0]["num_cached_partitions"] == 4 and rdd[0]["executors"] == ["0", "1"]
         job = _get(f"{base}/jobs")[0]
         assert job["task_binary_bytes"] > 0 and job["result_bytes"] > 0
+        dump = _get(f"{base}/executors/1/threads")
+        assert any("run_tasks" in t["stack"] for t in dump) and any("heartbeat" in t["name"] for t in dump)
+        assert any("MainThread" == t["name"] for t in _get(f"{base}/executors/driver/threads"))
         t = _get(f"{base}/jobs/{job['job_id']}")["tasks"][0]
         assert {"serialize_ms", "deserialize_ms", "result_bytes"} <= set(t["metrics"])      # TaskMetrics
 
