@@ -95,7 +95,12 @@ _alias(workerState, getStaleness=lambda self: self.staleness, getAvailability=la
 _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partitions_with_index", getNumPartitions="get_num_partitions",
        treeAggregate="tree_aggregate", flatMap="flat_map", mapPartitions="map_partitions", foreachPartition="foreach_partition",
        reduceByKey="reduce_by_key", groupByKey="group_by_key", keyBy="key_by", mapValues="map_values", countByKey="count_by_key",
-       countByValue="count_by_value", sortBy="sort_by", takeSample="take_sample", zipWithUniqueId="zip_with_unique_id")
+       countByValue="count_by_value", sortBy="sort_by", takeSample="take_sample", zipWithUniqueId="zip_with_unique_id",
+       partitionBy="partition_by", combineByKey="combine_by_key", aggregateByKey="aggregate_by_key", foldByKey="fold_by_key",
+       leftOuterJoin="left_outer_join", rightOuterJoin="right_outer_join", fullOuterJoin="full_outer_join",
+       subtractByKey="subtract_by_key", sortByKey="sort_by_key", collectAsMap="collect_as_map", takeOrdered="take_ordered",
+       isEmpty="is_empty", randomSplit="random_split", saveAsTextFile="save_as_text_file", toLocalIterator="to_local_iterator",
+       setName="set_name", toDebugString="to_debug_string")
 _alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
        cancelJob=lambda self, job_id: self.scheduler.cancel_job(job_id), cancelAllJobs=lambda self: self.scheduler.cancel_all_jobs())
 

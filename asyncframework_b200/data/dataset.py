@@ -84,6 +84,7 @@ def _cache_put(ds_id: int, p: int, kind: str, value) -> None:
 # mllib/regression/LinearRegressionSuite.scala:152-166).
 _SOURCE_STORE: dict = {}
 _block_ids = itertools.count(1)
+_shuffle_ids = itertools.count(0)
 _pickle_ctx = threading.local()
 
 
@@ -519,20 +520,83 @@ class ShardedDataset:
     def foreach(self, f) -> None:
         self._run(lambda t, it: [f(r) for r in it] and None)
 
-    def _shuffle(self, num_partitions: Optional[int], map_side) -> "ShardedDataset":
-        """Hash shuffle at data-prep scale: each map task returns its output bucketed by target partition, the driver regroups
-        (the reference only shuffles while preparing data: repartition / reduceByKey, SparkASGDThread.scala:73,77)."""
-        P = int(num_partitions or self.num_partitions)
+    def _shuffle(self, num_partitions: Optional[int], map_side, partitioner=None) -> "ShardedDataset":
+        """Hash (or custom-partitioner) shuffle.
 
-        def part(t, it):
+        In-process masters: every map task returns its output bucketed by target partition and the driver regroups — the
+        executors share the driver's memory, nothing is copied twice.  Cluster masters (an :class:`AsyncEnv` exists): a real
+        shuffle (SortShuffleManager / MapOutputTracker / ShuffleBlockFetcherIterator) — map tasks serialise +
+        compress every non-empty bucket into a ``shuffle_<id>_<map>_<reduce>`` block of THEIR BlockManager and return only
+        the sizes (``MapStatus``); the driver keeps that table (``MapOutputTracker``) and ships it inside the reduce-side
+        lineage; reduce tasks fetch their column of blocks from the executors that hold them over the bulk chunk path
+        (local blocks are read directly).  A block that has vanished with its executor is recomputed from lineage by the
+        reducer (fetch-failure recovery)."""
+        P = int(num_partitions or self.num_partitions)
+        part_of = partitioner or (lambda k: _stable_hash(k) % P)
+        env = getattr(self.scheduler, "env", None)
+        if env is None:
+            def part(t, it):
+                buckets: List[list] = [[] for _ in range(P)]
+                for k, v in map_side(it):
+                    buckets[part_of(k)].append((k, v))
+                return buckets
+            outs = self._run(part)
+            merged = [[kv for b in outs for kv in b[q]] for q in range(P)]
+            blk = SourceBlock(merged)
+            return ShardedDataset(self.scheduler, P, lambda p, t: iter(blk.data[p]), None, None, "shuffled")
+
+        sid = next(_shuffle_ids)
+        parent = self
+
+        def bucketize(it):
             buckets: List[list] = [[] for _ in range(P)]
             for k, v in map_side(it):
-                buckets[_stable_hash(k) % P].append((k, v))
+                buckets[part_of(k)].append((k, v))
             return buckets
-        outs = self._run(part)
-        merged = [[kv for b in outs for kv in b[q]] for q in range(P)]
-        blk = SourceBlock(merged)
-        return ShardedDataset(self.scheduler, P, lambda p, t: iter(blk.data[p]), None, None, "shuffled")
+
+        def map_task(t, it):
+            from ..core.env import AsyncEnv
+            from ..storage.block_manager import StorageLevel
+            e = AsyncEnv.get()
+            sizes = []
+            for q, b in enumerate(bucketize(it)):
+                if not b:
+                    sizes.append(0)
+                    continue
+                data = e.codec.compress(e.serializer.dumps(b))
+                e.block_manager.put_bytes(f"shuffle_{sid}_{t.partition_id}_{q}", data, StorageLevel.MEMORY_AND_DISK_SER)
+                sizes.append(len(data))
+            return sizes
+        statuses = self._run(map_task)                       # MapOutputTracker: statuses[m][q] = bytes of block (m, q)
+        num_maps = self.num_partitions
+
+        def reduce_side(p, t):
+            from ..core.env import AsyncEnv
+            e = AsyncEnv.get()
+            for m in range(num_maps):
+                if statuses[m][p] == 0:
+                    continue
+                data = e.block_manager.get_bytes(f"shuffle_{sid}_{m}_{p}") if e is not None else None
+                if data is None:                              # FetchFailed: the map output died with its executor
+                    yield from bucketize(parent.iterator(m, t))[p]
+                    continue
+                yield from e.serializer.loads(e.codec.decompress(data))
+        ds = ShardedDataset(self.scheduler, P, reduce_side, None, None, f"shuffled[{sid}]")
+        ds.shuffle_id = sid
+        ds.map_output_bytes = [sum(s) for s in statuses]
+        return ds
+
+    def remove_shuffle(self) -> int:
+        """Drop this dataset's shuffle blocks on every executor (``ContextCleaner.doCleanupShuffle``)."""
+        sid, env = getattr(self, "shuffle_id", None), getattr(self.scheduler, "env", None)
+        if sid is None or env is None:
+            return 0
+        n = 0
+        for st in env.bm_master.storage_status().values():
+            for b in st["blocks"]:
+                if b.startswith(f"shuffle_{sid}_"):
+                    n += env.bm_master.remove_block(b)
+        return n
 
     def reduce_by_key(self, f, num_partitions: Optional[int] = None) -> "ShardedDataset":
         """``rdd.reduceByKey`` with map-side combining."""
@@ -606,6 +670,215 @@ class ShardedDataset:
         """``rdd.zipWithUniqueId``: ids k, k+P, k+2P, ... in partition k — unique without the counting job zip_with_index needs."""
         P = self.num_partitions
         return self._derive(lambda p, t: ((r, p + i * P) for i, r in enumerate(self.iterator(p, t))), None, "zip_with_unique_id")
+
+    # ------------------------------------------------------------------ more pair / set operations (PairRDDFunctions)
+    def partition_by(self, num_partitions: int, partitioner=None) -> "ShardedDataset":
+        """``rdd.partitionBy``: ``partitioner(key) -> partition`` (default: the process-independent hash)."""
+        return self._shuffle(num_partitions, lambda it: it, partitioner)
+
+    def combine_by_key(self, create, merge_value, merge_combiners, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``combineByKey`` with map-side combining — the primitive under reduce/aggregate/fold-ByKey."""
+        def map_side(it):
+            acc: dict = {}
+            for k, v in it:
+                acc[k] = merge_value(acc[k], v) if k in acc else create(v)
+            return acc.items()
+        sh = self._shuffle(num_partitions, map_side)
+
+        def compute(p, t):
+            acc: dict = {}
+            for k, c in sh.iterator(p, t):
+                acc[k] = merge_combiners(acc[k], c) if k in acc else c
+            return iter(list(acc.items()))
+        return sh._derive(compute, None, "combine_by_key")
+
+    def aggregate_by_key(self, zero_factory, seq_op, comb_op, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.combine_by_key(lambda v: seq_op(zero_factory(), v), seq_op, comb_op, num_partitions)
+
+    def fold_by_key(self, zero_factory, f, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.combine_by_key(lambda v: f(zero_factory(), v), f, f, num_partitions)
+
+    def cogroup(self, other: "ShardedDataset", num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``(k, (values of self, values of other))`` for every key of either side."""
+        P = int(num_partitions or max(self.num_partitions, other.num_partitions))
+        tagged = self.map(lambda kv: (kv[0], (0, kv[1]))).union(other.map(lambda kv: (kv[0], (1, kv[1]))))
+        sh = tagged._shuffle(P, lambda it: it)
+
+        def compute(p, t):
+            acc: dict = {}
+            for k, (side, v) in sh.iterator(p, t):
+                acc.setdefault(k, ([], []))[side].append(v)
+            return iter(list(acc.items()))
+        return sh._derive(compute, None, "cogroup")
+
+    def join(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.cogroup(other, num_partitions).flat_map(lambda kv: [(kv[0], (a, b)) for a in kv[1][0] for b in kv[1][1]])
+
+    def left_outer_join(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.cogroup(other, num_partitions).flat_map(
+            lambda kv: [(kv[0], (a, b)) for a in kv[1][0] for b in (kv[1][1] or [None])])
+
+    def right_outer_join(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.cogroup(other, num_partitions).flat_map(
+            lambda kv: [(kv[0], (a, b)) for b in kv[1][1] for a in (kv[1][0] or [None])])
+
+    def full_outer_join(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.cogroup(other, num_partitions).flat_map(
+            lambda kv: [(kv[0], (a, b)) for a in (kv[1][0] or [None]) for b in (kv[1][1] or [None])])
+
+    def subtract_by_key(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.cogroup(other, num_partitions).flat_map(lambda kv: [(kv[0], a) for a in kv[1][0]] if not kv[1][1] else [])
+
+    def subtract(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.map(lambda r: (r, None)).subtract_by_key(other.map(lambda r: (r, None)), num_partitions).keys()
+
+    def intersection(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        return self.map(lambda r: (r, None)).cogroup(other.map(lambda r: (r, None)), num_partitions) \
+            .filter(lambda kv: kv[1][0] and kv[1][1]).keys()
+
+    def cartesian(self, other: "ShardedDataset") -> "ShardedDataset":
+        """``rdd.cartesian``: partition (i, j) pairs partition i of self with partition j of other."""
+        n2 = other.num_partitions
+        left, right = self, other
+
+        def compute(p, t):
+            rs = list(right.iterator(p % n2, t))
+            return ((a, b) for a in left.iterator(p // n2, t) for b in rs)
+        return ShardedDataset(self.scheduler, self.num_partitions * n2, compute, None, None, "cartesian")
+
+    def sort_by_key(self, ascending: bool = True, num_partitions: Optional[int] = None, key=lambda k: k) -> "ShardedDataset":
+        """``sortByKey`` with a **range partitioner** built from a sample of the keys (RangePartitioner.sketch): partition q
+        holds keys between boundaries q-1 and q, each partition is sorted locally, so reading the partitions in order is the
+        total order — no driver-side sort of the data."""
+        P = int(num_partitions or self.num_partitions)
+        sample = sorted((key(k) for k in self.keys().sample(False, min(1.0, max(0.01, 20.0 * P / max(self.count(), 1))), 17).collect()))
+        bounds = [sample[len(sample) * (i + 1) // P] for i in range(P - 1)] if sample and P > 1 else []
+        import bisect
+
+        def partitioner(k):
+            q = bisect.bisect_right(bounds, key(k))
+            return q if ascending else (len(bounds) - q)
+        sh = self._shuffle(P, lambda it: it, partitioner)
+        return sh._derive(lambda p, t: iter(sorted(sh.iterator(p, t), key=lambda kv: key(kv[0]), reverse=not ascending)), None, "sort_by_key")
+
+    def lookup(self, k) -> list:
+        return self.filter(lambda kv: kv[0] == k).values().collect()
+
+    def collect_as_map(self) -> dict:
+        """``collectAsMap`` (PairRDDFunctions.scala:742; the samples build their partition-size table with it)."""
+        return dict(self.collect())
+
+    def fold(self, zero_factory, f):
+        return self.aggregate(zero_factory, f, f)
+
+    def take_ordered(self, n: int, key=lambda r: r) -> list:
+        import heapq
+        parts = self._run(lambda t, it: heapq.nsmallest(n, it, key=key))
+        return heapq.nsmallest(n, [r for part in parts for r in part], key=key)
+
+    def is_empty(self) -> bool:
+        return not any(self._run(lambda t, it: any(True for _ in it)))
+
+    def stats(self) -> dict:
+        """``rdd.stats()`` (StatCounter): count, mean, variance (population), stdev, min, max in one pass, merged with the
+        numerically stable parallel formula."""
+        def seq(a, x):
+            n, mean, m2, lo, hi = a
+            n += 1
+            d = x - mean
+            mean += d / n
+            m2 += d * (x - mean)
+            return (n, mean, m2, min(lo, x), max(hi, x))
+
+        def comb(a, b):
+            if a[0] == 0:
+                return b
+            if b[0] == 0:
+                return a
+            n = a[0] + b[0]
+            d = b[1] - a[1]
+            return (n, a[1] + d * b[0] / n, a[2] + b[2] + d * d * a[0] * b[0] / n, min(a[3], b[3]), max(a[4], b[4]))
+        n, mean, m2, lo, hi = self.aggregate(lambda: (0, 0.0, 0.0, float("inf"), float("-inf")), seq, comb)
+        var = m2 / n if n else float("nan")
+        return {"count": n, "mean": mean if n else float("nan"), "variance": var, "stdev": var ** 0.5 if n else float("nan"),
+                "min": lo, "max": hi, "sample_variance": m2 / (n - 1) if n > 1 else float("nan")}
+
+    def variance(self) -> float:
+        return self.stats()["variance"]
+
+    def stdev(self) -> float:
+        return self.stats()["stdev"]
+
+    def histogram(self, buckets):
+        """``rdd.histogram(n | boundaries)`` -> (boundaries, counts); the last bucket is closed on the right."""
+        import bisect
+        if isinstance(buckets, int):
+            st = self.stats()
+            lo, hi = st["min"], st["max"]
+            bounds = [lo + (hi - lo) * i / buckets for i in range(buckets + 1)] if hi > lo else [lo, lo]
+        else:
+            bounds = list(buckets)
+        nb = len(bounds) - 1
+
+        def seq(acc, x):
+            if bounds[0] <= x <= bounds[-1]:
+                acc[min(bisect.bisect_right(bounds, x) - 1, nb - 1)] += 1
+            return acc
+        counts = self.aggregate(lambda: [0] * nb, seq, lambda a, b: [x + y for x, y in zip(a, b)])
+        return bounds, counts
+
+    def random_split(self, weights: Sequence[float], seed: int = 17) -> List["ShardedDataset"]:
+        """``rdd.randomSplit``: disjoint samples whose sizes follow ``weights`` (one hash draw per record)."""
+        tot = float(sum(weights))
+        cuts = [sum(weights[:i + 1]) / tot for i in range(len(weights))]
+        indexed = self.zip_with_unique_id()
+
+        def pick(lo, hi):
+            return indexed.filter(lambda ri: lo <= (_stable_hash((seed, ri[1])) % 1_000_003) / 1_000_003 < hi).map(lambda ri: ri[0])
+        return [pick(0.0 if i == 0 else cuts[i - 1], cuts[i] if i < len(cuts) - 1 else 1.1) for i in range(len(cuts))]
+
+    def save_as_text_file(self, directory: str) -> None:
+        """``saveAsTextFile``: one ``part-<p>`` file per partition + ``_SUCCESS`` (readable back with ``sc.text_file``)."""
+        os.makedirs(directory, exist_ok=True)
+
+        def write(t, it):
+            with open(os.path.join(directory, f"part-{t.partition_id:05d}"), "w") as f:
+                for r in it:
+                    f.write(str(r) + "\n")
+            return t.partition_id
+        self._run(write)
+        open(os.path.join(directory, "_SUCCESS"), "w").close()
+
+    def to_local_iterator(self):
+        """``toLocalIterator``: one partition at a time (one job each), so the driver never holds more than a partition."""
+        for p in range(self.num_partitions):
+            yield from self._run(lambda t, it: list(it), [p])[0]
+
+    def set_name(self, name: str) -> "ShardedDataset":
+        self.name = name
+        return self
+
+    def to_debug_string(self) -> str:
+        """``rdd.toDebugString``: the lineage, one line per ancestor."""
+        lines, ds, depth = [], self, 0
+        while ds is not None:
+            flags = [f"{ds.num_partitions} partitions"] + (["cached"] if ds._want_cache else []) + (["columnar"] if ds.batch_capable else [])
+            lines.append(" " * (2 * depth) + ("+- " if depth else "") + f"{ds.name} [{', '.join(flags)}]")
+            ds, depth = ds.parent, depth + 1
+        return "\n".join(lines)
+
+    def unpersist(self) -> "ShardedDataset":
+        """Drop the cached partitions everywhere (driver lists, executor dicts, executor BlockManagers)."""
+        self._want_cache = False
+        with self._cache_lock:
+            self._cached_batches = None
+            self._cached_records = None
+        for k in [k for k in list(_BLOCK_STORE) if k[0] == self.ds_id]:
+            _BLOCK_STORE.pop(k, None)
+        env = getattr(self.scheduler, "env", None)
+        if env is not None:
+            env.bm_master.remove_rdd(self.ds_id)
+        return self
 
     # ------------------------------------------------------------------ blocking actions
     def _run(self, func, partitions=None):

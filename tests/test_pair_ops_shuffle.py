@@ -1,0 +1,99 @@
+"""Wider RDD surface (PairRDDFunctionsSuite / RDDSuite / SortingSuite / ShuffleSuite scenarios) on the in-process master,
+and the block-manager shuffle on executor processes."""
+import math
+import os
+
+import pytest
+
+from asyncframework_b200 import AsyncSession
+
+
+@pytest.fixture(scope="module")
+def sc():
+    with AsyncSession("local[3]") as s:
+        yield s
+
+
+def test_joins_cogroup_and_set_operations(sc):
+    a = sc.parallelize([(1, "a"), (2, "b"), (2, "bb"), (3, "c")], 3)
+    b = sc.parallelize([(2, "x"), (3, "y"), (3, "yy"), (4, "z")], 2)
+    assert sorted(a.join(b).collect()) == [(2, ("b", "x")), (2, ("bb", "x")), (3, ("c", "y")), (3, ("c", "yy"))]
+    assert sorted(a.left_outer_join(b).collect())[0] == (1, ("a", None))
+    assert (4, (None, "z")) in a.right_outer_join(b).collect()
+    assert sorted(k for k, _ in a.full_outer_join(b).collect()) == [1, 2, 2, 3, 3, 4]
+    cg = dict(a.cogroup(b).collect())
+    assert sorted(cg[2][0]) == ["b", "bb"] and cg[2][1] == ["x"] and cg[1] == (["a"], []) and cg[4] == ([], ["z"])
+    assert sorted(a.subtract_by_key(b).collect()) == [(1, "a")]
+    x, y = sc.parallelize(range(10), 3), sc.parallelize(range(5, 15), 2)
+    assert sorted(x.subtract(y).collect()) == [0, 1, 2, 3, 4] and sorted(x.intersection(y).collect()) == [5, 6, 7, 8, 9]
+    assert sorted(sc.parallelize([1, 2], 2).cartesian(sc.parallelize("ab", 2)).collect()) == [(1, "a"), (1, "b"), (2, "a"), (2, "b")]
+    assert a.lookup(2) == ["b", "bb"] and a.collect_as_map()[3] == "c"
+
+
+def test_combine_aggregate_fold_by_key_and_partition_by(sc):
+    kv = sc.parallelize([(i % 4, i) for i in range(40)], 4)
+    assert dict(kv.aggregate_by_key(lambda: (0, 0), lambda a, v: (a[0] + v, a[1] + 1), lambda a, b: (a[0] + b[0], a[1] + b[1])).collect()) == \
+        {k: (sum(i for i in range(40) if i % 4 == k), 10) for k in range(4)}
+    assert dict(kv.fold_by_key(lambda: 0, lambda a, b: a + b).collect())[1] == sum(range(1, 40, 4))
+    assert dict(kv.combine_by_key(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b).map_values(len).collect()) == {k: 10 for k in range(4)}
+    pb = kv.partition_by(2, lambda k: k % 2)
+    assert [sorted({k for k, _ in part}) for part in pb.glom().collect()] == [[0, 2], [1, 3]]
+
+
+def test_sort_by_key_uses_a_range_partitioner(sc):
+    import random
+    rng = random.Random(3)
+    data = [(rng.randrange(10_000), i) for i in range(2000)]
+    srt = sc.parallelize(data, 4).sort_by_key(num_partitions=4)
+    parts = srt.glom().collect()
+    assert [k for k, _ in srt.collect()] == sorted(k for k, _ in data)                 # concatenation IS the total order
+    assert all(len(p) > 200 for p in parts)                                             # roughly balanced ranges
+    assert all(parts[i][-1][0] <= parts[i + 1][0][0] for i in range(3))
+    desc = sc.parallelize(data, 4).sort_by_key(ascending=False).keys().collect()
+    assert desc == sorted((k for k, _ in data), reverse=True)
+
+
+def test_numeric_actions_and_misc(sc, tmp_path):
+    ds = sc.parallelize([1.0, 2.0, 3.0, 4.0, 10.0], 3)
+    st = ds.stats()
+    assert st["count"] == 5 and st["mean"] == 4.0 and math.isclose(st["variance"], 10.0) and st["min"] == 1.0 and st["max"] == 10.0
+    assert math.isclose(ds.stdev(), math.sqrt(10.0)) and math.isclose(st["sample_variance"], 12.5)
+    assert ds.histogram([0, 2, 4, 10]) == ([0, 2, 4, 10], [1, 2, 2]) and ds.histogram(3)[1] == [3, 1, 1]
+    assert ds.fold(lambda: 0.0, lambda a, b: a + b) == 20.0 and ds.take_ordered(2) == [1.0, 2.0]
+    assert not ds.is_empty() and sc.parallelize([], 2).is_empty()
+    a, b = sc.parallelize(range(1000), 4).random_split([0.7, 0.3], seed=5)
+    na, nb = a.count(), b.count()
+    assert na + nb == 1000 and 620 < na < 780 and not set(a.collect()) & set(b.collect())
+    out = str(tmp_path / "txt")
+    sc.parallelize(range(10), 3).save_as_text_file(out)
+    assert sorted(os.listdir(out)) == ["_SUCCESS", "part-00000", "part-00001", "part-00002"]
+    assert sorted(int(l) for l in sc.text_file(out + "/part-00001").collect() + sc.text_file(out + "/part-00000").collect()
+                  + sc.text_file(out + "/part-00002").collect()) == list(range(10))
+    assert list(sc.parallelize(range(7), 3).to_local_iterator()) == list(range(7))
+    lin = sc.parallelize(range(4), 2).map(lambda x: x).filter(lambda x: True).cache().set_name("final")
+    dbg = lin.to_debug_string().splitlines()
+    assert dbg[0].startswith("final [2 partitions, cached]") and len(dbg) == 3 and dbg[2].lstrip().startswith("+- records")
+    assert lin.count() == 4 and lin._cached_records is not None
+    assert lin.unpersist()._cached_records is None and lin.count() == 4
+
+
+def test_shuffle_goes_through_executor_block_managers_on_cluster_masters():
+    with AsyncSession("local-cluster[2]") as sc:
+        kv = sc.parallelize([(i % 10, i) for i in range(1000)], 4)
+        red = kv.reduce_by_key(lambda a, b: a + b, 3)
+        assert dict(red.collect()) == {k: sum(i for i in range(1000) if i % 10 == k) for k in range(10)}
+        sh = red.parent
+        assert sh.shuffle_id is not None and sum(sh.map_output_bytes) > 0
+        st = sc.scheduler.storage_status()
+        blocks = {b: m.executor_id for m, s in st.items() for b in s["blocks"] if b.startswith(f"shuffle_{sh.shuffle_id}_")}
+        assert blocks and set(blocks.values()) == {"0", "1"}                         # written where the map tasks ran
+        assert all(b.count("_") == 3 for b in blocks)
+        # the driver never saw the records: only MapStatus sizes came back from the map stage
+        j = sc.parallelize([(k, str(k)) for k in range(10)], 2).join(red)
+        assert sorted(j.collect())[3] == (3, ("3", sum(i for i in range(1000) if i % 10 == 3)))
+        # fetch failure: a map output disappears -> the reducer recomputes that bucket from lineage
+        victim = sorted(blocks)[0]
+        assert sc.scheduler.env.bm_master.remove_block(victim) == 1
+        assert dict(red.collect())[7] == sum(i for i in range(1000) if i % 10 == 7)
+        assert sh.remove_shuffle() >= len(blocks) - 1
+        assert not any(b.startswith(f"shuffle_{sh.shuffle_id}_") for s in sc.scheduler.storage_status().values() for b in s["blocks"])
