@@ -470,6 +470,17 @@ class ClusterScheduler:
                 return
             if partition not in job["pending"]:
                 return
+            if "BlockMissing" in data and job.get("reshipped", 0) < 2 * self.num_executors:
+                # the executor was sent a block REFERENCE for data it does not hold (a replacement that raced with the
+                # bookkeeping of its predecessor's loss): forget what we think it holds and re-ship the binary with the data
+                job["reshipped"] = job.get("reshipped", 0) + 1
+                with self._lock:
+                    for held in self._blocks_held.values():
+                        held.discard(eid)
+                if eid in job["executors"]:
+                    job["executors"].remove(eid)
+                self._launch(job_id, job, partition, attempt, eid)
+                return
             attempt += 1
             self.listeners.post({"event": "task_failed", "job": job_id, "partition": partition, "attempt": attempt,
                                  "executor": eid, "error": data})

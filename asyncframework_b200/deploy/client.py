@@ -123,6 +123,9 @@ class StandaloneTransport:
 
     def send(self, eid: int, msg: tuple) -> None:
         ref = self.refs.get(eid)
+        if ref is None and self.sched is not None and self.sched.recover_lost_executors and not self.sched._stopped:
+            self.relaunch(eid)                 # the Master is re-filling the slot: wait for the replacement to register
+            ref = self.refs.get(eid)
         if ref is None:
             raise OSError(f"executor slot {eid} is down")
         ref.send(msg)

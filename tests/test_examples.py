@@ -38,3 +38,17 @@ def test_straggler_sweep_example():
     rows = [l.split() for l in out.strip().splitlines()[1:]]
     assert len(rows) == 8 and {r[0] for r in rows} == {"asaga", "saga_sync"}
     assert all(int(r[4]) > 0 for r in rows)
+
+
+def test_standalone_cluster_example_survives_a_killed_executor():
+    out = _run("standalone_cluster.py")
+    last = out.strip().splitlines()[-1]
+    assert "executors recovered: 1" in last and "FAILED" not in last
+    first, final = (float(x) for x in last.split("objective ")[1].split(" after")[0].split(" -> "))
+    assert final < 0.1 * first
+
+
+def test_python_api_example_on_a_local_cluster_master():
+    out = _run("async_sgd_python_api.py", "--updates", "60", "--master", "local-cluster[2]")
+    last = out.strip().splitlines()[-1]
+    assert "objective" in last and float(last.split()[-1]) < 0.1
