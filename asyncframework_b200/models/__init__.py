@@ -1,7 +1,7 @@
 from .glm import (GeneralizedLinearAlgorithm, GeneralizedLinearModel, LassoModel, LassoWithSGD,
                   LinearRegressionModel, LinearRegressionWithSGD, LogisticRegressionModel,
-                  LogisticRegressionWithSGD, RidgeRegressionModel, RidgeRegressionWithSGD, SVMModel, SVMWithSGD)
+                  LogisticRegressionWithLBFGS, LogisticRegressionWithSGD, RidgeRegressionModel, RidgeRegressionWithSGD, SVMModel, SVMWithSGD)
 
 __all__ = ["GeneralizedLinearAlgorithm", "GeneralizedLinearModel", "LassoModel", "LassoWithSGD",
            "LinearRegressionModel", "LinearRegressionWithSGD", "LogisticRegressionModel",
-           "LogisticRegressionWithSGD", "RidgeRegressionModel", "RidgeRegressionWithSGD", "SVMModel", "SVMWithSGD"]
+           "LogisticRegressionWithLBFGS", "LogisticRegressionWithSGD", "RidgeRegressionModel", "RidgeRegressionWithSGD", "SVMModel", "SVMWithSGD"]

@@ -348,6 +348,34 @@ class LogisticRegressionWithSGD(GeneralizedLinearAlgorithm):
         return alg.run(data, initial_weights)
 
 
+class LogisticRegressionWithLBFGS(GeneralizedLinearAlgorithm):
+    """``LogisticRegressionWithLBFGS`` (mllib/classification/LogisticRegression.scala:281-300, binary case): LogisticGradient +
+    SquaredL2Updater under L-BFGS, **feature scaling on** — the one algorithm of the family that turns it on
+    (GeneralizedLinearAlgorithm.scala:281) because the quasi-Newton iteration converges much faster on unit-variance
+    columns; the weights are mapped back to the original scale afterwards."""
+    model_class = LogisticRegressionModel
+
+    def __init__(self, reg_param: float = 0.0, num_corrections: int = 10, convergence_tol: float = 1e-6, max_iterations: int = 100):
+        super().__init__()
+        from ..optim.lbfgs import LBFGS
+        self.optimizer = (LBFGS(LogisticGradient(), SquaredL2Updater()).set_reg_param(reg_param).set_num_corrections(num_corrections)
+                          .set_convergence_tol(convergence_tol).set_max_num_iterations(max_iterations))
+        self.validators = [_binary_label_validator]
+        self.set_feature_scaling(True)
+
+    def _post_train(self, model):
+        model.weight_history = self.optimizer.get_all_weights()
+        model.loss_history = list(self.optimizer.loss_history)
+
+    @classmethod
+    def train(cls, data, iterations: int = 100, initial_weights=None, reg_param: float = 0.0, reg_type: Optional[str] = "l2",
+              intercept: bool = False, corrections: int = 10, tolerance: float = 1e-6, validate_data: bool = True):
+        """PySpark signature (python/pyspark/mllib/classification.py ``LogisticRegressionWithLBFGS.train``)."""
+        alg = cls(reg_param if reg_type is not None else 0.0, corrections, tolerance, iterations)
+        alg.set_intercept(intercept).set_validate_data(validate_data)
+        return alg.run(data, initial_weights)
+
+
 class SVMWithSGD(GeneralizedLinearAlgorithm):
     model_class = SVMModel
 

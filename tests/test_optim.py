@@ -144,3 +144,60 @@ def test_feature_scaling_path(scheduler):
     alg.set_feature_scaling(True)
     m = alg.run(ds)
     assert np.abs(m.weights.numpy() - w / np.array([1.0, 10.0, 0.1])).max() < 0.2
+
+
+# ---- L-BFGS (LBFGSSuite scenarios: loss decreasing, agrees with GD, regularisation, convergence tolerance) ----------------
+def _logistic_data(sched, n=600, d=5, seed=3):
+    import numpy as np
+    from asyncframework_b200.data import ShardedDataset
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d)) * np.array([1.0, 5.0, 0.2, 2.0, 1.0])          # badly scaled columns
+    w_true = np.array([1.5, -0.4, 3.0, 0.0, -1.0])
+    y = (rng.random(n) < 1 / (1 + np.exp(-(X @ w_true)))).astype(np.float64)
+    return ShardedDataset.from_arrays(sched, X, y, 3).cache(), X, y
+
+
+def test_lbfgs_loss_is_monotone_and_reaches_the_optimum_gd_creeps_towards():
+    from asyncframework_b200.core.scheduler import Scheduler
+    from asyncframework_b200.optim import LBFGS, GradientDescent, LogisticGradient, SquaredL2Updater, run_lbfgs
+    with Scheduler(3) as s:
+        data, X, y = _logistic_data(s)
+        w0 = torch.zeros(5, dtype=torch.float64)
+        opt = LBFGS(LogisticGradient(), SquaredL2Updater()).set_reg_param(0.01).set_max_num_iterations(60).set_convergence_tol(1e-10)
+        w = opt.optimize(data, w0)
+        h = opt.loss_history
+        assert all(b <= a + 1e-12 for a, b in zip(h, h[1:])) and h[-1] < 0.8 * h[0]
+        # first-order optimality of the regularised objective: (1/n) X^T (sigmoid(Xw) - y) + lambda w = 0
+        Xt, yt = torch.from_numpy(X), torch.from_numpy(y)
+        grad = Xt.T @ (torch.sigmoid(Xt @ w) - yt) / len(y) + 0.01 * w
+        assert float(grad.abs().max()) < 1e-5
+        assert opt.cost_evaluations < 4 * len(h) + 5                                  # the line search rarely backtracks
+        # plain GD on the same objective needs far more passes to get equally close
+        gd = (GradientDescent(LogisticGradient(), SquaredL2Updater()).set_step_size(0.05).set_num_iterations(len(h))
+              .set_reg_param(0.01).set_convergence_tol(0.0))
+        w_gd = gd.optimize(data, w0)
+        f = lambda v: float(torch.nn.functional.binary_cross_entropy_with_logits(Xt @ v, yt) + 0.005 * (v ** 2).sum())  # noqa: E731
+        assert f(w) < f(w_gd) - 1e-4
+        w2, hist2 = run_lbfgs(data, LogisticGradient(), SquaredL2Updater(), 10, 1e-10, 60, 0.01, w0)
+        assert torch.allclose(w2, w) and hist2 == h
+        loose = LBFGS(LogisticGradient(), SquaredL2Updater()).set_convergence_tol(0.1)
+        loose.optimize(data, w0)
+        assert len(loose.loss_history) < len(h)                                        # tolerance stops it early
+        with pytest.raises(ValueError):
+            LBFGS(LogisticGradient(), SquaredL2Updater()).set_num_corrections(0)
+
+
+def test_logistic_regression_with_lbfgs_scales_features_and_predicts():
+    from asyncframework_b200.core.scheduler import Scheduler
+    from asyncframework_b200.models import LogisticRegressionWithLBFGS, LogisticRegressionWithSGD
+    with Scheduler(3) as s:
+        data, X, y = _logistic_data(s, n=800)
+        m = LogisticRegressionWithLBFGS.train(data, iterations=50, intercept=True)
+        acc = float((m.predict(torch.from_numpy(X)) == torch.from_numpy(y)).double().mean())
+        m_sgd = LogisticRegressionWithSGD.train(data, iterations=50, step=1.0, intercept=True)
+        acc_sgd = float((m_sgd.predict(torch.from_numpy(X)) == torch.from_numpy(y)).double().mean())
+        import numpy as np
+        oracle = float(((X @ np.array([1.5, -0.4, 3.0, 0.0, -1.0]) > 0) == (y > 0.5)).mean())     # the generating weights
+        assert acc >= oracle - 0.02 and acc >= acc_sgd - 0.01
+        assert len(m.loss_history) >= 3 and m.loss_history[-1] < m.loss_history[0]
+        assert abs(float(m.weights[2])) > abs(float(m.weights[1]))          # back on the ORIGINAL scale: col 2 has the big true weight
