@@ -77,7 +77,9 @@ def make_scheduler(cfg: AsyncConfig, device: torch.device) -> Scheduler:
         # ``--master`` / ``spark.master``: the driver's closures run in executor processes (forked locally or by standalone
         # Workers); the data then lives on the CPU of those processes — GPU training at scale is the fused backend's job
         from ..core.session import AsyncSession
-        sess = AsyncSession(master, app_name=f"{cfg.algorithm}", conf=cfg)
+        from ..conf import AsyncConf
+        rc = AsyncConf()                                    # submit exported --name / --conf as AFB_CONF_* (system properties)
+        sess = AsyncSession(master, app_name=None if rc.contains("spark.app.name") else cfg.algorithm, conf=cfg, runtime_conf=rc)
         sess.scheduler.block_first_async_job = bool(cfg.extra.get("block_first_async_job", True))
         sess.scheduler._owning_session = sess
         return sess.scheduler
