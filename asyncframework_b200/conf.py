@@ -107,6 +107,7 @@ WORKER_TIMEOUT = _entry("spark.worker.timeout", parse_time, 60.0, "master declar
 LOCAL_DIR = _entry("spark.local.dir", str, "", "scratch directory of the disk block store (empty = system temp)")
 AUTH = _entry("spark.authenticate", _parse_bool, False, "require the shared secret on every RPC connection")
 AUTH_SECRET = _entry("spark.authenticate.secret", str, "", "the shared secret")
+CRYPTO = _entry("spark.network.crypto.enabled", _parse_bool, False, "AES-256-GCM on every RPC / block-transfer frame (needs spark.authenticate)")
 SPECULATION = _entry("spark.speculation", _parse_bool, False, "re-launch slow tasks speculatively (TaskSetManager.scala:64-70)")
 SPECULATION_MULTIPLIER = _entry("spark.speculation.multiplier", float, 1.5, "how many times slower than the median a task must be", _pos)
 SPECULATION_QUANTILE = _entry("spark.speculation.quantile", float, 0.75, "fraction of tasks that must finish before speculating", lambda v: 0 < v <= 1)
@@ -260,6 +261,8 @@ class AsyncConf:
         """``SparkConf.validateSettings``: cross-field checks."""
         if self.get("spark.authenticate") and not self.get("spark.authenticate.secret"):
             raise ValueError("spark.authenticate is on but spark.authenticate.secret is not set")
+        if self.get("spark.network.crypto.enabled") and not self.get("spark.authenticate"):
+            raise ValueError("spark.network.crypto.enabled requires spark.authenticate=true and a secret")
         if self.get("spark.task.maxDirectResultSize") > self.get("spark.driver.maxResultSize") > 0:
             raise ValueError("spark.task.maxDirectResultSize must not exceed spark.driver.maxResultSize")
         for k, v in self._settings.items():
@@ -280,7 +283,8 @@ class AsyncConf:
             compression_codec=g("spark.io.compression.codec"), serializer=g("spark.serializer"),
             local_dir=g("spark.local.dir") or None, network_timeout=g("spark.network.timeout"),
             heartbeat_interval=g("spark.executor.heartbeatInterval"),
-            auth_secret=(g("spark.authenticate.secret") or None) if g("spark.authenticate") else None)
+            auth_secret=(g("spark.authenticate.secret") or None) if g("spark.authenticate") else None,
+            encrypt=bool(g("spark.network.crypto.enabled") and g("spark.authenticate")))
 
     @staticmethod
     def describe() -> str:

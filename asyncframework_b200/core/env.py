@@ -35,6 +35,7 @@ class RuntimeLimits:
     network_timeout: float = 120.0                 # spark.network.timeout (also: executor heartbeat expiry)
     heartbeat_interval: float = 10.0               # spark.executor.heartbeatInterval
     auth_secret: Optional[str] = None              # spark.authenticate.secret
+    encrypt: bool = False                          # spark.network.crypto.enabled (AES-GCM on every RPC / block-transfer frame)
 
 
 class AsyncEnv:
@@ -76,7 +77,7 @@ class AsyncEnv:
     def create_driver(cls, limits: Optional[RuntimeLimits] = None, host: str = "127.0.0.1", port: int = 0,
                       name: str = "driver") -> "AsyncEnv":
         limits = limits or RuntimeLimits()
-        rpc = RpcEnv(name, host, port, secret=limits.auth_secret)
+        rpc = RpcEnv(name, host, port, secret=limits.auth_secret, encrypt=limits.encrypt)
         master_ep = BlockManagerMasterEndpoint()
         master_ref = rpc.setup_endpoint(BlockManagerMasterEndpoint.NAME, master_ep)
         bm = BlockManager("driver", rpc, master_ref, limits.storage_memory, limits.local_dir, limits.network_timeout)
@@ -91,7 +92,7 @@ class AsyncEnv:
     def create_executor(cls, executor_id: str, driver_address, limits: Optional[RuntimeLimits] = None,
                         host: str = "127.0.0.1", port: int = 0) -> "AsyncEnv":
         limits = limits or RuntimeLimits()
-        rpc = RpcEnv(f"executor-{executor_id}", host, port, secret=limits.auth_secret)
+        rpc = RpcEnv(f"executor-{executor_id}", host, port, secret=limits.auth_secret, encrypt=limits.encrypt)
         master_ref: RpcEndpointRef = rpc.endpoint_ref(driver_address, BlockManagerMasterEndpoint.NAME)
         bm = BlockManager(str(executor_id), rpc, master_ref, limits.storage_memory, limits.local_dir, limits.network_timeout)
         rpc.setup_endpoint(BlockUploadEndpoint.NAME, BlockUploadEndpoint(bm))

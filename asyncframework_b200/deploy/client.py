@@ -246,14 +246,15 @@ class LocalStandaloneCluster:
 
     def __init__(self, num_workers: int = 2, cores_per_worker: int = 1, memory_per_worker: int = 1024,
                  worker_timeout: float = 60.0, heartbeat_interval: float = 1.0, secret: Optional[str] = None,
-                 recovery_dir: Optional[str] = None):
-        self._master_args = dict(worker_timeout=worker_timeout, secret=secret, recovery_dir=recovery_dir, recovery_grace=1.5)
+                 recovery_dir: Optional[str] = None, encrypt: bool = False):
+        self._master_args = dict(worker_timeout=worker_timeout, secret=secret, recovery_dir=recovery_dir, recovery_grace=1.5,
+                                 encrypt=encrypt)
         self.master_env, self.master = start_master("127.0.0.1", 0, **self._master_args)
         self.master_url = f"spark://{self.master_env.address}"
         self.worker_envs, self.workers = [], []
         for i in range(num_workers):
             e, w = start_worker(self.master_url, cores_per_worker, memory_per_worker, heartbeat_interval=heartbeat_interval,
-                                secret=secret, worker_id=f"worker-{i}")
+                                secret=secret, worker_id=f"worker-{i}", encrypt=encrypt)
             self.worker_envs.append(e)
             self.workers.append(w)
 

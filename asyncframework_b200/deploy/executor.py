@@ -26,6 +26,7 @@ def main(argv=None) -> int:
     ap.add_argument("--worker-url", default="")
     ap.add_argument("--host", default="127.0.0.1")
     ap.add_argument("--secret", default=None)
+    ap.add_argument("--encrypt", action="store_true")
     a = ap.parse_args(argv)
 
     import torch
@@ -36,7 +37,7 @@ def main(argv=None) -> int:
 
     driver_addr = RpcAddress.parse(a.driver_url)
     # the driver's limits arrive with the registration reply; start with defaults sized by the worker's grant
-    limits = RuntimeLimits(auth_secret=a.secret)
+    limits = RuntimeLimits(auth_secret=a.secret, encrypt=a.encrypt)
     mem_mb = int(os.environ.get("AFB_EXECUTOR_MEMORY_MB", "0") or 0)
     if mem_mb:
         limits.storage_memory = int(mem_mb * (1 << 20) * 0.6)          # spark.memory.fraction of the executor's grant

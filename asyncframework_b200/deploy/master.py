@@ -404,9 +404,9 @@ class Master(RpcEndpoint):
 
 
 def start_master(host: str = "127.0.0.1", port: int = 7077, worker_timeout: float = 60.0, secret: Optional[str] = None,
-                 spread_out: bool = True, recovery_dir: Optional[str] = None, recovery_grace: float = 2.0):
+                 spread_out: bool = True, recovery_dir: Optional[str] = None, recovery_grace: float = 2.0, encrypt: bool = False):
     """Returns ``(rpc_env, master_endpoint)``; the URL is ``spark://<rpc_env.address>``."""
-    env = RpcEnv("master", host, port, secret=secret)
+    env = RpcEnv("master", host, port, secret=secret, encrypt=encrypt)
     master = Master(worker_timeout, spread_out, recovery_dir, recovery_grace)
     env.setup_endpoint(Master.NAME, master)
     return env, master
@@ -420,8 +420,9 @@ def main(argv=None) -> None:
     ap.add_argument("--worker-timeout", type=float, default=60.0)
     ap.add_argument("--secret", default=None)
     ap.add_argument("--recovery-dir", default=None, help="persist registrations here and recover them after a restart")
+    ap.add_argument("--encrypt", action="store_true", help="AES-GCM on every connection (needs --secret)")
     a = ap.parse_args(argv)
-    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret, recovery_dir=a.recovery_dir)
+    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret, recovery_dir=a.recovery_dir, encrypt=a.encrypt)
     print(f"Master started at spark://{env.address}", flush=True)
     if a.webui_port:
         from ..utils.status_server import serve_json

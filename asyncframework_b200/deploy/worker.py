@@ -42,6 +42,8 @@ class ExecutorRunner:
                "--app-id", self.app_id, "--worker-url", str(self.worker.rpc_env.address), "--host", self.worker.host]
         if self.worker.secret:
             cmd += ["--secret", self.worker.secret]
+        if self.worker.encrypt:
+            cmd += ["--encrypt"]
         env = dict(os.environ)
         root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
@@ -104,7 +106,8 @@ class Worker(RpcEndpoint):
 
     def __init__(self, master_url: str, cores: int, memory_mb: int, work_dir: Optional[str] = None,
                  heartbeat_interval: float = 15.0, host: str = "127.0.0.1", gpu: Optional[int] = None,
-                 secret: Optional[str] = None, worker_id: Optional[str] = None):
+                 secret: Optional[str] = None, worker_id: Optional[str] = None, encrypt: bool = False):
+        self.encrypt = encrypt
         self.master_address = RpcAddress.parse(master_url)
         self.cores, self.memory_mb = int(cores), int(memory_mb)
         self.host, self.gpu, self.secret = host, gpu, secret
@@ -199,7 +202,7 @@ class Worker(RpcEndpoint):
 def start_worker(master_url: str, cores: int = 1, memory_mb: int = 1024, host: str = "127.0.0.1", port: int = 0,
                  wait_registered: float = 10.0, **kw):
     """Returns ``(rpc_env, worker_endpoint)``."""
-    env = RpcEnv("worker", host, port, secret=kw.get("secret"))
+    env = RpcEnv("worker", host, port, secret=kw.get("secret"), encrypt=kw.get("encrypt", False))
     worker = Worker(master_url, cores, memory_mb, host=host, **kw)
     env.setup_endpoint(Worker.NAME, worker)
     if wait_registered:
@@ -217,8 +220,10 @@ def main(argv=None) -> None:
     ap.add_argument("--work-dir", default=None)
     ap.add_argument("--gpu", type=int, default=None, help="CUDA device index given to this worker's executors")
     ap.add_argument("--secret", default=None)
+    ap.add_argument("--encrypt", action="store_true")
     a = ap.parse_args(argv)
-    env, worker = start_worker(a.master, a.cores, a.memory, a.host, a.port, work_dir=a.work_dir, gpu=a.gpu, secret=a.secret)
+    env, worker = start_worker(a.master, a.cores, a.memory, a.host, a.port, work_dir=a.work_dir, gpu=a.gpu, secret=a.secret,
+                               encrypt=a.encrypt)
     print(f"Worker {worker.id} started at {env.address}, registered={worker.registered.is_set()}", flush=True)
     try:
         while True:

@@ -17,7 +17,8 @@ Design (not a transcription of Netty):
     frames are raw bytes (no serialisation on the bulk path);
   * a HELLO handshake advertises the dialer's own listening address (so the callee can ``send`` back and so
     ``on_disconnected`` reports a meaningful peer) and optionally proves knowledge of a shared secret
-    (HMAC-SHA256 over a server nonce — the role of ``spark.authenticate`` / SASL, common/network-common sasl/);
+    (HMAC-SHA256 over a server nonce — the role of ``spark.authenticate`` / SASL, common/network-common sasl/) and can
+    switch the connection to AES-256-GCM (``encrypt=True``; ``spark.network.crypto.enabled``, network-common crypto/);
   * every endpoint owns an inbox thread: messages to one endpoint are processed sequentially, different endpoints
     run concurrently (``ThreadSafeRpcEndpoint`` semantics);
   * connection loss fails all outstanding asks on that connection with :class:`RpcDisconnected` and posts
@@ -243,15 +244,31 @@ class _Connection:
         self.pending_lock = threading.Lock()
         self.closed = False
         self.reader: Optional[threading.Thread] = None
+        self._enc = self._dec = None            # AES-GCM ciphers per direction once the handshake enabled encryption
+        self._enc_ctr = self._dec_ctr = 0
         sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+
+    def enable_encryption(self, secret: bytes, nonce: bytes, dialed: bool) -> None:
+        """AES-256-GCM for every frame body after the handshake (``spark.network.crypto.enabled``, common/network-common
+        crypto/): one key per direction from HKDF(secret, nonce); the GCM nonce is the frame counter, the frame type and
+        request id are authenticated as associated data, so a tampered or replayed frame fails to decrypt."""
+        from cryptography.hazmat.primitives import hashes
+        from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+        from cryptography.hazmat.primitives.kdf.hkdf import HKDF
+        okm = HKDF(algorithm=hashes.SHA256(), length=64, salt=nonce, info=b"afb-rpc-v1").derive(secret)
+        c2s, s2c = AESGCM(okm[:32]), AESGCM(okm[32:])
+        self._enc, self._dec = (c2s, s2c) if dialed else (s2c, c2s)
 
     def send_frame(self, ftype: int, req_id: int, body: bytes) -> None:
         if len(body) >= MAX_FRAME:
             raise RpcError(f"frame of {len(body)} bytes exceeds the 2 GiB frame limit")
-        hdr = _HDR.pack(len(body), ftype, req_id)
         with self.send_lock:
             if self.closed:
                 raise OSError("connection closed")
+            if self._enc is not None:
+                body = self._enc.encrypt(self._enc_ctr.to_bytes(12, "big"), bytes(body), struct.pack("!BQ", ftype, req_id))
+                self._enc_ctr += 1
+            hdr = _HDR.pack(len(body), ftype, req_id)
             if len(body) <= 65536:
                 self.sock.sendall(hdr + bytes(body))
             else:                      # bulk path: no concatenation copy of a multi-MiB piece
@@ -271,7 +288,15 @@ class _Connection:
 
     def recv_frame(self) -> Tuple[int, int, bytearray]:
         length, ftype, req_id = _HDR.unpack(self.recv_exact(_HDR.size))
-        return ftype, req_id, (self.recv_exact(length) if length else bytearray())
+        body = self.recv_exact(length) if length else bytearray()
+        if self._dec is not None:
+            from cryptography.exceptions import InvalidTag
+            try:
+                body = bytearray(self._dec.decrypt(self._dec_ctr.to_bytes(12, "big"), bytes(body), struct.pack("!BQ", ftype, req_id)))
+            except InvalidTag:
+                raise ConnectionError("frame failed authentication (tampered, replayed or wrong key)") from None
+            self._dec_ctr += 1
+        return ftype, req_id, body
 
     def start_reader(self) -> None:
         self.reader = threading.Thread(target=self._read_loop, daemon=True, name=f"rpc-conn-{self.env.name}-{self.peer}")
@@ -317,10 +342,13 @@ class RpcEnv:
     _req_ids = itertools.count(1)
 
     def __init__(self, name: str = "rpc", host: str = "127.0.0.1", port: int = 0, server: bool = True,
-                 secret: Optional[str] = None, connect_timeout: float = 10.0):
+                 secret: Optional[str] = None, connect_timeout: float = 10.0, encrypt: bool = False):
         global _default_env
         self.name = name
         self.secret = secret.encode() if isinstance(secret, str) else secret
+        if encrypt and not self.secret:
+            raise ValueError("encrypt=True needs a shared secret (spark.authenticate.secret)")
+        self.encrypt = bool(encrypt)
         self.connect_timeout = connect_timeout
         self._inboxes: Dict[str, _Inbox] = {}
         self._conns: Dict[RpcAddress, _Connection] = {}
@@ -461,11 +489,16 @@ class RpcEnv:
                 ftype, _, body = conn.recv_frame()                   # server speaks first: challenge (nonce)
                 if ftype != F_CHALLENGE:
                     raise RpcError(f"bad handshake from {address}")
-                proof = hmac.new(self.secret, bytes(body), hashlib.sha256).digest() if self.secret else b""
-                conn.send_frame(F_HELLO, 0, pickle.dumps((tuple(self.address) if self.address else None, proof)))
+                nonce = bytes(body)
+                proof = hmac.new(self.secret, nonce, hashlib.sha256).digest() if self.secret else b""
+                conn.send_frame(F_HELLO, 0, pickle.dumps((tuple(self.address) if self.address else None, proof, self.encrypt)))
                 ftype, _, body = conn.recv_frame()
-                if ftype != F_HELLO_ACK or bytes(body) != b"ok":
+                if ftype != F_HELLO_ACK or bytes(body) not in (b"ok", b"ok+enc"):
                     raise RpcError(f"{address} rejected the handshake: {bytes(body).decode(errors='replace')}")
+                if bytes(body) == b"ok+enc":
+                    conn.enable_encryption(self.secret, nonce, dialed=True)
+                elif self.encrypt:
+                    raise RpcError(f"{address} refused encryption")
             except (OSError, ConnectionError, struct.error) as exc:
                 conn.close()
                 raise RpcDisconnected(f"handshake with {address} failed: {exc}") from None
@@ -497,13 +530,21 @@ class RpcEnv:
             ftype, _, body = conn.recv_frame()
             if ftype != F_HELLO:
                 raise RpcError("expected HELLO")
-            advertised, proof = pickle.loads(bytes(body))
+            hello = pickle.loads(bytes(body))
+            advertised, proof, wants_enc = hello[0], hello[1], (hello[2] if len(hello) > 2 else False)
             if self.secret is not None:
                 want = hmac.new(self.secret, nonce, hashlib.sha256).digest()
                 if not hmac.compare_digest(want, proof):
                     conn.send_frame(F_HELLO_ACK, 0, b"authentication failed")
                     raise RpcError("authentication failed")
-            conn.send_frame(F_HELLO_ACK, 0, b"ok")
+            if self.encrypt and not wants_enc:
+                conn.send_frame(F_HELLO_ACK, 0, b"this endpoint requires encryption")
+                raise RpcError("peer did not ask for encryption")
+            if (wants_enc or self.encrypt) and self.secret is not None:
+                conn.send_frame(F_HELLO_ACK, 0, b"ok+enc")
+                conn.enable_encryption(self.secret, nonce, dialed=False)
+            else:
+                conn.send_frame(F_HELLO_ACK, 0, b"ok")
         except BaseException:  # noqa: BLE001
             conn.close()
             return

@@ -190,3 +190,64 @@ def test_concurrent_asks_from_many_threads():
         [t.start() for t in ths]
         [t.join() for t in ths]
         assert not errs and len(out) == 8
+
+
+def test_aes_gcm_encryption_hides_payloads_and_rejects_tampering():
+    """spark.network.crypto.enabled: frames are encrypted + authenticated after the handshake."""
+    import socket
+    import threading
+    marker = b"TOP-SECRET-PAYLOAD-0123456789"
+    seen = bytearray()
+    with RpcEnv("s", secret="k", encrypt=True) as server:
+        server.setup_endpoint("echo", Echo())
+        server.set_stream_manager({"blk": marker * 1000}.get)
+        # a byte-copying proxy in the middle records everything on the wire
+        lsock = socket.socket()
+        lsock.bind(("127.0.0.1", 0))
+        lsock.listen(1)
+        flip = {"on": False}
+
+        def pump(a, b, record):
+            try:
+                while True:
+                    d = a.recv(65536)
+                    if not d:
+                        break
+                    if record:
+                        seen.extend(d)
+                    if flip["on"] and len(d) > 40:
+                        d = d[:30] + bytes([d[30] ^ 0x01]) + d[31:]
+                        flip["on"] = False
+                    b.sendall(d)
+            except OSError:
+                pass
+            finally:
+                for x in (a, b):
+                    try:
+                        x.close()
+                    except OSError:
+                        pass
+
+        def proxy():
+            c, _ = lsock.accept()
+            u = socket.create_connection(tuple(server.address))
+            threading.Thread(target=pump, args=(c, u, True), daemon=True).start()
+            threading.Thread(target=pump, args=(u, c, True), daemon=True).start()
+        threading.Thread(target=proxy, daemon=True).start()
+        client = RpcEnv("c", server=False, secret="k", encrypt=True)
+        via = ("127.0.0.1", lsock.getsockname()[1])
+        ref = client.endpoint_ref(via, "echo")
+        assert ref.ask_sync(marker) == ("echo", marker)
+        assert client.fetch_chunk(via, "blk") == marker * 1000
+        assert marker not in bytes(seen) and len(seen) > len(marker) * 1000          # ciphertext only on the wire
+        flip["on"] = True                                                              # now corrupt one byte in flight
+        with pytest.raises(RpcError):
+            ref.ask_sync(b"x" * 100, timeout=3)                                        # authentication fails -> connection dropped
+        client.shutdown()
+        # a peer that does not ask for encryption is refused by an encrypt-only server; plaintext servers accept both
+        plain = RpcEnv("p", server=False, secret="k")
+        with pytest.raises(RpcError, match="requires encryption"):
+            plain.endpoint_ref(server.address, "echo").ask_sync(1, timeout=3)
+        plain.shutdown()
+    with pytest.raises(ValueError):
+        RpcEnv("x", server=False, encrypt=True)

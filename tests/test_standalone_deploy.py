@@ -144,3 +144,19 @@ def test_dynamic_allocation_grows_and_shrinks_the_application(cluster):
         assert _wait(lambda: sum(w["cores_used"] for w in cluster.state()["workers"]) == 2)
         assert len(set(ds.map(lambda x: os.getpid()).collect())) == 2
         assert s.executors_recovered == 0                       # released executors are not "lost"
+
+
+def test_authenticated_and_encrypted_cluster_end_to_end():
+    """spark.authenticate + spark.network.crypto.enabled on every hop: driver<->master, master<->worker, driver<->executor,
+    executor<->executor block transfer."""
+    from asyncframework_b200.conf import AsyncConf
+    with LocalStandaloneCluster(num_workers=2, secret="s3cr3t", encrypt=True) as c:
+        conf = (AsyncConf(load_defaults=False).set_master(c.master_url).set("spark.authenticate", "true")
+                .set("spark.authenticate.secret", "s3cr3t").set("spark.network.crypto.enabled", "true"))
+        with AsyncSession(conf=conf) as sc:
+            bc = sc.broadcast(torch.arange(100_000, dtype=torch.float64))
+            assert sc.parallelize(range(8), 4).map(lambda i: float(bc.value[i])).collect() == [float(i) for i in range(8)]
+            assert sc.scheduler.env.rpc_env.encrypt
+        bad = AsyncConf(load_defaults=False).set_master(c.master_url)
+        with pytest.raises(Exception, match="authentication|requires encryption|handshake"):
+            AsyncSession(conf=bad)
