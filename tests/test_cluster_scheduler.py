@@ -325,7 +325,7 @@ def test_failing_executor_is_blacklisted_and_its_partitions_move():
     from asyncframework_b200.core.cluster import ClusterScheduler
     from asyncframework_b200.data.dataset import ShardedDataset
     events = []
-    with ClusterScheduler(2, max_failures=4, blacklist=True, blacklist_max_failures=2, blacklist_timeout=0.8) as s:
+    with ClusterScheduler(2, max_failures=4, blacklist=True, blacklist_max_failures=2, blacklist_timeout=3.0) as s:
         s.listeners.add(events.append)
         ds = ShardedDataset.from_records(s, list(range(40)), 4)
 
@@ -340,7 +340,7 @@ def test_failing_executor_is_blacklisted_and_its_partitions_move():
         assert any(e["event"] == "executor_blacklisted" and e["executor"] == 1 for e in events)
         out2 = s.run_job(ds, lambda tctx, it: tctx.executor_id)
         assert out2 == [0, 0, 0, 0]                                            # new jobs avoid it too
-        time.sleep(1.0)                                                        # blacklist timeout expires
+        time.sleep(3.2)                                                        # blacklist timeout expires
         assert not s.is_blacklisted(1)
         assert s.run_job(ds, lambda tctx, it: tctx.executor_id) == [0, 1, 0, 1]
         assert any(e["event"] == "executor_unblacklisted" for e in events)
@@ -367,7 +367,7 @@ def test_wedged_executor_is_expired_by_missing_heartbeats_and_replaced():
     from asyncframework_b200.core.env import RuntimeLimits
     from asyncframework_b200.data.dataset import ShardedDataset
     events = []
-    lim = RuntimeLimits(heartbeat_interval=0.1, network_timeout=1.0)
+    lim = RuntimeLimits(heartbeat_interval=0.1, network_timeout=2.5)      # generous: only the STOPPED process may expire
     with ClusterScheduler(2, limits=lim, recover_lost_executors=True) as s:
         s.listeners.add(events.append)
         ds = ShardedDataset.from_records(s, list(range(20)), 4)
