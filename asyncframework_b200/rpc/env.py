@@ -30,6 +30,7 @@ from __future__ import annotations
 import hashlib
 import hmac
 import itertools
+import json
 import os
 import queue
 import socket
@@ -491,7 +492,8 @@ class RpcEnv:
                     raise RpcError(f"bad handshake from {address}")
                 nonce = bytes(body)
                 proof = hmac.new(self.secret, nonce, hashlib.sha256).digest() if self.secret else b""
-                conn.send_frame(F_HELLO, 0, pickle.dumps((tuple(self.address) if self.address else None, proof, self.encrypt)))
+                conn.send_frame(F_HELLO, 0, json.dumps({"addr": list(self.address) if self.address else None,
+                                                        "proof": proof.hex(), "enc": self.encrypt}).encode())
                 ftype, _, body = conn.recv_frame()
                 if ftype != F_HELLO_ACK or bytes(body) not in (b"ok", b"ok+enc"):
                     raise RpcError(f"{address} rejected the handshake: {bytes(body).decode(errors='replace')}")
@@ -530,8 +532,12 @@ class RpcEnv:
             ftype, _, body = conn.recv_frame()
             if ftype != F_HELLO:
                 raise RpcError("expected HELLO")
-            hello = pickle.loads(bytes(body))
-            advertised, proof, wants_enc = hello[0], hello[1], (hello[2] if len(hello) > 2 else False)
+            # the HELLO is parsed as JSON, never unpickled: nothing from an unauthenticated peer reaches the unpickler
+            hello = json.loads(bytes(body).decode())
+            advertised = tuple(hello["addr"]) if hello.get("addr") else None
+            proof, wants_enc = bytes.fromhex(hello.get("proof", "")), bool(hello.get("enc", False))
+            if advertised is not None and not (isinstance(advertised[0], str) and isinstance(advertised[1], int)):
+                raise RpcError("malformed HELLO")
             if self.secret is not None:
                 want = hmac.new(self.secret, nonce, hashlib.sha256).digest()
                 if not hmac.compare_digest(want, proof):

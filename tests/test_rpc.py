@@ -251,3 +251,37 @@ def test_aes_gcm_encryption_hides_payloads_and_rejects_tampering():
         plain.shutdown()
     with pytest.raises(ValueError):
         RpcEnv("x", server=False, encrypt=True)
+
+
+def test_unauthenticated_peer_cannot_reach_the_unpickler():
+    """The handshake is JSON; a pickle bomb sent as HELLO (or as the first frame) is rejected before any unpickling."""
+    import pickle
+    import socket
+    import struct
+
+    class Bomb:
+        def __reduce__(self):
+            return (os.system, ("touch /tmp/afb_pwned_marker",))
+    import os
+    try:
+        os.remove("/tmp/afb_pwned_marker")
+    except FileNotFoundError:
+        pass
+    with RpcEnv("s", secret="k") as server:
+        server.setup_endpoint("echo", Echo())
+        for ftype in (0, 3):                                # F_HELLO, F_REQUEST
+            sock = socket.create_connection(tuple(server.address), timeout=3)
+            sock.recv(64)                                    # the server's challenge
+            body = pickle.dumps(Bomb())
+            sock.sendall(struct.pack("!IBQ", len(body), ftype, 1) + body)
+            sock.settimeout(3)
+            try:
+                while sock.recv(4096):
+                    pass
+            except OSError:
+                pass
+            sock.close()
+        assert not os.path.exists("/tmp/afb_pwned_marker")
+        good = RpcEnv("g", server=False, secret="k")
+        assert good.endpoint_ref(server.address, "echo").ask_sync(5) == ("echo", 5)      # the server is still healthy
+        good.shutdown()
