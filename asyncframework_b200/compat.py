@@ -16,6 +16,7 @@ from __future__ import annotations
 
 from typing import Any, Optional
 
+from .conf import AsyncConf as _AsyncConf
 from .core.broadcast import AsyncBroadcast as _AsyncBroadcast
 from .core.context import AsyncContext as _AsyncContext
 from .core.partial_result import PartialResult as RDDPartialRes
@@ -25,14 +26,59 @@ from .data.dataset import ShardedDataset as RDD
 from .data.libsvm import MLUtils as _MLUtils
 from .linalg import DenseVector, LabeledPoint, SparseVector, Vectors  # noqa: F401
 from .linalg.blas_util import axpy_op as axpyOp, dot_op as dotOp, scal_op as scalOp  # noqa: F401
-from .models import LinearRegressionWithSGD, LogisticRegressionWithSGD, SVMWithSGD  # noqa: F401
+from .linalg import DenseMatrix, Matrices, SparseMatrix  # noqa: F401
+from .models import (LassoWithSGD, LinearRegressionWithSGD, LogisticRegressionWithLBFGS, LogisticRegressionWithSGD,  # noqa: F401
+                     RidgeRegressionWithSGD, SVMWithSGD)
+from .optim import LBFGS  # noqa: F401
+from .storage import StorageLevel  # noqa: F401
+
+_checkpoint_root = {"dir": None}
 from .optim import (GradientDescent, HingeGradient, L1Updater, LeastSquaresGradient, LogisticGradient,  # noqa: F401
                     SimpleUpdater, SquaredL2Updater)
 
 
+class SparkConf(_AsyncConf):
+    """``new SparkConf().setMaster(...).setAppName(...).set(k, v)`` (core/SparkConf.scala:82-119)."""
+
+    def __init__(self, loadDefaults: bool = True):
+        super().__init__(load_defaults=loadDefaults)
+
+    def setMaster(self, m: str): return self.set_master(m)
+    def setAppName(self, n: str): return self.set_app_name(n)
+    def setAll(self, items): return self.set_all(items)
+    def setIfMissing(self, k, v): return self.set_if_missing(k, v)
+    def getAll(self): return self.get_all()
+    def getInt(self, k, d=0): return self.get_int(k, d)
+    def getDouble(self, k, d=0.0): return self.get_double(k, d)
+    def getBoolean(self, k, d=False): return self.get_boolean(k, d)
+    def getSizeAsBytes(self, k, d=0): return self.get_size_as_bytes(k, d)
+    def getTimeAsSeconds(self, k, d=0): return self.get_time_as_seconds(k, d)
+    def toDebugString(self): return self.to_debug_string()
+
+
 class SparkContext(_AsyncSession):
-    """``new SparkContext(conf)`` — master URL as first argument; ``setLogLevel``, ``set_mode``, ``broadcast``,
-    ``parallelize``, ``textFile``."""
+    """``new SparkContext(conf)`` / ``new SparkContext(master, appName)`` — ``setLogLevel``, ``set_mode``, ``broadcast``,
+    ``parallelize``, ``textFile``, ``setCheckpointDir``, ``getConf``, ``defaultParallelism``."""
+
+    def __init__(self, master=None, appName: Optional[str] = None, conf=None, **kw):
+        if isinstance(master, _AsyncConf):          # new SparkContext(conf)
+            master, conf = None, master
+        super().__init__(master, appName, conf=conf, **kw)
+        self._checkpoint_dir: Optional[str] = None
+
+    def getConf(self):
+        return self.runtime_conf.clone()
+
+    @property
+    def defaultParallelism(self) -> int:
+        return self.default_parallelism
+
+    def setCheckpointDir(self, directory: str) -> None:
+        """``sc.setCheckpointDir`` (SparkContext.scala:2337): ``rdd.checkpoint()`` without an argument writes below it."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        self._checkpoint_dir = directory
+        _checkpoint_root["dir"] = directory
 
     def setLogLevel(self, level: str) -> None:
         self.set_log_level(level)
@@ -104,7 +150,27 @@ _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partition
 _alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
        cancelJob=lambda self, job_id: self.scheduler.cancel_job(job_id), cancelAllJobs=lambda self: self.scheduler.cancel_all_jobs())
 
-__all__ = ["SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",
+def _persist(self, level=None):
+    """``rdd.persist(StorageLevel)``: the level is advisory — executor block managers store cached partitions MEMORY_ONLY and
+    recompute evicted ones (the behaviour every ASYNC sample relies on)."""
+    return self.cache()
+
+
+def _checkpoint(self, directory: Optional[str] = None):
+    import os
+    d = directory or (_checkpoint_root["dir"] and os.path.join(_checkpoint_root["dir"], f"rdd-{self.ds_id & 0xFFFFFFFF}"))
+    if not d:
+        raise RuntimeError("Checkpoint directory has not been set in the SparkContext")
+    return type(self).checkpoint_to(self, d)
+
+
+if not hasattr(RDD, "checkpoint_to"):
+    RDD.checkpoint_to = RDD.checkpoint                 # the explicit-directory form stays available
+    RDD.checkpoint = _checkpoint
+RDD.persist = _persist
+
+__all__ = ["SparkConf", "StorageLevel", "Matrices", "DenseMatrix", "SparseMatrix", "LBFGS", "LogisticRegressionWithLBFGS",
+           "RidgeRegressionWithSGD", "LassoWithSGD", "SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",
            "DenseVector", "SparseVector", "LabeledPoint", "axpyOp", "dotOp", "scalOp", "GradientDescent", "LeastSquaresGradient",
            "LogisticGradient", "HingeGradient", "SimpleUpdater", "L1Updater", "SquaredL2Updater", "LinearRegressionWithSGD",
            "LogisticRegressionWithSGD", "SVMWithSGD"]

@@ -119,6 +119,7 @@ EVENT_LOG = _entry("spark.eventLog.enabled", _parse_bool, False, "append every s
 EVENT_LOG_DIR = _entry("spark.eventLog.dir", str, "/tmp/afb-events", "directory of the event logs (history server input)")
 UI_ENABLED = _entry("spark.ui.enabled", _parse_bool, False, "serve the live status UI / REST API")
 UI_PORT = _entry("spark.ui.port", int, 4040, "port of the live UI (0 = any free port)", _nonneg)
+PROFILE = _entry("spark.python.profile", _parse_bool, False, "run every task under cProfile; sc.show_profiles() / sc.dump_profiles(dir)")
 METRICS_CONF = _entry("spark.metrics.conf", str, "", "path of a metrics.properties file")
 LOCALITY_WAIT = _entry("spark.locality.wait", parse_time, 3.0, "accepted for compatibility: shard->executor affinity is hard here, nothing waits")
 DEFAULT_PARALLELISM = _entry("spark.default.parallelism", int, 0, "default number of partitions (0 = number of executors)", _nonneg)

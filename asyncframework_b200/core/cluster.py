@@ -668,6 +668,8 @@ class ClusterScheduler:
                    on_task_lost: Optional[Callable[[int, BaseException], None]] = None) -> JobWaiter:
         if self._stopped:
             raise RuntimeError("scheduler stopped")
+        if getattr(self, "profiler", None) is not None:
+            func = self.profiler.wrap(func)               # spark.python.profile: every task under cProfile
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
         job_id = next(ClusterScheduler._job_ids)
         waiter = JobWaiter(job_id, len(parts), result_handler)

@@ -247,6 +247,8 @@ class Scheduler:
                    on_task_lost: Optional[Callable[[int, BaseException], None]] = None) -> JobWaiter:
         if self._stopped:
             raise RuntimeError("scheduler stopped")
+        if getattr(self, "profiler", None) is not None:
+            func = self.profiler.wrap(func)               # spark.python.profile: every task under cProfile
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
         job = JobWaiter(next(Scheduler._job_ids), len(parts), result_handler)
         job.on_task_lost = on_task_lost  # type: ignore[attr-defined]

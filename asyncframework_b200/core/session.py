@@ -78,6 +78,8 @@ class AsyncSession:
                 import time as _t
                 log = os.path.join(rc.get("spark.eventLog.dir"), f"{app_name}-{int(_t.time() * 1000)}.jsonl")
             self.start_ui(port=rc.get("spark.ui.port") if rc.get("spark.ui.enabled") else 0, event_log=log)
+        if rc.get("spark.python.profile"):
+            self.enable_profiling()
         if rc.get("spark.metrics.conf"):
             from ..utils.metrics import MetricsSystem, SchedulerSource
             self.metrics_system = MetricsSystem.from_properties(MetricsSystem.load_properties(rc.get("spark.metrics.conf")),
@@ -194,6 +196,18 @@ class AsyncSession:
             self._event_log = EventLog(event_log).attach(self.scheduler)
         self.ui = StatusServer(self.status_store, self.metrics, host, port)
         return self.ui
+
+    def enable_profiling(self):
+        """``spark.python.profile``: profile every task; read the result with ``sc.profiler.show_profiles()``."""
+        from ..utils.profiler import TaskProfiler
+        self.profiler = TaskProfiler().attach(self.scheduler)
+        return self.profiler
+
+    def show_profiles(self, top: int = 10) -> str:
+        return self.profiler.show_profiles(top)
+
+    def dump_profiles(self, directory: str) -> None:
+        self.profiler.dump_profiles(directory)
 
     def stop(self) -> None:
         if not self._stopped:

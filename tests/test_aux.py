@@ -85,3 +85,34 @@ def test_async_checkpoint_writer_orders_and_reports_errors(tmp_path):
     wr.submit(None, path=str(tmp_path / "ck"), w=torch.zeros(1), k=1)          # a directory: the write fails ...
     with pytest.raises(RuntimeError):
         wr.close()                                                            # ... and the failure surfaces on close
+
+
+def test_log4j_style_logging_configuration(tmp_path):
+    import logging
+    from asyncframework_b200.utils import logging as afb_logging
+    logf = tmp_path / "driver.log"
+    props = tmp_path / "log4j.properties"
+    props.write_text(f"""log4j.rootCategory=WARN, file
+log4j.appender.file=org.apache.log4j.FileAppender
+log4j.appender.file.File={logf}
+log4j.appender.file.layout.ConversionPattern=%p %c: %m%n
+log4j.logger.asyncframework_b200.gd=DEBUG
+""")
+    base = afb_logging.configure(str(props))
+    try:
+        logging.getLogger("asyncframework_b200.core").info("hidden")
+        logging.getLogger("asyncframework_b200.core").warning("shown")
+        logging.getLogger("asyncframework_b200.gd").debug("gd-debug")
+        for h in base.handlers:
+            h.flush()
+        text = logf.read_text()
+        assert "WARNING asyncframework_b200.core: shown" in text and "hidden" not in text and "gd-debug" in text
+        afb_logging.set_log_level("OFF")
+        logging.getLogger("asyncframework_b200.core").error("silenced")
+        assert "silenced" not in logf.read_text()
+        import pytest as _pt
+        with _pt.raises(ValueError):
+            afb_logging.set_log_level("LOUD")
+    finally:
+        afb_logging.configure(props={"log4j.rootCategory": "ERROR, console"})
+        logging.getLogger("asyncframework_b200.gd").setLevel(logging.NOTSET)

@@ -144,3 +144,29 @@ def test_prometheus_statsd_graphite_sinks_and_metrics_properties(tmp_path):
     assert g.errors == 1
     with pytest.raises(ValueError, match="unknown metrics sink"):
         MetricsSystem.from_properties({"*.sink.x.class": "NoSuchSink"})
+
+
+@pytest.mark.parametrize("master", ["local[2]", "local-cluster[2]"])
+def test_task_profiler_collects_cprofile_stats_per_job(master, tmp_path):
+    """ProfilerSuite (python/pyspark/tests.py): stats of every task come back through an accumulator, per job."""
+    import pstats
+    from asyncframework_b200.conf import AsyncConf
+
+    def busy(x):
+        return sum(i * i for i in range(2000)) + x
+    with AsyncSession(master, conf=AsyncConf(load_defaults=False).set("spark.python.profile", "true")) as sc:
+        ds = sc.parallelize(range(40), 4)
+        assert ds.map(busy).count() == 40
+        assert ds.map(lambda x: x).reduce(lambda a, b: a + b) == 780
+        jobs = sc.profiler.jobs()
+        assert len(jobs) == 2
+        st = sc.profiler.stats(jobs[0])
+        names = {f[2] for f in st.stats}
+        assert "busy" in names
+        calls = sum(v[1] for f, v in st.stats.items() if f[2] == "busy")
+        assert calls == 40                                                  # 4 tasks merged, each record exactly once
+        text = sc.show_profiles(top=5)
+        assert f"Profile of job {jobs[0]}" in text and "cumulative" in text
+        sc.dump_profiles(str(tmp_path))
+        loaded = pstats.Stats(str(tmp_path / f"job_{jobs[0]}.pstats"))
+        assert any(f[2] == "busy" for f in loaded.stats)
