@@ -146,6 +146,9 @@ def experimental() -> C.CDLL:
         _sig(lib, "afb_dense_round_bf16_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_void_p])
         _sig(lib, "afb_grid_bar_bytes", C.c_int, [])
         _sig(lib, "afb_csr_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+        if hasattr(lib, "afb_eval_loss_tc"):
+            _sig(lib, "afb_eval_loss_tc", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p])
         _experimental = lib
         return lib
 

@@ -9,7 +9,8 @@ export AFB_TEST_EXPERIMENTAL=1
 # 1. correctness, one test function at a time (a spin-wait bug shows up as a timeout of THAT test only)
 for t in test_persistent_rounds_match_single_round_launches test_persistent_launch_refuses_non_resident_grid \
          test_pipelined_rounds_match_the_simulator_semantics test_persistent_csr_round_matches_the_split_round \
-         test_bf16_row_storage_kernel_matches_fp32_kernel_on_bf16_exact_data; do
+         test_bf16_row_storage_kernel_matches_fp32_kernel_on_bf16_exact_data \
+         test_tensor_core_evaluation_with_loss_epilogue_matches_the_exact_kernel; do
   timeout 240 python -m pytest tests/test_gpu_experimental.py -x -q -k "$t" > gpurun_out/exp_$t.log 2>&1
   echo "[$t] rc=$? $(tail -1 gpurun_out/exp_$t.log)"
 done

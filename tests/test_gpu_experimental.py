@@ -145,3 +145,21 @@ def test_bf16_row_storage_kernel_matches_fp32_kernel_on_bf16_exact_data(algo, lo
     a, c = res[torch.float32], res[torch.bfloat16]
     assert a[1] == c[1] == rounds and a[2] == c[2]
     assert torch.allclose(a[0], c[0], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("loss", ["logistic", "hinge", "least_squares_half"])
+@pytest.mark.parametrize("T", [8, 20, 40])
+def test_tensor_core_evaluation_with_loss_epilogue_matches_the_exact_kernel(loss, T, monkeypatch):
+    """csrc/experimental/eval_tc_loss.cu: tcgen05 GEMM + logistic / hinge epilogue vs the exact CUDA-core kernel, on
+    bf16-exact data (where the tf32 product is exact, so only the fp32 loss arithmetic differs)."""
+    from asyncframework_b200.data.generators import synthetic_shard
+    from asyncframework_b200.ops.eval import eval_loss
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    loss_id = LOSS_IDS.get(loss, 3)
+    sh = synthetic_shard("mnist8m", 20_000, 0, 1, seed=5, device="cuda", labels="binary01")     # integer pixels: exact in tf32
+    W = (torch.randn(sh.num_features, T, device="cuda") * 1e-3)
+    exact = eval_loss(sh, W, loss_id, use_tensor_cores=False)
+    monkeypatch.setenv("AFB_EVAL_TC_LOSS", "1")
+    tc = eval_loss(sh, W, loss_id, use_tensor_cores=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(tc.cpu(), exact.cpu(), rtol=2e-4, atol=1e-2), (tc[:4], exact[:4])
