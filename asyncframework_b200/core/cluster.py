@@ -91,6 +91,9 @@ class ExecutorBackend:
             self.binaries.pop(msg[1], None)
         elif kind == "task":
             self.tasks.put(msg)
+        elif kind == "drop_source":                      # ContextCleaner: the driver's copy of this source block is gone
+            from ..data.dataset import drop_source_block
+            drop_source_block(msg[1])
         elif kind == "thread_dump":                      # ExecutorThreadDumpPage: answered by the receiver thread, even mid-task
             self.send(("threads", -1, -1, msg[1], thread_dump(), 0.0))
         return True
@@ -296,6 +299,7 @@ class ClusterScheduler:
         self._lock = threading.Lock()
         self._stopped = False
         self._blocks_held: Dict[int, set] = {}       # source block id -> executors that already hold its data
+        self._cleaner_registered: set = set()
         self.last_task_binary_bytes = 0
         self.indirect_results = 0
         self.executors_recovered = 0
@@ -337,6 +341,20 @@ class ClusterScheduler:
 
     def stream_for(self, partition: int):
         return None
+
+    def _make_block_dropper(self, block_id: int):
+        def drop() -> None:
+            if self._stopped:
+                return
+            with self._lock:
+                holders = self._blocks_held.pop(block_id, set())
+            self._cleaner_registered.discard(block_id)
+            for e in holders:
+                try:
+                    self._send(e, ("drop_source", block_id))
+                except Exception:  # noqa: BLE001
+                    pass
+        return drop
 
     # ------------------------------------------------------------------ placement
     def is_blacklisted(self, eid: int) -> bool:
@@ -686,6 +704,11 @@ class ClusterScheduler:
             with ShippingContext(lambda b: all(e in held.get(b, ()) for e in targets)) as ship:
                 payload = cloudpickle.dumps((dataset, func, fault))
             make_payload.shipped = ship.shipped        # type: ignore[attr-defined]
+            for bid, blk in ship.blocks.items():       # ContextCleaner: free the executors' copies when the driver's block dies
+                if bid not in self._cleaner_registered:
+                    self._cleaner_registered.add(bid)
+                    from .cleaner import ContextCleaner
+                    ContextCleaner.get().register(blk, "source_block", self._make_block_dropper(bid))
             return payload
 
         payload = make_payload(executors)

@@ -57,6 +57,9 @@ class TorrentBroadcast(Broadcast):
         self.num_blocks, self.checksums, self.compressed = self._write_blocks(env, self._value)
         with env.broadcast_lock:
             env.broadcast_cache[self.id] = self._value
+        # ContextCleaner: once this handle is unreachable, drop the pieces and cached values on every block manager
+        from .cleaner import ContextCleaner
+        ContextCleaner.get().register(self, "broadcast", _make_remover(env, self.id))
 
     # ------------------------------------------------------------------ driver side
     def _write_blocks(self, env: AsyncEnv, value: Any) -> Tuple[int, List[int], bool]:
@@ -114,6 +117,16 @@ class TorrentBroadcast(Broadcast):
                 env.broadcast_cache.pop(self.id, None)
         self._valid = False
         self._value = None
+
+
+def _make_remover(env: AsyncEnv, bid: int):
+    def remove() -> None:
+        if env._stopped:
+            return
+        env.bm_master.remove_broadcast(bid, remove_from_driver=True)
+        with env.broadcast_lock:
+            env.broadcast_cache.pop(bid, None)
+    return remove
 
 
 def _rebuild(bid: int, num_blocks: int, checksums: List[int], compressed: bool) -> TorrentBroadcast:

@@ -102,8 +102,13 @@ class BlockMissing(RuntimeError):
     """An executor was sent a block reference for data it does not hold (e.g. a replaced executor)."""
 
 
+def drop_source_block(block_id: int) -> bool:
+    """Executor side of the cleaner: forget a shipped source block."""
+    return _SOURCE_STORE.pop(block_id, None) is not None
+
+
 class SourceBlock:
-    __slots__ = ("block_id", "data")
+    __slots__ = ("block_id", "data", "__weakref__")
 
     def __init__(self, data, block_id: Optional[int] = None):
         self.block_id = block_id if block_id is not None else ((os.getpid() << 32) | next(_block_ids))
@@ -126,7 +131,7 @@ class SourceBlock:
         if ctx is not None and ctx.holds(self.block_id):
             return (SourceBlock._from_store, (self.block_id,))
         if ctx is not None:
-            ctx.shipping(self.block_id)
+            ctx.shipping(self.block_id, self)
         return (SourceBlock._with_data, (self.block_id, self.data))
 
 
@@ -137,9 +142,12 @@ class ShippingContext:
     def __init__(self, held_by_all_targets: Callable[[int], bool]):
         self.holds = held_by_all_targets
         self.shipped: List[int] = []
+        self.blocks: dict = {}
 
-    def shipping(self, block_id: int) -> None:
+    def shipping(self, block_id: int, block=None) -> None:
         self.shipped.append(block_id)
+        if block is not None:
+            self.blocks[block_id] = block
 
     def __enter__(self):
         _pickle_ctx.ctx = self

@@ -384,3 +384,36 @@ def test_wedged_executor_is_expired_by_missing_heartbeats_and_replaced():
         assert res == {p: sum(range(5 * p, 5 * p + 5)) for p in range(4)}
         assert s.executors_expired == 1 and s.executors_recovered == 1
         assert [e["executor"] for e in events if e["event"] == "executor_expired"] == [1]
+
+
+def test_context_cleaner_frees_broadcast_pieces_and_shipped_source_blocks():
+    """ContextCleanerSuite: state on the executors dies with its driver-side handle — one broadcast per round must not pile up."""
+    import gc
+    from asyncframework_b200.core.cleaner import ContextCleaner
+    from asyncframework_b200.core.session import AsyncSession
+    with AsyncSession("local-cluster[2]") as sc:
+        ds = sc.parallelize(range(8), 4)
+        ids = []
+        for r in range(5):                                        # the ASGD pattern: a new broadcast every round
+            bc = sc.broadcast(torch.full((50_000,), float(r)))
+            ids.append(bc.id)
+            assert ds.map(lambda i, bc=bc: float(bc.value[0])).collect() == [float(r)] * 8
+        def pieces():
+            st = sc.scheduler.storage_status()
+            return sorted({b.split("_")[1] for s in st.values() for b in s["blocks"] if b.startswith("broadcast_")})
+        assert len(pieces()) == 5
+        del bc
+        gc.collect()
+        ContextCleaner.get().flush()
+        assert pieces() == []                                     # every piece, on the driver and on both executors, is gone
+        # shipped source data of a dataset that is no longer referenced
+        big = sc.parallelize([bytes(1000)] * 400, 4)
+        assert big.count() == 400
+        held = lambda: sorted(set(sc.scheduler.run_job(ds, lambda t, it: __import__("asyncframework_b200.data.dataset", fromlist=["x"])._SOURCE_STORE.keys().__len__())))  # noqa: E731
+        before = held()
+        del big
+        gc.collect()
+        ContextCleaner.get().flush()
+        time.sleep(0.2)
+        after = held()
+        assert max(after) < max(before)
