@@ -46,6 +46,9 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
     if cfg.backend == "fused":
         from .fused_driver import run_fused
         return run_fused(cfg, points)
+    if cfg.backend == "nccl":                      # two-sided collectives cannot express the asynchronous protocol: clear error
+        from .nccl_driver import run_nccl
+        return run_nccl(cfg, points)
     device = resolve_device(cfg)
     dtype = compute_dtype(cfg, device)
     own = scheduler is None

@@ -24,6 +24,9 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
     if cfg.backend == "fused":
         from .fused_driver import run_fused
         return run_fused(cfg, points)
+    if cfg.backend == "nccl":
+        from .nccl_driver import run_nccl
+        return run_nccl(cfg, points)
     device = resolve_device(cfg)
     dtype = compute_dtype(cfg, device)
     own = scheduler is None

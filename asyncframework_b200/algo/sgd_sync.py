@@ -25,6 +25,9 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
     if cfg.backend == "fused":
         from .fused_driver import run_fused
         return run_fused(cfg, points)
+    if cfg.backend == "nccl":
+        from .nccl_driver import run_nccl
+        return run_nccl(cfg, points)
     if cfg.backend == "gloo":
         from ..parallel.cpu_backend import run_sync_gloo
         return run_sync_gloo(cfg)

@@ -98,6 +98,14 @@ def _stable_hash(key) -> int:
     return zlib.crc32(pickle.dumps(key, protocol=4))
 
 
+def _with_rows(sub: Shard, parent: Shard, rows: torch.Tensor) -> Shard:
+    """Record the sampled rows' positions in the UNSAMPLED partition (``meta['rows']``): per-row state that lives beside the
+    partition — the SAGA history table — is indexed with it.  Positions compose through nested samples."""
+    prev = parent.meta.get("rows")
+    sub.meta["rows"] = rows.to(torch.int64) if prev is None else prev.to(rows.device)[rows]
+    return sub
+
+
 class BlockMissing(RuntimeError):
     """An executor was sent a block reference for data it does not hold (e.g. a replaced executor)."""
 
@@ -389,11 +397,11 @@ class ShardedDataset:
             if b.device.type == "cuda":
                 from ..ops.sampling import sample_rows          # K11 compaction kernel, same hash
                 rows = sample_rows(b.num_rows, fraction, seed, b.gidx, p << 40, b.device)
-                return b.select(rows)
+                return _with_rows(b.select(rows), b, rows)
             idx = b.gidx if b.gidx is not None else (torch.arange(b.num_rows, dtype=torch.int64) + (p << 40))
             mask = _sampler.bernoulli_mask(seed, idx, fraction)
             rows = torch.from_numpy(np.nonzero(mask)[0])
-            return b.select(rows)
+            return _with_rows(b.select(rows), b, rows)
 
         def compute(p, t):
             thr = _sampler.threshold24(fraction)
@@ -1074,6 +1082,30 @@ class ShardedDataset:
                 return (0, _EMPTY)
             return (n if record_stat else -(2**31), acc)
         return self._async_submit(ctx, part, envelope_ts_only=True, empty_raises=strict_empty)
+
+    def async_grad(self, loss, w_bcast, ctx, history=None):
+        """Fused fast path of the ASYNC drivers: for every selected (and already sampled) partition compute the
+        mini-batch gradient of ``loss`` at ``w_bcast.value`` in ONE pass over the shard — the fused CUDA kernel on HBM-resident
+        shards, the vectorised torch path on CPU shards — and deliver ``[g, loss_sum, n]`` (``[g, loss_sum, n, coeff, rows]`` with
+        ``history``: the SAGA-corrected gradient Σ (r_i − hist_i) x_i, the new residuals and their local row positions) to ``ctx`` as each worker finishes, tagged with staleness / worker id.
+        ``loss`` is a name (``"logistic"`` …) or a :class:`Gradient`; ``history`` maps partition -> per-row tensor."""
+        from ..optim.gradient import Gradient, make_gradient
+        grad = loss if isinstance(loss, Gradient) else make_gradient(loss)
+
+        def fn(s, w_bcast=w_bcast, grad=grad, history=history):
+            from ..algo.common import partition_gradient
+            h = rows = None
+            if history is not None:
+                hp = history[s.partition]
+                rows = s.meta.get("rows")                      # local positions of the sampled rows (set by ``sample``)
+                h = hp if rows is None else hp[rows.to(hp.device)]
+            g, l, n, coeff = partition_gradient(grad, s, w_bcast.value, None if h is None else h.to(s.device))
+            return [g, float(l), int(n)] if history is None else [g, float(l), int(n), coeff, rows]
+
+        def merge(x, y):                              # a partition is ONE shard, so this only runs for multi-shard partitions
+            out = [x[0].add_(y[0]), x[1] + y[1], x[2] + y[2]]
+            return out if len(x) == 3 else out + [torch.cat([x[3], y[3]]), None]
+        return self.map_batch(fn).async_reduce(merge, ctx)
 
     ASYNCreduce = async_reduce
     ASYNCaggregate = async_aggregate

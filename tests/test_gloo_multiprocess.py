@@ -1,5 +1,7 @@
 """Multi-process-on-one-box tests (the `local-cluster` analogue): 2 CPU workers over gloo.
 Includes BASELINE config 1: SparkASGDSync logistic regression on 1k x 20 synthetic LIBSVM."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -51,3 +53,28 @@ def test_async_parameter_server_over_gloo(alg):
                       num_iterations=300, step_size=1.0 if alg == "asgd" else 0.05, batch_rate=0.2, backend="gloo")
     out = spawn_local(cfg, world=3, mode="async")
     assert out["iterations"] >= 300 and out["objective"][0][1] < 0.05
+
+
+def test_nccl_backend_driver_contract_single_process_and_two_ranks_over_gloo():
+    """``--backend=nccl`` (SURVEY §7.1 "cuda-nccl (baseline)"): the stock-collectives baseline behind the same driver contract.
+    Without CUDA the collectives run over gloo; 1 rank in-process, 2 ranks under torchrun."""
+    import subprocess
+    import sys
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    for name in ("sgd_sync", "saga_sync"):
+        cfg = AsyncConfig(algorithm=name, synthetic="linear", num_rows=600, num_features=8, num_partitions=2, num_iterations=40,
+                          step_size=0.5 if name == "sgd_sync" else 0.05, batch_rate=0.3, printer_freq=10, backend="nccl", quiet=True)
+        rep = algo.run(cfg)
+        assert len(rep.objective) == 6 and rep.objective[-1][1] < 0.5 * rep.objective[0][1]
+        assert "nccl-baseline" in rep.extra["backend"]
+    with pytest.raises(ValueError, match="synchronous drivers"):
+        algo.run(AsyncConfig(algorithm="asgd", synthetic="linear", num_rows=100, num_features=4, backend="nccl"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", "-m", "asyncframework_b200.algo.sgd_sync", "x", "x", "8", "600", "2", "40", "0.5", "0.3", "10", "0", "42",
+           "--backend=nccl", "--synthetic=linear"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=root,
+                         env={**os.environ, "PYTHONPATH": root, "CUDA_VISIBLE_DEVICES": ""})
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Iteration 40 is finished" in out.stdout and "Elapsed time" in out.stdout
