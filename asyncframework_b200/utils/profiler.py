@@ -14,7 +14,11 @@ import os
 import pstats
 from typing import Dict
 
+import threading
+
 from ..core.accumulator import Accumulator
+
+_PROFILE_LOCK = threading.Lock()
 
 
 def _merge_stats(a: dict, b: dict) -> dict:
@@ -41,6 +45,18 @@ def _merge_by_job(a: Dict[int, dict], b: Dict[int, dict]) -> Dict[int, dict]:
     return out
 
 
+def _run_profiled(func, tctx, it, acc):
+    # CPython allows ONE active cProfile per interpreter (sys.monitoring tool id): executor THREADS of an in-process master
+    # take turns while profiling is on; executor processes have one task thread each and never wait here
+    with _PROFILE_LOCK:
+        pr = cProfile.Profile()
+        try:
+            return pr.runcall(func, tctx, it)
+        finally:
+            pr.create_stats()
+            acc.add({tctx.job_id: pr.stats})
+
+
 class _Table:
     """Adapter so ``pstats.Stats`` can load a raw table."""
 
@@ -59,12 +75,7 @@ class TaskProfiler:
         acc = self.acc
 
         def profiled(tctx, it):
-            pr = cProfile.Profile()
-            try:
-                return pr.runcall(func, tctx, it)
-            finally:
-                pr.create_stats()
-                acc.add({tctx.job_id: pr.stats})
+            return _run_profiled(func, tctx, it, acc)      # module-level helper: pickled by reference (it touches a lock)
         return profiled
 
     def attach(self, scheduler) -> "TaskProfiler":
