@@ -72,3 +72,25 @@ def bernoulli_mask_torch(seed: int, idx: torch.Tensor, fraction: float) -> torch
 def uniform01(seed: int, idx) -> np.ndarray:
     """U[0,1) doubles from the same hash (used by the delay injector's long-tail draws)."""
     return hash_u24(seed, idx).astype(np.float64) / float(1 << 24)
+
+
+def poisson_counts(seed: int, idx, mean: float) -> np.ndarray:
+    """How many times each row appears in a sample WITH replacement: Poisson(mean) per row (``PoissonSampler``,
+    util/random/RandomSampler.scala:180-230), drawn by inverse CDF from the row's own 24-bit uniform — so, like the Bernoulli
+    mask, it is a pure function of (seed, global row index) that any party can replay."""
+    u = uniform01(seed, idx)
+    mean = float(mean)
+    if mean <= 0:
+        return np.zeros(u.shape, dtype=np.int64)
+    counts = np.zeros(u.shape, dtype=np.int64)
+    p = np.exp(-mean)
+    cdf = np.full(u.shape, p)
+    k = 0
+    todo = u >= cdf
+    while todo.any() and k < 64 + int(10 * mean):
+        k += 1
+        p = p * mean / k
+        cdf = cdf + p
+        counts[todo] = k
+        todo = u >= cdf
+    return counts

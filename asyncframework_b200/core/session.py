@@ -115,6 +115,43 @@ class AsyncSession:
         from ..data.dataset import ShardedDataset
         return ShardedDataset.from_records(self.scheduler, list(data), num_slices or self.default_parallelism)
 
+    def range(self, start: int, end: Optional[int] = None, step: int = 1, num_slices: Optional[int] = None):
+        """``sc.range``."""
+        if end is None:
+            start, end = 0, start
+        return self.parallelize(range(start, end, step), num_slices)
+
+    def empty_dataset(self):
+        """``sc.emptyRDD``."""
+        return self.parallelize([], 1)
+
+    def union(self, datasets):
+        """``sc.union(rdds)``."""
+        out = datasets[0]
+        for d in datasets[1:]:
+            out = out.union(d)
+        return out
+
+    def whole_text_files(self, path: str, min_partitions: Optional[int] = None):
+        """``sc.wholeTextFiles``: one ``(file path, content)`` record per file of a directory."""
+        from ..data.libsvm import _input_files
+        recs = []
+        for f in _input_files(path):
+            with open(f) as fh:
+                recs.append((f, fh.read()))
+        return self.parallelize(recs, min_partitions or min(self.default_parallelism, max(1, len(recs))))
+
+    def pickle_file(self, directory: str):
+        """``sc.pickleFile``: read back what ``ShardedDataset.save_as_pickle_file`` wrote (one partition per part file)."""
+        import pickle as _pickle
+        from ..data.dataset import ShardedDataset
+        parts = sorted(f for f in os.listdir(directory) if f.startswith("part-"))
+
+        def compute(p, t, parts=parts, directory=directory):
+            with open(os.path.join(directory, parts[p]), "rb") as fh:
+                return iter(_pickle.load(fh))
+        return ShardedDataset(self.scheduler, max(1, len(parts)), compute if parts else (lambda p, t: iter(())), None, None, "pickle_file")
+
     def text_file(self, path: str, min_partitions: Optional[int] = None):
         """Line records of a file or a directory of part files (``sc.textFile``, SparkContext.scala:837)."""
         from ..data.libsvm import _input_files

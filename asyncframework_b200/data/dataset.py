@@ -384,11 +384,11 @@ class ShardedDataset:
         """Bernoulli sample without replacement (the only mode the reference's drivers use).
         Membership = hash(seed, global row index) < fraction — see core/sampler.py; an unseeded
         call draws a fresh seed like the reference's unseeded ``.sample(false, 0.1)`` (B.9)."""
-        if with_replacement:
-            raise NotImplementedError("Poisson sampling with replacement is not used by ASYNC; use fraction<=1 without replacement")
         if seed is None:
             seed = int.from_bytes(np.random.bytes(8), "little")
         seed = int(seed)
+        if with_replacement:
+            return self._sample_with_replacement(fraction, seed)
 
         def batch(p, t):
             b = self.batch(p, t)
@@ -411,6 +411,26 @@ class ShardedDataset:
                     yield rec
 
         return self._derive(compute, batch if self.batch_capable else None, "sample")
+
+    def _sample_with_replacement(self, fraction: float, seed: int) -> "ShardedDataset":
+        """``sample(withReplacement = true, fraction)``: every row appears Poisson(fraction) times (PoissonSampler); the counts
+        are a pure function of (seed, global row index), see core/sampler.py::poisson_counts.  Not used by the ASYNC drivers
+        (they sample without replacement) but part of the RDD contract (bootstrap resampling)."""
+        def batch(p, t):
+            b = self.batch(p, t)
+            if b is None:
+                return None
+            idx = b.gidx if b.gidx is not None else (torch.arange(b.num_rows, dtype=torch.int64) + (p << 40))
+            counts = torch.from_numpy(_sampler.poisson_counts(seed, idx, fraction))
+            rows = torch.repeat_interleave(torch.arange(b.num_rows, dtype=torch.int64), counts)
+            return _with_rows(b.select(rows), b, rows)
+
+        def compute(p, t):
+            for pos, rec in enumerate(self.iterator(p, t)):
+                gi = rec[1] if (isinstance(rec, tuple) and len(rec) == 2 and isinstance(rec[1], int)) else (pos + (p << 40))
+                for _ in range(int(_sampler.poisson_counts(seed, np.asarray([gi]), fraction)[0])):
+                    yield rec
+        return self._derive(compute, batch if self.batch_capable else None, "sample_with_replacement")
 
     def zip_with_index(self) -> "ShardedDataset":
         """Global index = partition offset + position; runs a count job over the partitions to
@@ -861,6 +881,18 @@ class ShardedDataset:
             with open(os.path.join(directory, f"part-{t.partition_id:05d}"), "w") as f:
                 for r in it:
                     f.write(str(r) + "\n")
+            return t.partition_id
+        self._run(write)
+        open(os.path.join(directory, "_SUCCESS"), "w").close()
+
+    def save_as_pickle_file(self, directory: str) -> None:
+        """``saveAsPickleFile`` / ``saveAsObjectFile``: one pickled list per partition (``sc.pickle_file`` reads it back)."""
+        import pickle as _pickle
+        os.makedirs(directory, exist_ok=True)
+
+        def write(t, it):
+            with open(os.path.join(directory, f"part-{t.partition_id:05d}"), "wb") as f:
+                _pickle.dump(list(it), f, protocol=_pickle.HIGHEST_PROTOCOL)
             return t.partition_id
         self._run(write)
         open(os.path.join(directory, "_SUCCESS"), "w").close()

@@ -97,3 +97,33 @@ def test_shuffle_goes_through_executor_block_managers_on_cluster_masters():
         assert dict(red.collect())[7] == sum(i for i in range(1000) if i % 10 == 7)
         assert sh.remove_shuffle() >= len(blocks) - 1
         assert not any(b.startswith(f"shuffle_{sh.shuffle_id}_") for s in sc.scheduler.storage_status().values() for b in s["blocks"])
+
+
+def test_sampling_with_replacement_io_helpers_and_shell(sc, tmp_path):
+    import subprocess
+    import sys
+    import numpy as np
+    from asyncframework_b200.core.sampler import poisson_counts
+    c = poisson_counts(7, np.arange(200_000), 1.5)
+    assert abs(c.mean() - 1.5) < 0.02 and abs(c.var() - 1.5) < 0.05 and c.max() > 5          # Poisson(1.5)
+    assert (poisson_counts(7, np.arange(100), 1.5) == c[:100]).all()                          # replayable per row
+    ds = sc.parallelize(range(5000), 4)
+    boot = ds.sample(True, 1.0, seed=3).collect()
+    assert 4600 < len(boot) < 5400 and len(set(boot)) < len(boot) and max(np.bincount(boot)) >= 3
+    assert ds.sample(True, 1.0, seed=3).collect() == boot                                     # deterministic in the seed
+    assert sc.range(10).sum() == 45 and sc.range(2, 10, 2).collect() == [2, 4, 6, 8] and sc.empty_dataset().count() == 0
+    assert sc.union([sc.range(3), sc.range(3, 5), sc.range(5, 6)]).collect() == [0, 1, 2, 3, 4, 5]
+    d = tmp_path / "txt"
+    d.mkdir()
+    (d / "a.txt").write_text("x\ny\n")
+    (d / "b.txt").write_text("z\n")
+    assert sorted(os.path.basename(k) for k, _ in sc.whole_text_files(str(d)).collect()) == ["a.txt", "b.txt"]
+    out = str(tmp_path / "pk")
+    sc.parallelize([{"i": i} for i in range(7)], 3).save_as_pickle_file(out)
+    back = sc.pickle_file(out)
+    assert back.num_partitions == 3 and sorted(r["i"] for r in back.collect()) == list(range(7))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "asyncframework_b200.shell", "--master", "local[2]", "--", "-c",
+                          "print('SUM', sc.parallelize(range(10)).map(lambda x: x * x).reduce(lambda a, b: a + b))"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env={**os.environ, "PYTHONPATH": root})
+    assert res.returncode == 0 and "SUM 285" in res.stdout, res.stderr[-800:]
