@@ -50,8 +50,9 @@ def test_repartition_zip_with_index_sample(scheduler):
     rec_idx = sorted(i for _, i in s1.map(lambda r: r).collect())
     bat_idx = sorted(torch.cat([s.gidx for s in s1.shards()]).tolist())
     assert rec_idx == bat_idx
-    with pytest.raises(NotImplementedError):
-        zi.sample(True, 0.5, 1)
+    wr = zi.sample(True, 0.5, 1)                                             # with replacement: Poisson(0.5) copies per row
+    n_wr = wr.count()
+    assert abs(n_wr - 500) < 90 and wr.count() == n_wr
 
 
 def test_cache_materialises_once(scheduler):
