@@ -97,6 +97,9 @@ if os.path.exists(tm):
     for a, row in t["by_alpha"].items():
         out.append(f"| {a} | " + " | ".join(str(v) for v in row.values()) + " |")
     out.append("")
+rp = os.path.join(ROOT, "profiles", "roofline_per_path.md")      # hand-written analysis of the committed timestamps: included verbatim
+if os.path.exists(rp):
+    out += open(rp).read().rstrip("\n").split("\n") + [""]
 hr = os.path.join(ROOT, "profiles", "host_runtime.json")
 if os.path.exists(hr):
     h = json.load(open(hr))
