@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import queue
 import threading
-import traceback
 import weakref
 from typing import Callable, Optional
 

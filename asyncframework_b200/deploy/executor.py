@@ -13,7 +13,6 @@ from __future__ import annotations
 import argparse
 import os
 import sys
-import threading
 
 
 def main(argv=None) -> int:

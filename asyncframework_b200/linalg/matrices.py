@@ -9,7 +9,7 @@ row-major), sparse = CSC (``col_ptrs``, ``row_indices``, ``values``).
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import logging
 import time
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
 import torch
 
