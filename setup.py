@@ -35,7 +35,11 @@ setup(
     packages=find_packages(include=["asyncframework_b200", "asyncframework_b200.*"]),
     package_data={"asyncframework_b200": ["lib/*.so"]},
     python_requires=">=3.10",
-    install_requires=["torch", "numpy"],
+    install_requires=["torch", "numpy", "cloudpickle"],
+    extras_require={"crypto": ["cryptography"]},
     cmdclass={"build_ext": build_ext, "build_native": BuildNative},
-    entry_points={"console_scripts": ["afb-launch=asyncframework_b200.launch:main"]},
+    entry_points={"console_scripts": ["afb-launch=asyncframework_b200.launch:main", "afb-submit=asyncframework_b200.submit:main",
+                                      "afb-shell=asyncframework_b200.shell:main", "afb-master=asyncframework_b200.deploy.master:main",
+                                      "afb-worker=asyncframework_b200.deploy.worker:main",
+                                      "afb-history-server=asyncframework_b200.utils.status_server:main"]},
 )
