@@ -377,6 +377,25 @@ class ShardedDataset:
             return iter((f(b),))
         return self._derive(compute, None, "map_batch")
 
+    def map_shards(self, f: Callable[[Shard], Shard]) -> "ShardedDataset":
+        """Columnar transformation ``Shard -> Shard`` that KEEPS the batch-level lineage (feature scaling, bias append, dtype /
+        device moves …): the result is still batch-capable, so ``sample`` / ``async_grad`` / the fused kernels apply to it."""
+        if not self.batch_capable:
+            raise TypeError(f"dataset {self.name!r} has no batch-level view to transform")
+
+        def batch(p, t):
+            b = self.batch(p, t)
+            if b is None:
+                return None
+            out = f(b)
+            out.partition = p
+            return out
+
+        def compute(p, t):
+            b = batch(p, t)
+            return iter(()) if b is None else (b.indexed_records() if b.gidx is not None else b.records())
+        return self._derive(compute, batch, "map_shards")
+
     def glom(self) -> "ShardedDataset":
         return self._derive(lambda p, t: iter((list(self.iterator(p, t)),)), None, "glom")
 

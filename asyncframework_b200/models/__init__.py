@@ -2,6 +2,8 @@ from .glm import (GeneralizedLinearAlgorithm, GeneralizedLinearModel, LassoModel
                   LinearRegressionModel, LinearRegressionWithSGD, LogisticRegressionModel,
                   LogisticRegressionWithLBFGS, LogisticRegressionWithSGD, RidgeRegressionModel, RidgeRegressionWithSGD, SVMModel, SVMWithSGD)
 
-__all__ = ["GeneralizedLinearAlgorithm", "GeneralizedLinearModel", "LassoModel", "LassoWithSGD",
+from .feature import ColumnSummary, StandardScaler, StandardScalerModel, append_bias, col_stats  # noqa: E402
+
+__all__ = ["ColumnSummary", "StandardScaler", "StandardScalerModel", "append_bias", "col_stats", "GeneralizedLinearAlgorithm", "GeneralizedLinearModel", "LassoModel", "LassoWithSGD",
            "LinearRegressionModel", "LinearRegressionWithSGD", "LogisticRegressionModel",
            "LogisticRegressionWithLBFGS", "LogisticRegressionWithSGD", "RidgeRegressionModel", "RidgeRegressionWithSGD", "SVMModel", "SVMWithSGD"]

@@ -201,3 +201,40 @@ def test_logistic_regression_with_lbfgs_scales_features_and_predicts():
         assert acc >= oracle - 0.02 and acc >= acc_sgd - 0.01
         assert len(m.loss_history) >= 3 and m.loss_history[-1] < m.loss_history[0]
         assert abs(float(m.weights[2])) > abs(float(m.weights[1]))          # back on the ORIGINAL scale: col 2 has the big true weight
+
+
+def test_col_stats_standard_scaler_and_append_bias_dense_and_csr():
+    """MultivariateOnlineSummarizerSuite / StandardScalerSuite at the behaviour level, on dense and CSR shards."""
+    import numpy as np
+    from asyncframework_b200.core.scheduler import Scheduler
+    from asyncframework_b200.data import ShardedDataset
+    from asyncframework_b200.models import StandardScaler, append_bias, col_stats
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((500, 6)) * np.array([1, 10, 0.1, 3, 0, 2]) * (rng.random((500, 6)) < 0.6)
+    X[:, 4] = 0.0                                                          # a constant column: std 0 -> scaled to 0, not NaN
+    y = rng.standard_normal(500)
+    with Scheduler(3) as s:
+        dense = ShardedDataset.from_arrays(s, X, y, 3)
+        sparse = ShardedDataset.from_shards(s, [sh.to_csr() for sh in dense.shards()])
+        for ds in (dense, sparse):
+            st = col_stats(ds)
+            assert st.count == 500 and np.allclose(st.mean.numpy(), X.mean(0)) and np.allclose(st.variance.numpy(), X.var(0, ddof=1))
+            assert np.allclose(st.num_nonzeros.numpy(), (X != 0).sum(0)) and np.allclose(st.max.numpy(), X.max(0))
+            assert np.allclose(st.min.numpy(), X.min(0)) and np.allclose(st.norm_l1.numpy(), np.abs(X).sum(0))
+            assert np.allclose(st.norm_l2.numpy(), np.sqrt((X * X).sum(0)))
+            model = StandardScaler().fit(ds)
+            scaled = model.transform(ds)
+            Z = torch.cat([sh.to_dense().X[:, :6] for sh in scaled.shards()]).numpy()
+            order = np.concatenate([np.arange(p, 500, 3) for p in range(3)])                  # from_arrays is round-robin
+            std = X.std(0, ddof=1)
+            want = np.where(std > 0, X / np.where(std > 0, std, 1), 0.0)[order]
+            assert np.allclose(Z, want) and not np.isnan(Z).any()
+            assert all(sh.is_dense == orig.is_dense for sh, orig in zip(scaled.shards(), ds.shards()))   # sparsity preserved
+            centred = model.set_with_mean(True).transform(ds)
+            Zc = torch.cat([sh.X[:, :6] for sh in centred.shards()]).numpy()
+            assert np.allclose(Zc.mean(0), 0.0, atol=1e-10)
+            model.set_with_mean(False)
+            assert np.allclose(model.transform(torch.from_numpy(X[0])).numpy(), want[list(order).index(0)])
+            wb = append_bias(ds)
+            sh0 = wb.shards()[0]
+            assert sh0.num_features == 7 and bool((sh0.to_dense().X[:, 6] == 1.0).all())
