@@ -2,8 +2,9 @@ from .glm import (GeneralizedLinearAlgorithm, GeneralizedLinearModel, LassoModel
                   LinearRegressionModel, LinearRegressionWithSGD, LogisticRegressionModel,
                   LogisticRegressionWithLBFGS, LogisticRegressionWithSGD, RidgeRegressionModel, RidgeRegressionWithSGD, SVMModel, SVMWithSGD)
 
+from .evaluation import BinaryClassificationMetrics, RegressionMetrics  # noqa: E402
 from .feature import ColumnSummary, StandardScaler, StandardScalerModel, append_bias, col_stats  # noqa: E402
 
-__all__ = ["ColumnSummary", "StandardScaler", "StandardScalerModel", "append_bias", "col_stats", "GeneralizedLinearAlgorithm", "GeneralizedLinearModel", "LassoModel", "LassoWithSGD",
+__all__ = ["BinaryClassificationMetrics", "RegressionMetrics", "ColumnSummary", "StandardScaler", "StandardScalerModel", "append_bias", "col_stats", "GeneralizedLinearAlgorithm", "GeneralizedLinearModel", "LassoModel", "LassoWithSGD",
            "LinearRegressionModel", "LinearRegressionWithSGD", "LogisticRegressionModel",
            "LogisticRegressionWithLBFGS", "LogisticRegressionWithSGD", "RidgeRegressionModel", "RidgeRegressionWithSGD", "SVMModel", "SVMWithSGD"]

@@ -238,3 +238,27 @@ def test_col_stats_standard_scaler_and_append_bias_dense_and_csr():
             wb = append_bias(ds)
             sh0 = wb.shards()[0]
             assert sh0.num_features == 7 and bool((sh0.to_dense().X[:, 6] == 1.0).all())
+
+
+def test_regression_and_binary_classification_metrics_match_sklearn():
+    import numpy as np
+    from sklearn import metrics as skm
+    from asyncframework_b200.core.scheduler import Scheduler
+    from asyncframework_b200.data import ShardedDataset
+    from asyncframework_b200.models import BinaryClassificationMetrics, RegressionMetrics
+    rng = np.random.default_rng(4)
+    y = rng.standard_normal(300)
+    p = y + 0.3 * rng.standard_normal(300)
+    with Scheduler(2) as s:
+        rm = RegressionMetrics(ShardedDataset.from_records(s, list(zip(p.tolist(), y.tolist())), 3))
+    assert np.isclose(rm.mean_squared_error, skm.mean_squared_error(y, p)) and np.isclose(rm.mean_absolute_error, skm.mean_absolute_error(y, p))
+    assert np.isclose(rm.r2, skm.r2_score(y, p)) and np.isclose(rm.root_mean_squared_error, np.sqrt(skm.mean_squared_error(y, p)))
+    labels = (rng.random(400) < 0.4).astype(float)
+    scores = np.round(0.35 * labels + 0.65 * rng.random(400), 2)                  # rounded: ties between classes exist
+    bm = BinaryClassificationMetrics(torch.from_numpy(scores), torch.from_numpy(labels))
+    assert np.isclose(bm.area_under_roc, skm.roc_auc_score(labels, scores))
+    prec, rec, _ = skm.precision_recall_curve(labels, scores)
+    assert abs(bm.area_under_pr - skm.auc(rec, prec)) < 0.01                        # same curve, different end-point convention
+    assert bm.roc()[0] == (0.0, 0.0) and bm.roc()[-1] == (1.0, 1.0) and len(bm.thresholds()) == len(set(scores.tolist()))
+    best_t, best_f = max(bm.f_measure_by_threshold(), key=lambda tf: tf[1])
+    assert np.isclose(best_f, skm.f1_score(labels, scores >= best_t))
