@@ -65,8 +65,9 @@ class ExecutorBackend:
     immediately, task launches are queued for the task thread — so a cancellation overtakes the tasks that are
     still queued behind a running one."""
 
-    def __init__(self, eid: int, send: Callable[[tuple], None]):
+    def __init__(self, eid: int, send: Callable[[tuple], None], cores: int = 1):
         self.eid = eid
+        self.cores = max(1, int(cores))              # spark.executor.cores: task slots = concurrent task threads
         self._send = send
         self.binaries: Dict[int, Any] = {}
         self.tasks: "_queue.Queue" = _queue.Queue()
@@ -80,7 +81,8 @@ class ExecutorBackend:
     def handle(self, msg: tuple) -> bool:
         kind = msg[0]
         if kind == "stop":
-            self.tasks.put(None)
+            for _ in range(self.cores):
+                self.tasks.put(None)
             return False
         if kind == "binary":
             try:
@@ -100,7 +102,8 @@ class ExecutorBackend:
 
     def close(self) -> None:
         self._closed = True
-        self.tasks.put(None)
+        for _ in range(self.cores):
+            self.tasks.put(None)
 
     def start_heartbeats(self, interval: float) -> None:
         """Executor -> driver liveness + progress (``Executor.reportHeartBeat``, executor/Executor.scala:770-815): a
@@ -123,6 +126,16 @@ class ExecutorBackend:
     active_task = None
 
     def run_tasks(self) -> None:
+        """Runs the task loop on the calling thread plus ``cores - 1`` helper threads; returns when all have stopped."""
+        helpers = [threading.Thread(target=self._task_loop, daemon=True, name=f"executor-{self.eid}-task-{i}")
+                   for i in range(1, self.cores)]
+        for t in helpers:
+            t.start()
+        self._task_loop()
+        for t in helpers:
+            t.join(timeout=5)
+
+    def _task_loop(self) -> None:
         from .env import AsyncEnv
         from ..storage.block_manager import StorageLevel
         while True:
@@ -166,7 +179,7 @@ class ExecutorBackend:
                 self.active_task = None
 
 
-def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
+def _executor_main(eid: int, conn, driver_address=None, limits=None, cores: int = 1) -> None:
     """``local-cluster`` executor process: control messages over a pipe, blocks over its own RpcEnv."""
     import torch
     torch.set_num_threads(1)
@@ -174,7 +187,7 @@ def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
     if driver_address is not None:
         from .env import AsyncEnv
         env = AsyncEnv.create_executor(str(eid), driver_address, limits)
-    backend = ExecutorBackend(eid, conn.send)
+    backend = ExecutorBackend(eid, conn.send, cores)
 
     def receiver() -> None:
         while True:
@@ -200,8 +213,9 @@ def _executor_main(eid: int, conn, driver_address=None, limits=None) -> None:
 class PipeTransport:
     """``local-cluster[n]``: the scheduler forks ``n`` executor processes itself and talks to them over pipes."""
 
-    def __init__(self, num_executors: int, name: str):
+    def __init__(self, num_executors: int, name: str, cores_per_executor: int = 1):
         self.num_executors = num_executors
+        self.cores_per_executor = max(1, int(cores_per_executor))
         self.name = name
         self._ctx = mp.get_context("spawn")
         self._conns: List[Any] = [None] * num_executors
@@ -220,7 +234,7 @@ class PipeTransport:
         env = self.sched.env
         p = self._ctx.Process(target=_executor_main, name=f"{self.name}-executor-{e}", daemon=True,
                               args=(e, child, tuple(env.rpc_env.address) if env is not None else None,
-                                    env.limits if env is not None else None))
+                                    env.limits if env is not None else None, self.cores_per_executor))
         p.start()
         child.close()
         self._conns[e], self._procs[e] = parent, p
@@ -284,7 +298,8 @@ class ClusterScheduler:
                  name: str = "afb-cluster", transport=None, limits=None, recover_lost_executors: bool = False,
                  use_env: bool = True, speculation: bool = False, speculation_multiplier: float = 1.5,
                  speculation_quantile: float = 0.75, speculation_interval: float = 0.1, speculation_min_ms: float = 100.0,
-                 blacklist: bool = False, blacklist_max_failures: int = 2, blacklist_timeout: float = 3600.0):
+                 blacklist: bool = False, blacklist_max_failures: int = 2, blacklist_timeout: float = 3600.0,
+                 cores_per_executor: int = 1):
         self.num_executors = int(num_executors)
         self.max_failures = int(max_failures)
         self.block_first_async_job = block_first_async_job
@@ -324,7 +339,7 @@ class ClusterScheduler:
         if use_env:
             from .env import AsyncEnv, RuntimeLimits
             self.env = AsyncEnv.create_driver(limits or RuntimeLimits(), name=f"{name}-driver")
-        self.transport = transport if transport is not None else PipeTransport(self.num_executors, name)
+        self.transport = transport if transport is not None else PipeTransport(self.num_executors, name, cores_per_executor)
         try:
             self.transport.start(self)
         except BaseException:

@@ -56,6 +56,9 @@ class AsyncSession:
                           blacklist_timeout=rc.get("spark.blacklist.timeout"))
         if master.startswith("local-cluster"):
             from .cluster import ClusterScheduler
+            m = _LOCAL_CLUSTER.match(master)
+            if m and m.group(2):                          # local-cluster[n, coresPerExecutor, memoryMB]
+                cluster_kw["cores_per_executor"] = int(m.group(2))
             self.scheduler = ClusterScheduler(n, recover_lost_executors=rc.contains("spark.async.recoverLostExecutors")
                                               and rc.get("spark.async.recoverLostExecutors"), **cluster_kw)
         elif master.startswith(("spark://", "async://")):

@@ -29,7 +29,7 @@ def main(argv=None) -> int:
     a = ap.parse_args(argv)
 
     import torch
-    torch.set_num_threads(max(1, a.cores))
+    torch.set_num_threads(1)          # parallelism comes from a.cores concurrent task threads, not from intra-op threads
     from ..core.cluster import ExecutorBackend
     from ..core.env import AsyncEnv, RuntimeLimits
     from ..rpc import RpcAddress, RpcEndpoint, RpcError
@@ -42,7 +42,7 @@ def main(argv=None) -> int:
         limits.storage_memory = int(mem_mb * (1 << 20) * 0.6)          # spark.memory.fraction of the executor's grant
     env = AsyncEnv.create_executor(str(a.slot), driver_addr, limits, host=a.host)
     driver = env.rpc_env.endpoint_ref(driver_addr, "CoarseGrainedScheduler")
-    backend = ExecutorBackend(a.slot, lambda msg: driver.send(("status", a.slot, a.executor_id, msg)))
+    backend = ExecutorBackend(a.slot, lambda msg: driver.send(("status", a.slot, a.executor_id, msg)), a.cores)
 
     class ExecutorEndpoint(RpcEndpoint):
         def receive(self, msg, sender):

@@ -421,3 +421,23 @@ def test_context_cleaner_frees_broadcast_pieces_and_shipped_source_blocks():
         before = held()
         del big
         assert eventually(lambda: max(held()) < max(before))
+
+
+def test_executor_cores_are_concurrent_task_slots():
+    """``local-cluster[n, c, m]`` / ``spark.executor.cores``: an executor with c cores runs c tasks at the same time."""
+    from asyncframework_b200.core.session import AsyncSession
+
+    def slow(tctx, it):
+        t0 = time.time()
+        time.sleep(0.5)
+        return (os.getpid(), t0, time.time())
+    for cores, expect_overlap in ((1, False), (2, True)):
+        with AsyncSession(f"local-cluster[1,{cores},512]") as sc:
+            ds = sc.parallelize(range(4), 2)
+            assert ds.count() == 4                                           # warm the executor up
+            t0 = time.time()
+            (p0, a0, b0), (p1, a1, b1) = sc.scheduler.run_job(ds, slow)
+            wall = time.time() - t0
+            assert p0 == p1                                                  # one executor process
+            overlap = min(b0, b1) - max(a0, a1) > 0.2
+            assert overlap == expect_overlap and (wall < 0.95 if expect_overlap else wall > 0.95)
