@@ -146,15 +146,13 @@ _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partition
        leftOuterJoin="left_outer_join", rightOuterJoin="right_outer_join", fullOuterJoin="full_outer_join",
        subtractByKey="subtract_by_key", sortByKey="sort_by_key", collectAsMap="collect_as_map", takeOrdered="take_ordered",
        isEmpty="is_empty", randomSplit="random_split", saveAsTextFile="save_as_text_file", toLocalIterator="to_local_iterator",
-       setName="set_name", toDebugString="to_debug_string")
+       setName="set_name", toDebugString="to_debug_string", zipPartitions="zip_partitions", getStorageLevel="get_storage_level",
+       saveAsPickleFile="save_as_pickle_file", mapShards="map_shards", ASYNCgrad="async_grad")
+_alias(SparkContext, setJobGroup="set_job_group", clearJobGroup="clear_job_group", cancelJobGroup="cancel_job_group",
+       addFile="add_file", wholeTextFiles="whole_text_files", pickleFile="pickle_file", emptyRDD="empty_dataset",
+       applicationId=property(lambda self: self.application_id), uiWebUrl=property(lambda self: self.ui_web_url))
 _alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
        cancelJob=lambda self, job_id: self.scheduler.cancel_job(job_id), cancelAllJobs=lambda self: self.scheduler.cancel_all_jobs())
-
-def _persist(self, level=None):
-    """``rdd.persist(StorageLevel)``: the level is advisory — executor block managers store cached partitions MEMORY_ONLY and
-    recompute evicted ones (the behaviour every ASYNC sample relies on)."""
-    return self.cache()
-
 
 def _checkpoint(self, directory: Optional[str] = None):
     import os
@@ -167,7 +165,6 @@ def _checkpoint(self, directory: Optional[str] = None):
 if not hasattr(RDD, "checkpoint_to"):
     RDD.checkpoint_to = RDD.checkpoint                 # the explicit-directory form stays available
     RDD.checkpoint = _checkpoint
-RDD.persist = _persist
 
 __all__ = ["SparkConf", "StorageLevel", "Matrices", "DenseMatrix", "SparseMatrix", "LBFGS", "LogisticRegressionWithLBFGS",
            "RidgeRegressionWithSGD", "LassoWithSGD", "SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",

@@ -631,6 +631,16 @@ class ClusterScheduler:
             ids = list(self._jobs)
         return sum(1 for j in ids if self.cancel_job(j))
 
+    def cancel_job_group(self, group_id: str) -> int:
+        with self._lock:
+            ids = [j for j, job in self._jobs.items() if getattr(job["waiter"], "group", None) == group_id]
+        return sum(1 for j in ids if self.cancel_job(j, f"cancelled as part of job group {group_id}"))
+
+    def active_job_ids(self, group_id: Optional[str] = None) -> List[int]:
+        with self._lock:
+            return sorted(j for j, job in self._jobs.items()
+                          if not job["waiter"].done and (group_id is None or getattr(job["waiter"], "group", None) == group_id))
+
     def _executor_lost(self, eid: int) -> None:
         if self._stopped:
             return
@@ -706,6 +716,8 @@ class ClusterScheduler:
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
         job_id = next(ClusterScheduler._job_ids)
         waiter = JobWaiter(job_id, len(parts), result_handler)
+        from .scheduler import _job_group
+        waiter.group = getattr(_job_group, "id", None)   # type: ignore[attr-defined]
         now = time.perf_counter() * 1e3
         assigned = {p: self._route(p) for p in parts}
         executors = sorted(set(assigned.values()))

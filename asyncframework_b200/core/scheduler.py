@@ -46,6 +46,13 @@ class TaskContext:
         return bool(getattr(self.job, "cancelled", False))
 
 
+_job_group = threading.local()          # sc.setJobGroup: a property of the submitting thread (SparkContext.setLocalProperty)
+
+
+def set_job_group(group_id: Optional[str]) -> None:
+    _job_group.id = group_id
+
+
 class JobFailed(RuntimeError):
     pass
 
@@ -252,6 +259,7 @@ class Scheduler:
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
         job = JobWaiter(next(Scheduler._job_ids), len(parts), result_handler)
         job.on_task_lost = on_task_lost  # type: ignore[attr-defined]
+        job.group = getattr(_job_group, "id", None)       # type: ignore[attr-defined]  (sc.setJobGroup is per submitting thread)
         with self._jobs_lock:
             self._active = {j: w for j, w in self._active.items() if not w.done}
             self._active[job.job_id] = job
@@ -290,6 +298,16 @@ class Scheduler:
         job.cancel(reason)
         self.listeners.post({"event": "job_end", "job": job_id, "cancelled": True, "t_ms": time.perf_counter() * 1e3})
         return True
+
+    def cancel_job_group(self, group_id: str) -> int:
+        """``SparkContext.cancelJobGroup``: cancel every active job submitted under ``set_job_group(group_id)``."""
+        with self._jobs_lock:
+            ids = [j for j, w in self._active.items() if not w.done and getattr(w, "group", None) == group_id]
+        return sum(1 for j in ids if self.cancel_job(j, f"cancelled as part of job group {group_id}"))
+
+    def active_job_ids(self, group_id: Optional[str] = None) -> List[int]:
+        with self._jobs_lock:
+            return sorted(j for j, w in self._active.items() if not w.done and (group_id is None or getattr(w, "group", None) == group_id))
 
     def cancel_all_jobs(self) -> int:
         """``SparkContext.cancelAllJobs``: returns how many jobs were cancelled."""

@@ -24,6 +24,35 @@ _LOCAL_N = re.compile(r"^local\[(\*|\d+)(?:\s*,\s*(\d+))?\]$")
 _LOCAL_CLUSTER = re.compile(r"^local-cluster\[\s*(\d+)\s*(?:,\s*(\d+)\s*(?:,\s*(\d+)\s*)?)?\]$")
 
 
+_added_files: dict = {}            # file name -> Broadcast of its bytes (sc.addFile)
+
+
+class SparkFiles:
+    """``SparkFiles.get(name)`` inside a task: local path of a file shipped with ``sc.add_file``."""
+    _dir: Optional[str] = None
+    _written: set = set()
+    registry = _added_files           # pickled BY VALUE inside closures that call SparkFiles.get through `files=`
+
+    @classmethod
+    def get_root_directory(cls) -> str:
+        import tempfile
+        if cls._dir is None:
+            cls._dir = tempfile.mkdtemp(prefix="afb-files-")
+        return cls._dir
+
+    @classmethod
+    def get(cls, name: str, files: Optional[dict] = None) -> str:
+        reg = files if files is not None else cls.registry
+        if name not in reg:
+            raise FileNotFoundError(f"{name} was not added with sc.add_file (in a cluster closure pass files=sc.files)")
+        path = os.path.join(cls.get_root_directory(), name)
+        if name not in cls._written or not os.path.exists(path):
+            with open(path, "wb") as f:
+                f.write(reg[name].value)
+            cls._written.add(name)
+        return path
+
+
 class AsyncSession:
     def __init__(self, master: Optional[str] = None, app_name: Optional[str] = None, device=None,
                  conf=None, num_executors: Optional[int] = None, cores_per_executor: Optional[int] = None,
@@ -199,6 +228,46 @@ class AsyncSession:
 
     def async_broadcast(self, ctx: AsyncContext, value: Any, slots: int = 8) -> AsyncBroadcast:
         return AsyncBroadcast(ctx, value, slots)
+
+    # ---- job groups, files, identity ------------------------------------------------------------------------
+    def set_job_group(self, group_id: Optional[str], description: str = "") -> None:
+        """``sc.setJobGroup``: jobs submitted by THIS thread from now on belong to ``group_id`` (``None`` clears it)."""
+        from .scheduler import set_job_group
+        set_job_group(group_id)
+
+    def clear_job_group(self) -> None:
+        self.set_job_group(None)
+
+    def cancel_job_group(self, group_id: str) -> int:
+        return self.scheduler.cancel_job_group(group_id)
+
+    def add_file(self, path: str) -> None:
+        """``sc.addFile``: make a driver-side file available to every task as ``SparkFiles.get(name)`` (the bytes travel as a
+        broadcast — torrent on cluster masters — and are written once per executor process)."""
+        with open(path, "rb") as f:
+            data = f.read()
+        name = os.path.basename(path)
+        _added_files[name] = self.broadcast(data)
+
+    @property
+    def files(self) -> dict:
+        """The added files (name -> broadcast); capture it in closures that run on executor processes:
+        ``lambda x, files=sc.files: open(SparkFiles.get("lookup.txt", files))``."""
+        return dict(_added_files)
+
+    @property
+    def application_id(self) -> str:
+        t = getattr(self.scheduler, "transport", None)
+        return getattr(t, "app_id", None) or f"local-{id(self):x}"
+
+    @property
+    def ui_web_url(self) -> Optional[str]:
+        return self.ui.url if getattr(self, "ui", None) is not None else None
+
+    @property
+    def version(self) -> str:
+        from .. import __version__
+        return __version__
 
     # ---- job mode / misc ---------------------------------------------------------------------
     def set_mode(self, mode: int) -> None:

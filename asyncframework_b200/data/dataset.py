@@ -65,12 +65,14 @@ def _cache_get(ds_id: int, p: int, kind: str):
     return (True, _BLOCK_STORE[key]) if key in _BLOCK_STORE else (False, None)
 
 
-def _cache_put(ds_id: int, p: int, kind: str, value) -> None:
+def _cache_put(ds_id: int, p: int, kind: str, value, level=None) -> None:
     from ..core.env import AsyncEnv
     env = AsyncEnv.get()
     if env is not None and not env.is_driver:
         from ..storage.block_manager import StorageLevel
-        env.block_manager.put_single(f"rdd_{ds_id}_{p}{kind}", value, StorageLevel.MEMORY_ONLY)   # does not fit -> recomputed next time
+        # MEMORY_ONLY (``cache()``): a partition that does not fit is recomputed next time; ``persist(MEMORY_AND_DISK)`` /
+        # ``DISK_ONLY`` spill to the executor's disk store instead (RDD.persist, storage/StorageLevel.scala)
+        env.block_manager.put_single(f"rdd_{ds_id}_{p}{kind}", value, level or StorageLevel.MEMORY_ONLY)
         return
     _BLOCK_STORE[(ds_id, p, kind)] = value
 
@@ -261,7 +263,7 @@ class ShardedDataset:
                 if self._cached_records is None:
                     self._cached_records = [None] * self.num_partitions
                 self._cached_records[p] = recs
-            _cache_put(self.ds_id, p, "r", recs)
+            _cache_put(self.ds_id, p, "r", recs, getattr(self, "_storage_level", None))
             return iter(recs)
         return it
 
@@ -280,7 +282,7 @@ class ShardedDataset:
                 if self._cached_batches is None:
                     self._cached_batches = [_EMPTY] * self.num_partitions
                 self._cached_batches[p] = b
-            _cache_put(self.ds_id, p, "b", b)
+            _cache_put(self.ds_id, p, "b", b, getattr(self, "_storage_level", None))
         return b
 
     def cache(self) -> "ShardedDataset":
@@ -288,7 +290,17 @@ class ShardedDataset:
         self._want_cache = True
         return self
 
-    persist = cache
+    def persist(self, level=None) -> "ShardedDataset":
+        """``rdd.persist(StorageLevel)``: like ``cache()`` but executor processes store the partitions at ``level``
+        (``MEMORY_AND_DISK`` / ``DISK_ONLY`` spill instead of recomputing; in-process masters keep references either way)."""
+        self._storage_level = level
+        return self.cache()
+
+    def get_storage_level(self):
+        from ..storage.block_manager import StorageLevel
+        if not self._want_cache:
+            return StorageLevel.NONE
+        return getattr(self, "_storage_level", None) or StorageLevel.MEMORY_ONLY
 
     def checkpoint(self, directory: str) -> "ShardedDataset":
         """``rdd.checkpoint()`` (RDD.scala:1773, ReliableCheckpointRDD.scala:121-210): every partition is materialised by a job
@@ -717,9 +729,43 @@ class ShardedDataset:
             raise ValueError("empty collection")
         return s / n
 
-    def coalesce(self, num_partitions: int) -> "ShardedDataset":
-        """``rdd.coalesce(n, shuffle = true)`` == repartition (the form the reference uses, RDD.scala:420-475)."""
-        return self.repartition(num_partitions)
+    def coalesce(self, num_partitions: int, shuffle: bool = True) -> "ShardedDataset":
+        """``rdd.coalesce(n, shuffle = true)`` == repartition (the form the reference uses, RDD.scala:420-475).  With
+        ``shuffle=False`` the parent partitions are merged locally into ``n`` contiguous groups (narrow dependency: no data
+        leaves its executor group, like ``CoalescedRDD``); asking for more partitions than exist is then a no-op."""
+        if shuffle:
+            return self.repartition(num_partitions)
+        n = max(1, min(int(num_partitions), self.num_partitions))
+        P = self.num_partitions
+        groups = [list(range(P * g // n, P * (g + 1) // n)) for g in range(n)]
+        parent = self
+
+        def compute(p, t):
+            return itertools.chain.from_iterable(parent.iterator(q, t) for q in groups[p])
+        return ShardedDataset(self.scheduler, n, compute, None, self, "coalesce")
+
+    def zip_partitions(self, other: "ShardedDataset", f) -> "ShardedDataset":
+        """``rdd.zipPartitions(other)(f)``: ``f(iterator_a, iterator_b) -> iterator`` per co-indexed partition pair."""
+        if other.num_partitions != self.num_partitions:
+            raise ValueError("zip_partitions: both datasets must have the same number of partitions")
+        ds = self._derive(lambda p, t: f(self.iterator(p, t), other.iterator(p, t)), None, "zip_partitions")
+        ds._zip_other = other  # type: ignore[attr-defined]
+        return ds
+
+    def pipe(self, command, env: Optional[dict] = None) -> "ShardedDataset":
+        """``rdd.pipe(cmd)``: every partition is streamed line by line through an external process; its stdout lines are the
+        result (PipedRDD).  ``command`` is a string (split like a shell word list) or an argv list."""
+        import shlex
+        import subprocess
+        argv = shlex.split(command) if isinstance(command, str) else list(command)
+
+        def compute(p, t):
+            data = "".join(str(r) + "\n" for r in self.iterator(p, t))
+            res = subprocess.run(argv, input=data, capture_output=True, text=True, env={**os.environ, **(env or {})})
+            if res.returncode != 0:
+                raise RuntimeError(f"Subprocess exited with status {res.returncode}. Command ran: {' '.join(argv)}: {res.stderr[-300:]}")
+            return iter(res.stdout.splitlines())
+        return self._derive(compute, None, "pipe")
 
     def zip_with_unique_id(self) -> "ShardedDataset":
         """``rdd.zipWithUniqueId``: ids k, k+P, k+2P, ... in partition k — unique without the counting job zip_with_index needs."""

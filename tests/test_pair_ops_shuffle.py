@@ -127,3 +127,62 @@ def test_sampling_with_replacement_io_helpers_and_shell(sc, tmp_path):
                           "print('SUM', sc.parallelize(range(10)).map(lambda x: x * x).reduce(lambda a, b: a + b))"],
                          capture_output=True, text=True, timeout=120, cwd=root, env={**os.environ, "PYTHONPATH": root})
     assert res.returncode == 0 and "SUM 285" in res.stdout, res.stderr[-800:]
+
+
+def test_narrow_coalesce_zip_partitions_pipe_job_groups_and_files(sc, tmp_path):
+    import threading
+    from asyncframework_b200.core.scheduler import JobCancelled
+    from asyncframework_b200.core.session import SparkFiles
+    ds = sc.parallelize(range(12), 6)
+    co = ds.coalesce(2, shuffle=False)
+    assert co.num_partitions == 2 and co.glom().collect() == [[0, 1, 2, 3, 4, 5], [6, 7, 8, 9, 10, 11]]      # contiguous, order kept
+    assert ds.coalesce(50, shuffle=False).num_partitions == 6
+    zp = ds.zip_partitions(ds.map(lambda x: x * 10), lambda a, b: [sum(a) + sum(b)])
+    assert zp.collect() == [(2 * p + 2 * p + 1) * 11 for p in range(6)]
+    assert sc.parallelize(["b", "a", "c", "a"], 2).pipe("sort").collect() == ["a", "b", "a", "c"]
+    with pytest.raises(Exception, match="status"):
+        sc.parallelize(["x"], 1).pipe(["false"]).collect()
+    # job groups: cancel only the jobs of one group
+    sc.set_job_group("slow-group")
+    gate = threading.Event()
+    w1 = sc.scheduler.submit_job(ds, lambda t, it: gate.wait(10))
+    sc.set_job_group("other")
+    w2 = sc.scheduler.submit_job(ds, lambda t, it: sum(it))
+    sc.clear_job_group()
+    assert w1.job_id in sc.scheduler.active_job_ids("slow-group")
+    assert sc.cancel_job_group("slow-group") == 1
+    gate.set()
+    with pytest.raises(JobCancelled):
+        w1.wait(5)
+    assert w2.wait(5)
+    # files
+    f = tmp_path / "lookup.txt"
+    f.write_text("forty-two")
+    sc.add_file(str(f))
+    assert ds.map(lambda x, files=sc.files: open(SparkFiles.get("lookup.txt", files)).read()).distinct().collect() == ["forty-two"]
+    assert sc.version and sc.application_id.startswith("local-") and sc.ui_web_url is None
+
+
+def test_persist_levels_spill_to_the_executor_disk_store_and_files_reach_executor_processes(tmp_path):
+    from asyncframework_b200.conf import AsyncConf
+    from asyncframework_b200.core.session import SparkFiles
+    from asyncframework_b200.storage import StorageLevel
+    conf = AsyncConf(load_defaults=False).set("spark.executor.memory", "1m").set("spark.memory.fraction", 0.5)   # 512 KB of storage memory
+    with AsyncSession("local-cluster[2]", conf=conf) as sc:
+        big = sc.parallelize([bytes(2000)] * 800, 4)                                  # ~400 KB per partition, 2 partitions per executor
+        kept = big.map(lambda b: b).persist(StorageLevel.MEMORY_AND_DISK)
+        assert kept.count() == 800 and kept.get_storage_level() == StorageLevel.MEMORY_AND_DISK
+        st = sc.scheduler.storage_status()
+        mine = {b: v for s in st.values() for b, v in s["blocks"].items() if b.startswith(f"rdd_{kept.ds_id}_")}
+        assert len(mine) == 4 and any(disk > 0 for _, disk in mine.values())          # what did not fit in memory is on disk
+        assert kept.count() == 800
+        mem_only = big.map(lambda b: b + b"").cache()
+        assert mem_only.count() == 800
+        st = sc.scheduler.storage_status()
+        mo = {b: v for s in st.values() for b, v in s["blocks"].items() if b.startswith(f"rdd_{mem_only.ds_id}_")}
+        assert all(disk == 0 for _, disk in mo.values())                               # MEMORY_ONLY never spills
+        f = tmp_path / "side.txt"
+        f.write_text("side-data")
+        sc.add_file(str(f))
+        out = sc.parallelize(range(4), 2).map(lambda x, files=sc.files: (os.getpid(), open(SparkFiles.get("side.txt", files)).read())).collect()
+        assert {v for _, v in out} == {"side-data"} and os.getpid() not in {p for p, _ in out}
