@@ -31,6 +31,7 @@ class SparkFiles:
     """``SparkFiles.get(name)`` inside a task: local path of a file shipped with ``sc.add_file``."""
     _dir: Optional[str] = None
     _written: set = set()
+    _lock = __import__("threading").Lock()
     registry = _added_files           # pickled BY VALUE inside closures that call SparkFiles.get through `files=`
 
     @classmethod
@@ -46,10 +47,13 @@ class SparkFiles:
         if name not in reg:
             raise FileNotFoundError(f"{name} was not added with sc.add_file (in a cluster closure pass files=sc.files)")
         path = os.path.join(cls.get_root_directory(), name)
-        if name not in cls._written or not os.path.exists(path):
-            with open(path, "wb") as f:
-                f.write(reg[name].value)
-            cls._written.add(name)
+        with cls._lock:                                # executor THREADS of an in-process master share this directory
+            if name not in cls._written or not os.path.exists(path):
+                tmp = f"{path}.{os.getpid()}.tmp"
+                with open(tmp, "wb") as f:
+                    f.write(reg[name].value)
+                os.replace(tmp, path)                   # readers never see a half-written file
+                cls._written.add(name)
         return path
 
 

@@ -153,8 +153,8 @@ def test_narrow_coalesce_zip_partitions_pipe_job_groups_and_files(sc, tmp_path):
     assert sc.cancel_job_group("slow-group") == 1
     gate.set()
     with pytest.raises(JobCancelled):
-        w1.wait(5)
-    assert w2.wait(5)
+        w1.wait(30)
+    assert w2.wait(30)
     # files
     f = tmp_path / "lookup.txt"
     f.write_text("forty-two")

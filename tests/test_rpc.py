@@ -38,7 +38,7 @@ class Echo(RpcEndpoint):
         self.events.append(("disconnected", address))
 
 
-def _wait(pred, timeout=5.0):
+def _wait(pred, timeout=20.0):
     t0 = time.time()
     while time.time() - t0 < timeout:
         if pred():
@@ -127,7 +127,7 @@ def test_disconnect_fails_outstanding_asks_and_notifies_endpoints():
     client.setup_endpoint("watch", cep)
     server.shutdown()
     with pytest.raises(RpcDisconnected):
-        fut.result(5)
+        fut.result(20)
     assert _wait(lambda: any(e[0] == "disconnected" for e in cep.events))
     with pytest.raises(RpcError):
         ref.ask_sync(2, timeout=2)
