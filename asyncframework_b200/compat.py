@@ -125,6 +125,30 @@ class MLUtils(_MLUtils):
         save_as_libsvm_file(data, dir_path)
 
 
+# --- PySpark keyword spellings on the train() entry points ---------------------------------------------------------
+_KW = {"miniBatchFraction": "mini_batch_fraction", "initialWeights": "initial_weights", "regParam": "reg_param", "regType": "reg_type",
+       "validateData": "validate_data", "convergenceTol": "convergence_tol", "numIterations": "iterations", "stepSize": "step"}
+
+
+def _camel_train(cls):
+    """``LinearRegressionWithSGD.train(data, iterations=100, step=1.0, miniBatchFraction=1.0, initialWeights=None, regParam=0.0,
+    regType=None, intercept=False, validateData=True, convergenceTol=0.001)`` (python/pyspark/mllib/regression.py:229)."""
+    orig = cls.__dict__["train"].__func__
+    if getattr(orig, "_camel", False):
+        return
+
+    def train(klass, data, *args, **kw):
+        return orig(klass, data, *args, **{_KW.get(k, k): v for k, v in kw.items()})
+    train._camel = True          # type: ignore[attr-defined]
+    train.__doc__ = orig.__doc__
+    cls.train = classmethod(train)
+
+
+for _c in (LinearRegressionWithSGD, LogisticRegressionWithSGD, SVMWithSGD, LogisticRegressionWithLBFGS):
+    if "train" in _c.__dict__:
+        _camel_train(_c)
+
+
 # --- camelCase accessors on the shared classes (added once, idempotent) -----------------------------------
 def _alias(cls, **names):
     for new, old in names.items():
