@@ -9,4 +9,6 @@ DRIVERS = {"asgd": asgd.run, "asaga": asaga.run, "sgd_sync": sgd_sync.run, "saga
 
 
 def run(cfg, points=None, scheduler=None):
-    return DRIVERS[cfg.algorithm](cfg, points, scheduler) if cfg.algorithm != "sgd_mllib" else sgd_mllib.run(cfg, points, scheduler)
+    from .common import host_math_threads
+    with host_math_threads():          # the driver thread does small-vector math only; see host_math_threads
+        return DRIVERS[cfg.algorithm](cfg, points, scheduler) if cfg.algorithm != "sgd_mllib" else sgd_mllib.run(cfg, points, scheduler)

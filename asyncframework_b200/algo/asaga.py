@@ -92,6 +92,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         start = now_ms()
 
         def updater():
+            from .common import host_math_threads
+            host_math_threads.pin()                        # small-vector math: one intra-op thread for this thread
             while state["k"] < iters:
                 bsize = AC.size()
                 if bsize == 0:

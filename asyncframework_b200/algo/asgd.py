@@ -70,6 +70,8 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         wlock = threading.Lock() if cfg.extra.get("lock_w", False) else None   # Hogwild by default (:189 vs :242)
 
         def updater():
+            from .common import host_math_threads
+            host_math_threads.pin()                        # small-vector math: one intra-op thread for this thread
             while state["k"] < iters:
                 bsize = AC.size()
                 if bsize == 0:

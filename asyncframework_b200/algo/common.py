@@ -165,6 +165,32 @@ class HostCheckpointer:
             self._writer = None
 
 
+class host_math_threads:
+    """Driver-side vector math (``w`` updates, snapshots, broadcasts of d <= ~50 k elements) is far below the size where
+    intra-op threading pays, and on a shared box the OpenMP fork/join costs milliseconds per op (measured: 8.4 ms vs 11 us for a
+    378 KB clone).  ``with host_math_threads():`` pins the CALLING thread to one intra-op thread and restores the old value —
+    the setting is per thread, so executor threads and other sessions are unaffected.  Also usable as a plain call at the top of
+    a helper thread (``host_math_threads.pin()``)."""
+
+    def __init__(self, n: int = 1):
+        self.n = n
+        self.prev = None
+
+    def __enter__(self):
+        self.prev = torch.get_num_threads()
+        torch.set_num_threads(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.set_num_threads(self.prev)
+        return False
+
+    @staticmethod
+    def pin(n: int = 1) -> None:
+        torch.set_num_threads(n)
+
+
 class WorkerLost(RuntimeError):
     """A synchronous (BSP) run cannot make progress without every worker."""
 
@@ -182,7 +208,8 @@ def run_cli(algorithm: str, main_fn: Callable[[AsyncConfig], object], argv: Opti
                                              "step_size", "taw", "batch_rate", "bucket_ratio", "printer_freq", "coeff", "seed")]
     for k, v in layout:                       # the reference echoes its parameters
         print(f"{k}: {v}")
-    report = main_fn(cfg)
+    with host_math_threads():
+        report = main_fn(cfg)
     if report is not None and hasattr(report, "print_reference_style"):
         report.print_reference_style()
     return report

@@ -27,6 +27,15 @@ _bcast_ids = itertools.count(0)
 
 def _snapshot(value: Any) -> Any:
     if isinstance(value, torch.Tensor):
+        if not value.is_cuda and value.numel() < (1 << 20) and torch.get_num_threads() > 1:
+            # parameter-sized CPU copy: the OpenMP fork/join of a multi-threaded clone costs far more than the copy itself
+            # (measured on a shared box: 8.4 ms vs 11 us for 378 KB); at::set_num_threads is per calling thread
+            prev = torch.get_num_threads()
+            torch.set_num_threads(1)
+            try:
+                return value.detach().clone()
+            finally:
+                torch.set_num_threads(prev)
         return value.detach().clone()
     if isinstance(value, DenseVector):
         return value.copy()

@@ -173,6 +173,11 @@ class Scheduler:
 
     # ------------------------------------------------------------------ executors
     def _executor_loop(self, eid: int) -> None:
+        # ``local[N]`` = N task slots sharing the machine: every executor thread gets its share of the cores for intra-op
+        # parallelism (at::set_num_threads is per calling thread under OpenMP).  Without this, N tasks x all-cores intra-op
+        # threads oversubscribe the box — measured here: a 378 KB ``clone()`` costs 8.4 ms with 8 intra-op threads vs 11 us with 1.
+        import os as _os
+        torch.set_num_threads(max(1, (_os.cpu_count() or 1) // max(1, self.num_executors)))
         stream = None
         if self.device is not None and self.device.type == "cuda":
             torch.cuda.set_device(self.device)

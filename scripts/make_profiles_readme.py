@@ -113,6 +113,27 @@ if os.path.exists(hr):
             f"Result queue ({rq['producers']} producer threads, {rq['records']} records): {rq['single_take_mrec_s']} M records/s with single takes, "
             f"{rq['batch64_take_mrec_s']} M records/s with `take_batch(64)` (`AsyncContext.drain`).  Worker table (P = {wt['P']}, through ctypes): "
             f"{wt['task_done_mops_s']} M `task_done`/s, {wt['available_workers_scan_mops_s']} M `available_workers` scans/s.", ""]
+cp = os.path.join(ROOT, "profiles", "control_plane.json")
+if os.path.exists(cp):
+    c = json.load(open(cp))
+    out += ["## Host control plane (closure API on `local[N]` / `local-cluster[n]` / `spark://`; measured on the build container: "
+            "`benchmarks/control_plane_bench.py`)", "",
+            "What the reference pays EVERY round on its JVM/Netty plane (broadcast of `w`, task-binary broadcast, LaunchTask + StatusUpdate RPCs, "
+            "single-threaded driver loop) is what the fused backend moved into the kernel; this is the cost of the same plane here, for the closure API.", "",
+            "| RPC (loopback TCP, two envs in one process) | ask p50 | ask p99 | one-way msgs/s | chunk fetch 4 MiB | chunk fetch 64 MiB |", "|---|---|---|---|---|---|"]
+    for k, label in (("rpc_plain", "plain"), ("rpc_aes_gcm", "HMAC auth + AES-256-GCM")):
+        r = c[k]
+        out.append(f"| {label} | {r['ask_p50_us']} us | {r['ask_p99_us']} us | {r['oneway_msgs_per_s']} | {r['chunk_fetch_4MiB_MBps']} MB/s | {r['chunk_fetch_64MiB_MBps']} MB/s |")
+    out += ["", "| master | blocking job (4 tasks) | round with w = 6 KB (mnist8m): broadcast / async reduce | w = 378 KB (rcv1) | w = 32 MB |", "|---|---|---|---|---|"]
+    for m, v in c["masters"].items():
+        f = lambda x: f"{x['broadcast_ms']} / {x['async_round_ms']} ms"  # noqa: E731
+        out.append(f"| `{m}` | {v['blocking_job_ms']} ms | {f(v['w_mnist8m_6KB'])} | {f(v['w_rcv1_378KB'])} | {f(v['w_32MB'])} |")
+    out += ["", "| codec (16 MB payloads) | float parameters: ratio, compress / decompress MB/s | 19 %-dense pixel bytes: ratio, compress / decompress MB/s |", "|---|---|---|"]
+    for name in ("lz4", "zstd", "zlib"):
+        a, b = c["codecs"][f"{name}_float_params"], c["codecs"][f"{name}_sparse_pixels"]
+        out.append(f"| {name} | {a['ratio']}x, {a['compress_MBps']} / {a['decompress_MBps']} | {b['ratio']}x, {b['compress_MBps']} / {b['decompress_MBps']} |")
+    out += ["", "(an asynchronous round = `sc.broadcast(w)` + non-blocking `async_reduce` over 4 partitions + draining the 4 results; on cluster "
+            "masters the broadcast is a torrent broadcast — serialise, compress, 4 MiB pieces with Adler32, peer-to-peer fetch by 2 executor processes.)", ""]
 ev = os.path.join(ROOT, "profiles", "bench", "eval_bench_r1.log")
 if os.path.exists(ev):
     out += ["## Objective evaluation (K12): tcgen05/TMEM GEMM vs exact CUDA-core kernel (1 GPU, 2 M x 784)", "",
