@@ -393,16 +393,17 @@ def test_context_cleaner_frees_broadcast_pieces_and_shipped_source_blocks():
     from asyncframework_b200.core.session import AsyncSession
     with AsyncSession("local-cluster[2]") as sc:
         ds = sc.parallelize(range(8), 4)
-        ids = []
+        ids, keep = [], []
         for r in range(5):                                        # the ASGD pattern: a new broadcast every round
             bc = sc.broadcast(torch.full((50_000,), float(r)))
             ids.append(bc.id)
+            keep.append(bc)                                       # (held on purpose: a dropped handle is cleaned immediately)
             assert ds.map(lambda i, bc=bc: float(bc.value[0])).collect() == [float(r)] * 8
         def pieces():
             st = sc.scheduler.storage_status()
             return sorted({b.split("_")[1] for s in st.values() for b in s["blocks"] if b.startswith("broadcast_")})
         assert len(pieces()) == 5
-        del bc
+        del bc, keep
 
         def eventually(pred, timeout=10.0):                       # cleanup is asynchronous by design (ContextCleanerSuite uses `eventually`)
             t0 = time.time()
