@@ -160,3 +160,21 @@ def test_authenticated_and_encrypted_cluster_end_to_end():
         bad = AsyncConf(load_defaults=False).set_master(c.master_url)
         with pytest.raises(Exception, match="authentication|requires encryption|handshake"):
             AsyncSession(conf=bad)
+
+
+def test_synchronous_driver_is_bit_identical_on_the_standalone_cluster_and_in_process(cluster):
+    """The same driver, the same data, two very different runtimes (threads vs executor processes reached over TCP through a
+    Master and Workers): synchronous SGD must produce the same weights to the last bit — the distributed plumbing adds nothing."""
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.data import LinearDataGenerator
+    cfg = AsyncConfig(algorithm="sgd_sync", synthetic="linear", num_rows=600, num_features=8, num_partitions=2, num_iterations=15,
+                      step_size=0.8, batch_rate=0.3, printer_freq=5, backend="cpu", eval_objective=True, quiet=True)
+    with AsyncSession(cluster.master_url, app_name="exact") as sc:
+        ds = LinearDataGenerator.generate_linear_dataset(sc.scheduler, 600, 8, 0.1, 2, seed=42)
+        remote = algo.run(cfg, points=ds, scheduler=sc.scheduler)
+    with AsyncSession("local[2]") as sc:
+        ds = LinearDataGenerator.generate_linear_dataset(sc.scheduler, 600, 8, 0.1, 2, seed=42)
+        local = algo.run(cfg, points=ds, scheduler=sc.scheduler)
+    assert torch.equal(remote.final_weights, local.final_weights)
+    assert [round(o, 12) for _, o in remote.objective] == [round(o, 12) for _, o in local.objective]
