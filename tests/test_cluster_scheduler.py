@@ -442,3 +442,22 @@ def test_executor_cores_are_concurrent_task_slots():
             assert p0 == p1                                                  # one executor process
             overlap = min(b0, b1) - max(a0, a1) > 0.2
             assert overlap == expect_overlap and (wall < 0.95 if expect_overlap else wall > 0.95)
+
+
+def test_fused_backend_launched_through_the_cluster_master_single_rank_on_the_simulator():
+    """``deploy.run_fused_on_cluster``: executor processes become ranks of the fused engine (torchrun contract exported by the task).
+    Without CUDA the single-rank engine runs on the round simulator, so the launcher mechanics are testable here."""
+    from asyncframework_b200.core.session import AsyncSession
+    from asyncframework_b200.deploy import run_fused_on_cluster
+    cfg = AsyncConfig(algorithm="asgd", synthetic="mnist8m", num_rows=4000, num_features=40, num_partitions=2, num_iterations=30,
+                      step_size=1e-6, batch_rate=0.2, printer_freq=10, loss="logistic", backend="fused", quiet=True)
+    with AsyncSession("local-cluster[1]") as sc:
+        rep = run_fused_on_cluster(sc, cfg)
+    assert rep["accepted"] >= 30 and rep["final_weights"].numel() == 40 and float(rep["final_weights"].abs().sum()) > 0
+    assert rep["objective"][-1][1] < rep["objective"][0][1]
+    with AsyncSession("local[2]") as sc:
+        with pytest.raises(TypeError, match="cluster master"):
+            run_fused_on_cluster(sc, cfg)
+    with AsyncSession("local-cluster[2]") as sc:
+        with pytest.raises(ValueError, match="multiple"):
+            run_fused_on_cluster(sc, AsyncConfig(algorithm="asgd", synthetic="mnist8m", num_partitions=3, backend="fused"))
