@@ -246,7 +246,8 @@ class LocalStandaloneCluster:
 
     def __init__(self, num_workers: int = 2, cores_per_worker: int = 1, memory_per_worker: int = 1024,
                  worker_timeout: float = 60.0, heartbeat_interval: float = 1.0, secret: Optional[str] = None,
-                 recovery_dir: Optional[str] = None, encrypt: bool = False):
+                 recovery_dir: Optional[str] = None, encrypt: bool = False, gpus: Optional[List[int]] = None):
+        """``gpus=[0, 1, ...]`` pins worker i's executors to CUDA device ``gpus[i]`` (one executor per GPU on a B200 node)."""
         self._master_args = dict(worker_timeout=worker_timeout, secret=secret, recovery_dir=recovery_dir, recovery_grace=1.5,
                                  encrypt=encrypt)
         self.master_env, self.master = start_master("127.0.0.1", 0, **self._master_args)
@@ -254,7 +255,8 @@ class LocalStandaloneCluster:
         self.worker_envs, self.workers = [], []
         for i in range(num_workers):
             e, w = start_worker(self.master_url, cores_per_worker, memory_per_worker, heartbeat_interval=heartbeat_interval,
-                                secret=secret, worker_id=f"worker-{i}", encrypt=encrypt)
+                                secret=secret, worker_id=f"worker-{i}", encrypt=encrypt,
+                                gpu=(gpus[i] if gpus is not None and i < len(gpus) else None))
             self.worker_envs.append(e)
             self.workers.append(w)
 
