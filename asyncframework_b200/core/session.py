@@ -210,6 +210,17 @@ class AsyncSession:
             return TorrentBroadcast(value, self.scheduler.env)
         return Broadcast(value)
 
+    get_broadcast_with_id = broadcast     # ``BroadcastManager.getBroadcastwithID`` of the fork: an (unused) alias of newBroadcast
+
+    # ``sc.numFinishedPar`` of the fork (SparkContext.scala:90-99): a plain counter the samples may use
+    num_finished_par = 0
+
+    def set_num_finished_par(self, i: int) -> None:
+        self.num_finished_par = int(i)
+
+    def get_num_finished_par(self) -> int:
+        return self.num_finished_par
+
     def long_accumulator(self, name: Optional[str] = None):
         """``sc.longAccumulator``: tasks ``add``, the driver reads ``.value`` (updates of successful tasks only, exactly once)."""
         from .accumulator import Accumulator

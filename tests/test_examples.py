@@ -52,3 +52,9 @@ def test_python_api_example_on_a_local_cluster_master():
     out = _run("async_sgd_python_api.py", "--updates", "60", "--master", "local-cluster[2]")
     last = out.strip().splitlines()[-1]
     assert "objective" in last and float(last.split()[-1]) < 0.1
+
+
+def test_spark_mean_toy_example():
+    out = _run("spark_mean.py")
+    lines = out.strip().splitlines()
+    assert lines[-2] == "The Final results is: " and abs(float(lines[-1])) < 5.0 and "******** iteration 3********" in out
