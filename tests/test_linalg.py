@@ -138,3 +138,38 @@ def test_syr_and_spr_rank_one_updates():
         assert np.allclose(unpack_upper(U, 4).numpy(), A0 + 0.1 * np.outer(x, x))
     with pytest.raises(ValueError):
         spr(1.0, Vectors.dense(x), torch.zeros(9, dtype=torch.float64))
+
+
+def test_row_matrix_gramian_covariance_pca_svd_multiply_match_numpy():
+    """RowMatrixSuite at the behaviour level, dense and CSR shards."""
+    from asyncframework_b200.core.scheduler import Scheduler
+    from asyncframework_b200.data import ShardedDataset
+    from asyncframework_b200.linalg import DenseMatrix, RowMatrix
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((400, 5)) @ np.diag([5.0, 2.0, 1.0, 0.5, 0.1]) + np.array([1.0, -2.0, 0.0, 3.0, 0.5])
+    with Scheduler(3) as s:
+        dense = ShardedDataset.from_arrays(s, A, np.zeros(400), 3)
+        order = np.concatenate([np.arange(p, 400, 3) for p in range(3)])
+        for ds in (dense, ShardedDataset.from_shards(s, [sh.to_csr() for sh in dense.shards()])):
+            M = RowMatrix(ds)
+            assert (M.num_rows(), M.num_cols()) == (400, 5)
+            assert np.allclose(M.compute_gramian_matrix().to_array(), A.T @ A)
+            assert np.allclose(M.compute_covariance().to_array(), np.cov(A, rowvar=False))
+            pcs, var = M.compute_principal_components_and_explained_variance(2)
+            w, v = np.linalg.eigh(np.cov(A, rowvar=False))
+            top = v[:, np.argsort(w)[::-1][:2]]
+            assert np.allclose(np.abs(pcs.to_array().T @ top), np.eye(2), atol=1e-8)          # same subspace directions (sign-free)
+            assert np.allclose(var.to_array(), np.sort(w)[::-1][:2] / w.sum())
+            U, sv, V = M.compute_svd(3, compute_u=True)
+            assert np.allclose(sv.to_array(), np.linalg.svd(A, compute_uv=False)[:3])
+            recon = U.to_tensor().numpy() @ np.diag(sv.to_array()) @ V.to_array().T
+            best3 = (lambda u, s_, vt: (u[:, :3] * s_[:3]) @ vt[:3])(*np.linalg.svd(A[order], full_matrices=False))
+            assert np.allclose(recon, best3, atol=1e-8)                                      # the rank-3 truncation of A
+            B = rng.standard_normal((5, 2))
+            assert np.allclose(M.multiply(DenseMatrix.from_tensor(torch.from_numpy(B))).to_tensor().numpy(), A[order] @ B)
+            st = M.compute_column_summary_statistics()
+            assert np.allclose(st.mean.numpy(), A.mean(0))
+        with pytest.raises(ValueError):
+            RowMatrix(dense).compute_svd(6)
+        with pytest.raises(ValueError):
+            RowMatrix(dense).multiply(DenseMatrix.zeros(4, 2))
