@@ -199,7 +199,13 @@ class Master(RpcEndpoint):
             for app_id, exec_id, slot, ecores, emem in running:       # executors that survived a master restart
                 self._reported[(app_id, exec_id)] = (wid, slot, ecores, emem)
                 app = self.apps.get(app_id)
-                if app is not None:
+                known = app.executors.get(exec_id) if app is not None else None
+                if known is not None and known.state in ("LOST", "EXITED", "KILLED", "FAILED"):
+                    # the worker dropped off, its executors were declared LOST and their slots re-filled elsewhere; now it is
+                    # back with the old processes still alive: they are duplicates of a slot someone else owns
+                    self._reported.pop((app_id, exec_id), None)
+                    ref.send(("kill_executor", app_id, exec_id, False))
+                elif app is not None:
                     self._adopt(app, exec_id)
                 elif self.status == "ALIVE":                           # nobody owns it any more
                     ref.send(("kill_executor", app_id, exec_id, False))

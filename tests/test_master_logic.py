@@ -118,3 +118,24 @@ def test_duplicate_worker_id_is_refused_and_lost_worker_executors_move():
         assert [w["id"] for w in mref.ask_sync(("state",))["workers"]] == ["w0"]
     finally:
         env.shutdown()
+
+
+def test_worker_that_comes_back_with_superseded_executors_is_told_to_kill_them():
+    env, master, mref, recs, drv, dref = _setup(workers=((2, 2048), (2, 2048)))
+    try:
+        app_id, _ = mref.ask_sync(("register_app", "a", 2, 1, 512, dref, "127.0.0.1:1"))
+        assert _wait(lambda: [len(_launches(r)) for r in recs] == [1, 1])
+        old = _launches(recs[1])[0]
+        mref.send(("executor_state_changed", app_id, old[2], "RUNNING", "", None))
+        master.workers["w1"].last_heartbeat -= 1000
+        mref.send(("check_worker_timeouts",))                                  # w1 is declared dead, its slot moves to w0
+        assert _wait(lambda: len(_launches(recs[0])) == 2)
+        # w1 was only partitioned away: it re-registers and reports the executor it is STILL running
+        w1ref = env.endpoint_ref(None, "w1")
+        reply = mref.ask_sync(("register_worker", "w1", "127.0.0.1", 10_001, 2, 2048, w1ref, [(app_id, old[2], old[3], 1, 512)]))
+        assert reply[0] == "registered"
+        assert _wait(lambda: ("kill_executor", app_id, old[2], False) in recs[1].msgs)       # the duplicate is killed ...
+        st = mref.ask_sync(("state",))
+        assert [w["cores_used"] for w in sorted(st["workers"], key=lambda w: w["id"])] == [2, 0]   # ... and not accounted for
+    finally:
+        env.shutdown()
