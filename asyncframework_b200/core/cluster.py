@@ -747,16 +747,28 @@ class ClusterScheduler:
                                   "speculated": {}, "claimed": set()}
         self.listeners.post({"event": "job_start", "job": job_id, "partitions": parts, "t_ms": now,
                              "task_binary_bytes": len(payload)})
+        job = self._jobs[job_id]
+        unreachable: Dict[int, BaseException] = {}
         for e in executors:
-            self._send(e, ("binary", job_id, payload))
+            try:
+                self._send(e, ("binary", job_id, payload))
+            except Exception as exc:  # noqa: BLE001  (dead pipe / slot down): its tasks fail, the job is not left dangling
+                unreachable[e] = exc
+        reached = [e for e in executors if e not in unreachable]
         with self._lock:                              # only now may a later job refer to these blocks by id (message order)
             for b in make_payload.shipped:            # type: ignore[attr-defined]
-                self._blocks_held.setdefault(b, set()).update(executors)
+                self._blocks_held.setdefault(b, set()).update(reached)
         for p in parts:
-            self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0,
-                                 "executor": assigned[p], "t_ms": now})
-            self._send(assigned[p], ("task", job_id, p, 0, now))
-        if not parts:
+            e = assigned[p]
+            if e not in unreachable:
+                self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0, "executor": e, "t_ms": now})
+                try:
+                    self._send(e, ("task", job_id, p, 0, now))
+                    continue
+                except Exception as exc:  # noqa: BLE001
+                    unreachable[e] = exc
+            self._fail_task(job, p, RuntimeError(f"executor {e} is unreachable, cannot launch partition {p} of job {job_id}: {unreachable[e]}"))
+        if not parts or (unreachable and not job["pending"]):
             self._finish_job(job_id)
         return waiter
 

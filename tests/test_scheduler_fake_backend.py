@@ -193,3 +193,28 @@ def test_result_handler_exception_fails_the_job_not_the_scheduler():
         t.ok(e, w2.job_id, p, 0)
     assert w2.wait(0)
     s.stop()
+
+
+def test_unreachable_executor_fails_its_tasks_and_does_not_leave_the_job_dangling():
+    s, t, ds = make()
+    real_send = t.send
+
+    def flaky_send(eid, msg):
+        if eid == 1:
+            raise BrokenPipeError("executor 1 pipe is gone")
+        real_send(eid, msg)
+    t.send = flaky_send
+    lost = []
+    w = s.submit_job(ds, lambda tc, it: 0, result_handler=lambda i, r: None, on_task_lost=lambda p, e: lost.append(p))
+    assert sorted(lost) == [1, 3] and w.done
+    with pytest.raises(JobFailed, match="unreachable"):
+        w.wait(0)
+    for e, p in ((0, 0), (0, 2)):
+        t.ok(e, w.job_id, p, 0)                         # the healthy executor's results are simply late
+    assert s.active_job_ids() == []                     # nothing dangling
+    t.send = real_send
+    w2 = s.submit_job(ds, lambda tc, it: 0, result_handler=lambda i, r: None)
+    for e, p, _ in t.tasks(w2.job_id):
+        t.ok(e, w2.job_id, p, 0)
+    assert w2.wait(0)
+    s.stop()
