@@ -54,6 +54,7 @@ class AsyncEnv:
         self.codec = CompressionCodec.create(limits.compression_codec)
         self.broadcast_cache: dict = {}             # id -> value (BroadcastManager.cachedValues)
         self.broadcast_lock = threading.Lock()
+        self.broadcast_fetch_locks: dict = {}       # id -> lock held while one thread assembles that broadcast
         self._stopped = False
         block_manager.broadcast_removed_hooks.append(self._drop_broadcast_value)
 

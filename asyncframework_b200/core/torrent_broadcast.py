@@ -150,6 +150,19 @@ def read_broadcast(bid: int, meta: Optional[Tuple[int, List[int], bool]] = None)
     with env.broadcast_lock:
         if bid in env.broadcast_cache:
             return env.broadcast_cache[bid]
+        fetch_lock = env.broadcast_fetch_locks.setdefault(bid, threading.Lock())
+    with fetch_lock:                                   # concurrent tasks of one executor fetch a broadcast ONCE (TorrentBroadcast.synchronized)
+        with env.broadcast_lock:
+            if bid in env.broadcast_cache:
+                return env.broadcast_cache[bid]
+        try:
+            return _fetch_broadcast(env, bid, meta)
+        finally:
+            with env.broadcast_lock:
+                env.broadcast_fetch_locks.pop(bid, None)
+
+
+def _fetch_broadcast(env: AsyncEnv, bid: int, meta: Optional[Tuple[int, List[int], bool]]) -> Any:
     bm = env.block_manager
     if meta is None:
         raw = bm.get_bytes(_meta_id(bid))

@@ -221,3 +221,26 @@ def test_mutable_broadcast_id_reads_older_versions_from_the_block_store():
         assert float(h.value[0]) == 2.0
     finally:
         _stop(driver, [e0])
+
+
+def test_concurrent_readers_in_one_executor_fetch_a_broadcast_once():
+    import cloudpickle
+    driver, (e0,) = _cluster(1, broadcast_block_size=32 * 1024)
+    try:
+        bc = TorrentBroadcast(torch.arange(100_000, dtype=torch.float64))        # ~25 pieces
+        handle = cloudpickle.dumps(bc)
+        AsyncEnv.set(e0)
+        out, errs = [], []
+
+        def reader():
+            try:
+                out.append(cloudpickle.loads(handle).value)
+            except BaseException as exc:  # noqa: BLE001
+                errs.append(exc)
+        ts = [threading.Thread(target=reader) for _ in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs and len(out) == 6 and all(o is out[0] for o in out)       # one assembled object shared by all readers
+        assert e0.block_manager.remote_fetches == bc.num_blocks                   # every piece crossed the wire exactly once
+    finally:
+        _stop(driver, [e0])
