@@ -729,7 +729,12 @@ class ClusterScheduler:
             with self._lock:
                 held = {b: set(es) for b, es in self._blocks_held.items()}
             with ShippingContext(lambda b: all(e in held.get(b, ()) for e in targets)) as ship:
-                payload = cloudpickle.dumps((dataset, func, fault))
+                try:
+                    payload = cloudpickle.dumps((dataset, func, fault))
+                except Exception as exc:  # noqa: BLE001  ("Task not serializable": name the culprit, not just its type)
+                    from .closure import TaskNotSerializable, explain_pickle_failure
+                    why = explain_pickle_failure({"function": func, "dataset lineage": dataset, "fault injector": fault}, "task binary")
+                    raise TaskNotSerializable(f"Task not serializable: {why or exc!r}") from exc
             make_payload.shipped = ship.shipped        # type: ignore[attr-defined]
             for bid, blk in ship.blocks.items():       # ContextCleaner: free the executors' copies when the driver's block dies
                 if bid not in self._cleaner_registered:

@@ -461,3 +461,27 @@ def test_fused_backend_launched_through_the_cluster_master_single_rank_on_the_si
     with AsyncSession("local-cluster[2]") as sc:
         with pytest.raises(ValueError, match="multiple"):
             run_fused_on_cluster(sc, AsyncConfig(algorithm="asgd", synthetic="mnist8m", num_partitions=3, backend="fused"))
+
+
+def test_task_not_serializable_names_the_offending_reference(cluster):
+    """SerializationDebugger behaviour: the error shows the chain from the task to the object that cannot be pickled."""
+    import threading
+    from asyncframework_b200.core.closure import TaskNotSerializable, explain_pickle_failure
+
+    class Holder:
+        def __init__(self):
+            self.name = "cfg"
+            self.guard = threading.Lock()
+    h = Holder()
+    ds = ShardedDataset.from_records(cluster, list(range(8)), 4)
+    with pytest.raises(TaskNotSerializable) as ei:
+        ds.map(lambda x: (x, h.name)).collect()
+    msg = str(ei.value)
+    assert "Task not serializable" in msg and "<closure h>" in msg and ".guard" in msg and "lock" in msg.lower() and "hint:" in msg
+    assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 36             # the scheduler is still healthy
+    assert explain_pickle_failure(lambda x: x + 1) is None
+
+    def uses_torch_ops(x):
+        return torch.ops is not None and x
+    why = explain_pickle_failure(uses_torch_ops)
+    assert why is not None and "_Ops" in why or why is None                     # (by-reference functions of importable modules pickle fine)
