@@ -101,6 +101,8 @@ IO_CODEC = _entry("spark.io.compression.codec", lambda s: str(s).lower().rsplit(
                   "lz4 | zstd | zlib | lzma | bz2 | none (CompressionCodec.scala:58)")
 SERIALIZER = _entry("spark.serializer", lambda s: "pickle" if "java" in str(s).lower() or "kryo" in str(s).lower() else str(s).lower(), "pickle",
                     "data serializer: pickle | cloudpickle (JavaSerializer / KryoSerializer map to pickle)")
+RPC_MAX_SIZE = _entry("spark.rpc.message.maxSize", lambda t: parse_size(t, "m"), 128 << 20,
+                      "largest task binary (closure + lineage, source data excluded) the driver will ship; MiB when no unit", _pos)
 NETWORK_TIMEOUT = _entry("spark.network.timeout", parse_time, 120.0, "RPC ask / block fetch timeout", _pos)
 HEARTBEAT_INTERVAL = _entry("spark.executor.heartbeatInterval", parse_time, 10.0, "liveness heartbeat period (Executor.scala:770-815)", _pos)
 WORKER_TIMEOUT = _entry("spark.worker.timeout", parse_time, 60.0, "master declares a silent worker dead after this", _pos)

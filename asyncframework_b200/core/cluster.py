@@ -299,7 +299,7 @@ class ClusterScheduler:
                  use_env: bool = True, speculation: bool = False, speculation_multiplier: float = 1.5,
                  speculation_quantile: float = 0.75, speculation_interval: float = 0.1, speculation_min_ms: float = 100.0,
                  blacklist: bool = False, blacklist_max_failures: int = 2, blacklist_timeout: float = 3600.0,
-                 cores_per_executor: int = 1):
+                 cores_per_executor: int = 1, max_task_binary_bytes: int = 128 << 20):
         self.num_executors = int(num_executors)
         self.max_failures = int(max_failures)
         self.block_first_async_job = block_first_async_job
@@ -313,6 +313,7 @@ class ClusterScheduler:
         self._jobs: Dict[int, dict] = {}
         self._lock = threading.Lock()
         self._stopped = False
+        self.max_task_binary_bytes = int(max_task_binary_bytes)      # spark.rpc.message.maxSize
         self._blocks_held: Dict[int, set] = {}       # source block id -> executors that already hold its data
         self._cleaner_registered: set = set()
         self.last_task_binary_bytes = 0
@@ -736,6 +737,18 @@ class ClusterScheduler:
                     why = explain_pickle_failure({"function": func, "dataset lineage": dataset, "fault injector": fault}, "task binary")
                     raise TaskNotSerializable(f"Task not serializable: {why or exc!r}") from exc
             make_payload.shipped = ship.shipped        # type: ignore[attr-defined]
+            if not ship.shipped:                       # no source data travels with this binary: what is in it was CAPTURED
+                if len(payload) > self.max_task_binary_bytes:
+                    raise RuntimeError(
+                        f"Serialized task binary of job {job_id} is {len(payload)} bytes, which exceeds max allowed: "
+                        f"spark.rpc.message.maxSize ({self.max_task_binary_bytes} bytes).  Consider using broadcast variables for "
+                        f"large values captured by the closure.")
+                if len(payload) > 1000 * 1024 and not getattr(self, "_warned_big_task", False):
+                    self._warned_big_task = True
+                    import logging
+                    logging.getLogger("asyncframework_b200.scheduler").warning(
+                        "Job %d contains a task binary of very large size (%d KB). The maximum recommended task size is 1000 KB: "
+                        "a closure is probably capturing data that should be a broadcast.", job_id, len(payload) // 1024)
             for bid, blk in ship.blocks.items():       # ContextCleaner: free the executors' copies when the driver's block dies
                 if bid not in self._cleaner_registered:
                     self._cleaner_registered.add(bid)

@@ -86,7 +86,8 @@ class AsyncSession:
                           speculation_quantile=rc.get("spark.speculation.quantile"), speculation_interval=rc.get("spark.speculation.interval"),
                           blacklist=rc.get("spark.blacklist.enabled"),
                           blacklist_max_failures=rc.get("spark.blacklist.application.maxFailedTasksPerExecutor"),
-                          blacklist_timeout=rc.get("spark.blacklist.timeout"))
+                          blacklist_timeout=rc.get("spark.blacklist.timeout"),
+                          max_task_binary_bytes=rc.get("spark.rpc.message.maxSize"))
         if master.startswith("local-cluster"):
             from .cluster import ClusterScheduler
             m = _LOCAL_CLUSTER.match(master)

@@ -485,3 +485,17 @@ def test_task_not_serializable_names_the_offending_reference(cluster):
         return torch.ops is not None and x
     why = explain_pickle_failure(uses_torch_ops)
     assert why is not None and "_Ops" in why or why is None                     # (by-reference functions of importable modules pickle fine)
+
+
+def test_rpc_message_max_size_catches_data_captured_by_a_closure():
+    """LocalClusterSparkContext sets spark.rpc.message.maxSize = 1 MiB so tests catch closures that drag data along."""
+    from asyncframework_b200.conf import AsyncConf
+    from asyncframework_b200.core.session import AsyncSession
+    with AsyncSession("local-cluster[2]", conf=AsyncConf(load_defaults=False).set("spark.rpc.message.maxSize", "1")) as sc:
+        ds = sc.parallelize(range(8), 4)
+        assert ds.count() == 8                                                  # the source data itself may be as big as it likes
+        big = torch.zeros(400_000, dtype=torch.float64)                          # 3.2 MB captured by the closure
+        with pytest.raises(RuntimeError, match="spark.rpc.message.maxSize"):
+            ds.map(lambda i: float(big[i])).collect()
+        bc = sc.broadcast(big)                                                   # the fix the message recommends
+        assert ds.map(lambda i: float(bc.value[i])).collect() == [0.0] * 8
