@@ -95,6 +95,8 @@ MEMORY_FRACTION = _entry("spark.memory.fraction", float, 0.6, "share of executor
 MAX_DIRECT_RESULT = _entry("spark.task.maxDirectResultSize", parse_size, 1 << 20, "results above this travel through the block manager (Executor.scala:140-141)", _pos)
 MAX_RESULT_SIZE = _entry("spark.driver.maxResultSize", parse_size, 1 << 30, "abort a job whose serialized results exceed this (0 = unlimited)", _nonneg)
 BROADCAST_BLOCK = _entry("spark.broadcast.blockSize", lambda t: parse_size(t, "k"), 4 << 20, "TorrentBroadcast piece size (TorrentBroadcast.scala:81)", _pos)
+BROADCAST_INLINE = _entry("spark.async.broadcast.inlineThreshold", parse_size, 32 << 10,
+                          "broadcast values up to this serialized size travel inside the handle (0 = always use torrent pieces)", _nonneg)
 BROADCAST_COMPRESS = _entry("spark.broadcast.compress", _parse_bool, True, "compress broadcast pieces")
 BROADCAST_CHECKSUM = _entry("spark.broadcast.checksum", _parse_bool, True, "Adler32 per piece")
 IO_CODEC = _entry("spark.io.compression.codec", lambda s: str(s).lower().rsplit(".", 1)[-1].replace("compressioncodec", ""), "lz4",
@@ -281,6 +283,7 @@ class AsyncConf:
         return RuntimeLimits(
             max_direct_result_size=g("spark.task.maxDirectResultSize"), max_result_size=g("spark.driver.maxResultSize"),
             broadcast_block_size=g("spark.broadcast.blockSize"), broadcast_compress=g("spark.broadcast.compress"),
+            broadcast_inline_threshold=g("spark.async.broadcast.inlineThreshold"),
             broadcast_checksum=g("spark.broadcast.checksum"),
             storage_memory=int(g("spark.executor.memory") * g("spark.memory.fraction")),
             compression_codec=g("spark.io.compression.codec"), serializer=g("spark.serializer"),

@@ -127,7 +127,7 @@ class AsyncBroadcast:
             # cluster deployment: every version is a TorrentBroadcast, so executors can read ``value`` AND older versions
             # (``value(index)``) out of the block store by id — the reference's mutable-broadcast-id mechanism (A8/A9)
             from .torrent_broadcast import TorrentBroadcast
-            self._bc = TorrentBroadcast(value, env)
+            self._bc = TorrentBroadcast(value, env, allow_inline=False)     # versions must stay addressable by id in the store
             self._id = self._bc.id
             store.put(self._id, self._bc.value, self._bc)
         else:

@@ -26,6 +26,7 @@ class RuntimeLimits:
     max_direct_result_size: int = 1 << 20          # spark.task.maxDirectResultSize (Executor.scala:140-141)
     max_result_size: int = 1 << 30                 # spark.driver.maxResultSize (TaskSetManager.scala:706-712); 0 = unlimited
     broadcast_block_size: int = 4 << 20            # spark.broadcast.blockSize (TorrentBroadcast.scala:81)
+    broadcast_inline_threshold: int = 32 << 10     # payloads up to this size travel INSIDE the handle (no pieces, no block-manager RPCs)
     broadcast_compress: bool = True                # spark.broadcast.compress
     broadcast_checksum: bool = True                # spark.broadcast.checksum
     storage_memory: int = 1 << 30                  # executor storage memory (UnifiedMemoryManager storage region)

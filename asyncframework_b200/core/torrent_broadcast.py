@@ -45,7 +45,7 @@ def _meta_id(bid: int) -> str:
 class TorrentBroadcast(Broadcast):
     """Driver: ``TorrentBroadcast(value)`` writes the pieces.  Executors receive the handle by unpickling."""
 
-    def __init__(self, value: Any, env: Optional[AsyncEnv] = None, snapshot: bool = True):
+    def __init__(self, value: Any, env: Optional[AsyncEnv] = None, snapshot: bool = True, allow_inline: bool = True):
         env = env or AsyncEnv.get()
         if env is None:
             raise RuntimeError("TorrentBroadcast needs an AsyncEnv (cluster deployment); use Broadcast for local[N]")
@@ -54,6 +54,16 @@ class TorrentBroadcast(Broadcast):
         self._value = _snapshot(value) if snapshot else value
         self._valid = True
         self._lock = threading.Lock()
+        self._inline: Optional[bytes] = None
+        if allow_inline and env.limits.broadcast_inline_threshold > 0:
+            # parameter-sized values (w of mnist8m = 6 KB, epsilon = 16 KB) ride inside the handle, i.e. inside the task binary:
+            # zero block-manager round trips per round and nothing to clean up.  Versioned broadcasts (AsyncBroadcast) never
+            # inline — their older versions must stay addressable by id in the block store (A9).
+            data = env.serializer.dumps(self._value)
+            if len(data) <= env.limits.broadcast_inline_threshold:
+                self._inline = data
+                self.num_blocks, self.checksums, self.compressed = 0, [], False
+                return
         self.num_blocks, self.checksums, self.compressed = self._write_blocks(env, self._value)
         with env.broadcast_lock:
             env.broadcast_cache[self.id] = self._value
@@ -79,6 +89,8 @@ class TorrentBroadcast(Broadcast):
 
     # ------------------------------------------------------------------ pickling: only the handle travels
     def __reduce__(self):
+        if self._inline is not None:
+            return (_rebuild_inline, (self.id, self._inline))
         return (_rebuild, (self.id, self.num_blocks, self.checksums, self.compressed))
 
     # ------------------------------------------------------------------ mutable id (A9)
@@ -106,12 +118,12 @@ class TorrentBroadcast(Broadcast):
         """Remove the executors' copies (pieces + cached values); the driver keeps its pieces so the next ``.value``
         on an executor re-fetches (Broadcast.unpersist)."""
         env = AsyncEnv.get()
-        if env is not None and env.is_driver and env.bm_master is not None:
+        if self._inline is None and env is not None and env.is_driver and env.bm_master is not None:
             env.bm_master.remove_broadcast(self.id, remove_from_driver=False)
 
     def destroy(self) -> None:
         env = AsyncEnv.get()
-        if env is not None and env.is_driver and env.bm_master is not None:
+        if self._inline is None and env is not None and env.is_driver and env.bm_master is not None:
             env.bm_master.remove_broadcast(self.id, remove_from_driver=True)
             with env.broadcast_lock:
                 env.broadcast_cache.pop(self.id, None)
@@ -129,9 +141,19 @@ def _make_remover(env: AsyncEnv, bid: int):
     return remove
 
 
+def _rebuild_inline(bid: int, data: bytes) -> TorrentBroadcast:
+    tb = TorrentBroadcast.__new__(TorrentBroadcast)
+    tb.id, tb._changed_id, tb._valid, tb._inline = bid, None, True, data
+    tb.num_blocks, tb.checksums, tb.compressed = 0, [], False
+    tb._lock = threading.Lock()
+    import pickle as _p
+    tb._value = _p.loads(data)
+    return tb
+
+
 def _rebuild(bid: int, num_blocks: int, checksums: List[int], compressed: bool) -> TorrentBroadcast:
     tb = TorrentBroadcast.__new__(TorrentBroadcast)
-    tb.id, tb._changed_id, tb._valid = bid, None, True
+    tb.id, tb._changed_id, tb._valid, tb._inline = bid, None, True, None
     tb.num_blocks, tb.checksums, tb.compressed = num_blocks, checksums, compressed
     tb._lock = threading.Lock()
     env = AsyncEnv.get()

@@ -318,6 +318,7 @@ class BlockManagerMasterEndpoint(RpcEndpoint):
         self.managers: Dict[BlockManagerId, dict] = {}
         self.locations: Dict[str, Dict[BlockManagerId, Tuple[int, int]]] = {}
         self.slaves: Dict[BlockManagerId, RpcEndpointRef] = {}
+        self._values_cached_everywhere: set = set()          # (reserved: broadcasts whose values may be cached without blocks)
 
     def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
         op = msg[0]
@@ -367,9 +368,20 @@ class BlockManagerMasterEndpoint(RpcEndpoint):
             ctx.send_failure(RpcError(f"BlockManagerMaster: unknown op {op!r}"))
 
     def _fan_out(self, op: str, key, include_driver: bool) -> int:
+        # only the managers that actually hold matching blocks are asked (a per-round broadcast that one executor fetched costs
+        # one or two round trips to clean up, not one per process of the cluster)
+        if op == "remove_block":
+            match = lambda b: b == key  # noqa: E731
+        elif op == "remove_rdd":
+            match = lambda b: b.startswith(f"rdd_{key}_")  # noqa: E731
+        else:
+            match = lambda b: b == f"broadcast_{key}" or b.startswith(f"broadcast_{key}_")  # noqa: E731
+        holders = {m for b, h in self.locations.items() if match(b) for m in h}
+        if op == "remove_broadcast":
+            holders |= {m for m in self.slaves if m.executor_id != "driver"} if key in self._values_cached_everywhere else set()
         futs = []
         for bm_id, ref in list(self.slaves.items()):
-            if not include_driver and bm_id.executor_id == "driver":
+            if bm_id not in holders or (not include_driver and bm_id.executor_id == "driver"):
                 continue
             try:
                 futs.append(ref.ask((op, key)))

@@ -210,7 +210,7 @@ def test_mutable_broadcast_id_reads_older_versions_from_the_block_store():
     driver, (e0,) = _cluster(1)
     try:
         import cloudpickle
-        versions = [TorrentBroadcast(torch.full((10,), float(v))) for v in range(3)]
+        versions = [TorrentBroadcast(torch.full((10,), float(v)), allow_inline=False) for v in range(3)]   # what AsyncBroadcast does
         handle = cloudpickle.dumps(versions[2])
         AsyncEnv.set(e0)
         h = cloudpickle.loads(handle)
@@ -242,5 +242,33 @@ def test_concurrent_readers_in_one_executor_fetch_a_broadcast_once():
         [t.join() for t in ts]
         assert not errs and len(out) == 6 and all(o is out[0] for o in out)       # one assembled object shared by all readers
         assert e0.block_manager.remote_fetches == bc.num_blocks                   # every piece crossed the wire exactly once
+    finally:
+        _stop(driver, [e0])
+
+
+def test_parameter_sized_broadcasts_travel_inside_the_handle():
+    """w of mnist8m is 6 KB: no pieces, no block-manager round trips, nothing to clean up; big values still go through the swarm."""
+    import cloudpickle
+    driver, (e0,) = _cluster(1)
+    try:
+        small = TorrentBroadcast(torch.arange(784, dtype=torch.float64))
+        big = TorrentBroadcast(torch.arange(100_000, dtype=torch.float64))
+        assert small.num_blocks == 0 and big.num_blocks >= 1
+        assert not driver.block_manager.contains(f"broadcast_{small.id}_meta") and driver.block_manager.contains(f"broadcast_{big.id}_meta")
+        hs, hb = cloudpickle.dumps(small), cloudpickle.dumps(big)
+        assert 6000 < len(hs) < 8000 and len(hb) < 2000
+        AsyncEnv.set(e0)
+        before = e0.block_manager.remote_fetches
+        assert torch.equal(cloudpickle.loads(hs).value, torch.arange(784, dtype=torch.float64))
+        assert e0.block_manager.remote_fetches == before                         # nothing fetched for the inlined one
+        assert float(cloudpickle.loads(hb).value[-1]) == 99_999.0 and e0.block_manager.remote_fetches > before
+        AsyncEnv.set(driver)
+        small.unpersist()
+        small.destroy()
+        with pytest.raises(RuntimeError, match="destroyed"):
+            _ = small.value
+        never = TorrentBroadcast(torch.zeros(4), AsyncEnv.create_driver(RuntimeLimits(broadcast_inline_threshold=0)))
+        assert never.num_blocks == 1
+        AsyncEnv.get().stop()
     finally:
         _stop(driver, [e0])
