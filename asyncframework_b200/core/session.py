@@ -139,7 +139,7 @@ class AsyncSession:
             return max(1, int(m.group(1))), 4
         if master in ("fused", "gloo"):
             return 1, 4
-        if re.match(r"^(spark|async)://[^:/]+:\d+$", master):
+        if re.match(r"^(spark|async)://[^:/,]+:\d+(,[^:/,]+:\d+)*$", master):
             return 1, 4
         raise ValueError(f"Could not parse Master URL: '{master}'")
 

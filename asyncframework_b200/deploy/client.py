@@ -81,7 +81,9 @@ class StandaloneTransport:
 
     def __init__(self, master_url: str, num_executors: Optional[int] = None, cores_per_executor: int = 1,
                  memory_mb: int = 512, app_name: str = "asyncframework_b200", register_timeout: float = 60.0):
-        self.master_address = RpcAddress.parse(master_url)
+        from ..rpc import parse_master_urls
+        self.master_addresses = parse_master_urls(master_url)
+        self.master_address = self.master_addresses[0]
         self.num_executors = num_executors
         self.cores_per_executor, self.memory_mb, self.app_name = cores_per_executor, memory_mb, app_name
         self.register_timeout = register_timeout
@@ -105,10 +107,27 @@ class StandaloneTransport:
         self.sched = sched
         env = sched.env.rpc_env
         env.setup_endpoint(_DriverEndpoint.NAME, _DriverEndpoint(self))
-        self.master = env.endpoint_ref(self.master_address, "Master")
         me = env.endpoint_ref(None, _DriverEndpoint.NAME)
-        self.app_id, granted = self.master.ask_sync(
-            ("register_app", self.app_name, self.num_executors, self.cores_per_executor, self.memory_mb, me, str(env.address)), 30)
+        reply, last_err = None, None
+        deadline = time.time() + self.register_timeout
+        while reply is None:
+            for addr in self.master_addresses:                       # HA: the first master that is not a standby
+                try:
+                    ref = env.endpoint_ref(addr, "Master")
+                    r = ref.ask_sync(("register_app", self.app_name, self.num_executors, self.cores_per_executor, self.memory_mb, me,
+                                      str(env.address)), 30)
+                    if r[0] == "standby":
+                        last_err = RpcError(f"{addr} is a standby (leader: {r[1]})")
+                        continue
+                    reply, self.master, self.master_address = r, ref, addr
+                    break
+                except RpcError as exc:
+                    last_err = exc
+            if reply is None:
+                if len(self.master_addresses) == 1 or time.time() > deadline:
+                    raise last_err
+                time.sleep(0.3)
+        self.app_id, granted = reply
         self.num_executors = granted
         sched.num_executors = granted
         deadline = time.time() + self.register_timeout
@@ -158,16 +177,17 @@ class StandaloneTransport:
         me = env.endpoint_ref(None, _DriverEndpoint.NAME)
         delay = 0.2
         while not self.sched._stopped and self.app_state == "RUNNING":
-            try:
-                ref = env.endpoint_ref(self.master_address, "Master")
-                reply = ref.ask_sync(("reregister_app", self.app_id, self.app_name, self.num_executors, self.cores_per_executor,
-                                      self.memory_mb, me, str(env.address)), 5)
-                if reply[0] == "registered":
-                    self.master = ref
-                    self.master_reconnects += 1
-                    return
-            except RpcError:
-                pass
+            for addr in self.master_addresses:
+                try:
+                    ref = env.endpoint_ref(addr, "Master")
+                    reply = ref.ask_sync(("reregister_app", self.app_id, self.app_name, self.num_executors, self.cores_per_executor,
+                                          self.memory_mb, me, str(env.address)), 5)
+                    if reply[0] == "registered":
+                        self.master, self.master_address = ref, addr
+                        self.master_reconnects += 1
+                        return
+                except RpcError:
+                    pass
             time.sleep(delay)
             delay = min(delay * 2, 5.0)
 

@@ -72,7 +72,15 @@ class Master(RpcEndpoint):
     NAME = "Master"
 
     def __init__(self, worker_timeout: float = 60.0, spread_out: bool = True, recovery_dir: Optional[str] = None,
-                 recovery_grace: float = 2.0):
+                 recovery_grace: float = 2.0, ha: bool = False, lease_s: float = 3.0):
+        # HA (the ZooKeeper mode of the reference, ``spark.deploy.recoveryMode=ZOOKEEPER`` + standby masters,
+        # deploy/master/ZooKeeperLeaderElectionAgent.scala) with a shared directory instead of ZooKeeper: the leader holds a
+        # LEASE file in ``recovery_dir`` (renewed every lease/3 under an flock); standbys answer registrations with
+        # ("standby", leader url) and take over — RECOVERING, then ALIVE — when the lease has expired.  Workers and drivers are
+        # given every master address (``spark://h1:p1,h2:p2``) and walk the list.
+        self.ha = bool(ha and recovery_dir)
+        self.lease_s = float(lease_s)
+        self.leader_url: Optional[str] = None
         self.worker_timeout = worker_timeout
         self.spread_out = spread_out
         # FILESYSTEM recovery mode (spark.deploy.recoveryMode=FILESYSTEM, FileSystemPersistenceEngine): registrations are
@@ -97,6 +105,58 @@ class Master(RpcEndpoint):
     # ------------------------------------------------------------------ lifecycle
     def on_start(self) -> None:
         threading.Thread(target=self._timeout_loop, daemon=True, name="master-worker-timeout").start()
+        if self.ha:
+            self.status = "STANDBY"
+            threading.Thread(target=self._election_loop, daemon=True, name="master-election").start()
+            return
+        self._become_leader()
+
+    def _lease(self, acquire: bool) -> bool:
+        """Read-check-write of the lease file under an exclusive flock.  Returns True when this master holds the lease after
+        the call (``acquire=False`` only renews a lease that is already ours)."""
+        import fcntl
+        import json
+        import os
+        os.makedirs(self.recovery_dir, exist_ok=True)
+        me = f"spark://{self.rpc_env.address}"
+        with open(os.path.join(self.recovery_dir, "leader.lock"), "a+") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                path = os.path.join(self.recovery_dir, "leader.json")
+                cur = None
+                try:
+                    with open(path) as f:
+                        cur = json.load(f)
+                except (OSError, ValueError):
+                    pass
+                now = time.time()
+                mine = cur is not None and cur.get("url") == me
+                free = cur is None or cur.get("expires", 0) < now
+                self.leader_url = cur.get("url") if cur and not free else None
+                if mine or (acquire and free):
+                    tmp = path + f".{os.getpid()}.tmp"
+                    with open(tmp, "w") as f:
+                        json.dump({"url": me, "expires": now + self.lease_s}, f)
+                    os.replace(tmp, path)
+                    self.leader_url = me
+                    return True
+                return False
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
+
+    def _election_loop(self) -> None:
+        while not self._stop.wait(self.lease_s / 3):
+            try:
+                if self.status == "STANDBY":
+                    if self._lease(acquire=True):
+                        self.self_ref.send(("elected",))
+                elif not self._lease(acquire=False):               # we lost the lease (paused too long): step down hard
+                    self.self_ref.send(("revoked",))
+            except (OSError, RpcError):
+                continue
+
+    def _become_leader(self) -> None:
+        self.status = "ALIVE"
         prior = self._load_persisted()
         if prior is not None:
             self._app_ids = itertools.count(prior.get("next_app", 0))
@@ -160,6 +220,8 @@ class Master(RpcEndpoint):
     # ------------------------------------------------------------------ messages
     def receive(self, msg, sender: Optional[RpcAddress]) -> None:
         op = msg[0]
+        if self.status == "STANDBY" and op in ("heartbeat", "executor_state_changed", "unregister_app"):
+            return
         if op == "heartbeat":
             w = self.workers.get(msg[1])
             if w is not None and w.state == "ALIVE":
@@ -179,14 +241,28 @@ class Master(RpcEndpoint):
         elif op == "unregister_app":
             self._finish_app(msg[1], "FINISHED")
         elif op == "complete_recovery":
-            self.status = "ALIVE"
+            if self.status == "RECOVERING":
+                self.status = "ALIVE"
             self.recovering_until = 0.0
             self._schedule()
+        elif op == "elected":
+            if self.status == "STANDBY":
+                self._become_leader()
+                if self.status == "ALIVE":                          # nothing persisted to wait for
+                    self._schedule()
+        elif op == "revoked":
+            # another master holds the lease now: forget everything (it recovers the cluster from the workers / drivers)
+            self.status = "STANDBY"
+            self.workers.clear()
+            self.apps.clear()
         else:
             raise RpcError(f"Master: unknown one-way message {op!r}")
 
     def receive_and_reply(self, msg, ctx: RpcCallContext) -> None:
         op = msg[0]
+        if self.status == "STANDBY" and op in ("register_worker", "register_app", "reregister_app", "request_total_executors", "kill_executor"):
+            ctx.reply(("standby", self.leader_url))
+            return
         if op == "register_worker":
             _, wid, host, port, cores, memory_mb, ref = msg[:7]
             running = msg[7] if len(msg) > 7 else []
@@ -410,10 +486,11 @@ class Master(RpcEndpoint):
 
 
 def start_master(host: str = "127.0.0.1", port: int = 7077, worker_timeout: float = 60.0, secret: Optional[str] = None,
-                 spread_out: bool = True, recovery_dir: Optional[str] = None, recovery_grace: float = 2.0, encrypt: bool = False):
+                 spread_out: bool = True, recovery_dir: Optional[str] = None, recovery_grace: float = 2.0, encrypt: bool = False,
+                 ha: bool = False, lease_s: float = 3.0):
     """Returns ``(rpc_env, master_endpoint)``; the URL is ``spark://<rpc_env.address>``."""
     env = RpcEnv("master", host, port, secret=secret, encrypt=encrypt)
-    master = Master(worker_timeout, spread_out, recovery_dir, recovery_grace)
+    master = Master(worker_timeout, spread_out, recovery_dir, recovery_grace, ha, lease_s)
     env.setup_endpoint(Master.NAME, master)
     return env, master
 
@@ -427,8 +504,10 @@ def main(argv=None) -> None:
     ap.add_argument("--secret", default=None)
     ap.add_argument("--recovery-dir", default=None, help="persist registrations here and recover them after a restart")
     ap.add_argument("--encrypt", action="store_true", help="AES-GCM on every connection (needs --secret)")
+    ap.add_argument("--ha", action="store_true", help="leader election through a lease file in --recovery-dir (run several masters; "
+                    "give workers and applications spark://h1:p1,h2:p2)")
     a = ap.parse_args(argv)
-    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret, recovery_dir=a.recovery_dir, encrypt=a.encrypt)
+    env, master = start_master(a.host, a.port, a.worker_timeout, a.secret, recovery_dir=a.recovery_dir, encrypt=a.encrypt, ha=a.ha)
     print(f"Master started at spark://{env.address}", flush=True)
     if a.webui_port:
         from ..utils.status_server import serve_json

@@ -108,7 +108,9 @@ class Worker(RpcEndpoint):
                  heartbeat_interval: float = 15.0, host: str = "127.0.0.1", gpu: Optional[int] = None,
                  secret: Optional[str] = None, worker_id: Optional[str] = None, encrypt: bool = False):
         self.encrypt = encrypt
-        self.master_address = RpcAddress.parse(master_url)
+        from ..rpc import parse_master_urls
+        self.master_addresses = parse_master_urls(master_url)      # spark://h1:p1,h2:p2 — walked until one is the leader
+        self.master_address = self.master_addresses[0]
         self.cores, self.memory_mb = int(cores), int(memory_mb)
         self.host, self.gpu, self.secret = host, gpu, secret
         self.heartbeat_interval = heartbeat_interval
@@ -141,10 +143,14 @@ class Worker(RpcEndpoint):
                         self.registered.set()
                         delay = 0.2
                     else:
-                        raise RpcError(reply[1])
+                        raise RpcError(str(reply[1]))
                 except RpcError:
-                    self._stop.wait(delay)
-                    delay = min(delay * 2, 10.0)
+                    # dead, unreachable or a standby: try the next master of the list (with back-off once the list is exhausted)
+                    i = self.master_addresses.index(self.master_address)
+                    self.master_address = self.master_addresses[(i + 1) % len(self.master_addresses)]
+                    if (i + 1) % len(self.master_addresses) == 0 or len(self.master_addresses) == 1:
+                        self._stop.wait(delay)
+                        delay = min(delay * 2, 10.0)
                     continue
             try:
                 self.master.send(("heartbeat", self.id))

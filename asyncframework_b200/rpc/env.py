@@ -64,6 +64,12 @@ class RpcAddress(NamedTuple):
         return RpcAddress(host, int(port))
 
 
+def parse_master_urls(url: str) -> list:
+    """``spark://h1:p1,h2:p2`` (the HA form of a standalone master URL) -> [RpcAddress, ...]."""
+    body = url.split("://", 1)[1] if "://" in url else url
+    return [RpcAddress.parse(part.strip()) for part in body.split(",") if part.strip()]
+
+
 class RpcError(RuntimeError):
     pass
 

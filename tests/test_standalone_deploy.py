@@ -178,3 +178,43 @@ def test_synchronous_driver_is_bit_identical_on_the_standalone_cluster_and_in_pr
         local = algo.run(cfg, points=ds, scheduler=sc.scheduler)
     assert torch.equal(remote.final_weights, local.final_weights)
     assert [round(o, 12) for _, o in remote.objective] == [round(o, 12) for _, o in local.objective]
+
+
+def test_standby_master_takes_over_when_the_leader_dies(tmp_path):
+    """Master HA (ZooKeeper mode of the reference, here a lease file in a shared directory): two masters, one leader; workers and
+    the application know both addresses; the leader dies; the standby acquires the lease, recovers workers / application /
+    running executors, and the job stream continues."""
+    from asyncframework_b200.deploy.master import start_master
+    from asyncframework_b200.deploy.worker import start_worker
+    rec = str(tmp_path / "ha")
+    envs = [start_master("127.0.0.1", 0, recovery_dir=rec, ha=True, lease_s=0.6, recovery_grace=1.0) for _ in range(2)]
+    state = lambda i: envs[i][0].endpoint_ref(None, "Master").ask_sync(("state",), 5)  # noqa: E731
+    workers = []
+    try:
+        assert _wait(lambda: sorted(state(i)["status"] for i in range(2)) == ["ALIVE", "STANDBY"], 10)
+        leader = 0 if state(0)["status"] == "ALIVE" else 1
+        standby = 1 - leader
+        # list the STANDBY first on purpose: clients must walk past it
+        url = f"spark://{envs[standby][0].address},{envs[leader][0].address}"
+        workers = [start_worker(url, 1, 1024, heartbeat_interval=0.2, worker_id=f"w{i}") for i in range(2)]
+        assert _wait(lambda: len(state(leader)["workers"]) == 2, 10) and state(standby)["workers"] == []
+        with AsyncSession(url, app_name="ha-app") as sc:
+            ds = sc.parallelize(range(20), 4)
+            assert ds.count() == 20
+            app_id = sc.scheduler.transport.app_id
+            pids = set(ds.map(lambda x: os.getpid()).collect())
+            envs[leader][0].shutdown()                                              # the leader dies
+            assert _wait(lambda: state(standby)["status"] == "ALIVE" and len(state(standby)["workers"]) == 2, 20)
+            assert _wait(lambda: sc.scheduler.transport.master_reconnects >= 1, 20)
+            st = state(standby)
+            assert [a["id"] for a in st["active_apps"]] == [app_id] and st["recovered"]["executors"] == 2
+            assert set(ds.map(lambda x: os.getpid()).collect()) == pids              # the same executors: nothing was restarted
+            sc.scheduler.kill_executor(1)                                            # the new leader manages the app from now on
+            assert _wait(lambda: sc.scheduler.executors_recovered == 1, 60)
+            assert ds.map(lambda x: x + 1).reduce(lambda a, b: a + b) == 210
+        assert _wait(lambda: state(standby)["active_apps"] == [], 10)
+    finally:
+        for e, _ in workers:
+            e.shutdown()
+        for e, _ in envs:
+            e.shutdown()
