@@ -408,6 +408,12 @@ class ShardedDataset:
             return iter(()) if b is None else (b.indexed_records() if b.gidx is not None else b.records())
         return self._derive(compute, batch, "map_shards")
 
+    def to(self, device=None, dtype=None) -> "ShardedDataset":
+        """Move every shard to ``device`` / ``dtype`` where the partition is EVALUATED and cache it there: in an executor process
+        whose worker pinned a GPU (``deploy.worker --gpu I``) ``ds.to("cuda")`` makes the partition HBM-resident in that executor,
+        so later ``sample`` / ``async_grad`` rounds run the fused CUDA kernels on it."""
+        return self.map_shards(lambda s: s.to(device, dtype)).cache()
+
     def glom(self) -> "ShardedDataset":
         return self._derive(lambda p, t: iter((list(self.iterator(p, t)),)), None, "glom")
 
