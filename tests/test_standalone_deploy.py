@@ -218,3 +218,29 @@ def test_standby_master_takes_over_when_the_leader_dies(tmp_path):
             e.shutdown()
         for e, _ in envs:
             e.shutdown()
+
+
+@pytest.mark.parametrize("name,iters", [("asgd", 400), ("saga_sync", 300)])
+def test_drivers_survive_an_executor_killed_mid_run_on_the_standalone_cluster(cluster, name, iters):
+    """The paper's point, on the real deployment: an executor process is SIGKILLed while the optimiser runs; the Master replaces
+    it, the scheduler re-ships its shards and re-runs its tasks, and both the asynchronous and the synchronous driver finish all
+    their iterations and converge."""
+    import threading
+    from asyncframework_b200 import algo
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.data import LinearDataGenerator
+    cfg = AsyncConfig(algorithm=name, num_partitions=4, num_iterations=iters, step_size=0.3 if name == "asgd" else 0.05, batch_rate=0.3,
+                      printer_freq=100, backend="cpu", quiet=True, bucket_ratio=0.5, taw=50)
+    with AsyncSession(cluster.master_url, app_name=f"kill-{name}") as sc:
+        ds = LinearDataGenerator.generate_linear_dataset(sc.scheduler, 2000, 10, 0.1, 4, seed=1)
+        out = {}
+        th = threading.Thread(target=lambda: out.update(rep=algo.run(cfg, points=ds, scheduler=sc.scheduler)), daemon=True)
+        th.start()
+        time.sleep(0.6)
+        assert th.is_alive(), "the run finished before the fault could be injected: raise the iteration count"
+        sc.scheduler.kill_executor(1)
+        th.join(120)
+        assert not th.is_alive() and "rep" in out
+        rep = out["rep"]
+        assert rep.accepted == iters and sc.scheduler.executors_recovered == 1
+        assert rep.objective[-1][1] < 0.2 * rep.objective[0][1]
