@@ -441,11 +441,20 @@ class ShardedDataset:
             return _with_rows(b.select(rows), b, rows)
 
         def compute(p, t):
+            # record-level path: membership of a CHUNK of records is evaluated with one vectorised hash (a NumPy call per record
+            # costs more than the hash itself); same rows as the batch-level path, the hash is a pure function of the row index
             thr = _sampler.threshold24(fraction)
-            for pos, rec in enumerate(self.iterator(p, t)):
-                gi = rec[1] if (isinstance(rec, tuple) and len(rec) == 2 and isinstance(rec[1], int)) else (pos + (p << 40))
-                if int(_sampler.hash_u24(seed, np.asarray([gi]))[0]) < thr:
-                    yield rec
+            it = enumerate(self.iterator(p, t))
+            while True:
+                chunk = list(itertools.islice(it, 4096))
+                if not chunk:
+                    return
+                gis = np.fromiter((rec[1] if (isinstance(rec, tuple) and len(rec) == 2 and isinstance(rec[1], int)) else (pos + (p << 40))
+                                   for pos, rec in chunk), dtype=np.int64, count=len(chunk))
+                keep = _sampler.hash_u24(seed, gis) < thr
+                for (pos, rec), k in zip(chunk, keep):
+                    if k:
+                        yield rec
 
         return self._derive(compute, batch if self.batch_capable else None, "sample")
 
