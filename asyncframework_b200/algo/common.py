@@ -204,10 +204,18 @@ def say(cfg: AsyncConfig, *args) -> None:
 def run_cli(algorithm: str, main_fn: Callable[[AsyncConfig], object], argv: Optional[List[str]] = None):
     logging.basicConfig(level=logging.WARNING, format="%(levelname)s %(name)s: %(message)s")
     cfg = parse_cli(algorithm, sys.argv[1:] if argv is None else argv)
-    layout = [(f, getattr(cfg, f)) for f in ("path", "file", "num_features", "num_rows", "num_partitions", "num_iterations",
-                                             "step_size", "taw", "batch_rate", "bucket_ratio", "printer_freq", "coeff", "seed")]
-    for k, v in layout:                       # the reference echoes its parameters
-        print(f"{k}: {v}")
+    # the reference's banner and parameter echo, label for label (SparkASGDThread.scala:26-62, SparkASGDSync.scala:25-57,
+    # SparkSGDMLLIB.scala:16-42) — log scrapers written for the reference keep working
+    from ..config import LAYOUTS
+    banner = {"asgd": "Spark ASGD application started", "asaga": "Spark ASAGA application started", "sgd_sync": "Spark SGD application started",
+              "saga_sync": "Spark SAGA application started", "sgd_mllib": "Spark MLlib SGD application started"}[algorithm]
+    labels = {"path": "path name", "file": "file name", "num_features": "num columns", "num_rows": "num rows",
+              "num_partitions": "num partitions", "num_iterations": "num iterations", "step_size": "step size", "taw": "taw",
+              "batch_rate": "batch rate", "bucket_ratio": "bucket ratio", "printer_freq": "printer freq", "coeff": "coeff", "seed": "seed"}
+    print(banner)
+    print("Input arguments:")
+    for name, _ in LAYOUTS[algorithm]:
+        print(f"{labels[name]}: {getattr(cfg, name)}")
     with host_math_threads():
         report = main_fn(cfg)
     if report is not None and hasattr(report, "print_reference_style"):

@@ -59,12 +59,20 @@ class RunReport:
     extra: Dict[str, float] = field(default_factory=dict)
 
     def print_reference_style(self, out=print) -> None:
-        out(f"Elapsed time(ms):{self.elapsed_ms:.0f}")
-        for p in sorted(self.waiting_ms):
-            out(f"waiting time of worker {p}: {self.waiting_ms[p]:.0f}")
-        out(f"Average waiting time(ms) per worker and iteration: {self.avg_waiting_ms}")
+        """The reference's end-of-run report, line for line (SparkASGDThread.scala:346-401; the MLlib driver prints only the
+        objective table and ``finished``, SparkSGDMLLIB.scala:75-111)."""
+        if self.algorithm != "sgd_mllib":
+            out(f"Elapsed time(ms): {self.elapsed_ms:.0f}")
+            out("*********************************")
+            out("Individual waiting times:")
+            for p in sorted(self.waiting_ms):
+                out(f"{p},{self.waiting_ms[p]:.0f}")
+            out(f"Average waiting time(ms) per worker and iteration:{self.avg_waiting_ms}")
+        out("*********************************")
         for t, obj in self.objective:
             out(f"{t:.0f},{obj}")
+        if self.algorithm == "sgd_mllib":
+            out("finished")
 
     def to_dict(self) -> dict:
         return {"algorithm": self.algorithm, "num_partitions": self.num_partitions, "iterations": self.iterations,

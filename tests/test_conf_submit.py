@@ -84,4 +84,4 @@ def test_submit_runs_a_reference_style_command_line_end_to_end(tmp_path):
            str(tmp_path) + "/", "lin.libsvm", "6", "200", "2", "8", "0.5", "0.5", "4", "0", "42", "--backend=cpu", "--quiet=true"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT, env={**os.environ, "PYTHONPATH": ROOT})
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "num_iterations: 8" in out.stdout and "Elapsed time" in out.stdout
+    assert "Spark SGD application started" in out.stdout and "num iterations: 8" in out.stdout and "Elapsed time(ms): " in out.stdout
