@@ -1,14 +1,28 @@
 """The five reference drivers (SparkASGDThread, SparkASGDSync, SparkASAGAThread, SparkASAGASync,
-SparkSGDMLLIB) as Python entry points with the reference's positional CLIs."""
-from . import asaga, asgd, saga_sync, sgd_mllib, sgd_sync  # noqa: F401
-from .delay import DelayInjector
-from .telemetry import MetricsLog, RunReport, evaluate_objective
+SparkSGDMLLIB) as Python entry points with the reference's positional CLIs.
 
-DRIVERS = {"asgd": asgd.run, "asaga": asaga.run, "sgd_sync": sgd_sync.run, "saga_sync": saga_sync.run,
-           "sgd_mllib": sgd_mllib.run}
+Driver modules are imported lazily so that ``python -m asyncframework_b200.algo.<driver>`` does not find its own module
+pre-imported by the package."""
+import importlib
+
+_DRIVER_NAMES = ("asgd", "asaga", "sgd_sync", "saga_sync", "sgd_mllib")
+_LAZY = {"DelayInjector": "delay", "MetricsLog": "telemetry", "RunReport": "telemetry", "evaluate_objective": "telemetry"}
+
+
+def __getattr__(name):
+    if name in _DRIVER_NAMES:
+        return importlib.import_module(f"{__name__}.{name}")
+    if name in _LAZY:
+        return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    if name == "DRIVERS":
+        return {n: importlib.import_module(f"{__name__}.{n}").run for n in _DRIVER_NAMES}
+    raise AttributeError(name)
 
 
 def run(cfg, points=None, scheduler=None):
     from .common import host_math_threads
+    if cfg.algorithm not in _DRIVER_NAMES:
+        raise ValueError(f"unknown algorithm {cfg.algorithm!r}")
+    driver = importlib.import_module(f"{__name__}.{cfg.algorithm}").run
     with host_math_threads():          # the driver thread does small-vector math only; see host_math_threads
-        return DRIVERS[cfg.algorithm](cfg, points, scheduler) if cfg.algorithm != "sgd_mllib" else sgd_mllib.run(cfg, points, scheduler)
+        return driver(cfg, points, scheduler)

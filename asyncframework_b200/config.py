@@ -136,10 +136,17 @@ class AsyncConfig:
         return cfg
 
 
+_REF_LABELS = {"path": "path name", "file": "file name", "num_features": "num columns", "num_rows": "num rows",
+               "num_partitions": "num partitions", "num_iterations": "num iterations", "step_size": "step size", "taw": "taw",
+               "batch_rate": "batch rate", "bucket_ratio": "bucket ratio", "printer_freq": "printer freq", "coeff": "coeff", "seed": "seed"}
+
+
 def usage(algorithm: str) -> str:
+    """The reference's ``Input format: [path name] [file name] …`` line (SparkASGDThread.scala:28-30) + how to call this driver."""
     layout = LAYOUTS[algorithm]
     names = " ".join(f"<{n}>" for n, _ in layout)
-    return (f"usage: python -m asyncframework_b200.algo.{algorithm} {names} "
+    return ("Input format: " + " ".join(f"[{_REF_LABELS[n]}]" for n, _ in layout)
+            + f"\nusage: python -m asyncframework_b200.algo.{algorithm} {names} "
             f"[--key=value ...]\n  ({len(layout)} positional arguments, same order as the reference driver)")
 
 
@@ -207,7 +214,7 @@ def parse_cli(algorithm: str, argv: Sequence[str]) -> AsyncConfig:
             positional.append(tok)
         i += 1
     if len(positional) != len(layout):
-        raise SystemExit(f"expected {len(layout)} positional arguments, got {len(positional)}\n"
+        raise SystemExit(f"The input arguments are wrong. (expected {len(layout)} positional arguments, got {len(positional)})\n"
                          + usage(algorithm))
     cfg = AsyncConfig(algorithm=algorithm)
     for (name, tp), text in zip(layout, positional):
