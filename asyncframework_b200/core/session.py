@@ -146,7 +146,9 @@ class AsyncSession:
     # ---- datasets -----------------------------------------------------------------------
     @property
     def default_parallelism(self) -> int:
-        return self.scheduler.num_executors
+        """``spark.default.parallelism`` when set, else the number of executors (``sc.defaultParallelism``)."""
+        n = self.runtime_conf.get("spark.default.parallelism")
+        return n if n and n > 0 else self.scheduler.num_executors
 
     def parallelize(self, data: Iterable[Any], num_slices: Optional[int] = None):
         from ..data.dataset import ShardedDataset
