@@ -625,6 +625,8 @@ class RpcEnv:
                 pass
             return
         if ftype in (F_ONEWAY, F_REQUEST):
+            if self._stopped:          # shutting down: the peer will see the connection close, not a misleading "endpoint not found"
+                return
             try:
                 name, sender, msg = pickle.loads(body)
             except BaseException as exc:  # noqa: BLE001

@@ -25,6 +25,7 @@ class Echo(RpcEndpoint):
         if msg == "boom":
             raise ValueError("kaboom")
         if msg == "never":
+            self.got.append(("never", ctx.sender_address))
             return
         if isinstance(msg, tuple) and msg[0] == "callback":      # reply later, from another thread
             threading.Timer(0.05, lambda: ctx.reply(("late", msg[1]))).start()
@@ -116,23 +117,34 @@ def test_server_can_call_back_a_client_only_env_and_refs_travel_in_messages():
 
 def test_disconnect_fails_outstanding_asks_and_notifies_endpoints():
     server, client = RpcEnv("s"), RpcEnv("c")
-    ep = Echo()
-    server.setup_endpoint("echo", ep)
-    ref = client.endpoint_ref(server.address, "echo")
-    assert ref.ask_sync(1) == ("echo", 1)
-    assert _wait(lambda: ("connected", client.address) in ep.events)
-    fut = ref.ask("never")
-    client_addr = client.address
-    cep = Echo()
-    client.setup_endpoint("watch", cep)
-    server.shutdown()
-    with pytest.raises(RpcDisconnected):
-        fut.result(20)
-    assert _wait(lambda: any(e[0] == "disconnected" for e in cep.events))
-    with pytest.raises(RpcError):
-        ref.ask_sync(2, timeout=2)
-    client.shutdown()
-    assert client_addr is not None
+    try:
+        ep = Echo()
+        server.setup_endpoint("echo", ep)
+        ref = client.endpoint_ref(server.address, "echo")
+        assert ref.ask_sync(1) == ("echo", 1)
+        assert _wait(lambda: ("connected", client.address) in ep.events), f"no connected event: {ep.events}"
+        cep = Echo()
+        client.setup_endpoint("watch", cep)
+        assert cep.started.wait(5)
+        fut = ref.ask("never")
+        assert _wait(lambda: any(m == "never" for m, _ in ep.got))       # the request is IN the endpoint when the server goes away
+        server.shutdown()
+        try:
+            fut.result(20)
+            raise AssertionError("the outstanding ask completed instead of failing")
+        except RpcDisconnected:
+            pass
+        except BaseException as exc:  # noqa: BLE001
+            raise AssertionError(f"outstanding ask failed with {type(exc).__name__}: {exc!r} instead of RpcDisconnected")
+        assert _wait(lambda: any(e[0] == "disconnected" for e in cep.events)), f"no disconnected event on the client: {cep.events}"
+        try:
+            got = ref.ask_sync(2, timeout=15)
+            raise AssertionError(f"ask to a dead server returned {got!r}")
+        except RpcError:
+            pass
+    finally:
+        client.shutdown()
+        server.shutdown()
 
 
 def test_server_sees_client_loss():
