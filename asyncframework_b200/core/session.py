@@ -39,6 +39,9 @@ class SparkFiles:
         import tempfile
         if cls._dir is None:
             cls._dir = tempfile.mkdtemp(prefix="afb-files-")
+            import atexit
+            import shutil
+            atexit.register(shutil.rmtree, cls._dir, True)
         return cls._dir
 
     @classmethod

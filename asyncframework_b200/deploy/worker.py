@@ -114,6 +114,7 @@ class Worker(RpcEndpoint):
         self.cores, self.memory_mb = int(cores), int(memory_mb)
         self.host, self.gpu, self.secret = host, gpu, secret
         self.heartbeat_interval = heartbeat_interval
+        self._own_work_dir = work_dir is None        # a temp dir we made up is removed when the worker stops
         self.work_dir = work_dir or os.path.join(tempfile.gettempdir(), f"afb-worker-{uuid.uuid4().hex[:8]}")
         self.id = worker_id or f"worker-{time.strftime('%Y%m%d%H%M%S')}-{host}-{uuid.uuid4().hex[:6]}"
         self.master = None
@@ -203,6 +204,13 @@ class Worker(RpcEndpoint):
         self._stop.set()
         for r in list(self.executors.values()):
             r.kill("worker stopped")
+        if self._own_work_dir:
+            import shutil
+
+            def cleanup():                              # after the executors had a moment to exit and close their log files
+                time.sleep(1.0)
+                shutil.rmtree(self.work_dir, ignore_errors=True)
+            threading.Thread(target=cleanup, daemon=False, name=f"{self.id}-cleanup").start()
 
 
 def start_worker(master_url: str, cores: int = 1, memory_mb: int = 1024, host: str = "127.0.0.1", port: int = 0,

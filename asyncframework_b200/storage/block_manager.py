@@ -251,9 +251,8 @@ class DiskStore:
 
     def __init__(self, root: Optional[str] = None, subdirs: int = 64):
         base = root or tempfile.gettempdir()
-        self.dir = os.path.join(base, f"blockmgr-{uuid.uuid4().hex[:12]}")
-        os.makedirs(self.dir, exist_ok=True)
-        self.subdirs = subdirs
+        self.dir = os.path.join(base, f"blockmgr-{uuid.uuid4().hex[:12]}")      # created on the first spill, not before:
+        self.subdirs = subdirs                                                   # most block managers never touch the disk
         self.sizes: Dict[str, int] = {}
         self.lock = threading.Lock()
 
