@@ -111,6 +111,8 @@ class StatusServer:
         base = "/api/v1/applications"
         routes: Dict[str, Route] = {
             "/": self._index,
+            "/jobs/(\\d+)": self._job_page,
+            "/executors": self._executors_page,
             base: lambda: [store.application_info()],
             f"{base}/{app}": store.application_info,
             f"{base}/{app}/jobs": lambda status=None: store.job_list(status),
@@ -150,11 +152,32 @@ class StatusServer:
         from .metrics import prometheus_text
         return ("text/plain; version=0.0.4", prometheus_text(self.registry.snapshot() if self.registry is not None else {}))
 
+    @staticmethod
+    def _page(title: str, body: str, refresh: int = 5) -> tuple:
+        nav = "<p><a href='/'>overview</a> &middot; <a href='/executors'>executors</a> &middot; <a href='/metrics/json'>metrics</a></p>"
+        return ("text/html", f"<html><head><title>{html.escape(title)}</title><meta http-equiv='refresh' content='{refresh}'></head>"
+                             f"<body><h2>{html.escape(title)}</h2>{nav}{body}</body></html>")
+
+    def _job_page(self, job_id: str):
+        j = self._job(job_id)
+        tasks = [{"partition": t.get("partition"), "status": t.get("status"), "executor": t.get("executor"), "attempt": t.get("attempt"),
+                  "run_ms": round(t.get("run_ms", 0.0), 3) if "run_ms" in t else "", **{k: round(v, 3) if isinstance(v, float) else v
+                                                                                      for k, v in (t.get("metrics") or {}).items()},
+                  "error": t.get("error", "")} for t in j.pop("tasks", [])]
+        summary = [{k: v for k, v in j.items() if k != "task_run_ms"}]
+        return self._page(f"Job {job_id}", _table("Summary", summary) + _table("Task run time (ms)", [j.get("task_run_ms") or {}])
+                          + _table("Tasks", tasks))
+
+    def _executors_page(self):
+        rows = self.store.executor_list()
+        links = [{**r, "threads": f"/api/v1/applications/{self.store.app_id}/executors/{r['id']}/threads"} for r in rows]
+        return self._page("Executors", _table("Executors", links) + _table("Cached datasets", self.store.rdd_storage()))
+
     def _index(self):
         s = self.store
         info = s.summary()
-        jobs = [{k: j.get(k) for k in ("job_id", "status", "num_tasks", "num_completed_tasks", "num_failed_tasks", "duration_ms")}
-                for j in s.job_list()[:50]]
+        jobs = [{**{k: j.get(k) for k in ("job_id", "status", "num_tasks", "num_completed_tasks", "num_failed_tasks", "duration_ms")},
+                 "details": f"/jobs/{j['job_id']}"} for j in s.job_list()[:50]]
         page = (f"<html><head><title>{html.escape(s.app_name)}</title></head><body><h2>{html.escape(s.app_name)} "
                 f"<small>({html.escape(s.app_id)})</small></h2><p>{html.escape(json.dumps(info['jobs_by_status']))} &middot; "
                 f"{info['completed_tasks']} tasks &middot; {info['active_executors']}/{info['executors']} executors</p>"

@@ -57,6 +57,9 @@ def test_live_ui_rest_api_over_local_scheduler(tmp_path):
         assert "# TYPE afb_scheduler_jobs gauge" in prom and "afb_scheduler_jobs 3" in prom
         page = _get(ui.url + "/")
         assert "<table" in page and "ui-test" in page and "ASYNC workers" in page
+        jp = _get(f"{ui.url}/jobs/{ok['job_id']}")
+        assert "Tasks" in jp and "SUCCESS" in jp and "http-equiv='refresh'" in jp
+        assert "Executors" in _get(ui.url + "/executors")
         with pytest.raises(urllib.error.HTTPError) as e404:
             _get(f"{base}/{app_id}/jobs/999999")
         assert e404.value.code == 404
