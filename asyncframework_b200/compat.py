@@ -22,6 +22,7 @@ from .core.context import AsyncContext as _AsyncContext
 from .core.partial_result import PartialResult as RDDPartialRes
 from .core.session import AsyncSession as _AsyncSession
 from .core.worker_state import WorkerState as workerState
+from .data.dataset import HashPartitioner, RangePartitioner  # noqa: F401
 from .data.dataset import ShardedDataset as RDD
 from .data.libsvm import MLUtils as _MLUtils
 from .linalg import DenseVector, LabeledPoint, SparseVector, Vectors  # noqa: F401
@@ -173,6 +174,7 @@ _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partition
        setName="set_name", toDebugString="to_debug_string", zipPartitions="zip_partitions", getStorageLevel="get_storage_level",
        saveAsPickleFile="save_as_pickle_file", mapShards="map_shards", ASYNCgrad="async_grad")
 _alias(SparkContext, setJobGroup="set_job_group", clearJobGroup="clear_job_group", cancelJobGroup="cancel_job_group",
+       getExecutorMemoryStatus="get_executor_memory_status", statusTracker=property(lambda self: self.status_tracker),
        addFile="add_file", wholeTextFiles="whole_text_files", pickleFile="pickle_file", emptyRDD="empty_dataset",
        applicationId=property(lambda self: self.application_id), uiWebUrl=property(lambda self: self.ui_web_url))
 _alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
@@ -190,7 +192,7 @@ if not hasattr(RDD, "checkpoint_to"):
     RDD.checkpoint_to = RDD.checkpoint                 # the explicit-directory form stays available
     RDD.checkpoint = _checkpoint
 
-__all__ = ["SparkConf", "StorageLevel", "Matrices", "DenseMatrix", "SparseMatrix", "LBFGS", "LogisticRegressionWithLBFGS",
+__all__ = ["HashPartitioner", "RangePartitioner", "SparkConf", "StorageLevel", "Matrices", "DenseMatrix", "SparseMatrix", "LBFGS", "LogisticRegressionWithLBFGS",
            "RidgeRegressionWithSGD", "LassoWithSGD", "SparkContext", "ASYNCcontext", "ASYNCbroadcast", "RDDPartialRes", "workerState", "RDD", "MLUtils", "Vectors",
            "DenseVector", "SparseVector", "LabeledPoint", "axpyOp", "dotOp", "scalOp", "GradientDescent", "LeastSquaresGradient",
            "LogisticGradient", "HingeGradient", "SimpleUpdater", "L1Updater", "SquaredL2Updater", "LinearRegressionWithSGD",

@@ -60,6 +60,28 @@ class SparkFiles:
         return path
 
 
+class _StatusTracker:
+    """``SparkStatusTracker`` (core/SparkStatusTracker.scala): ``get_active_job_ids``, ``get_job_ids_for_group``, ``get_job_info``."""
+
+    def __init__(self, sc):
+        self.sc = sc
+
+    def get_active_job_ids(self):
+        return self.sc.scheduler.active_job_ids()
+
+    def get_job_ids_for_group(self, group_id):
+        return self.sc.scheduler.active_job_ids(group_id)
+
+    def get_job_info(self, job_id: int):
+        """Needs ``sc.start_ui()`` / ``spark.ui.enabled`` (the status store records the listener events); ``None`` when unknown."""
+        store = getattr(self.sc, "status_store", None)
+        return store.job(job_id) if store is not None else None
+
+    def get_executor_infos(self):
+        store = getattr(self.sc, "status_store", None)
+        return store.executor_list() if store is not None else [{"id": e} for e in range(self.sc.scheduler.num_executors)]
+
+
 class AsyncSession:
     def __init__(self, master: Optional[str] = None, app_name: Optional[str] = None, device=None,
                  conf=None, num_executors: Optional[int] = None, cores_per_executor: Optional[int] = None,
@@ -269,6 +291,16 @@ class AsyncSession:
             data = f.read()
         name = os.path.basename(path)
         _added_files[name] = self.broadcast(data)
+
+    def get_executor_memory_status(self) -> dict:
+        """``sc.getExecutorMemoryStatus``: ``{"executor-id host:port": (max storage memory, remaining)}`` on cluster masters."""
+        st = self.scheduler.storage_status() if hasattr(self.scheduler, "storage_status") else {}
+        return {f"{m.executor_id} {m.host}:{m.port}": (s["max_memory"], s["max_memory"] - s["mem_used"]) for m, s in st.items()}
+
+    @property
+    def status_tracker(self):
+        """``sc.statusTracker``: low-level job status without the UI."""
+        return _StatusTracker(self)
 
     @property
     def files(self) -> dict:

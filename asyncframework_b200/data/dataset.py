@@ -108,6 +108,39 @@ def _with_rows(sub: Shard, parent: Shard, rows: torch.Tensor) -> Shard:
     return sub
 
 
+class HashPartitioner:
+    """``new HashPartitioner(n)``: process-independent hash of the key modulo ``n`` (Partitioner.scala:86)."""
+
+    def __init__(self, num_partitions: int):
+        self.num_partitions = int(num_partitions)
+
+    def __call__(self, key) -> int:
+        return _stable_hash(key) % self.num_partitions
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, HashPartitioner) and other.num_partitions == self.num_partitions
+
+    __hash__ = None  # type: ignore[assignment]
+
+
+class RangePartitioner:
+    """``new RangePartitioner(n, rdd)``: boundaries from a sample of the keys; partition q holds keys in (bound[q-1], bound[q]]
+    (Partitioner.scala:127; what ``sort_by_key`` builds internally)."""
+
+    def __init__(self, num_partitions: int, keyed_dataset=None, ascending: bool = True, bounds: Optional[list] = None, key=lambda k: k):
+        self.num_partitions, self.ascending, self.key = int(num_partitions), ascending, key
+        if bounds is None:
+            n = max(keyed_dataset.count(), 1)
+            sample = sorted(key(k) for k in keyed_dataset.keys().sample(False, min(1.0, max(0.01, 20.0 * num_partitions / n)), 17).collect())
+            bounds = [sample[len(sample) * (i + 1) // num_partitions] for i in range(num_partitions - 1)] if sample and num_partitions > 1 else []
+        self.bounds = list(bounds)
+
+    def __call__(self, k) -> int:
+        import bisect
+        q = bisect.bisect_left(self.bounds, self.key(k))
+        return q if self.ascending else (len(self.bounds) - q)
+
+
 class BlockMissing(RuntimeError):
     """An executor was sent a block reference for data it does not hold (e.g. a replaced executor)."""
 

@@ -186,3 +186,25 @@ def test_persist_levels_spill_to_the_executor_disk_store_and_files_reach_executo
         sc.add_file(str(f))
         out = sc.parallelize(range(4), 2).map(lambda x, files=sc.files: (os.getpid(), open(SparkFiles.get("side.txt", files)).read())).collect()
         assert {v for _, v in out} == {"side-data"} and os.getpid() not in {p for p, _ in out}
+
+
+def test_partitioner_classes_status_tracker_and_memory_status(sc):
+    from asyncframework_b200.data import HashPartitioner, RangePartitioner
+    kv = sc.parallelize([(i, i * i) for i in range(100)], 4)
+    hp = kv.partition_by(3, HashPartitioner(3))
+    assert all({k % 3 for k, _ in part} == {p} for p, part in enumerate(hp.glom().collect())) and HashPartitioner(3) == HashPartitioner(3)
+    rp = RangePartitioner(4, kv)
+    parts = kv.partition_by(4, rp).glom().collect()
+    assert all(max(k for k, _ in parts[i]) <= min(k for k, _ in parts[i + 1]) for i in range(3)) and all(len(p) > 10 for p in parts)
+    assert RangePartitioner(3, bounds=[10, 20])(5) == 0 and RangePartitioner(3, bounds=[10, 20])(10) == 0 and RangePartitioner(3, bounds=[10, 20])(25) == 2
+    sc.start_ui()
+    n = kv.count()
+    tr = sc.status_tracker
+    assert n == 100 and tr.get_active_job_ids() == []
+    last = sc.status_store.job_list()[0]["job_id"]
+    assert tr.get_job_info(last)["status"] == "SUCCEEDED" and len(tr.get_executor_infos()) == 3
+    assert sc.get_executor_memory_status() == {}                      # in-process master: no block managers
+    with AsyncSession("local-cluster[2]") as c2:
+        assert c2.parallelize(range(4), 2).count() == 4               # executors (and their block managers) are up once a job ran
+        ms = c2.get_executor_memory_status()
+        assert len(ms) == 3 and all(free <= mx for mx, free in ms.values())
