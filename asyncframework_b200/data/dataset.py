@@ -900,13 +900,7 @@ class ShardedDataset:
         holds keys between boundaries q-1 and q, each partition is sorted locally, so reading the partitions in order is the
         total order — no driver-side sort of the data."""
         P = int(num_partitions or self.num_partitions)
-        sample = sorted((key(k) for k in self.keys().sample(False, min(1.0, max(0.01, 20.0 * P / max(self.count(), 1))), 17).collect()))
-        bounds = [sample[len(sample) * (i + 1) // P] for i in range(P - 1)] if sample and P > 1 else []
-        import bisect
-
-        def partitioner(k):
-            q = bisect.bisect_right(bounds, key(k))
-            return q if ascending else (len(bounds) - q)
+        partitioner = RangePartitioner(P, self, ascending, key=key)
         sh = self._shuffle(P, lambda it: it, partitioner)
         return sh._derive(lambda p, t: iter(sorted(sh.iterator(p, t), key=lambda kv: key(kv[0]), reverse=not ascending)), None, "sort_by_key")
 
