@@ -904,6 +904,44 @@ class ShardedDataset:
         sh = self._shuffle(P, lambda it: it, partitioner)
         return sh._derive(lambda p, t: iter(sorted(sh.iterator(p, t), key=lambda kv: key(kv[0]), reverse=not ascending)), None, "sort_by_key")
 
+    def tree_reduce(self, f, depth: int = 2):
+        """``rdd.treeReduce``: reduce inside the partitions, then combine the partials in a ``depth``-level tree."""
+        def seq(acc, x):
+            return x if acc is _EMPTY else f(acc, x)
+
+        def comb(a, b):
+            return b if a is _EMPTY else (a if b is _EMPTY else f(a, b))
+        out = self.tree_aggregate(lambda: _EMPTY, seq, comb, depth)
+        if out is _EMPTY:
+            raise ValueError("empty collection")
+        return out
+
+    def count_approx_distinct(self, relative_sd: float = 0.05) -> int:
+        """``rdd.countApproxDistinct`` with HyperLogLog (one register array per partition, merged by max): the standard error is
+        ``1.04 / sqrt(m)``, so ``m = 2^ceil(log2((1.04 / relative_sd)^2))`` registers; small-range (linear counting) correction."""
+        p_bits = max(4, min(18, math.ceil(math.log2((1.04 / max(relative_sd, 1e-4)) ** 2))))
+        m = 1 << p_bits
+
+        def seq(reg, x):
+            h = _sampler.mix64_int(_stable_hash(x) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
+            idx = h >> (64 - p_bits)
+            rest = (h << p_bits) & ((1 << 64) - 1)
+            rank = (64 - p_bits + 1) if rest == 0 else (64 - rest.bit_length() + 1)
+            if rank > reg[idx]:
+                reg[idx] = rank
+            return reg
+        reg = self.aggregate(lambda: np.zeros(m, dtype=np.uint8), seq, np.maximum)
+        alpha = 0.7213 / (1 + 1.079 / m) if m >= 128 else {16: 0.673, 32: 0.697, 64: 0.709}[m]
+        est = alpha * m * m / float(np.sum(np.power(2.0, -reg.astype(np.float64))))
+        zeros = int((reg == 0).sum())
+        if est <= 2.5 * m and zeros:
+            est = m * math.log(m / zeros)
+        return int(round(est))
+
+    def id(self) -> int:
+        """``rdd.id``: the unique id blocks of this dataset are stored under (``rdd_<id>_<partition>``)."""
+        return self.ds_id
+
     def lookup(self, k) -> list:
         return self.filter(lambda kv: kv[0] == k).values().collect()
 

@@ -208,3 +208,18 @@ def test_partitioner_classes_status_tracker_and_memory_status(sc):
         assert c2.parallelize(range(4), 2).count() == 4               # executors (and their block managers) are up once a job ran
         ms = c2.get_executor_memory_status()
         assert len(ms) == 3 and all(free <= mx for mx, free in ms.values())
+
+
+def test_tree_reduce_and_hyperloglog_count_approx_distinct(sc):
+    ds = sc.parallelize(range(1, 101), 7)
+    assert ds.tree_reduce(lambda a, b: a + b) == 5050 and ds.tree_reduce(max, depth=3) == 100
+    with pytest.raises(ValueError):
+        sc.parallelize([], 2).tree_reduce(lambda a, b: a + b)
+    import random
+    rng = random.Random(1)
+    data = [rng.randrange(20_000) for _ in range(60_000)]
+    true = len(set(data))
+    est = sc.parallelize(data, 4).count_approx_distinct(0.02)
+    assert abs(est - true) / true < 0.06, (est, true)                    # 3 sigma at relative_sd = 0.02
+    assert sc.parallelize(["a", "b", "a", "c"] * 10, 2).count_approx_distinct() == 3     # small range: linear counting is exact-ish
+    assert ds.id() == ds.ds_id
