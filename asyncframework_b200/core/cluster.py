@@ -535,6 +535,8 @@ class ClusterScheduler:
             job["failed_posted"] = True
             self.listeners.post({"event": "job_end", "job": job["waiter"].job_id, "failed": True, "error": str(exc)[:300],
                                  "t_ms": time.perf_counter() * 1e3})
+        if not job["pending"]:                        # nothing of this job is in flight any more: forget it (and its binary)
+            self._finish_job(job["waiter"].job_id)
 
     def _task_succeeded(self, eid: int, job_id: int, job: dict, partition: int, data: bytes, run_ms, nbytes: int,
                         extra: Optional[dict] = None) -> None:
@@ -645,6 +647,7 @@ class ClusterScheduler:
     def _executor_lost(self, eid: int) -> None:
         if self._stopped:
             return
+        self.executor_heartbeats.pop(eid, None)        # its replacement starts with a clean liveness record
         self.listeners.post({"event": "executor_lost", "executor": eid, "t_ms": time.perf_counter() * 1e3})
         with self._lock:
             jobs = list(self._jobs.items())
@@ -704,7 +707,8 @@ class ClusterScheduler:
                 self._send(e, ("drop", job_id))
             except Exception:  # noqa: BLE001
                 pass
-        self.listeners.post({"event": "job_end", "job": job_id, "t_ms": time.perf_counter() * 1e3})
+        if not job.get("failed_posted"):              # a failed job already announced its end
+            self.listeners.post({"event": "job_end", "job": job_id, "t_ms": time.perf_counter() * 1e3})
 
     # ------------------------------------------------------------------ jobs
     def submit_job(self, dataset, func, partitions: Optional[Sequence[int]] = None,

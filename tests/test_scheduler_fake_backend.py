@@ -218,3 +218,19 @@ def test_unreachable_executor_fails_its_tasks_and_does_not_leave_the_job_danglin
         t.ok(e, w2.job_id, p, 0)
     assert w2.wait(0)
     s.stop()
+
+
+def test_failed_job_is_forgotten_once_nothing_is_in_flight_and_announces_its_end_once():
+    s, t, ds = make(max_failures=1)
+    events = []
+    s.listeners.add(lambda e: events.append(e) if e["event"] == "job_end" else None)
+    w = s.submit_job(ds, lambda tc, it: 0, result_handler=lambda i, r: None)
+    for e, p in ((0, 0), (1, 1), (0, 2)):
+        t.ok(e, w.job_id, p, 0)
+    t.err(1, w.job_id, 3)                                   # the LAST outstanding task fails for good
+    with pytest.raises(JobFailed):
+        w.wait(0)
+    assert w.job_id not in s._jobs                          # not leaked
+    assert len(events) == 1 and events[0].get("failed") is True
+    assert ("drop", w.job_id) in [m for _, m in t.sent]     # executors were told to forget the binary
+    s.stop()
