@@ -134,6 +134,21 @@ if os.path.exists(cp):
         out.append(f"| {name} | {a['ratio']}x, {a['compress_MBps']} / {a['decompress_MBps']} | {b['ratio']}x, {b['compress_MBps']} / {b['decompress_MBps']} |")
     out += ["", "(an asynchronous round = `sc.broadcast(w)` + non-blocking `async_reduce` over 4 partitions + draining the 4 results; on cluster "
             "masters the broadcast is a torrent broadcast — serialise, compress, 4 MiB pieces with Adler32, peer-to-peer fetch by 2 executor processes.)", ""]
+sc_ = os.path.join(ROOT, "profiles", "straggler_cpu_cluster.json")
+if os.path.exists(sc_):
+    d = json.load(open(sc_))
+    out += [f"### Straggler sweep through the closure API on executor processes (`{d['master']}`, CPU, {d['rows']} x {d['features']}, "
+            f"{d['workers']} workers; `examples/straggler_sweep.py --master ...`)", "",
+            "Equal work per row pair (240 worker-updates): ASAGA applies every worker's result as it arrives, synchronous SAGA waits for all workers "
+            "each iteration.  Delay = multiple of the mean task time injected into worker 0 (-1 = production-cluster model, 25 % stragglers).", "",
+            "| delay | ASAGA elapsed ms | ASAGA objective | sync SAGA elapsed ms | sync SAGA objective |", "|---|---|---|---|---|"]
+    runs = {(r["algorithm"], r["delay"]): r for r in d["runs"]}
+    for c in sorted({r["delay"] for r in d["runs"]}, key=lambda x: (x < 0, x)):
+        a, s = runs[("asaga", c)], runs[("saga_sync", c)]
+        out.append(f"| {c} | {a['elapsed_ms']:.0f} | {a['objective']:.4f} | {s['elapsed_ms']:.0f} | {s['objective']:.4f} |")
+    out += ["", "The synchronous run slows down with the straggler (it waits for it every iteration); the asynchronous one is nearly flat and, for the "
+            "same amount of gradient work, is ~20x closer to the optimum — the reference's claim, reproduced on this framework's CPU closure path "
+            "(per-update overhead of the process transport is ~4 ms here, so absolute times are dominated by it).", ""]
 ev = os.path.join(ROOT, "profiles", "bench", "eval_bench_r1.log")
 if os.path.exists(ev):
     out += ["## Objective evaluation (K12): tcgen05/TMEM GEMM vs exact CUDA-core kernel (1 GPU, 2 M x 784)", "",
