@@ -17,7 +17,12 @@ def pytest_collection_modifyitems(config, items):
     ngpu = torch.cuda.device_count() if has_gpu else 0
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
     skip_multi = pytest.mark.skip(reason="needs >= 2 CUDA devices")
+    # a deadlock in a multi-process / networked test must fail THAT test, not hang the whole run (pytest-timeout, when installed;
+    # CPU tests only: the longest one takes ~15 s, GPU tests keep their own budgets)
+    has_timeout = config.pluginmanager.hasplugin("timeout")
     for item in items:
+        if has_timeout and "gpu" not in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(int(os.environ.get("AFB_TEST_TIMEOUT", "300"))))
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(skip_gpu)
         if "multigpu" in item.keywords and ngpu < 2:
