@@ -31,6 +31,7 @@ def run_nccl(cfg: AsyncConfig, points=None) -> RunReport:
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     from baseline.nccl_sync import NcclSyncSGD
+    owns_group = not dist.is_initialized()
     rank, local_rank, world = init_distributed()
     device = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
     if cfg.num_partitions % world != 0:
@@ -82,4 +83,11 @@ def run_nccl(cfg: AsyncConfig, points=None) -> RunReport:
             rep.objective = [(t, float(v)) for (t, _), v in zip(snaps, (tot / total).tolist())]
     metrics.emit("report", **rep.to_dict())
     metrics.close()
+    if owns_group and dist.is_initialized():
+        # leave the process group cleanly: a rank that exits with live gloo / NCCL threads can abort during interpreter teardown
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
     return rep
