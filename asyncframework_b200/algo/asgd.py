@@ -70,6 +70,12 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         wlock = threading.Lock() if cfg.extra.get("lock_w", False) else None   # Hogwild by default (:189 vs :242)
 
         def updater():
+            try:
+                _updater()
+            except BaseException as exc:  # noqa: BLE001 — surfaced by the submitter loop instead of spinning on state['k'] forever
+                state["error"] = exc
+
+        def _updater():
             from .common import host_math_threads
             host_math_threads.pin()                        # small-vector math: one intra-op thread for this thread
             while state["k"] < iters:
@@ -111,6 +117,10 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
         pred = barriers.bucket(P, cfg.bucket_ratio)
         last_k, resubmits, submitted = -1, 0, 0
         while state["k"] < iters:
+            if state.get("error") is not None:
+                raise RuntimeError(f"asgd updater thread failed: {state['error']!r}") from state["error"]
+            if AC.lost and len(AC.lost) >= cfg.extra.get("max_lost_tasks", 4 * P):
+                AC.raise_if_failed()                       # every retry of many tasks failed: stop instead of resubmitting forever
             k = state["k"]
             init_workers = P if submitted == 0 else AC.stat.available_workers()   # STAT is empty before the first submission
             if init_workers >= need:

@@ -79,6 +79,7 @@ def run(cfg: AsyncConfig, points=None, scheduler=None) -> RunReport:
             got = 0
             while got < expected:
                 info = AC.collect_all(timeout=0.05)
+                AC.raise_if_failed()         # a task that exhausted its retries fails the (conceptually blocking) BSP job
                 if watchdog.dead:
                     raise WorkerLost(f"worker(s) {watchdog.dead} stopped responding in iteration {k}: a BSP run cannot continue")
                 if info is None:

@@ -46,6 +46,9 @@ class AsyncContext(Generic[T]):
         self._inflight = [0] * self.num_workers
         self._inflight_lock = threading.Lock()
         self.merge_lock = threading.Lock()   # JobWaiter.taskSucceeded is `synchronized`
+        # tasks of async jobs that exhausted their retries: nobody awaits an async JobWaiter (DAGScheduler.scala:641-660,
+        # quirk B.15), so the failure is recorded here for the drivers to surface (`raise_if_failed`)
+        self.lost: list = []
 
     def __del__(self):
         try:
@@ -183,6 +186,17 @@ class AsyncContext(Generic[T]):
     ASYNCcollectAll = collect_all
     get_size = size
     get_current_time = lambda self: self.current_time  # noqa: E731
+
+    def record_lost(self, worker: int, exc) -> None:
+        """A task of an async job was lost for good (retries exhausted / result handler raised)."""
+        self.lost.append((int(worker), exc))
+
+    def raise_if_failed(self) -> None:
+        """BSP drivers call this while waiting for P results: a blocking Spark job would raise on the driver."""
+        if self.lost:
+            from .scheduler import JobFailed
+            worker, exc = self.lost[0]
+            raise JobFailed(f"async task of worker {worker} failed permanently: {exc!r}") from (exc if isinstance(exc, BaseException) else None)
 
     def set_record_stat(self, b: bool) -> None:
         self.record_stat = bool(b)

@@ -188,7 +188,10 @@ class Scheduler:
             task = q.get()
             if task is None:
                 return
-            self._run_task(task, eid, stream)
+            try:
+                self._run_task(task, eid, stream)
+            except BaseException as exc:  # noqa: BLE001 — an executor thread must never die: later tasks would never be dequeued
+                self._fail_job(task.job, task.partition, exc)
 
     def _run_task(self, task: _Task, eid: int, stream) -> None:
         job: JobWaiter = task.job
@@ -241,9 +244,32 @@ class Scheduler:
         dt = (time.perf_counter() - t0) * 1e3
         self.listeners.post({"event": "task_end", "job": job.job_id, "partition": task.partition,
                              "executor": eid, "run_ms": dt, "metrics": tctx.metrics})
-        job.task_succeeded(task.partition, result)
+        try:
+            job.task_succeeded(task.partition, result)
+        except Exception as exc:  # noqa: BLE001 — the user's result handler raised (e.g. merge of an empty aggregate with
+            # strict_empty=True): the job fails on the driver like a blocking Spark job would (JobWaiter.scala:56-64 runs the
+            # handler under the listener's lock and a throw fails the job), the worker is freed, the executor thread lives on
+            self._fail_job(job, task.partition, exc)
+            return
         if job.done:
             self.listeners.post({"event": "job_end", "job": job.job_id, "t_ms": time.perf_counter() * 1e3})
+
+    def _fail_job(self, job: JobWaiter, partition: int, exc: BaseException) -> None:
+        self.failed_jobs.append(job.job_id)
+        first_failure = job.failure is None
+        try:
+            job.job_failed(exc)
+        except Exception:  # noqa: BLE001
+            pass
+        if first_failure:
+            self.listeners.post({"event": "job_end", "job": job.job_id, "failed": True, "error": repr(exc)[:300],
+                                 "t_ms": time.perf_counter() * 1e3})
+        on_fail = getattr(job, "on_task_lost", None)
+        if on_fail is not None:
+            try:
+                on_fail(partition, exc)
+            except Exception:  # noqa: BLE001
+                pass
 
     @staticmethod
     def _task_lost(job: JobWaiter, partition: int) -> None:

@@ -1218,6 +1218,9 @@ class ShardedDataset:
             if index in sel:
                 ctx.mark_finished(index)
             ctx.stat.set_available(index, True)
+            from ..core.scheduler import JobCancelled
+            if exc is not None and not isinstance(exc, JobCancelled):
+                ctx.record_lost(index, exc)
 
         sched.set_mode(1)   # ASYNCreduce always switches the scheduler to non-blocking (RDD.scala:1167)
         # only the selected partitions do work; running the no-op tasks of the others is pure

@@ -44,9 +44,8 @@ def _partition_grad(gradient: Gradient, shard, w: torch.Tensor):
     if shard is None or shard.num_rows == 0:
         return None
     if shard.device.type == "cuda":
-        from ..ops import dense as dense_ops, csr as csr_ops
-        mod = dense_ops if shard.is_dense else csr_ops
-        g, loss, cnt = mod.grad_full(shard, w, gradient.loss_id)
+        from ..ops.grad import grad_full          # one entry point: dispatches on the shard layout (dense / CSR round kernel)
+        g, loss, cnt = grad_full(shard, w, gradient.loss_id)
         return g, loss, cnt
     g, loss, cnt, _ = gradient.batch(shard, w)
     return g, float(loss), cnt

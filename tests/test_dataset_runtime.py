@@ -441,3 +441,29 @@ def test_async_grad_fast_path_matches_manual_gradients_and_saga_correction():
         assert torch.allclose(g2, Xs.T @ (torch.sigmoid(Xs @ w) - ys - 0.25), atol=1e-10)
         r0 = [r for r in got if r.worker_id == 0][0]
         assert r0.data[3].numel() == r0.data[2] == r0.data[4].numel()          # residuals and row positions line up
+
+
+def test_result_handler_exception_fails_the_job_but_never_kills_an_executor_thread():
+    """A throwing result handler (``async_aggregate(strict_empty=True)`` on an empty partition: the reference's ``None.get``,
+    RDD.scala:1333) must fail THAT job, free the worker and leave the executor threads alive — the next blocking job still runs."""
+    sched = Scheduler(2, block_first_async_job=False)
+    try:
+        ds = ShardedDataset.from_records(sched, list(range(8)), 2)
+        empty = ds.filter(lambda x: x < 4)                      # partition 1 (records 4..7) becomes empty
+        ctx = AsyncContext(2, sched)
+        waiter = empty.async_aggregate(0, lambda a, r: a + r, lambda a, b: a + b, ctx, strict_empty=True)
+        r = ctx.collect_all(timeout=5)
+        assert r is not None and r.worker_id == 0 and r.data == 0 + 1 + 2 + 3
+        t0 = time.time()
+        while waiter.failure is None and time.time() - t0 < 5:
+            time.sleep(0.01)
+        assert isinstance(waiter.failure, ValueError)
+        assert all(t.is_alive() for t in sched._threads)
+        assert ds.count() == 8                                  # would hang forever if an executor thread had died
+        assert ctx.lost and ctx.lost[0][0] == 1
+        t0 = time.time()
+        while not ctx.stat[1].available and time.time() - t0 < 5:
+            time.sleep(0.01)
+        assert ctx.stat[1].available
+    finally:
+        sched.stop()

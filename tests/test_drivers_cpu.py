@@ -307,3 +307,23 @@ def test_host_driver_checkpoint_resume_async(name, step, tmp_path):
     assert resumed.accepted == 300
     assert resumed.objective[-1][1] <= first.objective[-1][1] * 1.5         # continued from the checkpoint (async runs are not bit-reproducible: loose factor)
     assert resumed.objective[0][1] < first.objective[0][1] * 0.5
+
+
+@pytest.mark.parametrize("name", ["sgd_sync", "saga_sync"])
+def test_bsp_driver_raises_when_a_task_exhausts_its_retries(name):
+    """A BSP round whose task fails for good must raise on the driver (a blocking Spark job would), not wait forever."""
+    import threading
+    from asyncframework_b200.core import JobFailed, Scheduler
+    sched = Scheduler(4, block_first_async_job=False, max_failures=2)
+    sched.fault_injector = lambda t: (_ for _ in ()).throw(RuntimeError("disk on fire")) if (t.partition_id == 0 and t.job_id > 6) else None
+    cfg = _cfg(name, num_iterations=30, step_size=0.05, quiet=True, printer_freq=1000)
+    cfg.eval_objective = False
+    holder = {}
+    runner = threading.Thread(target=lambda: holder.update(_try(lambda: getattr(__import__("asyncframework_b200.algo", fromlist=[name]), name).run(cfg, scheduler=sched))), daemon=True)
+    runner.start()
+    runner.join(60)
+    try:
+        assert not runner.is_alive(), "driver hung on a permanently failed task"
+        assert isinstance(holder.get("err"), JobFailed), holder
+    finally:
+        sched.stop()
