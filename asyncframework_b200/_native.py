@@ -118,41 +118,6 @@ def kernels() -> C.CDLL:
         return lib
 
 
-_experimental: Optional[C.CDLL] = None
-
-
-def experimental() -> C.CDLL:
-    """``libafb_experimental.so`` (csrc/experimental): loaded only on explicit request, never by the default path."""
-    global _experimental
-    if _experimental is not None:
-        return _experimental
-    with _lock:
-        if _experimental is not None:
-            return _experimental
-        path = LIBDIR / "libafb_experimental.so"
-        if not path.exists():
-            raise NativeLibraryError(f"{path} is missing: run `python -m asyncframework_b200.build`")
-        try:
-            lib = C.CDLL(str(path))
-        except OSError as e:
-            raise NativeLibraryError(f"cannot load {path}: {e}") from e
-        from .ops._signatures import RoundParams
-        _sig(lib, "afb_dense_round_persist_max_ld", C.c_int, [])
-        _sig(lib, "afb_dense_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p])
-        _sig(lib, "afb_pipe_state_bytes", C.c_int, [])
-        _sig(lib, "afb_dense_round_pipelined_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
-        _sig(lib, "afb_dense_round_bf16_max_ld", C.c_int, [])
-        _sig(lib, "afb_dense_round_bf16_ctas_per_sm", C.c_int, [C.c_longlong])
-        _sig(lib, "afb_dense_round_bf16_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_void_p])
-        _sig(lib, "afb_grid_bar_bytes", C.c_int, [])
-        _sig(lib, "afb_csr_round_persist_launch", C.c_int, [C.POINTER(RoundParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
-        if hasattr(lib, "afb_eval_loss_tc"):
-            _sig(lib, "afb_eval_loss_tc", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                                    C.c_void_p, C.c_void_p, C.c_void_p])
-        _experimental = lib
-        return lib
-
-
 def kernels_available() -> bool:
     try:
         kernels()

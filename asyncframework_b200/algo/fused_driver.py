@@ -118,6 +118,13 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
             h = ck.get("history", {}).get(wid)
             if h is not None and rk.hist is not None:
                 rk.hist.copy_(h.to(device))
+        # resume is EXACT: the accepted-update counter k, the logical clock and the per-worker round counters continue, so the
+        # step-size schedule (gamma/sqrt(floor(k/P)+1), rsqrt(round+1)) and the seed+round+1 sampling sequence pick up where
+        # the checkpoint left off, and `num_iterations` is a TOTAL (as in the host drivers)
+        rounds = (ck.get("extra") or {}).get("rounds")
+        if rounds is not None and len(rounds) != len(engine.kernels):
+            rounds = None
+        engine.restore_progress(k0, ck.get("clock"), rounds)
     engine.barrier()
     is_async = engine.is_async
     iters = cfg.num_iterations
@@ -126,8 +133,10 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
     next_snap = cfg.printer_freq
     R = max(1, int(cfg.rounds_per_graph))
     t0 = time.perf_counter()
-    k = 0
-    ck_next = cfg.checkpoint_every if cfg.checkpoint_every else None
+    k = k0
+    while next_snap <= k:
+        next_snap += cfg.printer_freq
+    ck_next = (k0 // cfg.checkpoint_every + 1) * cfg.checkpoint_every if cfg.checkpoint_every else None
     ck_writer = None
     if ck_next is not None and cfg.checkpoint_dir:
         from ..utils.checkpoint import AsyncCheckpointWriter
@@ -151,8 +160,9 @@ def run_fused(cfg: AsyncConfig, points=None) -> RunReport:
             say(cfg, f"Iteration {k} is finished")
             metrics.emit("snapshot", k=k, elapsed_ms=snaps[-1][0])
             if watchdog is not None:
-                for wdead in watchdog.check_once():
-                    say(cfg, f"worker {wdead} declared dead (no device heartbeat for {cfg.heartbeat_timeout_s} s)")
+                for wdead in watchdog.check_once(expect_running=True):
+                    say(cfg, f"worker {wdead} declared dead (no device heartbeat for {cfg.heartbeat_timeout_s} s): continuing with "
+                             f"{P - len(watchdog.dead)} workers")
                     metrics.emit("worker_dead", worker=wdead)
             while next_snap <= k:
                 next_snap += cfg.printer_freq

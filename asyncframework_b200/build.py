@@ -117,41 +117,9 @@ def build_kernels(force: bool = False, verbose: bool = False, keep_ptx: bool = F
     return out
 
 
-def build_experimental(force: bool = False, verbose: bool = False) -> Optional[Path]:
-    """``libafb_experimental.so``: kernels under ``csrc/experimental`` (persistent multi-round variant).  A separate
-    library so that work in progress can never change the binary of the validated default path; it is only ever
-    loaded on explicit request (``AFB_DENSE_VARIANT=persist``)."""
-    LIBDIR.mkdir(parents=True, exist_ok=True)
-    out = LIBDIR / "libafb_experimental.so"
-    srcs = sorted((CSRC / "experimental").glob("*.cu"))
-    if not srcs:
-        return None
-    stamp = LIBDIR / ".experimental.sha"
-    dg = _digest(srcs, "exp-v1")
-    if out.exists() and not force and stamp.exists() and stamp.read_text() == dg:
-        return out
-    nvcc = find_nvcc()
-    if nvcc is None:
-        raise RuntimeError("nvcc not found; cannot build CUDA kernels")
-    logdir = ROOT / "build"
-    logdir.mkdir(parents=True, exist_ok=True)
-    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *NVCC_ARCH, "-Xcompiler", "-fPIC", "-I", str(CSRC / "include"),
-           "--expt-relaxed-constexpr", "-Xptxas", "-v", "-shared", *[str(s) for s in srcs], "-o", str(out)]
-    if verbose:
-        print("[build]", " ".join(cmd), flush=True)
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    (logdir / "ptxas_experimental.log").write_text(res.stdout)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout)
-        raise RuntimeError("nvcc failed for csrc/experimental")
-    stamp.write_text(dg)
-    return out
-
-
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_runtime(force=force, verbose=verbose)
     build_kernels(force=force, verbose=verbose)
-    build_experimental(force=force, verbose=verbose)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,25 @@ class RoundParams(C.Structure):
         ("gamma", f32), ("inv_par_recs", f32), ("inv_n", f32), ("delay_coeff", f32),
         ("delay_mode", i32), ("warmup_updates", i32), ("seed_mode", i32), ("loss_id", i32),
         ("round_host", i32), ("pdl", i32),
+        ("reg_param", f32), ("reg_type", i32), ("ssp_bound", i32), ("use_mask", i32),
+        ("desc", vp), ("desc_slots", i32), ("pull_ahead_chunks", i32), ("spin_limit_ns", u64),
     ]
+
+
+REG_TYPES = {None: 0, "none": 0, "l2": 1, "squared_l2": 1, "l1": 2}
+
+# per-round descriptor of the end-to-end path (afb::RoundDesc): {gamma, thr24, delay_coeff, seq}
+ROUND_DESC_DTYPE = np.dtype([("gamma", "<f4"), ("thr24", "<i4"), ("delay_coeff", "<f4"), ("seq", "<u4")], align=False)
+assert ROUND_DESC_DTYPE.itemsize == 16
+
+# double-buffered per-round state of the pipelined persistent rounds (afb::PipeBuf x 2)
+PIPE_BUF_DTYPE = np.dtype([
+    ("chunk_ctr", "<u4"), ("done_ctas", "<u4"), ("pull_ticket", "<u4"), ("pull_flag", "<u4"),
+    ("proceed", "<i4"), ("batch_count", "<u4"), ("loss_sum", "<f4"), ("tk_flag", "<u4"),
+    ("ts", "<u8"), ("k_read", "<u8"), ("t_start_ns", "<u8"), ("tk_staleness", "<i8"), ("tk_k_after", "<i8"),
+    ("tk_accept", "<i4"), ("tk_step", "<f4"), ("tk_clock_old", "<u4"), ("pad", "<u4"), ("pad16", "<u8"),
+], align=False)
+assert PIPE_BUF_DTYPE.itemsize == 96      # alignas(16): 88 bytes of fields + tail padding
 
 
 class SyncPeers(C.Structure):
@@ -43,13 +61,15 @@ WORKER_CTL_DTYPE = np.dtype([
     ("dbg_ns", "<u8", (8,)),
     ("tk_flag", "<u4"), ("tk_accept", "<i4"), ("tk_step", "<f4"), ("tk_clock_old", "<u4"),
     ("tk_staleness", "<i8"), ("tk_k_after", "<i8"),
+    ("abort", "<i4"), ("skipped_rounds", "<u4"), ("pad_tail", "<u8"),
 ], align=False)
-assert WORKER_CTL_DTYPE.itemsize == 240
+assert WORKER_CTL_DTYPE.itemsize == 256
 
 SERVER_CTL_DTYPE = np.dtype({
-    "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns"],
-    "formats": ["<u8", "<i4", "<i4", "<u8", "<u4", "<u4", "<u8"],
-    "offsets": [0, 8, 12, 16, 24, 28, 32], "itemsize": 48})
+    "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns", "gate_dyn", "num_alive",
+              "enable_mask"],
+    "formats": ["<u8", "<i4", "<i4", "<u8", "<u4", "<u4", "<u8", "<i4", "<i4", ("<u8", (4,))],
+    "offsets": [0, 8, 12, 16, 24, 28, 32, 40, 44, 48], "itemsize": 80})
 
 WORKER_SLOT_DTYPE = np.dtype([
     ("available", "<i4"), ("alive", "<i4"), ("staleness", "<i8"), ("num_tasks", "<i8"),
@@ -74,6 +94,12 @@ def declare(lib: C.CDLL) -> None:
         fn.argtypes = argtypes
 
     P = C.POINTER
+    sig("afb_dense_stream_launch", C.c_int, [P(RoundParams), C.c_int, C.c_int, C.c_int, C.c_int, vp])
+    sig("afb_dense_stream_pipelined_launch", C.c_int, [P(RoundParams), C.c_int, C.c_int, vp, vp, vp, C.c_int, vp])
+    sig("afb_dense_stream_max_ld", C.c_int, [])
+    sig("afb_dense_stream_ctas_per_sm", C.c_int, [i64, C.c_int])
+    sig("afb_dense_stream_depth", C.c_int, [i64, C.c_int])
+    sig("afb_pipe_state_bytes", C.c_int, [])
     sig("afb_dense_round_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_dense_round_max_ld", C.c_int, [])
     sig("afb_dense_round_ctas_per_sm", C.c_int, [i64])
@@ -92,6 +118,9 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_eval_mse_dense", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, C.c_int, vp, vp])
     sig("afb_eval_mse_csr", C.c_int, [vp, vp, vp, vp, i64, C.c_int, vp, C.c_int, C.c_int, vp, vp])
     sig("afb_eval_mse_tc", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, vp, vp, vp])
+    sig("afb_eval_loss_tc", C.c_int, [vp, vp, i64, i64, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp])
+    sig("afb_csr_stream_launch", C.c_int, [P(RoundParams), C.c_int, C.c_int, C.c_int, vp, vp])
+    sig("afb_grid_bar_bytes", C.c_int, [])
     sig("afb_abi_sizeof", C.c_int, [C.c_int])
     sig("afb_ipc_get_handle", C.c_int, [vp, vp])
     sig("afb_ipc_open_handle", C.c_int, [vp, P(vp)])

@@ -1,9 +1,8 @@
 """Objective evaluation (K12) on HBM-resident shards: Σ_i loss(x_i·w_t, y_i) for T snapshots in one
-pass.  Dense shards with >= 8 snapshots and a squared-error objective go to the tcgen05 GEMM kernel
-(eval_tc.cu; X consumed as tf32, parameters split hi/lo => ~1e-3 relative accuracy on generic data,
-exact on integer/bf16-representable data); set AFB_EVAL_TC=0 to force the exact-fp32 CUDA-core
-kernels (eval.cu), which also serve CSR shards and the logistic / hinge objectives (AFB_EVAL_TC_LOSS=1 routes those
-through the experimental tensor-core epilogue in libafb_experimental.so instead)."""
+pass.  Dense shards with >= 8 snapshots go to the tcgen05 GEMM kernel for every objective (eval_tc.cu: squared error,
+logistic, hinge, half-squared applied in the TMEM epilogue; X consumed as tf32, parameters split hi/lo => ~1e-3 relative
+accuracy on generic data, exact on integer/bf16-representable data); set AFB_EVAL_TC=0 to force the exact-fp32 CUDA-core
+kernels (eval.cu), which also serve CSR shards and small evaluations."""
 from __future__ import annotations
 
 import os
@@ -25,21 +24,11 @@ def eval_loss(shard: Shard, W: torch.Tensor, loss_id: int, use_tensor_cores=None
     if shard.is_dense:
         if use_tensor_cores is None:
             use_tensor_cores = os.environ.get("AFB_EVAL_TC", "1") == "1" and T >= 8 and shard.num_rows >= 128
-        if use_tensor_cores and hasattr(lib, "afb_eval_mse_tc") and loss_id in (0, 3):
+        if use_tensor_cores:
+            # tcgen05 / TMEM / TMA GEMM with the loss applied in the TMEM -> register epilogue (csrc/kernels/eval_tc.cu)
             scratch = torch.empty(64 * ld, dtype=torch.float32, device=shard.device)
-            check(lib.afb_eval_mse_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,
-                                      out.data_ptr(), scratch.data_ptr(), current_stream_ptr()), "eval_mse_tc")
-            if loss_id == 3:
-                out *= 0.5
-            return out
-        if use_tensor_cores and os.environ.get("AFB_EVAL_TC_LOSS", "0") == "1":
-            # EXPERIMENTAL (not yet run on hardware): logistic / hinge through the same tcgen05 GEMM, loss applied in the
-            # TMEM epilogue (csrc/experimental/eval_tc_loss.cu).  Off by default; the exact CUDA-core kernel below is the default.
-            from .._native import experimental
-            xlib = experimental()
-            scratch = torch.empty(64 * ld, dtype=torch.float32, device=shard.device)
-            check(xlib.afb_eval_loss_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T, loss_id,
-                                        out.data_ptr(), scratch.data_ptr(), current_stream_ptr()), "eval_loss_tc")
+            check(lib.afb_eval_loss_tc(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T, loss_id,
+                                       out.data_ptr(), scratch.data_ptr(), current_stream_ptr()), "eval_loss_tc")
             return out
         check(lib.afb_eval_mse_dense(shard.X.data_ptr(), shard.y.data_ptr(), shard.num_rows, ld, d, Wt.data_ptr(), T,
                                      loss_id, out.data_ptr(), current_stream_ptr()), "eval_mse_dense")

@@ -20,8 +20,8 @@ import torch
 from ..core.sampler import threshold24
 from ..data.batch import Shard
 from . import check, kernels
-from ._signatures import (RESULT_REC_DTYPE, RoundParams, SERVER_CTL_DTYPE, SyncPeers, WORKER_CTL_DTYPE,
-                          WORKER_SLOT_DTYPE)
+from ._signatures import (REG_TYPES, RESULT_REC_DTYPE, ROUND_DESC_DTYPE, RoundParams, SERVER_CTL_DTYPE, SyncPeers,
+                          WORKER_CTL_DTYPE, WORKER_SLOT_DTYPE)
 
 ALGO = {"grad_only": 0, "asgd": 1, "asaga": 2, "sgd_sync": 3, "saga_sync": 4}
 NEVER_STALE = 1 << 40
@@ -89,6 +89,8 @@ class ServerBlock:
         self.status.copy_(torch.from_numpy(st.view(np.uint8)).to(self.buf.device))
         sc = np.zeros(1, dtype=SERVER_CTL_DTYPE)
         sc["avail_count"] = self.layout.num_workers
+        sc["num_alive"] = self.layout.num_workers
+        sc["enable_mask"] = np.uint64(0xFFFFFFFFFFFFFFFF)          # every worker enabled until a predicate says otherwise
         self.sctl.copy_(torch.from_numpy(sc.view(np.uint8)).to(self.buf.device))
 
     # host-side reads (sync D2H of a few hundred bytes)
@@ -96,7 +98,34 @@ class ServerBlock:
         a = self.sctl.cpu().numpy().view(SERVER_CTL_DTYPE)[0]
         ck = int(a["clock_k"])
         return {"clock": ck & 0xFFFFFFFF, "k": ck >> 32, "avail_count": int(a["avail_count"]), "stop": int(a["stop"]),
-                "avg_delay_ns": int(a["avg_delay_ns"]), "cul_count": int(a["cul_count"])}
+                "avg_delay_ns": int(a["avg_delay_ns"]), "cul_count": int(a["cul_count"]), "gate_dyn": int(a["gate_dyn"]),
+                "num_alive": int(a["num_alive"]), "enable_mask": [int(x) for x in a["enable_mask"]]}
+
+    def _poke(self, field: str, values: np.ndarray) -> None:
+        """Overwrite ONE field of the server control word in place (in-flight counters next to it are not clobbered)."""
+        off = self.layout.off_sctl + SERVER_CTL_DTYPE.fields[field][1]
+        raw = np.ascontiguousarray(values).view(np.uint8)
+        self.buf[off:off + raw.size].copy_(torch.from_numpy(raw.copy()).to(self.buf.device))
+
+    def set_enable_mask(self, enabled) -> None:
+        """ASYNCbarrier bridge: bit q of the mask = worker q may start rounds (workers with a clear bit skip theirs)."""
+        words = np.zeros(4, dtype=np.uint64)
+        for q, on in enumerate(enabled):
+            if on:
+                words[q >> 6] |= np.uint64(1) << np.uint64(q & 63)
+        self._poke("enable_mask", words)
+
+    def set_gate_dyn(self, threshold: int, num_alive: int) -> None:
+        self._poke("gate_dyn", np.asarray([int(threshold), int(num_alive)], dtype=np.int32))
+
+    def add_avail(self, delta: int) -> None:
+        """Host-side correction of the idle-worker counter (watchdog: a worker that died while idle no longer counts)."""
+        a = self.sctl.cpu().numpy().view(SERVER_CTL_DTYPE)[0]
+        self._poke("avail_count", np.asarray([int(a["avail_count"]) + int(delta)], dtype=np.int32))
+
+    def set_progress(self, k: int, clock: int) -> None:
+        """Restore the accepted-update counter and the logical clock (checkpoint resume)."""
+        self._poke("clock_k", np.asarray([(int(k) << 32) | (int(clock) & 0xFFFFFFFF)], dtype=np.uint64))
 
     def read_status(self) -> np.ndarray:
         return self.status.cpu().numpy().view(WORKER_SLOT_DTYPE).copy()
@@ -105,11 +134,8 @@ class ServerBlock:
         return self.ring.cpu().numpy().view(RESULT_REC_DTYPE).copy()
 
     def request_stop(self) -> None:
-        sc = self.sctl.cpu().numpy().view(SERVER_CTL_DTYPE).copy()
-        sc["stop"] = 1
         # only the stop word is rewritten so in-flight counters are not clobbered
-        self.buf[self.layout.off_sctl + 12:self.layout.off_sctl + 16].copy_(
-            torch.from_numpy(np.asarray([1], dtype=np.int32).view(np.uint8)).to(self.buf.device))
+        self._poke("stop", np.asarray([1], dtype=np.int32))
 
 
 @dataclass
@@ -138,6 +164,8 @@ class _SimLib:
     """Stand-in for libafb_kernels.so when a RoundKernel runs against the CPU simulator."""
 
     def afb_dense_round_max_ld(self): return 1 << 30
+    def afb_dense_stream_max_ld(self): return 1 << 30
+    def afb_dense_stream_ctas_per_sm(self, ld, bf16=0): return 2
     def afb_dense_round_ctas_per_sm(self, ld): return 2
     def afb_dense_round_ring_max_ld(self): return 0
     def afb_dense_round_pipe_max_ld(self): return 0
@@ -145,7 +173,18 @@ class _SimLib:
 
 
 class RoundKernel:
-    """One logical worker's fused round: ``launch()`` enqueues exactly one kernel."""
+    """One logical worker's fused rounds.
+
+    ``launch_rounds(n)`` enqueues ``n`` rounds as ONE persistent kernel (csrc/kernels/dense_stream.cu for dense shards,
+    csr_stream.cu for wide CSR models): the worker loop runs on the device, rounds are separated by flags in device memory.
+    ``launch()`` enqueues a single round.  Dense kernel variants (``variant=`` / ``AFB_DENSE_VARIANT``):
+
+    * ``stream`` (default) — TMA bulk-copy row rings + persistent rounds; ASGD without a gate additionally PIPELINES its
+      rounds (round r+1 streams while round r's NVLink tail is in flight; ``pipeline=False`` / ``AFB_PIPELINE=0`` turns
+      that off);
+    * ``simple`` — the register double-buffered one-round kernel (dense_round.cu; also used for SAGA rollback rounds);
+    * ``ring`` / ``pipe`` — earlier one-round TMA variants kept for A/B measurements.
+    """
 
     def __init__(self, shard: Shard, server: ServerPointers, *, algo: str, loss_id: int, num_workers: int,
                  worker_id: int, total_rows: int, batch_rate: float, gamma: float, seed: int,
@@ -153,14 +192,16 @@ class RoundKernel:
                  delay_mode: int = 0, delay_coeff: float = 0.0, warmup_updates: int = 0,
                  local_block: Optional[ServerBlock] = None, peer_blocks: Optional[List[ServerPointers]] = None,
                  grid: Optional[int] = None, seed_mode: Optional[int] = None, rollback: Optional[bool] = None,
-                 variant: Optional[str] = None, wctl: Optional[torch.Tensor] = None, sim_server_block=None):
+                 variant: Optional[str] = None, wctl: Optional[torch.Tensor] = None, sim_server_block=None,
+                 reg_param: float = 0.0, reg_type: Optional[str] = None, ssp_bound: int = -1, use_mask: bool = False,
+                 pipeline: Optional[bool] = None, multicast_base: int = 0, spin_limit_s: Optional[float] = None):
         # CPU shards run against the pure-Python round simulator (ops/round_sim.py): same byte layouts and
         # protocol, used by the CPU test-suite; CUDA shards always run the hand-written kernels.
         self.sim = shard.device.type != "cuda"
         if self.sim and os.environ.get("AFB_ALLOW_SIM", "1") != "1":
             raise ValueError("RoundKernel needs an HBM-resident shard")
-        # bf16 ROW STORAGE (dense shards only; EXPERIMENTAL, csrc/experimental/dense_round_bf16.cu): X is bf16, everything else
-        # (labels, parameters, gradient, accumulation) stays fp32.  Half the HBM bytes per round.
+        # bf16 ROW STORAGE (dense shards only): X is bf16, everything else (labels, parameters, gradient, accumulation)
+        # stays fp32.  Half the HBM bytes per round.
         self.bf16_rows = shard.is_dense and shard.X.dtype == torch.bfloat16
         if self.bf16_rows:
             if shard.y.dtype != torch.float32:
@@ -241,12 +282,18 @@ class RoundKernel:
             sp = SyncPeers()
             for q, pb in enumerate(peer_blocks):
                 sp.gstage[q] = pb.gstage; sp.flags[q] = pb.flags
+            if multicast_base and os.environ.get("AFB_NVLS_BSP", "1") == "1":
+                # NVLS: the all-gather of the BSP round is ONE multimem.st stream through the multicast alias of the
+                # symmetric block (same offsets on every rank) instead of P peer-store loops
+                sp.mc_gstage = multicast_base + server.layout.off_gstage
+                sp.mc_flags = multicast_base + server.layout.off_flags
             self._sync_peers_host = sp
             self.peers_buf = torch.from_numpy(np.frombuffer(bytes(sp), dtype=np.uint8).copy()).to(dev)
             p.peers = self.peers_buf.data_ptr()
             p.w_server = local_block.w.data_ptr()
         else:
             p.inv_par_recs = 1.0 / (batch_rate * total_rows / num_workers)
+        self.nvls_bsp = bool(algo in ("sgd_sync", "saga_sync") and multicast_base and os.environ.get("AFB_NVLS_BSP", "1") == "1")
         p.inv_n = 1.0 / total_rows
         p.delay_coeff = float(delay_coeff); p.delay_mode = int(delay_mode); p.warmup_updates = int(warmup_updates)
         if seed_mode is None:
@@ -256,80 +303,79 @@ class RoundKernel:
             if algo in ("asgd", "asaga") and os.environ.get("AFB_SEED_MODE", "round") == "round":
                 seed_mode = 1
         p.seed_mode = int(seed_mode); p.loss_id = int(loss_id)
+        # K8 fused into the apply (Updater.scala:114-158); ASYNCbarrier predicates on the device
+        p.reg_param = float(reg_param); p.reg_type = int(REG_TYPES[reg_type] if not isinstance(reg_type, int) else reg_type)
+        if p.reg_type and p.reg_param <= 0.0:
+            p.reg_type = 0
+        p.ssp_bound = int(ssp_bound) if algo in ("asgd", "asaga") else -1
+        p.use_mask = 1 if (use_mask and algo in ("asgd", "asaga")) else 0
+        if spin_limit_s is None:
+            spin_limit_s = float(os.environ.get("AFB_SPIN_LIMIT_S", "20"))
+        p.spin_limit_ns = int(spin_limit_s * 1e9)
         self.params = p
+        self.desc_dev = None                     # set by FusedEngine for the end-to-end path (RoundDesc ring)
         self.num_sms = torch.cuda.get_device_properties(dev).multi_processor_count if not self.sim else 148
-        # resident-CTA capacity of the kernel on this device; `grid` (if given) is the share of it
-        # this logical worker should occupy when several workers co-run on one GPU
-        self.ctas_per_sm = self.lib.afb_dense_round_ctas_per_sm(ld) if self.is_dense else 2
-        self.grid = int(grid) if grid else self.ctas_per_sm * self.num_sms
-        # dense variants: "simple" = register double-buffered LDG kernel, "pipe" = TMA (cp.async.bulk)
-        # producer/consumer pipeline.  Both are fully fused rounds with identical semantics.
-        variant = variant or os.environ.get("AFB_DENSE_VARIANT", "simple")
-        if self.is_dense and variant == "ring" and ld <= self.lib.afb_dense_round_ring_max_ld():
-            self.variant = "ring"
-            self._launch = self.lib.afb_dense_round_ring_launch
-            self.ctas_per_sm = 2
-            if not grid:
-                self.grid = 2 * self.num_sms
-        elif self.is_dense and variant == "pipe" and ld <= self.lib.afb_dense_round_pipe_max_ld():
-            self.variant = "pipe"
-            self._launch = self.lib.afb_dense_round_pipe_launch
-            self.ctas_per_sm = 2
-            if not grid:
-                self.grid = 2 * self.num_sms
+        # ---- kernel selection ------------------------------------------------------------------------------------
+        variant = variant or os.environ.get("AFB_DENSE_VARIANT", "stream")
+        if variant in ("persist", "pipelined"):          # round-1 spellings of the persistent kernels
+            variant = "stream"
+        self.stream = False                              # persistent TMA-ring kernel (dense)
+        self.stream_csr = False                          # persistent one-kernel CSR round
+        self._launch = None
+        if self.is_dense:
+            aligned = (shard.X.data_ptr() % 16 == 0) and (shard.y.data_ptr() % 16 == 0)
+            if self.bf16_rows and not (aligned and not self.rollback):
+                raise ValueError("bf16 row storage runs on the stream kernel only (16-byte aligned shard, no SAGA rollback rounds)")
+            if self.bf16_rows or (variant == "stream" and not self.rollback and aligned and ld <= self.lib.afb_dense_stream_max_ld()):
+                self.variant = "stream"
+                self.stream = True
+                self.ctas_per_sm = self.lib.afb_dense_stream_ctas_per_sm(ld, int(self.bf16_rows))
+            elif variant == "ring" and ld <= self.lib.afb_dense_round_ring_max_ld():
+                self.variant = "ring"
+                self._launch = self.lib.afb_dense_round_ring_launch
+                self.ctas_per_sm = 2
+            elif variant == "pipe" and ld <= self.lib.afb_dense_round_pipe_max_ld():
+                self.variant = "pipe"
+                self._launch = self.lib.afb_dense_round_pipe_launch
+                self.ctas_per_sm = 2
+            else:
+                self.variant = "simple"
+                self._launch = self.lib.afb_dense_round_launch
+                self.ctas_per_sm = self.lib.afb_dense_round_ctas_per_sm(ld)
         else:
-            self.variant = "simple" if self.is_dense else "csr"
-            self._launch = self.lib.afb_dense_round_launch if self.is_dense else self.lib.afb_csr_round_launch
-        if self.bf16_rows:
-            self.variant = "bf16"
-            if not self.sim:
-                from .._native import experimental
-                exp = experimental()
-                if ld > exp.afb_dense_round_bf16_max_ld():
-                    raise ValueError(f"bf16 dense kernel supports ld <= {exp.afb_dense_round_bf16_max_ld()}")
-                self._launch = exp.afb_dense_round_bf16_launch
-                self.ctas_per_sm = exp.afb_dense_round_bf16_ctas_per_sm(ld)
-                if not grid:
-                    self.grid = self.ctas_per_sm * self.num_sms
-            variant = "bf16"                       # the persistent / pipelined experimental kernels are fp32-row only
-        # "persist" (EXPERIMENTAL, csrc/experimental/dense_round_persist.cu): launch_rounds(n) is ONE resident kernel that
-        # loops over n rounds; single rounds (launch()) still use the simple kernel.  Never selected implicitly.
-        # "pipelined" (EXPERIMENTAL, csrc/experimental/dense_round_pipelined.cu): ASGD only; launch_rounds(n) is one resident
-        # kernel in which round r+1 overlaps round r's NVLink tail (one own update in flight).  Falls back to "persist" when
-        # the round is not eligible (other algorithm, bucket gate, delay injection, server-k sampling seed).
-        self.pipelined = (variant == "pipelined" and self.is_dense and algo == "asgd" and int(gate_threshold) == 0
-                          and int(delay_mode) == 0 and int(p.seed_mode) in (1, 2))
-        self.persist = (variant in ("persist", "pipelined") and not self.pipelined and self.is_dense and algo != "grad_only"
-                        and not self.rollback)
-        # CSR shards: "persist"/"pipelined" select the persistent fused wide-model round (csrc/experimental/csr_round_persist.cu):
-        # one resident grid, multi-CTA pull/push separated by in-kernel grid barriers instead of the 4-launch split round
-        self.persist_csr = (variant in ("persist", "pipelined") and not self.is_dense and algo in ("asgd", "asaga") and not self.rollback)
-        self._persist_lib = None
-        if self.persist_csr and not self.sim:
-            from .._native import experimental
-            self._persist_lib = experimental()
-            self._grid_bar = torch.zeros(self._persist_lib.afb_grid_bar_bytes(), dtype=torch.uint8, device=dev)
-        if (self.persist or self.pipelined) and not self.sim:
-            from .._native import experimental
-            self._persist_lib = experimental()
-            if ld > self._persist_lib.afb_dense_round_persist_max_ld():
-                self.persist = self.pipelined = False
-        if self.pipelined and not self.sim:
-            self._pipe_state = torch.zeros(self._persist_lib.afb_pipe_state_bytes(), dtype=torch.uint8, device=dev)
+            self.variant = "csr"
+            self._launch = self.lib.afb_csr_round_launch
+            self.ctas_per_sm = 2
+        self.grid = int(grid) if grid else self.ctas_per_sm * self.num_sms
+        # pipelined rounds: ASGD, no device gate, worker-local sampling seed
+        if pipeline is None:
+            pipeline = os.environ.get("AFB_PIPELINE", "1") == "1"
+        self.pipelined = bool(self.stream and pipeline and algo == "asgd" and int(gate_threshold) == 0 and p.ssp_bound < 0
+                              and not p.use_mask and int(p.seed_mode) in (1, 2))
+        if self.pipelined:
+            nbytes = 192 if self.sim else self.lib.afb_pipe_state_bytes()
+            self._pipe_state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             self._pipe_g2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
             self._pipe_w2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
+            # pull round r+1's parameters when ~6 us of round r remain: chunks/us = HBM bytes/us / (row bytes * 64 * b)
+            row_bytes = ld * shard.X.element_size()
+            per_us = 6.5e6 / (row_bytes * 64.0 * max(batch_rate, 1e-6))
+            p.pull_ahead_chunks = int(os.environ.get("AFB_PULL_AHEAD_CHUNKS", max(1, int(6.0 * per_us))))
+        # wide models (CSR, d = 47 236): async rounds run as ONE persistent kernel with in-kernel grid barriers
+        # (multi-CTA pull and push); rollback rounds keep the split launch sequence gate -> pull -> grad -> push
+        wide = (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
+        self.stream_csr = bool(wide and not self.rollback and variant != "simple" and (self.sim or hasattr(self.lib, "afb_csr_stream_launch")))
+        if self.stream_csr and not self.sim:
+            self._grid_bar = torch.zeros(self.lib.afb_grid_bar_bytes(), dtype=torch.uint8, device=dev)
         self.launches = 0
         self.rounds_launched = 0
         if self.sim:
             from .round_sim import RoundSim
             self._sim = RoundSim(self, sim_server_block)
-        # programmatic dependent launch (simple dense variant, non-split, no rollback kernel in between):
-        # the next round's grid starts its prologue while this round's last CTA is in its NVLink tail.
-        # Opt-in (AFB_PDL=1): measured +0.5 % at N=2 but -3 % at N=8 (profiles/README.md, run11), so off by default.
-        self.use_pdl = (not self.sim and self.variant == "simple" and not self.bf16_rows and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
+        # programmatic dependent launch (simple dense variant only; measured -3 % at N=8 in round 1: opt-in)
+        self.use_pdl = (not self.sim and self.variant == "simple" and not self.rollback and algo in ("asgd", "asaga", "sgd_sync", "saga_sync")
                         and os.environ.get("AFB_PDL", "0") == "1")
-        # wide models (CSR, d = 47 236): split round = gate -> multi-CTA pull -> grad -> multi-CTA push/apply
-        self.split = (not self.sim) and (not self.is_dense) and algo in ("asgd", "asaga") and ld >= int(os.environ.get("AFB_SPLIT_MIN_LD", "4096"))
+        self.split = (not self.sim) and wide and not self.stream_csr
         if self.split:
             pg = RoundParams.from_buffer_copy(bytes(p))
             pg.algo = ALGO["grad_only"]
@@ -338,16 +384,29 @@ class RoundKernel:
             self.push_ctl = torch.zeros(32, dtype=torch.uint8, device=dev)
             self.comm_grid = max(1, min(self.num_sms, (ld // 4 + 255) // 256))
 
+    # back-compat spellings used by older call sites / tests
+    @property
+    def persist(self) -> bool:
+        return self.stream and not self.pipelined
+
+    @property
+    def persist_csr(self) -> bool:
+        return self.stream_csr
+
     # ------------------------------------------------------------------
     def launch(self, stream=None) -> None:
+        """Enqueue ONE round."""
         if self.sim:
             self._sim.launch()
             self.launches += 1
             self.rounds_launched += 1
             return
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        sp = int(s.cuda_stream)
+        if self.stream or self.stream_csr:
+            self.launch_rounds(1, stream)
+            return
         if self.split:
-            sp = int(s.cuda_stream)
             check(self.lib.afb_gate_launch(C.byref(self.params), sp), "gate")
             check(self.lib.afb_pull_w_launch(C.byref(self.params), self.comm_grid, sp), "pull_w")
             check(self._launch(C.byref(self.params_grad), self.grid, sp), "grad (split round)")
@@ -360,52 +419,48 @@ class RoundKernel:
             self.params.round_host = self.rounds_launched
         else:
             self.params.pdl = 0
-        check(self._launch(C.byref(self.params), self.grid, int(s.cuda_stream)), "round kernel launch")
+        check(self._launch(C.byref(self.params), self.grid, sp), "round kernel launch")
         self.launches += 1
         self.rounds_launched += 1
         if self.rollback:
             check(self.lib.afb_saga_rollback_launch(self.hist.data_ptr(), self.hist_prev.data_ptr(), self.hist_tag.data_ptr(),
-                                                    self.shard.num_rows, self.wctl.data_ptr(), int(s.cuda_stream)), "saga rollback")
+                                                    self.shard.num_rows, self.wctl.data_ptr(), sp), "saga rollback")
             self.launches += 1
 
     def launch_rounds(self, n: int, stream=None, share: int = 1) -> None:
-        """Enqueue ``n`` consecutive rounds.  Default: ``n`` launches.  With the experimental persistent variant: one
-        resident kernel looping over the rounds (``share`` = persistent grids co-running on this GPU; the launcher refuses a
-        grid that cannot be fully co-resident, because the in-kernel round barrier would deadlock)."""
+        """Enqueue ``n`` consecutive rounds: ONE persistent kernel with the stream kernels (``share`` = persistent grids
+        co-running on this GPU; the launcher refuses a grid that cannot be fully co-resident, because the in-kernel round
+        barrier would deadlock), ``n`` launches with the legacy one-round variants."""
         if n <= 0:
             return
-        if not (self.persist or self.pipelined or self.persist_csr) or (n == 1 and not self.persist_csr):
-            for _ in range(n):
-                self.launch(stream)
-            return
         if self.sim:
-            if self.pipelined:
+            if self.pipelined and n > 1:
                 self._sim.launch_pipelined(n)
             else:
                 for _ in range(n):                   # protocol-wise a persistent launch IS n back-to-back rounds
                     self._sim.launch()
-            self.launches += 1
+            self.launches += 1 if (self.stream or self.stream_csr) else n
             self.rounds_launched += n
+            return
+        if not (self.stream or self.stream_csr):
+            for _ in range(n):
+                self.launch(stream)
             return
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        sp = int(s.cuda_stream)
         self.params.pdl = 0
-        if self.persist_csr:
-            check(self._persist_lib.afb_csr_round_persist_launch(C.byref(self.params), int(n), self.grid, int(share), self._grid_bar.data_ptr(),
-                                                                 int(s.cuda_stream)), "persistent CSR round kernel launch")
-            self.launches += 1
-            self.rounds_launched += n
-            return
-        if self.pipelined:
+        if self.stream_csr:
+            check(self.lib.afb_csr_stream_launch(C.byref(self.params), int(n), self.grid, int(share), self._grid_bar.data_ptr(), sp),
+                  "persistent CSR round kernel launch")
+        elif self.pipelined and n > 1:
             if share != 1:
-                raise ValueError("the pipelined variant needs the whole GPU: one logical worker per GPU")
-            check(self._persist_lib.afb_dense_round_pipelined_launch(C.byref(self.params), int(n), self.grid, self._pipe_state.data_ptr(),
-                                                                     self._pipe_g2.data_ptr(), self._pipe_w2.data_ptr(), int(s.cuda_stream)),
+                raise ValueError("pipelined rounds need the whole GPU: one logical worker per GPU")
+            check(self.lib.afb_dense_stream_pipelined_launch(C.byref(self.params), int(n), self.grid, self._pipe_state.data_ptr(),
+                                                             self._pipe_g2.data_ptr(), self._pipe_w2.data_ptr(), int(self.bf16_rows), sp),
                   "pipelined round kernel launch")
-            self.launches += 1
-            self.rounds_launched += n
-            return
-        check(self._persist_lib.afb_dense_round_persist_launch(C.byref(self.params), int(n), self.grid, int(share), int(s.cuda_stream)),
-              "persistent round kernel launch")
+        else:
+            check(self.lib.afb_dense_stream_launch(C.byref(self.params), int(n), self.grid, int(share), int(self.bf16_rows), sp),
+                  "persistent round kernel launch")
         self.launches += 1
         self.rounds_launched += n
 
@@ -415,6 +470,16 @@ class RoundKernel:
             if self.split and k not in ("algo", "seed_mode"):
                 setattr(self.params_grad, k, v)
 
+    def attach_desc(self, desc_dev: torch.Tensor, slots: int) -> None:
+        """Point the kernel at a device ring of ``RoundDesc`` (end-to-end path): slot ``round % slots`` overrides the step
+        size, the batch rate and the delay coefficient of that round."""
+        self.desc_dev = desc_dev
+        self.set(desc=desc_dev.data_ptr(), desc_slots=int(slots))
+
+    def detach_desc(self) -> None:
+        self.desc_dev = None
+        self.set(desc=None, desc_slots=0)
+
     def read_ctl_raw(self):
         return self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE)[0]
 
@@ -422,10 +487,27 @@ class RoundKernel:
         a = self.read_ctl_raw()
         return {n: (float(a[n]) if a[n].dtype.kind == "f" else int(a[n])) for n in WORKER_CTL_DTYPE.names if n != "dbg_ns"}
 
+    def check_abort(self) -> None:
+        """Raise if a bounded in-kernel spin expired in a previous launch (call after synchronising)."""
+        if int(self.read_ctl_raw()["abort"]):
+            raise RuntimeError(f"worker {self.worker_id}: a device-side wait expired (spin limit {self.params.spin_limit_ns / 1e9:.0f} s); "
+                               "the engine state is invalid")
+
+    def restore_progress(self, rounds_done: int) -> None:
+        """Checkpoint resume: continue the worker-local round counter (sampling seed / BSP step schedule)."""
+        a = self.wctl.cpu().numpy().view(WORKER_CTL_DTYPE).copy()
+        a["round"] = int(rounds_done)
+        a["rounds_done"] = int(rounds_done)
+        self.wctl.copy_(torch.from_numpy(a.view(np.uint8)).to(self.device))
+
     @property
     def variant_effective(self) -> str:
-        """The kernel ``launch_rounds`` actually uses (an experimental request that is not eligible falls back)."""
-        return "pipelined" if self.pipelined else ("persist" if (self.persist or self.persist_csr) else self.variant)
+        """The kernel ``launch_rounds`` actually uses."""
+        if self.stream:
+            return "stream-pipelined" if self.pipelined else "stream"
+        if self.stream_csr:
+            return "csr-stream"
+        return self.variant
 
     @property
     def w_view(self) -> torch.Tensor:

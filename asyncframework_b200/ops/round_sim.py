@@ -19,13 +19,17 @@ import numpy as np
 import torch
 
 from ..core.sampler import hash_u24, mix64_int
-from ._signatures import RESULT_REC_DTYPE, SERVER_CTL_DTYPE, WORKER_CTL_DTYPE, WORKER_SLOT_DTYPE
+from ._signatures import RESULT_REC_DTYPE, ROUND_DESC_DTYPE, SERVER_CTL_DTYPE, WORKER_CTL_DTYPE, WORKER_SLOT_DTYPE
 
 ALGO_GRAD_ONLY, ALGO_ASGD, ALGO_ASAGA, ALGO_SYNC_SGD, ALGO_SYNC_SAGA = 0, 1, 2, 3, 4
 
 
 def _now_ns() -> int:
     return time.perf_counter_ns()
+
+
+def _soft(t: torch.Tensor, shrink: float) -> torch.Tensor:
+    return torch.sign(t) * torch.clamp(t.abs() - shrink, min=0.0)
 
 
 def _coeff_loss(loss_id: int, margin: torch.Tensor, y: torch.Tensor):
@@ -60,7 +64,7 @@ class RoundSim:
         return block.sctl.numpy().view(SERVER_CTL_DTYPE)[0:1]
 
     def launch_pipelined(self, n: int) -> None:
-        """``n`` rounds of the pipelined persistent kernel (csrc/experimental/dense_round_pipelined.cu): round i+1's pull is
+        """``n`` rounds of the pipelined persistent kernel (csrc/kernels/dense_stream.cu, PIPE = true): round i+1's pull is
         issued before round i's update has been applied, so each round computes on parameters that lack the worker's own
         previous update (everything else — clock, tickets, ring, status — is identical to ``n`` single launches)."""
         w_next = None
@@ -77,6 +81,12 @@ class RoundSim:
         rnd = int(wc["round"][0])
         d = rk.shard.num_features
         t_entry = _now_ns()
+        # round descriptor (afb::round_desc): slot rnd % S overrides the launch scalars when its seq matches
+        gamma, thr24, delay_coeff = float(p.gamma), int(p.thr24), float(p.delay_coeff)
+        if rk.desc_dev is not None and int(p.desc_slots) > 0:
+            dsc = rk.desc_dev.numpy().view(ROUND_DESC_DTYPE).reshape(-1)[rnd % int(p.desc_slots)]
+            if int(dsc["seq"]) == rnd + 1:
+                gamma, thr24, delay_coeff = float(dsc["gamma"]), int(dsc["thr24"]), float(dsc["delay_coeff"])
         # ---------------------------------------------------------------- phase 0: gate + pull
         if algo != ALGO_GRAD_ONLY:
             if is_async:
@@ -88,6 +98,14 @@ class RoundSim:
                     wc["last_accepted"] = -1
                     wc["round"] = rnd + 1
                     return
+                if int(p.use_mask):
+                    word = int(sc["enable_mask"][0][(int(p.worker_id) >> 6) & 3])
+                    if not (word >> (int(p.worker_id) & 63)) & 1:      # masked by the host-evaluated ASYNCbarrier predicate
+                        wc["proceed"] = 2
+                        wc["last_accepted"] = -2
+                        wc["skipped_rounds"] += 1
+                        wc["round"] = rnd + 1
+                        return
                 sc["avail_count"] -= 1
                 st = srv.status.numpy().view(WORKER_SLOT_DTYPE)
                 me = st[int(p.worker_id):int(p.worker_id) + 1]
@@ -106,7 +124,7 @@ class RoundSim:
             wc["t_start_ns"] = t_entry
             avg = int(self._sctl(self.server if is_async else rk.local_block)["avg_delay_ns"][0])
             if int(p.delay_mode) != 0 and avg:
-                mult = float(p.delay_coeff)
+                mult = delay_coeff
                 if int(p.delay_mode) >= 2:
                     u = float(hash_u24(0, np.asarray([int(p.worker_id)]))[0]) / float(1 << 24)
                     mult = (2.5 + 7.5 * u) if int(p.delay_mode) == 3 else (1.5 + u)
@@ -126,7 +144,7 @@ class RoundSim:
                 self._f32_shard = Shard(sh.num_features, sh.y, sh.X.to(torch.float32), gidx=sh.gidx, partition=sh.partition)
             sh = self._f32_shard
         gidx = sh.gidx.numpy() if (sh.gidx is not None and int(p.gidx or 0)) else (np.arange(sh.num_rows, dtype=np.int64) + int(p.row_base))
-        rows = torch.from_numpy(np.nonzero(hash_u24(seed_eff, gidx) < int(p.thr24))[0])
+        rows = torch.from_numpy(np.nonzero(hash_u24(seed_eff, gidx) < thr24)[0])
         w = (rk.w_view if algo in (ALGO_SYNC_SGD, ALGO_SYNC_SAGA) else rk.w_local)[:d].to(torch.float32)
         g = torch.zeros(rk.ld, dtype=torch.float32)
         loss_sum, batch = 0.0, int(rows.numel())
@@ -173,15 +191,18 @@ class RoundSim:
                         accept = False
                     new += (1 << 32)
                 sc["clock_k"] = new
-            step = float(p.gamma) / math.sqrt(k_old // int(p.num_workers) + 1) if algo == ALGO_ASGD else float(p.gamma)
+            step = gamma / math.sqrt(k_old // int(p.num_workers) + 1) if algo == ALGO_ASGD else gamma
             if accept:
-                if algo == ALGO_ASGD:
-                    srv.w.add_(g, alpha=-step * float(p.inv_par_recs))                          # K5 (Hogwild red.add)
-                else:
-                    ab = srv.abar.clone()
-                    srv.w.add_(g, alpha=-step * float(p.inv_par_recs))
-                    srv.w.add_(ab, alpha=-step)                                                # K6
+                # hogwild_apply: delta = -step (g/parRecs [+ abar] [+ lambda w_pulled]); L1: prox against the CURRENT server value
+                delta = g * (-step * float(p.inv_par_recs))
+                if algo == ALGO_ASAGA:
+                    delta = delta - step * srv.abar                                            # abar BEFORE its update (K6)
                     srv.abar.add_(g, alpha=float(p.inv_n))
+                if int(p.reg_type) == 1:
+                    delta = delta - step * float(p.reg_param) * rk.w_local
+                elif int(p.reg_type) == 2:
+                    delta = _soft(srv.w + delta, step * float(p.reg_param)) - srv.w
+                srv.w.add_(delta)                                                              # K5 (Hogwild red.add)
             elif saga and rk.rollback:
                 tagged = rk.hist_tag == rnd
                 rk.hist[tagged] = rk.hist_prev[tagged]                                         # saga_rollback_kernel
@@ -215,8 +236,10 @@ class RoundSim:
             return
         # ---- BSP (single process: P == 1, the all-gather degenerates to the worker's own slot) ----
         blk = rk.local_block
-        step = float(p.gamma) / math.sqrt(rnd + 1) if algo == ALGO_SYNC_SGD else float(p.gamma)
+        step = gamma / math.sqrt(rnd + 1) if algo == ALGO_SYNC_SGD else gamma
         a = step * float(p.inv_par_recs)
+        if int(p.reg_type) == 1:
+            blk.w.mul_(1.0 - step * float(p.reg_param))                                        # SquaredL2Updater (Updater.scala:151-158)
         if algo == ALGO_SYNC_SGD:
             blk.w.add_(g, alpha=-a)
         else:
@@ -224,6 +247,8 @@ class RoundSim:
             blk.w.add_(g, alpha=-a)
             blk.w.add_(ab, alpha=-step)
             blk.abar.add_(g, alpha=float(p.inv_n))
+        if int(p.reg_type) == 2:
+            blk.w.copy_(_soft(blk.w, step * float(p.reg_param)))                               # L1Updater (Updater.scala:114-129)
         sc = self._sctl(blk)
         if rnd < int(p.warmup_updates):
             sc["cul_time_ns"] += _now_ns() - t_entry

@@ -26,7 +26,8 @@ import torch.distributed as dist
 from ..config import AsyncConfig
 from ..core.partial_result import PartialResult
 from ..data.batch import Shard
-from ..ops._signatures import RESULT_REC_DTYPE, WORKER_CTL_DTYPE
+from ..ops._signatures import RESULT_REC_DTYPE, ROUND_DESC_DTYPE, WORKER_CTL_DTYPE, WORKER_SLOT_DTYPE
+from ..core.sampler import threshold24
 from ..ops.round import NEVER_STALE, RoundKernel, ServerBlock, ServerLayout, ServerPointers
 from ..optim.gradient import LOSS_IDS
 from . import _devapi as _dev
@@ -67,7 +68,8 @@ def straggler_sets(num_partitions: int):
 class FusedEngine:
     def __init__(self, cfg: AsyncConfig, local_shards: Sequence[Shard], total_rows: int,
                  local_worker_ids: Optional[Sequence[int]] = None, device=None, group=None,
-                 ring_size: int = 4096, symm_provider: str = "auto", w0: Optional[torch.Tensor] = None):
+                 ring_size: int = 4096, symm_provider: str = "auto", w0: Optional[torch.Tensor] = None,
+                 worker_mask: Optional[bool] = None, pipeline: Optional[bool] = None):
         self.cfg = cfg
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -111,6 +113,15 @@ class FusedEngine:
             gate = int(math.floor(self.P * beta))
             if gate <= 1:
                 gate = 0          # >= 1 idle worker is always true for the asker itself
+        self.gate_threshold = gate
+        self.beta = (1.0 if cfg.barrier == "bsp" else cfg.bucket_ratio) if gate else 0.0
+        # device-side ASYNCbarrier beyond the bucket rule: SSP on the live status table, host-evaluated predicate mask
+        ssp_bound = int(cfg.ssp_bound) if (self.is_async and cfg.barrier == "ssp") else -1
+        if worker_mask is None:
+            worker_mask = bool(cfg.extra.get("worker_mask", False))
+        self.worker_mask = bool(worker_mask and self.is_async)
+        # K8 on the fused path: the regulariser of the reference's updaters (Updater.scala:114-158) folded into the apply
+        reg_type = {"l1": "l1", "squared_l2": "l2", "l2": "l2"}.get(str(cfg.updater).lower()) if cfg.reg_param > 0 else None
         normal, long_tail = straggler_sets(self.P) if cfg.production_cluster else ([], [])
         warm = cfg.warmup_updates_per_worker * (self.P if self.is_async else 1)
         n_local = len(self.local_worker_ids)
@@ -136,14 +147,22 @@ class FusedEngine:
                              max_iters=cfg.num_iterations if self.is_async else (1 << 40),
                              gate_threshold=gate, delay_mode=dmode, delay_coeff=max(cfg.coeff, 0.0),
                              warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid,
-                             wctl=self.wctl_all[li], sim_server_block=self.block if self.device.type != "cuda" else None)
+                             wctl=self.wctl_all[li], sim_server_block=self.block if self.device.type != "cuda" else None,
+                             reg_param=cfg.reg_param, reg_type=reg_type, ssp_bound=ssp_bound, use_mask=self.worker_mask,
+                             pipeline=pipeline, multicast_base=int(getattr(self.symm, "multicast_ptr", 0) or 0) if self.world > 1 else 0)
             self.kernels.append(rk)
             self.streams.append(_dev.new_stream(self.device) if n_local > 1 else _dev.current_stream(self.device))
         # pinned staging for the end-to-end path (double-buffered: step i+1 is submitted before the
         # result of step i is read, so the per-step host work never idles the GPU)
-        self._desc_host = _dev.pin(torch.zeros(2, 16, dtype=torch.float32), self.device)
-        self._desc_np = self._desc_host.numpy()
-        self._desc_dev = torch.zeros(2, 16, dtype=torch.float32, device=self.device)
+        # end-to-end path: a ring of per-round descriptors {step size, Bernoulli threshold, delay intensity, seq}; step()
+        # writes slot (round % S) in pinned memory and copies it H2D, the round kernel READS it (afb::round_desc)
+        self.desc_slots = 64
+        self._desc_host = _dev.pin(torch.zeros(self.desc_slots, ROUND_DESC_DTYPE.itemsize, dtype=torch.uint8), self.device)
+        self._desc_np = self._desc_host.numpy().view(ROUND_DESC_DTYPE).reshape(-1)
+        self._desc_dev = torch.zeros(self.desc_slots, ROUND_DESC_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        for rk in self.kernels:
+            rk.attach_desc(self._desc_dev, self.desc_slots)
+        self.dead_workers: List[int] = []
         self._ctl_host = _dev.pin(torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8), self.device)
         self._ctl_np = self._ctl_host.numpy()
         self._step_events = [_dev.new_event(self.device), _dev.new_event(self.device)]
@@ -160,8 +179,8 @@ class FusedEngine:
     # ------------------------------------------------------------------ hot path
     def run_rounds(self, n: int) -> None:
         """Enqueue ``n`` rounds on every local worker.  No host synchronisation."""
-        if all(rk.persist or rk.pipelined or rk.persist_csr for rk in self.kernels):
-            # experimental persistent variant: one resident kernel per worker loops over the n rounds
+        if all(rk.stream or rk.stream_csr or rk.sim for rk in self.kernels):
+            # persistent worker loops: ONE resident kernel per local worker runs its n rounds
             for rk, st in zip(self.kernels, self.streams):
                 rk.launch_rounds(n, st, share=len(self.kernels))
         else:
@@ -262,7 +281,8 @@ class FusedEngine:
                 "accepted": int((ctl["last_accepted"] == 1).sum()), "k": int(ctl["last_k_after"].max()),
                 "staleness": int(ctl["last_staleness"].max())}
 
-    def step(self, step_size: Optional[float] = None, lag: int = 0) -> Optional[Dict[str, float]]:
+    def step(self, step_size: Optional[float] = None, lag: int = 0, batch_rate: Optional[float] = None,
+             delay_coeff: Optional[float] = None) -> Optional[Dict[str, float]]:
         """One user-visible step: copy this round's descriptor (step size, batch rate, delay
         coefficient, round id) from pinned host memory to the device, run one fused round per local
         worker, copy every worker's result record back to pinned memory.
@@ -270,19 +290,18 @@ class FusedEngine:
         ``lag=0`` waits for this step's record and returns it.  ``lag=1`` returns the record of the
         PREVIOUS step (None on the first call): the copies still happen every step, but the host reads
         results one step behind so the device never waits for Python (call ``flush_steps()`` at the end)."""
-        if step_size is not None:
-            for rk in self.kernels:
-                rk.params.gamma = float(step_size)
         slot = self._step_idx & 1
         if self._step_pending[slot]:                 # slot reuse: its previous occupant must have been read
             self._step_events[slot].synchronize()
-        d = self._desc_np[slot]
-        d[0] = self.kernels[0].params.gamma
-        d[1] = self.cfg.batch_rate
-        d[2] = self.cfg.coeff
-        d[3] = float(self.rounds_enqueued)
+        rnd = self.kernels[0].rounds_launched        # == the device round counter of every local worker (lock-step launches)
+        ds = rnd % self.desc_slots
+        d = self._desc_np[ds:ds + 1]
+        d["gamma"] = self.kernels[0].params.gamma if step_size is None else float(step_size)
+        d["thr24"] = self.kernels[0].params.thr24 if batch_rate is None else threshold24(float(batch_rate))
+        d["delay_coeff"] = max(self.cfg.coeff, 0.0) if delay_coeff is None else float(delay_coeff)
+        d["seq"] = rnd + 1
         cur = _dev.current_stream(self.device)
-        self._desc_dev[slot].copy_(self._desc_host[slot], non_blocking=True)            # H2D (pinned)
+        self._desc_dev[ds].copy_(self._desc_host[ds], non_blocking=True)                # H2D (pinned): this round's descriptor
         multi = len(self.kernels) > 1
         if multi:
             fork = _dev.new_event(self.device)
@@ -321,11 +340,94 @@ class FusedEngine:
 
     @property
     def h2d_bytes_per_step(self) -> int:
-        return int(self._desc_host[0].numel() * 4)
+        return int(ROUND_DESC_DTYPE.itemsize)
 
     @property
     def d2h_bytes_per_step(self) -> int:
         return int(self._ctl_host[0].numel())
+
+    # ------------------------------------------------------------------ health, elasticity, resume
+    def check_health(self) -> None:
+        """Raise if any local worker's kernel gave up on a bounded device-side wait (call after synchronising)."""
+        for rk in self.kernels:
+            if not rk.sim:
+                rk.check_abort()
+
+    def set_worker_mask(self, enabled: Sequence[bool]) -> None:
+        """ASYNCbarrier(f, STAT) on the fused path (core/rdd/RDD.scala:1050-1064): the host evaluates the predicate over the
+        mirrored status table (``worker_states()``) and writes the selection; a worker whose bit is clear sits its rounds out
+        (an empty task in the reference).  Rank 0 owns the mask (workers read it from the server block)."""
+        if not self.worker_mask:
+            raise RuntimeError("construct the engine with worker_mask=True (cfg.extra['worker_mask']) to use predicate gating")
+        if len(enabled) != self.P:
+            raise ValueError("one flag per logical worker expected")
+        if self.rank == 0:
+            self.block.set_enable_mask([bool(x) for x in enabled])
+
+    def async_barrier(self, predicate) -> List[int]:
+        """Evaluate ``predicate(WorkerState) -> bool`` on the live device status table and select the workers for the next
+        rounds; returns the selected worker ids (rank 0; other ranks return [])."""
+        if self.rank != 0:
+            return []
+        states = self.worker_states()
+        sel = [bool(predicate(states[q])) and q not in self.dead_workers for q in range(self.P)]
+        self.set_worker_mask(sel)
+        return [q for q, on in enumerate(sel) if on]
+
+    def worker_states(self):
+        """The device status table as ``WorkerState`` objects (staleness, average task time, availability, task count, with
+        the table-wide queries ``available_workers()`` / ``max_staleness()`` the reference exposes on every record)."""
+        from ..core.worker_state import StatTable
+        st = self.worker_status()
+        table = StatTable(self.P)
+        for q in range(self.P):
+            table.set_state(q, int(st[q]["staleness"]), float(st[q]["avg_task_ms"]), bool(st[q]["available"]) and bool(st[q]["alive"]),
+                            int(st[q]["num_tasks"]))
+        return [table[q] for q in range(self.P)]
+
+    def declare_dead(self, worker: int) -> None:
+        """Continue with P-1 (the Spark side is HeartbeatReceiver.scala:193-220 expiring an executor): mark the
+        worker dead in the server's status table, take it out of the idle count if it died idle, lower the bucket threshold
+        to floor(P_alive * beta) and clear its enable bit.  Asynchronous modes only; rank 0 (the server) applies it."""
+        if worker in self.dead_workers:
+            return
+        self.dead_workers.append(int(worker))
+        if self.rank != 0 or not self.is_async:
+            return
+        st = self.block.read_status()
+        was_idle = bool(st[worker]["available"])
+        st[worker]["alive"] = 0
+        st[worker]["available"] = 0
+        off = self.layout.off_status + worker * WORKER_SLOT_DTYPE.itemsize
+        self.block.buf[off:off + 8].copy_(torch.from_numpy(st[worker:worker + 1].view(np.uint8)[:8].copy()).to(self.device))
+        if was_idle:
+            self.block.add_avail(-1)
+        alive = self.P - len(self.dead_workers)
+        self.block.set_gate_dyn(max(1, int(math.floor(alive * self.beta))) if self.gate_threshold else 0, alive)
+        if self.worker_mask:
+            self.block.set_enable_mask([q not in self.dead_workers for q in range(self.P)])
+
+    def request_stop_local(self) -> None:
+        """Stop THIS rank's rounds (BSP: a peer died — every surviving rank's watchdog calls this; the in-kernel flag
+        waits observe the local stop word and abort cleanly)."""
+        self.block.request_stop()
+
+    def restore_progress(self, k: int, clock: Optional[int] = None, rounds: Optional[Sequence[int]] = None) -> None:
+        """Checkpoint resume: restore the accepted-update counter / logical clock of the server and the per-worker round
+        counters, so the step-size schedule (gamma/sqrt(floor(k/P)+1), rsqrt(round+1)) and the seed+round+1 sampling
+        sequence continue where the checkpoint left off."""
+        if self.rank == 0 and self.is_async:
+            self.block.set_progress(int(k), int(k if clock is None else clock))
+        for i, rk in enumerate(self.kernels):
+            r = int(rounds[i]) if rounds is not None else (int(k) // max(self.P, 1) if self.is_async else int(k))
+            if rk.sim:
+                a = rk.wctl.numpy().view(WORKER_CTL_DTYPE)
+                a["round"] = r
+                a["rounds_done"] = r
+            else:
+                rk.restore_progress(r)
+            rk.rounds_launched = r
+        self.rounds_enqueued = max((rk.rounds_launched for rk in self.kernels), default=0)
 
     # ------------------------------------------------------------------ state
     def weights(self) -> torch.Tensor:

@@ -116,7 +116,7 @@ def save_engine_checkpoint(engine, cfg, k: int, writer: Optional[AsyncCheckpoint
     if writer is None:
         hist = {wid: rk.hist for rk, wid in zip(engine.kernels, engine.local_worker_ids) if rk.hist is not None}
         save_checkpoint(path, w=engine.weights(), k=k, clock=st["clock"], alpha_bar=engine.alpha_bar(), history=hist,
-                        config=cfg.to_dict(), extra={"world": world})
+                        config=cfg.to_dict(), extra={"world": world, "rounds": [int(rk.rounds_launched) for rk in engine.kernels]})
         publish_latest()
         return path
     from ..parallel import _devapi as _dev
@@ -134,7 +134,7 @@ def save_engine_checkpoint(engine, cfg, k: int, writer: Optional[AsyncCheckpoint
     done = _dev.new_event(engine.device)
     done.record(cur)
     writer.submit(done, after=publish_latest, path=path, w=w, k=k, clock=st["clock"], alpha_bar=ab, history=hist,
-                  config=cfg.to_dict(), extra={"world": world})
+                  config=cfg.to_dict(), extra={"world": world, "rounds": [int(rk.rounds_launched) for rk in engine.kernels]})
     return path
 
 

@@ -59,21 +59,38 @@ class HeartbeatWatchdog:
 
 class DeviceWatchdog:
     """Same policy for the fused backend: polls the device-side status table of the server block
-    (heartbeat_ns is a globaltimer stamp; compared against the newest stamp seen)."""
+    (heartbeat_ns is a globaltimer stamp; compared against the newest stamp seen) — and ACTS on what it finds:
 
-    def __init__(self, engine, timeout_s: float = 30.0):
+    * asynchronous modes: ``engine.declare_dead(p)`` marks the worker dead on the server (``alive = 0``), removes it from the
+      idle count / enable mask and lowers the bucket threshold to ``floor(P_alive * beta)``: the run continues with P-1
+      workers and still reaches its target k (SURVEY §5.3; HeartbeatReceiver.scala:193-220 is the Spark side);
+    * synchronous modes: ``engine.request_stop_local()`` — the in-kernel BSP flag waits observe the stop word and the round
+      kernels exit with the abort flag set, so the driver raises instead of hanging on the dead peer's flag forever.
+
+    ``expect_running=True`` (a run is in progress) also treats an IDLE worker with a stale heartbeat as dead: with persistent
+    round kernels a live worker is busy almost all the time, so "idle and silent while the others advance" means its process
+    is gone."""
+
+    def __init__(self, engine, timeout_s: float = 30.0, act: bool = True):
         self.engine = engine
         self.timeout_ns = int(timeout_s * 1e9)
         self.dead: List[int] = []
+        self.act = act
 
-    def check_once(self) -> List[int]:
+    def check_once(self, expect_running: bool = False) -> List[int]:
         st = self.engine.worker_status()
         newest = int(st["heartbeat_ns"].max())
         newly = []
         for p in range(len(st)):
             busy = int(st[p]["available"]) == 0
             hb = int(st[p]["heartbeat_ns"])
-            if busy and hb and newest - hb > self.timeout_ns and p not in self.dead:
+            if (busy or expect_running) and hb and newest - hb > self.timeout_ns and p not in self.dead:
                 self.dead.append(p)
                 newly.append(p)
+        if self.act and newly:
+            if getattr(self.engine, "is_async", True):
+                for p in newly:
+                    self.engine.declare_dead(p)
+            else:
+                self.engine.request_stop_local()
         return newly

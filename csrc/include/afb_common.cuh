@@ -100,6 +100,17 @@ AFB_DEVINL void red_add_release_sys_s32(int* p, int v) {
 AFB_DEVINL void red_add_release_sys_u32(unsigned int* p, unsigned int v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// NVLS multicast (NVSwitch replicates the store into every GPU bound to the multicast object; one store, P destinations)
+AFB_DEVINL void multimem_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+AFB_DEVINL void multimem_st_release_u32(unsigned int* mc, unsigned int v) {
+  asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+AFB_DEVINL void multimem_red_add_u32(unsigned int* mc, unsigned int v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
 AFB_DEVINL void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 AFB_DEVINL void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
@@ -108,6 +119,22 @@ AFB_DEVINL unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Bounded spinning: every in-kernel wait (round barrier, pull flag, clock ticket, BSP arrival flags, bucket gate) gives
+// up after `limit_ns` so that a protocol bug or a dead peer ends the kernel instead of hanging the GPU.  The caller
+// raises WorkerCtl.abort; the host checks it after synchronising and treats the engine as failed.
+struct SpinGuard {
+  unsigned long long t0;
+  unsigned int n;
+  AFB_DEVINL SpinGuard() : t0(0), n(0) {}
+  AFB_DEVINL bool expired(unsigned long long limit_ns) {
+    if ((++n & 63u) != 0u) return false;               // look at the clock every 64 polls
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) { t0 = now; return false; }
+    return limit_ns != 0 && now - t0 > limit_ns;
+  }
+};
+
 AFB_DEVINL void sleep_ns(unsigned long long ns) {
   unsigned long long t0 = globaltimer_ns();
   while (globaltimer_ns() - t0 < ns) __nanosleep(ns > 100000ULL ? 20000u : 1000u);
@@ -199,6 +226,10 @@ struct alignas(16) ServerCtl {
   unsigned int cul_count;
   unsigned int pad;
   unsigned long long avg_delay_ns; // calibrated average task time (0 until warm-up done)
+  // ---- runtime-adjustable gating (written by the host: watchdog / async_barrier bridge) ------------------------------
+  int gate_dyn;                    // > 0: overrides the launch-time bucket threshold when smaller (continue with P-1 workers)
+  int num_alive;                   // workers not declared dead by the watchdog (informational)
+  unsigned long long enable_mask[4];  // bit q = worker q may start a round (ASYNCbarrier predicate evaluated by the host); P <= 256
 };
 
 }  // namespace afb

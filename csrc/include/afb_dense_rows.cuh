@@ -40,11 +40,13 @@ struct RowScheduler {
   int n_big;                // number of 64-row chunks
   int num_chunks;           // total chunks (big + small)
   unsigned int static_chunks;
+  unsigned int thr24;       // Bernoulli threshold of this round (launch scalar or the round descriptor's)
 };
 
 constexpr int kSmallChunkRows = 16;
 
-AFB_DEVINL void sched_init(RowScheduler& s, int n_rows, unsigned int total_warps, unsigned int gwarp) {
+AFB_DEVINL void sched_init(RowScheduler& s, int n_rows, unsigned int total_warps, unsigned int gwarp, int thr24 = -1) {
+  s.thr24 = static_cast<unsigned int>(thr24);      // callers pass eff_thr24(p, round); -1 = "use p.thr24" (set below by load_chunk_masks)
   // small-chunk region: ~2 small chunks per warp at the very end of the shard (never more than 1/4 of it)
   long long small_rows = static_cast<long long>(total_warps) * 2 * kSmallChunkRows;
   if (small_rows > n_rows / 4) small_rows = n_rows / 4;
@@ -70,13 +72,14 @@ AFB_DEVINL void load_chunk_masks(RowScheduler& s, const RoundParams& p, unsigned
   else { s.base = s.n_big * kChunkRows + (static_cast<int>(chunk) - s.n_big) * kSmallChunkRows; size = kSmallChunkRows; }
   int r0 = s.base + lane, r1 = s.base + 32 + lane;
   bool s0 = false, s1 = false;
+  const unsigned int thr = (s.thr24 == 0xffffffffu) ? static_cast<unsigned int>(p.thr24) : s.thr24;
   if (lane < size && r0 < p.n_rows) {
     unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r0]) : static_cast<unsigned long long>(p.row_base + r0);
-    s0 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
+    s0 = hash_u24(key, g) < thr;
   }
   if (32 + lane < size && r1 < p.n_rows) {
     unsigned long long g = p.gidx ? static_cast<unsigned long long>(p.gidx[r1]) : static_cast<unsigned long long>(p.row_base + r1);
-    s1 = hash_u24(key, g) < static_cast<unsigned int>(p.thr24);
+    s1 = hash_u24(key, g) < thr;
   }
   s.m0 = __ballot_sync(0xffffffffu, s0);
   s.m1 = __ballot_sync(0xffffffffu, s1);

@@ -54,7 +54,43 @@ struct alignas(16) WorkerCtl {      // worker-local control block (device memory
   unsigned int tk_clock_old;
   long long tk_staleness;
   long long tk_k_after;
+  // ---- robustness -----------------------------------------------------------------------------------------------------
+  int abort;                        // != 0: a bounded spin expired (SpinGuard) — results of this launch are invalid
+  unsigned int skipped_rounds;      // rounds this worker sat out because its enable-mask bit was clear (ASYNCbarrier)
+  unsigned long long pad_tail;
 };
+
+// Per-round descriptor of the end-to-end path (FusedEngine.step): written on the host into pinned memory, copied H2D
+// every step, consumed by the round kernel (slot = round % desc_slots).  `seq` = round + 1 marks the slot valid.
+struct alignas(16) RoundDesc {
+  float gamma;                      // step size of this round
+  int thr24;                        // Bernoulli threshold (batch rate) of this round
+  float delay_coeff;                // controlled-delay intensity of this round
+  unsigned int seq;
+};
+
+// Double-buffered per-round state of the PIPELINED persistent rounds (dense_stream.cu): round r uses b[r & 1], so round
+// r+1's pull and gradient can run while round r's NVLink tail is still in flight.
+struct alignas(16) PipeBuf {
+  unsigned int chunk_ctr;
+  unsigned int done_ctas;
+  unsigned int pull_ticket;
+  unsigned int pull_flag;            // == round+1 once w / ts / proceed of this buffer are valid
+  int proceed;
+  unsigned int batch_count;
+  float loss_sum;
+  unsigned int tk_flag;              // == round+1 once the early clock ticket is valid
+  unsigned long long ts;
+  unsigned long long k_read;
+  unsigned long long t_start_ns;
+  long long tk_staleness;
+  long long tk_k_after;
+  int tk_accept;
+  float tk_step;
+  unsigned int tk_clock_old;
+  unsigned int pad;
+};
+struct PipeState { PipeBuf b[2]; };
 
 struct alignas(16) SyncPeers {      // BSP all-gather wiring (device array, one per worker)
   float* gstage[16];                // gstage[q] = peer q's staging buffer [2][P][ld+4] (double-buffered by round parity)
@@ -110,6 +146,37 @@ struct RoundParams {
   int loss_id;                      // afb::LossId
   int round_host;                   // PDL: the round index counted by the host (== wctl->round at kernel start)
   int pdl;                          // 1: launched with programmatic stream serialization (see dense_round.cu)
+  // ---- regularisation (K8 fused into the apply; Updater.scala:114-158) --------------------------------------------------
+  float reg_param;                  // lambda
+  int reg_type;                     // 0 none, 1 squared-L2 (w <- (1 - eta*lambda) w - eta g), 2 L1 (soft threshold by eta*lambda)
+  // ---- gating beyond the bucket rule (ASYNCbarrier on the device; RDD.scala:1050-1064, workerState.scala:74-82) ---------
+  int ssp_bound;                    // >= 0: start a round only while max_q staleness(q) <= bound (SSP); < 0: off
+  int use_mask;                     // 1: honour ServerCtl.enable_mask (host-evaluated predicate): a masked worker skips the round
+  // ---- end-to-end descriptor ring --------------------------------------------------------------------------------------
+  const RoundDesc* desc;            // null: scalars above are used; else slot (round % desc_slots) overrides gamma / thr24 / delay_coeff
+  int desc_slots;
+  int pull_ahead_chunks;            // pipelined rounds: pull round r+1's parameters when this many chunks of round r remain
+  unsigned long long spin_limit_ns; // bound of every in-kernel spin (0 = unbounded)
 };
+
+// The descriptor of `round`, or null when the ring holds none for it (slot not written / already reused): the launch
+// scalars apply then, so rounds enqueued without a fresh descriptor (run_rounds) simply ignore the ring.
+AFB_DEVINL const RoundDesc* round_desc(const RoundParams& p, unsigned int round) {
+  if (p.desc == nullptr) return nullptr;
+  const RoundDesc* d = p.desc + (round % static_cast<unsigned int>(p.desc_slots));
+  return (*reinterpret_cast<const volatile unsigned int*>(&d->seq) == round + 1u) ? d : nullptr;
+}
+AFB_DEVINL int eff_thr24(const RoundParams& p, unsigned int round) {
+  const RoundDesc* d = round_desc(p, round);
+  return d ? *reinterpret_cast<const volatile int*>(&d->thr24) : p.thr24;
+}
+AFB_DEVINL float eff_gamma(const RoundParams& p, unsigned int round) {
+  const RoundDesc* d = round_desc(p, round);
+  return d ? *reinterpret_cast<const volatile float*>(&d->gamma) : p.gamma;
+}
+AFB_DEVINL float eff_delay_coeff(const RoundParams& p, unsigned int round) {
+  const RoundDesc* d = round_desc(p, round);
+  return d ? *reinterpret_cast<const volatile float*>(&d->delay_coeff) : p.delay_coeff;
+}
 
 }  // namespace afb

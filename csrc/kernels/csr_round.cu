@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kCsrThreads, 2) csr_round_kernel(const RoundPa
   const bool saga = (p.hist != nullptr);
 
   if (p.algo != ALGO_GRAD_ONLY) {
-    if (!round_begin<kCsrThreads>(p, sh, round)) return;
+    if (round_begin<kCsrThreads>(p, sh, round) != PROCEED_RUN) return;
   }
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
   const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)

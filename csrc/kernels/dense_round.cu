@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, (kThreads == 256 && NV4 <= 8) ? 2 : 
   }
 
   // ------------------------------------------------------------------ phase 0b: w_local / ts / seed published
-  if (!round_begin_complete<kThreads>(p, sh, round, pl)) return;
+  if (round_begin_complete<kThreads>(p, sh, round, pl) != PROCEED_RUN) return;
 
   // ------------------------------------------------------------------ phase 1: fused gradient
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) dense_round_pipe_kernel(const
     tc::fence_barrier_init();
   }
   if (p.algo != ALGO_GRAD_ONLY) {
-    if (!round_begin<kPipeThreads>(p, sh, round)) return;       // contains __syncthreads(): barrier init is visible after it
+    if (round_begin<kPipeThreads>(p, sh, round) != PROCEED_RUN) return;       // contains __syncthreads(): barrier init is visible after it
   }
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;   // split round that was stopped at the gate
   const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) dense_round_ring_kernel(const
     tc::fence_barrier_init();
   }
   if (p.algo != ALGO_GRAD_ONLY) {
-    if (!round_begin<kRingThreads>(p, sh, round)) return;
+    if (round_begin<kRingThreads>(p, sh, round) != PROCEED_RUN) return;
   }
   if (p.seed_mode == 3 && !*reinterpret_cast<volatile int*>(&wc->proceed)) return;
   const unsigned long long key = (p.algo == ALGO_GRAD_ONLY && p.seed_mode != 3)

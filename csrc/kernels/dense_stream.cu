@@ -1,0 +1,739 @@
+// The default dense round kernel (sm_100a): a PERSISTENT worker loop whose row traffic moves with TMA bulk copies.
+//
+//   one launch  = `rounds` consecutive rounds of one logical worker (the executor task loop of the reference,
+//                 core/executor/Executor.scala:290-560, without a host in it: every piece of per-round protocol state lives in
+//                 device memory, rounds are separated by flags, not by kernel boundaries);
+//   one round   = pull(w) -> Bernoulli sample -> x.w -> loss coefficient -> g += c.x -> (SAGA history) -> CTA/grid reduce
+//                 -> logical-clock ticket -> Hogwild push-and-apply over NVLink (or the BSP all-gather + replicated apply).
+//
+// Data path (K1-K4, K7, K11): every warp owns a private ring of kDepth shared-memory stages and keeps kDepth sampled rows
+// in flight with `cp.async.bulk.shared::cluster.global` (SASS: UBLKCP) completing on per-stage mbarriers (SYNCS); lane 0
+// issues, all lanes consume with LDS.128.  The parameter vector lives in registers (the pull lands once per round), so a
+// row costs one TMA write + one LDS read of shared-memory bandwidth and zero registers while it is in flight: 100 KB of rows
+// are in flight per CTA at kDepth = 4, ld = 784, independent of register pressure.  The CTA-level gradient reduce reuses
+// the (then idle) ring stages: warps dump their register accumulators, one pass sums the 8 slices, `red.global.add.v4`
+// merges into the worker's g — no shared-memory atomics (sm_100a has no native fp32 shared atomic add: ATOMS.CAST.SPIN).
+//
+// Two round loops share that data path:
+//   * serial rounds (template PIPE = false): the protocol of afb_round_impl.cuh, round r+1 starts when round r is
+//     published; the sampling hash of the first chunk and the first kDepth row fetches are issued BEFORE that wait, so
+//     they overlap the previous round's NVLink tail.  Every algorithm / gate / delay / regulariser.
+//   * pipelined rounds (PIPE = true; ASGD without a bucket/SSP gate): per-round state double-buffered by round parity
+//     (PipeState); the last CTA to finish round r runs its NVLink tail (ticket -> red.add -> fence -> publish) while every
+//     other CTA is already streaming round r+1, and the parameters of round r+1 are pulled AHEAD — by the warp that draws
+//     one of the last `pull_ahead_chunks` chunk ids of round r — so no CTA ever waits for an NVLink round trip.  The
+//     worker computes round r+1 without its own round-r update (one own update in flight; the logical clock does not
+//     count it), which is within the asynchronous model's semantics (staleness is measured on the server's clock).
+#include <algorithm>
+#include "afb_dense_rows.cuh"
+#include "afb_tc.cuh"
+
+namespace afb {
+
+constexpr int kStreamWarps = 8;
+constexpr int kStreamThreads = 32 * kStreamWarps;
+constexpr int kStreamMetaBytes = 32;       // {float y[4]; float pad[4]} — the 16-byte quad of labels around the row
+
+AFB_DEVINL void stream_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+struct WarpRing {
+  uint8_t* base;            // this warp's kDepth stages
+  uint64_t* bars;           // this warp's kDepth mbarriers
+  uint32_t row_bytes;
+  uint32_t stage_bytes;
+};
+
+// lane 0 arms the stage barrier and launches the bulk copies of one row (+ its label quad)
+AFB_DEVINL void ring_issue(const WarpRing& rg, const RoundParams& p, const int row, const int slot, const int lane) {
+  if (lane == 0) {
+    uint8_t* st = rg.base + static_cast<size_t>(slot) * rg.stage_bytes;
+    float* meta = reinterpret_cast<float*>(st + rg.row_bytes);
+    const bool quad_ok = (row | 3) < p.n_rows;
+    if (!quad_ok) meta[row & 3] = __ldg(p.y + row);
+    tc::mbar_arrive_expect_tx(&rg.bars[slot], rg.row_bytes + (quad_ok ? 16u : 0u));
+    stream_bulk_g2s(st, reinterpret_cast<const uint8_t*>(p.X) + static_cast<long long>(row) * rg.row_bytes, rg.row_bytes, &rg.bars[slot]);
+    if (quad_ok) stream_bulk_g2s(meta, p.y + (row & ~3), 16u, &rg.bars[slot]);
+  }
+}
+
+AFB_DEVINL int pop_mask_row(RowScheduler& s) {
+  if (s.m0) { int b = __ffs(s.m0) - 1; s.m0 &= s.m0 - 1; return s.base + b; }
+  if (s.m1) { int b = __ffs(s.m1) - 1; s.m1 &= s.m1 - 1; return s.base + 32 + b; }
+  return -1;
+}
+
+// A row is consumed in 16-byte chunks: lane l owns chunks {l + 32 c}.  fp32 rows: 4 elements per chunk; bf16 rows
+// (row STORAGE only — labels, parameters, gradient and all arithmetic stay fp32): 8 elements per chunk, half the HBM bytes.
+template <bool BF16> struct RowElems { static constexpr int kE = BF16 ? 8 : 4; };
+
+template <bool BF16>
+AFB_DEVINL void unpack_chunk(const uint4 raw, float (&x)[RowElems<BF16>::kE]) {
+  if constexpr (BF16) {
+    x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xffff0000u);
+    x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xffff0000u);
+    x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xffff0000u);
+    x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xffff0000u);
+  } else {
+    x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y); x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
+  }
+}
+
+// Per-warp streaming state of one round.
+template <int NV, int kDepth, bool BF16>
+struct RowStream {
+  static constexpr int kE = RowElems<BF16>::kE;
+  RowScheduler sch;
+  int rows_q[kDepth];
+  float hq[kDepth];         // SAGA: history scalar of the row in each stage (plain load at issue time, consumed kDepth rows later)
+  float acc[NV][kE];
+  float loss_acc;
+  unsigned int cnt;
+};
+
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL void stream_reset(RowStream<NV, kDepth, BF16>& rs, const RoundParams& p, const int thr24) {
+#pragma unroll
+  for (int c = 0; c < NV; ++c)
+#pragma unroll
+    for (int j = 0; j < RowElems<BF16>::kE; ++j) rs.acc[c][j] = 0.f;
+#pragma unroll
+  for (int s = 0; s < kDepth; ++s) { rs.rows_q[s] = -1; rs.hq[s] = 0.f; }
+  rs.loss_acc = 0.f;
+  rs.cnt = 0;
+  sched_init(rs.sch, p.n_rows, gridDim.x * kStreamWarps, blockIdx.x * kStreamWarps + (threadIdx.x >> 5), thr24);
+}
+
+// Prologue on immutable inputs only (X, y, gidx): hash the statically assigned first chunk, put up to kDepth row fetches
+// in flight.  No atomics, no protocol state: legal before the round barrier / the pull.
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL void stream_prologue(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, const RoundParams& p, const unsigned long long key, const int lane) {
+  const unsigned int c0 = rs.sch.next_chunk;
+  rs.sch.next_chunk = 0xffffffffu;                 // "first dynamic chunk id not fetched yet"
+  if (c0 < static_cast<unsigned int>(rs.sch.num_chunks)) {
+    load_chunk_masks(rs.sch, p, c0, lane, key);
+#pragma unroll
+    for (int s = 0; s < kDepth; ++s) {
+      const int r = pop_mask_row(rs.sch);
+      rs.rows_q[s] = r;
+      if (r >= 0) ring_issue(rg, p, r, s, lane);
+    }
+  }
+}
+
+// The gradient phase of one round: fill the ring, then consume rows until the chunk pool is empty.
+// `saga`: history correction + write-through history update (K4/K7).  `on_tick(next_chunk)` is called once per consumed row
+// with the id of the chunk the warp will draw next (the pipelined loop hangs its pull-ahead on it).
+template <int NV, int kDepth, bool BF16, typename Tick>
+AFB_DEVINL void stream_rows(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, const RoundParams& p, unsigned int* chunk_ctr,
+                            const unsigned long long key, const float (&wreg)[NV][RowElems<BF16>::kE], unsigned int& phase,
+                            const bool prologue_done, const bool saga, const int lane, Tick&& on_tick) {
+  constexpr int kE = RowElems<BF16>::kE;
+  const int nchunks = static_cast<int>(p.ld) / kE;
+  const int LOSS = p.loss_id;
+  if (prologue_done) rs.sch.next_chunk = fetch_chunk(chunk_ctr, lane, rs.sch.static_chunks);
+#pragma unroll
+  for (int s = 0; s < kDepth; ++s) {
+    if (rs.rows_q[s] < 0) {
+      const int r = next_row(rs.sch, p, chunk_ctr, lane, key);
+      rs.rows_q[s] = r;
+      if (r >= 0) ring_issue(rg, p, r, s, lane);
+    }
+    if (saga && rs.rows_q[s] >= 0) rs.hq[s] = p.hist[rs.rows_q[s]];
+  }
+  while (true) {
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < kDepth; ++s) {
+      const int row = rs.rows_q[s];
+      if (row < 0) continue;
+      any = true;
+      on_tick(rs.sch.next_chunk);
+      tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u);
+      phase ^= (1u << s);
+      const uint8_t* st = rg.base + static_cast<size_t>(s) * rg.stage_bytes;
+      const float yy = reinterpret_cast<const float*>(st + rg.row_bytes)[row & 3];
+      const float hh = rs.hq[s];
+      uint4 raw[NV];
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const int v = lane + 32 * c;
+        raw[c] = (v < nchunks) ? *reinterpret_cast<const uint4*>(st + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      __syncwarp();                                           // every lane has read the stage: refill it
+      const int nrow = next_row(rs.sch, p, chunk_ctr, lane, key);
+      rs.rows_q[s] = nrow;
+      if (nrow >= 0) {
+        ring_issue(rg, p, nrow, s, lane);
+        if (saga) rs.hq[s] = p.hist[nrow];
+      }
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {                          // K1
+        float x[kE];
+        unpack_chunk<BF16>(raw[c], x);
+        d0 = fmaf(x[0], wreg[c][0], d0);
+        d1 = fmaf(x[1], wreg[c][1], d1);
+        d2 = fmaf(x[2], wreg[c][2], d2);
+        d3 = fmaf(x[3], wreg[c][3], d3);
+        if constexpr (BF16) {
+          d0 = fmaf(x[4], wreg[c][4], d0);
+          d1 = fmaf(x[5], wreg[c][5], d1);
+          d2 = fmaf(x[6], wreg[c][6], d2);
+          d3 = fmaf(x[7], wreg[c][7], d3);
+        }
+      }
+      const float margin = warp_sum((d0 + d1) + (d2 + d3));
+      float coeff, loss;
+      loss_coeff_rt(LOSS, margin, yy, coeff, loss);           // K2
+      float eff = coeff;
+      if (saga) {                                             // K4 + K7 (write-through: rollback rounds use dense_round.cu)
+        eff = coeff - hh;
+        if (lane == 0) p.hist[row] = coeff;
+      }
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {                          // K3
+        float x[kE];
+        unpack_chunk<BF16>(raw[c], x);
+#pragma unroll
+        for (int j = 0; j < kE; ++j) rs.acc[c][j] = fmaf(eff, x[j], rs.acc[c][j]);
+      }
+      rs.loss_acc += loss;
+      ++rs.cnt;
+    }
+    if (!any) break;
+  }
+}
+
+// CTA-level reduce of the per-warp register accumulators through the (idle) ring stages, merged into `g_dst` with vector
+// L2 reductions.  Contains two CTA barriers; on return the ring may be refilled.
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL void stream_reduce(const RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, uint8_t* s_raw, const RoundParams& p,
+                              float* g_dst, const int lane) {
+  constexpr int kE = RowElems<BF16>::kE;
+  const int nchunks = static_cast<int>(p.ld) / kE;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  float* mine = reinterpret_cast<float*>(rg.base);      // ld fp32 fit: kDepth * stage_bytes >= 2 * (2 ld + 32) >= 4 ld
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + 32 * c;
+    if (v < nchunks) {
+      *reinterpret_cast<float4*>(mine + kE * v) = make_float4(rs.acc[c][0], rs.acc[c][1], rs.acc[c][2], rs.acc[c][3]);
+      if constexpr (BF16)
+        *reinterpret_cast<float4*>(mine + kE * v + 4) = make_float4(rs.acc[c][4], rs.acc[c][5], rs.acc[c][6], rs.acc[c][7]);
+    }
+  }
+  __syncthreads();
+  const size_t warp_stride = static_cast<size_t>(kDepth) * rg.stage_bytes;
+  for (int v = threadIdx.x; v < nvec; v += kStreamThreads) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kStreamWarps; ++w) {
+      const float4 a = reinterpret_cast<const float4*>(s_raw + w * warp_stride)[v];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    red_add_gpu_f32x4(g_dst + 4 * v, t);
+  }
+  __syncthreads();
+  if (lane == 0) tc::fence_proxy_async();           // generic-proxy accesses to the stages are ordered before the next bulk copies
+}
+
+template <int NV, bool BF16>
+AFB_DEVINL void load_w_regs(float (&wreg)[NV][RowElems<BF16>::kE], const float* w, const int nchunks, const int lane) {
+  constexpr int kE = RowElems<BF16>::kE;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + 32 * c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (v < nchunks) {
+      a = __ldcg(reinterpret_cast<const float4*>(w + kE * v));
+      if constexpr (BF16) b = __ldcg(reinterpret_cast<const float4*>(w + kE * v + 4));
+    }
+    wreg[c][0] = a.x; wreg[c][1] = a.y; wreg[c][2] = a.z; wreg[c][3] = a.w;
+    if constexpr (BF16) { wreg[c][4] = b.x; wreg[c][5] = b.y; wreg[c][6] = b.z; wreg[c][7] = b.w; }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// serial persistent round (protocol of afb_round_impl.cuh)
+// ----------------------------------------------------------------------------------------------------------------------
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL int stream_round_serial(const RoundParams& p, RoundShared<kStreamThreads>& sh, uint8_t* s_raw, const WarpRing& rg,
+                                   unsigned int& phase, const unsigned int round, const bool wait) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int nchunks = static_cast<int>(p.ld) / RowElems<BF16>::kE;
+  WorkerCtl* wc = p.wctl;
+  const bool saga = (p.hist != nullptr);
+  RowStream<NV, kDepth, BF16> rs;
+  stream_reset(rs, p, eff_thr24(p, round));
+  // sampling key known without the server's k?  (seed_mode 1: seed + round + 1; 2 / grad-only: fixed seed)
+  const bool key_early = (p.algo == ALGO_GRAD_ONLY) ? (p.seed_mode != 3) : (p.seed_mode == 1 || p.seed_mode == 2);
+  unsigned long long key = 0;
+  bool prologue = false;
+  if (key_early) {
+    unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
+    if (p.algo != ALGO_GRAD_ONLY && p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+    key = mix64(seed_eff);
+    // SAGA reads the mutable history at issue time: not before the previous round of this launch is complete
+    if (!(saga && wait)) { stream_prologue(rs, rg, p, key, lane); prologue = true; }
+  }
+  if (wait) {                                       // round barrier: the previous round (tail included) is published
+    if (tid == 0) {
+      SpinGuard sg;
+      while (ld_acquire_gpu_u32(&wc->round) != round) {
+        __nanosleep(20);
+        if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+      }
+    }
+    if (cta_abort_vote<kStreamThreads>(sh, wc)) {
+#pragma unroll
+      for (int s = 0; s < kDepth; ++s)
+        if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+      return PROCEED_STOP;
+    }
+  }
+  RoundPull pl;
+  round_begin_issue<kStreamThreads>(p, sh, round, pl);
+  const int pr = round_begin_complete<kStreamThreads>(p, sh, round, pl);
+  if (pr != PROCEED_RUN) {
+    // rows put in flight by the prologue must land before the stages are reused (or the CTA exits)
+#pragma unroll
+    for (int s = 0; s < kDepth; ++s)
+      if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+    return pr;
+  }
+  if (!key_early) key = *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
+  float wreg[NV][RowElems<BF16>::kE];
+  load_w_regs<NV, BF16>(wreg, p.w_local, nchunks, lane);
+  stream_rows<NV, kDepth, BF16>(rs, rg, p, &wc->chunk_ctr, key, wreg, phase, prologue, saga, lane, [](unsigned int) {});
+  stream_reduce<NV, kDepth, BF16>(rs, rg, s_raw, p, p.g_local, lane);
+  round_finish<kStreamThreads>(p, sh, round, rs.loss_acc, rs.cnt);
+  return PROCEED_RUN;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// pipelined persistent round (ASGD; per-round state double-buffered by parity)
+// ----------------------------------------------------------------------------------------------------------------------
+// The pull of one round, executed by ONE warp that holds ticket 0 of the round's buffer: a single NVLink round trip brings
+// the logical clock and all of w; `first` marks the first round of the launch (the worker becomes busy).
+template <int NV4>
+AFB_DEVINL void pipe_pull_warp(const RoundParams& p, PipeBuf* S, float* w_loc, const unsigned int round, const bool first, const int lane) {
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  float4 wv[NV4];
+  unsigned long long ck = 0;
+  if (lane == 0) wc->dbg_ns[0] = globaltimer_ns();
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    const int v = lane + 32 * c;
+    wv[c] = (v < nvec) ? ld_relaxed_sys_f32x4(p.w_server + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);      // K10
+  }
+  if (lane == 0) ck = ld_acquire_sys_u64(&p.sctl->clock_k);
+#pragma unroll
+  for (int c = 0; c < NV4; ++c) {
+    const int v = lane + 32 * c;
+    if (v < nvec) __stcg(reinterpret_cast<float4*>(w_loc + 4 * v), wv[c]);
+  }
+  if (lane == 0) {
+    int proceed = 1;
+    if (static_cast<long long>(ck >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop) || aborted(wc)) proceed = 0;
+    const unsigned long long now = globaltimer_ns();
+    WorkerSlot* me = p.status + p.worker_id;
+    if (proceed && first) {
+      red_add_release_sys_s32(&p.sctl->avail_count, -1);        // busy for the whole persistent launch
+      if (wc->last_finish_ns) wc->wait_ns += now - wc->last_finish_ns;
+      me->available = 0;
+      me->busy_since_ns = now;
+      me->wait_ns = wc->wait_ns;
+    }
+    if (proceed) me->heartbeat_ns = now;
+    S->ts = ck & 0xffffffffULL;
+    S->k_read = ck >> 32;
+    S->proceed = proceed;
+    S->t_start_ns = now;
+    wc->dbg_ns[2] = now;
+    if (proceed && p.delay_mode != 0) {
+      // A18 straggler injector: sleep a multiple of the calibrated mean task time before the round may start
+      const unsigned long long avg = ld_acquire_sys_u64(&p.sctl->avg_delay_ns);
+      if (avg) {
+        float mult = eff_delay_coeff(p, round);
+        if (p.delay_mode >= 2) {
+          unsigned long long seed_eff = static_cast<unsigned long long>(p.seed) + static_cast<unsigned long long>(round) + 1ULL;
+          float u = static_cast<float>(hash_u24(mix64(seed_eff) ^ 0xD1B54A32D192ED03ULL, p.worker_id)) * (1.f / 16777216.f);
+          mult = (p.delay_mode == 3) ? (2.5f + 7.5f * u) : (1.5f + u);
+        }
+        sleep_ns(static_cast<unsigned long long>(mult * static_cast<float>(avg)));
+      }
+    }
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) st_release_gpu_u32(&S->pull_flag, round + 1u);
+}
+
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThreads>& sh, uint8_t* s_raw, const WarpRing& rg,
+                                 unsigned int& phase, const unsigned int round, const int it, const int rounds,
+                                 PipeState* ps, float* g2, float* w2) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  WorkerCtl* wc = p.wctl;
+  PipeBuf* S = &ps->b[round & 1u];
+  PipeBuf* Sn = &ps->b[(round + 1u) & 1u];
+  float* g_loc = g2 + static_cast<long long>(round & 1u) * p.ld;
+  float* w_loc = w2 + static_cast<long long>(round & 1u) * p.ld;
+  float* w_nxt = w2 + static_cast<long long>((round + 1u) & 1u) * p.ld;
+
+  constexpr int NVW = BF16 ? 2 * NV : NV;             // float4's of w per lane (the pull is always fp32)
+  const int nchunks = static_cast<int>(p.ld) / RowElems<BF16>::kE;
+  RowStream<NV, kDepth, BF16> rs;
+  stream_reset(rs, p, eff_thr24(p, round));
+  // ---- prologue on immutable inputs: sampling key of this round, first (static) chunk, first row fetches
+  unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
+  if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
+  const unsigned long long key = mix64(seed_eff);
+  stream_prologue(rs, rg, p, key, lane);
+  // ---- buffer reuse: round r-2 (same parity) must be published before anything of buffer r&1 is touched
+  if (it >= 2) {
+    if (tid == 0) {
+      SpinGuard sg;
+      while (static_cast<int>(ld_acquire_gpu_u32(&wc->round) - (round - 1u)) < 0) {
+        __nanosleep(20);
+        if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- puller election (ticket 0 may already have been taken by the previous round's pull-ahead)
+  if (tid == 0) sh.flag = atomicAdd(&S->pull_ticket, 1u);
+  __syncthreads();
+  const bool puller = (sh.flag == 0);
+  __syncthreads();                                   // sh.flag is reused by the finish sequence
+  if (puller) {
+    if (warp == 0) pipe_pull_warp<NVW>(p, S, w_loc, round, it == 0, lane);
+  }
+  // ---- wait for the pull; the decision is made CTA-uniform through shared memory
+  if (tid == 0) {
+    SpinGuard sg;
+    while (ld_acquire_gpu_u32(&S->pull_flag) != round + 1u) {
+      __nanosleep(32);
+      if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+    }
+    sh.flag = (*reinterpret_cast<volatile int*>(&S->proceed) != 0 && !aborted(wc)) ? 1u : 0u;
+  }
+  __syncthreads();
+  const int proceed = static_cast<int>(sh.flag);
+  if (!proceed) {
+    // stopped (k >= max_iters, stop flag or abort): drain the prologue's copies, then the last CTA to arrive resets the
+    // buffer and publishes, in round order
+#pragma unroll
+    for (int s = 0; s < kDepth; ++s)
+      if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(&S->done_ctas, 1u);
+      if (t == gridDim.x - 1) {
+        SpinGuard sg;
+        while (ld_acquire_gpu_u32(&wc->round) != round) {                    // the previous round's tail first
+          __nanosleep(20);
+          if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+        }
+        S->done_ctas = 0; S->pull_ticket = 0; S->chunk_ctr = 0;
+        if (it > 0) {                                                        // this launch had made the worker busy
+          (p.status + p.worker_id)->available = 1;
+          fence_sys();
+          red_add_release_sys_s32(&p.sctl->avail_count, 1);
+        }
+        wc->last_accepted = -1;
+        __threadfence();
+        st_release_gpu_u32(&wc->round, round + 1u);
+      }
+    }
+    return PROCEED_STOP;
+  }
+
+  // ---- phase 1: fused gradient; the warp that draws one of the last chunk ids pulls round r+1's parameters ahead
+  float wreg[NV][RowElems<BF16>::kE];
+  load_w_regs<NV, BF16>(wreg, w_loc, nchunks, lane);
+  const unsigned int dyn_chunks = rs.sch.num_chunks > static_cast<int>(rs.sch.static_chunks)
+                                      ? static_cast<unsigned int>(rs.sch.num_chunks) - rs.sch.static_chunks : 0u;
+  const unsigned int ahead = static_cast<unsigned int>(p.pull_ahead_chunks);
+  const unsigned int trigger = rs.sch.static_chunks + (dyn_chunks > ahead ? dyn_chunks - ahead : 0u);
+  bool ahead_armed = (p.pull_ahead_chunks > 0) && (it + 1 < rounds) && (p.delay_mode == 0);
+  stream_rows<NV, kDepth, BF16>(rs, rg, p, &S->chunk_ctr, key, wreg, phase, true, false, lane, [&](unsigned int next_chunk) {
+    if (ahead_armed && next_chunk != 0xffffffffu && next_chunk >= trigger) {
+      ahead_armed = false;                          // one attempt per warp and round
+      // buffer (r+1)&1 is free once round r-1 has been published; otherwise the regular election at the start of round r+1 pulls
+      unsigned int tk = 1u;
+      if (lane == 0 && static_cast<int>(ld_acquire_gpu_u32(&wc->round) - round) >= 0) tk = atomicAdd(&Sn->pull_ticket, 1u);
+      tk = __shfl_sync(0xffffffffu, tk, 0);
+      if (tk == 0u) pipe_pull_warp<NVW>(p, Sn, w_nxt, round + 1u, false, lane);
+    }
+  });
+
+  // ---- phase 2: CTA reduce -> g[parity]; loss / count; CTA ticket
+  stream_reduce<NV, kDepth, BF16>(rs, rg, s_raw, p, g_loc, lane);
+  if (lane == 0) { sh.red[warp] = rs.loss_acc; sh.cnt[warp] = rs.cnt; }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f; unsigned int n = 0;
+#pragma unroll
+    for (int w = 0; w < kStreamWarps; ++w) { l += sh.red[w]; n += sh.cnt[w]; }
+    atomicAdd(&S->loss_sum, l);
+    atomicAdd(&S->batch_count, n);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.flag = atomicAdd(&S->done_ctas, 1u);
+  __syncthreads();
+  const unsigned int my_ticket = sh.flag;
+  __syncthreads();                                   // sh.flag is reused below
+
+  // ---- early logical-clock ticket by the first CTA to finish (its NVLink round trip overlaps the drain)
+  if (my_ticket == 0 && tid == 0) {
+    const Ticket t = take_ticket(p, S->ts, round);
+    S->tk_accept = t.accept; S->tk_step = t.step; S->tk_clock_old = t.clock_old;
+    S->tk_staleness = t.staleness; S->tk_k_after = t.k_after;
+    __threadfence();
+    st_release_gpu_u32(&S->tk_flag, round + 1u);
+  }
+  if (my_ticket != gridDim.x - 1) return PROCEED_RUN;          // everybody else: on to round r+1
+
+  // ---- tail of round `round` (this CTA only), overlapping the other CTAs' round r+1
+  if (tid == 0) {
+    wc->dbg_ns[3] = globaltimer_ns();
+    SpinGuard sg;
+    while (ld_acquire_gpu_u32(&wc->round) != round) {                        // tails publish in round order
+      __nanosleep(20);
+      if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+    }
+    while (ld_acquire_gpu_u32(&S->tk_flag) != round + 1u) {
+      __nanosleep(32);
+      if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+    }
+    wc->dbg_ns[4] = globaltimer_ns();
+    sh.flag = static_cast<unsigned int>(*reinterpret_cast<volatile int*>(&S->tk_accept));
+    sh.bcast[0] = *reinterpret_cast<volatile float*>(&S->tk_step);
+  }
+  __threadfence();
+  __syncthreads();
+  const int accept = aborted(wc) ? 0 : static_cast<int>(sh.flag);
+  const float step = sh.bcast[0];
+  if (accept) hogwild_apply<kStreamThreads>(p, g_loc, w_loc, step);           // K9 + K5 (+ K8)
+  for (int v = tid; v < nvec; v += kStreamThreads)
+    *reinterpret_cast<float4*>(g_loc + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long now = 0, task_ns = 0;
+  unsigned int clock_old = 0;
+  ResultRec* rec = nullptr;
+  float round_loss = 0.f;
+  unsigned int round_batch = 0;
+  const bool last_of_launch = (it == rounds - 1);
+  if (tid == 0) {
+    round_loss = *reinterpret_cast<volatile float*>(&S->loss_sum);
+    round_batch = *reinterpret_cast<volatile unsigned int*>(&S->batch_count);
+    now = globaltimer_ns();
+    wc->dbg_ns[5] = now;
+    task_ns = now - S->t_start_ns;
+    clock_old = *reinterpret_cast<volatile unsigned int*>(&S->tk_clock_old);
+    rec = p.ring + (clock_old % static_cast<unsigned int>(p.ring_size));
+    rec->worker = p.worker_id; rec->accepted = accept;
+    rec->ts = static_cast<long long>(S->ts); rec->staleness = S->tk_staleness;
+    rec->k_after = S->tk_k_after; rec->batch = round_batch;
+    rec->loss_sum = round_loss; rec->step = accept ? step : 0.f;
+    rec->t_start_ns = S->t_start_ns; rec->t_end_ns = now;
+    WorkerSlot* me = p.status + p.worker_id;
+    const unsigned long long ntasks = wc->rounds_done + 1ULL;
+    const float task_ms = static_cast<float>(task_ns) * 1e-6f;
+    wc->avg_task_ms += (task_ms - wc->avg_task_ms) / static_cast<float>(ntasks);
+    wc->last_finish_ns = now;
+    me->staleness = S->tk_staleness;
+    me->num_tasks = static_cast<long long>(ntasks);
+    me->last_task_ms = task_ms;
+    me->avg_task_ms = wc->avg_task_ms;
+    me->heartbeat_ns = now; me->last_finish_ns = now;
+    if (accept && p.warmup_updates > 0 && S->tk_k_after <= static_cast<long long>(p.warmup_updates)) {
+      asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&p.sctl->cul_time_ns), "l"(task_ns) : "memory");
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(&p.sctl->cul_count), "r"(1u) : "memory");
+    }
+    if (last_of_launch) me->available = 1;                                   // the persistent launch ends with this round
+  }
+  fence_sys();                               // ONE fence: reductions + record + status performed before publication
+  __syncthreads();
+  if (tid == 0) {
+    wc->dbg_ns[6] = globaltimer_ns();
+    *reinterpret_cast<volatile unsigned long long*>(&rec->seq) = static_cast<unsigned long long>(clock_old) + 1ULL;
+    if (last_of_launch) red_add_release_sys_s32(&p.sctl->avail_count, 1);
+    if (accept && p.warmup_updates > 0 && S->tk_k_after == static_cast<long long>(p.warmup_updates)) {
+      unsigned long long tot = ld_acquire_sys_u64(&p.sctl->cul_time_ns);
+      unsigned int c = ld_acquire_sys_u32(&p.sctl->cul_count);
+      if (c) atomicExch_system(&p.sctl->avg_delay_ns, tot / c);
+    }
+    wc->last_accepted = accept; wc->last_batch = round_batch; wc->last_loss = round_loss;
+    wc->last_step = accept ? step : 0.f; wc->last_task_ns = task_ns;
+    wc->last_staleness = S->tk_staleness; wc->last_k_after = S->tk_k_after;
+    wc->ts = S->ts; wc->k_read = S->k_read;
+    wc->rounds_done += 1ULL;
+    S->done_ctas = 0; S->pull_ticket = 0; S->chunk_ctr = 0; S->loss_sum = 0.f; S->batch_count = 0;
+    wc->dbg_ns[7] = globaltimer_ns();
+    __threadfence();
+    st_release_gpu_u32(&wc->round, round + 1u);
+  }
+  __syncthreads();
+  return PROCEED_RUN;
+}
+
+template <int NV, int kDepth, bool PIPE, bool BF16>
+__global__ void __launch_bounds__(kStreamThreads, (NV * RowElems<BF16>::kE <= 32) ? 2 : 1)
+dense_stream_kernel(const __grid_constant__ RoundParams p, const int rounds, PipeState* ps, float* g2, float* w2) {
+  __shared__ RoundShared<kStreamThreads> sh;
+  __shared__ __align__(8) uint64_t s_bar[kStreamWarps][kDepth];
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpRing rg;
+  rg.row_bytes = static_cast<uint32_t>(p.ld * (BF16 ? 2 : 4));
+  rg.stage_bytes = rg.row_bytes + kStreamMetaBytes;
+  rg.base = s_raw + static_cast<size_t>(warp) * kDepth * rg.stage_bytes;
+  rg.bars = &s_bar[warp][0];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kDepth; ++s) tc::mbar_init(&s_bar[warp][s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  unsigned int phase = 0;                          // bit s = parity of the next completion of this warp's stage s
+  // No CTA of this grid can have finished a round before every CTA has started (the last-CTA election needs all of
+  // them), so this read is the same value in every CTA.
+  const unsigned int round0 = *reinterpret_cast<volatile unsigned int*>(&p.wctl->round);
+  for (int it = 0; it < rounds; ++it) {
+    const unsigned int round = round0 + static_cast<unsigned int>(it);
+    int r;
+    if (PIPE) r = stream_round_pipe<NV, kDepth, BF16>(p, sh, s_raw, rg, phase, round, it, rounds, ps, g2, w2);
+    else r = stream_round_serial<NV, kDepth, BF16>(p, sh, s_raw, rg, phase, round, it > 0);
+    if (r == PROCEED_STOP) return;
+    __syncthreads();                               // sh is reused by the next round
+  }
+}
+
+template <int NV, int kDepth, bool PIPE, bool BF16>
+static cudaError_t launch_stream(const RoundParams& p, int rounds, int grid, int share, PipeState* ps, float* g2, float* w2,
+                                 cudaStream_t stream) {
+  const size_t stage = static_cast<size_t>(p.ld) * (BF16 ? 2 : 4) + kStreamMetaBytes;
+  const size_t smem = static_cast<size_t>(kStreamWarps) * kDepth * stage + 128;
+  auto k = dense_stream_kernel<NV, kDepth, PIPE, BF16>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  if (rounds > 1) {
+    // rounds are separated by in-kernel waits: every CTA of every co-running persistent grid must be resident
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamThreads, smem)) != cudaSuccess) return e;
+    if (share < 1) share = 1;
+    if (static_cast<long long>(grid) * share > static_cast<long long>(per_sm) * sms) return cudaErrorLaunchOutOfResources;
+  }
+  k<<<grid, kStreamThreads, smem, stream>>>(p, rounds, ps, g2, w2);
+  return cudaGetLastError();
+}
+
+// floats per lane held for w / acc: <= 32 => 128 registers, two CTAs per SM; wider rows: one CTA per SM
+static int stream_nv(long long ld, bool bf16) { const int e = bf16 ? 8 : 4; return static_cast<int>((ld / e + 31) / 32); }
+static int stream_ctas(long long ld, bool bf16) { return stream_nv(ld, bf16) * (bf16 ? 8 : 4) <= 32 ? 2 : 1; }
+// ring depth: as deep as 227 KB of shared memory per SM allows for the resident CTAs, at most 4 (fp32) / 8 (bf16)
+static int stream_depth(long long ld, bool bf16) {
+  const long long per_cta = (stream_ctas(ld, bf16) == 2 ? 113 : 226) * 1024LL - 2048;
+  const long long stage = ld * (bf16 ? 2 : 4) + kStreamMetaBytes;
+  long long d = per_cta / (kStreamWarps * stage);
+  const long long cap = bf16 ? 8 : 4;
+  if (d > cap) d = cap;
+  return static_cast<int>(d);
+}
+
+template <bool PIPE, bool BF16>
+static cudaError_t dispatch_stream(const RoundParams& p, int rounds, int grid, int share, PipeState* ps, float* g2, float* w2, cudaStream_t s) {
+  const int nv = stream_nv(p.ld, BF16);
+  const int depth = stream_depth(p.ld, BF16);
+  if (depth < 2) return cudaErrorInvalidValue;
+#define AFB_STREAM_CASE(NVX, D) return launch_stream<NVX, D, PIPE, BF16>(p, rounds, grid, share, ps, g2, w2, s)
+  if constexpr (BF16) {
+    // bf16 rows: depth 8 / 6 / 4 / 3 / 2
+#define AFB_STREAM_DEPTH(NVX) \
+    do { if (depth >= 8) AFB_STREAM_CASE(NVX, 8); if (depth >= 6) AFB_STREAM_CASE(NVX, 6); if (depth >= 4) AFB_STREAM_CASE(NVX, 4); \
+         if (depth == 3) AFB_STREAM_CASE(NVX, 3); AFB_STREAM_CASE(NVX, 2); } while (0)
+    switch (nv) {
+      case 1: AFB_STREAM_CASE(1, 8);
+      case 2: AFB_STREAM_CASE(2, 8);
+      case 3: case 4: AFB_STREAM_DEPTH(4);
+      case 5: case 6: AFB_STREAM_DEPTH(6);
+      default: AFB_STREAM_DEPTH(8);
+    }
+#undef AFB_STREAM_DEPTH
+  } else {
+#define AFB_STREAM_DEPTH(NVX) \
+    do { if (depth >= 4) AFB_STREAM_CASE(NVX, 4); if (depth == 3) AFB_STREAM_CASE(NVX, 3); AFB_STREAM_CASE(NVX, 2); } while (0)
+    switch (nv) {
+      case 1: AFB_STREAM_CASE(1, 4);
+      case 2: AFB_STREAM_CASE(2, 4);
+      case 3: case 4: AFB_STREAM_CASE(4, 4);
+      case 5: case 6: case 7: AFB_STREAM_DEPTH(7);
+      case 8: AFB_STREAM_DEPTH(8);
+      case 9: case 10: case 11: case 12: AFB_STREAM_DEPTH(12);
+      default: AFB_STREAM_DEPTH(16);
+    }
+#undef AFB_STREAM_DEPTH
+  }
+#undef AFB_STREAM_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace afb
+
+extern "C" {
+
+int afb_dense_stream_max_ld() { return 2048; }
+int afb_dense_stream_ctas_per_sm(long long ld, int bf16) { return afb::stream_ctas(ld, bf16 != 0); }
+int afb_dense_stream_depth(long long ld, int bf16) { return afb::stream_depth(ld, bf16 != 0); }
+int afb_pipe_state_bytes() { return static_cast<int>(sizeof(afb::PipeState)); }
+
+static int stream_check(const afb::RoundParams& p, int rounds, int bf16) {
+  if (p.ld % (bf16 ? 8 : 4) != 0 || p.ld > 2048 || p.ld <= 0 || rounds <= 0) return static_cast<int>(cudaErrorInvalidValue);
+  if (p.hist_prev != nullptr || p.pdl != 0 || p.seed_mode == 3) return static_cast<int>(cudaErrorInvalidValue);
+  if ((reinterpret_cast<uintptr_t>(p.X) & 15) || (reinterpret_cast<uintptr_t>(p.y) & 15)) return static_cast<int>(cudaErrorMisalignedAddress);
+  return 0;
+}
+
+// Serial persistent rounds: every algorithm (rollback rounds excepted: hist_prev must be null), `rounds` >= 1.
+// `share` = persistent grids co-running on this GPU (logical workers per GPU); refused unless all of them fit.
+// `bf16` != 0: X holds bf16 rows (ld % 8 == 0).
+int afb_dense_stream_launch(const afb::RoundParams* params, int rounds, int grid, int share, int bf16, void* stream) {
+  using namespace afb;
+  const RoundParams& p = *params;
+  if (int rc = stream_check(p, rounds, bf16)) return rc;
+  if (p.algo == ALGO_GRAD_ONLY && rounds != 1) return static_cast<int>(cudaErrorInvalidValue);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return static_cast<int>(bf16 ? dispatch_stream<false, true>(p, rounds, grid, share, nullptr, nullptr, nullptr, s)
+                               : dispatch_stream<false, false>(p, rounds, grid, share, nullptr, nullptr, nullptr, s));
+}
+
+// Pipelined persistent rounds: ASGD only, no bucket / SSP gate, no enable mask, worker-local sampling seed (seed_mode 1 or 2);
+// the grid must be fully co-resident and is expected to be the only round kernel of its GPU (one logical worker per GPU).
+// `pipe_state` = afb_pipe_state_bytes() zeroed bytes, `g2` / `w2` = [2][ld] floats (g2 zeroed), all on the worker's GPU.
+int afb_dense_stream_pipelined_launch(const afb::RoundParams* params, int rounds, int grid, void* pipe_state, float* g2, float* w2,
+                                      int bf16, void* stream) {
+  using namespace afb;
+  const RoundParams& p = *params;
+  if (int rc = stream_check(p, rounds, bf16)) return rc;
+  if (p.algo != ALGO_ASGD || p.hist != nullptr || p.gate_threshold != 0 || p.ssp_bound >= 0 || p.use_mask != 0 ||
+      !(p.seed_mode == 1 || p.seed_mode == 2))
+    return static_cast<int>(cudaErrorInvalidValue);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PipeState* ps = static_cast<PipeState*>(pipe_state);
+  return static_cast<int>(bf16 ? dispatch_stream<true, true>(p, rounds, grid, 1, ps, g2, w2, s)
+                               : dispatch_stream<true, false>(p, rounds, grid, 1, ps, g2, w2, s));
+}
+
+}  // extern "C"

@@ -123,6 +123,8 @@ int afb_abi_sizeof(int which) {
     case 3: return static_cast<int>(sizeof(afb::WorkerSlot));
     case 4: return static_cast<int>(sizeof(afb::ResultRec));
     case 5: return static_cast<int>(sizeof(afb::SyncPeers));
+    case 6: return static_cast<int>(sizeof(afb::RoundDesc));
+    case 7: return static_cast<int>(sizeof(afb::PipeBuf));
     default: return -1;
   }
 }

@@ -14,13 +14,6 @@
 
 namespace afb {
 
-AFB_DEVINL void multimem_st_f32x4(float* mc, float4 v) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-AFB_DEVINL void multimem_red_add_u32(unsigned int* mc, unsigned int v) {
-  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
-}
 
 // dst_mc: multicast address of the destination region (same offset on every rank)
 __global__ void broadcast_mc_kernel(const float* __restrict__ src, float* dst_mc, long long n4, unsigned int* flag_mc,

@@ -98,6 +98,10 @@ def main():
         same = all(bool(torch.equal(lst[0], t)) for t in lst) if world > 1 else True
         out[f"{algo}_relerr"] = err
         out[f"{algo}_replicas_identical"] = same
+        out[f"{algo}_nvls"] = bool(eng.kernels[0].nvls_bsp)          # all-gather through the NVLS multicast alias (multimem.st)
+        out[f"{algo}_variant"] = eng.kernels[0].variant_effective
+        out[f"{algo}_launches"] = eng.launches                        # 20 rounds = ONE persistent launch
+        eng.check_health()
         del eng
 
     # ---- 2. async ASGD / ASAGA over NVLink: invariants + convergence ---------------------------
@@ -142,6 +146,56 @@ def main():
             out[key + "_max_staleness"] = max((r.staleness for r in res), default=0)
             out[key + "_stale_applied"] = sum(1 for r in res if r.data["accepted"] and taw == 0 and r.staleness > 0)
             out[key + "_workers_seen"] = sorted({r.worker_id for r in res})
+        eng.barrier()
+        del eng
+
+    # ---- 2b. persistent worker loops over NVLink: ONE launch = R rounds per worker ---------------------------------
+    #   pipelined ASGD (asp), serial persistent ASGD behind a bucket gate, SSP gate, ASAGA, and a host-evaluated predicate
+    #   that masks the last worker out (ASYNCbarrier on the fused path)
+    R = 40
+    for name, algo, loss, gamma, labels01, barrier, extra in (
+            ("pipelined", "asgd", "logistic", 0.8, True, "asp", {}),
+            ("bucket", "asgd", "logistic", 0.8, True, "bucket", {"bucket_ratio": 0.5}),
+            ("ssp", "asgd", "logistic", 0.8, True, "ssp", {"ssp_bound": 1 << 20}),
+            ("asaga_persist", "asaga", "least_squares", 0.05, False, "asp", {}),
+            ("masked", "asgd", "logistic", 0.8, True, "asp", {"mask": True})):
+        parts = make_parts(world, n_per, d, 13, labels01)
+        kw = {k: v for k, v in extra.items() if k != "mask"}
+        cfg = AsyncConfig(algorithm=algo, num_features=d, num_rows=n_per * world, num_partitions=world, num_iterations=1 << 30,
+                          step_size=gamma / world, batch_rate=0.3, loss=loss, seed=42, backend="fused", barrier=barrier, **kw)
+        eng = FusedEngine(cfg, [shard_of(parts[rank], d, dev, rank)], n_per * world, device=dev, worker_mask=bool(extra.get("mask")))
+        if extra.get("mask"):
+            sel = eng.async_barrier(lambda st: True)                 # everybody ...
+            if rank == 0:
+                eng.set_worker_mask([q != world - 1 for q in range(world)])     # ... except the last worker
+            eng.barrier()
+        eng.run_rounds(R)
+        eng.synchronize()
+        eng.check_health()
+        eng.barrier()
+        st = eng.server_state()
+        w = eng.weights().double().cpu().numpy()
+        key = "p_" + name
+        out[key + "_variant"] = eng.kernels[0].variant_effective
+        out[key + "_launches"] = eng.launches
+        out[key + "_k"] = st["k"]
+        out[key + "_clock"] = st["clock"]
+        out[key + "_avail"] = st["avail_count"]
+        out[key + "_finite"] = bool(np.isfinite(w).all())
+        ctl = eng.kernels[0].read_ctl()
+        sk = torch.tensor([float(ctl["skipped_rounds"])], device=dev)
+        lst_sk = [torch.zeros_like(sk) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(lst_sk, sk)
+        out[key + "_skipped"] = [int(t.item()) for t in lst_sk] if world > 1 else [int(sk.item())]
+        if rank == 0:
+            res = eng.drain_results()
+            out[key + "_ring"] = len(res)
+            out[key + "_workers_seen"] = sorted({r.worker_id for r in res})
+            by_seq = [r.data["loss_sum"] / max(r.batch_size, 1) for r in res if r.batch_size > 0]
+            out[key + "_loss_first"] = float(np.mean(by_seq[: world])) if by_seq else None
+            out[key + "_loss_last"] = float(np.mean(by_seq[-world:])) if by_seq else None
+            out[key + "_max_staleness"] = max((r.staleness for r in res), default=0)
         eng.barrier()
         del eng
 

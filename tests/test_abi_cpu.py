@@ -36,13 +36,20 @@ def test_every_declared_entry_point_exists():
     assert lib.afb_dense_round_max_ld() == 2048 and lib.afb_dense_round_ctas_per_sm(784) == 2 and lib.afb_dense_round_ctas_per_sm(2000) == 1
 
 
-def test_experimental_library_is_separate_and_declares_the_persistent_launcher():
+def test_stream_kernels_are_in_the_default_library():
+    """The persistent round kernels (dense TMA-ring stream kernel, one-kernel CSR round) and the tensor-core evaluation with a
+    loss epilogue ship in the default library: no opt-in side library exists any more."""
     from asyncframework_b200 import _native
-    path = _native.LIBDIR / "libafb_experimental.so"
-    if not path.exists():
-        pytest.skip("libafb_experimental.so not built")
-    lib = _native.experimental()
-    assert lib.afb_dense_round_persist_max_ld() == 2048
-    assert lib.afb_dense_round_persist_launch.argtypes is not None
-    # the default library must not contain the experimental entry point (work in progress cannot leak into the default path)
-    assert not hasattr(_native.kernels(), "afb_dense_round_persist_launch")
+    from asyncframework_b200.ops import _signatures as S
+    if not _native.kernels_path().exists():
+        pytest.skip("libafb_kernels.so not built")
+    lib = _native.kernels()
+    for name in ("afb_dense_stream_launch", "afb_dense_stream_pipelined_launch", "afb_csr_stream_launch", "afb_eval_loss_tc",
+                 "afb_pipe_state_bytes", "afb_grid_bar_bytes"):
+        assert getattr(lib, name).argtypes is not None, name
+    assert lib.afb_dense_stream_max_ld() == 2048
+    assert lib.afb_dense_stream_ctas_per_sm(784, 0) == 2 and lib.afb_dense_stream_ctas_per_sm(2000, 0) == 1
+    assert lib.afb_dense_stream_depth(784, 0) == 4 and lib.afb_dense_stream_depth(784, 1) == 8 and lib.afb_dense_stream_depth(2000, 0) == 3
+    assert lib.afb_abi_sizeof(6) == S.ROUND_DESC_DTYPE.itemsize and lib.afb_abi_sizeof(7) == S.PIPE_BUF_DTYPE.itemsize
+    assert lib.afb_pipe_state_bytes() == 2 * S.PIPE_BUF_DTYPE.itemsize
+    assert not (_native.LIBDIR / "libafb_experimental.so").exists()

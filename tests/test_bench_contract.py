@@ -26,12 +26,13 @@ def test_bench_json_contract_on_simulator():
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["higher_is_better"] is True
-    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "fp32" and d["device"] == "cpu"
+    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "bf16" and d["device"] == "cpu"
     assert abs(d["value"] - 5 / (d["ms_per_step"] * 5e-3)) < 1e-6 * d["value"]
     for k in ("model", "global_batch", "seq_len", "parallelism"):
         assert k in d["config"], k
     assert d["config"]["global_batch"] == 2000 and d["config"]["workers_per_gpu"] == 2
-    assert d["gpu_launches"] == 5 * 2                                  # one fused round per worker per step
+    assert d["gpu_launches"] == 2                                      # ONE persistent launch per worker for the 5 timed rounds
+    assert d["config"]["dense_variant"] == "stream-pipelined"
     e = d["e2e"]
     assert e["value"] > 0 and e["unit"] == "iterations/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert 0.0 < e["last_loss_per_row"] < 1.0

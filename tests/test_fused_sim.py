@@ -181,19 +181,19 @@ def test_device_watchdog_on_simulated_status_table():
 
 
 def test_persistent_variant_is_n_back_to_back_rounds_on_the_simulator():
-    """launch_rounds(n) of the (experimental) persistent variant must be protocol-identical to n single launches."""
+    """launch_rounds(n) of the persistent stream variant must be protocol-identical to n single launches."""
     P, d, n = 2, 12, 300
     parts = _parts(P, n, d, 5, False)
     cfg = AsyncConfig(algorithm="asaga", num_features=d, num_rows=n * P, num_partitions=P, num_iterations=1 << 30, step_size=0.05,
                       batch_rate=0.3, loss="least_squares", backend="fused", barrier="asp")
     outs = []
-    for variant in ("simple", "persist"):
+    for variant in ("simple", "stream"):
         os.environ["AFB_DENSE_VARIANT"] = variant
         try:
             eng = FusedEngine(cfg, [_shard(parts[p], d, p) for p in range(P)], n * P, list(range(P)), device="cpu")
         finally:
             os.environ.pop("AFB_DENSE_VARIANT", None)
-        assert all(rk.persist == (variant == "persist") for rk in eng.kernels)
+        assert all(rk.persist == (variant == "stream") for rk in eng.kernels)
         eng.run_rounds(6)
         st = eng.server_state()
         outs.append((eng.weights().clone(), st["k"], st["clock"], eng.launches))
@@ -211,13 +211,9 @@ def test_pipelined_variant_semantics_on_the_simulator():
     parts = _parts(1, n, d, 9, True)
     cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=gamma,
                       batch_rate=b, loss="logistic", backend="fused", barrier="asp", seed=seed)
-    os.environ["AFB_DENSE_VARIANT"] = "pipelined"
-    try:
-        eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")
-    finally:
-        os.environ.pop("AFB_DENSE_VARIANT", None)
+    eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")      # the default: stream kernel, pipelined ASGD
     rk = eng.kernels[0]
-    assert rk.pipelined and not rk.persist and rk.variant_effective == "pipelined"
+    assert rk.pipelined and not rk.persist and rk.variant_effective == "stream-pipelined"
     eng.run_rounds(rounds)
     st = eng.server_state()
     assert st["k"] == rounds and st["clock"] == rounds and eng.launches == 1
@@ -238,26 +234,27 @@ def test_pipelined_variant_semantics_on_the_simulator():
     # an ineligible request (ASAGA) falls back to the barrier-persistent variant and says so
     cfg2 = AsyncConfig(algorithm="asaga", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=0.05,
                        batch_rate=b, loss="least_squares", backend="fused", barrier="asp")
-    os.environ["AFB_DENSE_VARIANT"] = "pipelined"
-    try:
-        eng2 = FusedEngine(cfg2, [_shard(parts[0], d, 0)], n, [0], device="cpu")
-    finally:
-        os.environ.pop("AFB_DENSE_VARIANT", None)
-    assert eng2.kernels[0].variant_effective == "persist"
+    eng2 = FusedEngine(cfg2, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+    assert eng2.kernels[0].variant_effective == "stream"
+    # ... and so does ASGD behind a device gate (bucket) or with pipelining switched off
+    cfg3 = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=gamma,
+                       batch_rate=b, loss="logistic", backend="fused", barrier="asp", seed=seed)
+    eng3 = FusedEngine(cfg3, [_shard(parts[0], d, 0)], n, [0], device="cpu", pipeline=False)
+    assert eng3.kernels[0].variant_effective == "stream" and not eng3.kernels[0].pipelined
 
 
 def test_persistent_csr_variant_on_the_simulator():
-    """CSR shards + AFB_DENSE_VARIANT=persist select the persistent wide-model round; on the simulator that is n rounds."""
+    """Wide CSR shards run the persistent one-kernel round (csr_stream.cu) by default; on the simulator that is n rounds."""
     from asyncframework_b200.data.generators import synthetic_shard
     cfg = AsyncConfig(algorithm="asgd", num_features=300, num_rows=600, num_partitions=2, num_iterations=1 << 30, step_size=0.5,
                       batch_rate=0.3, loss="logistic", backend="fused", barrier="asp")
     shards = [synthetic_shard("rcv1", 300, p, 2, seed=3, device="cpu", num_features=300, row_offset=300 * p) for p in range(2)]
-    os.environ["AFB_DENSE_VARIANT"] = "persist"
+    os.environ["AFB_SPLIT_MIN_LD"] = "64"
     try:
         eng = FusedEngine(cfg, shards, 600, [0, 1], device="cpu")
     finally:
-        os.environ.pop("AFB_DENSE_VARIANT", None)
-    assert all(rk.persist_csr and rk.variant_effective == "persist" for rk in eng.kernels)
+        os.environ.pop("AFB_SPLIT_MIN_LD", None)
+    assert all(rk.persist_csr and rk.variant_effective == "csr-stream" for rk in eng.kernels)
     eng.run_rounds(4)
     st = eng.server_state()
     assert st["k"] == 8 and eng.launches == 2 and torch.isfinite(eng.weights()).all()
@@ -274,7 +271,7 @@ def test_bf16_row_storage_on_the_simulator_is_exact_for_integer_pixels():
                           batch_rate=0.3, loss="logistic", backend="fused", barrier="asp")
         eng = FusedEngine(cfg, [sh], 500, [0], device="cpu")
         assert eng.kernels[0].bf16_rows == (row_dtype is not None)
-        assert eng.kernels[0].variant_effective == ("bf16" if row_dtype is not None else "simple")
+        assert eng.kernels[0].variant_effective == "stream-pipelined"        # one kernel family for fp32 and bf16 rows
         eng.run_rounds(4)
         outs.append(eng.weights().clone())
     assert torch.equal(outs[0], outs[1]) and outs[0].abs().sum() > 0

@@ -31,3 +31,18 @@ def test_fused_paths_on_all_visible_gpus():
     assert out["asgd_taw0_stale_applied"] == 0                # no update applied with staleness > taw
     assert out["asgd_tawinf_accepted"] >= 60 * n
     assert out["versioned_broadcast_ok"]
+    # BSP rounds are persistent (20 rounds = 1 launch) and use the NVLS multicast all-gather whenever the fabric offers it
+    assert out["sgd_sync_variant"] == "stream" and out["sgd_sync_launches"] == 1
+    assert out["sgd_sync_nvls"] == out["multicast"]
+    # persistent worker loops: one launch, R rounds per worker, every round accepted exactly once
+    R = 40
+    for name, variant in (("pipelined", "stream-pipelined"), ("bucket", "stream"), ("ssp", "stream"), ("asaga_persist", "stream")):
+        key = "p_" + name
+        assert out[key + "_variant"] == variant and out[key + "_launches"] == 1
+        assert out[key + "_k"] == R * n and out[key + "_clock"] == R * n and out[key + "_ring"] == R * n
+        assert out[key + "_avail"] == n and out[key + "_finite"]
+        assert out[key + "_workers_seen"] == list(range(n))
+        assert out[key + "_loss_last"] < out[key + "_loss_first"]
+    # ASYNCbarrier on the fused path: the masked worker sat every round out, the others ran theirs
+    assert out["p_masked_k"] == R * (n - 1) and out["p_masked_workers_seen"] == list(range(n - 1))
+    assert out["p_masked_skipped"] == [0] * (n - 1) + [R] and out["p_masked_avail"] == n
