@@ -312,6 +312,13 @@ class RoundKernel:
         if spin_limit_s is None:
             spin_limit_s = float(os.environ.get("AFB_SPIN_LIMIT_S", "20"))
         p.spin_limit_ns = int(spin_limit_s * 1e9)
+        # stream kernel: which ring stages are filled by the TMA unit (one cp.async.bulk per row, ~64 cycles of TMA service
+        # per operation) and which by per-lane 16-byte cp.async through the LSU path; alternating stages keeps BOTH copy
+        # engines busy (profiles/README.md: all-TMA caps at 5.2 TB/s on 3 KB rows)
+        # Measured at N = 1 (profiles/README.md): bf16 rows: all-TMA 3583 it/s > alternating 3499 > all-LSU 3434 (a 1.5 KB row
+        # amortises the per-operation TMA cost); fp32 rows: all-LSU 2278 > alternating 2178 > all-TMA 2038 (TMA cap 5.2 TB/s).
+        default_mask = "0xFF" if self.bf16_rows else "0x00"
+        p.tma_mask = int(os.environ.get("AFB_TMA_MASK", default_mask), 0)
         self.params = p
         self.desc_dev = None                     # set by FusedEngine for the end-to-end path (RoundDesc ring)
         self.num_sms = torch.cuda.get_device_properties(dev).multi_processor_count if not self.sim else 148

@@ -149,7 +149,8 @@ class FusedEngine:
                              warmup_updates=warm, local_block=self.block, peer_blocks=peer_blocks, grid=grid,
                              wctl=self.wctl_all[li], sim_server_block=self.block if self.device.type != "cuda" else None,
                              reg_param=cfg.reg_param, reg_type=reg_type, ssp_bound=ssp_bound, use_mask=self.worker_mask,
-                             pipeline=pipeline, multicast_base=int(getattr(self.symm, "multicast_ptr", 0) or 0) if self.world > 1 else 0)
+                             pipeline=(pipeline if n_local == 1 else False),      # pipelined rounds own every SM of their GPU
+                             multicast_base=int(getattr(self.symm, "multicast_ptr", 0) or 0) if self.world > 1 else 0)
             self.kernels.append(rk)
             self.streams.append(_dev.new_stream(self.device) if n_local > 1 else _dev.current_stream(self.device))
         # pinned staging for the end-to-end path (double-buffered: step i+1 is submitted before the

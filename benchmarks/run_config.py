@@ -5,6 +5,9 @@
   epsilon_asaga  ASAGA (per-sample history), dense 400k x 2000, sampling 0.1
   rcv1_asgd      ASGD, CSR 677k x 47 236 (~74 nnz/row), sampling 0.05
   straggler      ASAGA vs synchronous SAGA under delay intensity {0.3, 0.6, 1.0}, mnist8m shape
+  production     the reference's production-cluster experiment (README.md:72-74): 32 logical workers (4 per GPU at 8 GPUs),
+                 25 % stragglers (delay -1: 80 % normal U[1.5,2.5), 20 % long-tail U[2.5,10) x the mean task time), beta = 0.7:
+                 ASGD / ASAGA vs the synchronous variants at equal work
 
 Each run reports device-timed iterations/s (max over ranks) and wall-clock to a target training loss
 (full-data objective evaluated with the K12 kernel every `--eval-every` iterations).
@@ -39,14 +42,31 @@ CONFIGS = {
 }
 
 
+_SHARD_CACHE = {}
+
+
+def shards_for(shape, total, P, world, rank, dev, loss, row_dtype):
+    """HBM-resident shards of this rank, generated once per (shape, P, dtype) and shared by every run of the sweep."""
+    key = (shape, total, P, str(row_dtype))
+    if key not in _SHARD_CACHE:
+        _SHARD_CACHE.clear()                   # one resident dataset at a time
+        torch.cuda.empty_cache()
+        sizes = shard_rows(total, P)
+        ids = [p for p in range(P) if p % world == rank]
+        labels = "regression" if loss.startswith("least_squares") else "binary01"
+        dense = SHAPES[shape][2] == "dense"
+        _SHARD_CACHE[key] = ([synthetic_shard(shape, sizes[p], p, P, 42, dev, torch.float32, None, labels, sum(sizes[:p]),
+                                              row_dtype=(row_dtype if dense else None)) for p in ids], ids)
+    return _SHARD_CACHE[key]
+
+
 def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, eval_every, target_frac, coeff=0.0,
-            wpg=1, warm_per_worker=20, rounds_per_batch=10, by_updates=False):
-    P = world * wpg if algo in ("asgd", "asaga") else world
+            wpg=1, warm_per_worker=20, rounds_per_batch=50, by_updates=False, row_dtype=None, barrier="asp", beta=0.0):
+    P = world * wpg
+    if algo in ("sgd_sync", "saga_sync") and wpg != 1:
+        raise ValueError("BSP fused rounds run one worker per rank")
     total = int(rows or SHAPES[shape][0])
-    sizes = shard_rows(total, P)
-    ids = [p for p in range(P) if p % world == rank]
-    labels = "regression" if loss.startswith("least_squares") else "binary01"
-    shards = [synthetic_shard(shape, sizes[p], p, P, 42, dev, torch.float32, None, labels, sum(sizes[:p])) for p in ids]
+    shards, ids = shards_for(shape, total, P, world, rank, dev, loss, row_dtype)
     if algo in ("asgd", "asaga"):
         gamma = gamma / P
     is_async = algo in ("asgd", "asaga")
@@ -55,7 +75,7 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
     max_updates = iters * P if (by_updates and is_async) else (1 << 40)
     cfg = AsyncConfig(algorithm=algo, num_features=shards[0].num_features, num_rows=total, num_partitions=P,
                       num_iterations=max_updates, step_size=gamma, batch_rate=b, loss=loss, seed=42, backend="fused",
-                      barrier="asp", coeff=coeff, warmup_updates_per_worker=warm_per_worker)
+                      barrier=barrier if is_async else "asp", bucket_ratio=beta, coeff=coeff, warmup_updates_per_worker=warm_per_worker)
     eng = FusedEngine(cfg, shards, total, ids, device=dev)
 
     def objective():
@@ -101,7 +121,9 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
         res = {"config": name, "algo": algo, "shape": shape, "n_gpus": world, "workers": P, "delay_intensity": coeff,
                "iterations": iters, "iterations_per_s": iters / (dev_ms * 1e-3), "ms_per_iteration": dev_ms / iters,
                "objective_start": obj0, "objective_end": obj, "accepted_updates": min(st["k"], max_updates),
-               "local_rounds_rank0": rounds, "avg_delay_ms": st["avg_delay_ns"] * 1e-6, "mode": "fixed total updates (iters*P)"}
+               "local_rounds_rank0": rounds, "avg_delay_ms": st["avg_delay_ns"] * 1e-6, "mode": "fixed total updates (iters*P)",
+               "variant": eng.kernels[0].variant_effective, "row_dtype": str(row_dtype or torch.float32), "barrier": barrier, "beta": beta}
+        eng.check_health()
         eng.barrier()
         del eng
         torch.cuda.empty_cache()
@@ -143,7 +165,9 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
            "iterations": done, "iterations_per_s": done / (dev_ms * 1e-3), "ms_per_iteration": dev_ms / done,
            "objective_start": obj0, "objective_end": curve[-1][1], "target": target, "wall_ms_to_target": t_target,
            "accepted_updates": st["k"] if eng.is_async else done, "avg_delay_ms": st["avg_delay_ns"] * 1e-6,
-           "curve": [(round(a, 2), round(o, 6)) for a, o in curve]}
+           "curve": [(round(a, 2), round(o, 6)) for a, o in curve],
+           "variant": eng.kernels[0].variant_effective, "row_dtype": str(row_dtype or torch.float32), "launches": eng.launches}
+    eng.check_health()
     eng.barrier()
     del eng
     torch.cuda.empty_cache()
@@ -152,7 +176,9 @@ def run_one(name, algo, shape, loss, b, gamma, rows, world, rank, dev, iters, ev
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=list(CONFIGS) + ["straggler"])
+    ap.add_argument("--config", required=True, choices=list(CONFIGS) + ["straggler", "production"])
+    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"], help="row storage of the mnist8m-shape shards (exact for integer pixels)")
+    ap.add_argument("--gamma", type=float, default=0.0, help="override the per-iteration step size of the config")
     ap.add_argument("--iters", type=int, default=400)
     ap.add_argument("--eval-every", type=int, default=50)
     ap.add_argument("--target-frac", type=float, default=0.9, help="target = this fraction of the initial objective")
@@ -165,21 +191,36 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     results = []
+    mnist_dt = torch.bfloat16 if args.dtype == "bf16" else None
     if args.config == "straggler":
         for coeff in args.delays:
             for algo, gamma in (("asaga", 3e-6), ("saga_sync", 3e-6)):
                 results.append(run_one("straggler", algo, "mnist8m", "logistic", 0.1, gamma, args.rows or None, world, rank, dev,
                                        args.iters, args.iters, args.target_frac, coeff=coeff,
-                                       wpg=args.workers_per_gpu if algo == "asaga" else 1, by_updates=True))
+                                       wpg=args.workers_per_gpu if algo == "asaga" else 1, by_updates=True, row_dtype=mnist_dt))
                 if rank == 0:
                     r = results[-1]
                     print(f"[straggler] {algo:10s} delay={coeff:.1f} equal-work it/s={r['iterations_per_s']:.1f} "
                           f"ms/it={r['ms_per_iteration']:.4f} obj {r['objective_start']:.4f}->{r['objective_end']:.4f} "
                           f"avg_delay_ms={r['avg_delay_ms']:.4f}", flush=True)
+    elif args.config == "production":
+        # README.md:72-74: 32 workers, 8 of them stragglers (delay -1), beta 0.7, b 0.1; ASYNC vs sync at equal work
+        wpg = max(1, 32 // world)
+        for algo, gamma in (("asgd", 8e-6), ("asaga", 3e-6), ("sgd_sync", 8e-6), ("saga_sync", 3e-6)):
+            sync = algo.endswith("sync")
+            results.append(run_one("production", algo, "mnist8m", "logistic", 0.1, gamma, args.rows or None, world, rank, dev,
+                                   args.iters, args.iters, args.target_frac, coeff=-1.0, wpg=1 if sync else wpg, by_updates=True,
+                                   row_dtype=mnist_dt, barrier="asp" if sync else "bucket", beta=0.7))
+            if rank == 0:
+                r = results[-1]
+                print(f"[production] {algo:10s} workers={r['workers']} equal-work it/s={r['iterations_per_s']:.1f} "
+                      f"ms/it={r['ms_per_iteration']:.4f} obj {r['objective_start']:.4f}->{r['objective_end']:.4f} "
+                      f"avg_delay_ms={r['avg_delay_ms']:.4f}", flush=True)
     else:
         c = CONFIGS[args.config]
-        results.append(run_one(args.config, c["algo"], c["shape"], c["loss"], c["b"], c["gamma"], args.rows or c["rows"], world,
-                               rank, dev, args.iters, args.eval_every, args.target_frac, wpg=args.workers_per_gpu))
+        results.append(run_one(args.config, c["algo"], c["shape"], c["loss"], c["b"], args.gamma or c["gamma"], args.rows or c["rows"], world,
+                               rank, dev, args.iters, args.eval_every, args.target_frac, wpg=args.workers_per_gpu,
+                               row_dtype=mnist_dt if c["shape"] == "mnist8m" else None))
     if rank == 0:
         for r in results:
             print("CONFIG_RESULT " + json.dumps(r))

@@ -157,26 +157,45 @@ struct RoundParams {
   int desc_slots;
   int pull_ahead_chunks;            // pipelined rounds: pull round r+1's parameters when this many chunks of round r remain
   unsigned long long spin_limit_ns; // bound of every in-kernel spin (0 = unbounded)
+  int tma_mask;                     // stream kernel: bit s = ring stage s is filled by a TMA bulk copy (else by per-lane cp.async)
+  int pad_tail;
 };
 
 // The descriptor of `round`, or null when the ring holds none for it (slot not written / already reused): the launch
 // scalars apply then, so rounds enqueued without a fresh descriptor (run_rounds) simply ignore the ring.
+// NB: the descriptor words are read with opaque `ld.relaxed.gpu.global` asm and the launch scalar is read FIRST into a
+// register: written as `d ? d->x : p.x` nvcc merges the two loads into one `ld.global` through a selected POINTER, and the
+// generic address of a __grid_constant__ parameter is not a global address (compute-sanitizer: invalid global read at
+// offsetof(RoundParams, thr24)).
+AFB_DEVINL unsigned int ld_desc_u32(const void* ptr) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
 AFB_DEVINL const RoundDesc* round_desc(const RoundParams& p, unsigned int round) {
-  if (p.desc == nullptr) return nullptr;
-  const RoundDesc* d = p.desc + (round % static_cast<unsigned int>(p.desc_slots));
-  return (*reinterpret_cast<const volatile unsigned int*>(&d->seq) == round + 1u) ? d : nullptr;
+  const RoundDesc* base = p.desc;
+  const int slots = p.desc_slots;
+  if (base == nullptr || slots <= 0) return nullptr;
+  const RoundDesc* d = base + (round % static_cast<unsigned int>(slots));
+  return (ld_desc_u32(&d->seq) == round + 1u) ? d : nullptr;
 }
 AFB_DEVINL int eff_thr24(const RoundParams& p, unsigned int round) {
+  int v = p.thr24;
   const RoundDesc* d = round_desc(p, round);
-  return d ? *reinterpret_cast<const volatile int*>(&d->thr24) : p.thr24;
+  if (d != nullptr) v = static_cast<int>(ld_desc_u32(&d->thr24));
+  return v;
 }
 AFB_DEVINL float eff_gamma(const RoundParams& p, unsigned int round) {
+  float v = p.gamma;
   const RoundDesc* d = round_desc(p, round);
-  return d ? *reinterpret_cast<const volatile float*>(&d->gamma) : p.gamma;
+  if (d != nullptr) v = __uint_as_float(ld_desc_u32(&d->gamma));
+  return v;
 }
 AFB_DEVINL float eff_delay_coeff(const RoundParams& p, unsigned int round) {
+  float v = p.delay_coeff;
   const RoundDesc* d = round_desc(p, round);
-  return d ? *reinterpret_cast<const volatile float*>(&d->delay_coeff) : p.delay_coeff;
+  if (d != nullptr) v = __uint_as_float(ld_desc_u32(&d->delay_coeff));
+  return v;
 }
 
 }  // namespace afb

@@ -32,30 +32,83 @@ namespace afb {
 
 constexpr int kStreamWarps = 8;
 constexpr int kStreamThreads = 32 * kStreamWarps;
-constexpr int kStreamMetaBytes = 32;       // {float y[4]; float pad[4]} — the 16-byte quad of labels around the row
+constexpr int kStreamMetaBytes = 16;       // {int row; pad} behind the row
 
 AFB_DEVINL void stream_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
 
+// packed fp32 pairs: sm_100a executes two fp32 FMAs per instruction (fma.rn.f32x2 -> FFMA2), which halves the FMA-pipe
+// instructions of the dot and of the axpy (the kernel is issue-bound, not FLOP-bound: ncu, profiles/ncu_stream_*)
+typedef unsigned long long f32x2;
+AFB_DEVINL f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+AFB_DEVINL void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+AFB_DEVINL f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 struct WarpRing {
-  uint8_t* base;            // this warp's kDepth stages
-  uint64_t* bars;           // this warp's kDepth mbarriers
+  uint8_t* base;            // this warp's kDepth stages (generic pointer: used by the once-per-round reduce)
+  uint32_t base_s;          // ... the same as a shared-window address: the per-row path uses 32-bit shared addresses only
+  uint32_t bars_s;          // this warp's kDepth mbarriers (shared-window address)
   uint32_t row_bytes;
   uint32_t stage_bytes;
 };
 
-// lane 0 arms the stage barrier and launches the bulk copies of one row (+ its label quad)
-AFB_DEVINL void ring_issue(const WarpRing& rg, const RoundParams& p, const int row, const int slot, const int lane) {
-  if (lane == 0) {
-    uint8_t* st = rg.base + static_cast<size_t>(slot) * rg.stage_bytes;
-    float* meta = reinterpret_cast<float*>(st + rg.row_bytes);
-    const bool quad_ok = (row | 3) < p.n_rows;
-    if (!quad_ok) meta[row & 3] = __ldg(p.y + row);
-    tc::mbar_arrive_expect_tx(&rg.bars[slot], rg.row_bytes + (quad_ok ? 16u : 0u));
-    stream_bulk_g2s(st, reinterpret_cast<const uint8_t*>(p.X) + static_cast<long long>(row) * rg.row_bytes, rg.row_bytes, &rg.bars[slot]);
-    if (quad_ok) stream_bulk_g2s(meta, p.y + (row & ~3), 16u, &rg.bars[slot]);
+AFB_DEVINL uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+AFB_DEVINL uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+AFB_DEVINL void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+AFB_DEVINL void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// Two asynchronous copy engines fill a warp's ring, stage by stage (RoundParams.tma_mask):
+//   * TMA stages: lane 0 arms the stage's mbarrier (expect_tx) and launches ONE `cp.async.bulk` for the row.  The TMA unit
+//     serves ~64 cycles per operation per SM on top of the bytes, so 3 KB rows alone cap at ~5.2 TB/s (fp32) — measured,
+//     profiles/README.md; a second 16-byte copy for the label cost as much as half a row;
+//   * LSU stages: every lane issues its 16-byte `cp.async.cg` chunks of the row (LDGSTS, no register staging) and a
+//     `cp.async.mbarrier.arrive.noinc` on the same mbarrier (initialised with 32 arrivals): same completion mechanism,
+//     different engine.
+// Alternating the two keeps both engines busy.  The row id travels with the stage (plain shared store, published to the
+// warp by the __syncwarp of the consume loop), so a warp keeps NO per-stage state in registers and the consume loop is a
+// single un-unrolled body.  Label / history scalars are fetched with plain loads one row AHEAD of their use (stream_rows).
+template <int NV>
+AFB_DEVINL void ring_issue(const WarpRing& rg, const RoundParams& p, const int row, const uint32_t st_s, const uint32_t bar_s,
+                           const bool tma, const int lane, const int nchunks) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(p.X) + static_cast<long long>(row) * rg.row_bytes;
+  if (lane == 0) sts_u32(st_s + rg.row_bytes, static_cast<uint32_t>(row));
+  if (tma) {
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(rg.row_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(st_s), "l"(src), "r"(rg.row_bytes), "r"(bar_s) : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int v = lane + 32 * c;
+      if (c < NV - 1 || v < nchunks)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_s + 16u * v), "l"(src + 16 * v) : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_s) : "memory");
   }
 }
 
@@ -67,28 +120,30 @@ AFB_DEVINL int pop_mask_row(RowScheduler& s) {
 
 // A row is consumed in 16-byte chunks: lane l owns chunks {l + 32 c}.  fp32 rows: 4 elements per chunk; bf16 rows
 // (row STORAGE only — labels, parameters, gradient and all arithmetic stay fp32): 8 elements per chunk, half the HBM bytes.
-template <bool BF16> struct RowElems { static constexpr int kE = BF16 ? 8 : 4; };
+template <bool BF16> struct RowElems { static constexpr int kE = BF16 ? 8 : 4; static constexpr int kP = kE / 2; };
 
+// one 16-byte chunk -> kP packed fp32 pairs
 template <bool BF16>
-AFB_DEVINL void unpack_chunk(const uint4 raw, float (&x)[RowElems<BF16>::kE]) {
+AFB_DEVINL void unpack_chunk(const uint4 raw, f32x2 (&x)[RowElems<BF16>::kP]) {
   if constexpr (BF16) {
-    x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xffff0000u);
-    x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xffff0000u);
-    x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xffff0000u);
-    x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xffff0000u);
+    x[0] = pack2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u));
+    x[1] = pack2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+    x[2] = pack2(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u));
+    x[3] = pack2(__uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xffff0000u));
   } else {
-    x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y); x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
+    x[0] = (static_cast<f32x2>(raw.y) << 32) | raw.x;
+    x[1] = (static_cast<f32x2>(raw.w) << 32) | raw.z;
   }
 }
 
-// Per-warp streaming state of one round.
+// Per-warp streaming state of one round: the chunk scheduler, the ring cursor and the register accumulators.
 template <int NV, int kDepth, bool BF16>
 struct RowStream {
-  static constexpr int kE = RowElems<BF16>::kE;
+  static constexpr int kP = RowElems<BF16>::kP;
   RowScheduler sch;
-  int rows_q[kDepth];
-  float hq[kDepth];         // SAGA: history scalar of the row in each stage (plain load at issue time, consumed kDepth rows later)
-  float acc[NV][kE];
+  int head;                 // stage holding the oldest row in flight
+  int n_in;                 // rows in flight (stages head, head+1, ... in ring order)
+  f32x2 acc[NV][kP];
   float loss_acc;
   unsigned int cnt;
 };
@@ -98,9 +153,9 @@ AFB_DEVINL void stream_reset(RowStream<NV, kDepth, BF16>& rs, const RoundParams&
 #pragma unroll
   for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int j = 0; j < RowElems<BF16>::kE; ++j) rs.acc[c][j] = 0.f;
-#pragma unroll
-  for (int s = 0; s < kDepth; ++s) { rs.rows_q[s] = -1; rs.hq[s] = 0.f; }
+    for (int j = 0; j < RowElems<BF16>::kP; ++j) rs.acc[c][j] = 0ULL;
+  rs.head = 0;
+  rs.n_in = 0;
   rs.loss_acc = 0.f;
   rs.cnt = 0;
   sched_init(rs.sch, p.n_rows, gridDim.x * kStreamWarps, blockIdx.x * kStreamWarps + (threadIdx.x >> 5), thr24);
@@ -109,102 +164,147 @@ AFB_DEVINL void stream_reset(RowStream<NV, kDepth, BF16>& rs, const RoundParams&
 // Prologue on immutable inputs only (X, y, gidx): hash the statically assigned first chunk, put up to kDepth row fetches
 // in flight.  No atomics, no protocol state: legal before the round barrier / the pull.
 template <int NV, int kDepth, bool BF16>
-AFB_DEVINL void stream_prologue(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, const RoundParams& p, const unsigned long long key, const int lane) {
+AFB_DEVINL void stream_prologue(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, const RoundParams& p, const unsigned long long key,
+                                const int lane) {
+  const int nchunks = static_cast<int>(p.ld) / RowElems<BF16>::kE;
   const unsigned int c0 = rs.sch.next_chunk;
   rs.sch.next_chunk = 0xffffffffu;                 // "first dynamic chunk id not fetched yet"
   if (c0 < static_cast<unsigned int>(rs.sch.num_chunks)) {
     load_chunk_masks(rs.sch, p, c0, lane, key);
-#pragma unroll
-    for (int s = 0; s < kDepth; ++s) {
+    while (rs.n_in < kDepth) {
       const int r = pop_mask_row(rs.sch);
-      rs.rows_q[s] = r;
-      if (r >= 0) ring_issue(rg, p, r, s, lane);
+      if (r < 0) break;
+      ring_issue<NV>(rg, p, r, rg.base_s + rs.n_in * rg.stage_bytes, rg.bars_s + 8u * rs.n_in, (p.tma_mask >> rs.n_in) & 1, lane, nchunks);
+      ++rs.n_in;
     }
   }
 }
 
-// The gradient phase of one round: fill the ring, then consume rows until the chunk pool is empty.
-// `saga`: history correction + write-through history update (K4/K7).  `on_tick(next_chunk)` is called once per consumed row
-// with the id of the chunk the warp will draw next (the pipelined loop hangs its pull-ahead on it).
-template <int NV, int kDepth, bool BF16, typename Tick>
+// wait for every row still in flight (a CTA must not exit, nor may its stages be reused, with copies pending)
+template <int NV, int kDepth, bool BF16>
+AFB_DEVINL void stream_drain(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, unsigned int& phase) {
+  while (rs.n_in > 0) {
+    mbar_wait_s(rg.bars_s + 8u * rs.head, (phase >> rs.head) & 1u);
+    phase ^= (1u << rs.head);
+    rs.head = (rs.head + 1 == kDepth) ? 0 : rs.head + 1;
+    --rs.n_in;
+  }
+}
+
+// log(1 + e) for e in (0, 1]: the fast-math log of the rounded sum is accurate to ~1e-7 absolute here, which is far below
+// the fp32 noise of a loss SUM over thousands of rows (the loss value is reporting only: it never feeds the gradient)
+AFB_DEVINL void loss_coeff_fast(const int loss_id, const float margin, const float y, float& coeff, float& loss) {
+  if (loss_id == LOSS_LOGISTIC) {
+    const float e = __expf(-fabsf(margin));
+    const float inv = __fdividef(1.f, 1.f + e);
+    const float sig = margin >= 0.f ? inv : e * inv;
+    coeff = sig - y;
+    const float l1p = __logf(1.f + e) + fmaxf(-margin, 0.f);
+    loss = (y > 0.f) ? l1p : l1p + margin;
+  } else {
+    loss_coeff_rt(loss_id, margin, y, coeff, loss);
+  }
+}
+
+// The gradient phase of one round: fill the ring, then consume rows in FIFO order until the chunk pool is empty.
+// `saga`: history correction + write-through history update (K4/K7).  `trigger`: the pipelined loop's pull-ahead fires
+// (on_trigger()) when the warp draws a chunk id >= trigger; 0xffffffff disarms it.
+template <int NV, int kDepth, bool BF16, typename Trigger>
 AFB_DEVINL void stream_rows(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, const RoundParams& p, unsigned int* chunk_ctr,
-                            const unsigned long long key, const float (&wreg)[NV][RowElems<BF16>::kE], unsigned int& phase,
-                            const bool prologue_done, const bool saga, const int lane, Tick&& on_tick) {
+                            const unsigned long long key, const f32x2 (&wreg)[NV][RowElems<BF16>::kP], unsigned int& phase,
+                            const bool prologue_done, const bool saga, const int lane, unsigned int trigger, Trigger&& on_trigger) {
   constexpr int kE = RowElems<BF16>::kE;
+  constexpr int kP = RowElems<BF16>::kP;
   const int nchunks = static_cast<int>(p.ld) / kE;
   const int LOSS = p.loss_id;
+  const uint32_t stage = rg.stage_bytes, row_bytes = rg.row_bytes;
+  const uint32_t tma_mask = static_cast<uint32_t>(p.tma_mask);
+  const bool last_partial = (lane + 32 * (NV - 1)) >= nchunks;       // this lane has no part of the last chunk column
   if (prologue_done) rs.sch.next_chunk = fetch_chunk(chunk_ctr, lane, rs.sch.static_chunks);
-#pragma unroll
-  for (int s = 0; s < kDepth; ++s) {
-    if (rs.rows_q[s] < 0) {
+  {
+    int tail = rs.head + rs.n_in;                             // first free stage (head == 0 here)
+    while (rs.n_in < kDepth) {
       const int r = next_row(rs.sch, p, chunk_ctr, lane, key);
-      rs.rows_q[s] = r;
-      if (r >= 0) ring_issue(rg, p, r, s, lane);
+      if (r < 0) break;
+      ring_issue<NV>(rg, p, r, rg.base_s + tail * stage, rg.bars_s + 8u * tail, (tma_mask >> tail) & 1u, lane, nchunks);
+      ++tail;
+      ++rs.n_in;
     }
-    if (saga && rs.rows_q[s] >= 0) rs.hq[s] = p.hist[rs.rows_q[s]];
   }
-  while (true) {
-    bool any = false;
-#pragma unroll
-    for (int s = 0; s < kDepth; ++s) {
-      const int row = rs.rows_q[s];
-      if (row < 0) continue;
-      any = true;
-      on_tick(rs.sch.next_chunk);
-      tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u);
-      phase ^= (1u << s);
-      const uint8_t* st = rg.base + static_cast<size_t>(s) * rg.stage_bytes;
-      const float yy = reinterpret_cast<const float*>(st + rg.row_bytes)[row & 3];
-      const float hh = rs.hq[s];
-      uint4 raw[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        const int v = lane + 32 * c;
-        raw[c] = (v < nchunks) ? *reinterpret_cast<const uint4*>(st + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      __syncwarp();                                           // every lane has read the stage: refill it
-      const int nrow = next_row(rs.sch, p, chunk_ctr, lane, key);
-      rs.rows_q[s] = nrow;
-      if (nrow >= 0) {
-        ring_issue(rg, p, nrow, s, lane);
-        if (saga) rs.hq[s] = p.hist[nrow];
-      }
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {                          // K1
-        float x[kE];
-        unpack_chunk<BF16>(raw[c], x);
-        d0 = fmaf(x[0], wreg[c][0], d0);
-        d1 = fmaf(x[1], wreg[c][1], d1);
-        d2 = fmaf(x[2], wreg[c][2], d2);
-        d3 = fmaf(x[3], wreg[c][3], d3);
-        if constexpr (BF16) {
-          d0 = fmaf(x[4], wreg[c][4], d0);
-          d1 = fmaf(x[5], wreg[c][5], d1);
-          d2 = fmaf(x[6], wreg[c][6], d2);
-          d3 = fmaf(x[7], wreg[c][7], d3);
-        }
-      }
-      const float margin = warp_sum((d0 + d1) + (d2 + d3));
-      float coeff, loss;
-      loss_coeff_rt(LOSS, margin, yy, coeff, loss);           // K2
-      float eff = coeff;
-      if (saga) {                                             // K4 + K7 (write-through: rollback rounds use dense_round.cu)
-        eff = coeff - hh;
-        if (lane == 0) p.hist[row] = coeff;
-      }
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {                          // K3
-        float x[kE];
-        unpack_chunk<BF16>(raw[c], x);
-#pragma unroll
-        for (int j = 0; j < kE; ++j) rs.acc[c][j] = fmaf(eff, x[j], rs.acc[c][j]);
-      }
-      rs.loss_acc += loss;
-      ++rs.cnt;
+  __syncwarp();                                               // lane 0's row-id stores are visible to the warp
+  int head = rs.head;
+  int n_in = rs.n_in;
+  uint32_t st_s = rg.base_s + head * stage;                   // shared-window address of the head stage
+  uint32_t bar_s = rg.bars_s + 8u * head;
+  const uint32_t st_end = rg.base_s + kDepth * stage;
+  // label / history of the row at the head of the ring: plain loads issued one row ahead of their use
+  int row_nxt = 0;
+  float y_nxt = 0.f, h_nxt = 0.f;
+  if (n_in > 0) {
+    row_nxt = static_cast<int>(lds_u32(st_s + row_bytes));
+    y_nxt = __ldg(p.y + row_nxt);
+    if (saga) h_nxt = __ldcg(p.hist + row_nxt);
+  }
+  while (n_in > 0) {
+    if (rs.sch.next_chunk >= trigger) { trigger = 0xffffffffu; on_trigger(); }
+    const int row = row_nxt;
+    const float yy = y_nxt, hh = h_nxt;
+    uint32_t nst_s = st_s + stage, nbar_s = bar_s + 8u;
+    int nhead = head + 1;
+    if (nst_s == st_end) { nst_s = rg.base_s; nbar_s = rg.bars_s; nhead = 0; }
+    if (n_in >= 2) {                                          // the next row in FIFO order sits in the next stage
+      row_nxt = static_cast<int>(lds_u32(nst_s + row_bytes));
+      y_nxt = __ldg(p.y + row_nxt);
+      if (saga) h_nxt = __ldcg(p.hist + row_nxt);
     }
-    if (!any) break;
+    mbar_wait_s(bar_s, (phase >> head) & 1u);
+    phase ^= (1u << head);
+    uint4 raw[NV];
+#pragma unroll
+    for (int c = 0; c < NV - 1; ++c) raw[c] = lds_v4(st_s + 16u * (lane + 32 * c));
+    // only the last chunk column can fall outside the row (NV = ceil(nchunks / 32)): those lanes compute on zeros
+    raw[NV - 1] = last_partial ? make_uint4(0u, 0u, 0u, 0u) : lds_v4(st_s + 16u * (lane + 32 * (NV - 1)));
+    __syncwarp();                                             // every lane has read the stage: refill it
+    const int nrow = next_row(rs.sch, p, chunk_ctr, lane, key);
+    if (nrow >= 0) ring_issue<NV>(rg, p, nrow, st_s, bar_s, (tma_mask >> head) & 1u, lane, nchunks);
+    else --n_in;
+    head = nhead; st_s = nst_s; bar_s = nbar_s;
+    f32x2 dp0 = 0ULL, dp1 = 0ULL;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {                            // K1
+      f32x2 x[kP];
+      unpack_chunk<BF16>(raw[c], x);
+      dp0 = ffma2(x[0], wreg[c][0], dp0);
+      dp1 = ffma2(x[1], wreg[c][1], dp1);
+      if constexpr (BF16) {
+        dp0 = ffma2(x[2], wreg[c][2], dp0);
+        dp1 = ffma2(x[3], wreg[c][3], dp1);
+      }
+    }
+    float d0, d1, d2, d3;
+    unpack2(dp0, d0, d1);
+    unpack2(dp1, d2, d3);
+    const float margin = warp_sum((d0 + d1) + (d2 + d3));
+    float coeff, loss;
+    loss_coeff_fast(LOSS, margin, yy, coeff, loss);           // K2
+    float eff = coeff;
+    if (saga) {                                               // K4 + K7 (write-through: rollback rounds use dense_round.cu)
+      eff = coeff - hh;
+      if (lane == 0) p.hist[row] = coeff;
+    }
+    const f32x2 ee = pack2(eff, eff);
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {                            // K3 (lanes outside the row accumulate zeros)
+      f32x2 x[kP];
+      unpack_chunk<BF16>(raw[c], x);
+#pragma unroll
+      for (int j = 0; j < kP; ++j) rs.acc[c][j] = ffma2(ee, x[j], rs.acc[c][j]);
+    }
+    rs.loss_acc += loss;
+    ++rs.cnt;
   }
+  rs.head = head;
+  rs.n_in = 0;
 }
 
 // CTA-level reduce of the per-warp register accumulators through the (idle) ring stages, merged into `g_dst` with vector
@@ -213,16 +313,16 @@ template <int NV, int kDepth, bool BF16>
 AFB_DEVINL void stream_reduce(const RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg, uint8_t* s_raw, const RoundParams& p,
                               float* g_dst, const int lane) {
   constexpr int kE = RowElems<BF16>::kE;
+  constexpr int kP = RowElems<BF16>::kP;
   const int nchunks = static_cast<int>(p.ld) / kE;
   const int nvec = static_cast<int>(p.ld >> 2);
-  float* mine = reinterpret_cast<float*>(rg.base);      // ld fp32 fit: kDepth * stage_bytes >= 2 * (2 ld + 32) >= 4 ld
+  float* mine = reinterpret_cast<float*>(rg.base);      // ld fp32 fit: kDepth * stage_bytes >= 2 * (2 ld + 16) >= 4 ld
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
     const int v = lane + 32 * c;
     if (v < nchunks) {
-      *reinterpret_cast<float4*>(mine + kE * v) = make_float4(rs.acc[c][0], rs.acc[c][1], rs.acc[c][2], rs.acc[c][3]);
-      if constexpr (BF16)
-        *reinterpret_cast<float4*>(mine + kE * v + 4) = make_float4(rs.acc[c][4], rs.acc[c][5], rs.acc[c][6], rs.acc[c][7]);
+#pragma unroll
+      for (int j = 0; j < kP; ++j) *reinterpret_cast<f32x2*>(mine + kE * v + 2 * j) = rs.acc[c][j];
     }
   }
   __syncthreads();
@@ -241,7 +341,7 @@ AFB_DEVINL void stream_reduce(const RowStream<NV, kDepth, BF16>& rs, const WarpR
 }
 
 template <int NV, bool BF16>
-AFB_DEVINL void load_w_regs(float (&wreg)[NV][RowElems<BF16>::kE], const float* w, const int nchunks, const int lane) {
+AFB_DEVINL void load_w_regs(f32x2 (&wreg)[NV][RowElems<BF16>::kP], const float* w, const int nchunks, const int lane) {
   constexpr int kE = RowElems<BF16>::kE;
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
@@ -251,8 +351,8 @@ AFB_DEVINL void load_w_regs(float (&wreg)[NV][RowElems<BF16>::kE], const float* 
       a = __ldcg(reinterpret_cast<const float4*>(w + kE * v));
       if constexpr (BF16) b = __ldcg(reinterpret_cast<const float4*>(w + kE * v + 4));
     }
-    wreg[c][0] = a.x; wreg[c][1] = a.y; wreg[c][2] = a.z; wreg[c][3] = a.w;
-    if constexpr (BF16) { wreg[c][4] = b.x; wreg[c][5] = b.y; wreg[c][6] = b.z; wreg[c][7] = b.w; }
+    wreg[c][0] = pack2(a.x, a.y); wreg[c][1] = pack2(a.z, a.w);
+    if constexpr (BF16) { wreg[c][2] = pack2(b.x, b.y); wreg[c][3] = pack2(b.z, b.w); }
   }
 }
 
@@ -277,8 +377,8 @@ AFB_DEVINL int stream_round_serial(const RoundParams& p, RoundShared<kStreamThre
     unsigned long long seed_eff = static_cast<unsigned long long>(p.seed);
     if (p.algo != ALGO_GRAD_ONLY && p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
     key = mix64(seed_eff);
-    // SAGA reads the mutable history at issue time: not before the previous round of this launch is complete
-    if (!(saga && wait)) { stream_prologue(rs, rg, p, key, lane); prologue = true; }
+    stream_prologue(rs, rg, p, key, lane);         // immutable inputs only: the history is read later, with plain loads
+    prologue = true;
   }
   if (wait) {                                       // round barrier: the previous round (tail included) is published
     if (tid == 0) {
@@ -289,9 +389,7 @@ AFB_DEVINL int stream_round_serial(const RoundParams& p, RoundShared<kStreamThre
       }
     }
     if (cta_abort_vote<kStreamThreads>(sh, wc)) {
-#pragma unroll
-      for (int s = 0; s < kDepth; ++s)
-        if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+      stream_drain(rs, rg, phase);
       return PROCEED_STOP;
     }
   }
@@ -300,15 +398,13 @@ AFB_DEVINL int stream_round_serial(const RoundParams& p, RoundShared<kStreamThre
   const int pr = round_begin_complete<kStreamThreads>(p, sh, round, pl);
   if (pr != PROCEED_RUN) {
     // rows put in flight by the prologue must land before the stages are reused (or the CTA exits)
-#pragma unroll
-    for (int s = 0; s < kDepth; ++s)
-      if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+    stream_drain(rs, rg, phase);
     return pr;
   }
   if (!key_early) key = *reinterpret_cast<volatile unsigned long long*>(&wc->seed_key);
-  float wreg[NV][RowElems<BF16>::kE];
+  f32x2 wreg[NV][RowElems<BF16>::kP];
   load_w_regs<NV, BF16>(wreg, p.w_local, nchunks, lane);
-  stream_rows<NV, kDepth, BF16>(rs, rg, p, &wc->chunk_ctr, key, wreg, phase, prologue, saga, lane, [](unsigned int) {});
+  stream_rows<NV, kDepth, BF16>(rs, rg, p, &wc->chunk_ctr, key, wreg, phase, prologue, saga, lane, 0xffffffffu, []() {});
   stream_reduce<NV, kDepth, BF16>(rs, rg, s_raw, p, p.g_local, lane);
   round_finish<kStreamThreads>(p, sh, round, rs.loss_acc, rs.cnt);
   return PROCEED_RUN;
@@ -431,9 +527,7 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   if (!proceed) {
     // stopped (k >= max_iters, stop flag or abort): drain the prologue's copies, then the last CTA to arrive resets the
     // buffer and publishes, in round order
-#pragma unroll
-    for (int s = 0; s < kDepth; ++s)
-      if (rs.rows_q[s] >= 0) { tc::mbar_wait(&rg.bars[s], (phase >> s) & 1u); phase ^= (1u << s); }
+    stream_drain(rs, rg, phase);
     __syncthreads();
     if (tid == 0) {
       const unsigned int t = atomicAdd(&S->done_ctas, 1u);
@@ -458,22 +552,20 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   }
 
   // ---- phase 1: fused gradient; the warp that draws one of the last chunk ids pulls round r+1's parameters ahead
-  float wreg[NV][RowElems<BF16>::kE];
+  f32x2 wreg[NV][RowElems<BF16>::kP];
   load_w_regs<NV, BF16>(wreg, w_loc, nchunks, lane);
   const unsigned int dyn_chunks = rs.sch.num_chunks > static_cast<int>(rs.sch.static_chunks)
                                       ? static_cast<unsigned int>(rs.sch.num_chunks) - rs.sch.static_chunks : 0u;
   const unsigned int ahead = static_cast<unsigned int>(p.pull_ahead_chunks);
   const unsigned int trigger = rs.sch.static_chunks + (dyn_chunks > ahead ? dyn_chunks - ahead : 0u);
-  bool ahead_armed = (p.pull_ahead_chunks > 0) && (it + 1 < rounds) && (p.delay_mode == 0);
-  stream_rows<NV, kDepth, BF16>(rs, rg, p, &S->chunk_ctr, key, wreg, phase, true, false, lane, [&](unsigned int next_chunk) {
-    if (ahead_armed && next_chunk != 0xffffffffu && next_chunk >= trigger) {
-      ahead_armed = false;                          // one attempt per warp and round
-      // buffer (r+1)&1 is free once round r-1 has been published; otherwise the regular election at the start of round r+1 pulls
-      unsigned int tk = 1u;
-      if (lane == 0 && static_cast<int>(ld_acquire_gpu_u32(&wc->round) - round) >= 0) tk = atomicAdd(&Sn->pull_ticket, 1u);
-      tk = __shfl_sync(0xffffffffu, tk, 0);
-      if (tk == 0u) pipe_pull_warp<NVW>(p, Sn, w_nxt, round + 1u, false, lane);
-    }
+  const bool ahead_armed = (p.pull_ahead_chunks > 0) && (it + 1 < rounds) && (p.delay_mode == 0);
+  stream_rows<NV, kDepth, BF16>(rs, rg, p, &S->chunk_ctr, key, wreg, phase, true, false, lane, ahead_armed ? trigger : 0xffffffffu, [&]() {
+    // one attempt per warp and round.  Buffer (r+1)&1 is free once round r-1 has been published; otherwise the regular
+    // election at the start of round r+1 pulls
+    unsigned int tk = 1u;
+    if (lane == 0 && static_cast<int>(ld_acquire_gpu_u32(&wc->round) - round) >= 0) tk = atomicAdd(&Sn->pull_ticket, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk == 0u) pipe_pull_warp<NVW>(p, Sn, w_nxt, round + 1u, false, lane);
   });
 
   // ---- phase 2: CTA reduce -> g[parity]; loss / count; CTA ticket
@@ -598,10 +690,11 @@ dense_stream_kernel(const __grid_constant__ RoundParams p, const int rounds, Pip
   rg.row_bytes = static_cast<uint32_t>(p.ld * (BF16 ? 2 : 4));
   rg.stage_bytes = rg.row_bytes + kStreamMetaBytes;
   rg.base = s_raw + static_cast<size_t>(warp) * kDepth * rg.stage_bytes;
-  rg.bars = &s_bar[warp][0];
+  rg.base_s = tc::smem_u32(rg.base);
+  rg.bars_s = tc::smem_u32(&s_bar[warp][0]);
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kDepth; ++s) tc::mbar_init(&s_bar[warp][s], 1);
+    for (int s = 0; s < kDepth; ++s) tc::mbar_init(&s_bar[warp][s], ((p.tma_mask >> s) & 1) ? 1u : 32u);
     tc::fence_barrier_init();
   }
   __syncthreads();

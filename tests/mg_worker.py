@@ -155,7 +155,7 @@ def main():
     R = 40
     for name, algo, loss, gamma, labels01, barrier, extra in (
             ("pipelined", "asgd", "logistic", 0.8, True, "asp", {}),
-            ("bucket", "asgd", "logistic", 0.8, True, "bucket", {"bucket_ratio": 0.5}),
+            ("bucket", "asgd", "logistic", 0.8, True, "bucket", {"bucket_ratio": 1.0}),    # gate = P: a round starts only while every worker is idle
             ("ssp", "asgd", "logistic", 0.8, True, "ssp", {"ssp_bound": 1 << 20}),
             ("asaga_persist", "asaga", "least_squares", 0.05, False, "asp", {}),
             ("masked", "asgd", "logistic", 0.8, True, "asp", {"mask": True})):
