@@ -27,7 +27,7 @@ class RoundParams(C.Structure):
         ("round_host", i32), ("pdl", i32),
         ("reg_param", f32), ("reg_type", i32), ("ssp_bound", i32), ("use_mask", i32),
         ("desc", vp), ("desc_slots", i32), ("pull_ahead_chunks", i32), ("spin_limit_ns", u64),
-        ("tma_mask", i32), ("pad_tail", i32),
+        ("tma_mask", i32), ("g_copies", i32),
     ]
 
 

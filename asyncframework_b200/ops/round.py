@@ -228,7 +228,11 @@ class RoundKernel:
         dev = self.device
         self.w_local = torch.zeros(ld, dtype=torch.float32, device=dev)
         self.abar_local = torch.zeros(ld, dtype=torch.float32, device=dev)
-        self.g_local = torch.zeros(ld, dtype=torch.float32, device=dev)
+        # worker-local gradient: `g_copies` replicas (replica 0 is the one every consumer reads); the stream kernels spread
+        # the per-CTA merges over the replicas, every other kernel uses replica 0 only
+        self.g_copies = int(os.environ.get("AFB_G_COPIES", "16")) if shard.is_dense else 1
+        self.g_all = torch.zeros(self.g_copies, ld, dtype=torch.float32, device=dev)
+        self.g_local = self.g_all[0]
         # control block: caller may pass a slice of a contiguous per-rank array (one D2H for all workers)
         self.wctl = wctl if wctl is not None else torch.zeros(WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         assert self.wctl.numel() == WORKER_CTL_DTYPE.itemsize and self.wctl.is_contiguous()
@@ -266,7 +270,7 @@ class RoundKernel:
         p.w_server = server.w; p.abar_server = server.abar; p.sctl = server.sctl
         p.status = server.status; p.ring = server.ring
         p.w_local = self.w_local.data_ptr(); p.abar_local = self.abar_local.data_ptr()
-        p.g_local = self.g_local.data_ptr(); p.wctl = self.wctl.data_ptr()
+        p.g_local = self.g_all.data_ptr(); p.wctl = self.wctl.data_ptr(); p.g_copies = self.g_copies
         p.n_rows = shard.num_rows; p.d = d; p.algo = ALGO[algo]; p.ring_size = server.layout.ring_size
         p.num_workers = num_workers; p.worker_id = worker_id
         p.thr24 = threshold24(batch_rate); p.gate_threshold = int(gate_threshold)
@@ -362,7 +366,7 @@ class RoundKernel:
         if self.pipelined:
             nbytes = 192 if self.sim else self.lib.afb_pipe_state_bytes()
             self._pipe_state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            self._pipe_g2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
+            self._pipe_g2 = torch.zeros(2, self.g_copies, ld, dtype=torch.float32, device=dev)
             self._pipe_w2 = torch.zeros(2, ld, dtype=torch.float32, device=dev)
             # pull round r+1's parameters when ~6 us of round r remain: chunks/us = HBM bytes/us / (row bytes * 64 * b)
             row_bytes = ld * shard.X.element_size()

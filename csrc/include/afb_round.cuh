@@ -158,7 +158,7 @@ struct RoundParams {
   int pull_ahead_chunks;            // pipelined rounds: pull round r+1's parameters when this many chunks of round r remain
   unsigned long long spin_limit_ns; // bound of every in-kernel spin (0 = unbounded)
   int tma_mask;                     // stream kernel: bit s = ring stage s is filled by a TMA bulk copy (else by per-lane cp.async)
-  int pad_tail;
+  int g_copies;                     // replicas of g_local ([g_copies][ld]; >= 1) the CTAs of a grid spread their merges over
 };
 
 // The descriptor of `round`, or null when the ring holds none for it (slot not written / already reused): the launch

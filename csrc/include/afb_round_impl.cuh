@@ -320,6 +320,26 @@ AFB_DEVINL void hogwild_apply(const RoundParams& p, const float* g_loc, const fl
   hogwild_apply_range(p, g_loc, w_pulled, step, threadIdx.x, kThreads);
 }
 
+// Sum the `g_copies` replicas of the worker-local gradient into replica 0 and re-zero the others (stream kernels spread
+// the per-CTA merges over replicas to cut same-address L2 reduction traffic).  Whole CTA; ends with a CTA barrier.
+template <int kThreads>
+AFB_DEVINL void merge_g_copies(const RoundParams& p, float* g) {
+  if (p.g_copies <= 1) return;
+  const int nvec = static_cast<int>(p.ld >> 2);
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(g + 4 * v));
+    for (int c = 1; c < p.g_copies; ++c) {
+      float* gc = g + static_cast<long long>(c) * p.ld + 4 * v;
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(gc));
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+      *reinterpret_cast<float4*>(gc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    *reinterpret_cast<float4*>(g + 4 * v) = t;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 // Phase 2b + 3.  Called by every thread after the CTA has flushed its partial gradient into
 // g_local; `loss_acc` / `cnt` are the per-thread (lane-0-valid per warp) loss sum and row count.
 template <int kThreads>
@@ -363,6 +383,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
   // ------------------------------------------------------------------ phase 3 (last CTA): push-and-apply
   if (tid == 0) wc->dbg_ns[3] = globaltimer_ns();
   __threadfence();
+  merge_g_copies<kThreads>(p, p.g_local);
   const float round_loss = *reinterpret_cast<volatile float*>(&wc->loss_sum);
   const unsigned int round_batch = *reinterpret_cast<volatile unsigned int*>(&wc->batch_count);
 

@@ -112,6 +112,30 @@ AFB_DEVINL void ring_issue(const WarpRing& rg, const RoundParams& p, const int r
   }
 }
 
+// Chunk ids are requested one ahead with an atomic whose RESULT IS NOT TOUCHED until the id is needed: the `__shfl_sync`
+// that broadcasts lane 0's ticket is deferred to the moment the current chunk runs dry, so the ~1 us L2 round trip of the
+// atomic overlaps row processing (the eager shuffle of afb_dense_rows.cuh::fetch_chunk showed up as 11 % of all stall
+// samples in the first ncu capture).  `RowScheduler.next_chunk` holds lane 0's raw ticket, or 0xffffffff for "none requested".
+AFB_DEVINL void stream_request_chunk(RowScheduler& s, unsigned int* ctr, const int lane) {
+  unsigned int t = 0;
+  if (lane == 0) t = atomicAdd(ctr, 1u);
+  s.next_chunk = t;                                // valid in lane 0 only; broadcast on demand
+}
+// next selected row of this warp, -1 once the pool is exhausted; `cur_chunk` = id of the chunk the row comes from
+AFB_DEVINL int stream_next_row(RowScheduler& s, const RoundParams& p, unsigned int* ctr, const int lane, const unsigned long long key,
+                               unsigned int& cur_chunk, bool& exhausted) {
+  while (true) {
+    if (s.m0) { int b = __ffs(s.m0) - 1; s.m0 &= s.m0 - 1; return s.base + b; }
+    if (s.m1) { int b = __ffs(s.m1) - 1; s.m1 &= s.m1 - 1; return s.base + 32 + b; }
+    if (exhausted) return -1;
+    const unsigned int c = __shfl_sync(0xffffffffu, s.next_chunk, 0) + s.static_chunks;
+    if (c >= static_cast<unsigned int>(s.num_chunks)) { exhausted = true; return -1; }
+    stream_request_chunk(s, ctr, lane);            // one ahead
+    cur_chunk = c;
+    load_chunk_masks(s, p, c, lane, key);
+  }
+}
+
 AFB_DEVINL int pop_mask_row(RowScheduler& s) {
   if (s.m0) { int b = __ffs(s.m0) - 1; s.m0 &= s.m0 - 1; return s.base + b; }
   if (s.m1) { int b = __ffs(s.m1) - 1; s.m1 &= s.m1 - 1; return s.base + 32 + b; }
@@ -220,11 +244,18 @@ AFB_DEVINL void stream_rows(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg,
   const uint32_t stage = rg.stage_bytes, row_bytes = rg.row_bytes;
   const uint32_t tma_mask = static_cast<uint32_t>(p.tma_mask);
   const bool last_partial = (lane + 32 * (NV - 1)) >= nchunks;       // this lane has no part of the last chunk column
-  if (prologue_done) rs.sch.next_chunk = fetch_chunk(chunk_ctr, lane, rs.sch.static_chunks);
+  // the statically assigned first chunk: consumed by the prologue, or still pending (no prologue: seed known only now)
+  unsigned int cur_chunk = 0;
+  bool exhausted = false;
+  if (!prologue_done) {
+    const unsigned int c0 = rs.sch.next_chunk;
+    if (c0 < static_cast<unsigned int>(rs.sch.num_chunks)) load_chunk_masks(rs.sch, p, c0, lane, key);
+  }
+  stream_request_chunk(rs.sch, chunk_ctr, lane);              // first dynamic chunk id: requested, not awaited
   {
     int tail = rs.head + rs.n_in;                             // first free stage (head == 0 here)
     while (rs.n_in < kDepth) {
-      const int r = next_row(rs.sch, p, chunk_ctr, lane, key);
+      const int r = stream_next_row(rs.sch, p, chunk_ctr, lane, key, cur_chunk, exhausted);
       if (r < 0) break;
       ring_issue<NV>(rg, p, r, rg.base_s + tail * stage, rg.bars_s + 8u * tail, (tma_mask >> tail) & 1u, lane, nchunks);
       ++tail;
@@ -246,7 +277,7 @@ AFB_DEVINL void stream_rows(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg,
     if (saga) h_nxt = __ldcg(p.hist + row_nxt);
   }
   while (n_in > 0) {
-    if (rs.sch.next_chunk >= trigger) { trigger = 0xffffffffu; on_trigger(); }
+    if (cur_chunk >= trigger) { trigger = 0xffffffffu; on_trigger(); }
     const int row = row_nxt;
     const float yy = y_nxt, hh = h_nxt;
     uint32_t nst_s = st_s + stage, nbar_s = bar_s + 8u;
@@ -265,7 +296,7 @@ AFB_DEVINL void stream_rows(RowStream<NV, kDepth, BF16>& rs, const WarpRing& rg,
     // only the last chunk column can fall outside the row (NV = ceil(nchunks / 32)): those lanes compute on zeros
     raw[NV - 1] = last_partial ? make_uint4(0u, 0u, 0u, 0u) : lds_v4(st_s + 16u * (lane + 32 * (NV - 1)));
     __syncwarp();                                             // every lane has read the stage: refill it
-    const int nrow = next_row(rs.sch, p, chunk_ctr, lane, key);
+    const int nrow = stream_next_row(rs.sch, p, chunk_ctr, lane, key, cur_chunk, exhausted);
     if (nrow >= 0) ring_issue<NV>(rg, p, nrow, st_s, bar_s, (tma_mask >> head) & 1u, lane, nchunks);
     else --n_in;
     head = nhead; st_s = nst_s; bar_s = nbar_s;
@@ -316,6 +347,9 @@ AFB_DEVINL void stream_reduce(const RowStream<NV, kDepth, BF16>& rs, const WarpR
   constexpr int kP = RowElems<BF16>::kP;
   const int nchunks = static_cast<int>(p.ld) / kE;
   const int nvec = static_cast<int>(p.ld >> 2);
+  // the 296 CTAs of a grid finish a round at about the same time: spreading their merges over `g_copies` replicas of g
+  // divides the same-address L2 reduction traffic (the last CTA sums the replicas before it pushes)
+  g_dst += static_cast<long long>(blockIdx.x % static_cast<unsigned int>(p.g_copies)) * p.ld;
   float* mine = reinterpret_cast<float*>(rg.base);      // ld fp32 fit: kDepth * stage_bytes >= 2 * (2 ld + 16) >= 4 ld
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
@@ -415,6 +449,8 @@ AFB_DEVINL int stream_round_serial(const RoundParams& p, RoundShared<kStreamThre
 // ----------------------------------------------------------------------------------------------------------------------
 // The pull of one round, executed by ONE warp that holds ticket 0 of the round's buffer: a single NVLink round trip brings
 // the logical clock and all of w; `first` marks the first round of the launch (the worker becomes busy).
+// (out of line: the pull-ahead calls it from inside the row loop once per round — its 28-32 staging registers must not
+// raise the register pressure of the loop itself; only the rare call site pays for saving live state)
 template <int NV4>
 AFB_DEVINL void pipe_pull_warp(const RoundParams& p, PipeBuf* S, float* w_loc, const unsigned int round, const bool first, const int lane) {
   const int nvec = static_cast<int>(p.ld >> 2);
@@ -470,6 +506,20 @@ AFB_DEVINL void pipe_pull_warp(const RoundParams& p, PipeBuf* S, float* w_loc, c
   if (lane == 0) st_release_gpu_u32(&S->pull_flag, round + 1u);
 }
 
+// one warp: wait until `*flag == want` (gpu-scope acquire); false on abort / timeout
+AFB_DEVINL bool warp_wait_flag(const RoundParams& p, const unsigned int* flag, const unsigned int want, const int lane) {
+  int ok = 1;
+  if (lane == 0) {
+    SpinGuard sg;
+    while (ld_acquire_gpu_u32(flag) != want) {
+      __nanosleep(32);
+      if (sg.expired(p.spin_limit_ns) || aborted(p.wctl)) { raise_abort(p.wctl); ok = 0; break; }
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok != 0;
+}
+
 template <int NV, int kDepth, bool BF16>
 AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThreads>& sh, uint8_t* s_raw, const WarpRing& rg,
                                  unsigned int& phase, const unsigned int round, const int it, const int rounds,
@@ -481,7 +531,7 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   WorkerCtl* wc = p.wctl;
   PipeBuf* S = &ps->b[round & 1u];
   PipeBuf* Sn = &ps->b[(round + 1u) & 1u];
-  float* g_loc = g2 + static_cast<long long>(round & 1u) * p.ld;
+  float* g_loc = g2 + static_cast<long long>(round & 1u) * p.ld * p.g_copies;      // [parity][copy][ld]
   float* w_loc = w2 + static_cast<long long>(round & 1u) * p.ld;
   float* w_nxt = w2 + static_cast<long long>((round + 1u) & 1u) * p.ld;
 
@@ -494,33 +544,36 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   if (p.seed_mode == 1) seed_eff += static_cast<unsigned long long>(round) + 1ULL;
   const unsigned long long key = mix64(seed_eff);
   stream_prologue(rs, rg, p, key, lane);
-  // ---- buffer reuse: round r-2 (same parity) must be published before anything of buffer r&1 is touched
-  if (it >= 2) {
-    if (tid == 0) {
-      SpinGuard sg;
+  // ---- the pull.  Usually done AHEAD by a warp of the previous round (ticket 0 of this buffer already taken); otherwise
+  //      CTA 0's warp 0 pulls right away and any other CTA's warp 0 steps in if the flag has not appeared after ~1 us
+  //      (CTA 0 may be busy in a tail).  No election atomic and no extra CTA barrier for the other CTAs.
+  if (warp == 0) {
+    unsigned int tries = 0;
+    SpinGuard sg;
+    // buffer reuse: round r-2 (same parity) must be published before anything of buffer r&1 is touched
+    if (it >= 2 && lane == 0) {
       while (static_cast<int>(ld_acquire_gpu_u32(&wc->round) - (round - 1u)) < 0) {
         __nanosleep(20);
         if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
       }
     }
-    __syncthreads();
-  }
-  // ---- puller election (ticket 0 may already have been taken by the previous round's pull-ahead)
-  if (tid == 0) sh.flag = atomicAdd(&S->pull_ticket, 1u);
-  __syncthreads();
-  const bool puller = (sh.flag == 0);
-  __syncthreads();                                   // sh.flag is reused by the finish sequence
-  if (puller) {
-    if (warp == 0) pipe_pull_warp<NVW>(p, S, w_loc, round, it == 0, lane);
-  }
-  // ---- wait for the pull; the decision is made CTA-uniform through shared memory
-  if (tid == 0) {
-    SpinGuard sg;
-    while (ld_acquire_gpu_u32(&S->pull_flag) != round + 1u) {
-      __nanosleep(32);
-      if (sg.expired(p.spin_limit_ns) || aborted(wc)) { raise_abort(wc); break; }
+    __syncwarp();
+    while (true) {
+      unsigned int f = 0;
+      if (lane == 0) f = ld_acquire_gpu_u32(&S->pull_flag);
+      f = __shfl_sync(0xffffffffu, f, 0);
+      if (f == round + 1u) break;
+      if ((blockIdx.x == 0 && tries == 0) || tries == 24) {
+        unsigned int tk = 1u;
+        if (lane == 0) tk = atomicAdd(&S->pull_ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk == 0u) { pipe_pull_warp<NVW>(p, S, w_loc, round, it == 0, lane); break; }
+      }
+      ++tries;
+      __nanosleep(40);
+      if (sg.expired(p.spin_limit_ns) || aborted(wc)) { if (lane == 0) raise_abort(wc); break; }
     }
-    sh.flag = (*reinterpret_cast<volatile int*>(&S->proceed) != 0 && !aborted(wc)) ? 1u : 0u;
+    if (lane == 0) sh.flag = (*reinterpret_cast<volatile int*>(&S->proceed) != 0 && !aborted(wc)) ? 1u : 0u;
   }
   __syncthreads();
   const int proceed = static_cast<int>(sh.flag);
@@ -616,6 +669,7 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   __syncthreads();
   const int accept = aborted(wc) ? 0 : static_cast<int>(sh.flag);
   const float step = sh.bcast[0];
+  merge_g_copies<kStreamThreads>(p, g_loc);                                   // replicas -> copy 0 (replicas re-zeroed)
   if (accept) hogwild_apply<kStreamThreads>(p, g_loc, w_loc, step);           // K9 + K5 (+ K8)
   for (int v = tid; v < nvec; v += kStreamThreads)
     *reinterpret_cast<float4*>(g_loc + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -737,7 +791,8 @@ static cudaError_t launch_stream(const RoundParams& p, int rounds, int grid, int
 static int stream_nv(long long ld, bool bf16) { const int e = bf16 ? 8 : 4; return static_cast<int>((ld / e + 31) / 32); }
 static int stream_ctas(long long ld, bool bf16) { return stream_nv(ld, bf16) * (bf16 ? 8 : 4) <= 32 ? 2 : 1; }
 // ring depth: as deep as 227 KB of shared memory per SM allows for the resident CTAs, at most 4 (fp32) / 8 (bf16)
-static int stream_depth(long long ld, bool bf16) {
+static int stream_depth(long long ld, bool bf16, bool pipe = false) {
+  (void)pipe;
   const long long per_cta = (stream_ctas(ld, bf16) == 2 ? 113 : 226) * 1024LL - 2048;
   const long long stage = ld * (bf16 ? 2 : 4) + kStreamMetaBytes;
   long long d = per_cta / (kStreamWarps * stage);
@@ -749,7 +804,7 @@ static int stream_depth(long long ld, bool bf16) {
 template <bool PIPE, bool BF16>
 static cudaError_t dispatch_stream(const RoundParams& p, int rounds, int grid, int share, PipeState* ps, float* g2, float* w2, cudaStream_t s) {
   const int nv = stream_nv(p.ld, BF16);
-  const int depth = stream_depth(p.ld, BF16);
+  const int depth = stream_depth(p.ld, BF16, PIPE);
   if (depth < 2) return cudaErrorInvalidValue;
 #define AFB_STREAM_CASE(NVX, D) return launch_stream<NVX, D, PIPE, BF16>(p, rounds, grid, share, ps, g2, w2, s)
   if constexpr (BF16) {
@@ -790,11 +845,12 @@ extern "C" {
 int afb_dense_stream_max_ld() { return 2048; }
 int afb_dense_stream_ctas_per_sm(long long ld, int bf16) { return afb::stream_ctas(ld, bf16 != 0); }
 int afb_dense_stream_depth(long long ld, int bf16) { return afb::stream_depth(ld, bf16 != 0); }
+int afb_dense_stream_depth_pipe(long long ld, int bf16) { return afb::stream_depth(ld, bf16 != 0, true); }
 int afb_pipe_state_bytes() { return static_cast<int>(sizeof(afb::PipeState)); }
 
 static int stream_check(const afb::RoundParams& p, int rounds, int bf16) {
   if (p.ld % (bf16 ? 8 : 4) != 0 || p.ld > 2048 || p.ld <= 0 || rounds <= 0) return static_cast<int>(cudaErrorInvalidValue);
-  if (p.hist_prev != nullptr || p.pdl != 0 || p.seed_mode == 3) return static_cast<int>(cudaErrorInvalidValue);
+  if (p.hist_prev != nullptr || p.pdl != 0 || p.seed_mode == 3 || p.g_copies < 1) return static_cast<int>(cudaErrorInvalidValue);
   if ((reinterpret_cast<uintptr_t>(p.X) & 15) || (reinterpret_cast<uintptr_t>(p.y) & 15)) return static_cast<int>(cudaErrorMisalignedAddress);
   return 0;
 }
