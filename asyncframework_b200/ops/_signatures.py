@@ -62,12 +62,12 @@ WORKER_CTL_DTYPE = np.dtype([
     ("dbg_ns", "<u8", (8,)),
     ("tk_flag", "<u4"), ("tk_accept", "<i4"), ("tk_step", "<f4"), ("tk_clock_old", "<u4"),
     ("tk_staleness", "<i8"), ("tk_k_after", "<i8"),
-    ("abort", "<i4"), ("skipped_rounds", "<u4"), ("pad_tail", "<u8"),
+    ("abort", "<i4"), ("skipped_rounds", "<u4"), ("wave_seen", "<u4"), ("pad_tail", "<u4"),
 ], align=False)
 assert WORKER_CTL_DTYPE.itemsize == 256
 
 SERVER_CTL_DTYPE = np.dtype({
-    "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "pad", "avg_delay_ns", "gate_dyn", "num_alive",
+    "names": ["clock_k", "avail_count", "stop", "cul_time_ns", "cul_count", "wave", "avg_delay_ns", "gate_dyn", "num_alive",
               "enable_mask"],
     "formats": ["<u8", "<i4", "<i4", "<u8", "<u4", "<u4", "<u8", "<i4", "<i4", ("<u8", (4,))],
     "offsets": [0, 8, 12, 16, 24, 28, 32, 40, 44, 48], "itemsize": 80})

@@ -15,6 +15,17 @@ from . import check, current_stream_ptr, kernels
 
 def eval_loss(shard: Shard, W: torch.Tensor, loss_id: int, use_tensor_cores=None) -> torch.Tensor:
     """``W``: [d, T] snapshots.  Returns float64[T] loss sums over the shard's rows."""
+    if shard.is_dense and shard.X.dtype == torch.bfloat16:
+        # bf16 row storage: the evaluation kernels consume fp32 tiles — widen the shard in chunks (evaluation is not a
+        # hot path; the shard itself stays bf16 in HBM).  The chunk row stride must be a multiple of 4 floats.
+        d, T = W.shape
+        out = torch.zeros(T, dtype=torch.float64, device=shard.device)
+        step = 262_144
+        for a in range(0, shard.num_rows, step):
+            b = min(shard.num_rows, a + step)
+            sub = Shard(shard.num_features, shard.y[a:b].contiguous(), shard.X[a:b].to(torch.float32))
+            out += eval_loss(sub, W, loss_id, use_tensor_cores)
+        return out
     lib = kernels()
     d, T = W.shape
     ld = shard.ld if shard.is_dense else (shard.num_features + 3) // 4 * 4

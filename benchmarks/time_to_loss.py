@@ -37,6 +37,13 @@ def full_objective(shards, w, total_rows, world):
     dev = shards[0].y.device
     acc = torch.zeros((), dtype=torch.float64, device=dev)
     for s in shards:
+        if s.is_dense and s.X.dtype != s.y.dtype:          # bf16 row storage: widen in chunks (the shard stays bf16 in HBM)
+            wv = w[: s.num_features].float()
+            for a in range(0, s.num_rows, 262144):
+                m = s.X[a:a + 262144, : s.num_features].float() @ wv
+                yy = s.y[a:a + 262144]
+                acc += (torch.nn.functional.softplus(-m) + m * (1 - yy)).double().sum()
+            continue
         margin = s.matvec(w[: s.num_features].to(s.y.dtype))
         acc += (torch.nn.functional.softplus(-margin) + margin * (1 - s.y)).double().sum()
     if world > 1:
@@ -112,7 +119,7 @@ def run_nccl(args, rank, world, dev, shards, total):
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     from nccl_sync import NcclSyncSGD
     s = shards[0]
-    opt = NcclSyncSGD(s.X, s.y, s.num_features, total, args.b, args.gamma, seed=42, loss="logistic")
+    opt = NcclSyncSGD(s.X, s.y, s.num_features, total, args.b, args.gamma, seed=42, loss="logistic", variant=args.nccl_variant)
     for _ in range(args.warmup):                  # untimed warm-up, then restart from w = 0
         opt.step()
     opt.w.zero_()
@@ -143,6 +150,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workers-per-gpu", type=int, default=0)
     ap.add_argument("--impl", default="both", choices=["both", "ours", "nccl"])
+    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"], help="row storage of BOTH arms (exact for the integer pixels)")
+    ap.add_argument("--nccl-variant", default="nosync", choices=["stock", "nosync"])
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     rank, local_rank, world = init_distributed()
@@ -155,16 +164,18 @@ def main():
     total = int(args.rows or (SHAPES[args.shape][0] if cuda else 4000))
     results = []
     if args.impl in ("both", "ours"):
-        wpg = args.workers_per_gpu or (2 if world > 1 else 1)
+        wpg = args.workers_per_gpu or 1            # one persistent, pipelined worker loop per GPU
         P = world * wpg
         sizes = shard_rows(total, P)
         ids = [p for p in range(P) if p % world == rank]
-        shards = [synthetic_shard(args.shape, sizes[p], p, P, 42, dev, torch.float32, None, "binary01", sum(sizes[:p])) for p in ids]
+        rdt = torch.bfloat16 if (args.dtype == "bf16" and cuda) else None
+        shards = [synthetic_shard(args.shape, sizes[p], p, P, 42, dev, torch.float32, None, "binary01", sum(sizes[:p]), row_dtype=rdt) for p in ids]
         results.append(run_ours(args, rank, world, dev, shards, ids, total, P))
         del shards
     if args.impl in ("both", "nccl"):
         sizes = shard_rows(total, world)
-        shards = [synthetic_shard(args.shape, sizes[rank], rank, world, 42, dev, torch.float32, None, "binary01", sum(sizes[:rank]))]
+        rdt = torch.bfloat16 if (args.dtype == "bf16" and cuda) else None
+        shards = [synthetic_shard(args.shape, sizes[rank], rank, world, 42, dev, torch.float32, None, "binary01", sum(sizes[:rank]), row_dtype=rdt)]
         results.append(run_nccl(args, rank, world, dev, shards, total))
     if rank == 0:
         for r in results:

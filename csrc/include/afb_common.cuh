@@ -94,6 +94,11 @@ AFB_DEVINL int atom_add_acqrel_sys_s32(int* p, int v) {
   asm volatile("atom.acq_rel.sys.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+AFB_DEVINL unsigned int atom_cas_acqrel_sys_u32(unsigned int* p, unsigned int cmp, unsigned int val) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
 AFB_DEVINL void red_add_release_sys_s32(int* p, int v) {
   asm volatile("red.release.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -224,7 +229,7 @@ struct alignas(16) ServerCtl {
   int stop;                        // host/device stop request
   unsigned long long cul_time_ns;  // delay-injector calibration: Σ task time over warm-up updates
   unsigned int cul_count;
-  unsigned int pad;
+  unsigned int wave;               // bucket-gate submission waves (SparkASGDThread.scala:230-234: one job per wave of free workers)
   unsigned long long avg_delay_ns; // calibrated average task time (0 until warm-up done)
   // ---- runtime-adjustable gating (written by the host: watchdog / async_barrier bridge) ------------------------------
   int gate_dyn;                    // > 0: overrides the launch-time bucket threshold when smaller (continue with P-1 workers)

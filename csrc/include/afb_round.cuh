@@ -57,7 +57,8 @@ struct alignas(16) WorkerCtl {      // worker-local control block (device memory
   // ---- robustness -----------------------------------------------------------------------------------------------------
   int abort;                        // != 0: a bounded spin expired (SpinGuard) — results of this launch are invalid
   unsigned int skipped_rounds;      // rounds this worker sat out because its enable-mask bit was clear (ASYNCbarrier)
-  unsigned long long pad_tail;
+  unsigned int wave_seen;           // last bucket-gate wave this worker joined (ServerCtl.wave)
+  unsigned int pad_tail;
 };
 
 // Per-round descriptor of the end-to-end path (FusedEngine.step): written on the host into pinned memory, copied H2D

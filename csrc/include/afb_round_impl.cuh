@@ -59,12 +59,23 @@ AFB_DEVINL void gate_wait_warp(const RoundParams& p, WorkerCtl* wc, const int la
       const unsigned long long ck0 = ld_acquire_sys_u64(&p.sctl->clock_k);
       if (static_cast<long long>(ck0 >> 32) >= p.max_iters || ld_relaxed_sys_s32(&p.sctl->stop)) open = 2;   // stopped: let the pull decide
       else if (p.gate_threshold > 0) {
-        // partial barrier: start only while >= floor(P*beta) workers are idle (this one included); the host watchdog
-        // lowers the threshold when it declares workers dead (continue with P-1)
+        // partial barrier with the reference's WAVE semantics (SparkASGDThread.scala:230-234: the submitter waits until
+        // >= floor(P*beta) workers are free, then submits ONE job to every free worker): the first idle worker to see the
+        // threshold met opens wave w+1 (CAS on ServerCtl.wave); every worker that has not run in the current wave joins it;
+        // a worker that finishes mid-wave waits for the next one.  The host watchdog lowers the threshold when it
+        // declares workers dead (continue with P-1).
         int thr = p.gate_threshold;
         const int dyn = ld_relaxed_sys_s32(&p.sctl->gate_dyn);
         if (dyn > 0 && dyn < thr) thr = dyn;
-        if (ld_relaxed_sys_s32(&p.sctl->avail_count) < thr) open = 0;
+        const unsigned int w = ld_acquire_sys_u32(&p.sctl->wave);
+        if (w != wc->wave_seen) {
+          wc->wave_seen = w;                                   // a wave opened since this worker last ran: join it
+        } else if (ld_relaxed_sys_s32(&p.sctl->avail_count) >= thr) {
+          const unsigned int old = atom_cas_acqrel_sys_u32(&p.sctl->wave, w, w + 1u);
+          wc->wave_seen = (old == w) ? w + 1u : old;           // opened it, or somebody else just did
+        } else {
+          open = 0;
+        }
       }
     }
     open = __shfl_sync(0xffffffffu, open, 0);

@@ -303,3 +303,18 @@ def test_step_descriptor_is_consumed_by_the_kernel():
         assert eng.h2d_bytes_per_step == 16
     assert torch.allclose(upd[1], 2.0 * upd[0], rtol=1e-5, atol=1e-9)
     assert abs(batches[2] / batches[0] - 0.5) < 0.05 and batches[0] == batches[1]
+
+
+def test_objective_evaluation_accepts_bf16_row_storage():
+    """Shards stored with bf16 rows are evaluated through the same kernels (widened chunk by chunk) with identical results."""
+    from asyncframework_b200.data.batch import Shard
+    from asyncframework_b200.data.generators import synthetic_shard
+    from asyncframework_b200.ops.eval import eval_loss
+    from asyncframework_b200.optim.gradient import LOSS_IDS
+    sh = synthetic_shard("mnist8m", 300_000, 0, 1, seed=5, device="cuda", labels="binary01", row_dtype=torch.bfloat16)
+    ref = Shard(sh.num_features, sh.y, sh.X.to(torch.float32))
+    W = torch.randn(sh.num_features, 12, device="cuda") * 1e-3
+    a = eval_loss(sh, W, LOSS_IDS["logistic"])
+    b = eval_loss(ref, W, LOSS_IDS["logistic"])
+    torch.cuda.synchronize()
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
