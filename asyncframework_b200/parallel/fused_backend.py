@@ -347,6 +347,17 @@ class FusedEngine:
     def d2h_bytes_per_step(self) -> int:
         return int(self._ctl_host[0].numel())
 
+    # ------------------------------------------------------------------ side stream (reads / pokes while rounds are running)
+    def side_stream_ctx(self):
+        """Context manager: torch ops inside run on a dedicated NON-BLOCKING stream, so the watchdog / result pump can read
+        and poke the server block while a persistent round kernel occupies the launching stream."""
+        import contextlib
+        if self.device.type != "cuda":
+            return contextlib.nullcontext()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = _dev.new_stream(self.device)
+        return _dev.stream_ctx(self._side_stream, self.device)
+
     # ------------------------------------------------------------------ health, elasticity, resume
     def check_health(self) -> None:
         """Raise if any local worker's kernel gave up on a bounded device-side wait (call after synchronising)."""

@@ -77,13 +77,49 @@ class DeviceWatchdog:
         self.dead: List[int] = []
         self.act = act
 
+    def start(self, period_s: float = 0.2, expect_running: bool = True) -> "DeviceWatchdog":
+        """Poll from a daemon thread (on the engine's side stream: the launching stream may be occupied by a persistent round
+        kernel that is itself waiting for the dead worker)."""
+        self._stop = threading.Event()
+
+        def loop():
+            from ..parallel import _devapi as _dev
+            _dev.set_device(self.engine.device)
+            while not self._stop.wait(period_s):
+                try:
+                    self.check_once(expect_running=expect_running)
+                except Exception as exc:  # noqa: BLE001 — the watchdog must never take the run down
+                    self.error = exc
+        self._thread = threading.Thread(target=loop, name="afb-device-watchdog", daemon=True)
+        self._thread.start()
+        return self
+
+    def stop(self) -> None:
+        if getattr(self, "_stop", None) is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+
     def check_once(self, expect_running: bool = False) -> List[int]:
+        ctx = self.engine.side_stream_ctx() if hasattr(self.engine, "side_stream_ctx") else None
+        if ctx is None:
+            return self._check(expect_running)
+        with ctx:
+            out = self._check(expect_running)
+            if hasattr(self.engine, "_side_stream") and getattr(self.engine, "_side_stream", None) is not None:
+                self.engine._side_stream.synchronize()
+            return out
+
+    def _check(self, expect_running: bool = False) -> List[int]:
         st = self.engine.worker_status()
         newest = int(st["heartbeat_ns"].max())
+        if newest and not getattr(self, "_base_ns", 0):
+            self._base_ns = newest                  # device time of the first sign of life seen by this watchdog
         newly = []
         for p in range(len(st)):
             busy = int(st[p]["available"]) == 0
             hb = int(st[p]["heartbeat_ns"])
+            if not hb and expect_running:
+                hb = getattr(self, "_base_ns", 0)   # a worker that NEVER reported (its process died before its first round)
             if (busy or expect_running) and hb and newest - hb > self.timeout_ns and p not in self.dead:
                 self.dead.append(p)
                 newly.append(p)

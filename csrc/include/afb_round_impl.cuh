@@ -94,6 +94,8 @@ AFB_DEVINL void gate_wait_warp(const RoundParams& p, WorkerCtl* wc, const int la
     if (open) return;
     __nanosleep(200);
     if (sg.expired(p.spin_limit_ns)) { if (lane == 0) raise_abort(wc); return; }
+    // a worker waiting at the gate is alive: keep its heartbeat fresh so the watchdog can tell it from a dead one
+    if (lane == 0 && (sg.n & 1023u) == 0u) (p.status + p.worker_id)->heartbeat_ns = globaltimer_ns();
   }
 }
 
@@ -172,8 +174,10 @@ AFB_DEVINL int round_begin_complete(const RoundParams& p, RoundShared<kThreads>&
         } else if (proceed == PROCEED_SKIP) {
           (p.status + p.worker_id)->heartbeat_ns = globaltimer_ns();
         }
-      } else if (*reinterpret_cast<volatile int*>(&p.sctl->stop) || aborted(wc)) {
-        proceed = PROCEED_STOP;                                   // BSP: the host asked every rank to stop (a worker died)
+      } else {
+        (p.status + p.worker_id)->heartbeat_ns = globaltimer_ns();      // BSP workers report liveness to the server's table too
+        if (*reinterpret_cast<volatile int*>(&p.sctl->stop) || aborted(wc))
+          proceed = PROCEED_STOP;                                 // BSP: the host asked this rank to stop (a peer died)
       }
       wc->ts = ck & 0xffffffffULL;
       wc->k_read = is_async ? (ck >> 32) : round;
@@ -532,6 +536,7 @@ AFB_DEVINL void round_finish(const RoundParams& p, RoundShared<kThreads>& sh, co
       while (ld_acquire_sys_u32(f) != round + 1u) {
         __nanosleep(100);
         if (sg.expired(p.spin_limit_ns) || ((sg.n & 63u) == 1u && *reinterpret_cast<volatile int*>(&p.sctl->stop))) { raise_abort(wc); break; }
+        if (tid == 0 && (sg.n & 1023u) == 0u) (p.status + p.worker_id)->heartbeat_ns = globaltimer_ns();    // waiting, not dead
       }
     }
     if (cta_abort_vote<kThreads>(sh, wc)) {

@@ -46,3 +46,42 @@ def test_fused_paths_on_all_visible_gpus():
     # ASYNCbarrier on the fused path: the masked worker sat every round out, the others ran theirs
     assert out["p_masked_k"] == R * (n - 1) and out["p_masked_workers_seen"] == list(range(n - 1))
     assert out["p_masked_skipped"] == [0] * (n - 1) + [R] and out["p_masked_avail"] == n
+
+
+def _spawn_pair(mode, port):
+    here = os.path.dirname(os.path.abspath(__file__))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   TORCH_NCCL_ASYNC_ERROR_HANDLING="0", NCCL_ASYNC_ERROR_HANDLING="0")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "mg_elastic.py"), mode], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    try:
+        out0, err0 = procs[0].communicate(timeout=150)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    rc1 = procs[1].wait(timeout=30)
+    line = [l for l in out0.splitlines() if l.startswith("ELASTIC_RESULT ")]
+    assert line, out0[-1500:] + err0[-3000:]
+    return json.loads(line[0][len("ELASTIC_RESULT "):]), rc1
+
+
+@pytest.mark.timeout(200)
+def test_async_run_continues_with_p_minus_1_when_a_rank_dies():
+    """SIGKILL one rank mid-run: the server's watchdog declares its worker dead on the device (alive = 0, gate threshold
+    lowered) and the asynchronous run still reaches the target number of accepted updates with the surviving worker."""
+    out, rc1 = _spawn_pair("async", 29571)
+    assert rc1 == -9, out                                    # the rank really died by SIGKILL
+    assert out["raised"] is None and out["k"] >= 200_000 and out["finite"], out
+    assert out["dead"] == [1] and out["alive_flags"] == [1, 0] and out["num_alive"] == 1 and out["gate_dyn"] == 1
+
+
+@pytest.mark.timeout(200)
+def test_sync_run_aborts_cleanly_when_a_rank_dies():
+    """BSP: a dead peer can never deliver its gradient slot — the watchdog stops the local rounds, the in-kernel flag wait
+    observes the stop word, the kernel exits with the abort flag and the driver raises (no hang)."""
+    out, rc1 = _spawn_pair("sync", 29572)
+    assert rc1 == -9, out
+    assert out["raised"] is not None and out["abort"] == 1 and out["dead"] == [1] and out["elapsed_s"] < 30, out
