@@ -38,22 +38,29 @@ struct RowScheduler {
   int base;                 // first row of the current chunk
   unsigned int next_chunk;  // prefetched chunk id
   int n_big;                // number of 64-row chunks
-  int num_chunks;           // total chunks (big + small)
+  int n_mid;                // number of 32-row chunks (between the big and the small ones)
+  int num_chunks;           // total chunks (big + medium + small)
   unsigned int static_chunks;
   unsigned int thr24;       // Bernoulli threshold of this round (launch scalar or the round descriptor's)
 };
 
 constexpr int kSmallChunkRows = 16;
+constexpr int kMidChunkRows = 32;
 
 AFB_DEVINL void sched_init(RowScheduler& s, int n_rows, unsigned int total_warps, unsigned int gwarp, int thr24 = -1) {
   s.thr24 = static_cast<unsigned int>(thr24);      // callers pass eff_thr24(p, round); -1 = "use p.thr24" (set below by load_chunk_masks)
-  // small-chunk region: ~2 small chunks per warp at the very end of the shard (never more than 1/4 of it)
+  // guided self-scheduling in three tiers: 64-row chunks, then ~2 chunks of 32 rows per warp, then ~2 chunks of 16 rows per
+  // warp at the very end of the shard (never more than 1/4 of it for the two tail tiers together): a warp that draws its
+  // last chunk late is at most a few sampled rows behind the others when they meet at the CTA reduce
   long long small_rows = static_cast<long long>(total_warps) * 2 * kSmallChunkRows;
-  if (small_rows > n_rows / 4) small_rows = n_rows / 4;
-  const int big_rows = n_rows - static_cast<int>(small_rows);
-  s.n_big = big_rows / kChunkRows;
-  const int rest = n_rows - s.n_big * kChunkRows;
-  s.num_chunks = s.n_big + (rest + kSmallChunkRows - 1) / kSmallChunkRows;
+  long long mid_rows = static_cast<long long>(total_warps) * 2 * kMidChunkRows;
+  if (small_rows + mid_rows > n_rows / 4) { small_rows = n_rows / 12; mid_rows = n_rows / 6; }
+  mid_rows = mid_rows / kMidChunkRows * kMidChunkRows;
+  const int big_rows = n_rows - static_cast<int>(small_rows) - static_cast<int>(mid_rows);
+  s.n_big = big_rows > 0 ? big_rows / kChunkRows : 0;
+  s.n_mid = static_cast<int>(mid_rows / kMidChunkRows);
+  const int rest = n_rows - s.n_big * kChunkRows - s.n_mid * kMidChunkRows;
+  s.num_chunks = s.n_big + s.n_mid + (rest + kSmallChunkRows - 1) / kSmallChunkRows;
   s.static_chunks = total_warps;
   s.m0 = s.m1 = 0; s.base = 0;
   s.next_chunk = gwarp;                       // first unit: no atomic
@@ -68,8 +75,10 @@ AFB_DEVINL unsigned int fetch_chunk(unsigned int* ctr, int lane, unsigned int st
 AFB_DEVINL void load_chunk_masks(RowScheduler& s, const RoundParams& p, unsigned int chunk, int lane,
                                  unsigned long long key) {
   int size;
-  if (static_cast<int>(chunk) < s.n_big) { s.base = static_cast<int>(chunk) * kChunkRows; size = kChunkRows; }
-  else { s.base = s.n_big * kChunkRows + (static_cast<int>(chunk) - s.n_big) * kSmallChunkRows; size = kSmallChunkRows; }
+  const int c = static_cast<int>(chunk);
+  if (c < s.n_big) { s.base = c * kChunkRows; size = kChunkRows; }
+  else if (c < s.n_big + s.n_mid) { s.base = s.n_big * kChunkRows + (c - s.n_big) * kMidChunkRows; size = kMidChunkRows; }
+  else { s.base = s.n_big * kChunkRows + s.n_mid * kMidChunkRows + (c - s.n_big - s.n_mid) * kSmallChunkRows; size = kSmallChunkRows; }
   int r0 = s.base + lane, r1 = s.base + 32 + lane;
   bool s0 = false, s1 = false;
   const unsigned int thr = (s.thr24 == 0xffffffffu) ? static_cast<unsigned int>(p.thr24) : s.thr24;

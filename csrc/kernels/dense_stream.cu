@@ -607,10 +607,22 @@ AFB_DEVINL int stream_round_pipe(const RoundParams& p, RoundShared<kStreamThread
   // ---- phase 1: fused gradient; the warp that draws one of the last chunk ids pulls round r+1's parameters ahead
   f32x2 wreg[NV][RowElems<BF16>::kP];
   load_w_regs<NV, BF16>(wreg, w_loc, nchunks, lane);
-  const unsigned int dyn_chunks = rs.sch.num_chunks > static_cast<int>(rs.sch.static_chunks)
-                                      ? static_cast<unsigned int>(rs.sch.num_chunks) - rs.sch.static_chunks : 0u;
-  const unsigned int ahead = static_cast<unsigned int>(p.pull_ahead_chunks);
-  const unsigned int trigger = rs.sch.static_chunks + (dyn_chunks > ahead ? dyn_chunks - ahead : 0u);
+  // pull-ahead trigger: the chunk id from which `pull_ahead_chunks` x 64 raw rows remain in the pool (the pool ends with
+  // the 32- and 16-row tiers of the guided schedule, so the id is found by walking the tiers from the end)
+  unsigned int trigger;
+  {
+    long long rows_left = static_cast<long long>(p.pull_ahead_chunks) * kChunkRows;
+    const int n_small = rs.sch.num_chunks - rs.sch.n_big - rs.sch.n_mid;
+    long long from_end = 0;
+    long long take = rows_left / kSmallChunkRows; if (take > n_small) take = n_small;
+    from_end += take; rows_left -= take * kSmallChunkRows;
+    take = rows_left / kMidChunkRows; if (take > rs.sch.n_mid) take = rs.sch.n_mid;
+    from_end += take; rows_left -= take * kMidChunkRows;
+    take = rows_left / kChunkRows; if (take > rs.sch.n_big) take = rs.sch.n_big;
+    from_end += take;
+    const long long id = static_cast<long long>(rs.sch.num_chunks) - from_end;
+    trigger = static_cast<unsigned int>(id > static_cast<long long>(rs.sch.static_chunks) ? id : static_cast<long long>(rs.sch.static_chunks));
+  }
   const bool ahead_armed = (p.pull_ahead_chunks > 0) && (it + 1 < rounds) && (p.delay_mode == 0);
   stream_rows<NV, kDepth, BF16>(rs, rg, p, &S->chunk_ctr, key, wreg, phase, true, false, lane, ahead_armed ? trigger : 0xffffffffu, [&]() {
     // one attempt per warp and round.  Buffer (r+1)&1 is free once round r-1 has been published; otherwise the regular
