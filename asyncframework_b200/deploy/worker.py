@@ -40,11 +40,11 @@ class ExecutorRunner:
         cmd = [sys.executable, "-m", "asyncframework_b200.deploy.executor", "--driver-url", self.driver_url,
                "--executor-id", str(self.exec_id), "--slot", str(self.slot), "--cores", str(self.cores),
                "--app-id", self.app_id, "--worker-url", str(self.worker.rpc_env.address), "--host", self.worker.host]
-        if self.worker.secret:
-            cmd += ["--secret", self.worker.secret]
         if self.worker.encrypt:
             cmd += ["--encrypt"]
         env = dict(os.environ)
+        if self.worker.secret:
+            env["AFB_RPC_SECRET"] = self.worker.secret           # never in argv: `ps` shows command lines to every local user
         root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
         env["AFB_EXECUTOR_MEMORY_MB"] = str(self.memory_mb)

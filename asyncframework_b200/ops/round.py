@@ -378,6 +378,13 @@ class RoundKernel:
         self.stream_csr = bool(wide and not self.rollback and variant != "simple" and (self.sim or hasattr(self.lib, "afb_csr_stream_launch")))
         if self.stream_csr and not self.sim:
             self._grid_bar = torch.zeros(self.lib.afb_grid_bar_bytes(), dtype=torch.uint8, device=dev)
+            if not grid:
+                # a wide-model round is a few thousand sampled rows: its cost is the three in-kernel grid barriers (one
+                # same-address arrival per CTA each) and the NVLink round trips, not the arithmetic — size the grid by the
+                # work (~64 sampled rows per 16-warp CTA, every thread still moves one float4 of the pull / push)
+                want = int(math.ceil(batch_rate * shard.num_rows / 64.0))
+                need_comm = int(math.ceil(ld / 4 / 512.0))           # CTAs needed for one float4 per thread
+                self.grid = int(os.environ.get("AFB_CSR_GRID", max(32, min(self.grid, max(want, min(need_comm, self.num_sms))))))
         self.launches = 0
         self.rounds_launched = 0
         if self.sim:

@@ -352,10 +352,14 @@ class RpcEnv:
                  secret: Optional[str] = None, connect_timeout: float = 10.0, encrypt: bool = False):
         global _default_env
         self.name = name
+        if secret is None:
+            secret = os.environ.get("AFB_RPC_SECRET") or None      # the secret never travels in argv (visible to `ps`)
         self.secret = secret.encode() if isinstance(secret, str) else secret
         if encrypt and not self.secret:
             raise ValueError("encrypt=True needs a shared secret (spark.authenticate.secret)")
-        self.encrypt = bool(encrypt)
+        # with a secret, EVERY frame after the handshake is authenticated: AES-GCM per direction (a MAC-only mode would need a
+        # second framing; encryption is cheap next to pickling), so `encrypt` is implied by `secret`
+        self.encrypt = bool(encrypt) or bool(self.secret)
         self.connect_timeout = connect_timeout
         self._inboxes: Dict[str, _Inbox] = {}
         self._conns: Dict[RpcAddress, _Connection] = {}
@@ -372,6 +376,10 @@ class RpcEnv:
             srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
             srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
             srv.bind((host, port))
+            if not self.secret and host not in ("127.0.0.1", "localhost", "::1"):
+                import warnings
+                warnings.warn(f"RpcEnv {name!r} listens on {host} WITHOUT a shared secret: any peer that can reach the port can "
+                              "send pickled messages (set spark.authenticate.secret / AFB_RPC_SECRET)", RuntimeWarning, stacklevel=2)
             srv.listen(128)
             self._server = srv
             self.address = RpcAddress(host, srv.getsockname()[1])
@@ -497,12 +505,22 @@ class RpcEnv:
                 if ftype != F_CHALLENGE:
                     raise RpcError(f"bad handshake from {address}")
                 nonce = bytes(body)
-                proof = hmac.new(self.secret, nonce, hashlib.sha256).digest() if self.secret else b""
+                # MUTUAL, direction-labelled, session-bound authentication: each side proves the secret over BOTH nonces with
+                # its own label, so a proof cannot be relayed to another server (different server nonce) nor reflected back
+                # (different label), and a rogue server that does not know the secret is rejected before any reply is unpickled
+                cnonce = os.urandom(16)
+                proof = hmac.new(self.secret, b"afb-rpc-client|" + nonce + cnonce, hashlib.sha256).digest() if self.secret else b""
                 conn.send_frame(F_HELLO, 0, json.dumps({"addr": list(self.address) if self.address else None,
-                                                        "proof": proof.hex(), "enc": self.encrypt}).encode())
+                                                        "proof": proof.hex(), "cnonce": cnonce.hex(), "enc": self.encrypt}).encode())
                 ftype, _, body = conn.recv_frame()
-                if ftype != F_HELLO_ACK or bytes(body) not in (b"ok", b"ok+enc"):
+                status, _, sproof = bytes(body).partition(b"|")
+                if ftype != F_HELLO_ACK or status not in (b"ok", b"ok+enc"):
                     raise RpcError(f"{address} rejected the handshake: {bytes(body).decode(errors='replace')}")
+                if self.secret:
+                    want = hmac.new(self.secret, b"afb-rpc-server|" + nonce + cnonce, hashlib.sha256).hexdigest().encode()
+                    if not hmac.compare_digest(want, sproof):
+                        raise RpcError(f"{address} did not prove knowledge of the shared secret (rogue or misconfigured server)")
+                body = status
                 if bytes(body) == b"ok+enc":
                     conn.enable_encryption(self.secret, nonce, dialed=True)
                 elif self.encrypt:
@@ -542,21 +560,24 @@ class RpcEnv:
             hello = json.loads(bytes(body).decode())
             advertised = tuple(hello["addr"]) if hello.get("addr") else None
             proof, wants_enc = bytes.fromhex(hello.get("proof", "")), bool(hello.get("enc", False))
+            cnonce = bytes.fromhex(hello.get("cnonce", ""))
             if advertised is not None and not (isinstance(advertised[0], str) and isinstance(advertised[1], int)):
                 raise RpcError("malformed HELLO")
+            sproof = b""
             if self.secret is not None:
-                want = hmac.new(self.secret, nonce, hashlib.sha256).digest()
-                if not hmac.compare_digest(want, proof):
+                want = hmac.new(self.secret, b"afb-rpc-client|" + nonce + cnonce, hashlib.sha256).digest()
+                if len(cnonce) != 16 or not hmac.compare_digest(want, proof):
                     conn.send_frame(F_HELLO_ACK, 0, b"authentication failed")
                     raise RpcError("authentication failed")
+                sproof = b"|" + hmac.new(self.secret, b"afb-rpc-server|" + nonce + cnonce, hashlib.sha256).hexdigest().encode()
             if self.encrypt and not wants_enc:
                 conn.send_frame(F_HELLO_ACK, 0, b"this endpoint requires encryption")
                 raise RpcError("peer did not ask for encryption")
             if (wants_enc or self.encrypt) and self.secret is not None:
-                conn.send_frame(F_HELLO_ACK, 0, b"ok+enc")
+                conn.send_frame(F_HELLO_ACK, 0, b"ok+enc" + sproof)
                 conn.enable_encryption(self.secret, nonce, dialed=False)
             else:
-                conn.send_frame(F_HELLO_ACK, 0, b"ok")
+                conn.send_frame(F_HELLO_ACK, 0, b"ok" + sproof)
         except BaseException:  # noqa: BLE001
             conn.close()
             return

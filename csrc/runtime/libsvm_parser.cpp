@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cerrno>
 #include <cmath>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -35,8 +36,8 @@ struct Chunk {
   std::vector<int32_t> indices;
   std::vector<double> values;
   int32_t max_index = -1;
-  std::string error;
-  int64_t first_line = 0;
+  std::string error;          // "{LINE}" is replaced by the absolute line number by afb_libsvm_parse
+  int64_t error_line = 0;     // line of the error, relative to the chunk (1-based)
 };
 
 // A parsed file stays in its per-thread chunks; afb_libsvm_copy() scatters them straight into the caller's arrays
@@ -132,7 +133,8 @@ void parse_range(const char* data, size_t begin, size_t end, Chunk* out) {
     while (t < e && *t != ' ') ++t;
     double label;
     if (!parse_double(b, t, &label)) {
-      out->error = "bad label at line " + std::to_string(line_no) + " of chunk: '" + std::string(b, t) + "'";
+      out->error = "bad label at line {LINE}: '" + std::string(b, t) + "'";
+      out->error_line = line_no;
       return;
     }
     out->labels.push_back(label);
@@ -164,14 +166,22 @@ void parse_range(const char* data, size_t begin, size_t end, Chunk* out) {
       while (t < e && *t != ' ') ++t;
       double val;
       if (!ok || !parse_double(colon + 1, t, &val)) {
-        out->error = "bad index:value token '" + std::string(b, t) + "' at line " + std::to_string(line_no) + " of chunk";
+        out->error = "bad index:value token '" + std::string(b, t) + "' at line {LINE}";
+        out->error_line = line_no;
         return;
       }
       int64_t idx0 = idx1 - 1;  // 1-based -> 0-based
       if (!(idx0 > prev)) {
         out->error = "indices should be one-based and in ascending order; found current=" +
-                     std::to_string(idx0) + ", previous=" + std::to_string(prev) +
-                     " at line " + std::to_string(line_no) + " of chunk";
+                     std::to_string(idx0) + ", previous=" + std::to_string(prev) + " at line {LINE}";
+        out->error_line = line_no;
+        return;
+      }
+      if (idx0 > static_cast<int64_t>(INT32_MAX)) {
+        // MLlib's `toInt` fails on such an index; narrowing it silently would wrap to a small or negative column and let the
+        // gather / scatter kernels go out of bounds
+        out->error = "feature index " + std::to_string(idx1) + " does not fit a 32-bit column id at line {LINE}";
+        out->error_line = line_no;
         return;
       }
       prev = idx0;
@@ -226,6 +236,21 @@ void* afb_libsvm_parse(const char* path, int num_threads, char* err, int errlen)
   for (int t = 0; t < T; ++t)
     threads.emplace_back(parse_range, data, cuts[t], cuts[t + 1], &chunks[t]);
   for (auto& th : threads) th.join();
+  // errors carry ABSOLUTE line numbers: lines before the failing chunk are counted here (error path only)
+  for (int t = 0; t < T; ++t) {
+    if (chunks[t].error.empty()) continue;
+    int64_t before = 0;
+    for (const char* q = data; q < data + cuts[t]; ) {
+      const void* nl = memchr(q, '\n', static_cast<size_t>(data + cuts[t] - q));
+      if (!nl) break;
+      ++before;
+      q = static_cast<const char*>(nl) + 1;
+    }
+    std::string& msg = chunks[t].error;
+    const size_t at = msg.find("{LINE}");
+    if (at != std::string::npos) msg.replace(at, 6, std::to_string(before + chunks[t].error_line));
+    break;                                       // the first failing chunk in file order is the one reported
+  }
   munmap(map, size);
 
   for (auto& c : chunks) {

@@ -22,6 +22,13 @@ if what in ("csr", "csr_split"):
     for _ in range(3):
         rk.launch_rounds(8)
     torch.cuda.synchronize()
+    if len(sys.argv) > 2 and sys.argv[2] == "time":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rk.launch_rounds(400)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"CSR_ROUND_US grid={rk.grid} variant={rk.variant_effective} {e0.elapsed_time(e1) * 1e3 / 400:.2f}")
     print("k", blk.read_sctl()["k"], rk.variant_effective)
 elif what == "eval":
     from asyncframework_b200.data.generators import synthetic_shard

@@ -275,3 +275,71 @@ def test_bf16_row_storage_on_the_simulator_is_exact_for_integer_pixels():
         eng.run_rounds(4)
         outs.append(eng.weights().clone())
     assert torch.equal(outs[0], outs[1]) and outs[0].abs().sum() > 0
+
+
+@pytest.mark.parametrize("alg,step", [("sgd_sync", 1.0), ("saga_sync", 0.3), ("asgd", 1.0)])
+def test_fused_resume_is_exact_and_num_iterations_is_a_total(alg, step, tmp_path):
+    """A run interrupted at k = 40 and resumed to a total of 80 ends on exactly the weights of an uninterrupted 80-iteration run:
+    the accepted-update counter, the logical clock and the per-worker round counters are restored, so the step-size schedule
+    (gamma / sqrt(round + 1), gamma / sqrt(floor(k / P) + 1)) and the seed + round + 1 sampling sequence continue."""
+    from asyncframework_b200.utils import load_checkpoint
+    base = dict(algorithm=alg, synthetic="linear", num_rows=1500, num_features=10, num_partitions=1, step_size=step, batch_rate=0.3,
+                printer_freq=1000, backend="fused", loss="least_squares", barrier="asp", rounds_per_graph=4, layout="dense",
+                eval_objective=False, quiet=True)
+    full = algo.run(AsyncConfig(num_iterations=80, **base))
+    part = algo.run(AsyncConfig(num_iterations=40, checkpoint_dir=str(tmp_path / "ck"), checkpoint_every=40, **base))
+    ck = load_checkpoint(str(tmp_path / "ck"))
+    assert ck["k"] == 40 and ck["extra"]["rounds"] == [40]
+    assert not torch.equal(part.final_weights, full.final_weights)
+    resumed = algo.run(AsyncConfig(num_iterations=80, resume=str(tmp_path / "ck"), **base))
+    assert resumed.iterations == 80
+    assert torch.allclose(resumed.final_weights, full.final_weights, rtol=0, atol=0), (resumed.final_weights - full.final_weights).abs().max()
+    # num_iterations is a TOTAL: resuming with a target already reached runs nothing more
+    again = algo.run(AsyncConfig(num_iterations=40, resume=str(tmp_path / "ck"), **base))
+    assert torch.equal(again.final_weights, part.final_weights)
+
+
+def test_predicate_mask_and_declare_dead_on_the_simulator():
+    """ASYNCbarrier on the fused path (host-evaluated predicate -> device enable mask) and the continue-with-P-1 bookkeeping:
+    masked workers skip their rounds, a worker declared dead leaves the idle count / the mask and lowers the bucket threshold."""
+    P, d, n = 4, 8, 300
+    parts = _parts(P, n, d, 2, True)
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n * P, num_partitions=P, num_iterations=1 << 30, step_size=0.5,
+                      batch_rate=0.5, loss="logistic", backend="fused", barrier="bucket", bucket_ratio=0.75)
+    eng = FusedEngine(cfg, [_shard(parts[p], d, p) for p in range(P)], n * P, list(range(P)), device="cpu", worker_mask=True)
+    assert eng.gate_threshold == 3 and all(rk.params.use_mask == 1 and not rk.pipelined for rk in eng.kernels)
+    eng.run_rounds(2)
+    assert eng.server_state()["k"] == 2 * P
+    # predicate over the mirrored WorkerState table: only workers 0 and 2 take part in the next rounds
+    sel = eng.async_barrier(lambda st: st.worker_id % 2 == 0 if hasattr(st, "worker_id") else True)
+    eng.set_worker_mask([True, False, True, False])
+    eng.run_rounds(3)
+    st = eng.server_state()
+    assert st["k"] == 2 * P + 3 * 2
+    skipped = [int(rk.read_ctl()["skipped_rounds"]) for rk in eng.kernels]
+    assert skipped == [0, 3, 0, 3]
+    # worker 3 is declared dead while idle: the idle count drops, the threshold follows floor(P_alive * beta), its bit stays clear
+    eng.set_worker_mask([True] * P)
+    eng.declare_dead(3)
+    st = eng.server_state()
+    assert st["avail_count"] == P - 1 and st["num_alive"] == 3 and st["gate_dyn"] == 2
+    assert int(eng.worker_status()[3]["alive"]) == 0 and (st["enable_mask"][0] & 0b1000) == 0
+    eng.run_rounds(2)
+    assert eng.server_state()["k"] == 2 * P + 3 * 2 + 2 * 3          # the three live workers keep going
+
+
+def test_regularised_fused_rounds_on_the_simulator_match_the_updater_formulas():
+    """reg_param / updater reach the fused backend (K8 fused into the apply): BSP rounds with the squared-L2 / L1 updaters
+    shrink the weights exactly like SquaredL2Updater / L1Updater (Updater.scala:114-158)."""
+    d, n = 10, 400
+    parts = _parts(1, n, d, 4, False)
+    outs = {}
+    for upd, lam in (("simple", 0.0), ("squared_l2", 0.5), ("l1", 0.05)):
+        cfg = AsyncConfig(algorithm="sgd_sync", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=0.2,
+                          batch_rate=0.5, loss="least_squares", backend="fused", updater=upd, reg_param=lam)
+        eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+        assert eng.kernels[0].params.reg_type == {"simple": 0, "squared_l2": 1, "l1": 2}[upd]
+        eng.run_rounds(25)
+        outs[upd] = eng.weights().clone()
+    assert outs["squared_l2"].norm() < 0.9 * outs["simple"].norm()
+    assert int((outs["l1"] == 0).sum()) >= int((outs["simple"] == 0).sum()) and outs["l1"].abs().sum() < outs["simple"].abs().sum()

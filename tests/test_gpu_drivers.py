@@ -130,7 +130,7 @@ def test_fused_checkpoint_and_resume(tmp_path):
     rep = algo.run(cfg)
     ck = load_checkpoint(str(tmp_path / "ck"))
     assert ck["k"] >= 100 and ck["alpha_bar"] is not None and sorted(ck["history"]) == [0, 1]
-    cfg2 = AsyncConfig(num_iterations=100, resume=str(tmp_path / "ck"), **base)
+    cfg2 = AsyncConfig(num_iterations=300, resume=str(tmp_path / "ck"), **base)      # num_iterations is a TOTAL: 100 more than the checkpoint
     rep2 = algo.run(cfg2)
     # resumed run starts from the checkpointed model: its first objective is far below the cold-start one
     assert rep2.objective[0][1] < 0.5 * rep.objective[0][1]

@@ -129,3 +129,20 @@ def test_native_parser_rejects_malformed_tokens(tmp_path, bad):
     path.write_text("1 1:1\n" + bad + "\n")
     with pytest.raises(ValueError):
         parse_libsvm_file_csr(str(path))
+
+
+def test_native_parser_rejects_indices_beyond_int32_and_reports_absolute_line_numbers(tmp_path):
+    """A feature index above 2^31 must fail like MLlib's `toInt` (not wrap to a small / negative column), and parse errors
+    carry the line number in the FILE even when the file is parsed in parallel chunks."""
+    from asyncframework_b200.data.libsvm import parse_libsvm_file_csr as load_libsvm_file_native
+    good = "1 1:0.5 3:1.5\n"
+    p = tmp_path / "big.libsvm"
+    p.write_text(good * 4000 + "0 2:1.0 3000000000:2.0\n" + good * 10)
+    with pytest.raises(ValueError) as ei:
+        load_libsvm_file_native(str(p), num_threads=4)
+    assert "32-bit" in str(ei.value) and "line 4001" in str(ei.value)
+    q = tmp_path / "order.libsvm"
+    q.write_text(good * 7000 + "1 5:1.0 2:1.0\n")
+    with pytest.raises(ValueError) as ei:
+        load_libsvm_file_native(str(q), num_threads=4)
+    assert "ascending" in str(ei.value) and "line 7001" in str(ei.value)

@@ -256,11 +256,11 @@ def test_aes_gcm_encryption_hides_payloads_and_rejects_tampering():
         with pytest.raises(RpcError):
             ref.ask_sync(b"x" * 100, timeout=3)                                        # authentication fails -> connection dropped
         client.shutdown()
-        # a peer that does not ask for encryption is refused by an encrypt-only server; plaintext servers accept both
-        plain = RpcEnv("p", server=False, secret="k")
-        with pytest.raises(RpcError, match="requires encryption"):
-            plain.endpoint_ref(server.address, "echo").ask_sync(1, timeout=3)
-        plain.shutdown()
+        # a shared secret implies encryption: an env built with only ``secret=`` never sends plaintext frames
+        implied = RpcEnv("p", server=False, secret="k")
+        assert implied.encrypt
+        assert implied.endpoint_ref(server.address, "echo").ask_sync(1, timeout=3) == ("echo", 1)
+        implied.shutdown()
     with pytest.raises(ValueError):
         RpcEnv("x", server=False, encrypt=True)
 
