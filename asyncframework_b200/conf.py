@@ -128,6 +128,18 @@ METRICS_CONF = _entry("spark.metrics.conf", str, "", "path of a metrics.properti
 LOCALITY_WAIT = _entry("spark.locality.wait", parse_time, 3.0, "accepted for compatibility: shard->executor affinity is hard here, nothing waits")
 DEFAULT_PARALLELISM = _entry("spark.default.parallelism", int, 0, "default number of partitions (0 = number of executors)", _nonneg)
 BLOCK_FIRST_ASYNC = _entry("spark.async.blockFirstJob", _parse_bool, True, "reproduce the reference's blocking first async job (SURVEY B.4)")
+SHUFFLE_MEMORY = _entry("spark.shuffle.spill.memoryThreshold", parse_size, 256 << 20,
+                        "estimated bytes a shuffle sorter / combine map holds before it spills a sorted run (ExternalSorter.scala:89)", _pos)
+SHUFFLE_FORCE_SPILL = _entry("spark.shuffle.spill.numElementsForceSpillThreshold", int, 0, "spill after this many in-memory records (0 = off)", _nonneg)
+SHUFFLE_SPILL_BATCH = _entry("spark.shuffle.spill.batchSize", int, 10000, "records per serialized batch of a spill file", _pos)
+SHUFFLE_SPILL_COMPRESS = _entry("spark.shuffle.spill.compress", _parse_bool, True, "compress spill files")
+DYN_ALLOC = _entry("spark.dynamicAllocation.enabled", _parse_bool, False, "grow / shrink the executor set with the task backlog (ExecutorAllocationManager.scala:228)")
+DYN_ALLOC_MIN = _entry("spark.dynamicAllocation.minExecutors", int, 1, "lower bound of the executor target", _pos)
+DYN_ALLOC_MAX = _entry("spark.dynamicAllocation.maxExecutors", int, 1 << 30, "upper bound of the executor target", _pos)
+DYN_ALLOC_INITIAL = _entry("spark.dynamicAllocation.initialExecutors", int, 0, "initial executor target (0 = minExecutors)", _nonneg)
+DYN_ALLOC_BACKLOG = _entry("spark.dynamicAllocation.schedulerBacklogTimeout", parse_time, 1.0, "backlog must persist this long before executors are added", _pos)
+DYN_ALLOC_SUSTAINED = _entry("spark.dynamicAllocation.sustainedSchedulerBacklogTimeout", parse_time, 1.0, "interval of the following (doubling) additions", _pos)
+DYN_ALLOC_IDLE = _entry("spark.dynamicAllocation.executorIdleTimeout", parse_time, 60.0, "remove an executor that ran no task for this long", _pos)
 RECOVER_EXECUTORS = _entry("spark.async.recoverLostExecutors", _parse_bool, True, "replace a lost executor and re-run its tasks instead of failing the job")
 
 DEPRECATED = {      # old key -> (new key, version it changed in), SparkConf.deprecatedConfigs / configsWithAlternatives
@@ -290,7 +302,10 @@ class AsyncConf:
             local_dir=g("spark.local.dir") or None, network_timeout=g("spark.network.timeout"),
             heartbeat_interval=g("spark.executor.heartbeatInterval"),
             auth_secret=(g("spark.authenticate.secret") or None) if g("spark.authenticate") else None,
-            encrypt=bool(g("spark.network.crypto.enabled") and g("spark.authenticate")))
+            encrypt=bool(g("spark.network.crypto.enabled") and g("spark.authenticate")),
+            shuffle_memory=g("spark.shuffle.spill.memoryThreshold"),
+            shuffle_spill_elements=g("spark.shuffle.spill.numElementsForceSpillThreshold"),
+            shuffle_spill_batch=g("spark.shuffle.spill.batchSize"), shuffle_spill_compress=g("spark.shuffle.spill.compress"))
 
     @staticmethod
     def describe() -> str:

@@ -57,6 +57,22 @@ def thread_dump() -> List[dict]:
 
 
 # =================================================================================================== executor side
+class TaskKilled(BaseException):
+    """Raised INSIDE a running task when the driver kills that attempt (``TaskKilledException``; the reference interrupts
+    the task thread, executor/Executor.scala:223-243 ``kill(interruptThread)``).  A BaseException so that a task's own
+    ``except Exception`` blocks do not swallow it."""
+
+
+def _interrupt_thread(thread_id: int, exc_type) -> bool:
+    """``Thread.interrupt`` for a python thread: the exception is raised at that thread's next bytecode boundary (a task
+    blocked inside a C call sees it when the call returns)."""
+    import ctypes
+    n = ctypes.pythonapi.PyThreadState_SetAsyncExc(ctypes.c_ulong(thread_id), ctypes.py_object(exc_type))
+    if n > 1:                                          # "should never happen": undo
+        ctypes.pythonapi.PyThreadState_SetAsyncExc(ctypes.c_ulong(thread_id), None)
+    return n == 1
+
+
 class ExecutorBackend:
     """Transport-agnostic executor.  Feed it driver messages with :meth:`handle` (from a receiver thread / an RPC
     inbox) and run :meth:`run_tasks` on the task thread; status messages leave through ``send``.
@@ -73,6 +89,10 @@ class ExecutorBackend:
         self.tasks: "_queue.Queue" = _queue.Queue()
         self._send_lock = threading.Lock()
         self.tasks_run = 0
+        self.tasks_killed = 0
+        self._run_lock = threading.Lock()
+        self._running: Dict[tuple, tuple] = {}       # (job, partition, attempt) -> (thread id, TaskContext) while the body runs
+        self._kill_requests: set = set()             # attempts killed before they left the queue
 
     def send(self, msg: tuple) -> None:
         with self._send_lock:
@@ -93,12 +113,27 @@ class ExecutorBackend:
             self.binaries.pop(msg[1], None)
         elif kind == "task":
             self.tasks.put(msg)
+        elif kind == "kill_task":                        # TaskSetManager.scala:736: the other copy of this task won
+            self.kill_task(msg[1], msg[2], msg[3])
         elif kind == "drop_source":                      # ContextCleaner: the driver's copy of this source block is gone
             from ..data.dataset import drop_source_block
             drop_source_block(msg[1])
         elif kind == "thread_dump":                      # ExecutorThreadDumpPage: answered by the receiver thread, even mid-task
             self.send(("threads", -1, -1, msg[1], thread_dump(), 0.0))
         return True
+
+    def kill_task(self, job_id: int, partition: int, attempt: int) -> None:
+        """Interrupt one attempt: running -> ``TaskKilled`` is raised in its thread (and ``TaskContext.is_cancelled()`` turns
+        true for cooperative bodies); still queued -> it is skipped when it reaches the head of the queue."""
+        key = (job_id, partition, attempt)
+        with self._run_lock:
+            running = self._running.get(key)
+            if running is None:
+                self._kill_requests.add(key)
+                return
+            tid, tctx = running
+            tctx.killed = True
+            _interrupt_thread(tid, TaskKilled)
 
     def close(self) -> None:
         self._closed = True
@@ -148,22 +183,38 @@ class ExecutorBackend:
             if binary is None:                        # job finished or cancelled while this task was queued
                 self.send(("gone", job_id, partition, attempt, "", 0.0))
                 continue
+            key = (job_id, partition, attempt)
+            with self._run_lock:
+                if key in self._kill_requests:            # killed while it was still queued
+                    self._kill_requests.discard(key)
+                    self.tasks_killed += 1
+                    self.send(("killed", job_id, partition, attempt, "before start", 0.0))
+                    continue
             self.send(("started", job_id, partition, attempt, "", 0.0))     # queued != running: speculation needs to know
             self.active_task = (job_id, partition, attempt)
+            registered = False
             try:
                 if isinstance(binary, BaseException):
                     raise binary
                 dataset, func, fault = binary
                 tctx = TaskContext(job_id, partition, attempt, self.eid, None, None, submit_ms)
+                with self._run_lock:
+                    self._running[key] = (threading.get_ident(), tctx)
+                    registered = True
                 _acc.begin_task()
                 if fault is not None:
                     fault(tctx)
                 result = func(tctx, dataset.iterator(partition, tctx))
+                with self._run_lock:                      # past this point a kill can no longer interrupt the thread
+                    self._running.pop(key, None)
+                    registered = False
                 t1 = time.perf_counter()
                 data = cloudpickle.dumps((result, _acc.end_task(True)))      # accumulator updates ride with the result
                 t2 = time.perf_counter()
                 # TaskMetrics (executor/TaskMetrics.scala): executorRunTime, resultSerializationTime
                 run_ms = {"run_ms": (t1 - t0) * 1e3, "serialize_ms": (t2 - t1) * 1e3}
+                # what the task recorded itself: memoryBytesSpilled / diskBytesSpilled / peakExecutionMemory of its sorters
+                run_ms.update({k: v for k, v in tctx.metrics.items() if isinstance(v, (int, float)) and k not in run_ms})
                 self.tasks_run += 1
                 env = AsyncEnv.get()
                 if env is not None and len(data) > env.limits.max_direct_result_size:
@@ -172,10 +223,17 @@ class ExecutorBackend:
                     self.send(("indirect", job_id, partition, attempt, (block_id, len(data), tuple(env.block_manager.id)), run_ms))
                 else:
                     self.send(("ok", job_id, partition, attempt, data, run_ms))
+            except TaskKilled:
+                _acc.end_task(False)
+                self.tasks_killed += 1
+                self.send(("killed", job_id, partition, attempt, "interrupted", (time.perf_counter() - t0) * 1e3))
             except BaseException as exc:  # noqa: BLE001
                 _acc.end_task(False)
                 self.send(("err", job_id, partition, attempt, repr(exc) + "\n" + traceback.format_exc(limit=5), 0.0))
             finally:
+                if registered:
+                    with self._run_lock:
+                        self._running.pop(key, None)
                 self.active_task = None
 
 
@@ -336,8 +394,12 @@ class ClusterScheduler:
         self.speculation = speculation
         self.speculation_multiplier, self.speculation_quantile = speculation_multiplier, speculation_quantile
         self.speculation_interval, self.speculation_min_ms = speculation_interval, speculation_min_ms
+        self.allocation_manager = None       # ExecutorAllocationManager once enable_dynamic_allocation() ran
+        self._submit_lock = threading.RLock()
         self.speculated_tasks = 0
         self.speculative_wins = 0
+        self.speculative_kills_sent = 0      # kill_task messages to the losing copy (TaskSetManager.scala:736)
+        self.tasks_killed = 0                # "killed" acknowledgements from executors
         self.blacklist_enabled = blacklist
         self.blacklist_max_failures, self.blacklist_timeout = blacklist_max_failures, blacklist_timeout
         self._dump_waiters: Dict[int, Any] = {}
@@ -425,6 +487,7 @@ class ClusterScheduler:
                     self._blocks_held.setdefault(b, set()).add(eid)
         if not speculative:
             job["assigned"][partition] = eid
+            job.setdefault("attempts", {})[partition] = attempt
             job["started"].pop(partition, None)       # set again by the executor's "started" message
         self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
 
@@ -501,6 +564,11 @@ class ClusterScheduler:
             if job is not None and attempt < 1000:
                 job["started"][partition] = time.perf_counter()
             return
+        if kind == "killed":                              # the losing copy of a speculated task was interrupted
+            self.tasks_killed += 1
+            self.listeners.post({"event": "task_killed", "job": job_id, "partition": partition, "attempt": attempt,
+                                 "executor": eid, "reason": data, "ran_ms": run_ms})
+            return
         if job is None or kind == "gone":
             if kind == "indirect" and self.env is not None:       # nobody will read it: free the executor's block
                 self._getter.submit(self._drop_result_block, data[0])
@@ -556,8 +624,19 @@ class ClusterScheduler:
             if partition not in job["pending"] or partition in job["claimed"]:
                 return                                 # the other copy of a speculated / resubmitted task already delivered
             job["claimed"].add(partition)
-        if job["speculated"].get(partition) == eid:
-            self.speculative_wins += 1
+        twin = job["speculated"].get(partition)
+        if twin is not None:                              # two copies ran: stop the one that lost (TaskSetManager.scala:736)
+            if twin == eid:
+                self.speculative_wins += 1
+                loser, loser_attempt = job["assigned"].get(partition), job.get("attempts", {}).get(partition, 0)
+            else:
+                loser, loser_attempt = twin, 1000
+            if loser is not None and loser != eid:
+                try:
+                    self._send(loser, ("kill_task", job_id, partition, loser_attempt))
+                    self.speculative_kills_sent += 1
+                except Exception:  # noqa: BLE001  (the executor is gone: nothing left to kill)
+                    pass
         metrics = dict(run_ms) if isinstance(run_ms, dict) else {"run_ms": float(run_ms)}
         metrics.update(extra or {})
         metrics["result_bytes"] = nbytes
@@ -730,6 +809,14 @@ class ClusterScheduler:
         if getattr(self, "profiler", None) is not None:
             func = self.profiler.wrap(func)               # spark.python.profile: every task under cProfile
         parts = list(range(dataset.num_partitions)) if partitions is None else list(partitions)
+        am = self.allocation_manager
+        if am is not None:                                # dynamic allocation: a pending executor target is applied while no
+            with self._submit_lock:                       # job is routed (partition p lives on slot p % num_executors)
+                am.before_job()
+                return self._submit_job_routed(dataset, func, parts, result_handler, on_task_lost)
+        return self._submit_job_routed(dataset, func, parts, result_handler, on_task_lost)
+
+    def _submit_job_routed(self, dataset, func, parts, result_handler, on_task_lost) -> JobWaiter:
         job_id = next(ClusterScheduler._job_ids)
         waiter = JobWaiter(job_id, len(parts), result_handler)
         from .scheduler import _job_group
@@ -829,6 +916,17 @@ class ClusterScheduler:
             raise NotImplementedError(f"{type(self.transport).__name__} has a fixed set of executors")
         return self.transport.request_total_executors(int(total))
 
+    def enable_dynamic_allocation(self, policy=None, start: bool = True):
+        """``spark.dynamicAllocation.enabled``: start the backlog-driven policy loop (core/allocation.py)."""
+        from .allocation import ExecutorAllocationManager
+        if not hasattr(self.transport, "request_total_executors"):
+            raise NotImplementedError(f"{type(self.transport).__name__} has a fixed set of executors")
+        if self.allocation_manager is None:
+            self.allocation_manager = ExecutorAllocationManager(self, policy)
+            if start:
+                self.allocation_manager.start()
+        return self.allocation_manager
+
     def kill_executor(self, eid: int) -> None:
         """Fault injection: kill one executor process (FailureSuite / DistributedSuite style)."""
         self.transport.kill(eid)
@@ -854,6 +952,8 @@ class ClusterScheduler:
         if self._stopped:
             return
         self._stopped = True
+        if self.allocation_manager is not None:
+            self.allocation_manager.stop()
         self.transport.stop()
         self._getter.shutdown(wait=False)
         if self.env is not None:

@@ -37,6 +37,10 @@ class RuntimeLimits:
     heartbeat_interval: float = 10.0               # spark.executor.heartbeatInterval
     auth_secret: Optional[str] = None              # spark.authenticate.secret
     encrypt: bool = False                          # spark.network.crypto.enabled (AES-GCM on every RPC / block-transfer frame)
+    shuffle_memory: int = 256 << 20                # estimated bytes a shuffle sorter / combine map may hold before it spills
+    shuffle_spill_elements: int = 0                # spark.shuffle.spill.numElementsForceSpillThreshold (0 = off)
+    shuffle_spill_batch: int = 10000               # spark.shuffle.spill.batchSize
+    shuffle_spill_compress: bool = True            # spark.shuffle.spill.compress
 
 
 class AsyncEnv:

@@ -40,10 +40,11 @@ class TaskContext:
     submit_ms: float = 0.0
     metrics: Dict[str, float] = field(default_factory=dict)
     job: Any = None
+    killed: bool = False                     # this ATTEMPT was killed (the other copy of a speculated task won)
 
     def is_cancelled(self) -> bool:
-        """``TaskContext.isInterrupted``: true once the job this task belongs to has been cancelled."""
-        return bool(getattr(self.job, "cancelled", False))
+        """``TaskContext.isInterrupted``: true once the job this task belongs to has been cancelled, or this attempt killed."""
+        return self.killed or bool(getattr(self.job, "cancelled", False))
 
 
 _job_group = threading.local()          # sc.setJobGroup: a property of the submitting thread (SparkContext.setLocalProperty)

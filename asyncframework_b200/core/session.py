@@ -133,6 +133,12 @@ class AsyncSession:
             self.scheduler = Scheduler(n, max_failures=max_fail, device=self.device, name=app_name,
                                        block_first_async_job=rc.get("spark.async.blockFirstJob"))
         self._stopped = False
+        if rc.get("spark.dynamicAllocation.enabled"):
+            # ExecutorAllocationManager (SparkContext.scala:552-566 starts it when the cluster manager can resize the app)
+            from .allocation import AllocationPolicy
+            if not hasattr(getattr(self.scheduler, "transport", None), "request_total_executors"):
+                raise ValueError(f"spark.dynamicAllocation.enabled needs a cluster manager (spark://...), not master {master!r}")
+            self.scheduler.enable_dynamic_allocation(AllocationPolicy.from_conf(rc))
         if rc.get("spark.ui.enabled") or rc.get("spark.eventLog.enabled"):
             log = None
             if rc.get("spark.eventLog.enabled"):

@@ -87,6 +87,25 @@ def _cache_put(ds_id: int, p: int, kind: str, value, level=None) -> None:
 _SOURCE_STORE: dict = {}
 _block_ids = itertools.count(1)
 _shuffle_ids = itertools.count(0)
+
+
+def _spill_config():
+    """Spill thresholds of the running task: the executor's ``RuntimeLimits`` (``spark.shuffle.spill.*``), else the process default."""
+    from ..core.env import AsyncEnv
+    from ..storage import external_sorter as xs
+    e = AsyncEnv.get()
+    return xs.SpillConfig.from_limits(e.limits) if e is not None else xs.DEFAULT_CONFIG
+
+
+def _note_spill(t, m: dict) -> None:
+    """Fold a sorter's counters into the task metrics (TaskMetrics.memoryBytesSpilled / diskBytesSpilled / peakExecutionMemory)."""
+    tm = getattr(t, "metrics", None)
+    if not isinstance(tm, dict):
+        return
+    tm["memory_bytes_spilled"] = tm.get("memory_bytes_spilled", 0) + m["memory_bytes_spilled"]
+    tm["disk_bytes_spilled"] = tm.get("disk_bytes_spilled", 0) + m["disk_bytes_spilled"]
+    tm["spills"] = tm.get("spills", 0) + m["spills"]
+    tm["peak_execution_memory"] = max(tm.get("peak_execution_memory", 0), m["peak_memory"])
 _pickle_ctx = threading.local()
 
 
@@ -635,27 +654,38 @@ class ShardedDataset:
     def foreach(self, f) -> None:
         self._run(lambda t, it: [f(r) for r in it] and None)
 
-    def _shuffle(self, num_partitions: Optional[int], map_side, partitioner=None) -> "ShardedDataset":
+    def _shuffle(self, num_partitions: Optional[int], map_side, partitioner=None, aggregator=None) -> "ShardedDataset":
         """Hash (or custom-partitioner) shuffle.
 
         In-process masters: every map task returns its output bucketed by target partition and the driver regroups — the
         executors share the driver's memory, nothing is copied twice.  Cluster masters (an :class:`AsyncEnv` exists): a real
-        shuffle (SortShuffleManager / MapOutputTracker / ShuffleBlockFetcherIterator) — map tasks serialise +
-        compress every non-empty bucket into a ``shuffle_<id>_<map>_<reduce>`` block of THEIR BlockManager and return only
-        the sizes (``MapStatus``); the driver keeps that table (``MapOutputTracker``) and ships it inside the reduce-side
-        lineage; reduce tasks fetch their column of blocks from the executors that hold them over the bulk chunk path
-        (local blocks are read directly).  A block that has vanished with its executor is recomputed from lineage by the
-        reducer (fetch-failure recovery)."""
+        shuffle (SortShuffleManager / MapOutputTracker / ShuffleBlockFetcherIterator) — map tasks push their
+        records through a spillable :class:`~asyncframework_b200.storage.external_sorter.ExternalSorter` (partition, optional
+        map-side combine with ``aggregator``; sorted runs go to disk once the estimated footprint passes
+        ``spark.shuffle.spill.memoryThreshold``, ExternalSorter.scala:89), then serialise + compress ONE partition's bucket at
+        a time into a ``shuffle_<id>_<map>_<reduce>`` block of THEIR BlockManager and return only the sizes (``MapStatus``);
+        the driver keeps that table (``MapOutputTracker``) and ships it inside the reduce-side lineage; reduce tasks fetch
+        their column of blocks from the executors that hold them over the bulk chunk path (local blocks are read directly).
+        A block that has vanished with its executor is recomputed from lineage by the reducer (fetch-failure recovery)."""
         P = int(num_partitions or self.num_partitions)
         part_of = partitioner or (lambda k: _stable_hash(k) % P)
         env = getattr(self.scheduler, "env", None)
-        if env is None:
-            def part(t, it):
-                buckets: List[list] = [[] for _ in range(P)]
+
+        def bucketize(it):
+            buckets: List[list] = [[] for _ in range(P)]
+            if aggregator is None:
                 for k, v in map_side(it):
                     buckets[part_of(k)].append((k, v))
                 return buckets
-            outs = self._run(part)
+            acc: dict = {}
+            for k, v in map_side(it):
+                acc[k] = aggregator.merge_value(acc[k], v) if k in acc else aggregator.create_combiner(v)
+            for k, c in acc.items():
+                buckets[part_of(k)].append((k, c))
+            return buckets
+
+        if env is None:
+            outs = self._run(lambda t, it: bucketize(it))
             merged = [[kv for b in outs for kv in b[q]] for q in range(P)]
             blk = SourceBlock(merged)
             return ShardedDataset(self.scheduler, P, lambda p, t: iter(blk.data[p]), None, None, "shuffled")
@@ -663,24 +693,22 @@ class ShardedDataset:
         sid = next(_shuffle_ids)
         parent = self
 
-        def bucketize(it):
-            buckets: List[list] = [[] for _ in range(P)]
-            for k, v in map_side(it):
-                buckets[part_of(k)].append((k, v))
-            return buckets
-
         def map_task(t, it):
             from ..core.env import AsyncEnv
             from ..storage.block_manager import StorageLevel
+            from ..storage.external_sorter import ExternalSorter, SpillConfig
             e = AsyncEnv.get()
-            sizes = []
-            for q, b in enumerate(bucketize(it)):
-                if not b:
-                    sizes.append(0)
-                    continue
-                data = e.codec.compress(e.serializer.dumps(b))
-                e.block_manager.put_bytes(f"shuffle_{sid}_{t.partition_id}_{q}", data, StorageLevel.MEMORY_AND_DISK_SER)
-                sizes.append(len(data))
+            sizes = [0] * P
+            with ExternalSorter(P, part_of, aggregator, config=SpillConfig.from_limits(e.limits)) as sorter:
+                sorter.insert_all(map_side(it))
+                for q, records in sorter.partitioned_iterator():
+                    b = list(records)                         # one bucket at a time (the sorter streams spilled runs)
+                    if not b:
+                        continue
+                    data = e.codec.compress(e.serializer.dumps(b))
+                    e.block_manager.put_bytes(f"shuffle_{sid}_{t.partition_id}_{q}", data, StorageLevel.MEMORY_AND_DISK_SER)
+                    sizes[q] = len(data)
+                _note_spill(t, sorter.metrics())
             return sizes
         statuses = self._run(map_task)                       # MapOutputTracker: statuses[m][q] = bytes of block (m, q)
         num_maps = self.num_partitions
@@ -715,25 +743,16 @@ class ShardedDataset:
 
     def reduce_by_key(self, f, num_partitions: Optional[int] = None) -> "ShardedDataset":
         """``rdd.reduceByKey`` with map-side combining."""
-        def combine(it):
-            acc: dict = {}
-            for k, v in it:
-                acc[k] = f(acc[k], v) if k in acc else v
-            return acc.items()
-        sh = self._shuffle(num_partitions, combine)
-
-        def compute(p, t):
-            return iter(list(combine(sh.iterator(p, t))))
-        return sh._derive(compute, None, "reduce_by_key")
+        return self.combine_by_key(lambda v: v, f, f, num_partitions, _name="reduce_by_key")
 
     def group_by_key(self, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``rdd.groupByKey``: no map-side combine (it would not shrink the data, PairRDDFunctions.scala:501-511); the reduce
+        side groups through a spillable map (ExternalAppendOnlyMap)."""
+        from ..storage.external_sorter import Aggregator, external_combine
         sh = self._shuffle(num_partitions, lambda it: it)
 
         def compute(p, t):
-            acc: dict = {}
-            for k, v in sh.iterator(p, t):
-                acc.setdefault(k, []).append(v)
-            return iter(list(acc.items()))
+            return external_combine(sh.iterator(p, t), Aggregator.grouping(), _spill_config(), on_metrics=lambda m: _note_spill(t, m))
         return sh._derive(compute, None, "group_by_key")
 
     def distinct(self, num_partitions: Optional[int] = None) -> "ShardedDataset":
@@ -746,10 +765,9 @@ class ShardedDataset:
         return dict(self.map(lambda r: (r, 1)).reduce_by_key(lambda a, b: a + b).collect())
 
     def sort_by(self, key=lambda r: r, ascending: bool = True, num_partitions: Optional[int] = None) -> "ShardedDataset":
-        """``rdd.sortBy``: total order across partitions (range partitioning on the driver; data-prep scale)."""
-        P = int(num_partitions or self.num_partitions)
-        recs = sorted(self.collect(), key=key, reverse=not ascending)
-        return ShardedDataset.from_records(self.scheduler, recs, max(1, P), "sorted")
+        """``rdd.sortBy`` = ``keyBy(f).sortByKey().values`` (RDD.scala:622-628): range-partitioned, spillable, nothing is
+        collected on the driver except the key sample of the range partitioner."""
+        return self.map(lambda r: (key(r), r)).sort_by_key(ascending, num_partitions).values()
 
     def top(self, n: int, key=lambda r: r) -> list:
         import heapq
@@ -825,21 +843,18 @@ class ShardedDataset:
         """``rdd.partitionBy``: ``partitioner(key) -> partition`` (default: the process-independent hash)."""
         return self._shuffle(num_partitions, lambda it: it, partitioner)
 
-    def combine_by_key(self, create, merge_value, merge_combiners, num_partitions: Optional[int] = None) -> "ShardedDataset":
-        """``combineByKey`` with map-side combining — the primitive under reduce/aggregate/fold-ByKey."""
-        def map_side(it):
-            acc: dict = {}
-            for k, v in it:
-                acc[k] = merge_value(acc[k], v) if k in acc else create(v)
-            return acc.items()
-        sh = self._shuffle(num_partitions, map_side)
+    def combine_by_key(self, create, merge_value, merge_combiners, num_partitions: Optional[int] = None,
+                       _name: str = "combine_by_key") -> "ShardedDataset":
+        """``combineByKey`` with map-side combining — the primitive under reduce/aggregate/fold-ByKey.  Both sides combine
+        through a spillable map (``Aggregator.combineValuesByKey`` / ``combineCombinersByKey``)."""
+        from ..storage.external_sorter import Aggregator, external_combine
+        agg = Aggregator(create, merge_value, merge_combiners)
+        sh = self._shuffle(num_partitions, lambda it: it, aggregator=agg)
 
         def compute(p, t):
-            acc: dict = {}
-            for k, c in sh.iterator(p, t):
-                acc[k] = merge_combiners(acc[k], c) if k in acc else c
-            return iter(list(acc.items()))
-        return sh._derive(compute, None, "combine_by_key")
+            return external_combine(sh.iterator(p, t), agg, _spill_config(), values_are_combiners=True,
+                                    on_metrics=lambda m: _note_spill(t, m))
+        return sh._derive(compute, None, _name)
 
     def aggregate_by_key(self, zero_factory, seq_op, comb_op, num_partitions: Optional[int] = None) -> "ShardedDataset":
         return self.combine_by_key(lambda v: seq_op(zero_factory(), v), seq_op, comb_op, num_partitions)
@@ -853,11 +868,19 @@ class ShardedDataset:
         tagged = self.map(lambda kv: (kv[0], (0, kv[1]))).union(other.map(lambda kv: (kv[0], (1, kv[1]))))
         sh = tagged._shuffle(P, lambda it: it)
 
+        def mv(c, sv):
+            c[sv[0]].append(sv[1])
+            return c
+
+        def mc(a, b):
+            a[0].extend(b[0])
+            a[1].extend(b[1])
+            return a
+        from ..storage.external_sorter import Aggregator, external_combine
+        agg = Aggregator(lambda sv: mv(([], []), sv), mv, mc)
+
         def compute(p, t):
-            acc: dict = {}
-            for k, (side, v) in sh.iterator(p, t):
-                acc.setdefault(k, ([], []))[side].append(v)
-            return iter(list(acc.items()))
+            return external_combine(sh.iterator(p, t), agg, _spill_config(), on_metrics=lambda m: _note_spill(t, m))
         return sh._derive(compute, None, "cogroup")
 
     def join(self, other, num_partitions: Optional[int] = None) -> "ShardedDataset":
@@ -902,7 +925,11 @@ class ShardedDataset:
         P = int(num_partitions or self.num_partitions)
         partitioner = RangePartitioner(P, self, ascending, key=key)
         sh = self._shuffle(P, lambda it: it, partitioner)
-        return sh._derive(lambda p, t: iter(sorted(sh.iterator(p, t), key=lambda kv: key(kv[0]), reverse=not ascending)), None, "sort_by_key")
+        from ..storage.external_sorter import external_sort
+
+        def compute(p, t):                                     # spillable local sort (ExternalSorter with an ordering)
+            return external_sort(sh.iterator(p, t), key, not ascending, _spill_config(), on_metrics=lambda m: _note_spill(t, m))
+        return sh._derive(compute, None, "sort_by_key")
 
     def tree_reduce(self, f, depth: int = 2):
         """``rdd.treeReduce``: reduce inside the partitions, then combine the partials in a ``depth``-level tree."""

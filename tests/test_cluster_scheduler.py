@@ -318,6 +318,42 @@ def test_speculative_copy_of_a_straggling_task_wins():
         assert spec[3]["executor"] == 0                                        # home of partition 3 is executor 1
         time.sleep(0.2)
         assert len(res) == 4                                                   # nothing delivered twice
+        assert s.speculative_kills_sent >= 1
+
+
+def test_losing_copy_of_a_speculated_task_is_interrupted():
+    """TaskSetManager.scala:736 / Executor.killTask: once the speculative copy has delivered, the straggling original is
+    interrupted — its python loop stops within milliseconds instead of burning the slot to the end."""
+    from asyncframework_b200.core.cluster import ClusterScheduler
+    from asyncframework_b200.data.dataset import ShardedDataset
+    events = []
+    with ClusterScheduler(2, speculation=True, speculation_multiplier=2.0, speculation_quantile=0.5,
+                          speculation_interval=0.05, speculation_min_ms=50.0) as s:
+        s.listeners.add(events.append)
+        ds = ShardedDataset.from_records(s, list(range(40)), 4)
+        assert ds.count() == 40
+
+        def work(tctx, it):
+            if tctx.partition_id == 3 and tctx.attempt < 1000:
+                t_end = time.time() + 20.0         # a busy python loop for 20 s unless somebody interrupts it
+                while time.time() < t_end:
+                    time.sleep(0.005)
+            else:
+                time.sleep(0.1)
+            return sum(it)
+        res = {}
+        w = s.submit_job(ds, work, result_handler=res.__setitem__)
+        assert w.wait(20)
+        t0 = time.time()
+        while not any(e["event"] == "task_killed" for e in events) and time.time() - t0 < 5.0:
+            time.sleep(0.02)
+        killed = [e for e in events if e["event"] == "task_killed"]
+        assert killed and killed[0]["partition"] == 3 and killed[0]["executor"] == 1 and killed[0]["reason"] == "interrupted"
+        assert killed[0]["ran_ms"] < 10_000                                    # nowhere near the 20 s it wanted
+        # the freed slot is usable at once: a follow-up job on the same executors returns promptly
+        t1 = time.time()
+        assert ds.map(lambda x: 2 * x).reduce(lambda a, b: a + b) == 2 * sum(range(40))
+        assert time.time() - t1 < 5.0
 
 
 def test_failing_executor_is_blacklisted_and_its_partitions_move():

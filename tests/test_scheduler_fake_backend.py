@@ -129,8 +129,32 @@ def test_speculation_needs_running_tasks_a_quantile_and_a_slow_outlier():
     assert s.speculated_tasks == 1                                                         # at most one copy per task
     t.ok(0, w.job_id, 3, "copy", attempt=1000)
     assert w.done and got[3] == "copy" and s.speculative_wins == 1
+    # the losing ORIGINAL is told to stop (TaskSetManager.scala:736 killTask on the other attempts)
+    assert [(e, m[1:]) for e, m in t.sent if m[0] == "kill_task"] == [(1, (w.job_id, 3, 0))] and s.speculative_kills_sent == 1
     t.ok(1, w.job_id, 3, "original")                                                       # loser arrives late: dropped
     assert got[3] == "copy"
+    seen = []
+    s.listeners.add(seen.append)
+    s._on_message(1, ("killed", w.job_id, 3, 0, "interrupted", 12.0))                      # ... or acknowledges the kill
+    assert s.tasks_killed == 1 and seen[-1]["event"] == "task_killed" and seen[-1]["executor"] == 1
+    s.stop()
+
+
+def test_original_winning_kills_the_speculative_copy():
+    s, t, ds = make(speculation=False, speculation_quantile=0.5, speculation_multiplier=2.0, speculation_min_ms=0.0)
+    got = {}
+    w = s.submit_job(ds, lambda tc, it: 0, result_handler=got.__setitem__)
+    job = s._jobs[w.job_id]
+    for e, p in ((0, 0), (1, 1), (0, 2)):
+        t.started(e, w.job_id, p)
+        t.ok(e, w.job_id, p, p, run_ms=10.0)
+    t.started(1, w.job_id, 3)
+    job["started"][3] -= 1.0
+    s._check_speculatable(w.job_id, job)
+    assert t.tasks()[-1] == (0, 3, 1000)
+    t.ok(1, w.job_id, 3, "original")                                                       # the original finishes first after all
+    assert got[3] == "original" and s.speculative_wins == 0
+    assert [(e, m[1:]) for e, m in t.sent if m[0] == "kill_task"] == [(0, (w.job_id, 3, 1000))]
     s.stop()
 
 
