@@ -110,6 +110,12 @@ def declare(lib: C.CDLL) -> None:
     sig("afb_dense_round_ring_launch", C.c_int, [P(RoundParams), C.c_int, vp])
     sig("afb_dense_round_ring_max_ld", C.c_int, [])
     sig("afb_sleep", C.c_int, [i64, vp])
+    sig("afb_e2e_create", vp, [])
+    sig("afb_e2e_destroy", None, [vp])
+    sig("afb_e2e_pre", C.c_int, [vp, C.c_int, vp, vp, i64, vp])
+    sig("afb_e2e_post", C.c_int, [vp, C.c_int, vp, vp, vp, i64, vp])
+    sig("afb_e2e_wait", C.c_int, [vp, C.c_int])
+    sig("afb_e2e_sync", C.c_int, [vp])
     sig("afb_saga_rollback_launch", C.c_int, [vp, vp, vp, C.c_int, vp, vp])
     sig("afb_axpy", C.c_int, [f32, vp, vp, i64, vp])
     sig("afb_scal", C.c_int, [f32, vp, i64, vp])

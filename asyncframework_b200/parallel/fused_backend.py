@@ -168,6 +168,22 @@ class FusedEngine:
         self._ctl_np = self._ctl_host.numpy()
         self._step_events = [_dev.new_event(self.device), _dev.new_event(self.device)]
         self._step_pending = [False, False]
+        # overlapped end-to-end plumbing (csrc/kernels/e2e_step.cu): the per-step H2D / D2H copies ride on side streams, so
+        # the launching stream carries nothing but rounds.  One local worker on a GPU only; AFB_E2E_OVERLAP=0 keeps both
+        # copies on the launching stream (the previous behaviour, and the one multi-worker engines use).
+        import os as _os
+        self._e2e = None
+        self._e2e_lib = None
+        if (self.device.type == "cuda" and n_local == 1 and not self.kernels[0].sim and _os.environ.get("AFB_E2E_OVERLAP", "1") != "0"
+                and hasattr(self.kernels[0].lib, "afb_e2e_create")):
+            self._e2e_lib = self.kernels[0].lib
+            self._e2e = self._e2e_lib.afb_e2e_create()
+            if not self._e2e:
+                raise RuntimeError("afb_e2e_create failed (side streams / events for the end-to-end step)")
+            self._snap = torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+            self._e2e_ptrs = (self._desc_dev.data_ptr(), self._desc_host.data_ptr(), self.wctl_all.data_ptr(),
+                              [self._snap[0].data_ptr(), self._snap[1].data_ptr()],
+                              [self._ctl_host[0].data_ptr(), self._ctl_host[1].data_ptr()])
         self._step_idx = 0
         self._ring_seen = 0
         self.rounds_enqueued = 0
@@ -247,6 +263,25 @@ class FusedEngine:
     def synchronize(self) -> None:
         for st in self.streams:
             st.synchronize()
+        if self._e2e is not None:
+            from ..ops import check
+            check(self._e2e_lib.afb_e2e_sync(self._e2e), "end-to-end side streams")
+
+    def _wait_step(self, slot: int) -> None:
+        """Block until the result record of the step that used ``slot`` is in pinned host memory."""
+        if self._e2e is not None:
+            from ..ops import check
+            check(self._e2e_lib.afb_e2e_wait(self._e2e, slot), "end-to-end result wait")
+        else:
+            self._step_events[slot].synchronize()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_e2e", None):
+                self._e2e_lib.afb_e2e_destroy(self._e2e)
+                self._e2e = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def stagger(self, period_us: float) -> None:
         """Offset the local workers' round cadence by ``period/num_local`` each (one-time device-side
@@ -293,7 +328,7 @@ class FusedEngine:
         results one step behind so the device never waits for Python (call ``flush_steps()`` at the end)."""
         slot = self._step_idx & 1
         if self._step_pending[slot]:                 # slot reuse: its previous occupant must have been read
-            self._step_events[slot].synchronize()
+            self._wait_step(slot)
         rnd = self.kernels[0].rounds_launched        # == the device round counter of every local worker (lock-step launches)
         ds = rnd % self.desc_slots
         d = self._desc_np[ds:ds + 1]
@@ -302,29 +337,40 @@ class FusedEngine:
         d["delay_coeff"] = max(self.cfg.coeff, 0.0) if delay_coeff is None else float(delay_coeff)
         d["seq"] = rnd + 1
         cur = _dev.current_stream(self.device)
-        self._desc_dev[ds].copy_(self._desc_host[ds], non_blocking=True)                # H2D (pinned): this round's descriptor
-        multi = len(self.kernels) > 1
-        if multi:
-            fork = _dev.new_event(self.device)
-            fork.record(cur)
-        for rk, st in zip(self.kernels, self.streams):
-            if multi and st != cur:
-                st.wait_event(fork)
-            rk.launch(st)
-        if multi:
-            self.join()
+        if self._e2e is not None:
+            # H2D on the descriptor stream (the round waits for it through an event), round on the launching stream, result
+            # snapshot behind it, D2H on the result stream: the launching stream never waits for a copy engine
+            from ..ops import check
+            lib, ctx, sp = self._e2e_lib, self._e2e, int(cur.cuda_stream)
+            desc_dev, desc_host, wctl, snaps, hosts = self._e2e_ptrs
+            nb = ROUND_DESC_DTYPE.itemsize
+            check(lib.afb_e2e_pre(ctx, slot, desc_dev + ds * nb, desc_host + ds * nb, nb, sp), "end-to-end descriptor copy")
+            self.kernels[0].launch(self.streams[0])
+            check(lib.afb_e2e_post(ctx, slot, wctl, snaps[slot], hosts[slot], self._snap[slot].numel(), sp), "end-to-end result copy")
+        else:
+            self._desc_dev[ds].copy_(self._desc_host[ds], non_blocking=True)            # H2D (pinned): this round's descriptor
+            multi = len(self.kernels) > 1
+            if multi:
+                fork = _dev.new_event(self.device)
+                fork.record(cur)
+            for rk, st in zip(self.kernels, self.streams):
+                if multi and st != cur:
+                    st.wait_event(fork)
+                rk.launch(st)
+            if multi:
+                self.join()
+            self._ctl_host[slot].copy_(self.wctl_all, non_blocking=True)                # D2H (pinned), all local workers
+            self._step_events[slot].record(cur)
         self.rounds_enqueued += 1
-        self._ctl_host[slot].copy_(self.wctl_all, non_blocking=True)                    # D2H (pinned), all local workers
-        self._step_events[slot].record(cur)
         self._step_pending[slot] = True
         self._step_idx += 1
         if lag == 0:
-            self._step_events[slot].synchronize()
+            self._wait_step(slot)
             self._step_pending[slot] = False
             return self._parse_result(slot)
         prev = slot ^ 1
         if self._step_pending[prev]:
-            self._step_events[prev].synchronize()
+            self._wait_step(prev)
             self._step_pending[prev] = False
             return self._parse_result(prev)
         return None
@@ -334,7 +380,7 @@ class FusedEngine:
         last = None
         for slot in ((self._step_idx & 1), (self._step_idx & 1) ^ 1):
             if self._step_pending[slot]:
-                self._step_events[slot].synchronize()
+                self._wait_step(slot)
                 self._step_pending[slot] = False
                 last = self._parse_result(slot)
         return last

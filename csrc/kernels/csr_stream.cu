@@ -274,13 +274,21 @@ int afb_csr_stream_launch(const afb::RoundParams* params, int rounds, int grid, 
   if (p.ld % 4 != 0 || p.ld <= 0 || rounds <= 0 || p.indptr == nullptr) return static_cast<int>(cudaErrorInvalidValue);
   if (!(p.algo == ALGO_ASGD || p.algo == ALGO_ASAGA) || p.hist_prev != nullptr || p.seed_mode == 3 || p.pdl != 0)
     return static_cast<int>(cudaErrorInvalidValue);
-  int dev = 0, sms = 0, per_sm = 0;
+  int dev = 0;
   cudaError_t e;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return static_cast<int>(e);
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return static_cast<int>(e);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_stream_kernel, kCsrSThreads, 0)) != cudaSuccess) return static_cast<int>(e);
+  // resident-CTA capacity of this device: queried once (host-side driver calls sit inside the callers' timed regions)
+  static int s_capacity[64] = {0};
+  int capacity = (dev >= 0 && dev < 64) ? s_capacity[dev] : 0;
+  if (capacity == 0) {
+    int sms = 0, per_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return static_cast<int>(e);
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_stream_kernel, kCsrSThreads, 0)) != cudaSuccess) return static_cast<int>(e);
+    capacity = per_sm * sms;
+    if (dev >= 0 && dev < 64) s_capacity[dev] = capacity;
+  }
   if (share < 1) share = 1;
-  if (static_cast<long long>(grid) * share > static_cast<long long>(per_sm) * sms) return static_cast<int>(cudaErrorLaunchOutOfResources);
+  if (static_cast<long long>(grid) * share > static_cast<long long>(capacity)) return static_cast<int>(cudaErrorLaunchOutOfResources);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((e = cudaMemsetAsync(grid_bar, 0, sizeof(GridBar), st)) != cudaSuccess) return static_cast<int>(e);
   csr_stream_kernel<<<grid, kCsrSThreads, 0, st>>>(p, rounds, static_cast<GridBar*>(grid_bar));

@@ -778,22 +778,35 @@ dense_stream_kernel(const __grid_constant__ RoundParams p, const int rounds, Pip
   }
 }
 
+constexpr int kMaxCachedDevices = 64;
+
 template <int NV, int kDepth, bool PIPE, bool BF16>
 static cudaError_t launch_stream(const RoundParams& p, int rounds, int grid, int share, PipeState* ps, float* g2, float* w2,
                                  cudaStream_t stream) {
   const size_t stage = static_cast<size_t>(p.ld) * (BF16 ? 2 : 4) + kStreamMetaBytes;
   const size_t smem = static_cast<size_t>(kStreamWarps) * kDepth * stage + 128;
   auto k = dense_stream_kernel<NV, kDepth, PIPE, BF16>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  if (rounds > 1) {
-    // rounds are separated by in-kernel waits: every CTA of every co-running persistent grid must be resident
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  // The attribute / occupancy queries are host-side driver calls inside every caller's timed region (the GPU idles until the
+  // launch arrives): do them once per (instantiation, device, shared-memory size), not once per launch.
+  struct Setup { size_t smem = 0; int capacity = 0; };
+  static Setup s_setup[kMaxCachedDevices];
+  cudaError_t e;
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  Setup local;
+  Setup& su = (dev >= 0 && dev < kMaxCachedDevices) ? s_setup[dev] : local;
+  if (su.smem != smem) {
+    int sms = 0, per_sm = 0;
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kStreamThreads, smem)) != cudaSuccess) return e;
+    su.capacity = per_sm * sms;
+    su.smem = smem;
+  }
+  if (rounds > 1) {
+    // rounds are separated by in-kernel waits: every CTA of every co-running persistent grid must be resident
     if (share < 1) share = 1;
-    if (static_cast<long long>(grid) * share > static_cast<long long>(per_sm) * sms) return cudaErrorLaunchOutOfResources;
+    if (static_cast<long long>(grid) * share > static_cast<long long>(su.capacity)) return cudaErrorLaunchOutOfResources;
   }
   k<<<grid, kStreamThreads, smem, stream>>>(p, rounds, ps, g2, w2);
   return cudaGetLastError();

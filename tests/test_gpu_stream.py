@@ -305,6 +305,39 @@ def test_step_descriptor_is_consumed_by_the_kernel():
     assert abs(batches[2] / batches[0] - 0.5) < 0.05 and batches[0] == batches[1]
 
 
+@pytest.mark.parametrize("lag", [0, 1])
+def test_overlapped_step_copies_return_the_same_records_as_same_stream_copies(lag, monkeypatch):
+    """csrc/kernels/e2e_step.cu: with the per-step H2D / D2H copies on side streams (default) every step returns exactly the
+    record the same-stream plumbing returns (AFB_E2E_OVERLAP=0), lagged or not, and the models end up identical."""
+    from asyncframework_b200.config import AsyncConfig
+    from asyncframework_b200.parallel.fused_backend import FusedEngine
+    n, d = 60_000, 128
+    sh = _dense_shard(n, d, seed=6, labels01=True)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AFB_E2E_OVERLAP", mode)
+        cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=0.02,
+                          batch_rate=0.2, loss="logistic", backend="fused", barrier="asp", seed=11)
+        eng = FusedEngine(cfg, [sh], n, [0], device="cuda")
+        assert (eng._e2e is not None) == (mode == "1")
+        recs = []
+        for i in range(40):
+            r = eng.step(step_size=0.02 / (1 + i), batch_rate=0.1 + 0.01 * (i % 7), lag=lag)
+            if r is not None:
+                recs.append((r["k"], r["batch"], r["accepted"], round(r["loss_sum"], 3)))
+        last = eng.flush_steps()
+        if last is not None:
+            recs.append((last["k"], last["batch"], last["accepted"], round(last["loss_sum"], 3)))
+        eng.synchronize()
+        eng.check_health()
+        out[mode] = (recs, eng.weights().clone())
+    assert len(out["1"][0]) == 40 and [r[0] for r in out["1"][0]] == list(range(1, 41))      # one record per step, in order
+    assert [r[:3] for r in out["1"][0]] == [r[:3] for r in out["0"][0]]
+    for a, b in zip(out["1"][0], out["0"][0]):                       # the CTA merge order is not deterministic: low bits differ
+        assert abs(a[3] - b[3]) <= 1e-4 * abs(b[3]) + 1e-2
+    assert torch.allclose(out["1"][1], out["0"][1], rtol=1e-4, atol=1e-7)
+
+
 def test_objective_evaluation_accepts_bf16_row_storage():
     """Shards stored with bf16 rows are evaluated through the same kernels (widened chunk by chunk) with identical results."""
     from asyncframework_b200.data.batch import Shard
