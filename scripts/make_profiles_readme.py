@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Regenerate profiles/README.md from the JSON results copied under profiles/bench/."""
+"""Regenerate profiles/README_round1.md (the round-1 tables) from the JSON results copied under profiles/bench/.  The round-2 summary, profiles/README.md, is written by hand from profiles/bench/r2/."""
 import glob
 import json
 import os
@@ -169,5 +169,5 @@ out += ["## Kernel evidence", "",
         "  TMA round variants, `REDG.E.ADD.F32x4...STRONG.SYS` + `LDG.E.128.STRONG.SYS` (NVLink peer reductions/loads) and",
         "  `ATOMG.E.ADD.64.STRONG.SYS` (logical clock) in every round kernel, `ACQBULK`/`PREEXIT` (programmatic dependent launch).",
         "* `sanitizer/` — compute-sanitizer memcheck / racecheck / synccheck summaries.", ""]
-open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(out) + "\n")
-print("profiles/README.md written,", len(out), "lines")
+open(os.path.join(ROOT, "profiles", "README_round1.md"), "w").write("\n".join(out) + "\n")
+print("profiles/README_round1.md written,", len(out), "lines")
