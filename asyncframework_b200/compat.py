@@ -172,6 +172,9 @@ _alias(RDD, zipWithIndex="zip_with_index", mapPartitionsWithIndex="map_partition
        subtractByKey="subtract_by_key", sortByKey="sort_by_key", collectAsMap="collect_as_map", takeOrdered="take_ordered",
        isEmpty="is_empty", randomSplit="random_split", saveAsTextFile="save_as_text_file", toLocalIterator="to_local_iterator",
        setName="set_name", toDebugString="to_debug_string", zipPartitions="zip_partitions", getStorageLevel="get_storage_level",
+       flatMapValues="flat_map_values", groupBy="group_by", sampleByKey="sample_by_key", sampleVariance="sample_variance",
+       sampleStdev="sample_stdev", countApprox="count_approx", localCheckpoint="local_checkpoint", isCheckpointed="is_checkpointed",
+       getCheckpointFile="get_checkpoint_file", repartitionAndSortWithinPartitions="repartition_and_sort_within_partitions",
        treeReduce="tree_reduce", countApproxDistinct="count_approx_distinct", saveAsPickleFile="save_as_pickle_file", mapShards="map_shards", ASYNCgrad="async_grad")
 _alias(SparkContext, setJobGroup="set_job_group", clearJobGroup="clear_job_group", cancelJobGroup="cancel_job_group",
        getExecutorMemoryStatus="get_executor_memory_status", statusTracker=property(lambda self: self.status_tracker),

@@ -376,6 +376,24 @@ class ShardedDataset:
             f.write(f"{self.num_partitions} {int(batchy)}\n")
         return ShardedDataset.from_checkpoint(self.scheduler, directory)
 
+    def local_checkpoint(self) -> "ShardedDataset":
+        """``rdd.localCheckpoint()`` (RDD.scala:1600-1640): materialise the partitions once at ``MEMORY_AND_DISK`` in the
+        executors' block stores and serve every later job from there, without reliable storage (lost with its executor —
+        the reference trades fault tolerance for speed the same way).  Unlike :meth:`checkpoint` the parent chain is kept as
+        the recomputation fallback for a lost block."""
+        from ..storage.block_manager import StorageLevel
+        self.persist(StorageLevel.MEMORY_AND_DISK)
+        self._run(lambda t, it: sum(1 for _ in it))              # materialise now
+        self._local_checkpointed = True
+        return self
+
+    def is_checkpointed(self) -> bool:
+        """``rdd.isCheckpointed``: true for datasets re-opened from a reliable checkpoint and for locally checkpointed ones."""
+        return bool(getattr(self, "_checkpoint_dir", None) or getattr(self, "_local_checkpointed", False))
+
+    def get_checkpoint_file(self) -> Optional[str]:
+        return getattr(self, "_checkpoint_dir", None)
+
     @classmethod
     def from_checkpoint(cls, scheduler, directory: str) -> "ShardedDataset":
         """Re-open a dataset written by :meth:`checkpoint` (``sc.checkpointFile``)."""
@@ -397,7 +415,9 @@ class ShardedDataset:
             if s is not None:
                 s.partition = p
             return s
-        return cls(scheduler, n, compute, batch if batchy else None, None, f"checkpoint:{os.path.basename(directory)}")
+        ds = cls(scheduler, n, compute, batch if batchy else None, None, f"checkpoint:{os.path.basename(directory)}")
+        ds._checkpoint_dir = directory
+        return ds
 
     def _derive(self, compute=None, batch=None, name="") -> "ShardedDataset":
         ds = ShardedDataset(self.scheduler, self.num_partitions, compute, batch, self, name or self.name)
@@ -650,6 +670,42 @@ class ShardedDataset:
 
     def map_values(self, f) -> "ShardedDataset":
         return self.map(lambda kv: (kv[0], f(kv[1])))
+
+    def flat_map_values(self, f) -> "ShardedDataset":
+        """``rdd.flatMapValues`` (PairRDDFunctions.scala:768): keys are kept, every value expands to zero or more values."""
+        return self.flat_map(lambda kv: [(kv[0], v) for v in f(kv[1])])
+
+    def group_by(self, f, num_partitions: Optional[int] = None) -> "ShardedDataset":
+        """``rdd.groupBy(f)`` = ``map(x => (f(x), x)).groupByKey()`` (RDD.scala:685-705)."""
+        return self.key_by(f).group_by_key(num_partitions)
+
+    def sample_by_key(self, with_replacement: bool, fractions: dict, seed: Optional[int] = None) -> "ShardedDataset":
+        """``rdd.sampleByKey`` (stratified sampling, PairRDDFunctions.scala:262-284): every key has its own sampling rate;
+        Bernoulli per record without replacement, Poisson counts with replacement.  Deterministic in ``(seed, partition,
+        position)`` like the other samplers here (a retried task reproduces its sample)."""
+        if seed is None:
+            seed = int.from_bytes(np.random.bytes(8), "little")
+        seed = int(seed)
+        missing = object()
+
+        def compute(p, t):
+            import random
+            rng = random.Random((seed * 0x9E3779B97F4A7C15 + p) & ((1 << 64) - 1))
+            for kv in self.iterator(p, t):
+                f = fractions.get(kv[0], missing)
+                if f is missing:
+                    raise KeyError(f"sample_by_key: no sampling fraction for key {kv[0]!r}")
+                if with_replacement:
+                    # Poisson(f) copies, Knuth's method (f is a sampling rate: small)
+                    L, k, prod = math.exp(-float(f)), 0, rng.random()
+                    while prod > L:
+                        k += 1
+                        prod *= rng.random()
+                    for _ in range(k):
+                        yield kv
+                elif rng.random() < f:
+                    yield kv
+        return self._derive(compute, None, "sample_by_key")
 
     def foreach(self, f) -> None:
         self._run(lambda t, it: [f(r) for r in it] and None)
@@ -931,6 +987,17 @@ class ShardedDataset:
             return external_sort(sh.iterator(p, t), key, not ascending, _spill_config(), on_metrics=lambda m: _note_spill(t, m))
         return sh._derive(compute, None, "sort_by_key")
 
+    def repartition_and_sort_within_partitions(self, num_partitions: Optional[int] = None, partitioner=None, ascending: bool = True,
+                                               key=lambda k: k) -> "ShardedDataset":
+        """``repartitionAndSortWithinPartitions`` (OrderedRDDFunctions.scala:71-79): shuffle by the given partitioner (hash by
+        default) and sort every output partition by key — the sort happens in the spillable reduce-side sorter, not after it."""
+        from ..storage.external_sorter import external_sort
+        sh = self._shuffle(num_partitions, lambda it: it, partitioner)
+
+        def compute(p, t):
+            return external_sort(sh.iterator(p, t), key, not ascending, _spill_config(), on_metrics=lambda m: _note_spill(t, m))
+        return sh._derive(compute, None, "repartition_and_sort_within_partitions")
+
     def tree_reduce(self, f, depth: int = 2):
         """``rdd.treeReduce``: reduce inside the partitions, then combine the partials in a ``depth``-level tree."""
         def seq(acc, x):
@@ -1016,6 +1083,49 @@ class ShardedDataset:
 
     def stdev(self) -> float:
         return self.stats()["stdev"]
+
+    def sample_variance(self) -> float:
+        """``rdd.sampleVariance()``: the unbiased estimator (divides by n - 1; StatCounter.sampleVariance)."""
+        st = self.stats()
+        n = st["count"]
+        return float("nan") if n <= 1 else st["variance"] * n / (n - 1)
+
+    def sample_stdev(self) -> float:
+        return math.sqrt(self.sample_variance())
+
+    def count_approx(self, timeout: float, confidence: float = 0.95) -> dict:
+        """``rdd.countApprox(timeout, confidence)`` (RDD.scala:1185-1198, partial/CountEvaluator.scala): start the counting job,
+        wait at most ``timeout`` seconds and answer from the partitions that have finished — ``{"mean", "low", "high",
+        "confidence", "final", "partitions_done"}``.  With every partition in, the answer is exact (``low == high``); with a
+        fraction p of them, the total is extrapolated as ``sum / p`` with a normal interval of variance ``sum (1 - p) / p^2``
+        (the evaluator's large-count branch).  The job keeps running in the background; its late results are ignored."""
+        import statistics
+        import threading
+        total = self.num_partitions
+        lock = threading.Lock()
+        got: dict = {}
+
+        def handler(i, r):
+            with lock:
+                got[i] = int(r)
+        waiter = self.scheduler.submit_job(self, lambda t, it: sum(1 for _ in it), None, handler)
+        try:
+            waiter.wait(max(0.0, float(timeout)))
+        except Exception:  # noqa: BLE001  (a failed partition simply does not contribute; count() is the strict form)
+            pass
+        with lock:
+            done, part_sum = len(got), sum(got.values())
+        if done == total:
+            return {"mean": float(part_sum), "low": float(part_sum), "high": float(part_sum), "confidence": 1.0, "final": True,
+                    "partitions_done": done}
+        if done == 0:
+            return {"mean": 0.0, "low": 0.0, "high": float("inf"), "confidence": float(confidence), "final": False, "partitions_done": 0}
+        p = done / total
+        mean = part_sum / p
+        sd = math.sqrt(part_sum * (1.0 - p)) / p
+        z = statistics.NormalDist().inv_cdf(0.5 + min(max(confidence, 0.0), 0.999999) / 2.0)
+        return {"mean": mean, "low": max(float(part_sum), mean - z * sd), "high": mean + z * sd, "confidence": float(confidence),
+                "final": False, "partitions_done": done}
 
     def histogram(self, buckets):
         """``rdd.histogram(n | boundaries)`` -> (boundaries, counts); the last bucket is closed on the right."""

@@ -223,3 +223,54 @@ def test_tree_reduce_and_hyperloglog_count_approx_distinct(sc):
     assert abs(est - true) / true < 0.06, (est, true)                    # 3 sigma at relative_sd = 0.02
     assert sc.parallelize(["a", "b", "a", "c"] * 10, 2).count_approx_distinct() == 3     # small range: linear counting is exact-ish
     assert ds.id() == ds.ds_id
+
+
+def test_group_by_flat_map_values_stratified_sampling_and_sorted_repartition(sc):
+    """PairRDDFunctions / OrderedRDDFunctions leftovers: groupBy, flatMapValues, sampleByKey, repartitionAndSortWithinPartitions."""
+    ds = sc.parallelize(range(60), 4)
+    groups = dict(ds.group_by(lambda x: x % 3, 2).collect())
+    assert {k: sorted(v) for k, v in groups.items()} == {r: [x for x in range(60) if x % 3 == r] for r in range(3)}
+    pairs = sc.parallelize([("a", 2), ("b", 0), ("c", 3)], 2)
+    assert sorted(pairs.flat_map_values(lambda n: range(n)).collect()) == [("a", 0), ("a", 1), ("c", 0), ("c", 1), ("c", 2)]
+    strat = sc.parallelize([("x", i) for i in range(2000)] + [("y", i) for i in range(2000)], 4)
+    s1 = strat.sample_by_key(False, {"x": 0.5, "y": 0.05}, seed=7).collect()
+    assert s1 == strat.sample_by_key(False, {"x": 0.5, "y": 0.05}, seed=7).collect()          # deterministic in the seed
+    nx, ny = sum(1 for k, _ in s1 if k == "x"), sum(1 for k, _ in s1 if k == "y")
+    assert 900 < nx < 1100 and 60 < ny < 140
+    s2 = strat.sample_by_key(True, {"x": 2.0, "y": 0.0}, seed=7).collect()
+    assert 3700 < len(s2) < 4300 and all(k == "x" for k, _ in s2)
+    with pytest.raises(Exception, match="no sampling fraction"):
+        strat.sample_by_key(False, {"x": 0.5}, seed=1).collect()
+    import random
+    rng = random.Random(3)
+    recs = [(rng.randrange(1000), i) for i in range(500)]
+    out = sc.parallelize(recs, 5).repartition_and_sort_within_partitions(3, partitioner=lambda k: k % 3, ascending=False)
+    parts = out.glom().collect()
+    assert len(parts) == 3
+    for p, rows in enumerate(parts):
+        ks = [k for k, _ in rows]
+        assert all(k % 3 == p for k in ks) and ks == sorted(ks, reverse=True)
+    assert sorted(kv for rows in parts for kv in rows) == sorted(recs)
+
+
+def test_sample_statistics_count_approx_and_local_checkpoint(sc):
+    import statistics
+    import time
+    xs = [float(i * i % 17) for i in range(200)]
+    ds = sc.parallelize(xs, 4)
+    assert abs(ds.sample_variance() - statistics.variance(xs)) < 1e-9 and abs(ds.sample_stdev() - statistics.stdev(xs)) < 1e-9
+    assert math.isnan(sc.parallelize([1.0], 1).sample_variance())
+    full = ds.count_approx(timeout=30.0)
+    assert full == {"mean": 200.0, "low": 200.0, "high": 200.0, "confidence": 1.0, "final": True, "partitions_done": 4}
+
+    def slow(x):
+        if x >= 150:                     # the last partition takes much longer than the timeout
+            time.sleep(0.02)
+        return x
+    part = sc.parallelize(range(200), 4).map(slow).count_approx(timeout=0.25, confidence=0.9)
+    assert part["final"] is False and 1 <= part["partitions_done"] < 4
+    assert part["low"] <= 200.0 <= part["high"] * 1.5 and part["low"] >= 50 * part["partitions_done"]
+    lc = sc.parallelize(range(40), 4).map(lambda x: x + 1)
+    assert not lc.is_checkpointed()
+    lc.local_checkpoint()
+    assert lc.is_checkpointed() and lc.get_checkpoint_file() is None and lc.reduce(lambda a, b: a + b) == sum(range(1, 41))
