@@ -77,15 +77,24 @@ class ExecutorAllocationManager:
         with s._lock:
             jobs = list(s._jobs.values())
         for job in jobs:
-            pend = set(job["pending"])
-            run = sum(1 for p in pend if p in job["started"])
+            for _ in range(4):                       # receiver threads mutate these containers: retry a torn snapshot
+                try:
+                    pend = set(job["pending"])
+                    started = set(job["started"])
+                    assigned = dict(job["assigned"])
+                    spec = dict(job["speculated"])
+                    break
+                except RuntimeError:
+                    continue
+            else:
+                continue
             pending += len(pend)
-            running += run
+            running += sum(1 for p in pend if p in started)
             for p in pend:
-                e = job["assigned"].get(p)
+                e = assigned.get(p)
                 if e is not None:
                     busy.add(e)
-            for p, e in job["speculated"].items():
+            for p, e in spec.items():
                 if p in pend:
                     busy.add(e)
         return {"pending": pending, "running": running, "backlog": pending - running, "busy": busy, "jobs": len(jobs)}
