@@ -3,7 +3,7 @@
 ``ops/round_sim.py`` is the sequential spec of one round.  This module models what the simulator cannot: the
 *concurrency inside a grid* — G CTAs of one worker racing through puller election, dynamic chunk scheduling,
 the grid-level reduction, the early clock ticket, last-CTA election, the reset of the per-round counters and
-(persistent variant, ``csrc/experimental/dense_round_persist.cu``) the in-kernel round barrier on
+(persistent rounds, ``csrc/kernels/dense_stream.cu::stream_round_serial``) the in-kernel round barrier on
 ``WorkerCtl.round`` — with several workers sharing one server.  Every CTA is a Python generator that yields
 after each access to shared state, in the order the CUDA code performs them (``csrc/include/afb_round_impl.cuh``,
 ``csrc/kernels/dense_round.cu``); ``explore`` runs them under a seeded random / bursty scheduler and checks:
@@ -236,7 +236,7 @@ class WorkerModel:
         wc.round = rnd + 1
         yield
 
-    # ------------------------------------------------------------------ pipelined persistent rounds (experimental design)
+    # ------------------------------------------------------------------ pipelined persistent rounds (dense_stream.cu::stream_round_pipe)
     def _pipe_state(self):
         return WorkerCtl()
 

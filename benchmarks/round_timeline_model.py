@@ -16,7 +16,7 @@ Model (per GPU; GPUs are symmetric, contention at the server is not modelled):
 Variants:
   lockstep      W workers start together every round (what run11 shows: the two kernels launch back to back)
   antiphase     workers offset by half a cycle (device-side handshake instead of the one-time stagger sleep)
-  persist       lockstep, inter-kernel gap replaced by the in-kernel round barrier (csrc/experimental/dense_round_persist.cu)
+  persist       lockstep, inter-kernel gap replaced by the in-kernel round barrier (the serial persistent rounds of csrc/kernels/dense_stream.cu)
   persist+anti  both
   pipelined     ONE worker per GPU owning all SMs (2 CTAs/SM), round r+1's pull/compute overlapping round r's tail
                 (double-buffered g_local / counters): serial work hides behind streaming entirely

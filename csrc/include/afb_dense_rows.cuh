@@ -1,6 +1,6 @@
 // Row streaming helpers of the dense round kernels: register-resident rows (`RowRegs`), and the warp-level
 // guided self-scheduler that yields the next Bernoulli-selected local row (`RowScheduler`).  Shared by
-// csrc/kernels/dense_round.cu and csrc/experimental/dense_round_persist.cu.
+// csrc/kernels/dense_round.cu and csrc/kernels/dense_stream.cu (scheduler + chunk masks).
 #pragma once
 #include "afb_round_impl.cuh"
 

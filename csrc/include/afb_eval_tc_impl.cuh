@@ -1,5 +1,5 @@
-// tcgen05 / TMEM / TMA evaluation GEMM, templated on the loss applied in the epilogue (shared by csrc/kernels/eval_tc.cu —
-// squared error, the validated default — and csrc/experimental/eval_tc_loss.cu — logistic / hinge / half-squared).
+// tcgen05 / TMEM / TMA evaluation GEMM, templated on the loss applied in the epilogue; instantiated by csrc/kernels/eval_tc.cu
+// for squared error, logistic, hinge and half-squared error (afb_eval_tc / afb_eval_loss_tc).
 #pragma once
 #include <algorithm>
 #include "afb_common.cuh"

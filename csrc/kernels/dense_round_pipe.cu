@@ -215,7 +215,7 @@ static cudaError_t launch_pipe(const RoundParams& p, int grid, cudaStream_t stre
 
 extern "C" {
 
-int afb_dense_round_pipe_max_ld() { return 896; }   // NV4 <= 7 validated on B200 (experimental variant)
+int afb_dense_round_pipe_max_ld() { return 896; }   // NV4 <= 7 validated on B200 (A/B arm, not a default)
 
 int afb_dense_round_pipe_launch(const afb::RoundParams* params, int grid, void* stream) {
   using namespace afb;

@@ -90,7 +90,7 @@ if os.path.exists(tm):
             "The HBM roofline (bytes / measured copy bandwidth = 20.7 k it/s at N=8) ignores the ~29 us of serial work per round (inter-kernel gap 11.5,",
             "pull 3.7, fill/drain 10, tail 4 us; device timestamps above).  A fluid timeline of the co-resident workers with those measured terms",
             "reproduces the measured rates (`w1_launch` / `w2_lockstep` 12.6 k vs measured 12.7-12.8 k it/s: the two workers of a GPU run in lock-step, so",
-            "their serial phases do not hide behind each other) and predicts what the experimental kernels under `csrc/experimental/` can buy",
+            "their serial phases do not hide behind each other) and predicted (in round 1) what persistent / pipelined round kernels could buy",
             "(alpha = share of the HBM bandwidth one of two co-resident workers can draw alone, unknown until measured):", "",
             "| alpha | " + " | ".join(k for k in next(iter(t["by_alpha"].values()))) + " |",
             "|---|" + "---|" * len(next(iter(t["by_alpha"].values())))]
