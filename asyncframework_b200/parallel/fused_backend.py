@@ -177,9 +177,12 @@ class FusedEngine:
         if (self.device.type == "cuda" and n_local == 1 and not self.kernels[0].sim and _os.environ.get("AFB_E2E_OVERLAP", "1") != "0"
                 and hasattr(self.kernels[0].lib, "afb_e2e_create")):
             self._e2e_lib = self.kernels[0].lib
-            self._e2e = self._e2e_lib.afb_e2e_create()
-            if not self._e2e:
-                raise RuntimeError("afb_e2e_create failed (side streams / events for the end-to-end step)")
+            self._e2e = self._e2e_lib.afb_e2e_create() or None
+        if self._e2e is None and self._e2e_lib is not None:
+            import warnings
+            warnings.warn("afb_e2e_create failed (side streams / events): FusedEngine.step() keeps its copies on the launching stream")
+            self._e2e_lib = None
+        if self._e2e is not None:
             self._snap = torch.zeros(2, n_local, WORKER_CTL_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
             self._e2e_ptrs = (self._desc_dev.data_ptr(), self._desc_host.data_ptr(), self.wctl_all.data_ptr(),
                               [self._snap[0].data_ptr(), self._snap[1].data_ptr()],
@@ -337,6 +340,19 @@ class FusedEngine:
         d["delay_coeff"] = max(self.cfg.coeff, 0.0) if delay_coeff is None else float(delay_coeff)
         d["seq"] = rnd + 1
         cur = _dev.current_stream(self.device)
+        if self._e2e is not None and self._step_idx == 0:
+            # first step: if the side-stream copy cannot even be enqueued (nothing has been launched yet), fall back to the
+            # launching-stream plumbing for good instead of failing the run
+            rc = self._e2e_lib.afb_e2e_pre(self._e2e, slot, self._e2e_ptrs[0] + ds * ROUND_DESC_DTYPE.itemsize,
+                                           self._e2e_ptrs[1] + ds * ROUND_DESC_DTYPE.itemsize, ROUND_DESC_DTYPE.itemsize, int(cur.cuda_stream))
+            if rc != 0:
+                import warnings
+                warnings.warn(f"side-stream descriptor copy failed (cuda error {rc}): step() keeps its copies on the launching stream")
+                self._e2e_lib.afb_e2e_destroy(self._e2e)
+                self._e2e, self._e2e_lib = None, None
+            first_pre_done = self._e2e is not None
+        else:
+            first_pre_done = False
         if self._e2e is not None:
             # H2D on the descriptor stream (the round waits for it through an event), round on the launching stream, result
             # snapshot behind it, D2H on the result stream: the launching stream never waits for a copy engine
@@ -344,7 +360,8 @@ class FusedEngine:
             lib, ctx, sp = self._e2e_lib, self._e2e, int(cur.cuda_stream)
             desc_dev, desc_host, wctl, snaps, hosts = self._e2e_ptrs
             nb = ROUND_DESC_DTYPE.itemsize
-            check(lib.afb_e2e_pre(ctx, slot, desc_dev + ds * nb, desc_host + ds * nb, nb, sp), "end-to-end descriptor copy")
+            if not first_pre_done:
+                check(lib.afb_e2e_pre(ctx, slot, desc_dev + ds * nb, desc_host + ds * nb, nb, sp), "end-to-end descriptor copy")
             self.kernels[0].launch(self.streams[0])
             check(lib.afb_e2e_post(ctx, slot, wctl, snaps[slot], hosts[slot], self._snap[slot].numel(), sp), "end-to-end result copy")
         else:

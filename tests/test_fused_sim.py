@@ -343,3 +343,83 @@ def test_regularised_fused_rounds_on_the_simulator_match_the_updater_formulas():
         outs[upd] = eng.weights().clone()
     assert outs["squared_l2"].norm() < 0.9 * outs["simple"].norm()
     assert int((outs["l1"] == 0).sum()) >= int((outs["simple"] == 0).sum()) and outs["l1"].abs().sum() < outs["simple"].abs().sum()
+
+
+class _FakeE2eLib:
+    """Stands in for the CUDA side-stream plumbing (csrc/kernels/e2e_step.cu) so the host logic of FusedEngine.step() — slot
+    rotation, one descriptor copy per step, result copy into the pinned slot the parser reads, first-step fallback — runs on CPU."""
+
+    def __init__(self, eng, fail_first_pre=False):
+        self.eng, self.calls, self.fail_first_pre, self.destroyed = eng, [], fail_first_pre, False
+
+    def afb_e2e_pre(self, ctx, slot, desc_dev, desc_host, nbytes, stream):
+        self.calls.append(("pre", slot, desc_dev - self.eng._e2e_ptrs[0], nbytes))
+        if self.fail_first_pre and len(self.calls) == 1:
+            return 2
+        ds = (desc_dev - self.eng._e2e_ptrs[0]) // nbytes
+        self.eng._desc_dev[ds].copy_(self.eng._desc_host[ds])         # what the H2D copy does on the device
+        return 0
+
+    def afb_e2e_post(self, ctx, slot, wctl, snap, host, nbytes, stream):
+        self.calls.append(("post", slot, nbytes))
+        self.eng._ctl_host[slot].copy_(self.eng.wctl_all)            # what snapshot kernel + D2H do on the device
+        return 0
+
+    def afb_e2e_wait(self, ctx, slot):
+        self.calls.append(("wait", slot))
+        return 0
+
+    def afb_e2e_sync(self, ctx):
+        return 0
+
+    def afb_e2e_destroy(self, ctx):
+        self.destroyed = True
+
+
+def _engine_with_fake_side_streams(fail_first_pre=False):
+    d, n = 16, 400
+    parts = _parts(1, n, d, 3, True)
+    cfg = AsyncConfig(algorithm="asgd", num_features=d, num_rows=n, num_partitions=1, num_iterations=1 << 30, step_size=0.5,
+                      batch_rate=0.3, loss="logistic", seed=2, backend="fused", barrier="asp")
+    eng = FusedEngine(cfg, [_shard(parts[0], d, 0)], n, [0], device="cpu")
+    assert eng._e2e is None                                           # CPU engines never create the CUDA context
+    eng._e2e_ptrs = (1 << 20, 2 << 20, 3 << 20, [4 << 20, 5 << 20], [6 << 20, 7 << 20])
+    eng._snap = torch.zeros(2, 1, eng.wctl_all.shape[1], dtype=torch.uint8)
+    eng._e2e_lib = _FakeE2eLib(eng, fail_first_pre)
+    eng._e2e = 1
+    return eng
+
+
+@pytest.mark.parametrize("lag", [0, 1])
+def test_step_with_side_stream_plumbing_rotates_slots_and_returns_every_record(lag):
+    eng = _engine_with_fake_side_streams()
+    lib = eng._e2e_lib
+    ref = FusedEngine(eng.cfg, [eng.kernels[0].shard], eng.total_rows, [0], device="cpu")
+    got, want = [], []
+    for i in range(7):
+        r = eng.step(step_size=0.5 / (i + 1), lag=lag)
+        if r is not None:
+            got.append((r["k"], r["batch"], r["accepted"]))
+        w = ref.step(step_size=0.5 / (i + 1))
+        want.append((w["k"], w["batch"], w["accepted"]))
+    last = eng.flush_steps()
+    if last is not None:
+        got.append((last["k"], last["batch"], last["accepted"]))
+    assert got == want and torch.allclose(eng.weights(), ref.weights())
+    pres = [c for c in lib.calls if c[0] == "pre"]
+    posts = [c for c in lib.calls if c[0] == "post"]
+    assert len(pres) == 7 and len(posts) == 7                         # exactly one H2D and one D2H per step
+    assert [c[1] for c in pres] == [i & 1 for i in range(7)] and [c[1] for c in posts] == [i & 1 for i in range(7)]
+    assert [c[2] for c in pres] == [16 * i for i in range(7)] and all(c[3] == 16 for c in pres)     # descriptor ring slot = round % slots
+    assert all(c[2] == eng.wctl_all.shape[1] for c in posts)
+    eng._e2e = None                                                   # nothing to destroy for the fake
+
+
+def test_first_step_falls_back_to_the_launching_stream_when_the_side_stream_copy_fails():
+    eng = _engine_with_fake_side_streams(fail_first_pre=True)
+    lib = eng._e2e_lib
+    with pytest.warns(UserWarning, match="side-stream descriptor copy failed"):
+        r = eng.step(step_size=0.1)
+    assert r["k"] == 1 and r["accepted"] == 1 and eng._e2e is None and lib.destroyed
+    r = eng.step(step_size=0.1)                                        # later steps use the same-stream path
+    assert r["k"] == 2 and [c[0] for c in lib.calls] == ["pre"]
