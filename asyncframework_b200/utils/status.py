@@ -42,6 +42,8 @@ class AppStatusStore:
         self._lock = threading.Lock()
         self._contexts: List[Any] = []
         self._scheduler = None
+        self.killed_tasks = 0
+        self.allocation_events: List[dict] = []
 
     # ------------------------------------------------------------------ wiring
     def attach(self, scheduler, environment: Optional[dict] = None) -> "AppStatusStore":
@@ -80,6 +82,16 @@ class AppStatusStore:
                 while len(self.jobs) > self.max_jobs:
                     self.jobs.popitem(last=False)
                 return
+            if kind == "executors_resized":                  # dynamic allocation applied a new executor target
+                self.allocation_events.append({"time": now, "from": ev.get("from"), "to": ev.get("to"), "reason": ev.get("reason")})
+                del self.allocation_events[:-200]
+                return
+            if kind == "task_killed":                        # the losing copy of a speculated task was interrupted
+                self.killed_tasks += 1
+                j = self.jobs.get(ev.get("job"))
+                if j is not None:
+                    j["num_killed_tasks"] = j.get("num_killed_tasks", 0) + 1
+                return
             if kind == "executor_lost":
                 ex = self._executor(ev["executor"])
                 ex["active"], ex["removed"], ex["active_tasks"] = False, now, 0
@@ -105,6 +117,9 @@ class AppStatusStore:
                 job["run_ms"].append(run_ms)
                 m = ev.get("metrics") or {}
                 job["result_bytes"] += int(m.get("result_bytes", 0) or 0)
+                # shuffle sorters that spilled (TaskMetrics.memoryBytesSpilled / diskBytesSpilled, stage page "Spill" columns)
+                job["memory_bytes_spilled"] = job.get("memory_bytes_spilled", 0) + int(m.get("memory_bytes_spilled", 0) or 0)
+                job["disk_bytes_spilled"] = job.get("disk_bytes_spilled", 0) + int(m.get("disk_bytes_spilled", 0) or 0)
                 t = job["tasks"].setdefault(p, {"partition": p})
                 t.update(status="SUCCESS", run_ms=run_ms, executor=ev.get("executor"), metrics=dict(m), finish_time=now)
                 ex = self._executor(ev.get("executor"))
@@ -160,6 +175,8 @@ class AppStatusStore:
                                "task_binary_bytes", "result_bytes")}
         if j.get("error"):
             v["error"] = j["error"]
+        for k in ("memory_bytes_spilled", "disk_bytes_spilled", "num_killed_tasks"):
+            v[k] = j.get(k, 0)
         v["task_run_ms"] = _quantiles(j["run_ms"])
         if j["completion_time"] is not None:
             v["duration_ms"] = (j["completion_time"] - j["submission_time"]) * 1e3
@@ -223,7 +240,10 @@ class AppStatusStore:
                 by[j["status"]] = by.get(j["status"], 0) + 1
             tasks = sum(j["num_completed_tasks"] for j in self.jobs.values())
             fails = sum(j["num_failed_tasks"] for j in self.jobs.values())
+            spilled = sum(j.get("disk_bytes_spilled", 0) for j in self.jobs.values())
         return {"application": self.application_info(), "jobs_by_status": by, "completed_tasks": tasks, "failed_task_attempts": fails,
+                "killed_task_attempts": self.killed_tasks, "disk_bytes_spilled": spilled,
+                "executor_allocation_events": list(self.allocation_events[-20:]),
                 "executors": len(self.executors), "active_executors": sum(1 for e in self.executors.values() if e["active"])}
 
     def stop(self) -> None:

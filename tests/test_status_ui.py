@@ -173,3 +173,23 @@ def test_task_profiler_collects_cprofile_stats_per_job(master, tmp_path):
         sc.dump_profiles(str(tmp_path))
         loaded = pstats.Stats(str(tmp_path / f"job_{jobs[0]}.pstats"))
         assert any(f[2] == "busy" for f in loaded.stats)
+
+
+def test_status_store_aggregates_spills_killed_attempts_and_allocation_events():
+    """AppStatusListener counterparts for the round-2 scheduler events: spill bytes of a job's tasks, `task_killed` (the losing
+    copy of a speculated task) and `executors_resized` (dynamic allocation) show up in the job view and the summary."""
+    from asyncframework_b200.utils.status import AppStatusStore
+    st = AppStatusStore("t")
+    st({"event": "job_start", "job": 1, "partitions": [0, 1]})
+    for p, spill in ((0, 1000), (1, 0)):
+        st({"event": "task_start", "job": 1, "partition": p, "attempt": 0, "executor": p})
+        st({"event": "task_end", "job": 1, "partition": p, "executor": p, "run_ms": 3.0,
+            "metrics": {"result_bytes": 10, "memory_bytes_spilled": 4 * spill, "disk_bytes_spilled": spill, "spills": int(spill > 0)}})
+    st({"event": "task_killed", "job": 1, "partition": 1, "attempt": 0, "executor": 1, "reason": "interrupted", "ran_ms": 12.0})
+    st({"event": "job_end", "job": 1})
+    st({"event": "executors_resized", "from": 1, "to": 4, "reason": "dynamic_allocation"})
+    j = st.job(1)
+    assert j["status"] == "SUCCEEDED" and j["memory_bytes_spilled"] == 4000 and j["disk_bytes_spilled"] == 1000 and j["num_killed_tasks"] == 1
+    s = st.summary()
+    assert s["killed_task_attempts"] == 1 and s["disk_bytes_spilled"] == 1000
+    assert [(e["from"], e["to"]) for e in s["executor_allocation_events"]] == [(1, 4)]
