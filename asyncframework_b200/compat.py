@@ -125,6 +125,11 @@ class MLUtils(_MLUtils):
         from .data.libsvm import save_as_libsvm_file
         save_as_libsvm_file(data, dir_path)
 
+    kFold = staticmethod(_MLUtils.k_fold)
+    loadVectors = staticmethod(_MLUtils.load_vectors)
+    loadLabeledPoints = staticmethod(_MLUtils.load_labeled_points)
+    appendBias = staticmethod(_MLUtils.append_bias)
+
 
 # --- PySpark keyword spellings on the train() entry points ---------------------------------------------------------
 _KW = {"miniBatchFraction": "mini_batch_fraction", "initialWeights": "initial_weights", "regParam": "reg_param", "regType": "reg_type",

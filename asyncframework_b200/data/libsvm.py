@@ -184,6 +184,47 @@ class MLUtils:
         return DenseVector(torch.cat([v.values, torch.ones(1, dtype=v.values.dtype)]), dtype=v.values.dtype)
 
     @staticmethod
+    def k_fold(ds, num_folds: int, seed: int = 42):
+        """``MLUtils.kFold`` (MLUtils.scala:232-249): ``num_folds`` pairs ``(training, validation)``; fold f's validation set is
+        the records whose per-record uniform draw falls in ``[(f-1)/k, f/k)`` (BernoulliCellSampler), its training set the
+        complement — the k validation sets partition the data.  The draw is a counter hash of (seed, partition, position), so
+        every fold sees the same draw for the same record and a retried task reproduces it."""
+        from ..core.sampler import uniform01
+        import numpy as np
+        k = int(num_folds)
+        if k < 2:
+            raise ValueError("k_fold needs at least two folds")
+
+        def cell(lo, hi, complement):
+            def compute(p, t):
+                recs = list(ds.iterator(p, t))
+                if not recs:
+                    return iter(())
+                u = uniform01(int(seed) * 1_000_003 + p, np.arange(len(recs), dtype=np.int64))
+                inside = (u >= lo) & (u < hi)
+                keep = ~inside if complement else inside
+                return (r for r, kp in zip(recs, keep.tolist()) if kp)
+            return ds._derive(compute, None, "k_fold")
+        return [(cell((f - 1) / k, f / k, True), cell((f - 1) / k, f / k, False)) for f in range(1, k + 1)]
+
+    @staticmethod
+    def load_vectors(sc, path: str, min_partitions=None):
+        """``MLUtils.loadVectors`` (MLUtils.scala:197-205): text files written by ``RDD[Vector].saveAsTextFile``."""
+        from ..linalg.vectors import Vectors
+        return sc.text_file(path, min_partitions).filter(lambda l: l.strip() != "").map(Vectors.parse)
+
+    @staticmethod
+    def load_labeled_points(sc, path: str, min_partitions=None):
+        """``MLUtils.loadLabeledPoints`` (MLUtils.scala:215-224): text files written by ``RDD[LabeledPoint].saveAsTextFile``
+        (also the pre-1.0 ``label,f0 f1 ...`` lines)."""
+        from ..linalg.vectors import LabeledPoint
+        return sc.text_file(path, min_partitions).filter(lambda l: l.strip() != "").map(LabeledPoint.parse)
+
+    kFold = k_fold
+    loadVectors = load_vectors
+    loadLabeledPoints = load_labeled_points
+
+    @staticmethod
     def log1p_exp(x: float) -> float:
         """MLUtils.log1pExp (MLUtils.scala:548-554): numerically stable log(1+e^x)."""
         import math

@@ -72,6 +72,10 @@ class DenseVector(Vector):
     def __repr__(self) -> str:
         return f"DenseVector({self.values.tolist()})"
 
+    def __str__(self) -> str:
+        """Spark's text form ``[v0,v1,...]`` (what ``RDD[Vector].saveAsTextFile`` writes and ``Vectors.parse`` reads)."""
+        return "[" + ",".join(repr(float(v)) for v in self.values.tolist()) + "]"
+
 
 class SparseVector(Vector):
     """``size, indices:int32[], values[]`` with strictly increasing indices."""
@@ -114,6 +118,11 @@ class SparseVector(Vector):
     def __repr__(self) -> str:
         return f"SparseVector({self._size}, {self.indices.tolist()}, {self.values.tolist()})"
 
+    def __str__(self) -> str:
+        """Spark's text form ``(size,[i0,i1,...],[v0,v1,...])``."""
+        return (f"({self._size},[" + ",".join(str(int(i)) for i in self.indices.tolist()) + "],["
+                + ",".join(repr(float(v)) for v in self.values.tolist()) + "])")
+
 
 class Vectors:
     """Factory methods, named like ``org.apache.spark.mllib.linalg.Vectors``."""
@@ -136,6 +145,12 @@ class Vectors:
             pairs = sorted((int(i), float(v)) for i, v in pairs)
             return SparseVector(size, [p[0] for p in pairs], [p[1] for p in pairs], dtype=dtype, device=device)
         raise TypeError("Vectors.sparse(size, indices, values) or Vectors.sparse(size, pairs)")
+
+    @staticmethod
+    def parse(s: str, dtype: torch.dtype = torch.float64) -> Vector:
+        """``Vectors.parse`` (linalg/Vectors.scala:389-410, util/NumericParser.scala): ``[1.0,2.0]`` -> dense,
+        ``(4,[0,2],[1.0,3.0])`` -> sparse."""
+        return _vector_from_parsed(_parse_numeric(s), dtype)
 
     @staticmethod
     def zeros(size: int, dtype: torch.dtype = torch.float64, device=None) -> DenseVector:
@@ -162,3 +177,88 @@ class LabeledPoint:
 
     def __repr__(self) -> str:
         return f"LabeledPoint({self.label}, {self.features!r})"
+
+    def __str__(self) -> str:
+        """Spark's text form ``(label,features)`` (regression/LabeledPoint.scala:41-43)."""
+        return f"({float(self.label)!r},{self.features})"
+
+    @staticmethod
+    def parse(s: str, dtype: torch.dtype = torch.float64) -> "LabeledPoint":
+        """``LabeledPoint.parse`` (regression/LabeledPoint.scala:60-74): ``(label,[...])`` / ``(label,(size,[..],[..]))`` or the
+        pre-1.0 dense form ``label,f0 f1 f2``."""
+        s = s.strip()
+        if s.startswith("("):
+            parsed = _parse_numeric(s)
+            if not (isinstance(parsed, tuple) and len(parsed) == 2 and isinstance(parsed[0], float)):
+                raise ValueError(f"Cannot parse {s!r} as a labeled point")
+            return LabeledPoint(parsed[0], _vector_from_parsed(parsed[1], dtype))
+        label, _, rest = s.partition(",")
+        return LabeledPoint(float(label), DenseVector([float(t) for t in rest.split()], dtype=dtype))
+
+
+def _parse_numeric(s: str):
+    """The grammar of util/NumericParser.scala: numbers, ``[a,b,...]`` arrays (-> list of floats) and ``(x,y,...)`` tuples
+    (-> tuple), nested.  Raises ``ValueError`` on anything else."""
+    s = s.strip()
+    pos = 0
+
+    def fail(msg):
+        raise ValueError(f"Cannot parse {s!r}: {msg} at position {pos}")
+
+    def skip():
+        nonlocal pos
+        while pos < len(s) and s[pos].isspace():
+            pos += 1
+
+    def value():
+        nonlocal pos
+        skip()
+        if pos >= len(s):
+            fail("unexpected end")
+        c = s[pos]
+        if c in "[(":
+            close = "]" if c == "[" else ")"
+            pos += 1
+            items = []
+            skip()
+            if pos < len(s) and s[pos] == close:
+                pos += 1
+                return items if c == "[" else tuple(items)
+            while True:
+                items.append(value())
+                skip()
+                if pos >= len(s):
+                    fail(f"missing {close!r}")
+                if s[pos] == ",":
+                    pos += 1
+                    continue
+                if s[pos] == close:
+                    pos += 1
+                    break
+                fail(f"unexpected {s[pos]!r}")
+            if c == "[":
+                if not all(isinstance(x, float) for x in items):
+                    fail("arrays hold numbers only")
+                return items
+            return tuple(items)
+        start = pos
+        while pos < len(s) and s[pos] not in ",[]()" and not s[pos].isspace():
+            pos += 1
+        try:
+            return float(s[start:pos])
+        except ValueError:
+            fail(f"bad number {s[start:pos]!r}")
+
+    out = value()
+    skip()
+    if pos != len(s):
+        fail("trailing characters")
+    return out
+
+
+def _vector_from_parsed(parsed, dtype: torch.dtype = torch.float64) -> Vector:
+    if isinstance(parsed, list):
+        return DenseVector(parsed, dtype=dtype)
+    if isinstance(parsed, tuple) and len(parsed) == 3 and isinstance(parsed[0], float) and isinstance(parsed[1], list) and isinstance(parsed[2], list):
+        return SparseVector(int(parsed[0]), [int(i) for i in parsed[1]], parsed[2], dtype=dtype)
+    raise ValueError(f"Cannot parse {parsed!r} as a vector")

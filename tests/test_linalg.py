@@ -173,3 +173,22 @@ def test_row_matrix_gramian_covariance_pca_svd_multiply_match_numpy():
             RowMatrix(dense).compute_svd(6)
         with pytest.raises(ValueError):
             RowMatrix(dense).multiply(DenseMatrix.zeros(4, 2))
+
+
+def test_vector_and_labeled_point_text_forms_round_trip():
+    """Vectors.parse / LabeledPoint.parse (NumericParser grammar) read back what str() — Spark's saveAsTextFile form — writes."""
+    import pytest
+    from asyncframework_b200.linalg.vectors import LabeledPoint, Vectors
+    dv = Vectors.dense(1.5, -2.0, 0.0, 3e-7)
+    sv = Vectors.sparse(6, [1, 4], [2.5, -1.0])
+    assert str(dv) == "[1.5,-2.0,0.0,3e-07]" and str(sv) == "(6,[1,4],[2.5,-1.0])"
+    assert Vectors.parse(str(dv)) == dv and Vectors.parse(str(sv)) == sv and Vectors.parse(" [ 1.0 , 2.0 ] ") == Vectors.dense(1.0, 2.0)
+    assert Vectors.parse("[]").size == 0 and Vectors.parse("(3,[],[])") == Vectors.sparse(3, [], [])
+    for lp in (LabeledPoint(1.0, dv), LabeledPoint(-3.5, sv)):
+        back = LabeledPoint.parse(str(lp))
+        assert back.label == lp.label and back.features == lp.features
+    old = LabeledPoint.parse("1.0,0.5 2.5 -1")                     # the pre-1.0 dense line format
+    assert old.label == 1.0 and old.features == Vectors.dense(0.5, 2.5, -1.0)
+    for bad in ("[1.0,2.0", "(1.0,[1.0,x])", "[1.0](", "(4,[0],[1.0],[2.0])", "(1.0)"):
+        with pytest.raises(ValueError):
+            (LabeledPoint.parse if bad.startswith("(1.0") else Vectors.parse)(bad)

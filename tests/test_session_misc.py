@@ -78,3 +78,31 @@ def test_compat_layer_and_transcribed_example():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main(numIteration=25) < 0.1            # record-level closures, the reference's own spelling
+
+
+def test_mlutils_k_fold_and_text_loaders(tmp_path):
+    """MLUtils.kFold: the k validation sets partition the data, each training set is the complement; loadVectors /
+    loadLabeledPoints read what saveAsTextFile wrote (MLUtilsSuite "kFold", "loadVectors", "loadLabeledPoints")."""
+    from asyncframework_b200 import AsyncSession
+    from asyncframework_b200.data.libsvm import MLUtils
+    from asyncframework_b200.linalg.vectors import LabeledPoint, Vectors
+    with AsyncSession("local[2]") as sc:
+        data = sc.parallelize(range(1, 101), 3)
+        for k in (2, 5, 10):
+            folds = MLUtils.kFold(data, k, 42)
+            assert len(folds) == k
+            seen = []
+            for train, val in folds:
+                v, t = val.collect(), train.collect()
+                assert sorted(v + t) == list(range(1, 101)) and not set(v) & set(t)
+                assert 0 < len(v) < 100 if k < 10 else len(v) < 100
+                seen += v
+            assert sorted(seen) == list(range(1, 101))                    # validation sets: a partition of the data
+            assert [val.collect() for _, val in MLUtils.k_fold(data, k, 42)] == [val.collect() for _, val in folds]   # seeded
+        vecs = [Vectors.dense(1.0, 2.0), Vectors.sparse(4, [0, 3], [1.5, -2.0])]
+        sc.parallelize(vecs, 2).save_as_text_file(str(tmp_path / "vecs"))
+        assert sorted(map(str, MLUtils.loadVectors(sc, str(tmp_path / "vecs")).collect())) == sorted(map(str, vecs))
+        pts = [LabeledPoint(1.0, vecs[0]), LabeledPoint(0.0, vecs[1])]
+        sc.parallelize(pts, 2).save_as_text_file(str(tmp_path / "pts"))
+        back = sorted(MLUtils.loadLabeledPoints(sc, str(tmp_path / "pts")).collect(), key=lambda lp: lp.label)
+        assert [(lp.label, str(lp.features)) for lp in back] == [(0.0, str(vecs[1])), (1.0, str(vecs[0]))]
