@@ -78,6 +78,43 @@ class LogisticRegressionDataGenerator:
         return ShardedDataset.from_arrays(scheduler, X, y, num_partitions, dtype=dtype, device=device, name="logistic")
 
 
+class SVMDataGenerator:
+    """``mllib/util/SVMDataGenerator.scala``: features U[-1, 1)^d, label 1 when ``x . w_true + 0.1 * N(0, 1) >= 0`` else 0,
+    ``w_true ~ N(0, 1)^d`` drawn from a fixed global seed."""
+
+    @staticmethod
+    def generate_svm_arrays(n: int, d: int = 2, seed: int = 42, weights_seed: int = 94720):
+        w = np.random.RandomState(weights_seed).randn(d)
+        rng = np.random.RandomState(seed)
+        X = rng.rand(n, d) * 2.0 - 1.0
+        y = ((X @ w + 0.1 * rng.randn(n)) >= 0).astype(np.float64)
+        return X, y, w
+
+    @staticmethod
+    def generate_svm_dataset(scheduler, n: int = 1000, d: int = 2, num_partitions: int = 2, seed: int = 42,
+                             dtype=torch.float64, device=None):
+        X, y, w = SVMDataGenerator.generate_svm_arrays(n, d, seed)
+        ds = ShardedDataset.from_arrays(scheduler, X, y, num_partitions, dtype=dtype, device=device, name="svm")
+        ds.true_weights = w  # type: ignore[attr-defined]
+        return ds
+
+    @staticmethod
+    def main(argv=None) -> int:
+        """``SVMGenerator <master> <output_dir> [num_examples] [num_features] [num_partitions]``: writes labeled points as text."""
+        import sys
+        from ..core.session import AsyncSession
+        a = list(sys.argv[1:] if argv is None else argv)
+        if len(a) < 2:
+            print("Usage: SVMGenerator <master> <output_dir> [num_examples] [num_features] [num_partitions]")
+            return 1
+        n, d, parts = (int(a[2]) if len(a) > 2 else 1000), (int(a[3]) if len(a) > 3 else 2), (int(a[4]) if len(a) > 4 else 2)
+        with AsyncSession(a[0], app_name="SVMGenerator") as sc:
+            X, y, _ = SVMDataGenerator.generate_svm_arrays(n, d)
+            pts = [LabeledPoint(float(y[i]), DenseVector(X[i])) for i in range(n)]
+            sc.parallelize(pts, parts).save_as_text_file(a[1])
+        return 0
+
+
 def generate_gd_input(offset: float, scale: float, n_points: int, seed: int) -> List[LabeledPoint]:
     """GradientDescentSuite.generateGDInput: x1 ~ N(0,1); y = 1{sigmoid(offset + scale*x1) > u}."""
     rng = np.random.RandomState(seed)

@@ -106,3 +106,19 @@ def test_mlutils_k_fold_and_text_loaders(tmp_path):
         sc.parallelize(pts, 2).save_as_text_file(str(tmp_path / "pts"))
         back = sorted(MLUtils.loadLabeledPoints(sc, str(tmp_path / "pts")).collect(), key=lambda lp: lp.label)
         assert [(lp.label, str(lp.features)) for lp in back] == [(0.0, str(vecs[1])), (1.0, str(vecs[0]))]
+
+
+def test_svm_data_generator_cli_writes_loadable_labeled_points(tmp_path):
+    """SVMDataGenerator: separable-with-noise data; its command line writes text that loadLabeledPoints reads back and an SVM fits."""
+    from asyncframework_b200 import AsyncSession
+    from asyncframework_b200.data.generators import SVMDataGenerator
+    from asyncframework_b200.data.libsvm import MLUtils
+    X, y, w = SVMDataGenerator.generate_svm_arrays(2000, 3, seed=1)
+    agree = ((X @ w >= 0) == (y > 0.5)).mean()
+    assert agree > 0.93 and 0.3 < y.mean() < 0.7                     # labels follow the true hyperplane up to the 0.1 noise
+    out = tmp_path / "svm"
+    assert SVMDataGenerator.main(["local[2]", str(out), "300", "4", "3"]) == 0
+    assert SVMDataGenerator.main(["local[2]"]) == 1
+    with AsyncSession("local[2]") as sc:
+        pts = MLUtils.load_labeled_points(sc, str(out)).collect()
+        assert len(pts) == 300 and all(p.features.size == 4 and p.label in (0.0, 1.0) for p in pts)
