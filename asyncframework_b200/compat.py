@@ -185,7 +185,7 @@ _alias(SparkContext, setJobGroup="set_job_group", clearJobGroup="clear_job_group
        getExecutorMemoryStatus="get_executor_memory_status", statusTracker=property(lambda self: self.status_tracker),
        addFile="add_file", wholeTextFiles="whole_text_files", pickleFile="pickle_file", emptyRDD="empty_dataset",
        applicationId=property(lambda self: self.application_id), uiWebUrl=property(lambda self: self.ui_web_url))
-_alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator",
+_alias(SparkContext, longAccumulator="long_accumulator", doubleAccumulator="double_accumulator", collectionAccumulator="collection_accumulator",
        cancelJob=lambda self, job_id: self.scheduler.cancel_job(job_id), cancelAllJobs=lambda self: self.scheduler.cancel_all_jobs())
 
 def _checkpoint(self, directory: Optional[str] = None):

@@ -74,17 +74,70 @@ class Accumulator:
 
     # ---- shipping to executor processes: a write-only proxy with the same id ----------------------------------------
     def __reduce__(self):
-        return (_proxy, (self.acc_id, self.name, self.zero, self._op))
+        return (_proxy, (type(self), self.acc_id, self.name, self.zero, self._op))
 
     def __repr__(self) -> str:
-        return f"Accumulator(id={self.acc_id}, name={self.name!r}, value={self._value!r})"
+        return f"{type(self).__name__}(id={self.acc_id}, name={self.name!r}, value={self.value if self._on_driver else '<task side>'!r})"
 
 
-def _proxy(acc_id: int, name, zero, op) -> Accumulator:
+def _pair_add(a, b):
+    return (a[0] + b[0], a[1] + b[1])
+
+
+class NumericAccumulator(Accumulator):
+    """``LongAccumulator`` / ``DoubleAccumulator`` (AccumulatorV2.scala:290-420): besides the running ``sum`` (= ``value``) the
+    driver can read how many values were added (``count``) and their mean (``avg``)."""
+
+    def __init__(self, zero: Any = 0, name: Optional[str] = None):
+        super().__init__((zero, 0), name, _pair_add)
+
+    def add(self, v: Any) -> None:
+        super().add((v, 1))
+
+    __iadd__ = lambda self, v: (self.add(v), self)[1]   # noqa: E731
+
+    @property
+    def value(self) -> Any:
+        return Accumulator.value.fget(self)[0]
+
+    @property
+    def sum(self) -> Any:
+        return self.value
+
+    @property
+    def count(self) -> int:
+        return Accumulator.value.fget(self)[1]
+
+    @property
+    def avg(self) -> float:
+        s, n = Accumulator.value.fget(self)
+        return float("nan") if n == 0 else s / n
+
+
+def _list_add(a, b):
+    return a + (b if isinstance(b, list) else [b])
+
+
+class CollectionAccumulator(Accumulator):
+    """``sc.collectionAccumulator`` (AccumulatorV2.scala:446-480): tasks append elements, the driver reads the list (order across
+    tasks is the order in which their results were merged)."""
+
+    def __init__(self, name: Optional[str] = None):
+        super().__init__([], name, _list_add)
+
+    def add(self, v: Any) -> None:
+        super().add([v])
+
+    @property
+    def value(self) -> list:
+        return list(Accumulator.value.fget(self))
+
+
+def _proxy(cls, acc_id: int, name, zero, op) -> Accumulator:
     existing = _registry.get(acc_id)
     if existing is not None:                      # unpickled in the driver process itself (in-process scheduler, tests)
         return existing
-    a = Accumulator.__new__(Accumulator)
+    a = cls.__new__(cls)
     a.acc_id, a.name, a.zero, a._op = acc_id, name, zero, op
     a._value, a._lock, a._on_driver = zero, threading.Lock(), False
     return a

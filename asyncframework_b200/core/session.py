@@ -257,12 +257,17 @@ class AsyncSession:
 
     def long_accumulator(self, name: Optional[str] = None):
         """``sc.longAccumulator``: tasks ``add``, the driver reads ``.value`` (updates of successful tasks only, exactly once)."""
-        from .accumulator import Accumulator
-        return Accumulator(0, name)
+        from .accumulator import NumericAccumulator
+        return NumericAccumulator(0, name)
 
     def double_accumulator(self, name: Optional[str] = None):
-        from .accumulator import Accumulator
-        return Accumulator(0.0, name)
+        from .accumulator import NumericAccumulator
+        return NumericAccumulator(0.0, name)
+
+    def collection_accumulator(self, name: Optional[str] = None):
+        """``sc.collectionAccumulator``: tasks append elements, the driver reads the list."""
+        from .accumulator import CollectionAccumulator
+        return CollectionAccumulator(name)
 
     def accumulator(self, zero, name: Optional[str] = None, op=None):
         """General accumulator: ``op`` must be associative and commutative (default ``+``)."""

@@ -535,3 +535,24 @@ def test_rpc_message_max_size_catches_data_captured_by_a_closure():
             ds.map(lambda i: float(big[i])).collect()
         bc = sc.broadcast(big)                                                   # the fix the message recommends
         assert ds.map(lambda i: float(bc.value[i])).collect() == [0.0] * 8
+
+
+def test_numeric_and_collection_accumulators_over_executor_processes(cluster):
+    """LongAccumulator sum / count / avg and CollectionAccumulator (AccumulatorV2.scala:290-480) with updates travelling back
+    from executor processes with the task results."""
+    from asyncframework_b200.core.accumulator import CollectionAccumulator, NumericAccumulator
+    acc, odd = NumericAccumulator(0, "x"), CollectionAccumulator("odd")
+    ds = ShardedDataset.from_records(cluster, list(range(1, 41)), 4)
+
+    def f(x):
+        acc.add(x)
+        if x % 2:
+            odd.add(x)
+        return x
+    assert ds.map(f).count() == 40
+    assert acc.value == acc.sum == 820 and acc.count == 40 and acc.avg == 20.5
+    assert sorted(odd.value) == list(range(1, 41, 2))
+    acc.reset()
+    assert acc.count == 0 and acc.value == 0 and acc.avg != acc.avg          # NaN on an empty accumulator
+    with pytest.raises(Exception):
+        ds.map(lambda x: len(odd.value)).collect()                            # tasks may only add

@@ -336,6 +336,10 @@ def test_accumulators_count_successful_attempts_exactly_once():
             return x
         assert ds.map(f).count() == 100
         assert rows.value == 100 and big.value == float(sum(range(100)))
+        assert rows.count == 100 and rows.avg == 1.0 and big.count == 100 and big.avg == 49.5      # LongAccumulator.count / avg
+        names = sc.collection_accumulator("names")
+        ds.foreach(lambda x: names.add(x) if x % 25 == 0 else None)
+        assert sorted(names.value) == [0, 25, 50, 75]
         # a task that fails on its first attempt after adding: only the successful retry is counted
         attempts = {}
 
