@@ -176,13 +176,15 @@ class StatusServer:
     def _index(self):
         s = self.store
         info = s.summary()
-        jobs = [{**{k: j.get(k) for k in ("job_id", "status", "num_tasks", "num_completed_tasks", "num_failed_tasks", "duration_ms")},
+        jobs = [{**{k: j.get(k) for k in ("job_id", "status", "num_tasks", "num_completed_tasks", "num_failed_tasks", "num_killed_tasks",
+                                          "disk_bytes_spilled", "duration_ms")},
                  "details": f"/jobs/{j['job_id']}"} for j in s.job_list()[:50]]
         page = (f"<html><head><title>{html.escape(s.app_name)}</title></head><body><h2>{html.escape(s.app_name)} "
                 f"<small>({html.escape(s.app_id)})</small></h2><p>{html.escape(json.dumps(info['jobs_by_status']))} &middot; "
                 f"{info['completed_tasks']} tasks &middot; {info['active_executors']}/{info['executors']} executors</p>"
                 + _table("Jobs (latest 50)", jobs) + _table("Executors", s.executor_list())
                 + _table("Cached datasets", s.rdd_storage()) + _table("ASYNC workers", s.async_workers())
+                + _table("Executor allocation (dynamic)", info.get("executor_allocation_events") or [])
                 + "<p>REST: <code>/api/v1/applications</code>, metrics: <code>/metrics/json</code>, <code>/metrics/prometheus</code></p></body></html>")
         return ("text/html", page)
 
