@@ -465,3 +465,124 @@ def explore(P: int = 2, G: int = 3, n_chunks: int = 7, rounds: int = 4, mode: st
     assert sv.avail == P, f"avail_count {sv.avail} != P"
     assert sorted(r[0] for r in sv.ring) == list(range(finished)), "result-ring sequence numbers are not a permutation of the clock"
     return {"steps": steps, "accepted": accepted, "finished": finished, "k": sv.k}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-side ASYNCbarrier (csrc/include/afb_round_impl.cuh::gate_wait_warp): bucket rule with WAVE semantics, the watchdog's
+# dynamic threshold, the SSP rule.  One generator per worker = the elected gate warp of its pulling CTA; every access to
+# shared state is one step, in the order of the CUDA code.
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class GateState:
+    P: int
+    threshold: int                    # RoundParams.gate_threshold = floor(P * beta); 0 = no bucket gate
+    ssp_bound: int = -1               # RoundParams.ssp_bound; < 0 = off
+    wave: int = 0                     # ServerCtl.wave
+    avail: int = 0                    # ServerCtl.avail_count
+    gate_dyn: int = 0                 # ServerCtl.gate_dyn (watchdog override; 0 = none)
+    clock: int = 0
+    staleness: List[int] = field(default_factory=list)      # WorkerSlot.staleness (last reported)
+    runs: List[tuple] = field(default_factory=list)         # (worker, wave joined, avail seen by the opener or None)
+    opened: List[tuple] = field(default_factory=list)       # (wave opened, avail read that justified it, threshold used)
+
+    def __post_init__(self):
+        self.avail = self.P
+        self.staleness = [0] * self.P
+
+
+def gate_worker(gs: GateState, wid: int, rounds: int, work_steps: int = 3, dies_after: Optional[int] = None,
+                bug: Optional[str] = None) -> Generator:
+    """``rounds`` rounds of one worker: gate -> busy (avail_count - 1) -> work -> finish (clock, staleness, avail_count + 1).
+    ``dies_after``: the worker stops for good after that many rounds WITHOUT becoming available again mid-round (a rank that
+    was killed while busy).  Mutations: ``no_wave_check`` (threshold test only: the pre-wave gate), ``cas_blind`` (opens the
+    next wave without the compare)."""
+    wave_seen = 0
+    last_fail = None
+    for r in range(rounds):
+        if dies_after is not None and r == dies_after:
+            gs.avail -= 1                                 # dies busy: it never reports back
+            return
+        # ---- gate_wait_warp
+        while True:
+            open_ = True
+            if gs.threshold > 0:
+                thr = gs.threshold
+                dyn = gs.gate_dyn; yield
+                if 0 < dyn < thr:
+                    thr = dyn
+                w = gs.wave; yield
+                if bug != "no_wave_check" and w != wave_seen:
+                    wave_seen = w                         # a wave opened since this worker last ran: join it
+                else:
+                    a = gs.avail; yield
+                    if a >= thr:
+                        if bug == "no_wave_check":
+                            pass                          # the round-1 gate: run whenever the threshold holds
+                        elif bug == "cas_blind":
+                            gs.wave = w + 1; wave_seen = w + 1
+                            gs.opened.append((w + 1, a, thr)); yield
+                        else:
+                            old = gs.wave                 # atom.cas.acq_rel.sys(wave, w, w + 1)
+                            if old == w:
+                                gs.wave = w + 1
+                                gs.opened.append((w + 1, a, thr))
+                            wave_seen = w + 1 if old == w else old
+                            yield
+                    else:
+                        open_ = False
+            if open_ and gs.ssp_bound >= 0:
+                m = 0
+                for q in range(gs.P):                     # one sweep of the status table (not atomic as a whole)
+                    m = max(m, gs.staleness[q]); yield
+                if m > gs.ssp_bound:
+                    open_ = False
+            if open_:
+                break
+            # a failed attempt is a "spin" for the deadlock detector only if nothing it depends on has changed since the
+            # previous failed attempt (its reads may be stale with respect to workers that have just finished)
+            snap = (gs.wave, gs.avail, gs.gate_dyn, tuple(gs.staleness))
+            yield SPIN if snap == last_fail else None
+            last_fail = snap
+        last_fail = None
+        gs.runs.append((wid, wave_seen))
+        # ---- pull: the worker becomes busy, remembers the clock it read
+        ts = gs.clock
+        gs.avail -= 1; yield
+        for _ in range(work_steps):
+            yield
+        # ---- finish: logical clock, own staleness, available again
+        st = gs.clock - ts
+        gs.clock += 1; yield
+        gs.staleness[wid] = st; yield
+        gs.avail += 1; yield
+
+
+def explore_gate(P: int = 4, threshold: int = 2, rounds: int = 5, seed: int = 0, burst: int = 1, ssp_bound: int = -1,
+                 dead: Optional[Dict[int, int]] = None, watchdog_after: Optional[int] = None, bug: Optional[str] = None,
+                 work_steps: int = 3) -> GateState:
+    """One random schedule of P gate warps.  ``dead`` = {worker: rounds completed before it dies}; ``watchdog_after`` = number
+    of scheduler steps after which the watchdog declares the dead workers dead (lowers ``gate_dyn`` to threshold - #dead, like
+    ``FusedEngine.declare_dead``).  Checks: a worker joins each wave at most once; every wave was opened on a threshold that
+    held when it was read; the clock counts every finished round; everybody idle at the end; no deadlock."""
+    rng = random.Random(seed)
+    gs = GateState(P, threshold, ssp_bound)
+    dead = dead or {}
+    gens = [gate_worker(gs, w, rounds, work_steps, dead.get(w), bug) for w in range(P)]
+    if watchdog_after is not None:
+        def watchdog() -> Generator:
+            for _ in range(watchdog_after):
+                yield
+            gs.gate_dyn = max(1, threshold - len(dead)); yield
+        gens.append(watchdog())
+    run_schedule(gens, rng, burst)
+    if threshold > 0 and bug is None:
+        per_wave: Dict[tuple, int] = {}
+        for wid, wave in gs.runs:
+            per_wave[(wid, wave)] = per_wave.get((wid, wave), 0) + 1
+        assert all(c == 1 for c in per_wave.values()), f"a worker ran twice in one wave: {[k for k, c in per_wave.items() if c > 1]}"
+        assert [o[0] for o in gs.opened] == list(range(1, len(gs.opened) + 1)), f"waves were not opened one at a time: {gs.opened}"
+        assert all(a >= thr for _, a, thr in gs.opened), f"a wave was opened below its threshold: {gs.opened}"
+    finished = sum(min(rounds, dead.get(w, rounds)) for w in range(P))
+    assert gs.clock == finished, f"clock {gs.clock} != finished rounds {finished}"
+    assert gs.avail == P - len(dead), f"avail_count {gs.avail} != live workers {P - len(dead)}"
+    return gs
