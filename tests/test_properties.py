@@ -93,3 +93,34 @@ def test_tree_aggregate_equals_aggregate(vals, P, depth):
     seq, comb = (lambda a, x: a + x), (lambda a, b: a + b)
     assert ds.tree_aggregate(lambda: 0, seq, comb, depth=depth) == ds.aggregate(lambda: 0, seq, comb) == sum(vals)
     assert ds.reduce(lambda a, b: a + b) == sum(vals)
+
+
+@settings(**COMMON)
+@given(recs=st.lists(st.tuples(st.integers(-20, 20), st.integers(-5, 5)), max_size=120), P=st.integers(1, 4),
+       spill=st.integers(1, 40), batch=st.integers(1, 9), mode=st.sampled_from(["plain", "sorted", "sorted_desc", "combine", "combine_sorted"]))
+def test_external_sorter_equals_the_in_memory_answer(tmp_path_factory, recs, P, spill, batch, mode):
+    """Whatever the spill cadence, batch size and partition count: partitioned (+ ordered) (+ combined) output of the spillable
+    sorter == the plain in-memory computation."""
+    from asyncframework_b200.storage.external_sorter import Aggregator, ExternalSorter, SpillConfig
+    cfg = SpillConfig(force_spill_elements=spill, batch_size=batch, local_dir=str(tmp_path_factory.mktemp("spill")))
+    part = lambda k: k % P                              # noqa: E731
+    agg = Aggregator.from_reduce(lambda a, b: a + b) if mode.startswith("combine") else None
+    key = (lambda k: k) if "sorted" in mode else None
+    reverse = mode == "sorted_desc"
+    with ExternalSorter(P, part, agg, key=key, reverse=reverse, config=cfg) as s:
+        s.insert_all(recs)
+        out = {p: list(it) for p, it in s.partitioned_iterator()}
+    for p in range(P):
+        mine = [(k, v) for k, v in recs if k % P == p]
+        if agg is not None:
+            want = {}
+            for k, v in mine:
+                want[k] = want.get(k, 0) + v
+            assert dict(out[p]) == want and len(out[p]) == len(want)
+            if key is not None:
+                assert [k for k, _ in out[p]] == sorted(want)
+        elif key is not None:
+            assert [k for k, _ in out[p]] == sorted((k for k, _ in mine), reverse=reverse)
+            assert sorted(out[p]) == sorted(mine)
+        else:
+            assert sorted(out[p]) == sorted(mine)
