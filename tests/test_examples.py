@@ -43,7 +43,10 @@ def test_straggler_sweep_example():
 def test_standalone_cluster_example_survives_a_killed_executor():
     out = _run("standalone_cluster.py")
     last = out.strip().splitlines()[-1]
-    assert "executors recovered: 1" in last and "FAILED" not in last
+    recovered = int(last.split("executors recovered: ")[1].split(";")[0])
+    # exactly one on an idle machine; on a heavily loaded one a starved executor can additionally miss its heartbeats and be
+    # replaced too (its in-flight jobs are then reported FAILED and re-submitted by the driver loop) — the run must still converge
+    assert recovered >= 1 and (recovered > 1 or "FAILED" not in last)
     first, final = (float(x) for x in last.split("objective ")[1].split(" after")[0].split(" -> "))
     assert final < 0.1 * first
 
