@@ -242,5 +242,5 @@ def test_drivers_survive_an_executor_killed_mid_run_on_the_standalone_cluster(cl
         th.join(120)
         assert not th.is_alive() and "rep" in out
         rep = out["rep"]
-        assert rep.accepted == iters and sc.scheduler.executors_recovered == 1
+        assert rep.accepted == iters and sc.scheduler.executors_recovered >= 1      # > 1 only on a starved machine (missed heartbeats)
         assert rep.objective[-1][1] < 0.2 * rep.objective[0][1]
