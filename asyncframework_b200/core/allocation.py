@@ -128,11 +128,19 @@ class ExecutorAllocationManager:
             # idle executors: a slot without unfinished tasks since idle_timeout is released (highest slots first: slots
             # are dense, partition p lives on slot p % n)
             n = self.sched.num_executors
+            # an executor is idle since the later of: the first tick that saw it without unfinished tasks, and its last task
+            # launch / status message (short tasks start and finish between two ticks: polling alone would call a busy
+            # executor idle; ExecutorAllocationManager resets the idle timer in onTaskStart for the same reason)
+            last_active = getattr(self.sched, "executor_last_active", {})
+            mono_to_clock = now - time.monotonic() if self.clock is time.monotonic else None
             for e in range(n):
                 if e in ld["busy"]:
                     self._idle_since.pop(e, None)
                 else:
-                    self._idle_since.setdefault(e, now)
+                    since = self._idle_since.setdefault(e, now)
+                    la = last_active.get(e)
+                    if la is not None and mono_to_clock is not None and la + mono_to_clock > since:
+                        self._idle_since[e] = la + mono_to_clock
             for e in list(self._idle_since):
                 if e >= n:
                     self._idle_since.pop(e, None)

@@ -394,6 +394,7 @@ class ClusterScheduler:
         self.speculation = speculation
         self.speculation_multiplier, self.speculation_quantile = speculation_multiplier, speculation_quantile
         self.speculation_interval, self.speculation_min_ms = speculation_interval, speculation_min_ms
+        self.executor_last_active: Dict[int, float] = {}   # monotonic time of the last task launch / completion per executor slot
         self.allocation_manager = None       # ExecutorAllocationManager once enable_dynamic_allocation() ran
         self._submit_lock = threading.RLock()
         self.speculated_tasks = 0
@@ -489,6 +490,7 @@ class ClusterScheduler:
             job["assigned"][partition] = eid
             job.setdefault("attempts", {})[partition] = attempt
             job["started"].pop(partition, None)       # set again by the executor's "started" message
+        self.executor_last_active[eid] = time.monotonic()
         self._send(eid, ("task", job_id, partition, attempt, job["submit_ms"]))
 
     # ------------------------------------------------------------------ liveness
@@ -550,6 +552,8 @@ class ClusterScheduler:
 
     def _on_message(self, eid: int, msg: tuple) -> None:
         kind, job_id, partition, attempt, data, run_ms = msg
+        if kind in ("ok", "indirect", "err", "started", "killed"):
+            self.executor_last_active[eid] = time.monotonic()
         with self._lock:
             job = self._jobs.get(job_id)
         if kind == "heartbeat":
@@ -882,6 +886,7 @@ class ClusterScheduler:
             e = assigned[p]
             if e not in unreachable:
                 self.listeners.post({"event": "task_start", "job": job_id, "partition": p, "attempt": 0, "executor": e, "t_ms": now})
+                self.executor_last_active[e] = time.monotonic()
                 try:
                     self._send(e, ("task", job_id, p, 0, now))
                     continue

@@ -68,7 +68,8 @@ def main(argv=None) -> int:
     driver_limits = reply[1]
     if driver_limits is not None:                       # result / broadcast limits are the application's, not the worker's
         for k in ("max_direct_result_size", "max_result_size", "broadcast_block_size", "broadcast_compress",
-                  "broadcast_checksum", "broadcast_inline_threshold", "network_timeout", "heartbeat_interval"):
+                  "broadcast_checksum", "broadcast_inline_threshold", "network_timeout", "heartbeat_interval",
+                  "shuffle_memory", "shuffle_spill_elements", "shuffle_spill_batch", "shuffle_spill_compress"):
             setattr(env.limits, k, getattr(driver_limits, k))
     backend.start_heartbeats(env.limits.heartbeat_interval)
     try:

@@ -177,3 +177,29 @@ def test_policy_loop_grows_a_standalone_application_under_backlog_and_shrinks_it
             assert len(set(ds.map(slow).collect())) == 1
             events = [h["event"] for h in am.history]
             assert events.count("applied") >= 2
+
+
+def test_short_tasks_between_ticks_keep_executors_from_looking_idle():
+    """Tasks that start and finish between two policy passes never appear in the job table when the policy looks; the idle
+    timer must still be reset by their launches / status messages (ExecutorAllocationManager resets it in onTaskStart)."""
+    t = ResizableTransport(3)
+    s = ClusterScheduler(3, transport=t, use_env=False)
+    am = ExecutorAllocationManager(s, AllocationPolicy(min_executors=1, max_executors=3, idle_timeout=0.4))     # real monotonic clock
+    s.allocation_manager = am
+    am.target = 3
+    ds = ShardedDataset.from_records(s, list(range(6)), 3)
+    t_end = time.monotonic() + 1.2
+    while time.monotonic() < t_end:                                  # 1.2 s of activity, three times the idle timeout
+        w = s.submit_job(ds, lambda tc, it: 0, result_handler=lambda i, r: None)
+        for p in range(3):
+            t.started(p, w.job_id, p)
+            t.ok(p, w.job_id, p, 0)
+        assert w.done
+        am.tick()                                                    # the job table is empty every time the policy looks
+        time.sleep(0.05)
+    assert am.target == 3 and t.requests == []
+    t0 = time.monotonic()
+    while am.tick() == 3 and time.monotonic() - t0 < 3.0:            # activity stops: now the timer runs out
+        time.sleep(0.05)
+    assert am.target == 1 and t.requests == [1] and 0.3 < time.monotonic() - t0 < 2.0
+    s.stop()

@@ -61,3 +61,14 @@ def test_spark_mean_toy_example():
     out = _run("spark_mean.py")
     lines = out.strip().splitlines()
     assert lines[-2] == "The Final results is: " and abs(float(lines[-1])) < 5.0 and "******** iteration 3********" in out
+
+
+def test_data_prep_example_spills_grows_and_shrinks():
+    out = _run("data_prep_on_a_cluster.py")
+    lines = out.strip().splitlines()
+    assert "distinct tokens: 997" in lines[1] and int(lines[1].rsplit(": ", 1)[1]) > 0          # the sorters really spilled
+    grown = lines[2].split("job: ")[1].split(" (")[0]
+    assert max(int(x) for x in grown.split(" -> ")) >= 2                                          # ran on more than one executor
+    assert "executors after the idle timeout: 1" in lines[-1]
+    changes = eval(lines[-1].split("applied: ")[1])                                               # noqa: S307  (our own output)
+    assert changes[0][0] == 1 and changes[-1][1] == 1 and max(b for _, b in changes) >= 2
